@@ -1,0 +1,208 @@
+/* rlzero_b200 -- C ABI of the B200-native batched self-play MCTS hot path.
+ *
+ * The reference (jianzhnie/RLZero) has no FFI layer; its boundary is the
+ * duck-typed Python API of rlzero/mcts/alphazero_mcts.py and
+ * rlzero/games/gomoku/*.py.  This header is the C-ABI a
+ * maintainer would bind underneath those classes (ctypes stub in
+ * INTEGRATION.md).  Each entry point cites the reference function it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it is marked
+ *     "host"; the library allocates nothing and keeps no global state except
+ *     the last-error string;
+ *   - every call is asynchronous on the cudaStream_t passed as `stream`
+ *     (void* so that this header needs no CUDA include), performs no host
+ *     synchronisation and is CUDA-graph capturable;
+ *   - return value 0 = launched, <0 = argument/launch error (rz_last_error()).
+ *     Data-dependent faults (illegal move, pool overflow) are reported through
+ *     the per-game `fault` words, which the host shim turns into the
+ *     reference's exceptions (AssertionError illegal move gomoku_env.py:51,
+ *     ValueError('Node has no children.') node.py:39).
+ *
+ * Layouts
+ *   board      : per game 2 x H uint32 row bitmasks, rows[g][c][r] bit w set <=>
+ *                stone of player c on square r*W+w  (gomoku_env.py: states dict)
+ *   meta       : per game RZ_META_STRIDE int32 (enum rz_meta)
+ *   edge block : per expanded node A slots indexed BY ACTION (slot a <=> child
+ *                reached by move a; children of a reference node are keyed by
+ *                action in ascending order, node.py:71-73), padded to
+ *                AS = round_up(A,32):  N int32 (-1 = illegal/no child),
+ *                W float64, P float32, child int32.
+ */
+#ifndef RLZERO_B200_H
+#define RLZERO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RZ_ABI_VERSION 3
+#define RZ_MAX_BOARD 19          /* rows live one per lane; A = H*W <= 361 */
+#define RZ_META_STRIDE 8
+
+enum rz_meta {                   /* int32 words of a game's meta record */
+  RZ_META_PLAYER = 0,            /* player to move, 0/1 (gomoku_env.py:29,67-68) */
+  RZ_META_LAST_MOVE = 1,         /* -1 on an empty board (gomoku_env.py:45) */
+  RZ_META_STONES = 2,            /* len(states) */
+  RZ_META_STATUS = 3,            /* enum rz_status */
+  RZ_META_WINNER = 4,            /* -1 none/tie, else player id (game_end_winner) */
+  RZ_META_PLY = 5,               /* plies played in this episode (trajectory length) */
+  RZ_META_FAULT = 6,             /* sticky bit set, enum rz_fault */
+  RZ_META_EPISODE = 7            /* episodes finished in this slot */
+};
+
+enum rz_status { RZ_ACTIVE = 0, RZ_ENDED_WIN = 1, RZ_ENDED_TIE = 2, RZ_IDLE = 3 };
+
+enum rz_fault {
+  RZ_FAULT_ILLEGAL_MOVE = 1,     /* AssertionError in gomoku_env.py:51 */
+  RZ_FAULT_POOL_OVERFLOW = 2,    /* node pool exhausted: leaf left unexpanded */
+  RZ_FAULT_DEPTH_OVERFLOW = 4,
+  RZ_FAULT_LN_TABLE = 8,         /* parent visit count beyond ln table */
+  RZ_FAULT_NO_CHILDREN = 16,     /* ValueError in node.py:39 */
+  RZ_FAULT_CARRY_DROPPED = 32,   /* reused subtree larger than max_carry: tree reset */
+  RZ_FAULT_TRAJ_OVERFLOW = 64
+};
+
+enum rz_rule {
+  RZ_RULE_UCT = 0,               /* reference: W/n + c*sqrt(ln(Np)/n), +inf if n==0 (node.py:75-88) */
+  RZ_RULE_PUCT = 1               /* (n and W/n) + c*P*sqrt(Np)/(n+1) (deepmind_mcts.py:149-151) */
+};
+
+enum rz_eval {                   /* closed-form evaluators, oracle/evaluators.py */
+  RZ_EVAL_ZERO = 0, RZ_EVAL_KAT = 1, RZ_EVAL_HASH = 2
+};
+
+enum rz_child {                  /* values of edge child[] when N >= 1 */
+  RZ_CHILD_TERMINAL = -1,        /* visited, game over there: never expanded (alphazero_mcts.py:60-68) */
+  RZ_CHILD_OVERFLOW = -2         /* visited, pool was full: re-evaluated like a leaf */
+};
+
+/* ---- game geometry ------------------------------------------------------- */
+typedef struct rz_game_desc {
+  int32_t board_size;            /* H == W  (GomokuEnv.board_size) */
+  int32_t n_in_row;              /* k       (GomokuEnv.n_in_row) */
+  int32_t n_actions;             /* A = H*W */
+  int32_t action_stride;         /* AS = round_up(A, 32) */
+} rz_game_desc;
+
+/* ---- one search forest: G trees, one per game ---------------------------- */
+typedef struct rz_tree_desc {
+  rz_game_desc game;
+  int32_t n_trees;               /* G */
+  int32_t max_nodes;             /* expanded-node capacity per tree */
+  int32_t max_depth;             /* path capacity per tree (<= A+1) */
+  int32_t rule;                  /* enum rz_rule */
+  int32_t ln_table_len;
+  int32_t store_priors;          /* 0: edge_P may be NULL (UCT ignores priors) */
+  double c_puct;                 /* AlphaZeroMCTS._c_puct */
+  int64_t global_offset;         /* global id of tree 0 (shard-invariant RNG streams) */
+  /* node pools, [G][max_nodes][AS] */
+  int32_t* edge_N;
+  double* edge_W;
+  float* edge_P;
+  int32_t* edge_child;
+  /* node headers, [G][max_nodes] */
+  int32_t* node_parent;          /* -1 for the root */
+  int32_t* node_paction;         /* action leading here from the parent */
+  /* per tree, [G] */
+  int32_t* n_nodes;              /* expanded nodes in use; 0 <=> root is an unexpanded leaf */
+  int32_t* root_N;               /* TreeNode.explore_count of the root */
+  double* root_W;                /* TreeNode.total_reward of the root */
+  /* root positions */
+  uint32_t* root_rows;           /* [G][2][H] */
+  int32_t* root_meta;            /* [G][RZ_META_STRIDE] */
+  /* per-wave scratch written by rz_tree_select, read by eval / expand_backup */
+  int32_t* path_node;            /* [G][max_depth] */
+  int32_t* path_action;          /* [G][max_depth] */
+  int32_t* depth;                /* [G]; -1 = tree skipped this wave */
+  uint32_t* leaf_rows;           /* [G][2][H] */
+  int32_t* leaf_meta;            /* [G][RZ_META_STRIDE] (status = terminal state of the leaf) */
+  const double* ln_table;        /* ln_table[k] = math.log(k) computed by the HOST libm (k>=1) */
+} rz_tree_desc;
+
+/* ---- trajectory store (GameControl.start_self_play, game.py:96-134) ------- */
+typedef struct rz_traj_desc {
+  int32_t max_plies;             /* staging capacity per game (<= A) */
+  int32_t ring_capacity;         /* finished-ply records the ring holds */
+  /* staging, per game per ply */
+  uint32_t* stage_rows;          /* [G][max_plies][2][H] position BEFORE the move */
+  int32_t* stage_info;           /* [G][max_plies][4]: mover, last_move, move played, stones */
+  float* stage_pi;               /* [G][max_plies][AS] */
+  /* ring of finished plies (z known) */
+  uint32_t* ring_rows;           /* [cap][2][H] */
+  int32_t* ring_info;            /* [cap][6]: mover, last_move, z (+1/-1/0), slot, episode, ply */
+  float* ring_pi;                /* [cap][AS] */
+  unsigned long long* ring_cursor; /* [1] records ever written (monotone) */
+  unsigned long long* games_done;  /* [1] */
+  unsigned long long* plies_done;  /* [1] */
+} rz_traj_desc;
+
+int rz_abi_version(void);
+const char* rz_last_error(void);                 /* host string, thread-local */
+int rz_sizeof_tree_desc(void);
+int rz_sizeof_traj_desc(void);
+
+/* ---- game dynamics: GomokuEnv (rlzero/games/gomoku/gomoku_env.py) -------- */
+/* reset (gomoku_env.py:33-47): empty boards, player 0 to move, last_move -1.
+   only_ended != 0: touch only games whose status is ENDED_* (continuous refill). */
+int rz_gomoku_reset(const rz_game_desc* g, uint32_t* rows, int32_t* meta, int n_games,
+                    int only_ended, void* stream);
+/* step (gomoku_env.py:49-70): place stone, win check, flip player.  actions[i] < 0
+   skips game i.  reward/win may be NULL.  Illegal move -> RZ_FAULT_ILLEGAL_MOVE. */
+int rz_gomoku_step(const rz_game_desc* g, uint32_t* rows, int32_t* meta, const int32_t* actions,
+                   int32_t* reward, int32_t* win, int n_games, void* stream);
+/* leagel_actions (gomoku_env.py:72-73) as a byte mask [n][A]. */
+int rz_gomoku_legal_mask(const rz_game_desc* g, const uint32_t* rows, uint8_t* mask,
+                         int n_games, void* stream);
+/* has_a_winner / game_end_winner (gomoku_env.py:116-170,196-203): end[i] 0/1, winner[i]. */
+int rz_gomoku_winner(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
+                     int32_t* end, int32_t* winner, int n_games, void* stream);
+/* current_state (gomoku_env.py:95-114) as float32 [n][4][H][W]. */
+int rz_gomoku_encode_f32(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
+                         float* planes, int n_games, void* stream);
+/* same planes as bf16 in the tensor-core trunk's layout [n][256][64]: position
+   p = y*16+x (x,y < 15 real, else zero), channels 0..3 = planes, 4..63 zero. */
+int rz_gomoku_encode_tc(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
+                        void* act_bf16, int n_games, void* stream);
+
+/* ---- search: AlphaZeroMCTS (rlzero/mcts/alphazero_mcts.py, node.py) ------- */
+/* fresh trees: _root = TreeNode(None, 1.0) (alphazero_mcts.py:36).  tree_mask NULL = all. */
+int rz_tree_reset(const rz_tree_desc* t, const uint8_t* tree_mask, void* stream);
+/* descent of one playout per tree (alphazero_mcts.py:48-54 + node.py:32-42,75-88 +
+   gomoku_env.py:49-70), then game_end_winner on the leaf (alphazero_mcts.py:60). */
+int rz_tree_select(const rz_tree_desc* t, void* stream);
+/* expand (node.py:44-73) + terminal value rule (alphazero_mcts.py:60-68) + sign-flipping
+   backup (node.py:135-144).  prior: [G][AS] float32; prior_is_log != 0 means it holds
+   log-probabilities and exp() is applied (alphazero_agent.py:43).  value: [G] float32 (the
+   network's output type); value64 != NULL overrides it with [G] float64 (a Python
+   policy_value_fn returns a Python float, alphazero_mcts.py:59).
+   noise_eps > 0 mixes Dirichlet(noise_alpha) noise into every expanded node
+   (node.py:63-69, eps = 0.25, alpha = 0.3), counter-based RNG keyed by (seed, game, node). */
+int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, int prior_is_log,
+                          const float* value, const double* value64, float noise_eps, float noise_alpha,
+                          unsigned long long seed, void* stream);
+/* root statistics + move choice (alphazero_mcts.py:86-94, 144-148):
+   visits int32 [G][AS] (0 where no child), pi float32 [G][AS] = softmax(log(N+1e-10)/T),
+   move[g] sampled from pi with a counter-based RNG (seed, game, ply); u01 != NULL supplies
+   the uniforms instead (tests).  Any output may be NULL. */
+int rz_tree_root_policy(const rz_tree_desc* t, double temperature, int32_t* visits, float* pi,
+                        int32_t* move, const double* u01, unsigned long long seed, void* stream);
+/* play moves[g] on the root position and re-root (update_with_move, alphazero_mcts.py:96-103):
+   keep_subtree != 0 compacts the chosen child's subtree to the front of the pool (self-play),
+   else the tree is reset (play mode :157-158).  moves[g] < 0 resets the tree without a move
+   (reset_player, :132-134).  traj != NULL records (position, pi, mover) first and, when the
+   game ends, assigns z and flushes the episode to the ring (game.py:113-134); auto_reset != 0
+   then restarts the slot from an empty board. */
+int rz_tree_advance(const rz_tree_desc* t, const int32_t* moves, int keep_subtree, int max_carry,
+                    const rz_traj_desc* traj, const float* pi, int auto_reset, void* stream);
+
+/* ---- closed-form evaluators for parity tests (oracle/evaluators.py) ------- */
+int rz_eval_closed_form(const rz_tree_desc* t, int eval_id, float* prior, float* value,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLZERO_B200_H */

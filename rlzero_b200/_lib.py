@@ -1,0 +1,121 @@
+"""ctypes binding of ``librlzero_b200.so`` (the C ABI in ``include/rlzero_b200.h``).
+
+There is deliberately NO fallback: if the CUDA library is missing, cannot be loaded, or
+disagrees with this file about the ABI, importing the product path raises.
+"""
+import ctypes as C
+import os
+
+import torch  # noqa: F401  -- loads libcudart.so.12 into the process before our library
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'librlzero_b200.so')
+
+ABI_VERSION = 3
+META_STRIDE = 8
+(META_PLAYER, META_LAST_MOVE, META_STONES, META_STATUS, META_WINNER, META_PLY, META_FAULT,
+ META_EPISODE) = range(8)
+ACTIVE, ENDED_WIN, ENDED_TIE, IDLE = range(4)
+FAULT_ILLEGAL_MOVE, FAULT_POOL_OVERFLOW, FAULT_DEPTH_OVERFLOW, FAULT_LN_TABLE = 1, 2, 4, 8
+FAULT_NO_CHILDREN, FAULT_CARRY_DROPPED, FAULT_TRAJ_OVERFLOW = 16, 32, 64
+RULE_UCT, RULE_PUCT = 0, 1
+EVAL_ZERO, EVAL_KAT, EVAL_HASH = 0, 1, 2
+CHILD_TERMINAL, CHILD_OVERFLOW = -1, -2
+MAX_BOARD = 19
+
+_vp = C.c_void_p
+
+
+class GameDesc(C.Structure):
+    _fields_ = [('board_size', C.c_int32), ('n_in_row', C.c_int32), ('n_actions', C.c_int32),
+                ('action_stride', C.c_int32)]
+
+
+class TreeDesc(C.Structure):
+    _fields_ = [('game', GameDesc), ('n_trees', C.c_int32), ('max_nodes', C.c_int32),
+                ('max_depth', C.c_int32), ('rule', C.c_int32), ('ln_table_len', C.c_int32),
+                ('store_priors', C.c_int32), ('c_puct', C.c_double), ('global_offset', C.c_int64),
+                ('edge_N', _vp), ('edge_W', _vp), ('edge_P', _vp), ('edge_child', _vp),
+                ('node_parent', _vp), ('node_paction', _vp),
+                ('n_nodes', _vp), ('root_N', _vp), ('root_W', _vp),
+                ('root_rows', _vp), ('root_meta', _vp),
+                ('path_node', _vp), ('path_action', _vp), ('depth', _vp),
+                ('leaf_rows', _vp), ('leaf_meta', _vp), ('ln_table', _vp)]
+
+
+class TrajDesc(C.Structure):
+    _fields_ = [('max_plies', C.c_int32), ('ring_capacity', C.c_int32),
+                ('stage_rows', _vp), ('stage_info', _vp), ('stage_pi', _vp),
+                ('ring_rows', _vp), ('ring_info', _vp), ('ring_pi', _vp),
+                ('ring_cursor', _vp), ('games_done', _vp), ('plies_done', _vp)]
+
+
+# name -> (restype, argtypes); every symbol include/rlzero_b200.h declares
+_GD, _TD, _TJ = C.POINTER(GameDesc), C.POINTER(TreeDesc), C.POINTER(TrajDesc)
+SIGNATURES = {
+    'rz_abi_version': (C.c_int, []),
+    'rz_last_error': (C.c_char_p, []),
+    'rz_sizeof_tree_desc': (C.c_int, []),
+    'rz_sizeof_traj_desc': (C.c_int, []),
+    'rz_gomoku_reset': (C.c_int, [_GD, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rz_gomoku_step': (C.c_int, [_GD, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_gomoku_legal_mask': (C.c_int, [_GD, _vp, _vp, C.c_int, _vp]),
+    'rz_gomoku_winner': (C.c_int, [_GD, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_gomoku_encode_f32': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_gomoku_encode_tc': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_tree_reset': (C.c_int, [_TD, _vp, _vp]),
+    'rz_tree_select': (C.c_int, [_TD, _vp]),
+    'rz_tree_expand_backup': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,
+                                        C.c_ulonglong, _vp]),
+    'rz_tree_root_policy': (C.c_int, [_TD, C.c_double, _vp, _vp, _vp, _vp, C.c_ulonglong, _vp]),
+    'rz_tree_advance': (C.c_int, [_TD, _vp, C.c_int, C.c_int, _TJ, _vp, C.c_int, _vp]),
+    'rz_eval_closed_form': (C.c_int, [_TD, C.c_int, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared object (once) and type every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            'rlzero_b200 CUDA library not built: %s is missing. Run `python -m rlzero_b200.build` '
+            '(there is no CPU fallback).' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise NativeLibraryError('symbol %s missing from %s' % (name, LIB_PATH))
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rz_abi_version() != ABI_VERSION:
+        raise NativeLibraryError('ABI mismatch: library %d, binding %d (rebuild)' % (
+            lib.rz_abi_version(), ABI_VERSION))
+    if lib.rz_sizeof_tree_desc() != C.sizeof(TreeDesc) or lib.rz_sizeof_traj_desc() != C.sizeof(TrajDesc):
+        raise NativeLibraryError('descriptor struct size mismatch between header and binding')
+    _lib = lib
+    return lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise NativeLibraryError('%s failed (%d): %s' % (what, rc, load().rz_last_error().decode()))
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, None -> NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)

@@ -1,0 +1,19 @@
+// rlzero_b200 -- ABI bookkeeping: version, struct sizes, last-error string.
+#include <stdarg.h>
+#include <string.h>
+
+#include "rz_common.cuh"
+
+static thread_local char rz_error_buf[512] = "";
+
+void rz_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(rz_error_buf, sizeof(rz_error_buf), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int rz_abi_version(void) { return RZ_ABI_VERSION; }
+extern "C" const char* rz_last_error(void) { return rz_error_buf; }
+extern "C" int rz_sizeof_tree_desc(void) { return (int)sizeof(rz_tree_desc); }
+extern "C" int rz_sizeof_traj_desc(void) { return (int)sizeof(rz_traj_desc); }

@@ -1,0 +1,91 @@
+// rlzero_b200 -- Gomoku position held by one warp, one board row per lane.
+//
+// Lane r (< H) keeps row r of each colour as a bitmask (bit w = column w); lanes >= H
+// keep zero.  Every rule of rlzero/games/gomoku/gomoku_env.py becomes a handful of
+// shifts, ANDs and warp shuffles:
+//   step            gomoku_env.py:49-70   -> one lane sets one bit
+//   has_a_winner    gomoku_env.py:116-170 -> AND of k shifted copies along 4 directions
+//   leagel_actions  gomoku_env.py:72-73   -> ~(p0|p1) & row mask
+//   current_state   gomoku_env.py:95-114  -> plane bits read straight from the rows
+#pragma once
+#include "rz_common.cuh"
+
+struct rz_wboard {
+  uint32_t p[2];    // this lane's row of player 0 / player 1
+  int player;       // to move
+  int last_move;    // -1 on an empty board
+  int stones;
+};
+
+__device__ __forceinline__ void rz_board_load(rz_wboard& b, const uint32_t* __restrict__ rows,
+                                              const int32_t* __restrict__ meta, int H) {
+  const int lane = rz_lane();
+  b.p[0] = lane < H ? rows[lane] : 0u;
+  b.p[1] = lane < H ? rows[H + lane] : 0u;
+  b.player = meta[RZ_META_PLAYER];
+  b.last_move = meta[RZ_META_LAST_MOVE];
+  b.stones = meta[RZ_META_STONES];
+}
+
+__device__ __forceinline__ void rz_board_store_rows(const rz_wboard& b, uint32_t* __restrict__ rows,
+                                                    int H) {
+  const int lane = rz_lane();
+  if (lane < H) {
+    rows[lane] = b.p[0];
+    rows[H + lane] = b.p[1];
+  }
+}
+
+// occupied(a) for a warp-uniform action a
+__device__ __forceinline__ bool rz_board_occupied(const rz_wboard& b, int a, int W) {
+  const int r = a / W, c = a - r * W;
+  const uint32_t occ = __shfl_sync(RZ_FULL, b.p[0] | b.p[1], r);
+  return (occ >> c) & 1u;
+}
+
+// gomoku_env.py:55-57,67-68 -- place the mover's stone and flip the player (a is warp-uniform)
+__device__ __forceinline__ void rz_board_play(rz_wboard& b, int a, int W) {
+  const int r = a / W, c = a - r * W;
+  if (rz_lane() == r) b.p[b.player] |= (1u << c);
+  b.player ^= 1;
+  b.last_move = a;
+  b.stones += 1;
+}
+
+// k stones in a row for one colour (x = this lane's row of that colour); warp-uniform result.
+__device__ __forceinline__ bool rz_rows_have_line(uint32_t x, int k) {
+  uint32_t h = x, v = x, d = x, e = x;
+  for (int i = 1; i < k; ++i) {
+    const uint32_t below = __shfl_down_sync(RZ_FULL, x, i);  // row r+i (0 beyond the board)
+    const uint32_t up = (rz_lane() + i < 32) ? below : 0u;
+    h &= (x >> i);          // (r, c..c+k-1)          gomoku_env.py:139-142
+    v &= up;                // (r..r+k-1, c)          gomoku_env.py:144-150
+    d &= (up >> i);         // (r+i, c+i)             gomoku_env.py:152-159
+    e &= (up << i);         // (r+i, c-i)             gomoku_env.py:161-168
+  }
+  return __any_sync(RZ_FULL, (h | v | d | e) != 0u);
+}
+
+// game_end_winner (gomoku_env.py:196-203) incl. the stones < 2k-1 early-out of
+// has_a_winner (gomoku_env.py:131-133).  Returns rz_status; winner via reference.
+__device__ __forceinline__ int rz_board_status(const rz_wboard& b, int H, int k, int& winner) {
+  winner = -1;
+  if (b.stones >= 2 * k - 1) {
+    const bool w0 = rz_rows_have_line(b.p[0], k);
+    const bool w1 = rz_rows_have_line(b.p[1], k);
+    if (w0 || w1) {
+      winner = w0 ? 0 : 1;
+      return RZ_ENDED_WIN;
+    }
+  }
+  if (b.stones >= H * H) return RZ_ENDED_TIE;
+  return RZ_ACTIVE;
+}
+
+// legality of slot s (per-lane s, all lanes must call): empty square inside the board
+__device__ __forceinline__ bool rz_board_slot_legal(const rz_wboard& b, int s, int W, int A) {
+  const int sc = s < A ? s : 0;
+  const int r = sc / W, c = sc - r * W;
+  const uint32_t occ = __shfl_sync(RZ_FULL, b.p[0] | b.p[1], r);
+  return s < A && !((occ >> c) & 1u);
+}

@@ -1,0 +1,119 @@
+// rlzero_b200 -- shared device/host helpers (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rlzero_b200.h"
+
+#define RZ_WARP 32
+#define RZ_FULL 0xffffffffu
+
+// ---- host-side error plumbing ---------------------------------------------
+void rz_set_error(const char* fmt, ...);
+
+#define RZ_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      rz_set_error(__VA_ARGS__);     \
+      return -1;                     \
+    }                                \
+  } while (0)
+
+#define RZ_LAUNCH_CHECK(name)                                           \
+  do {                                                                  \
+    cudaError_t e__ = cudaGetLastError();                               \
+    if (e__ != cudaSuccess) {                                           \
+      rz_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return -2;                                                        \
+    }                                                                   \
+  } while (0)
+
+static inline int rz_check_game(const rz_game_desc* g) {
+  if (!g) { rz_set_error("null game desc"); return -1; }
+  if (g->board_size < 1 || g->board_size > RZ_MAX_BOARD) {
+    rz_set_error("board_size %d outside [1,%d]", g->board_size, RZ_MAX_BOARD); return -1; }
+  if (g->n_actions != g->board_size * g->board_size) {
+    rz_set_error("n_actions %d != board_size^2", g->n_actions); return -1; }
+  if (g->action_stride < g->n_actions || (g->action_stride & 31)) {
+    rz_set_error("action_stride %d must be a multiple of 32 >= n_actions", g->action_stride); return -1; }
+  if (g->n_in_row < 1 || g->n_in_row > g->board_size) {
+    rz_set_error("n_in_row %d outside [1,board_size]", g->n_in_row); return -1; }
+  return 0;
+}
+
+// ---- device helpers --------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ int rz_lane() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ unsigned rz_warp_sum_u32(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(RZ_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ int rz_warp_sum_i32(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(RZ_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double rz_warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(RZ_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float rz_warp_sum_f32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(RZ_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double rz_warp_max_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(RZ_FULL, v, o));
+  return v;
+}
+// inclusive prefix sum over the warp
+__device__ __forceinline__ double rz_warp_scan_f64(double v) {
+  const int lane = rz_lane();
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(RZ_FULL, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// Philox-4x32-10: counter-based RNG, so that a game's random stream depends only on
+// (seed, global game id, episode, ply, ...) and not on which GPU or slot runs it.
+struct rz_philox {
+  uint32_t c[4];
+  uint32_t k[2];
+};
+__device__ __forceinline__ void rz_philox_round(uint32_t (&c)[4], const uint32_t (&k)[2]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void rz_philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           unsigned long long seed, uint32_t (&out)[4]) {
+  uint32_t c[4] = {c0, c1, c2, c3};
+  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    rz_philox_round(c, k);
+    k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+// uniform in (0,1) with 53 random bits
+__device__ __forceinline__ double rz_u01_53(uint32_t a, uint32_t b) {
+  unsigned long long x = (((unsigned long long)a << 32) | b) >> 11;
+  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ float rz_u01_24(uint32_t a) {
+  return ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+#endif  // __CUDACC__

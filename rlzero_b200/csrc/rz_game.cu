@@ -1,0 +1,291 @@
+// rlzero_b200 -- batched GomokuEnv kernels (one warp per game) and closed-form evaluators.
+// Reference: rlzero/games/gomoku/gomoku_env.py (reset 33-47, step 49-70, leagel_actions 72-73,
+// current_state 95-114, has_a_winner 116-170, game_end_winner 196-203).
+#include <cuda_bf16.h>
+
+#include "rz_board.cuh"
+
+#define RZ_GAME_WARPS 4
+#define RZ_GAME_THREADS (RZ_GAME_WARPS * 32)
+
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_gomoku_reset_kernel(rz_game_desc gd, uint32_t* rows, int32_t* meta, int n, int only_ended) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const int lane = rz_lane(), H = gd.board_size;
+  int32_t* m = meta + (size_t)g * RZ_META_STRIDE;
+  const int st = m[RZ_META_STATUS];
+  if (only_ended && !(st == RZ_ENDED_WIN || st == RZ_ENDED_TIE)) return;
+  if (lane < H) { rows[(size_t)g * 2 * H + lane] = 0u; rows[(size_t)g * 2 * H + H + lane] = 0u; }
+  if (lane == 0) {
+    m[RZ_META_PLAYER] = 0;
+    m[RZ_META_LAST_MOVE] = -1;
+    m[RZ_META_STONES] = 0;
+    m[RZ_META_STATUS] = RZ_ACTIVE;
+    m[RZ_META_WINNER] = -1;
+    m[RZ_META_PLY] = 0;
+    m[RZ_META_FAULT] = 0;
+    m[RZ_META_EPISODE] = only_ended ? m[RZ_META_EPISODE] + 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_gomoku_step_kernel(rz_game_desc gd, uint32_t* rows, int32_t* meta, const int32_t* actions,
+                      int32_t* reward, int32_t* win, int n) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const int lane = rz_lane(), H = gd.board_size;
+  const int a = actions[g];
+  if (a < 0) return;
+  int32_t* m = meta + (size_t)g * RZ_META_STRIDE;
+  rz_wboard b;
+  rz_board_load(b, rows + (size_t)g * 2 * H, m, H);
+  if (a >= gd.n_actions || rz_board_occupied(b, a, H)) {  // gomoku_env.py:51
+    if (lane == 0) m[RZ_META_FAULT] |= RZ_FAULT_ILLEGAL_MOVE;
+    return;
+  }
+  const int mover = b.player;
+  rz_board_play(b, a, H);
+  int winner;
+  const int status = rz_board_status(b, H, gd.n_in_row, winner);
+  rz_board_store_rows(b, rows + (size_t)g * 2 * H, H);
+  if (lane == 0) {
+    m[RZ_META_PLAYER] = b.player;
+    m[RZ_META_LAST_MOVE] = b.last_move;
+    m[RZ_META_STONES] = b.stones;
+    m[RZ_META_STATUS] = status;
+    m[RZ_META_WINNER] = winner;
+    m[RZ_META_PLY] += 1;
+    const int w = status == RZ_ENDED_WIN;                   // gomoku_env.py:59-65
+    if (win) win[g] = w;
+    if (reward) reward[g] = w ? (winner == mover ? 1 : -1) : 0;
+  }
+}
+
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_gomoku_legal_kernel(rz_game_desc gd, const uint32_t* rows, uint8_t* mask, int n) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const int lane = rz_lane(), H = gd.board_size, A = gd.n_actions;
+  const uint32_t occ = lane < H ? (rows[(size_t)g * 2 * H + lane] | rows[(size_t)g * 2 * H + H + lane]) : 0u;
+  for (int s0 = 0; s0 < A; s0 += 32) {
+    const int s = s0 + lane;
+    const int sc = s < A ? s : 0;
+    const int r = sc / H, c = sc - r * H;
+    const uint32_t o = __shfl_sync(RZ_FULL, occ, r);
+    if (s < A) mask[(size_t)g * A + s] = ((o >> c) & 1u) ? 0 : 1;
+  }
+}
+
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_gomoku_winner_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t* meta, int32_t* end,
+                        int32_t* winner_out, int n) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const int H = gd.board_size;
+  rz_wboard b;
+  rz_board_load(b, rows + (size_t)g * 2 * H, meta + (size_t)g * RZ_META_STRIDE, H);
+  int winner;
+  const int status = rz_board_status(b, H, gd.n_in_row, winner);
+  if (rz_lane() == 0) {
+    end[g] = status != RZ_ACTIVE;
+    winner_out[g] = winner;
+  }
+}
+
+// plane value for (plane, r, c) from the distributed rows -- gomoku_env.py:95-114
+__device__ __forceinline__ float rz_plane_value(const rz_wboard& b, uint32_t mine, uint32_t theirs,
+                                                int plane, int r, int c, int W) {
+  // all lanes call (shuffles inside)
+  const uint32_t mrow = __shfl_sync(RZ_FULL, mine, r);
+  const uint32_t trow = __shfl_sync(RZ_FULL, theirs, r);
+  float v = 0.0f;
+  if (plane == 0) v = (float)((mrow >> c) & 1u);
+  else if (plane == 1) v = (float)((trow >> c) & 1u);
+  else if (plane == 2) v = (b.stones > 0 && b.last_move == r * W + c) ? 1.0f : 0.0f;
+  else v = (b.stones & 1) ? 0.0f : 1.0f;
+  return v;
+}
+
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_gomoku_encode_f32_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t* meta,
+                            float* planes, int n) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const int lane = rz_lane(), H = gd.board_size, A = gd.n_actions;
+  rz_wboard b;
+  rz_board_load(b, rows + (size_t)g * 2 * H, meta + (size_t)g * RZ_META_STRIDE, H);
+  const uint32_t mine = b.p[b.player], theirs = b.p[b.player ^ 1];
+  const int total = 4 * A;
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    const int ic = i < total ? i : 0;
+    const int plane = ic / A, pos = ic - plane * A;
+    const int r = pos / H, c = pos - r * H;
+    const float v = rz_plane_value(b, mine, theirs, plane, r, c, H);
+    if (i < total) planes[(size_t)g * total + i] = v;
+  }
+}
+
+// bf16 [n][256 positions][64 channels]: position p = y*16 + x, channels 0..3 = the 4 planes.
+// One 16-byte store per (position, 8-channel group); only group 0 carries data.
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_gomoku_encode_tc_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t* meta,
+                           __nv_bfloat16* act, int n) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const int lane = rz_lane(), H = gd.board_size;
+  rz_wboard b;
+  rz_board_load(b, rows + (size_t)g * 2 * H, meta + (size_t)g * RZ_META_STRIDE, H);
+  const uint32_t mine = b.p[b.player], theirs = b.p[b.player ^ 1];
+  uint4* out = reinterpret_cast<uint4*>(act + (size_t)g * 256 * 64);
+  const float colour = (b.stones & 1) ? 0.0f : 1.0f;
+  for (int p0 = 0; p0 < 256; p0 += 32) {
+    const int p = p0 + lane;
+    const int y = p >> 4, x = p & 15;
+    const uint32_t mrow = __shfl_sync(RZ_FULL, mine, y & 31);
+    const uint32_t trow = __shfl_sync(RZ_FULL, theirs, y & 31);
+    const bool inside = (y < H) && (x < H);
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+    if (inside) {
+      f0 = (float)((mrow >> x) & 1u);
+      f1 = (float)((trow >> x) & 1u);
+      f2 = (b.stones > 0 && b.last_move == y * H + x) ? 1.0f : 0.0f;
+      f3 = colour;
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(f0, f1), hi = __floats2bfloat162_rn(f2, f3);
+    uint4 v0;
+    v0.x = *reinterpret_cast<uint32_t*>(&lo);
+    v0.y = *reinterpret_cast<uint32_t*>(&hi);
+    v0.z = 0u; v0.w = 0u;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4* dst = out + (size_t)p * 8;  // 64 bf16 = 8 x 16 B
+    dst[0] = v0;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) dst[j] = z;
+  }
+}
+
+// closed-form evaluators (oracle/evaluators.py) on the leaf positions of a wave
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* value) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  if (t.depth[g] < 0) return;
+  const int lane = rz_lane(), H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  rz_wboard b;
+  rz_board_load(b, t.leaf_rows + (size_t)g * 2 * H, t.leaf_meta + (size_t)g * RZ_META_STRIDE, H);
+  uint32_t h = 0;
+  if (eval_id == RZ_EVAL_HASH) {
+    for (int c = 0; c < 2; ++c) {
+      uint32_t w = b.p[c];
+      while (w) {
+        const int col = __ffs(w) - 1;
+        w &= w - 1;
+        const uint32_t m1 = (uint32_t)(lane * H + col + 1);
+        h += m1 * m1 * (3u + 4u * (uint32_t)c);
+      }
+    }
+    h = rz_warp_sum_u32(h);
+    h += 7u * (uint32_t)(b.last_move + 1);
+    h *= 2654435761u;
+  }
+  float v = 0.0f;
+  if (eval_id == RZ_EVAL_KAT) v = (float)((17 * b.stones + 31 * (b.last_move + 1)) % 13 - 6) / 8.0f;
+  else if (eval_id == RZ_EVAL_HASH) v = (float)((int)((h >> 16) % 129u) - 64) / 64.0f;
+  if (lane == 0) value[g] = v;
+  const int n_legal = A - b.stones;
+  const float uni = n_legal > 0 ? __fdiv_rn(1.0f, (float)n_legal) : 0.0f;
+  for (int s0 = 0; s0 < AS; s0 += 32) {
+    const int s = s0 + lane;
+    const bool legal = rz_board_slot_legal(b, s, H, A);
+    float p = 0.0f;
+    if (legal) p = (eval_id == RZ_EVAL_HASH) ? (float)(((uint32_t)s * 29u + (h >> 8)) % 32u + 1u) / 256.0f : uni;
+    prior[(size_t)g * AS + s] = p;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+static inline dim3 rz_grid(int n, int warps) { return dim3((unsigned)((n + warps - 1) / warps)); }
+
+extern "C" int rz_gomoku_reset(const rz_game_desc* g, uint32_t* rows, int32_t* meta, int n_games,
+                               int only_ended, void* stream) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(rows && meta && n_games >= 0, "rz_gomoku_reset: bad arguments");
+  if (n_games == 0) return 0;
+  rz_gomoku_reset_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream>>>(
+      *g, rows, meta, n_games, only_ended);
+  RZ_LAUNCH_CHECK("rz_gomoku_reset");
+  return 0;
+}
+
+extern "C" int rz_gomoku_step(const rz_game_desc* g, uint32_t* rows, int32_t* meta,
+                              const int32_t* actions, int32_t* reward, int32_t* win, int n_games,
+                              void* stream) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(rows && meta && actions && n_games >= 0, "rz_gomoku_step: bad arguments");
+  if (n_games == 0) return 0;
+  rz_gomoku_step_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream>>>(
+      *g, rows, meta, actions, reward, win, n_games);
+  RZ_LAUNCH_CHECK("rz_gomoku_step");
+  return 0;
+}
+
+extern "C" int rz_gomoku_legal_mask(const rz_game_desc* g, const uint32_t* rows, uint8_t* mask,
+                                    int n_games, void* stream) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(rows && mask && n_games >= 0, "rz_gomoku_legal_mask: bad arguments");
+  if (n_games == 0) return 0;
+  rz_gomoku_legal_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream>>>(
+      *g, rows, mask, n_games);
+  RZ_LAUNCH_CHECK("rz_gomoku_legal_mask");
+  return 0;
+}
+
+extern "C" int rz_gomoku_winner(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
+                                int32_t* end, int32_t* winner, int n_games, void* stream) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(rows && meta && end && winner && n_games >= 0, "rz_gomoku_winner: bad arguments");
+  if (n_games == 0) return 0;
+  rz_gomoku_winner_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream>>>(
+      *g, rows, meta, end, winner, n_games);
+  RZ_LAUNCH_CHECK("rz_gomoku_winner");
+  return 0;
+}
+
+extern "C" int rz_gomoku_encode_f32(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
+                                    float* planes, int n_games, void* stream) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(rows && meta && planes && n_games >= 0, "rz_gomoku_encode_f32: bad arguments");
+  if (n_games == 0) return 0;
+  rz_gomoku_encode_f32_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+                                (cudaStream_t)stream>>>(*g, rows, meta, planes, n_games);
+  RZ_LAUNCH_CHECK("rz_gomoku_encode_f32");
+  return 0;
+}
+
+extern "C" int rz_gomoku_encode_tc(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
+                                   void* act_bf16, int n_games, void* stream) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(rows && meta && act_bf16 && n_games >= 0, "rz_gomoku_encode_tc: bad arguments");
+  RZ_REQUIRE(g->board_size <= 15, "rz_gomoku_encode_tc: the 16x16 tile layout holds boards up to 15x15");
+  if (n_games == 0) return 0;
+  rz_gomoku_encode_tc_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+                               (cudaStream_t)stream>>>(*g, rows, meta, (__nv_bfloat16*)act_bf16, n_games);
+  RZ_LAUNCH_CHECK("rz_gomoku_encode_tc");
+  return 0;
+}
+
+extern "C" int rz_eval_closed_form(const rz_tree_desc* t, int eval_id, float* prior, float* value,
+                                   void* stream) {
+  RZ_REQUIRE(t && prior && value, "rz_eval_closed_form: null argument");
+  if (rz_check_game(&t->game)) return -1;
+  RZ_REQUIRE(eval_id >= RZ_EVAL_ZERO && eval_id <= RZ_EVAL_HASH, "rz_eval_closed_form: eval_id %d", eval_id);
+  if (t->n_trees == 0) return 0;
+  rz_eval_closed_form_kernel<<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+                               (cudaStream_t)stream>>>(*t, eval_id, prior, value);
+  RZ_LAUNCH_CHECK("rz_eval_closed_form");
+  return 0;
+}

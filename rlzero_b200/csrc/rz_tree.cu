@@ -1,0 +1,703 @@
+// rlzero_b200 -- search-tree kernels: one warp owns one tree.
+//
+// Reference semantics (file:line under /root/reference):
+//   select         rlzero/mcts/alphazero_mcts.py:48-54, rlzero/mcts/node.py:32-42,75-88
+//   PUCT rule      rlzero/mcts/deepmind_mcts.py:149-151
+//   expand         rlzero/mcts/node.py:44-73
+//   terminal value rlzero/mcts/alphazero_mcts.py:60-68
+//   backup         rlzero/mcts/node.py:119-144
+//   root policy    rlzero/mcts/alphazero_mcts.py:86-94,144-148
+//   re-root        rlzero/mcts/alphazero_mcts.py:96-103
+//   trajectory     rlzero/games/gomoku/game.py:113-134
+//
+// Layout: an expanded node owns an "edge block" of AS slots indexed by action; a child's
+// visit count / value sum live in its parent's block, so one descent step is one coalesced
+// sweep over N (and W only when every child has been visited).  The reference runs one
+// playout at a time; here every tree runs exactly one playout per wave, which keeps the
+// per-tree order of updates -- and therefore every fp64 sum and every tie-break -- identical.
+//
+// Bit-exactness: scores are formed with the explicit round-to-nearest fp64 intrinsics
+// (__ddiv_rn/__dsqrt_rn/__dmul_rn/__dadd_rn never contract into FMA), ln(Np) comes from a
+// host-libm table (CPython's math.log), and ties go to the lowest action (Python max()).
+#include <string.h>
+
+#include "rz_board.cuh"
+
+#define RZ_TREE_WARPS 4
+#define RZ_TREE_THREADS (RZ_TREE_WARPS * 32)
+#define RZ_MAX_ITERS 12  // AS/32 <= 12  (A <= 361 -> AS <= 384)
+
+__device__ __forceinline__ size_t rz_edge_base(const rz_tree_desc& t, int g, int node) {
+  return ((size_t)g * t.max_nodes + node) * (size_t)t.game.action_stride;
+}
+
+// argmax over (score desc, slot asc) across the warp; n rides along.
+__device__ __forceinline__ void rz_warp_argmax(double& s, int& slot, int& n) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double s2 = __shfl_xor_sync(RZ_FULL, s, o);
+    const int slot2 = __shfl_xor_sync(RZ_FULL, slot, o);
+    const int n2 = __shfl_xor_sync(RZ_FULL, n, o);
+    const bool take = (slot2 >= 0) && (slot < 0 || s2 > s || (s2 == s && slot2 < slot));
+    if (take) { s = s2; slot = slot2; n = n2; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1: select.  One playout descent per tree + leaf terminal test.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc t) {
+  const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  const int lane = rz_lane();
+  const int H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  const int iters = AS >> 5;
+  int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
+  if (rmeta[RZ_META_STATUS] != RZ_ACTIVE) {
+    if (lane == 0) t.depth[g] = -1;
+    return;
+  }
+  rz_wboard b;
+  rz_board_load(b, t.root_rows + (size_t)g * 2 * H, rmeta, H);
+
+  int fault = 0;
+  int depth = 0;
+  int node = 0;
+  int Np = t.root_N[g];
+  bool descend = t.n_nodes[g] > 0;
+  int32_t* pnode = t.path_node + (size_t)g * t.max_depth;
+  int32_t* pact = t.path_action + (size_t)g * t.max_depth;
+
+  while (descend) {
+    if (depth >= t.max_depth) { fault |= RZ_FAULT_DEPTH_OVERFLOW; break; }
+    const size_t base = rz_edge_base(t, g, node);
+    const int32_t* __restrict__ eN = t.edge_N + base;
+    // pass 1: visit counts (coalesced, all loads in flight at once)
+    int nv[RZ_MAX_ITERS];
+#pragma unroll
+    for (int i = 0; i < RZ_MAX_ITERS; ++i) nv[i] = (i < iters) ? eN[lane + 32 * i] : -1;
+
+    double best_s = 0.0;
+    int best_slot = -1, best_n = 0;
+    if (t.rule == RZ_RULE_UCT) {
+      // node.py:76-80: +inf when the parent or the child is unvisited -> first such child wins
+      int first_unvisited = -1;
+#pragma unroll
+      for (int i = RZ_MAX_ITERS - 1; i >= 0; --i)
+        if (i < iters && (nv[i] == 0 || (nv[i] > 0 && Np == 0))) first_unvisited = lane + 32 * i;
+      // lowest slot over the warp
+      int cand = first_unvisited < 0 ? 0x7fffffff : first_unvisited;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(RZ_FULL, cand, o));
+      if (cand != 0x7fffffff) {
+        best_slot = cand;
+        best_n = eN[cand];
+      } else {
+        // every child visited: W/n + c*sqrt(ln(Np)/n)   (node.py:82-88)
+        const double* __restrict__ eW = t.edge_W + base;
+        double wv[RZ_MAX_ITERS];
+#pragma unroll
+        for (int i = 0; i < RZ_MAX_ITERS; ++i)
+          wv[i] = (i < iters && nv[i] > 0) ? eW[lane + 32 * i] : 0.0;
+        int NpC = Np;
+        if (NpC >= t.ln_table_len) { fault |= RZ_FAULT_LN_TABLE; NpC = t.ln_table_len - 1; }
+        const double lnNp = t.ln_table[NpC];
+#pragma unroll
+        for (int i = 0; i < RZ_MAX_ITERS; ++i) {
+          if (i < iters && nv[i] > 0) {
+            const double n = (double)nv[i];
+            const double q = __ddiv_rn(wv[i], n);
+            const double u = __dsqrt_rn(__ddiv_rn(lnNp, n));
+            const double s = __dadd_rn(q, __dmul_rn(t.c_puct, u));
+            if (best_slot < 0 || s > best_s) { best_s = s; best_slot = lane + 32 * i; best_n = nv[i]; }
+          }
+        }
+        rz_warp_argmax(best_s, best_slot, best_n);
+      }
+    } else {
+      // deepmind_mcts.py:149-151: (n and W/n) + ((c*P)*sqrt(Np))/(n+1)
+      const double* __restrict__ eW = t.edge_W + base;
+      const float* __restrict__ eP = t.edge_P + base;
+      const double sq = __dsqrt_rn((double)Np);
+#pragma unroll
+      for (int i = 0; i < RZ_MAX_ITERS; ++i) {
+        if (i < iters && nv[i] >= 0) {
+          const int slot = lane + 32 * i;
+          const double q = nv[i] > 0 ? __ddiv_rn(eW[slot], (double)nv[i]) : 0.0;
+          const double u = __ddiv_rn(__dmul_rn(__dmul_rn(t.c_puct, (double)eP[slot]), sq),
+                                     (double)(nv[i] + 1));
+          const double s = __dadd_rn(q, u);
+          if (best_slot < 0 || s > best_s) { best_s = s; best_slot = slot; best_n = nv[i]; }
+        }
+      }
+      rz_warp_argmax(best_s, best_slot, best_n);
+    }
+    if (best_slot < 0) { fault |= RZ_FAULT_NO_CHILDREN; break; }  // node.py:38-39
+
+    if (lane == 0) { pnode[depth] = node; pact[depth] = best_slot; }
+    depth += 1;
+    rz_board_play(b, best_slot, H);  // game_env.step(action), alphazero_mcts.py:54
+    if (best_n == 0) break;          // never visited -> unexpanded leaf
+    const int child = t.edge_child[base + best_slot];
+    if (child < 0) break;            // terminal (or overflowed) leaf, re-evaluated every visit
+    node = child;
+    Np = best_n;
+  }
+
+  // leaf: game_end_winner() (alphazero_mcts.py:60)
+  int winner;
+  const int status = rz_board_status(b, H, t.game.n_in_row, winner);
+  rz_board_store_rows(b, t.leaf_rows + (size_t)g * 2 * H, H);
+  if (lane == 0) {
+    int32_t* lm = t.leaf_meta + (size_t)g * RZ_META_STRIDE;
+    lm[RZ_META_PLAYER] = b.player;
+    lm[RZ_META_LAST_MOVE] = b.last_move;
+    lm[RZ_META_STONES] = b.stones;
+    lm[RZ_META_STATUS] = status;
+    lm[RZ_META_WINNER] = winner;
+    lm[RZ_META_PLY] = depth;
+    lm[RZ_META_FAULT] = fault;
+    lm[RZ_META_EPISODE] = rmeta[RZ_META_EPISODE];
+    t.depth[g] = depth;
+    if (fault) rmeta[RZ_META_FAULT] |= fault;
+  }
+  (void)A;
+}
+
+// ---------------------------------------------------------------------------
+// Dirichlet(alpha) noise: one Gamma(alpha,1) draw per legal slot (Marsaglia-Tsang on
+// alpha+1, boosted by U^(1/alpha)), normalised over the node (node.py:63-69).
+// ---------------------------------------------------------------------------
+__device__ float rz_gamma_draw(float alpha, unsigned long long seed, uint32_t c0, uint32_t c1,
+                               uint32_t c2) {
+  const float d = alpha + 1.0f - 1.0f / 3.0f;
+  const float c = rsqrtf(9.0f * d);
+  for (uint32_t it = 0; it < 64; ++it) {
+    uint32_t r[4];
+    rz_philox4(c0, c1, c2, it, seed, r);
+    // Box-Muller normal from r[0], r[1]
+    const float u1 = rz_u01_24(r[0]), u2 = rz_u01_24(r[1]);
+    const float x = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    float v = 1.0f + c * x;
+    if (v <= 0.0f) continue;
+    v = v * v * v;
+    const float u = rz_u01_24(r[2]);
+    if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) {
+      const float boost = powf(rz_u01_24(r[3]), 1.0f / alpha);
+      return d * v * boost;
+    }
+  }
+  return alpha;  // unreachable in practice
+}
+
+// ---------------------------------------------------------------------------
+// K5+K6: expand the leaf (unless terminal) and back the value up the path.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(RZ_TREE_THREADS)
+rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int prior_is_log,
+                        const float* __restrict__ value, const double* __restrict__ value64,
+                        float noise_eps, float noise_alpha,
+                        unsigned long long seed, long long global_offset) {
+  const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  const int depth = t.depth[g];
+  if (depth < 0) return;
+  const int lane = rz_lane();
+  const int H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  const int32_t* lm = t.leaf_meta + (size_t)g * RZ_META_STRIDE;
+  const int32_t* rm = t.root_meta + (size_t)g * RZ_META_STRIDE;
+  const int status = lm[RZ_META_STATUS];
+  int32_t* pnode = t.path_node + (size_t)g * t.max_depth;
+  int32_t* pact = t.path_action + (size_t)g * t.max_depth;
+
+  // alphazero_mcts.py:59-68: network value unless the game is over at the leaf
+  double v;
+  int child_mark = 0;  // what to store in the parent's child[] slot
+  bool have_mark = false;
+  if (status == RZ_ENDED_WIN) {
+    v = (lm[RZ_META_WINNER] == lm[RZ_META_PLAYER]) ? 1.0 : -1.0;
+    child_mark = RZ_CHILD_TERMINAL; have_mark = true;
+  } else if (status == RZ_ENDED_TIE) {
+    v = 0.0;
+    child_mark = RZ_CHILD_TERMINAL; have_mark = true;
+  } else {
+    v = value64 ? value64[g] : (double)value[g];
+    const int nn = t.n_nodes[g];
+    if (nn < t.max_nodes) {
+      // node.py:71-73: one child per legal move, in ascending action order
+      const uint32_t myocc = lane < H ? (t.leaf_rows[(size_t)g * 2 * H + lane] |
+                                         t.leaf_rows[(size_t)g * 2 * H + H + lane]) : 0u;
+      const size_t nb = rz_edge_base(t, g, nn);
+      const float* pr = prior + (size_t)g * AS;
+      float noise_sum = 0.0f;
+      float nz[RZ_MAX_ITERS];
+      const bool noisy = noise_eps > 0.0f;
+#pragma unroll
+      for (int i = 0; i < RZ_MAX_ITERS; ++i) {
+        if (i >= (AS >> 5)) break;
+        const int s = lane + 32 * i;
+        const int sc = s < A ? s : 0;
+        const int r = sc / H, c = sc - r * H;
+        const uint32_t occ = __shfl_sync(RZ_FULL, myocc, r);
+        const bool legal = s < A && !((occ >> c) & 1u);
+        t.edge_N[nb + s] = legal ? 0 : -1;
+        nz[i] = 0.0f;
+        if (noisy && legal) {
+          nz[i] = rz_gamma_draw(noise_alpha, seed, (uint32_t)(global_offset + g),
+                                (uint32_t)rm[RZ_META_EPISODE],
+                                ((uint32_t)rm[RZ_META_PLY] << 21) | ((uint32_t)nn << 9) | (uint32_t)s);
+          noise_sum += nz[i];
+        }
+        if (t.store_priors && !noisy) {
+          float p = legal ? pr[s] : 0.0f;
+          if (legal && prior_is_log) p = expf(p);
+          t.edge_P[nb + s] = p;
+        }
+      }
+      if (noisy) {
+        noise_sum = rz_warp_sum_f32(noise_sum);
+        const float inv = noise_sum > 0.0f ? 1.0f / noise_sum : 0.0f;
+        if (t.store_priors) {
+#pragma unroll
+          for (int i = 0; i < RZ_MAX_ITERS; ++i) {
+            if (i >= (AS >> 5)) break;
+            const int s = lane + 32 * i;
+            const bool legal = t.edge_N[nb + s] == 0;
+            float p = legal ? pr[s] : 0.0f;
+            if (legal && prior_is_log) p = expf(p);
+            t.edge_P[nb + s] = legal ? (1.0f - noise_eps) * p + noise_eps * nz[i] * inv : 0.0f;
+          }
+        }
+      }
+      if (lane == 0) {
+        t.node_parent[(size_t)g * t.max_nodes + nn] = depth > 0 ? pnode[depth - 1] : -1;
+        t.node_paction[(size_t)g * t.max_nodes + nn] = depth > 0 ? pact[depth - 1] : -1;
+        t.n_nodes[g] = nn + 1;
+      }
+      child_mark = nn; have_mark = true;
+    } else {
+      child_mark = RZ_CHILD_OVERFLOW; have_mark = true;
+      if (lane == 0) t.root_meta[(size_t)g * RZ_META_STRIDE + RZ_META_FAULT] |= RZ_FAULT_POOL_OVERFLOW;
+    }
+  }
+  if (have_mark && depth > 0 && lane == 0) {
+    t.edge_child[rz_edge_base(t, g, pnode[depth - 1]) + pact[depth - 1]] = child_mark;
+  }
+
+  // node.py:135-144 with update_recursive(-leaf_value): the leaf gets -v, its parent +v, ...
+  // edge k (0-based from the root) holds the node at depth k+1 and gets (-1)^(depth-k) * v.
+  for (int k = lane; k < depth; k += 32) {
+    const size_t e = rz_edge_base(t, g, pnode[k]) + pact[k];
+    const double x = ((depth - k) & 1) ? -v : v;
+    const int n = t.edge_N[e];
+    t.edge_W[e] = n > 0 ? __dadd_rn(t.edge_W[e], x) : __dadd_rn(0.0, x);
+    t.edge_N[e] = n + 1;
+  }
+  if (lane == 0) {
+    const double x = (depth & 1) ? v : -v;  // root at depth 0: (-1)^(depth+1) * v
+    t.root_W[g] = __dadd_rn(t.root_W[g], x);
+    t.root_N[g] += 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K7: root policy  pi = softmax(log(N + 1e-10) / T) over the root's children and move sampling
+// (alphazero_mcts.py:86-94, 144-148).  Sampling mirrors numpy.random.choice: first index
+// whose normalised cumulative probability exceeds u.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(RZ_TREE_THREADS)
+rz_root_policy_kernel(rz_tree_desc t, double temperature, int32_t* __restrict__ visits,
+                      float* __restrict__ pi, int32_t* __restrict__ move,
+                      const double* __restrict__ u01, unsigned long long seed,
+                      long long global_offset) {
+  const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  const int lane = rz_lane();
+  const int AS = t.game.action_stride;
+  const int iters = AS >> 5;
+  int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
+  const bool active = rmeta[RZ_META_STATUS] == RZ_ACTIVE;
+  const bool expanded = t.n_nodes[g] > 0;
+  const size_t base = rz_edge_base(t, g, 0);
+  int nv[RZ_MAX_ITERS];
+  double x[RZ_MAX_ITERS];
+  double mx = -1.0e300;
+#pragma unroll
+  for (int i = 0; i < RZ_MAX_ITERS; ++i) {
+    nv[i] = (i < iters && active && expanded) ? t.edge_N[base + lane + 32 * i] : -1;
+    x[i] = 0.0;
+    if (nv[i] >= 0) {
+      x[i] = (1.0 / temperature) * log((double)nv[i] + 1e-10);
+      mx = fmax(mx, x[i]);
+    }
+  }
+  mx = rz_warp_max_f64(mx);
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < RZ_MAX_ITERS; ++i) {
+    x[i] = nv[i] >= 0 ? exp(x[i] - mx) : 0.0;
+    sum += x[i];
+  }
+  sum = rz_warp_sum_f64(sum);
+  const bool any = sum > 0.0;
+  if (active && !any && lane == 0) rmeta[RZ_META_FAULT] |= RZ_FAULT_NO_CHILDREN;
+#pragma unroll
+  for (int i = 0; i < RZ_MAX_ITERS; ++i) {
+    if (i < iters) {
+      const size_t o = (size_t)g * AS + lane + 32 * i;
+      x[i] = any ? x[i] / sum : 0.0;
+      if (visits) visits[o] = nv[i] > 0 ? nv[i] : 0;
+      if (pi) pi[o] = (float)x[i];
+    }
+  }
+  if (move) {
+    double u;
+    if (u01) {
+      u = u01[g];
+    } else {
+      uint32_t r[4];
+      rz_philox4((uint32_t)(global_offset + g), (uint32_t)rmeta[RZ_META_EPISODE],
+                 (uint32_t)rmeta[RZ_META_STONES], 0x5eedu, seed, r);
+      u = rz_u01_53(r[0], r[1]);
+    }
+    // cumulative sum in action order: slot = lane + 32*i, so scan chunk by chunk
+    int chosen = -1, last_legal = -1;
+    double carry = 0.0;
+    for (int i = 0; i < iters; ++i) {
+      double xi = 0.0; int ni = -1;
+#pragma unroll
+      for (int j = 0; j < RZ_MAX_ITERS; ++j) if (j == i) { xi = x[j]; ni = nv[j]; }
+      const double inc = rz_warp_scan_f64(xi) + carry;
+      const unsigned hit = __ballot_sync(RZ_FULL, ni >= 0 && inc > u);
+      const unsigned leg = __ballot_sync(RZ_FULL, ni >= 0);
+      if (leg) last_legal = 32 * i + (31 - __clz(leg));
+      if (hit && chosen < 0) chosen = 32 * i + (__ffs(hit) - 1);
+      carry = __shfl_sync(RZ_FULL, inc, 31);
+    }
+    if (chosen < 0) chosen = last_legal;  // u beyond the rounded total
+    if (lane == 0) move[g] = (active && any) ? chosen : -1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K8 (+K9): play the move on the root position, record the trajectory ply, re-root.
+// ---------------------------------------------------------------------------
+extern __shared__ uint32_t rz_adv_smem[];
+
+__device__ void rz_tree_fresh(const rz_tree_desc& t, int g, int n, double w) {
+  t.n_nodes[g] = 0;
+  t.root_N[g] = n;
+  t.root_W[g] = w;
+}
+
+__device__ __forceinline__ int rz_newidx(const uint32_t* bits, const uint32_t* wprefix, int i) {
+  return (int)wprefix[i >> 5] + __popc(bits[i >> 5] & ((1u << (i & 31)) - 1u));
+}
+
+// In-place compaction of the subtree rooted at old node c to indices 0..m-1, ascending
+// old index (parents always precede children, so dst <= src and nothing unread is clobbered).
+__device__ int rz_tree_compact(const rz_tree_desc& t, int g, int c, uint32_t* bits,
+                               uint32_t* wprefix, int max_carry) {
+  const int lane = rz_lane();
+  const int nn = t.n_nodes[g];
+  const int nwords = (nn + 31) >> 5;
+  const int AS = t.game.action_stride;
+  int32_t* parent = t.node_parent + (size_t)g * t.max_nodes;
+  int32_t* paction = t.node_paction + (size_t)g * t.max_nodes;
+  for (int w = lane; w < nwords; w += 32) bits[w] = 0u;
+  __syncwarp();
+  // 1. membership sweep
+  for (int i0 = (c >> 5) << 5; i0 < nn; i0 += 32) {
+    const int i = i0 + lane;
+    const int p = i < nn ? parent[i] : -1;
+    bool in = (i == c);
+    if (i < nn && i > c && p >= 0 && p < i0) in = (bits[p >> 5] >> (p & 31)) & 1u;
+    const bool local = (i < nn && i > c && p >= i0);
+    for (int it = 0; it < 32; ++it) {
+      const bool pin = __shfl_sync(RZ_FULL, in, local ? (p - i0) : 0);
+      const bool nin = in || (local && pin);
+      const unsigned changed = __ballot_sync(RZ_FULL, nin != in);
+      in = nin;
+      if (!changed) break;
+    }
+    const unsigned word = __ballot_sync(RZ_FULL, in);
+    if (lane == 0) bits[i0 >> 5] = word;
+    __syncwarp();
+  }
+  // 2. exclusive prefix of popcounts per word
+  int total = 0;
+  for (int w0 = 0; w0 < nwords; w0 += 32) {
+    const int w = w0 + lane;
+    const int cnt = w < nwords ? __popc(bits[w]) : 0;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tt = __shfl_up_sync(RZ_FULL, inc, o);
+      if (lane >= o) inc += tt;
+    }
+    if (w < nwords) wprefix[w] = total + inc - cnt;
+    total += __shfl_sync(RZ_FULL, inc, 31);
+  }
+  __syncwarp();
+  if (total > max_carry) return -1;
+  // 3. move blocks
+  for (int w = c >> 5; w < nwords; ++w) {
+    uint32_t word = bits[w];
+    while (word) {
+      const int bit = __ffs(word) - 1;
+      word &= word - 1;
+      const int src = (w << 5) + bit;
+      const int dst = rz_newidx(bits, wprefix, src);
+      const size_t sb = rz_edge_base(t, g, src), db = rz_edge_base(t, g, dst);
+      for (int s = lane; s < AS; s += 32) {
+        const int n = t.edge_N[sb + s];
+        const double wv = t.edge_W[sb + s];
+        int ch = t.edge_child[sb + s];
+        if (n >= 1 && ch >= 0) ch = rz_newidx(bits, wprefix, ch);
+        t.edge_N[db + s] = n;
+        t.edge_W[db + s] = wv;
+        t.edge_child[db + s] = ch;
+        if (t.store_priors) t.edge_P[db + s] = t.edge_P[sb + s];
+      }
+      if (lane == 0) {
+        const int p = parent[src];
+        const int pa = paction[src];
+        parent[dst] = (src == c) ? -1 : rz_newidx(bits, wprefix, p);
+        paction[dst] = (src == c) ? -1 : pa;
+      }
+      __syncwarp();
+    }
+  }
+  return total;
+}
+
+__global__ void __launch_bounds__(RZ_TREE_THREADS)
+rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_subtree,
+                  int max_carry, rz_traj_desc traj, int have_traj, const float* __restrict__ pi,
+                  int auto_reset, int words_per_warp) {
+  const int wib = threadIdx.x >> 5;
+  const int g = blockIdx.x * RZ_TREE_WARPS + wib;
+  if (g >= t.n_trees) return;
+  const int lane = rz_lane();
+  const int H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  uint32_t* bits = rz_adv_smem + (size_t)wib * 2 * words_per_warp;
+  uint32_t* wprefix = bits + words_per_warp;
+  int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
+  const int m = moves[g];
+  if (m < 0) {  // reset_player(): update_with_move(-1)  (alphazero_mcts.py:132-134)
+    if (lane == 0) rz_tree_fresh(t, g, 0, 0.0);
+    return;
+  }
+  if (rmeta[RZ_META_STATUS] != RZ_ACTIVE) return;
+  rz_wboard b;
+  uint32_t* rrows = t.root_rows + (size_t)g * 2 * H;
+  rz_board_load(b, rrows, rmeta, H);
+  if (m >= A || rz_board_occupied(b, m, H)) {  // gomoku_env.py:51
+    if (lane == 0) rmeta[RZ_META_FAULT] |= RZ_FAULT_ILLEGAL_MOVE;
+    return;
+  }
+  const int ply = rmeta[RZ_META_PLY];
+  // game.py:113-115: (current_state, move_probs, current_player) before the move
+  if (have_traj) {
+    if (ply < traj.max_plies) {
+      const size_t so = (size_t)g * traj.max_plies + ply;
+      rz_board_store_rows(b, traj.stage_rows + so * 2 * H, H);
+      if (lane == 0) {
+        int32_t* si = traj.stage_info + so * 4;
+        si[0] = b.player; si[1] = b.last_move; si[2] = m; si[3] = b.stones;
+      }
+      for (int s = lane; s < AS; s += 32)
+        traj.stage_pi[so * AS + s] = pi ? pi[(size_t)g * AS + s] : 0.0f;
+    } else if (lane == 0) {
+      rmeta[RZ_META_FAULT] |= RZ_FAULT_TRAJ_OVERFLOW;
+    }
+  }
+  // game.py:117: game_env.step(move)
+  rz_board_play(b, m, H);
+  int winner;
+  const int status = rz_board_status(b, H, t.game.n_in_row, winner);
+
+  // alphazero_mcts.py:96-103
+  const bool root_expanded = t.n_nodes[g] > 0;
+  const size_t rb = rz_edge_base(t, g, 0);
+  const int cn = root_expanded ? t.edge_N[rb + m] : -1;  // -1: move not among the children
+  const double cw = (cn > 0) ? t.edge_W[rb + m] : 0.0;
+  const int cc = (cn > 0) ? t.edge_child[rb + m] : -1;
+  if (!keep_subtree || cn < 0) {
+    if (lane == 0) rz_tree_fresh(t, g, 0, 0.0);
+  } else if (cc < 0) {  // child exists but was never expanded: it keeps its own counts
+    if (lane == 0) rz_tree_fresh(t, g, cn, cw);
+  } else {
+    const int kept = rz_tree_compact(t, g, cc, bits, wprefix, max_carry);
+    if (lane == 0) {
+      if (kept < 0) {
+        rz_tree_fresh(t, g, 0, 0.0);
+        rmeta[RZ_META_FAULT] |= RZ_FAULT_CARRY_DROPPED;
+      } else {
+        t.n_nodes[g] = kept; t.root_N[g] = cn; t.root_W[g] = cw;
+      }
+    }
+  }
+
+  rz_board_store_rows(b, rrows, H);
+  if (lane == 0) {
+    rmeta[RZ_META_PLAYER] = b.player;
+    rmeta[RZ_META_LAST_MOVE] = b.last_move;
+    rmeta[RZ_META_STONES] = b.stones;
+    rmeta[RZ_META_STATUS] = status;
+    rmeta[RZ_META_WINNER] = winner;
+    rmeta[RZ_META_PLY] = ply + 1;
+  }
+  if (status == RZ_ACTIVE) return;
+
+  // game.py:121-134: episode over -> z per ply, flush to the ring, reset_player()
+  if (have_traj) {
+    const int n = min(ply + 1, traj.max_plies);
+    unsigned long long start = 0;
+    if (lane == 0) {
+      start = atomicAdd(traj.ring_cursor, (unsigned long long)n);
+      atomicAdd(traj.games_done, 1ull);
+      atomicAdd(traj.plies_done, (unsigned long long)(ply + 1));
+    }
+    start = __shfl_sync(RZ_FULL, start, 0);
+    const int episode = rmeta[RZ_META_EPISODE];
+    for (int j = 0; j < n; ++j) {
+      const size_t so = (size_t)g * traj.max_plies + j;
+      const size_t ro = (size_t)((start + j) % (unsigned long long)traj.ring_capacity);
+      if (lane < H) {
+        traj.ring_rows[ro * 2 * H + lane] = traj.stage_rows[so * 2 * H + lane];
+        traj.ring_rows[ro * 2 * H + H + lane] = traj.stage_rows[so * 2 * H + H + lane];
+      }
+      if (lane == 0) {
+        const int mover = traj.stage_info[so * 4 + 0];
+        int32_t* ri = traj.ring_info + ro * 6;
+        ri[0] = mover;
+        ri[1] = traj.stage_info[so * 4 + 1];
+        ri[2] = winner < 0 ? 0 : (mover == winner ? 1 : -1);
+        ri[3] = g;
+        ri[4] = episode;
+        ri[5] = j;
+      }
+      for (int s = lane; s < AS; s += 32) traj.ring_pi[ro * AS + s] = traj.stage_pi[so * AS + s];
+    }
+  }
+  if (lane == 0) rz_tree_fresh(t, g, 0, 0.0);
+  if (auto_reset) {
+    if (lane < H) { rrows[lane] = 0u; rrows[H + lane] = 0u; }
+    if (lane == 0) {
+      rmeta[RZ_META_PLAYER] = 0;
+      rmeta[RZ_META_LAST_MOVE] = -1;
+      rmeta[RZ_META_STONES] = 0;
+      rmeta[RZ_META_STATUS] = RZ_ACTIVE;
+      rmeta[RZ_META_WINNER] = -1;
+      rmeta[RZ_META_PLY] = 0;
+      rmeta[RZ_META_EPISODE] += 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Utility kernels + C ABI
+// ---------------------------------------------------------------------------
+__global__ void rz_tree_reset_kernel(rz_tree_desc t, const uint8_t* __restrict__ mask) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= t.n_trees) return;
+  if (mask && !mask[g]) return;
+  t.n_nodes[g] = 0;
+  t.root_N[g] = 0;
+  t.root_W[g] = 0.0;
+  t.depth[g] = -1;
+}
+
+static int rz_check_tree(const rz_tree_desc* t, const char* who) {
+  RZ_REQUIRE(t, "%s: null tree desc", who);
+  if (rz_check_game(&t->game)) return -1;
+  RZ_REQUIRE(t->n_trees >= 0, "%s: n_trees %d", who, t->n_trees);
+  RZ_REQUIRE(t->max_nodes >= 1, "%s: max_nodes %d", who, t->max_nodes);
+  RZ_REQUIRE(t->max_depth >= 1, "%s: max_depth %d", who, t->max_depth);
+  RZ_REQUIRE(t->game.action_stride <= 32 * RZ_MAX_ITERS, "%s: action_stride %d > %d", who,
+             t->game.action_stride, 32 * RZ_MAX_ITERS);
+  RZ_REQUIRE(t->rule == RZ_RULE_UCT || t->rule == RZ_RULE_PUCT, "%s: rule %d", who, t->rule);
+  RZ_REQUIRE(t->edge_N && t->edge_W && t->edge_child && t->node_parent && t->node_paction,
+             "%s: null node pool", who);
+  RZ_REQUIRE(t->rule != RZ_RULE_PUCT || (t->edge_P && t->store_priors),
+             "%s: the PUCT rule needs stored priors", who);
+  RZ_REQUIRE(!t->store_priors || t->edge_P, "%s: store_priors set but edge_P is null", who);
+  RZ_REQUIRE(t->n_nodes && t->root_N && t->root_W && t->root_rows && t->root_meta,
+             "%s: null per-tree array", who);
+  RZ_REQUIRE(t->path_node && t->path_action && t->depth && t->leaf_rows && t->leaf_meta,
+             "%s: null wave scratch", who);
+  RZ_REQUIRE(t->ln_table && t->ln_table_len >= 2, "%s: ln table missing", who);
+  return 0;
+}
+
+static inline dim3 rz_tree_grid(int n) { return dim3((unsigned)((n + RZ_TREE_WARPS - 1) / RZ_TREE_WARPS)); }
+
+extern "C" int rz_tree_reset(const rz_tree_desc* t, const uint8_t* tree_mask, void* stream) {
+  if (rz_check_tree(t, "rz_tree_reset")) return -1;
+  if (t->n_trees == 0) return 0;
+  rz_tree_reset_kernel<<<(t->n_trees + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*t, tree_mask);
+  RZ_LAUNCH_CHECK("rz_tree_reset");
+  return 0;
+}
+
+extern "C" int rz_tree_select(const rz_tree_desc* t, void* stream) {
+  if (rz_check_tree(t, "rz_tree_select")) return -1;
+  if (t->n_trees == 0) return 0;
+  rz_select_kernel<<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(*t);
+  RZ_LAUNCH_CHECK("rz_tree_select");
+  return 0;
+}
+
+extern "C" int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, int prior_is_log,
+                                     const float* value, const double* value64, float noise_eps,
+                                     float noise_alpha,
+                                     unsigned long long seed, void* stream) {
+  if (rz_check_tree(t, "rz_tree_expand_backup")) return -1;
+  RZ_REQUIRE(value || value64, "rz_tree_expand_backup: null value");
+  RZ_REQUIRE(prior || !t->store_priors, "rz_tree_expand_backup: null prior with store_priors");
+  RZ_REQUIRE(noise_eps >= 0.0f && noise_eps <= 1.0f, "rz_tree_expand_backup: noise_eps %f", noise_eps);
+  RZ_REQUIRE(noise_eps == 0.0f || noise_alpha > 0.0f, "rz_tree_expand_backup: noise_alpha %f", noise_alpha);
+  if (t->n_trees == 0) return 0;
+  rz_expand_backup_kernel<<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(
+      *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset);
+  RZ_LAUNCH_CHECK("rz_tree_expand_backup");
+  return 0;
+}
+
+extern "C" int rz_tree_root_policy(const rz_tree_desc* t, double temperature, int32_t* visits,
+                                   float* pi, int32_t* move, const double* u01,
+                                   unsigned long long seed, void* stream) {
+  if (rz_check_tree(t, "rz_tree_root_policy")) return -1;
+  RZ_REQUIRE(temperature > 0.0, "rz_tree_root_policy: temperature %g", temperature);
+  if (t->n_trees == 0) return 0;
+  rz_root_policy_kernel<<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(
+      *t, temperature, visits, pi, move, u01, seed, t->global_offset);
+  RZ_LAUNCH_CHECK("rz_tree_root_policy");
+  return 0;
+}
+
+extern "C" int rz_tree_advance(const rz_tree_desc* t, const int32_t* moves, int keep_subtree,
+                               int max_carry, const rz_traj_desc* traj, const float* pi,
+                               int auto_reset, void* stream) {
+  if (rz_check_tree(t, "rz_tree_advance")) return -1;
+  RZ_REQUIRE(moves, "rz_tree_advance: null moves");
+  RZ_REQUIRE(max_carry >= 0 && max_carry <= t->max_nodes, "rz_tree_advance: max_carry %d", max_carry);
+  rz_traj_desc td;
+  memset(&td, 0, sizeof(td));
+  if (traj) {
+    td = *traj;
+    RZ_REQUIRE(td.max_plies >= 1 && td.ring_capacity >= td.max_plies, "rz_tree_advance: trajectory sizes");
+    RZ_REQUIRE(td.stage_rows && td.stage_info && td.stage_pi && td.ring_rows && td.ring_info &&
+                   td.ring_pi && td.ring_cursor && td.games_done && td.plies_done,
+               "rz_tree_advance: null trajectory buffer");
+  }
+  if (t->n_trees == 0) return 0;
+  const int words = (t->max_nodes + 31) / 32;
+  const size_t smem = (size_t)RZ_TREE_WARPS * 2 * words * sizeof(uint32_t);
+  RZ_REQUIRE(smem <= 48 * 1024, "rz_tree_advance: max_nodes %d needs %zu B of shared memory", t->max_nodes, smem);
+  rz_advance_kernel<<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, smem, (cudaStream_t)stream>>>(
+      *t, moves, keep_subtree, max_carry, td, traj != nullptr, pi, auto_reset, words);
+  RZ_LAUNCH_CHECK("rz_tree_advance");
+  return 0;
+}

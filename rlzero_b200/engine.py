@@ -1,0 +1,369 @@
+"""Host side of the batched search: structure-of-arrays node pools in HBM + the wave loop.
+
+``SearchForest`` owns G search trees (one per game) as flat torch CUDA tensors and drives
+the C-ABI kernels of ``include/rlzero_b200.h``.  One *wave* = one playout for every tree:
+
+    rz_tree_select  ->  evaluator (net forward / closed form / host callback)
+                    ->  rz_tree_expand_backup
+
+which is exactly ``AlphaZeroMCTS._playout`` (rlzero/mcts/alphazero_mcts.py:42-71) for every
+game at once; ``n_playout`` waves are ``AlphaZeroMCTS.simulate`` (:73-94).  Because each tree
+advances by one playout per wave, the per-tree order of updates is the reference's, and visit
+counts / value sums are bit-identical to it.
+
+PyTorch is used for device memory, streams and CUDA graphs only.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+_LN_CACHE = {}
+
+
+def ln_table(n):
+    """ln_table[k] = math.log(k): CPython's libm log, the function node.py:84 calls.  numpy's
+    vectorised log may differ in the last bit, so the table is built with math.log."""
+    if n not in _LN_CACHE:
+        t = np.zeros(n, dtype=np.float64)
+        for k in range(1, n):
+            t[k] = math.log(k)
+        _LN_CACHE[n] = t
+    return _LN_CACHE[n]
+
+
+class SearchForest(object):
+    """G independent search trees + their root positions, resident in HBM."""
+
+    def __init__(self, n_trees, board_size, n_in_row, n_playout=800, c_puct=5.0,
+                 rule=L.RULE_UCT, max_carry=None, max_nodes=None, store_priors=True,
+                 device='cuda', global_offset=0, ln_table_len=None, with_trajectories=False,
+                 ring_capacity=None):
+        if not torch.cuda.is_available():
+            raise L.NativeLibraryError('rlzero_b200 needs a CUDA device (no CPU fallback)')
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.G = int(n_trees)
+        self.H = int(board_size)
+        self.k = int(n_in_row)
+        if not (1 <= self.H <= L.MAX_BOARD):
+            raise ValueError('board_size must be in [1, %d]' % L.MAX_BOARD)
+        if self.H < self.k:
+            raise ValueError('Board board_size can not less than %d' % self.k)  # gomoku_env.py:35
+        self.A = self.H * self.H
+        self.AS = _round_up(self.A, 32)
+        self.n_playout = int(n_playout)
+        self.c_puct = float(c_puct)
+        self.rule = int(rule)
+        if max_carry is None:
+            max_carry = 64 if rule == L.RULE_UCT else self.n_playout
+        self.max_carry = int(max_carry)
+        self.max_nodes = int(max_nodes) if max_nodes else self.n_playout + self.max_carry
+        if self.max_nodes > 6144:
+            raise ValueError('max_nodes %d > 6144 (re-root bitmap lives in shared memory)' % self.max_nodes)
+        self.max_depth = self.A + 1
+        self.store_priors = bool(store_priors) or rule == L.RULE_PUCT
+        G, AS, H, dev = self.G, self.AS, self.H, self.device
+        i32, f64, f32 = torch.int32, torch.float64, torch.float32
+        n_edges = G * self.max_nodes * AS
+        self.edge_N = torch.empty(n_edges, dtype=i32, device=dev)
+        self.edge_W = torch.empty(n_edges, dtype=f64, device=dev)
+        self.edge_child = torch.empty(n_edges, dtype=i32, device=dev)
+        self.edge_P = torch.empty(n_edges, dtype=f32, device=dev) if self.store_priors else None
+        self.node_parent = torch.empty(G * self.max_nodes, dtype=i32, device=dev)
+        self.node_paction = torch.empty(G * self.max_nodes, dtype=i32, device=dev)
+        self.n_nodes = torch.zeros(G, dtype=i32, device=dev)
+        self.root_N = torch.zeros(G, dtype=i32, device=dev)
+        self.root_W = torch.zeros(G, dtype=f64, device=dev)
+        self.root_rows = torch.zeros(G, 2, H, dtype=i32, device=dev)
+        self.root_meta = torch.zeros(G, L.META_STRIDE, dtype=i32, device=dev)
+        self.path_node = torch.zeros(G, self.max_depth, dtype=i32, device=dev)
+        self.path_action = torch.zeros(G, self.max_depth, dtype=i32, device=dev)
+        self.depth = torch.full((G,), -1, dtype=i32, device=dev)
+        self.leaf_rows = torch.zeros(G, 2, H, dtype=i32, device=dev)
+        self.leaf_meta = torch.zeros(G, L.META_STRIDE, dtype=i32, device=dev)
+        n_ln = int(ln_table_len) if ln_table_len else max(1 << 16, 4 * self.n_playout + 2)
+        self.ln_table = torch.from_numpy(ln_table(n_ln)).to(dev)
+        # evaluator outputs for one wave
+        self.prior = torch.zeros(G, AS, dtype=f32, device=dev)
+        self.value = torch.zeros(G, dtype=f32, device=dev)
+        # root policy outputs
+        self.visits = torch.zeros(G, AS, dtype=i32, device=dev)
+        self.pi = torch.zeros(G, AS, dtype=f32, device=dev)
+        self.move = torch.full((G,), -1, dtype=i32, device=dev)
+
+        self.gdesc = L.GameDesc(self.H, self.k, self.A, self.AS)
+        d = L.TreeDesc()
+        d.game = self.gdesc
+        d.n_trees, d.max_nodes, d.max_depth = G, self.max_nodes, self.max_depth
+        d.rule, d.ln_table_len, d.store_priors = self.rule, n_ln, int(self.store_priors)
+        d.c_puct = self.c_puct
+        d.global_offset = int(global_offset)
+        for name in ('edge_N', 'edge_W', 'edge_child', 'node_parent', 'node_paction', 'n_nodes',
+                     'root_N', 'root_W', 'root_rows', 'root_meta', 'path_node', 'path_action',
+                     'depth', 'leaf_rows', 'leaf_meta', 'ln_table'):
+            setattr(d, name, getattr(self, name).data_ptr())
+        d.edge_P = self.edge_P.data_ptr() if self.edge_P is not None else None
+        self.desc = d
+        self.traj = None
+        self.tdesc = None
+        if with_trajectories:
+            self._alloc_trajectories(ring_capacity)
+        self.reset_games()
+
+    # ------------------------------------------------------------------ memory
+    def _alloc_trajectories(self, ring_capacity):
+        G, H, AS, dev = self.G, self.H, self.AS, self.device
+        P = self.A
+        cap = int(ring_capacity) if ring_capacity else max(4 * P, 2 * G * 16)
+        cap = max(cap, P)
+        i32, f32 = torch.int32, torch.float32
+        self.traj = dict(
+            stage_rows=torch.zeros(G, P, 2, H, dtype=i32, device=dev),
+            stage_info=torch.zeros(G, P, 4, dtype=i32, device=dev),
+            stage_pi=torch.zeros(G, P, AS, dtype=f32, device=dev),
+            ring_rows=torch.zeros(cap, 2, H, dtype=i32, device=dev),
+            ring_info=torch.zeros(cap, 6, dtype=i32, device=dev),
+            ring_pi=torch.zeros(cap, AS, dtype=f32, device=dev),
+            ring_cursor=torch.zeros(1, dtype=torch.int64, device=dev),
+            games_done=torch.zeros(1, dtype=torch.int64, device=dev),
+            plies_done=torch.zeros(1, dtype=torch.int64, device=dev))
+        td = L.TrajDesc()
+        td.max_plies, td.ring_capacity = P, cap
+        for k, v in self.traj.items():
+            setattr(td, k, v.data_ptr())
+        self.tdesc = td
+        self.ring_capacity = cap
+        self._ring_read = 0
+
+    def hbm_bytes(self):
+        tot = 0
+        for v in vars(self).values():
+            if isinstance(v, torch.Tensor):
+                tot += v.numel() * v.element_size()
+        if self.traj:
+            tot += sum(v.numel() * v.element_size() for v in self.traj.values())
+        return tot
+
+    # --------------------------------------------------------------- positions
+    def _s(self):
+        return L.stream_ptr()
+
+    def reset_games(self):
+        """GomokuEnv.reset() for every game + fresh trees (gomoku_env.py:33-47)."""
+        L.check(self.lib.rz_gomoku_reset(C.byref(self.gdesc), L.ptr(self.root_rows),
+                                         L.ptr(self.root_meta), self.G, 0, self._s()), 'rz_gomoku_reset')
+        self.reset_trees()
+
+    def reset_trees(self, mask=None):
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, dtype=torch.uint8, device=self.device).contiguous()
+        L.check(self.lib.rz_tree_reset(C.byref(self.desc), L.ptr(m), self._s()), 'rz_tree_reset')
+
+    def play_moves(self, actions):
+        """env.step for every game (actions[g] < 0 skips); roots only, trees untouched."""
+        a = torch.as_tensor(actions, dtype=torch.int32, device=self.device).contiguous()
+        L.check(self.lib.rz_gomoku_step(C.byref(self.gdesc), L.ptr(self.root_rows), L.ptr(self.root_meta),
+                                        L.ptr(a), None, None, self.G, self._s()), 'rz_gomoku_step')
+
+    def set_positions(self, move_lists):
+        """Start every game from the position reached by its move list (legal, non-terminal)."""
+        self.reset_games()
+        longest = max((len(m) for m in move_lists), default=0)
+        for t in range(longest):
+            self.play_moves([m[t] if t < len(m) else -1 for m in move_lists])
+        self.root_meta[:, L.META_PLY] = 0
+        self.raise_faults()
+
+    # -------------------------------------------------------------------- wave
+    def select(self):
+        L.check(self.lib.rz_tree_select(C.byref(self.desc), self._s()), 'rz_tree_select')
+
+    def expand_backup(self, prior_is_log=False, noise_eps=0.0, noise_alpha=0.3, seed=0,
+                      prior=None, value=None, value64=None):
+        prior = self.prior if prior is None else prior
+        value = self.value if value is None else value
+        L.check(self.lib.rz_tree_expand_backup(C.byref(self.desc), L.ptr(prior), int(prior_is_log),
+                                               L.ptr(value), L.ptr(value64), float(noise_eps),
+                                               float(noise_alpha), int(seed), self._s()),
+                'rz_tree_expand_backup')
+
+    def eval_closed_form(self, eval_id):
+        L.check(self.lib.rz_eval_closed_form(C.byref(self.desc), int(eval_id), L.ptr(self.prior),
+                                             L.ptr(self.value), self._s()), 'rz_eval_closed_form')
+
+    def root_policy(self, temperature=1e-3, u01=None, seed=0, want_move=True):
+        u = None
+        if u01 is not None:
+            u = torch.as_tensor(u01, dtype=torch.float64, device=self.device).contiguous()
+        L.check(self.lib.rz_tree_root_policy(C.byref(self.desc), float(temperature), L.ptr(self.visits),
+                                             L.ptr(self.pi), L.ptr(self.move) if want_move else None,
+                                             L.ptr(u), int(seed), self._s()), 'rz_tree_root_policy')
+
+    def advance(self, moves=None, keep_subtree=True, record=False, auto_reset=False):
+        """env.step(move) on the roots + update_with_move (alphazero_mcts.py:96-103)."""
+        mv = self.move if moves is None else torch.as_tensor(
+            moves, dtype=torch.int32, device=self.device).contiguous()
+        td = C.byref(self.tdesc) if (record and self.tdesc is not None) else None
+        L.check(self.lib.rz_tree_advance(C.byref(self.desc), L.ptr(mv), int(keep_subtree),
+                                         self.max_carry, td, L.ptr(self.pi) if record else None,
+                                         int(auto_reset), self._s()), 'rz_tree_advance')
+
+    # ------------------------------------------------------------------ search
+    def run_waves(self, n_waves, evaluator, noise_eps=0.0, noise_alpha=0.3, seed=0, use_graph=True):
+        """``n_waves`` playouts for every tree.  ``evaluator(forest)`` must fill ``forest.prior``
+        / ``forest.value`` for the leaves of the wave on the current stream."""
+        prior_is_log = bool(getattr(evaluator, 'prior_is_log', False))
+        capturable = bool(getattr(evaluator, 'graph_capturable', False))
+
+        def wave():
+            self.select()
+            evaluator(self)
+            self.expand_backup(prior_is_log, noise_eps, noise_alpha, seed,
+                               value64=getattr(evaluator, 'value64', None))
+
+        if not (use_graph and capturable) or n_waves < 4:
+            for _ in range(n_waves):
+                wave()
+            return
+        key = (id(evaluator), prior_is_log, float(noise_eps), float(noise_alpha), int(seed))
+        graphs = self.__dict__.setdefault('_graphs', {})
+        if key not in graphs:
+            # warm-up outside capture (lazy module loads etc.), then capture one wave
+            wave()
+            n_waves -= 1
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                wave()
+            graphs[key] = g
+            # the capture itself did not run the wave
+        g = graphs[key]
+        for _ in range(n_waves):
+            g.replay()
+
+    def search(self, evaluator, n_playout=None, **kw):
+        self.run_waves(self.n_playout if n_playout is None else n_playout, evaluator, **kw)
+
+    # ---------------------------------------------------------------- readback
+    def faults(self):
+        return self.root_meta[:, L.META_FAULT].cpu().numpy()
+
+    def raise_faults(self):
+        """Turn device fault bits into the reference's exceptions."""
+        f = self.faults()
+        if not f.any():
+            return
+        g = int(np.nonzero(f)[0][0])
+        bits = int(f[g])
+        self.root_meta[:, L.META_FAULT] = 0
+        if bits & L.FAULT_ILLEGAL_MOVE:
+            raise AssertionError('You input illegal action (game %d)' % g)  # gomoku_env.py:51
+        if bits & L.FAULT_NO_CHILDREN:
+            raise ValueError('Node has no children.')  # node.py:39
+        raise RuntimeError('search fault bits 0x%x in game %d' % (bits, g))
+
+    def root_stats(self):
+        """(visits[G,A] int32, W[G,A] float64, has_child[G,A] bool, root_N[G], root_W[G]) on host."""
+        G, A, AS = self.G, self.A, self.AS
+        stride = self.max_nodes * AS
+        idx = (torch.arange(G, device=self.device, dtype=torch.int64) * stride)[:, None] + \
+            torch.arange(AS, device=self.device, dtype=torch.int64)[None, :]
+        n = self.edge_N[idx][:, :A].cpu().numpy()
+        w = self.edge_W[idx][:, :A].cpu().numpy()
+        expanded = (self.n_nodes.cpu().numpy() > 0)[:, None]
+        has = (n >= 0) & expanded
+        visits = np.where(has, n, 0).astype(np.int32)
+        wv = np.where(has & (n > 0), w, 0.0)
+        return visits, wv, has, self.root_N.cpu().numpy(), self.root_W.cpu().numpy()
+
+    def dump_tree(self, g):
+        """Host copy of tree g as nested dicts (for the TreeNode view / debugging)."""
+        nn = int(self.n_nodes[g])
+        AS, A = self.AS, self.A
+        base = g * self.max_nodes * AS
+        sl = slice(base, base + max(nn, 1) * AS)
+        N = self.edge_N[sl].cpu().numpy().reshape(-1, AS)[:, :A]
+        W = self.edge_W[sl].cpu().numpy().reshape(-1, AS)[:, :A]
+        Cc = self.edge_child[sl].cpu().numpy().reshape(-1, AS)[:, :A]
+        P = (self.edge_P[sl].cpu().numpy().reshape(-1, AS)[:, :A] if self.edge_P is not None
+             else np.ones_like(W, dtype=np.float32))
+        return dict(n_nodes=nn, N=N, W=W, child=Cc, P=P, root_N=int(self.root_N[g]),
+                    root_W=float(self.root_W[g]))
+
+    def boards(self):
+        """Root positions as (rows[G,2,H] uint32, meta[G,8] int32) numpy arrays."""
+        return (self.root_rows.cpu().numpy().view(np.uint32), self.root_meta.cpu().numpy())
+
+    def leaf_boards(self):
+        return (self.leaf_rows.cpu().numpy().view(np.uint32), self.leaf_meta.cpu().numpy(),
+                self.depth.cpu().numpy())
+
+    # ------------------------------------------------------------ trajectories
+    def drain_trajectories(self):
+        """Finished-episode plies written since the last drain: dict of host arrays
+        rows[n,2,H] uint32, info[n,6] (mover,last_move,z,slot,episode,ply), pi[n,A] float32."""
+        if self.traj is None:
+            raise RuntimeError('forest was built without trajectories')
+        cur = int(self.traj['ring_cursor'].item())
+        lo = max(self._ring_read, cur - self.ring_capacity)
+        dropped = lo - self._ring_read  # overwritten before they were drained
+        idx = (np.arange(lo, cur) % self.ring_capacity).astype(np.int64)
+        self._ring_read = cur
+        ti = torch.from_numpy(idx).to(self.device)
+        return dict(rows=self.traj['ring_rows'][ti].cpu().numpy().view(np.uint32),
+                    info=self.traj['ring_info'][ti].cpu().numpy(),
+                    pi=self.traj['ring_pi'][ti][:, :self.A].cpu().numpy(),
+                    dropped=int(dropped))
+
+
+class ClosedFormEvaluator(object):
+    """Device-side closed-form evaluator (parity tests, tree-only benchmarks)."""
+    graph_capturable = True
+    prior_is_log = False
+
+    def __init__(self, eval_id):
+        self.eval_id = int(eval_id)
+
+    def __call__(self, forest):
+        forest.eval_closed_form(self.eval_id)
+
+
+class HostCallbackEvaluator(object):
+    """Slow path honouring a user-supplied ``policy_value_fn(env)`` (alphazero_mcts.py:27-31):
+    leaf positions are copied to the host, rebuilt as env objects, evaluated one by one, and
+    the priors/values copied back.  Not graph-capturable; used by the single-game API shim
+    and by record/replay parity tests."""
+    graph_capturable = False
+    prior_is_log = False
+
+    def __init__(self, policy_value_fn, env_factory):
+        self.fn = policy_value_fn
+        self.env_factory = env_factory
+        self.value64 = None
+
+    def __call__(self, forest):
+        rows, meta, depth = forest.leaf_boards()
+        prior = np.zeros((forest.G, forest.AS), dtype=np.float32)
+        value = np.zeros(forest.G, dtype=np.float64)
+        if self.value64 is None:
+            self.value64 = torch.zeros(forest.G, dtype=torch.float64, device=forest.device)
+        for g in range(forest.G):
+            if depth[g] < 0:
+                continue
+            env = self.env_factory(rows[g], meta[g])
+            act_probs, v = self.fn(env)
+            for a, p in act_probs:
+                prior[g, int(a)] = p
+            value[g] = v
+        forest.prior.copy_(torch.from_numpy(prior))
+        self.value64.copy_(torch.from_numpy(value))  # python floats are fp64: keep them exact

@@ -1,0 +1,78 @@
+"""CPU tests: the C-ABI library builds, loads and exports every symbol the header declares
+(no compute calls -- there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from rlzero_b200 import build
+    build.build()
+    from rlzero_b200 import _lib
+    return _lib.load()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'rlzero_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(rz_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_header_symbols_exported(lib):
+    from rlzero_b200 import _lib
+    syms = header_symbols()
+    assert len(syms) >= 16
+    for s in syms:
+        assert hasattr(lib, s), 'library does not export ' + s
+        assert s in _lib.SIGNATURES, 'binding does not type ' + s
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_abi_version_and_struct_sizes(lib):
+    from rlzero_b200 import _lib
+    assert lib.rz_abi_version() == _lib.ABI_VERSION
+    assert lib.rz_sizeof_tree_desc() == C.sizeof(_lib.TreeDesc)
+    assert lib.rz_sizeof_traj_desc() == C.sizeof(_lib.TrajDesc)
+
+
+def test_argument_errors_are_reported(lib):
+    """Argument validation happens on the host before any launch, so it is testable here."""
+    from rlzero_b200 import _lib
+    g = _lib.GameDesc(40, 5, 1600, 1600)
+    rc = lib.rz_gomoku_reset(C.byref(g), None, None, 1, 0, None)
+    assert rc != 0 and b'board_size' in lib.rz_last_error()
+    g = _lib.GameDesc(15, 5, 225, 230)
+    rc = lib.rz_gomoku_step(C.byref(g), None, None, None, None, None, 1, None)
+    assert rc != 0 and b'action_stride' in lib.rz_last_error()
+    t = _lib.TreeDesc()
+    t.game = _lib.GameDesc(15, 5, 225, 256)
+    t.n_trees, t.max_nodes, t.max_depth, t.rule = 1, 8, 226, 7
+    rc = lib.rz_tree_select(C.byref(t), None)
+    assert rc != 0 and b'rule' in lib.rz_last_error()
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never reach into oracle/ (test infrastructure)."""
+    for base, _, files in os.walk(os.path.join(ROOT, 'rlzero_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(base, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from rlzero_b200 import _lib
+    from rlzero_b200.engine import SearchForest
+    from rlzero_b200.games.gomoku import GomokuEnv
+    with pytest.raises(_lib.NativeLibraryError):
+        SearchForest(1, 3, 3, n_playout=10)
+    with pytest.raises(_lib.NativeLibraryError):
+        GomokuEnv(3, 3).reset()
