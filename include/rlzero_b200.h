@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define RZ_ABI_VERSION 3
+#define RZ_ABI_VERSION 4
 #define RZ_MAX_BOARD 19          /* rows live one per lane; A = H*W <= 361 */
 #define RZ_META_STRIDE 8
 
@@ -162,6 +162,9 @@ int rz_gomoku_winner(const rz_game_desc* g, const uint32_t* rows, const int32_t*
 /* current_state (gomoku_env.py:95-114) as float32 [n][4][H][W]. */
 int rz_gomoku_encode_f32(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
                          float* planes, int n_games, void* stream);
+/* the same planes channels-last, float32 [n][HW][4] (input of the fp32 trunk). */
+int rz_gomoku_encode_nhwc_f32(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
+                              float* planes, int n_games, void* stream);
 /* same planes as bf16 in the tensor-core trunk's layout [n][256][64]: position
    p = y*16+x (x,y < 15 real, else zero), channels 0..3 = planes, 4..63 zero. */
 int rz_gomoku_encode_tc(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
@@ -201,6 +204,41 @@ int rz_tree_advance(const rz_tree_desc* t, const int32_t* moves, int keep_subtre
 /* ---- closed-form evaluators for parity tests (oracle/evaluators.py) ------- */
 int rz_eval_closed_form(const rz_tree_desc* t, int eval_id, float* prior, float* value,
                         void* stream);
+
+/* ---- policy-value network forward (rlzero/games/gomoku/policy_value_net.py:34-52) -------- */
+/* heads weights, all float32 device pointers.  FC weights are stored TRANSPOSED ([in][out]);
+   the flatten order of the FC inputs is c*HW + pos (x.view(-1, C*H*W) on NCHW, :42,48). */
+typedef struct rz_heads_desc {
+  int32_t board_size;
+  int32_t action_stride;         /* AS: row stride of wp / logp */
+  const float* w1x1;             /* [6][128]  act_conv1 (4 filters) then val_conv1 (2 filters) */
+  const float* b1x1;             /* [6] */
+  const float* wp;               /* [4*HW][AS] act_fc1.weight^T, zero padded */
+  const float* bp;               /* [AS] */
+  const float* wv1;              /* [2*HW][64] val_fc1.weight^T */
+  const float* bv1;              /* [64] */
+  const float* wv2;              /* [64]       val_fc2.weight */
+  const float* bv2;              /* [1] */
+} rz_heads_desc;
+
+/* 3x3 convolution (padding 1) + bias (+ residual) (+ ReLU) on the tensor cores (tcgen05/TMEM/TMA):
+   act_in bf16 [n][256][c_in] tile layout (see rz_gomoku_encode_tc), c_in in {64,128};
+   weight bf16 [9][128][c_in] (tap = kh*3+kw, then out channel, then in channel); bias f32 [128];
+   residual/act_out bf16 [n][256][128] (residual may alias act_out, may be NULL).
+   n_ctas <= 0 picks one persistent CTA per SM.  nn.Conv2d + folded BatchNorm + ReLU of the trunk. */
+int rz_net_conv3x3_tc(const void* act_in, const void* weight, const float* bias, const void* residual,
+                      void* act_out, int n_boards, int board_size, int c_in, int relu, int n_ctas,
+                      void* stream);
+/* the same operator in float32 on CUDA cores for the reference's stock network at any board size:
+   in [n][HW][c_in], weight [9][c_in][c_out], out [n][HW][c_out] (channels last). */
+int rz_net_conv3x3_f32(const float* in, const float* weight, const float* bias, const float* residual,
+                       float* out, int n_boards, int board_size, int c_in, int c_out, int relu,
+                       void* stream);
+/* both heads from the 128-channel trunk output: logp f32 [n][AS] = log_softmax(policy logits)
+   (0 in the padding), value f32 [n] = tanh(...).  act is bf16 tile layout (act_is_tile_bf16 != 0)
+   or f32 [n][HW][128]. */
+int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_tile_bf16, float* logp,
+                 float* value, int n_boards, void* stream);
 
 #ifdef __cplusplus
 }

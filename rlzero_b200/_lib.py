@@ -11,7 +11,7 @@ import torch  # noqa: F401  -- loads libcudart.so.12 into the process before our
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'librlzero_b200.so')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 META_STRIDE = 8
 (META_PLAYER, META_LAST_MOVE, META_STONES, META_STATUS, META_WINNER, META_PLY, META_FAULT,
  META_EPISODE) = range(8)
@@ -50,6 +50,12 @@ class TrajDesc(C.Structure):
                 ('ring_cursor', _vp), ('games_done', _vp), ('plies_done', _vp)]
 
 
+class HeadsDesc(C.Structure):
+    _fields_ = [('board_size', C.c_int32), ('action_stride', C.c_int32),
+                ('w1x1', _vp), ('b1x1', _vp), ('wp', _vp), ('bp', _vp),
+                ('wv1', _vp), ('bv1', _vp), ('wv2', _vp), ('bv2', _vp)]
+
+
 # name -> (restype, argtypes); every symbol include/rlzero_b200.h declares
 _GD, _TD, _TJ = C.POINTER(GameDesc), C.POINTER(TreeDesc), C.POINTER(TrajDesc)
 SIGNATURES = {
@@ -62,6 +68,7 @@ SIGNATURES = {
     'rz_gomoku_legal_mask': (C.c_int, [_GD, _vp, _vp, C.c_int, _vp]),
     'rz_gomoku_winner': (C.c_int, [_GD, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     'rz_gomoku_encode_f32': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_gomoku_encode_nhwc_f32': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, _vp]),
     'rz_gomoku_encode_tc': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, _vp]),
     'rz_tree_reset': (C.c_int, [_TD, _vp, _vp]),
     'rz_tree_select': (C.c_int, [_TD, _vp]),
@@ -70,6 +77,11 @@ SIGNATURES = {
     'rz_tree_root_policy': (C.c_int, [_TD, C.c_double, _vp, _vp, _vp, _vp, C.c_ulonglong, _vp]),
     'rz_tree_advance': (C.c_int, [_TD, _vp, C.c_int, C.c_int, _TJ, _vp, C.c_int, _vp]),
     'rz_eval_closed_form': (C.c_int, [_TD, C.c_int, _vp, _vp, _vp]),
+    'rz_net_conv3x3_tc': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, _vp]),
+    'rz_net_conv3x3_f32': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, _vp]),
+    'rz_net_heads': (C.c_int, [C.POINTER(HeadsDesc), _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
 }
 
 _lib = None

@@ -127,6 +127,27 @@ rz_gomoku_encode_f32_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t
   }
 }
 
+// channels-last float32 [n][HW][4] for the fp32 trunk
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_gomoku_encode_nhwc_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t* meta,
+                             float* planes, int n) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const int lane = rz_lane(), H = gd.board_size, A = gd.n_actions;
+  rz_wboard b;
+  rz_board_load(b, rows + (size_t)g * 2 * H, meta + (size_t)g * RZ_META_STRIDE, H);
+  const uint32_t mine = b.p[b.player], theirs = b.p[b.player ^ 1];
+  const int total = 4 * A;
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    const int ic = i < total ? i : 0;
+    const int pos = ic >> 2, plane = ic & 3;
+    const int r = pos / H, c = pos - r * H;
+    const float v = rz_plane_value(b, mine, theirs, plane, r, c, H);
+    if (i < total) planes[(size_t)g * total + i] = v;
+  }
+}
+
 // bf16 [n][256 positions][64 channels]: position p = y*16 + x, channels 0..3 = the 4 planes.
 // One 16-byte store per (position, 8-channel group); only group 0 carries data.
 __global__ void __launch_bounds__(RZ_GAME_THREADS)
@@ -263,6 +284,17 @@ extern "C" int rz_gomoku_encode_f32(const rz_game_desc* g, const uint32_t* rows,
   rz_gomoku_encode_f32_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
                                 (cudaStream_t)stream>>>(*g, rows, meta, planes, n_games);
   RZ_LAUNCH_CHECK("rz_gomoku_encode_f32");
+  return 0;
+}
+
+extern "C" int rz_gomoku_encode_nhwc_f32(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
+                                         float* planes, int n_games, void* stream) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(rows && meta && planes && n_games >= 0, "rz_gomoku_encode_nhwc_f32: bad arguments");
+  if (n_games == 0) return 0;
+  rz_gomoku_encode_nhwc_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+                                 (cudaStream_t)stream>>>(*g, rows, meta, planes, n_games);
+  RZ_LAUNCH_CHECK("rz_gomoku_encode_nhwc_f32");
   return 0;
 }
 

@@ -1,0 +1,232 @@
+// rlzero_b200 -- policy / value heads and the generic fp32 3x3 convolution.
+//
+// Reference: rlzero/games/gomoku/policy_value_net.py
+//   trunk  conv1..3 (3x3, pad 1) + ReLU                         :14-16, 36-38
+//   policy act_conv1 (1x1 -> 4) + ReLU, act_fc1 (4HW -> HW), log_softmax   :19-21, 41-44
+//   value  val_conv1 (1x1 -> 2) + ReLU, val_fc1 (2HW -> 64) + ReLU, val_fc2 (64 -> 1), tanh  :23-25, 47-51
+// The flatten order of x.view(-1, C*H*W) on an NCHW tensor is c*HW + pos; the fully connected
+// weights are stored transposed ([in][out]) so that threads over `out` read them coalesced.
+//
+// The fp32 convolution is the plain CUDA-core path used for the reference's stock network
+// (3 layers, <= 64 input channels) at any board size; the benchmark trunk runs on the tensor
+// cores (rz_net_tc.cu).  The heads kernel serves both (template on the activation layout).
+#include <cuda_bf16.h>
+
+#include "rz_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// fp32 conv3x3, NHWC: in [B][HW][Cin], w [9][Cin][Cout], out [B][HW][Cout]
+// one block per board; the input board sits in shared memory.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rz_conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                      const float* __restrict__ bias, const float* __restrict__ residual,
+                      float* __restrict__ out, int H, int Cin, int Cout, int relu) {
+  extern __shared__ float s_in[];  // [HW][Cin]
+  const int b = blockIdx.x, HW = H * H;
+  const float* ib = in + (size_t)b * HW * Cin;
+  for (int i = threadIdx.x; i < HW * Cin; i += blockDim.x) s_in[i] = ib[i];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < HW * Cout; idx += blockDim.x) {
+    const int co = idx % Cout, pos = idx / Cout;
+    const int y = pos / H, x = pos - y * H;
+    float acc = bias[co];
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= H) continue;
+      const float* src = s_in + (yy * H + xx) * Cin;
+      const float* wt = w + (size_t)tap * Cin * Cout + co;
+      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(src[ci], wt[(size_t)ci * Cout], acc);
+    }
+    const size_t o = ((size_t)b * HW + pos) * Cout + co;
+    if (residual) acc += residual[o];
+    if (relu) acc = fmaxf(acc, 0.0f);
+    out[o] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// heads: NB boards per block
+// ---------------------------------------------------------------------------
+constexpr int HEAD_NB = 8;
+constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_C = 128;
+
+struct HeadsParams {
+  const void* act;        // trunk output: bf16 [B][256][128] (tile layout) or fp32 [B][HW][128]
+  const float* w1x1;      // [6][128]: 4 policy + 2 value 1x1 filters
+  const float* b1x1;      // [6]
+  const float* wp;        // [4*HW][AS] policy FC, transposed + padded
+  const float* bp;        // [AS]
+  const float* wv1;       // [2*HW][64] value FC1, transposed
+  const float* bv1;       // [64]
+  const float* wv2;       // [64]
+  const float* bv2;       // [1]
+  float* logp;            // [B][AS]
+  float* value;           // [B]
+  int n_boards, H, A, AS;
+};
+
+// 6 dot products of one position's 128 channels with the 1x1 filters in shared memory
+template <bool kTile>
+__device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos, int H,
+                                                 const float* __restrict__ s_w, float (&acc)[6]) {
+  if constexpr (kTile) {
+    const int y = pos / H, x = pos - y * H;
+    const uint4* src = reinterpret_cast<const uint4*>(
+        reinterpret_cast<const __nv_bfloat16*>(act) + ((size_t)b * 256 + y * 16 + x) * HEAD_C);
+#pragma unroll 4
+    for (int j = 0; j < HEAD_C / 8; ++j) {
+      const uint4 q = src[j];
+      const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ws[e]);
+        const float v0 = __low2float(h2), v1 = __high2float(h2);
+        const int c = j * 8 + e * 2;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) acc[f] = fmaf(v1, s_w[f * HEAD_C + c + 1], fmaf(v0, s_w[f * HEAD_C + c], acc[f]));
+      }
+    }
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(
+        reinterpret_cast<const float*>(act) + ((size_t)b * H * H + pos) * HEAD_C);
+#pragma unroll 4
+    for (int j = 0; j < HEAD_C / 4; ++j) {
+      const float4 q = src[j];
+      const float vs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int f = 0; f < 6; ++f) acc[f] = fmaf(vs[e], s_w[f * HEAD_C + j * 4 + e], acc[f]);
+      }
+    }
+  }
+}
+
+template <bool kTile>
+__global__ void __launch_bounds__(HEAD_THREADS) rz_heads_kernel(const HeadsParams p) {
+  extern __shared__ float sm[];
+  const int HW = p.A;
+  float* s_w = sm;                          // [6][128]
+  float* s_fp = s_w + 6 * HEAD_C;           // [NB][4*HW]  policy features
+  float* s_fv = s_fp + HEAD_NB * 4 * HW;    // [NB][2*HW]  value features
+  float* s_lg = s_fv + HEAD_NB * 2 * HW;    // [NB][AS]    logits
+  float* s_h = s_lg + HEAD_NB * p.AS;       // [NB][64]    value hidden
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b0 = blockIdx.x * HEAD_NB;
+  const int nb = min(HEAD_NB, p.n_boards - b0);
+  for (int i = tid; i < 6 * HEAD_C; i += HEAD_THREADS) s_w[i] = p.w1x1[i];
+  __syncthreads();
+  // phase 1: 1x1 convolutions + ReLU  (policy_value_net.py:41, 47)
+  for (int i = tid; i < nb * HW; i += HEAD_THREADS) {
+    const int bi = i / HW, pos = i - bi * HW;
+    float acc[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) acc[f] = p.b1x1[f];
+    conv1x1_position<kTile>(p.act, b0 + bi, pos, p.H, s_w, acc);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) s_fp[bi * 4 * HW + f * HW + pos] = fmaxf(acc[f], 0.0f);
+#pragma unroll
+    for (int f = 0; f < 2; ++f) s_fv[bi * 2 * HW + f * HW + pos] = fmaxf(acc[4 + f], 0.0f);
+  }
+  __syncthreads();
+  // phase 2: policy FC (:43)
+  for (int j = tid; j < p.AS; j += HEAD_THREADS) {
+    float acc[HEAD_NB];
+    const float bj = j < p.A ? p.bp[j] : 0.0f;
+#pragma unroll
+    for (int bi = 0; bi < HEAD_NB; ++bi) acc[bi] = bj;
+    if (j < p.A) {
+      const float* wcol = p.wp + j;
+      for (int k = 0; k < 4 * HW; ++k) {
+        const float wkj = wcol[(size_t)k * p.AS];
+#pragma unroll
+        for (int bi = 0; bi < HEAD_NB; ++bi) acc[bi] = fmaf(s_fp[bi * 4 * HW + k], wkj, acc[bi]);
+      }
+    }
+#pragma unroll
+    for (int bi = 0; bi < HEAD_NB; ++bi) s_lg[bi * p.AS + j] = acc[bi];
+  }
+  // phase 3a: value FC1 + ReLU (:49)
+  for (int i = tid; i < HEAD_NB * 64; i += HEAD_THREADS) {
+    const int bi = i >> 6, o = i & 63;
+    float acc = p.bv1[o];
+    if (bi < nb)
+      for (int k = 0; k < 2 * HW; ++k) acc = fmaf(s_fv[bi * 2 * HW + k], p.wv1[k * 64 + o], acc);
+    s_h[i] = fmaxf(acc, 0.0f);
+  }
+  __syncthreads();
+  // phase 3b: log_softmax (:44) and value FC2 + tanh (:50-51): one warp per board
+  for (int bi = warp; bi < nb; bi += HEAD_THREADS / 32) {
+    float mx = -3.0e38f;
+    for (int j = lane; j < p.A; j += 32) mx = fmaxf(mx, s_lg[bi * p.AS + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(RZ_FULL, mx, o));
+    float sum = 0.0f;
+    for (int j = lane; j < p.A; j += 32) sum += expf(s_lg[bi * p.AS + j] - mx);
+    sum = rz_warp_sum_f32(sum);
+    const float lse = mx + logf(sum);
+    float* lp = p.logp + (size_t)(b0 + bi) * p.AS;
+    for (int j = lane; j < p.AS; j += 32) lp[j] = j < p.A ? s_lg[bi * p.AS + j] - lse : 0.0f;
+    float hv = s_h[bi * 64 + lane] * p.wv2[lane] + s_h[bi * 64 + 32 + lane] * p.wv2[32 + lane];
+    hv = rz_warp_sum_f32(hv);
+    if (lane == 0) p.value[b0 + bi] = tanhf(hv + p.bv2[0]);
+  }
+}
+
+size_t heads_smem(int A, int AS) {
+  return sizeof(float) * (6 * HEAD_C + (size_t)HEAD_NB * 4 * A + (size_t)HEAD_NB * 2 * A +
+                          (size_t)HEAD_NB * AS + HEAD_NB * 64);
+}
+
+}  // namespace
+
+extern "C" int rz_net_conv3x3_f32(const float* in, const float* weight, const float* bias,
+                                  const float* residual, float* out, int n_boards, int board_size,
+                                  int c_in, int c_out, int relu, void* stream) {
+  RZ_REQUIRE(in && weight && bias && out, "rz_net_conv3x3_f32: null argument");
+  RZ_REQUIRE(board_size >= 1 && board_size <= RZ_MAX_BOARD, "rz_net_conv3x3_f32: board_size %d", board_size);
+  RZ_REQUIRE(c_in >= 1 && c_out >= 1 && n_boards >= 0, "rz_net_conv3x3_f32: bad sizes");
+  RZ_REQUIRE(in != out, "rz_net_conv3x3_f32: in-place convolution is not supported");
+  const size_t smem = sizeof(float) * (size_t)board_size * board_size * c_in;
+  RZ_REQUIRE(smem <= 200 * 1024, "rz_net_conv3x3_f32: input board needs %zu B of shared memory", smem);
+  if (n_boards == 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(rz_conv3x3_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_f32: smem attribute: %s", cudaGetErrorString(e)); return -2; }
+  rz_conv3x3_f32_kernel<<<n_boards, 256, smem, (cudaStream_t)stream>>>(in, weight, bias, residual, out,
+                                                                      board_size, c_in, c_out, relu);
+  RZ_LAUNCH_CHECK("rz_net_conv3x3_f32");
+  return 0;
+}
+
+extern "C" int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_tile_bf16, float* logp,
+                            float* value, int n_boards, void* stream) {
+  RZ_REQUIRE(h && act && logp && value, "rz_net_heads: null argument");
+  RZ_REQUIRE(h->w1x1 && h->b1x1 && h->wp && h->bp && h->wv1 && h->bv1 && h->wv2 && h->bv2,
+             "rz_net_heads: null weight pointer");
+  RZ_REQUIRE(h->board_size >= 1 && h->board_size <= RZ_MAX_BOARD, "rz_net_heads: board_size %d", h->board_size);
+  RZ_REQUIRE(!act_is_tile_bf16 || h->board_size <= 15, "rz_net_heads: tile layout holds boards up to 15x15");
+  const int A = h->board_size * h->board_size;
+  RZ_REQUIRE(h->action_stride >= A && (h->action_stride & 31) == 0, "rz_net_heads: action_stride %d", h->action_stride);
+  if (n_boards <= 0) return 0;
+  HeadsParams p;
+  p.act = act; p.w1x1 = h->w1x1; p.b1x1 = h->b1x1; p.wp = h->wp; p.bp = h->bp; p.wv1 = h->wv1;
+  p.bv1 = h->bv1; p.wv2 = h->wv2; p.bv2 = h->bv2; p.logp = logp; p.value = value;
+  p.n_boards = n_boards; p.H = h->board_size; p.A = A; p.AS = h->action_stride;
+  const size_t smem = heads_smem(A, p.AS);
+  const int grid = (n_boards + HEAD_NB - 1) / HEAD_NB;
+  cudaError_t e;
+  if (act_is_tile_bf16) {
+    e = cudaFuncSetAttribute(rz_heads_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) rz_heads_kernel<true><<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(rz_heads_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) rz_heads_kernel<false><<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>(p);
+  }
+  if (e != cudaSuccess) { rz_set_error("rz_net_heads: smem attribute: %s", cudaGetErrorString(e)); return -2; }
+  RZ_LAUNCH_CHECK("rz_net_heads");
+  return 0;
+}

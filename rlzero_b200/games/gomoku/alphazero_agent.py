@@ -1,0 +1,97 @@
+"""``AlphaZeroAgent`` with the reference's API (rlzero/games/gomoku/alphazero_agent.py:12-125).
+
+Inference (``policy_value_fn``, ``policy_value``, ``predict``) runs on the hand-written CUDA
+forward (``NativeForward``); ``policy_value_fn`` additionally carries a ``device_evaluator`` so
+that ``AlphaZeroMCTS`` evaluates whole waves of leaves on the device without the per-leaf
+host round trip the reference makes (alphazero_agent.py:41-45).  ``learn`` is the reference's
+training step in plain PyTorch (the training side is outside this round's hot path); the packed
+inference weights are refreshed after every step.
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+import torch.optim as optim
+
+from .policy_value_net import NativeForward, PolicyValueNet
+
+
+class _PolicyValueFn(object):
+    """Callable ``policy_value_fn(game_env) -> (zip(legal, probs), value)`` (:31-46)."""
+
+    def __init__(self, agent):
+        self._agent = agent
+
+    @property
+    def device_evaluator(self):
+        return self._agent.native
+
+    def __call__(self, game_env):
+        agent = self._agent
+        legal_positions = game_env.leagel_actions()
+        state = np.ascontiguousarray(game_env.current_state().reshape(
+            -1, 4, agent.board_size, agent.board_size))
+        logp, value = agent.native.forward_planes(state)
+        act_probs = np.exp(logp[0].cpu().numpy())
+        return zip(legal_positions, act_probs[legal_positions]), float(value[0].item())
+
+
+class AlphaZeroAgent(object):
+
+    def __init__(self, board_size, learning_rate=0.001, weight_decay=1e-4, device='cuda',
+                 net=None, mode=None):
+        self.board_size = board_size
+        self.policy_value_net = net if net is not None else PolicyValueNet(board_size)
+        self.policy_value_net.to(device)
+        self.optimizer = optim.Adam(self.policy_value_net.parameters(), lr=learning_rate,
+                                    weight_decay=weight_decay)
+        self.device = device
+        self.native = NativeForward(self.policy_value_net, mode=mode, device=device)
+        self.policy_value_fn = _PolicyValueFn(self)
+
+    def policy_value(self, state_batch):
+        """a batch of states -> (action probabilities [B,HW], state values [B,1]) (:48-57)."""
+        logp, value = self.native.forward_planes(np.array(state_batch))
+        return np.exp(logp.cpu().numpy()), value.cpu().numpy().reshape(-1, 1)
+
+    def predict(self, state_batch):
+        """(:88-97)"""
+        return self.policy_value(state_batch)
+
+    def learn(self, state_batch, mcts_probs, target_vs):
+        """perform a training step: loss = (z - v)^2 - pi^T log p (+ L2 in the optimizer) (:59-86)."""
+        net = self.policy_value_net
+        net.train()
+        dev = self.device
+        state_batch = torch.FloatTensor(np.array(state_batch)).to(dev)
+        mcts_probs = torch.FloatTensor(np.array(mcts_probs)).to(dev)
+        target_batch = torch.FloatTensor(np.array(target_vs)).to(dev)
+        log_act_probs, value = net(state_batch)
+        value_loss = F.mse_loss(value.view(-1), target_batch)
+        policy_loss = -torch.mean(torch.sum(mcts_probs * log_act_probs, dim=1))
+        loss = value_loss + policy_loss
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        entropy = -torch.mean(torch.sum(torch.exp(log_act_probs) * log_act_probs, dim=1))
+        net.eval()
+        self.native.refresh_weights()
+        return loss.item(), entropy.item()
+
+    def save_model(self, save_dir, model_name='model.th', opt_name='optimizer.th'):
+        """(:99-111) same files and state_dict keys as the reference."""
+        if not os.path.exists(save_dir):
+            os.mkdir(save_dir)
+        torch.save(self.policy_value_net.state_dict(), os.path.join(save_dir, model_name))
+        torch.save(self.optimizer.state_dict(), os.path.join(save_dir, opt_name))
+        print('save model successfully!')
+
+    def restore(self, save_dir, model_name='model.th', opt_name='optimizer.th'):
+        """(:113-125)"""
+        if not os.path.exists(save_dir):
+            os.mkdir(save_dir)
+        self.policy_value_net.load_state_dict(torch.load(os.path.join(save_dir, model_name)))
+        self.optimizer.load_state_dict(torch.load(os.path.join(save_dir, opt_name)))
+        self.native.refresh_weights()
+        print('restore model successfully!')

@@ -1,0 +1,290 @@
+"""Policy-value networks: parameter containers (torch modules, state_dict compatible with the
+reference) and ``NativeForward``, the CUDA inference path that the search uses.
+
+* ``PolicyValueNet``       = rlzero/games/gomoku/policy_value_net.py:6-52, same parameter names
+                             and shapes, so reference checkpoints load unchanged
+                             (alphazero_agent.py:99-125).
+* ``ResNetPolicyValueNet`` = the benchmark trunk SURVEY.md section 7 defines (the reference has no
+                             ResNet): stem conv3x3(4->C)+ReLU, N blocks of
+                             2x[conv3x3(C->C)+BN] + skip + ReLU, reference heads unchanged.
+
+``forward`` of the modules is plain PyTorch (training side and fp32 checker).  Inference for the
+search never goes through it: ``NativeForward`` packs the weights (BatchNorm folded) into the
+layouts of include/rlzero_b200.h and runs the hand-written kernels -- tcgen05 tensor-core
+convolutions in bf16 for 128-channel trunks on boards up to 15x15, the fp32 CUDA-core path for
+the stock network / other shapes.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import _lib as L
+
+
+class PolicyValueNet(nn.Module):
+    """policy-value network module (reference architecture and parameter names)."""
+
+    def __init__(self, board_size):
+        super().__init__()
+        self.board_size = board_size
+        hw = board_size * board_size
+        self.conv1 = nn.Conv2d(4, 32, kernel_size=3, padding=1)
+        self.conv2 = nn.Conv2d(32, 64, kernel_size=3, padding=1)
+        self.conv3 = nn.Conv2d(64, 128, kernel_size=3, padding=1)
+        self.act_conv1 = nn.Conv2d(128, 4, kernel_size=1)
+        self.act_fc1 = nn.Linear(4 * hw, hw)
+        self.val_conv1 = nn.Conv2d(128, 2, kernel_size=1)
+        self.val_fc1 = nn.Linear(2 * hw, 64)
+        self.val_fc2 = nn.Linear(64, 1)
+
+    def trunk(self, obs):
+        x = F.relu(self.conv1(obs))
+        x = F.relu(self.conv2(x))
+        return F.relu(self.conv3(x))
+
+    def heads(self, x):
+        hw = self.board_size * self.board_size
+        a = F.relu(self.act_conv1(x)).reshape(-1, 4 * hw)
+        logp = F.log_softmax(self.act_fc1(a), dim=1)
+        v = F.relu(self.val_conv1(x)).reshape(-1, 2 * hw)
+        v = torch.tanh(self.val_fc2(F.relu(self.val_fc1(v))))
+        return logp, v
+
+    def forward(self, obs):
+        return self.heads(self.trunk(obs))
+
+    def trunk_layers(self):
+        """[(conv, bn_or_None, residual_from_layer_index_or_None, relu)] in execution order."""
+        return [(self.conv1, None, None, True), (self.conv2, None, None, True),
+                (self.conv3, None, None, True)]
+
+
+class _ResBlock(nn.Module):
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Conv2d(c, c, 3, padding=1)
+        self.bn1 = nn.BatchNorm2d(c)
+        self.conv2 = nn.Conv2d(c, c, 3, padding=1)
+        self.bn2 = nn.BatchNorm2d(c)
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        return F.relu(self.bn2(self.conv2(y)) + x)
+
+
+class ResNetPolicyValueNet(PolicyValueNet):
+    """ResNet-N trunk (C channels) with the reference's heads."""
+
+    def __init__(self, board_size, n_blocks=10, channels=128):
+        nn.Module.__init__(self)
+        if channels != 128:
+            raise ValueError('the reference heads take 128 trunk channels (policy_value_net.py:19,23)')
+        self.board_size = board_size
+        self.n_blocks = n_blocks
+        hw = board_size * board_size
+        self.stem = nn.Conv2d(4, channels, 3, padding=1)
+        self.blocks = nn.ModuleList([_ResBlock(channels) for _ in range(n_blocks)])
+        self.act_conv1 = nn.Conv2d(channels, 4, kernel_size=1)
+        self.act_fc1 = nn.Linear(4 * hw, hw)
+        self.val_conv1 = nn.Conv2d(channels, 2, kernel_size=1)
+        self.val_fc1 = nn.Linear(2 * hw, 64)
+        self.val_fc2 = nn.Linear(64, 1)
+
+    def trunk(self, obs):
+        x = F.relu(self.stem(obs))
+        for blk in self.blocks:
+            x = blk(x)
+        return x
+
+    def trunk_layers(self):
+        layers = [(self.stem, None, None, True)]
+        for blk in self.blocks:
+            skip = len(layers) - 1           # output of the previous layer
+            layers.append((blk.conv1, blk.bn1, None, True))
+            layers.append((blk.conv2, blk.bn2, skip, True))
+        return layers
+
+    def flops_per_eval(self):
+        hw = self.board_size ** 2
+        c = 128
+        trunk = 2 * hw * (4 * c * 9) + self.n_blocks * 2 * 2 * hw * c * c * 9
+        heads = 2 * hw * c * 6 + 2 * (4 * hw) * hw + 2 * (2 * hw) * 64 + 2 * 64
+        return trunk + heads
+
+
+def _fold_bn(conv, bn):
+    """Conv weight/bias with an eval-mode BatchNorm folded in (float64 arithmetic)."""
+    w = conv.weight.detach().double()
+    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    if bn is not None:
+        s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        w = w * s[:, None, None, None]
+        b = (b - bn.running_mean.detach().double()) * s + bn.bias.detach().double()
+    return w, b
+
+
+class NativeForward(object):
+    """CUDA forward of a policy-value module through the C ABI (no PyTorch ops on the hot path).
+
+    mode 'tc'  : bf16 tensor-core trunk (all trunk convs must output 128 channels, board <= 15)
+    mode 'f32' : fp32 CUDA-core trunk (any channel counts, any board <= 19)
+    """
+    graph_capturable = True
+    prior_is_log = True       # the network emits log-probabilities (policy_value_net.py:44)
+
+    def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0):
+        if not torch.cuda.is_available():
+            raise L.NativeLibraryError('NativeForward needs a CUDA device (no CPU fallback)')
+        self.lib = L.load()
+        self.module = module
+        self.device = torch.device(device)
+        self.H = int(module.board_size)
+        self.A = self.H * self.H
+        self.AS = (self.A + 31) // 32 * 32
+        layers = module.trunk_layers()
+        all128 = all(l[0].out_channels == 128 for l in layers)
+        if mode is None:
+            mode = 'tc' if (all128 and self.H <= 15) else 'f32'
+        if mode == 'tc' and not (all128 and self.H <= 15):
+            raise ValueError("mode 'tc' needs a 128-channel trunk and board_size <= 15")
+        self.mode = mode
+        self.n_ctas = int(n_ctas)
+        self.max_batch = 0
+        self.refresh_weights()
+        self._alloc(max_batch)
+
+    # ------------------------------------------------------------------ weights
+    def refresh_weights(self):
+        """(Re)pack the module's current parameters for the kernels (after load / a training step)."""
+        dev = self.device
+        m = self.module
+        self.layers = []
+        for conv, bn, skip, relu in m.trunk_layers():
+            w, b = _fold_bn(conv, bn)                      # [Cout][Cin][3][3]
+            cout, cin = w.shape[0], w.shape[1]
+            if self.mode == 'tc':
+                cin_p = 64 if cin <= 64 else 128
+                wt = torch.zeros(9, cout, cin_p, dtype=torch.float64)
+                wt[:, :, :cin] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)   # [tap][cout][cin]
+                wd = wt.to(torch.bfloat16).contiguous().to(dev)
+            else:
+                cin_p = cin
+                wd = w.permute(2, 3, 1, 0).reshape(9, cin, cout).float().contiguous().to(dev)  # [tap][cin][cout]
+            self.layers.append(dict(w=wd, b=b.float().contiguous().to(dev), cin=cin_p, cout=cout,
+                                    skip=skip, relu=bool(relu)))
+        hw, AS = self.A, self.AS
+        f32 = torch.float32
+        w1 = torch.cat([m.act_conv1.weight.detach().reshape(4, 128), m.val_conv1.weight.detach().reshape(2, 128)])
+        b1 = torch.cat([m.act_conv1.bias.detach(), m.val_conv1.bias.detach()])
+        wp = torch.zeros(4 * hw, AS, dtype=f32)
+        wp[:, :hw] = m.act_fc1.weight.detach().t().float()
+        bp = torch.zeros(AS, dtype=f32)
+        bp[:hw] = m.act_fc1.bias.detach().float()
+        self.heads = dict(
+            w1x1=w1.float().contiguous().to(dev), b1x1=b1.float().contiguous().to(dev),
+            wp=wp.contiguous().to(dev), bp=bp.to(dev),
+            wv1=m.val_fc1.weight.detach().t().float().contiguous().to(dev),
+            bv1=m.val_fc1.bias.detach().float().contiguous().to(dev),
+            wv2=m.val_fc2.weight.detach().reshape(64).float().contiguous().to(dev),
+            bv2=m.val_fc2.bias.detach().float().contiguous().to(dev))
+        hd = L.HeadsDesc()
+        hd.board_size, hd.action_stride = self.H, AS
+        for k, v in self.heads.items():
+            setattr(hd, k, v.data_ptr())
+        self.hdesc = hd
+
+    def _alloc(self, n):
+        if n <= self.max_batch:
+            return
+        dev = self.device
+        self.max_batch = n
+        if self.mode == 'tc':
+            bf = torch.bfloat16
+            self.act0 = torch.zeros(n, 256, 64, dtype=bf, device=dev)
+            self.bufs = [torch.zeros(n, 256, 128, dtype=bf, device=dev) for _ in range(2)]
+        else:
+            cmax = max(max(l['cin'], l['cout']) for l in self.layers)
+            self.act0 = torch.zeros(n, self.A, self.layers[0]['cin'], dtype=torch.float32, device=dev)
+            self.bufs = [torch.zeros(n, self.A, cmax, dtype=torch.float32, device=dev) for _ in range(3)]
+        self.logp = torch.zeros(n, self.AS, dtype=torch.float32, device=dev)
+        self.value = torch.zeros(n, dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------ forward
+    def _gdesc(self, k=5):
+        return L.GameDesc(self.H, min(k, self.H), self.A, self.AS)
+
+    def _trunk_and_heads(self, n, logp, value):
+        s = L.stream_ptr()
+        lib = self.lib
+        if self.mode == 'tc':
+            # ping-pong: the residual of a block is the buffer its second conv overwrites
+            src, outs = self.act0, self.bufs
+            cur = -1   # index in outs holding the latest activation, -1 = act0
+            for i, l in enumerate(self.layers):
+                dst = 0 if cur != 0 else 1
+                res = None
+                if l['skip'] is not None:
+                    # skip always refers to the activation two layers back = the other buffer
+                    res = outs[dst]
+                inp = src if cur < 0 else outs[cur]
+                L.check(lib.rz_net_conv3x3_tc(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
+                                              L.ptr(outs[dst]), n, self.H, l['cin'], int(l['relu']),
+                                              self.n_ctas, s), 'rz_net_conv3x3_tc')
+                cur = dst
+            L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(outs[cur]), 1, L.ptr(logp), L.ptr(value), n, s),
+                    'rz_net_heads')
+        else:
+            outs = self.bufs
+            hist = []   # buffer index holding the output of layer i
+            inp = self.act0
+            for i, l in enumerate(self.layers):
+                busy = {hist[-1]} if hist else set()
+                if l['skip'] is not None:
+                    busy.add(hist[l['skip']])
+                dst = [j for j in range(3) if j not in busy][0]
+                res = outs[hist[l['skip']]] if l['skip'] is not None else None
+                L.check(lib.rz_net_conv3x3_f32(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
+                                               L.ptr(outs[dst]), n, self.H, l['cin'], l['cout'],
+                                               int(l['relu']), s), 'rz_net_conv3x3_f32')
+                hist.append(dst)
+                inp = outs[dst]
+            L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(inp), 0, L.ptr(logp), L.ptr(value), n, s),
+                    'rz_net_heads')
+
+    def forward_boards(self, rows, meta, n, logp=None, value=None):
+        """Positions in the device board layout -> (logp [n][AS], value [n]) float32 tensors."""
+        self._alloc(n)
+        logp = self.logp if logp is None else logp
+        value = self.value if value is None else value
+        g = self._gdesc()
+        if self.mode == 'tc':
+            L.check(self.lib.rz_gomoku_encode_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(self.act0), n,
+                                                 L.stream_ptr()), 'rz_gomoku_encode_tc')
+        else:
+            L.check(self.lib.rz_gomoku_encode_nhwc_f32(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(self.act0),
+                                                       n, L.stream_ptr()), 'rz_gomoku_encode_nhwc_f32')
+        self._trunk_and_heads(n, logp, value)
+        return logp[:n], value[:n]
+
+    def forward_planes(self, planes):
+        """[n,4,H,W] float planes (current_state format) -> (logp [n][A], value [n]).  Used by
+        AlphaZeroAgent.policy_value / predict (alphazero_agent.py:48-57,88-97); the plane -> kernel
+        layout repack is a handful of torch ops (off the search path)."""
+        x = torch.as_tensor(planes, dtype=torch.float32, device=self.device)
+        n = x.shape[0]
+        self._alloc(n)
+        if self.mode == 'tc':
+            self.act0[:n].zero_()
+            t = self.act0[:n].view(n, 16, 16, 64)
+            t[:, :self.H, :self.H, :4] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+        else:
+            self.act0[:n] = x.permute(0, 2, 3, 1).reshape(n, self.A, 4)
+        self._trunk_and_heads(n, self.logp, self.value)
+        return self.logp[:n, :self.A], self.value[:n]
+
+    def __call__(self, forest):
+        """Evaluator protocol of engine.SearchForest.run_waves: evaluate the wave's leaves."""
+        self.forward_boards(forest.leaf_rows, forest.leaf_meta, forest.G, forest.prior, forest.value)

@@ -1,0 +1,194 @@
+"""GPU tests of the policy-value forward: tcgen05 convolution and heads against PyTorch, the
+stock network against the reference's golden outputs, and search parity with the real net."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _to_tile(x_nchw):
+    """[n,C,H,W] float -> bf16 tile layout [n,256,C] (p = y*16+x, zero padded)."""
+    n, c, h, w = x_nchw.shape
+    t = torch.zeros(n, 16, 16, c, dtype=torch.bfloat16, device=x_nchw.device)
+    t[:, :h, :w, :] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return t.reshape(n, 256, c).contiguous()
+
+
+def _from_tile(t, h):
+    n, _, c = t.shape
+    return t.reshape(n, 16, 16, c)[:, :h, :h, :].permute(0, 3, 1, 2).float()
+
+
+@pytest.mark.parametrize('n,h,cin,relu,res', [(1, 15, 128, 1, 0), (3, 15, 128, 1, 1), (5, 9, 64, 0, 0),
+                                              (300, 15, 128, 1, 1), (2, 3, 64, 1, 0), (37, 15, 64, 1, 0)])
+def test_conv3x3_tc_matches_torch(n, h, cin, relu, res):
+    from rlzero_b200 import _lib as L
+    lib = L.load()
+    torch.manual_seed(n * 100 + h)
+    dev = 'cuda'
+    x = (torch.randn(n, cin, h, h, device=dev) * 0.5).to(torch.bfloat16).float()
+    w = (torch.randn(128, cin, 3, 3, device=dev) / (3.0 * cin ** 0.5)).to(torch.bfloat16).float()
+    b = torch.randn(128, device=dev) * 0.1
+    r = (torch.randn(n, 128, h, h, device=dev) * 0.5).to(torch.bfloat16).float() if res else None
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if res:
+        ref = ref + r.double()
+    if relu:
+        ref = torch.relu(ref)
+    xt = _to_tile(x)
+    wt = w.permute(2, 3, 0, 1).reshape(9, 128, cin).to(torch.bfloat16).contiguous()
+    out = torch.full((n, 256, 128), 7.0, dtype=torch.bfloat16, device=dev)
+    rt = None
+    if res:
+        out.copy_(_to_tile(r))   # residual aliases the output buffer, as in the trunk
+        rt = out
+    L.check(lib.rz_net_conv3x3_tc(L.ptr(xt), L.ptr(wt), L.ptr(b.contiguous()), L.ptr(rt), L.ptr(out),
+                                  n, h, cin, relu, 0, L.stream_ptr()), 'conv')
+    torch.cuda.synchronize()
+    got = _from_tile(out, h).double()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-2 * max(scale, 1.0), (err, scale)   # bf16 output rounding: 2^-9 relative
+    # relative to bf16 rounding of the exact result the error is tiny
+    ref_bf = ref.float().to(torch.bfloat16).double()
+    frac_exact = ((got - ref_bf).abs() <= 1e-6).double().mean().item()
+    assert frac_exact > 0.97, frac_exact
+    # padding squares must be exactly zero (they are the halo of the next layer)
+    full = out.reshape(n, 16, 16, 128).float()
+    assert full[:, h:, :, :].abs().max().item() == 0.0
+    assert full[:, :, h:, :].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize('size', [3, 6])
+def test_stock_net_matches_reference_golden(size):
+    """PolicyValueNet through the fp32 CUDA path == the reference's outputs (1e-5)."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, PolicyValueNet
+    z = np.load(os.path.join(HERE, 'golden', 'net_pvn_%d.npz' % size))
+    net = PolicyValueNet(size)
+    net.load_state_dict({k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('w_')})
+    net.cuda().eval()
+    nf = NativeForward(net)
+    assert nf.mode == 'f32'
+    logp, v = nf.forward_planes(z['x'])
+    np.testing.assert_allclose(logp.cpu().numpy(), z['logp'], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(v.cpu().numpy().reshape(-1, 1), z['v'], atol=1e-5, rtol=0)
+
+
+def _random_boards(n, size, seed):
+    rs = np.random.RandomState(seed)
+    x = np.zeros((n, 4, size, size), dtype=np.float32)
+    for i in range(n):
+        k = rs.randint(0, size * size // 2)
+        sq = rs.permutation(size * size)[:k]
+        for j, s in enumerate(sq):
+            x[i, j % 2, s // size, s % size] = 1.0
+        if k:
+            x[i, 2, sq[-1] // size, sq[-1] % size] = 1.0
+        if k % 2 == 0:
+            x[i, 3] = 1.0
+    return x
+
+
+@pytest.mark.parametrize('size,blocks,n', [(15, 10, 64), (9, 3, 17), (6, 2, 5)])
+def test_resnet_tc_forward_vs_torch(size, blocks, n):
+    """bf16 tensor-core trunk: probabilities and value within 1e-3 of the fp32 PyTorch forward."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(0)
+    net = ResNetPolicyValueNet(size, n_blocks=blocks).cuda().eval()
+    nf = NativeForward(net)
+    assert nf.mode == 'tc'
+    x = _random_boards(n, size, 1)
+    logp, v = (t.cpu() for t in nf.forward_planes(x))
+    # plain PyTorch fp32 reference on the CPU (cuDNN would silently use TF32)
+    ref = ResNetPolicyValueNet(size, n_blocks=blocks).eval()
+    ref.load_state_dict({k: t.cpu() for k, t in net.state_dict().items()})
+    with torch.no_grad():
+        lt, vt = ref(torch.from_numpy(x))
+    p_err = (logp.exp() - lt.exp()).abs().max().item()
+    v_err = (v - vt.reshape(-1)).abs().max().item()
+    print('resnet%d %dx%d bf16: max |dp| %.3e  max |dv| %.3e' % (blocks, size, size, p_err, v_err))
+    assert p_err < 1e-3 and v_err < 1e-3          # north_star tolerance for bf16
+    assert torch.allclose(logp.exp().sum(1), torch.ones(n), atol=1e-4)
+    # fp32 CUDA-core path of the same net: 1e-5 on the same outputs
+    nf32 = NativeForward(net, mode='f32')
+    l32, v32 = (t.cpu() for t in nf32.forward_planes(x[:6]))
+    p32 = (l32.exp() - lt[:6].exp()).abs().max().item()
+    v32e = (v32 - vt[:6].reshape(-1)).abs().max().item()
+    print('resnet%d %dx%d fp32: max |dp| %.3e  max |dv| %.3e  max |dlogp| %.3e' % (
+        blocks, size, size, p32, v32e, (l32 - lt[:6]).abs().max().item()))
+    assert p32 < 1e-5 and v32e < 1e-5             # north_star tolerance for fp32
+
+
+def test_forward_is_batch_invariant():
+    """A board's outputs do not depend on its batch neighbours (needed for search parity)."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(1)
+    net = ResNetPolicyValueNet(9, n_blocks=2).cuda().eval()
+    nf = NativeForward(net)
+    x = _random_boards(33, 9, 2)
+    l_all, v_all = (t.clone() for t in nf.forward_planes(x))
+    for i in (0, 7, 32):
+        l1, v1 = nf.forward_planes(x[i:i + 1])
+        assert torch.equal(l1[0], l_all[i]) and torch.equal(v1[0], v_all[i])
+
+
+@pytest.mark.parametrize('kind', ['stock', 'resnet'])
+def test_search_with_native_net_matches_oracle(kind):
+    """Visit counts with the real network on the device == the oracle search fed the same
+    network outputs (its policy_value_fn calls the same CUDA forward board by board)."""
+    from oracle import pyoracle
+    from rlzero_b200.games.gomoku import GomokuEnv
+    from rlzero_b200.games.gomoku.alphazero_agent import AlphaZeroAgent
+    from rlzero_b200.games.gomoku.policy_value_net import ResNetPolicyValueNet
+    from rlzero_b200.mcts import AlphaZeroMCTS
+    size, k, n_playout = 6, 4, 150
+    torch.manual_seed(3)
+    agent = AlphaZeroAgent(size, net=ResNetPolicyValueNet(size, n_blocks=2) if kind == 'resnet' else None)
+    agent.policy_value_net.eval()
+    env = GomokuEnv(size, k)
+    env.reset()
+    for m in (14, 15, 20):
+        env.step(m)
+    mcts = AlphaZeroMCTS(agent.policy_value_fn, n_playout=n_playout, c_puct=5)
+    acts, probs = mcts.simulate(env, 1.0)
+    board = pyoracle.Board(size, k)
+    board.reset()
+    for m in (14, 15, 20):
+        board.step(m)
+    s = pyoracle.Search(agent.policy_value_fn, n_playout, 5)
+    acts2, probs2 = s.simulate(board, 1.0)
+    assert tuple(acts) == tuple(acts2)
+    root = mcts._root
+    assert [root._children[a].explore_count for a in acts] == [s.root.children[a].n for a in acts]
+    assert [float(root._children[a].total_reward).hex() for a in acts] == [
+        float(s.root.children[a].w).hex() for a in acts]
+    assert [float(p).hex() for p in probs] == [float(p).hex() for p in probs2]
+    # priors stored on the device are exp(log p) of the same forward
+    pri = np.array([root._children[a].prior for a in acts])
+    ref = np.array([s.root.children[a].prior for a in acts], dtype=np.float64)
+    np.testing.assert_allclose(pri, ref, rtol=2e-6)
+
+
+def test_agent_api_shapes():
+    from rlzero_b200.games.gomoku import GomokuEnv
+    from rlzero_b200.games.gomoku.alphazero_agent import AlphaZeroAgent
+    torch.manual_seed(0)
+    agent = AlphaZeroAgent(5)
+    env = GomokuEnv(5, 4)
+    env.reset()
+    env.step(12)
+    ap, v = agent.policy_value_fn(env)
+    ap = list(ap)
+    assert len(ap) == 24 and -1.0 <= v <= 1.0 and all(a != 12 for a, _ in ap)
+    probs, vals = agent.policy_value([env.current_state()] * 3)
+    assert probs.shape == (3, 25) and vals.shape == (3, 1)
+    np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-5)
+    loss, ent = agent.learn([env.current_state()] * 4, [np.full(25, 0.04)] * 4, [1.0, -1.0, 0.0, 1.0])
+    assert np.isfinite(loss) and np.isfinite(ent)
+    probs2, _ = agent.predict(np.array([env.current_state()]))
+    assert not np.allclose(probs2[0], probs[0])   # weights were refreshed after the step
