@@ -1,0 +1,194 @@
+"""Batched self-play: G games searched and played concurrently on one GPU.
+
+This is ``GameControl.start_self_play`` + ``AlphaZeroPlayer.get_action`` + ``AlphaZeroMCTS``
+(rlzero/games/gomoku/game.py:96-134, rlzero/mcts/alphazero_mcts.py:73-165) for thousands of
+games at once, entirely on the device:
+
+    per wave  : rz_tree_select -> rz_gomoku_encode_tc -> 21 x rz_net_conv3x3_tc -> rz_net_heads
+                -> rz_tree_expand_backup                          (one CUDA graph, replayed)
+    per move  : rz_tree_root_policy (pi, sampled move) -> rz_tree_advance (record ply, play the
+                move, re-root with the kept subtree, finish episode -> z -> ring, restart slot)
+
+Games are independent, so a multi-GPU job is one ``BatchedSelfPlay`` per rank with
+``global_offset = rank * n_games`` and no communication on this path; per-game random streams
+are keyed by the global game id, so results do not depend on how games are sharded.
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import SearchForest
+from .games.gomoku.policy_value_net import NativeForward
+
+
+class BatchedSelfPlay(object):
+
+    def __init__(self, n_games, board_size=15, n_in_row=5, net=None, n_playout=800, c_puct=5.0,
+                 rule=L.RULE_UCT, temperature=1.0, add_noise=True, noise_eps=0.25, noise_alpha=0.3,
+                 device='cuda', global_offset=0, seed=0, evaluator=None, ring_capacity=None,
+                 store_priors=True, n_ctas=0):
+        self.G = int(n_games)
+        self.n_playout = int(n_playout)
+        self.temperature = float(temperature)
+        self.noise_eps = float(noise_eps) if add_noise else 0.0
+        self.noise_alpha = float(noise_alpha)
+        self.seed = int(seed)
+        self.forest = SearchForest(self.G, board_size, n_in_row, n_playout=n_playout, c_puct=c_puct,
+                                   rule=rule, device=device, global_offset=global_offset,
+                                   with_trajectories=True, ring_capacity=ring_capacity,
+                                   store_priors=store_priors)
+        if evaluator is None:
+            if net is None:
+                raise ValueError('BatchedSelfPlay needs a policy-value module (net=) or an evaluator')
+            evaluator = NativeForward(net, max_batch=self.G, device=device, n_ctas=n_ctas)
+        self.evaluator = evaluator
+        self.waves_in_move = 0
+        self.moves_played = 0
+        self._graph = None
+        self._pinned = None
+
+    # ------------------------------------------------------------------ set-up
+    def set_random_start_positions(self, global_ids=None, max_random_moves=31):
+        """Game g starts after k_g = (1000+g) mod 31 uniformly random moves drawn with
+        RandomState(1000+g); positions that happen to be over restart empty."""
+        f = self.forest
+        ids = np.arange(self.G) + int(f.desc.global_offset) if global_ids is None else np.asarray(global_ids)
+        lists = []
+        for gid in ids:
+            rs = np.random.RandomState(1000 + int(gid))
+            k = (1000 + int(gid)) % max_random_moves
+            lists.append(rs.permutation(f.A)[:k].tolist())
+        f.set_positions(lists)
+        import ctypes as C
+        L.check(f.lib.rz_gomoku_reset(C.byref(f.gdesc), L.ptr(f.root_rows), L.ptr(f.root_meta), f.G, 1,
+                                      L.stream_ptr()), 'rz_gomoku_reset')
+        f.root_meta[:, L.META_EPISODE] = 0
+        self.waves_in_move = 0
+
+    # -------------------------------------------------------------------- waves
+    def _wave(self):
+        f = self.forest
+        f.select()
+        self.evaluator(f)
+        f.expand_backup(bool(getattr(self.evaluator, 'prior_is_log', False)), self.noise_eps,
+                        self.noise_alpha, self.seed)
+
+    def kernels_per_wave(self):
+        n_conv = len(getattr(self.evaluator, 'layers', []))
+        return 1 + (1 + n_conv + 1 if n_conv else 1) + 1
+
+    def warm_up(self):
+        """One eager wave (lazy attribute set-up) and capture of the wave graph."""
+        if self._graph is not None:
+            return
+        self._wave()
+        torch.cuda.synchronize()
+        if getattr(self.evaluator, 'graph_capturable', False):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._wave()
+            self._graph = g
+        self.waves_in_move += 1
+
+    def step_wave(self):
+        """One playout for every game; commits the move when ``n_playout`` waves are done."""
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._wave()
+        self.waves_in_move += 1
+        if self.waves_in_move >= self.n_playout:
+            self.commit_move()
+
+    def commit_move(self):
+        """pi + sampled move on the device, play it, re-root, record, refill finished games."""
+        f = self.forest
+        f.root_policy(self.temperature, seed=self.seed + 0x9E37)
+        f.advance(keep_subtree=True, record=True, auto_reset=True)
+        self.waves_in_move = 0
+        self.moves_played += 1
+
+    def play(self, n_moves):
+        self.warm_up()
+        for _ in range(n_moves * self.n_playout):
+            self.step_wave()
+
+    # ------------------------------------------------- host-buffer API (end to end)
+    def get_actions(self, rows_host, meta_host, temperature=None):
+        """Batched ``AlphaZeroPlayer.get_action(env, temperature, return_prob=True)`` with HOST
+        buffers: positions come from pinned host memory, the search runs ``n_playout`` playouts
+        per game from fresh trees, and (moves [G], pi [G,A], visits [G,A]) come back to the host.
+        ``rows_host``: uint32/int32 [G,2,H]; ``meta_host``: int32 [G,8] (include/rlzero_b200.h)."""
+        f = self.forest
+        if self._pinned is None:
+            self._pinned = dict(
+                rows=torch.empty(f.G, 2, f.H, dtype=torch.int32).pin_memory(),
+                meta=torch.empty(f.G, L.META_STRIDE, dtype=torch.int32).pin_memory(),
+                move=torch.empty(f.G, dtype=torch.int32).pin_memory(),
+                pi=torch.empty(f.G, f.AS, dtype=torch.float32).pin_memory(),
+                visits=torch.empty(f.G, f.AS, dtype=torch.int32).pin_memory())
+        p = self._pinned
+        p['rows'].copy_(torch.as_tensor(np.asarray(rows_host).view(np.int32)))
+        p['meta'].copy_(torch.as_tensor(np.asarray(meta_host)))
+        f.root_rows.copy_(p['rows'], non_blocking=True)
+        f.root_meta.copy_(p['meta'], non_blocking=True)
+        f.reset_trees()
+        self.warm_up_for_api()
+        for _ in range(self.n_playout):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._wave()
+        f.root_policy(self.temperature if temperature is None else temperature, seed=self.seed + 0x9E37)
+        p['move'].copy_(f.move, non_blocking=True)
+        p['pi'].copy_(f.pi, non_blocking=True)
+        p['visits'].copy_(f.visits, non_blocking=True)
+        torch.cuda.synchronize()
+        f.raise_faults()
+        A = f.A
+        return p['move'].numpy().copy(), p['pi'].numpy()[:, :A].copy(), p['visits'].numpy()[:, :A].copy()
+
+    def warm_up_for_api(self):
+        if self._graph is None and getattr(self.evaluator, 'graph_capturable', False):
+            # capture without disturbing the trees: run the eager warm-up wave, then reset
+            f = self.forest
+            self._wave()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._wave()
+            self._graph = g
+            f.reset_trees()
+
+    def api_bytes(self):
+        f = self.forest
+        h2d = f.G * (2 * f.H * 4 + L.META_STRIDE * 4)
+        d2h = f.G * (4 + f.AS * 4 + f.AS * 4)
+        return h2d, d2h
+
+    # ------------------------------------------------------------------- output
+    def stats(self):
+        t = self.forest.traj
+        return dict(games_done=int(t['games_done'].item()), plies_done=int(t['plies_done'].item()),
+                    moves_played=self.moves_played)
+
+    def drain(self):
+        """Finished episodes as training tuples in the reference's format (game.py:113-134):
+        states float32 [n,4,H,W] (current_state planes), pis float32 [n,A], z float32 [n]."""
+        f = self.forest
+        out = f.drain_trajectories()
+        rows, info = out['rows'], out['info']
+        n, H = len(info), f.H
+        states = np.zeros((n, 4, H, H), dtype=np.float32)
+        if n:
+            bits = ((rows[:, :, :, None] >> np.arange(H, dtype=np.uint32)[None, None, None, :]) & 1).astype(np.float32)
+            mover = info[:, 0]
+            idx = np.arange(n)
+            states[:, 0] = bits[idx, mover]
+            states[:, 1] = bits[idx, 1 - mover]
+            last = info[:, 1]
+            has_last = last >= 0
+            states[idx[has_last], 2, last[has_last] // H, last[has_last] % H] = 1.0
+            stones = bits.sum(axis=(1, 2, 3)).astype(np.int64)
+            states[stones % 2 == 0, 3] = 1.0
+        return states, out['pi'], info[:, 2].astype(np.float32), info
