@@ -14,8 +14,8 @@ Contents
                  (``rlzero/mcts/node.py``, ``rlzero/mcts/alphazero_mcts.py``,
                  ``rlzero/games/gomoku/gomoku_env.py``,
                  ``rlzero/games/gomoku/game.py``).
-``c/``           plain-C restatement of the same search for large cases
-                 (built by ``oracle/build_oracle.py`` into ``oracle/_build``).
+``c/``           (planned) plain-C restatement of the same search for large cases
+                 (``oracle/build_oracle.py``; absent until written).
 ``evaluators``   closed-form evaluators shared by both sides of a parity test.
 
 Pinning: the reference's own tests hold no golden vector for this path
