@@ -198,40 +198,6 @@ rz_conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act,
   }
 }
 
-// ---- host: tensor maps -----------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-// bf16 matrix [rows][cols] row-major, box = [box_rows][64 cols], 128-byte swizzle
-int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) { rz_set_error("cuTensorMapEncodeTiled entry point unavailable"); return -1; }
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { rz_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
-  return 0;
-}
-
 }  // namespace
 
 extern "C" int rz_net_conv3x3_tc(const void* act_in, const void* weight, const float* bias,
@@ -250,8 +216,8 @@ extern "C" int rz_net_conv3x3_tc(const void* act_in, const void* weight, const f
     attr_set = true;
   }
   CUtensorMap tmap_act, tmap_w;
-  if (make_tmap_2d(&tmap_act, act_in, (uint64_t)n_boards * 256, (uint64_t)c_in, TILE_M)) return -1;
-  if (make_tmap_2d(&tmap_w, weight, (uint64_t)9 * 128, (uint64_t)c_in, TILE_N)) return -1;
+  if (rz::make_tmap_2d(&tmap_act, act_in, (uint64_t)n_boards * 256, (uint64_t)c_in, TILE_M)) return -1;
+  if (rz::make_tmap_2d(&tmap_w, weight, (uint64_t)9 * 128, (uint64_t)c_in, TILE_N)) return -1;
   ConvParams p;
   p.bias = bias;
   p.residual = (const __nv_bfloat16*)residual;
