@@ -238,8 +238,8 @@ def run_b200(args):
         for i in range(3 + reps):
             if i == 3:
                 k0.record()
-            L.check(lib.rz_net_conv3x3_tc(L.ptr(x), L.ptr(layer['w']), L.ptr(layer['b']), None, L.ptr(y), G,
-                                          BOARD, 128, 1, 0, L.stream_ptr()))
+            L.check(lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(layer['w']), L.ptr(layer['b']), None, L.ptr(y), G,
+                                           BOARD, 128, 1, 2, 0, 0, L.stream_ptr()))
         k1.record()
         torch.cuda.synchronize()
         conv_ms = k0.elapsed_time(k1) / reps
@@ -258,7 +258,7 @@ def run_b200(args):
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'conv3x3_tc_traffic.json')))['dram_bytes_per_launch']
         except Exception:
             pass
-        roof = {'bound': 'tensor', 'kernel': 'rz_conv3x3_tc_kernel (128->128, %d boards)' % G,
+        roof = {'bound': 'tensor', 'kernel': 'rz_conv3x3_tc2_kernel<2> (128->128, %d boards)' % G,
                 'achieved': flops / conv_ms / 1e9, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': flops / conv_ms / 1e9 / peak,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst, of measured)' if peaks else 'fallback 1590',

@@ -229,6 +229,15 @@ typedef struct rz_heads_desc {
 int rz_net_conv3x3_tc(const void* act_in, const void* weight, const float* bias, const void* residual,
                       void* act_out, int n_boards, int board_size, int c_in, int relu, int n_ctas,
                       void* stream);
+/* revision 2 of the same operator (same tensors, same results): the 9x128x128 weights stay resident
+   in shared memory, split over a CTA pair (cta_group = 2: tcgen05 cta_group::2 MMAs, cluster of 2),
+   and each 128-position activation tile is loaded once with its 17-row halo; the 9 taps are
+   row-shifted UMMA descriptors on that tile.  cta_group = 1 runs the same data path on single CTAs
+   (each computes 64 of the 128 output channels).  flags bit 0: set the base-offset field of the
+   shifted descriptors.  n_ctas <= 0 picks 148. */
+int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias, const void* residual,
+                       void* act_out, int n_boards, int board_size, int c_in, int relu, int cta_group,
+                       int flags, int n_ctas, void* stream);
 /* the same operator in float32 on CUDA cores for the reference's stock network at any board size:
    in [n][HW][c_in], weight [9][c_in][c_out], out [n][HW][c_out] (channels last). */
 int rz_net_conv3x3_f32(const float* in, const float* weight, const float* bias, const float* residual,

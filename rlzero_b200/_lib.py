@@ -79,6 +79,8 @@ SIGNATURES = {
     'rz_eval_closed_form': (C.c_int, [_TD, C.c_int, _vp, _vp, _vp]),
     'rz_net_conv3x3_tc': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, _vp]),
+    'rz_net_conv3x3_tc2': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, _vp]),
     'rz_net_conv3x3_f32': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, _vp]),
     'rz_net_heads': (C.c_int, [C.POINTER(HeadsDesc), _vp, C.c_int, _vp, _vp, C.c_int, _vp]),

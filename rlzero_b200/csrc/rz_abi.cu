@@ -17,3 +17,7 @@ extern "C" int rz_abi_version(void) { return RZ_ABI_VERSION; }
 extern "C" const char* rz_last_error(void) { return rz_error_buf; }
 extern "C" int rz_sizeof_tree_desc(void) { return (int)sizeof(rz_tree_desc); }
 extern "C" int rz_sizeof_traj_desc(void) { return (int)sizeof(rz_traj_desc); }
+
+namespace rz {
+void set_error_tmap(const char* what, int code) { rz_set_error("%s (%d)", what, code); }
+}  // namespace rz

@@ -48,9 +48,15 @@ rz_conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
 }
 
 // ---------------------------------------------------------------------------
-// heads: NB boards per block
+// heads: NB boards per block.
+//
+// Shared-memory feature layout is [k][NB] (k = flattened FC input index c*HW + pos, policy
+// features first, value features after them), so that the FC loops read the NB boards of one k
+// as float4 broadcasts: per k a thread issues 1 coalesced weight load + NB/4 LDS.128 + NB FMAs.
+// (The first revision kept [board][k] and spent 54 M shared-memory wavefronts per launch on
+// scalar broadcasts -- profiles/r1_run4_*: 532 us for 6.6 GFLOP.)
 // ---------------------------------------------------------------------------
-constexpr int HEAD_NB = 8;
+constexpr int HEAD_NB = 16;
 constexpr int HEAD_THREADS = 256;
 constexpr int HEAD_C = 128;
 
@@ -73,6 +79,7 @@ struct HeadsParams {
 template <bool kTile>
 __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos, int H,
                                                  const float* __restrict__ s_w, float (&acc)[6]) {
+  const float4* w4 = reinterpret_cast<const float4*>(s_w);
   if constexpr (kTile) {
     const int y = pos / H, x = pos - y * H;
     const uint4* src = reinterpret_cast<const uint4*>(
@@ -80,14 +87,18 @@ __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos
 #pragma unroll 4
     for (int j = 0; j < HEAD_C / 8; ++j) {
       const uint4 q = src[j];
-      const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+      float v[8];
+      v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+      v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+      v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xffff0000u);
+      v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xffff0000u);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ws[e]);
-        const float v0 = __low2float(h2), v1 = __high2float(h2);
-        const int c = j * 8 + e * 2;
-#pragma unroll
-        for (int f = 0; f < 6; ++f) acc[f] = fmaf(v1, s_w[f * HEAD_C + c + 1], fmaf(v0, s_w[f * HEAD_C + c], acc[f]));
+      for (int f = 0; f < 6; ++f) {
+        const float4 wa = w4[f * (HEAD_C / 4) + j * 2], wb = w4[f * (HEAD_C / 4) + j * 2 + 1];
+        float a = acc[f];
+        a = fmaf(v[0], wa.x, a); a = fmaf(v[1], wa.y, a); a = fmaf(v[2], wa.z, a); a = fmaf(v[3], wa.w, a);
+        a = fmaf(v[4], wb.x, a); a = fmaf(v[5], wb.y, a); a = fmaf(v[6], wb.z, a); a = fmaf(v[7], wb.w, a);
+        acc[f] = a;
       }
     }
   } else {
@@ -96,44 +107,42 @@ __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos
 #pragma unroll 4
     for (int j = 0; j < HEAD_C / 4; ++j) {
       const float4 q = src[j];
-      const float vs[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-#pragma unroll
-        for (int f = 0; f < 6; ++f) acc[f] = fmaf(vs[e], s_w[f * HEAD_C + j * 4 + e], acc[f]);
+      for (int f = 0; f < 6; ++f) {
+        const float4 w = w4[f * (HEAD_C / 4) + j];
+        float a = acc[f];
+        a = fmaf(q.x, w.x, a); a = fmaf(q.y, w.y, a); a = fmaf(q.z, w.z, a); a = fmaf(q.w, w.w, a);
+        acc[f] = a;
       }
     }
   }
 }
 
 template <bool kTile>
-__global__ void __launch_bounds__(HEAD_THREADS) rz_heads_kernel(const HeadsParams p) {
-  extern __shared__ float sm[];
+__global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsParams p) {
+  extern __shared__ __align__(16) float sm[];
   const int HW = p.A;
-  float* s_w = sm;                          // [6][128]
-  float* s_fp = s_w + 6 * HEAD_C;           // [NB][4*HW]  policy features
-  float* s_fv = s_fp + HEAD_NB * 4 * HW;    // [NB][2*HW]  value features
-  float* s_lg = s_fv + HEAD_NB * 2 * HW;    // [NB][AS]    logits
-  float* s_h = s_lg + HEAD_NB * p.AS;       // [NB][64]    value hidden
+  float* s_w = sm;                              // [6][128]
+  float* s_f = s_w + 6 * HEAD_C;                // [6*HW][NB]  k-major features (policy 4*HW, then value 2*HW)
+  float* s_lg = s_f + 6 * HW * HEAD_NB;         // [NB][AS]    logits
+  float* s_h = s_lg + HEAD_NB * p.AS;           // [NB][64]    value hidden
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b0 = blockIdx.x * HEAD_NB;
   const int nb = min(HEAD_NB, p.n_boards - b0);
   for (int i = tid; i < 6 * HEAD_C; i += HEAD_THREADS) s_w[i] = p.w1x1[i];
   __syncthreads();
-  // phase 1: 1x1 convolutions + ReLU  (policy_value_net.py:41, 47)
-  for (int i = tid; i < nb * HW; i += HEAD_THREADS) {
-    const int bi = i / HW, pos = i - bi * HW;
+  // phase 1: 1x1 convolutions + ReLU  (policy_value_net.py:41, 47); boards beyond nb hold zeros
+  for (int i = tid; i < HEAD_NB * HW; i += HEAD_THREADS) {
+    const int bi = i % HEAD_NB, pos = i / HEAD_NB;   // board fastest: conflict-free feature stores
     float acc[6];
 #pragma unroll
     for (int f = 0; f < 6; ++f) acc[f] = p.b1x1[f];
-    conv1x1_position<kTile>(p.act, b0 + bi, pos, p.H, s_w, acc);
+    if (bi < nb) conv1x1_position<kTile>(p.act, b0 + bi, pos, p.H, s_w, acc);
 #pragma unroll
-    for (int f = 0; f < 4; ++f) s_fp[bi * 4 * HW + f * HW + pos] = fmaxf(acc[f], 0.0f);
-#pragma unroll
-    for (int f = 0; f < 2; ++f) s_fv[bi * 2 * HW + f * HW + pos] = fmaxf(acc[4 + f], 0.0f);
+    for (int f = 0; f < 6; ++f) s_f[(f * HW + pos) * HEAD_NB + bi] = bi < nb ? fmaxf(acc[f], 0.0f) : 0.0f;
   }
   __syncthreads();
-  // phase 2: policy FC (:43)
+  // phase 2: policy FC (:43): thread j owns output column j for all NB boards
   for (int j = tid; j < p.AS; j += HEAD_THREADS) {
     float acc[HEAD_NB];
     const float bj = j < p.A ? p.bp[j] : 0.0f;
@@ -141,22 +150,56 @@ __global__ void __launch_bounds__(HEAD_THREADS) rz_heads_kernel(const HeadsParam
     for (int bi = 0; bi < HEAD_NB; ++bi) acc[bi] = bj;
     if (j < p.A) {
       const float* wcol = p.wp + j;
-      for (int k = 0; k < 4 * HW; ++k) {
-        const float wkj = wcol[(size_t)k * p.AS];
+      const float4* f4 = reinterpret_cast<const float4*>(s_f);
+      const int K = 4 * HW;
+      int k = 0;
+      for (; k + 4 <= K; k += 4) {
+        float w[4];
 #pragma unroll
-        for (int bi = 0; bi < HEAD_NB; ++bi) acc[bi] = fmaf(s_fp[bi * 4 * HW + k], wkj, acc[bi]);
+        for (int u = 0; u < 4; ++u) w[u] = wcol[(size_t)(k + u) * p.AS];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int g = 0; g < HEAD_NB / 4; ++g) {
+            const float4 f = f4[(k + u) * (HEAD_NB / 4) + g];
+            acc[g * 4 + 0] = fmaf(f.x, w[u], acc[g * 4 + 0]);
+            acc[g * 4 + 1] = fmaf(f.y, w[u], acc[g * 4 + 1]);
+            acc[g * 4 + 2] = fmaf(f.z, w[u], acc[g * 4 + 2]);
+            acc[g * 4 + 3] = fmaf(f.w, w[u], acc[g * 4 + 3]);
+          }
+        }
+      }
+      for (; k < K; ++k) {
+        const float w = wcol[(size_t)k * p.AS];
+#pragma unroll
+        for (int g = 0; g < HEAD_NB / 4; ++g) {
+          const float4 f = f4[k * (HEAD_NB / 4) + g];
+          acc[g * 4 + 0] = fmaf(f.x, w, acc[g * 4 + 0]);
+          acc[g * 4 + 1] = fmaf(f.y, w, acc[g * 4 + 1]);
+          acc[g * 4 + 2] = fmaf(f.z, w, acc[g * 4 + 2]);
+          acc[g * 4 + 3] = fmaf(f.w, w, acc[g * 4 + 3]);
+        }
       }
     }
 #pragma unroll
     for (int bi = 0; bi < HEAD_NB; ++bi) s_lg[bi * p.AS + j] = acc[bi];
   }
-  // phase 3a: value FC1 + ReLU (:49)
-  for (int i = tid; i < HEAD_NB * 64; i += HEAD_THREADS) {
-    const int bi = i >> 6, o = i & 63;
-    float acc = p.bv1[o];
-    if (bi < nb)
-      for (int k = 0; k < 2 * HW; ++k) acc = fmaf(s_fv[bi * 2 * HW + k], p.wv1[k * 64 + o], acc);
-    s_h[i] = fmaxf(acc, 0.0f);
+  // phase 3a: value FC1 + ReLU (:49): thread = (output o, group of 4 boards)
+  for (int i = tid; i < (HEAD_NB / 4) * 64; i += HEAD_THREADS) {
+    const int o = i & 63, g = i >> 6;
+    const float bo = p.bv1[o];
+    float a0 = bo, a1 = bo, a2 = bo, a3 = bo;
+    const float4* f4 = reinterpret_cast<const float4*>(s_f + (size_t)4 * HW * HEAD_NB);
+#pragma unroll 4
+    for (int k = 0; k < 2 * HW; ++k) {
+      const float w = p.wv1[k * 64 + o];
+      const float4 f = f4[k * (HEAD_NB / 4) + g];
+      a0 = fmaf(f.x, w, a0); a1 = fmaf(f.y, w, a1); a2 = fmaf(f.z, w, a2); a3 = fmaf(f.w, w, a3);
+    }
+    s_h[(g * 4 + 0) * 64 + o] = fmaxf(a0, 0.0f);
+    s_h[(g * 4 + 1) * 64 + o] = fmaxf(a1, 0.0f);
+    s_h[(g * 4 + 2) * 64 + o] = fmaxf(a2, 0.0f);
+    s_h[(g * 4 + 3) * 64 + o] = fmaxf(a3, 0.0f);
   }
   __syncthreads();
   // phase 3b: log_softmax (:44) and value FC2 + tanh (:50-51): one warp per board
@@ -178,8 +221,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) rz_heads_kernel(const HeadsParam
 }
 
 size_t heads_smem(int A, int AS) {
-  return sizeof(float) * (6 * HEAD_C + (size_t)HEAD_NB * 4 * A + (size_t)HEAD_NB * 2 * A +
-                          (size_t)HEAD_NB * AS + HEAD_NB * 64);
+  return sizeof(float) * (6 * HEAD_C + (size_t)HEAD_NB * 6 * A + (size_t)HEAD_NB * AS + HEAD_NB * 64);
 }
 
 }  // namespace

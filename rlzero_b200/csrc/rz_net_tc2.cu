@@ -1,0 +1,315 @@
+// rlzero_b200 -- 3x3 convolution of the policy-value trunk, revision 2: weights resident in
+// shared memory, activation tile loaded once with its halo, CTA pairs (tcgen05 cta_group::2).
+//
+// Reference op: nn.Conv2d(C, 128, kernel_size=3, padding=1) (+ folded BatchNorm, residual add,
+// ReLU), trunk of rlzero/games/gomoku/policy_value_net.py:14-16,36-38 / the ResNet-N trunk of
+// SURVEY.md section 7.  Same tensors and layouts as rz_net_tc.cu (act[b][p = y*16+x][c] bf16 with
+// zero pad squares, w[tap][cout][cin]).
+//
+// Why: revision 1 streams a 128x64 activation tile AND a 128x64 weight tile from L2 for every
+// (tap, k-block) -- 128 B/clk/SM, 8.5-11 GB of L2->SM traffic per layer against 1.07 GB
+// algorithmic (profiles/r1_run4_*): it is L2-bandwidth bound at ~50 % tensor-pipe activity.
+// Here
+//   * the 9 x 128 x 128 weights stay in shared memory for the whole launch.  295 KB do not fit one
+//     SM, so two CTAs form a pair: each keeps the 64 output channels it contributes as the B
+//     operand of a cta_group::2 MMA (147 KB), the pair computes 256 positions x 128 channels;
+//   * the activation tile of a CTA (128 positions) is loaded ONCE per tile together with its
+//     17-row halo (162 rows x 128 channels = 41 KB, double buffered); tap (dy,dx) is the same
+//     tile read 16*dy+dx rows further on, i.e. only the UMMA descriptor start address moves.
+// L2->SM traffic drops to 41 KB per 128x128x1152 tile (14x less); the MMA issuer never waits
+// for operands inside a tile (72 back-to-back tcgen05.mma per tile).
+//
+// kCG = 2: the production kernel (cluster of 2).  kCG = 1: the same data path on a single CTA
+// (UMMA 128x64, each CTA computes one half of the output channels) -- kept as a bisecting aid
+// and for odd SM counts.
+#include <cuda_bf16.h>
+
+#include "rz_common.cuh"
+#include "rz_tc.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int HALO = 17;                          // |16*dy + dx| <= 17
+constexpr int A_ROWS = TILE_M + 2 * HALO;         // 162
+constexpr int A_KB_BYTES = A_ROWS * 128;          // one k-block (64 channels) of the halo tile
+constexpr int A_BUF_BYTES = 2 * A_KB_BYTES;       // 41472
+constexpr int B_TILE_BYTES = 64 * 128;            // 64 output channels x 64 input channels
+constexpr int B_BYTES = 9 * 2 * B_TILE_BYTES;     // 147456
+constexpr int CTRL_OFF = B_BYTES + 2 * A_BUF_BYTES;  // 230400
+constexpr int SMEM_BYTES = CTRL_OFF + 1024;       // 231424 <= 232448
+constexpr int NUM_THREADS = 192;
+
+struct Conv2Params {
+  const float* bias;               // [128]
+  const __nv_bfloat16* residual;   // [rows][128] or null
+  __nv_bfloat16* out;              // [rows][128]
+  int n_items;                     // kCG=2: boards; kCG=1: half boards
+  int board;                       // H
+  int kblocks;                     // Cin / 64
+  int relu;
+  int flags;                       // bit 0: set the descriptor base-offset field for shifted A tiles
+};
+
+template <int kCG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
+                      const __grid_constant__ CUtensorMap tmap_w,
+                      const __grid_constant__ CUtensorMap tmap_out, const Conv2Params p) {
+  constexpr int ACC_N = (kCG == 2) ? 128 : 64;     // accumulator columns per buffer
+  constexpr int TMEM_COLS = 2 * ACC_N;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = rz::smem_u32(smem_raw);
+  const uint32_t a_base = smem_base + B_BYTES;
+  const uint32_t ctrl = smem_base + CTRL_OFF;
+  uint8_t* ctrl_ptr = smem_raw + CTRL_OFF;
+  const uint32_t bar_bfull = ctrl, bar_afull = ctrl + 8, bar_aempty = ctrl + 24;
+  const uint32_t bar_tfull = ctrl + 40, bar_tempty = ctrl + 56;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ctrl_ptr + 72);
+  float* s_bias = reinterpret_cast<float*>(ctrl_ptr + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (kCG == 2) ? rz::cluster_ctarank() : 0u;
+  const int half = (kCG == 2) ? (int)rank : (int)(blockIdx.x & 1);   // which 64 output channels live here
+  const bool leader = rank == 0;
+  const int worker = blockIdx.x >> 1, n_workers = gridDim.x >> 1;
+
+  if (threadIdx.x == 0 && (smem_base & 1023u)) __trap();  // layout below assumes a 1024-byte base
+  if (warp == 0 && lane == 0) {
+    rz::tma_prefetch_desc(&tmap_act);
+    rz::tma_prefetch_desc(&tmap_w);
+    rz::tma_prefetch_desc(&tmap_out);
+    rz::mbar_init(bar_bfull, 1);
+    for (int b = 0; b < 2; ++b) {
+      rz::mbar_init(bar_afull + 8 * b, 1);
+      rz::mbar_init(bar_aempty + 8 * b, 1);
+      rz::mbar_init(bar_tfull + 8 * b, 1);
+      rz::mbar_init(bar_tempty + 8 * b, 4 * kCG);
+    }
+    rz::fence_barrier_init();
+  }
+  if (warp == 1) {
+    if (kCG == 2) { rz::tmem_alloc_pair(rz::smem_u32(tmem_holder), TMEM_COLS); rz::tmem_relinquish_pair(); }
+    else          { rz::tmem_alloc(rz::smem_u32(tmem_holder), TMEM_COLS); rz::tmem_relinquish(); }
+  }
+  if (threadIdx.x >= 64) s_bias[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+  rz::tc_fence_before();
+  if (kCG == 2) rz::cluster_sync_all(); else __syncthreads();
+  rz::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  // first row of this CTA's 128 output positions for work item `item`
+  auto row_of = [&](int item) -> int {
+    return (kCG == 2) ? item * 256 + (int)rank * TILE_M : item * TILE_M;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer (every CTA loads its own operands; completion is credited to the leader) =====
+    if (lane == 0) {
+      const uint32_t l_bfull = (kCG == 2) ? rz::mapa_shared(bar_bfull, 0) : bar_bfull;
+      if (leader) rz::mbar_expect_tx(bar_bfull, (uint32_t)(kCG * 9 * p.kblocks * B_TILE_BYTES));
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          const uint32_t dst = smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES;
+          if (kCG == 2) rz::tma_load_2d_pair(dst, &tmap_w, l_bfull, kb * 64, tap * 128 + half * 64);
+          else          rz::tma_load_2d(dst, &tmap_w, l_bfull, kb * 64, tap * 128 + half * 64);
+        }
+      int it = 0;
+      for (int item = worker; item < p.n_items; item += n_workers, ++it) {
+        const int buf = it & 1;
+        rz::mbar_wait(bar_aempty + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        const uint32_t l_afull = (kCG == 2) ? rz::mapa_shared(bar_afull + 8 * buf, 0) : bar_afull + 8 * buf;
+        if (leader) rz::mbar_expect_tx(bar_afull + 8 * buf, (uint32_t)(kCG * p.kblocks * A_KB_BYTES));
+        const int row0 = row_of(item) - HALO;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          const uint32_t dst = a_base + (uint32_t)buf * A_BUF_BYTES + (uint32_t)kb * A_KB_BYTES;
+          if (kCG == 2) rz::tma_load_2d_pair(dst, &tmap_act, l_afull, kb * 64, row0);
+          else          rz::tma_load_2d(dst, &tmap_act, l_afull, kb * 64, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA =====
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = rz::umma_idesc_bf16(kCG == 2 ? 256 : 128, ACC_N);
+      rz::mbar_wait(bar_bfull, 0);
+      int it = 0;
+      for (int item = worker; item < p.n_items; item += n_workers, ++it) {
+        const int buf = it & 1;
+        const uint32_t par = (uint32_t)(it >> 1) & 1u;
+        rz::mbar_wait(bar_tempty + 8 * buf, par ^ 1u);
+        rz::mbar_wait(bar_afull + 8 * buf, par);
+        rz::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_N);
+        const uint32_t a_buf = a_base + (uint32_t)buf * A_BUF_BYTES;
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int shift = HALO + (tap / 3 - 1) * 16 + (tap % 3 - 1);   // 0..34 rows into the halo tile
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            const uint32_t a_addr = a_buf + (uint32_t)kb * A_KB_BYTES + (uint32_t)shift * 128u;
+            const uint32_t b_addr = smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES;
+            const uint64_t adesc = rz::umma_desc_sw128_bo(a_addr, (p.flags & 1) ? (a_addr >> 7) & 7u : 0u);
+            const uint64_t bdesc = rz::umma_desc_sw128(b_addr);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kCG == 2) rz::umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
+              else          rz::umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
+              acc = 1;
+            }
+          }
+        }
+        // accumulator complete: both CTAs drain their half; the A buffers are recycled by the
+        // epilogues (they stage the output tile in them), not here
+        if (kCG == 2) rz::umma_commit_pair(bar_tfull + 8 * buf, 3);
+        else          rz::umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4, one output row per thread =====
+    // TMEM -> registers -> (+bias, +residual, ReLU, pad mask, bf16) -> shared-memory staging in the
+    // A buffer the tile's MMAs have just finished with -> TMA store.  The A buffer is handed back
+    // to the producer (a_empty) once the store has read it.
+    const int q = warp & 3;
+    const int col_base = (kCG == 2) ? 0 : half * 64;
+    constexpr int NCH = ACC_N / 32;
+    int it = 0;
+    for (int item = worker; item < p.n_items; item += n_workers, ++it) {
+      const int buf = it & 1;
+      const int row0 = row_of(item);
+      const int r_in_tile = q * 32 + lane;
+      const size_t row = (size_t)row0 + r_in_tile;
+      const int pos = (int)(row & 255);
+      const bool valid = ((pos & 15) < p.board) && ((pos >> 4) < p.board);
+      // residual row: issued before the accumulator is ready, so its latency hides behind the MMAs
+      uint4 res[NCH * 4];
+      const bool have_res = p.residual != nullptr && valid;
+      if (have_res) {
+        const uint4* rrow = reinterpret_cast<const uint4*>(p.residual + row * 128 + col_base);
+#pragma unroll
+        for (int j = 0; j < NCH * 4; ++j) res[j] = rrow[j];
+      }
+      rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
+      rz::tc_fence_after();
+      const uint32_t stage_row = a_base + (uint32_t)buf * A_BUF_BYTES + (uint32_t)r_in_tile * 128u;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t acc[32];
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_N + ch * 32), acc);
+        rz::tmem_ld_wait();
+        if (ch == NCH - 1) {
+          // accumulator drained: the MMA issuer may overwrite it (no memory payload -> relaxed)
+          rz::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kCG == 2) rz::mbar_arrive_cluster_relaxed(rz::mapa_shared(bar_tempty + 8 * buf, 0));
+            else          rz::mbar_arrive(bar_tempty + 8 * buf);
+          }
+        }
+        // staging: k-block (64 columns) `ch / 2` is a [128 rows][128 B] tile with the 128-byte
+        // swizzle of the absolute shared-memory address, as the TMA store expects
+        const uint32_t srow = stage_row + (uint32_t)(ch >> 1) * (TILE_M * 128u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = j * 8 + e * 2;
+            float v0 = __uint_as_float(acc[c]) + s_bias[col_base + ch * 32 + c];
+            float v1 = __uint_as_float(acc[c + 1]) + s_bias[col_base + ch * 32 + c + 1];
+            if (have_res) {
+              const uint32_t rw = (&res[ch * 4 + j].x)[e];
+              v0 += __uint_as_float(rw << 16);
+              v1 += __uint_as_float(rw & 0xffff0000u);
+            }
+            if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+            if (!valid) { v0 = 0.0f; v1 = 0.0f; }
+            const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
+            packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
+          }
+          const uint32_t chunk = (uint32_t)((ch & 1) * 4 + j);
+          rz::st_shared_v4(srow + ((chunk ^ ((srow >> 7) & 7u)) << 4), packed[0], packed[1], packed[2], packed[3]);
+        }
+      }
+      rz::fence_proxy_async();              // staging writes -> visible to the TMA engine
+      rz::named_bar_sync(1, 128);           // the 4 epilogue warps
+      if (warp == 2 && lane == 0) {
+        const uint32_t stage = a_base + (uint32_t)buf * A_BUF_BYTES;
+#pragma unroll
+        for (int kb = 0; kb < ACC_N / 64; ++kb)
+          rz::tma_store_2d(&tmap_out, stage + (uint32_t)kb * (TILE_M * 128u), col_base + kb * 64, row0);
+        rz::tma_store_commit();
+        rz::tma_store_wait_read();
+        rz::mbar_arrive(bar_aempty + 8 * buf);   // this CTA's producer may refill the buffer
+      }
+    }
+    if (warp == 2 && lane == 0) rz::tma_store_wait_all();
+  }
+
+  rz::tc_fence_before();
+  if (kCG == 2) rz::cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    rz::tc_fence_after();
+    if (kCG == 2) rz::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else          rz::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int kCG>
+int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const Conv2Params& p, int ctas,
+           cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rz_conv3x3_tc2_kernel<kCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc2: smem attribute: %s", cudaGetErrorString(e)); return -2; }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, rz_conv3x3_tc2_kernel<kCG>, ta, tw, to, p);
+  if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc2: launch failed: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias,
+                                  const void* residual, void* act_out, int n_boards, int board_size,
+                                  int c_in, int relu, int cta_group, int flags, int n_ctas, void* stream) {
+  RZ_REQUIRE(act_in && weight && bias && act_out, "rz_net_conv3x3_tc2: null argument");
+  RZ_REQUIRE(n_boards >= 0, "rz_net_conv3x3_tc2: n_boards %d", n_boards);
+  RZ_REQUIRE(board_size >= 1 && board_size <= 15, "rz_net_conv3x3_tc2: board_size %d not in [1,15]", board_size);
+  RZ_REQUIRE(c_in == 64 || c_in == 128, "rz_net_conv3x3_tc2: c_in %d (64 or 128)", c_in);
+  RZ_REQUIRE(cta_group == 1 || cta_group == 2, "rz_net_conv3x3_tc2: cta_group %d (1 or 2)", cta_group);
+  RZ_REQUIRE(act_in != act_out, "rz_net_conv3x3_tc2: in-place convolution is not supported");
+  if (n_boards == 0) return 0;
+  CUtensorMap tmap_act, tmap_w, tmap_out;
+  if (rz::make_tmap_2d(&tmap_act, act_in, (uint64_t)n_boards * 256, (uint64_t)c_in, A_ROWS)) return -1;
+  if (rz::make_tmap_2d(&tmap_w, weight, (uint64_t)9 * 128, (uint64_t)c_in, 64)) return -1;
+  if (rz::make_tmap_2d(&tmap_out, act_out, (uint64_t)n_boards * 256, 128, TILE_M)) return -1;
+  Conv2Params p;
+  p.bias = bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.out = (__nv_bfloat16*)act_out;
+  p.n_items = cta_group == 2 ? n_boards : n_boards * 2;
+  p.board = board_size;
+  p.kblocks = c_in / 64;
+  p.relu = relu;
+  p.flags = flags;
+  int ctas = n_ctas > 0 ? n_ctas : 148;
+  ctas &= ~1;                                       // workers are CTA pairs in both modes
+  if (ctas < 2) ctas = 2;
+  if (ctas / 2 > p.n_items) ctas = 2 * p.n_items;   // every worker gets at least one item
+  return cta_group == 2 ? launch<2>(tmap_act, tmap_w, tmap_out, p, ctas, (cudaStream_t)stream)
+                        : launch<1>(tmap_act, tmap_w, tmap_out, p, ctas, (cudaStream_t)stream);
+}

@@ -135,7 +135,7 @@ class NativeForward(object):
     graph_capturable = True
     prior_is_log = True       # the network emits log-probabilities (policy_value_net.py:44)
 
-    def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0):
+    def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0, conv_rev=2):
         if not torch.cuda.is_available():
             raise L.NativeLibraryError('NativeForward needs a CUDA device (no CPU fallback)')
         self.lib = L.load()
@@ -152,6 +152,7 @@ class NativeForward(object):
             raise ValueError("mode 'tc' needs a 128-channel trunk and board_size <= 15")
         self.mode = mode
         self.n_ctas = int(n_ctas)
+        self.conv_rev = int(conv_rev)   # 2: resident weights + CTA pairs (rz_net_tc2.cu); 1: rz_net_tc.cu
         self.max_batch = 0
         self.refresh_weights()
         self._alloc(max_batch)
@@ -230,9 +231,14 @@ class NativeForward(object):
                     # skip always refers to the activation two layers back = the other buffer
                     res = outs[dst]
                 inp = src if cur < 0 else outs[cur]
-                L.check(lib.rz_net_conv3x3_tc(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
-                                              L.ptr(outs[dst]), n, self.H, l['cin'], int(l['relu']),
-                                              self.n_ctas, s), 'rz_net_conv3x3_tc')
+                if self.conv_rev == 2:
+                    L.check(lib.rz_net_conv3x3_tc2(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
+                                                   L.ptr(outs[dst]), n, self.H, l['cin'], int(l['relu']),
+                                                   2, 0, self.n_ctas, s), 'rz_net_conv3x3_tc2')
+                else:
+                    L.check(lib.rz_net_conv3x3_tc(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
+                                                  L.ptr(outs[dst]), n, self.H, l['cin'], int(l['relu']),
+                                                  self.n_ctas, s), 'rz_net_conv3x3_tc')
                 cur = dst
             L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(outs[cur]), 1, L.ptr(logp), L.ptr(value), n, s),
                     'rz_net_heads')

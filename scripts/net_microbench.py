@@ -46,6 +46,14 @@ def main():
     flops_issued = 2.0 * B * 256 * 128 * 128 * 9
     print(json.dumps({'kernel': 'conv3x3_tc', 'B': B, 'ms': ms, 'TFLOPs_algorithmic': flops_alg / ms / 1e9,
                       'TFLOPs_issued': flops_issued / ms / 1e9}))
+    z = nf.bufs[1]
+    for name, res in (('conv3x3_tc2', None), ('conv3x3_tc2+residual', z)):
+        def conv2():
+            L.check(lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), L.ptr(y), B, H,
+                                           128, 1, 2, 0, ctas, L.stream_ptr()))
+        ms = timeit(conv2)
+        print(json.dumps({'kernel': name, 'B': B, 'ms': ms, 'TFLOPs_algorithmic': flops_alg / ms / 1e9,
+                          'TFLOPs_issued': flops_issued / ms / 1e9}))
 
     def heads():
         L.check(lib.rz_net_heads(nf.hdesc, L.ptr(x), 1, L.ptr(nf.logp), L.ptr(nf.value), B, L.stream_ptr()))

@@ -24,9 +24,10 @@ def _from_tile(t, h):
     return t.reshape(n, 16, 16, c)[:, :h, :h, :].permute(0, 3, 1, 2).float()
 
 
+@pytest.mark.parametrize('rev', ['v1', 'v2_pair', 'v2_single'])
 @pytest.mark.parametrize('n,h,cin,relu,res', [(1, 15, 128, 1, 0), (3, 15, 128, 1, 1), (5, 9, 64, 0, 0),
                                               (300, 15, 128, 1, 1), (2, 3, 64, 1, 0), (37, 15, 64, 1, 0)])
-def test_conv3x3_tc_matches_torch(n, h, cin, relu, res):
+def test_conv3x3_tc_matches_torch(n, h, cin, relu, res, rev):
     from rlzero_b200 import _lib as L
     lib = L.load()
     torch.manual_seed(n * 100 + h)
@@ -47,8 +48,13 @@ def test_conv3x3_tc_matches_torch(n, h, cin, relu, res):
     if res:
         out.copy_(_to_tile(r))   # residual aliases the output buffer, as in the trunk
         rt = out
-    L.check(lib.rz_net_conv3x3_tc(L.ptr(xt), L.ptr(wt), L.ptr(b.contiguous()), L.ptr(rt), L.ptr(out),
-                                  n, h, cin, relu, 0, L.stream_ptr()), 'conv')
+    if rev == 'v1':
+        L.check(lib.rz_net_conv3x3_tc(L.ptr(xt), L.ptr(wt), L.ptr(b.contiguous()), L.ptr(rt), L.ptr(out),
+                                      n, h, cin, relu, 0, L.stream_ptr()), 'conv')
+    else:
+        L.check(lib.rz_net_conv3x3_tc2(L.ptr(xt), L.ptr(wt), L.ptr(b.contiguous()), L.ptr(rt), L.ptr(out),
+                                       n, h, cin, relu, 2 if rev == 'v2_pair' else 1, 0, 0, L.stream_ptr()),
+                'conv2')
     torch.cuda.synchronize()
     got = _from_tile(out, h).double()
     err = (got - ref).abs().max().item()
