@@ -238,6 +238,16 @@ int rz_net_conv3x3_tc(const void* act_in, const void* weight, const float* bias,
 int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias, const void* residual,
                        void* act_out, int n_boards, int board_size, int c_in, int relu, int cta_group,
                        int flags, int n_ctas, void* stream);
+/* fused current_state (gomoku_env.py:95-114) + first trunk convolution (policy_value_net.py:14,36):
+   the 36-wide im2col row of every position (k = tap*4 + plane) is built from the bitboards in
+   registers, so the observation planes never exist in HBM.  weight bf16 [128][64] (k padded with
+   zeros from 36), bias f32 [128], act_out bf16 [n][256][128] tile layout. */
+int rz_net_stem_tc(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta, const void* weight,
+                   const float* bias, void* act_out, int n_boards, int relu, int n_ctas, void* stream);
+/* the same kernel fed from float32 observation planes [n][4][H][W] (the current_state format,
+   AlphaZeroAgent.policy_value / predict, alphazero_agent.py:48-57,88-97); planes are rounded to bf16. */
+int rz_net_stem_tc_planes(const rz_game_desc* g, const float* planes, const void* weight, const float* bias,
+                          void* act_out, int n_boards, int relu, int n_ctas, void* stream);
 /* the same operator in float32 on CUDA cores for the reference's stock network at any board size:
    in [n][HW][c_in], weight [9][c_in][c_out], out [n][HW][c_out] (channels last). */
 int rz_net_conv3x3_f32(const float* in, const float* weight, const float* bias, const float* residual,

@@ -75,6 +75,13 @@ struct HeadsParams {
   int n_boards, H, A, AS;
 };
 
+// 256-bit read-only global load: one full 32-byte sector per lane (sm_100 LDG.E.256)
+__device__ __forceinline__ void rz_ld_global_nc_v8(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+
 // 6 dot products of one position's 128 channels with the 1x1 filters in shared memory
 template <bool kTile>
 __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos, int H,
@@ -82,16 +89,19 @@ __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos
   const float4* w4 = reinterpret_cast<const float4*>(s_w);
   if constexpr (kTile) {
     const int y = pos / H, x = pos - y * H;
-    const uint4* src = reinterpret_cast<const uint4*>(
-        reinterpret_cast<const __nv_bfloat16*>(act) + ((size_t)b * 256 + y * 16 + x) * HEAD_C);
-#pragma unroll 4
-    for (int j = 0; j < HEAD_C / 8; ++j) {
-      const uint4 q = src[j];
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(act) + ((size_t)b * 256 + y * 16 + x) * HEAD_C;
+    uint32_t raw[8][8];  // the whole row: 8 x 32 B, all loads in flight before the first use
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rz_ld_global_nc_v8(src + j * 16, raw[j]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
       float v[8];
-      v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
-      v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
-      v[4] = __uint_as_float(q.z << 16); v[5] = __uint_as_float(q.z & 0xffff0000u);
-      v[6] = __uint_as_float(q.w << 16); v[7] = __uint_as_float(q.w & 0xffff0000u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t q = raw[j >> 1][(j & 1) * 4 + e];
+        v[2 * e] = __uint_as_float(q << 16);
+        v[2 * e + 1] = __uint_as_float(q & 0xffff0000u);
+      }
 #pragma unroll
       for (int f = 0; f < 6; ++f) {
         const float4 wa = w4[f * (HEAD_C / 4) + j * 2], wb = w4[f * (HEAD_C / 4) + j * 2 + 1];
@@ -152,32 +162,30 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
       const float* wcol = p.wp + j;
       const float4* f4 = reinterpret_cast<const float4*>(s_f);
       const int K = 4 * HW;
-      int k = 0;
-      for (; k + 4 <= K; k += 4) {
-        float w[4];
+      constexpr int PF = 8;  // weights of the next 8 k are in flight while 8 x NB FMAs run
+      float wn[PF];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = wcol[(size_t)(k + u) * p.AS];
+      for (int u = 0; u < PF; ++u) wn[u] = u < K ? wcol[(size_t)u * p.AS] : 0.0f;
+      for (int k = 0; k < K; k += PF) {
+        float w[PF];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-          for (int g = 0; g < HEAD_NB / 4; ++g) {
-            const float4 f = f4[(k + u) * (HEAD_NB / 4) + g];
-            acc[g * 4 + 0] = fmaf(f.x, w[u], acc[g * 4 + 0]);
-            acc[g * 4 + 1] = fmaf(f.y, w[u], acc[g * 4 + 1]);
-            acc[g * 4 + 2] = fmaf(f.z, w[u], acc[g * 4 + 2]);
-            acc[g * 4 + 3] = fmaf(f.w, w[u], acc[g * 4 + 3]);
-          }
+        for (int u = 0; u < PF; ++u) {
+          w[u] = wn[u];
+          const int kn = k + PF + u;
+          wn[u] = kn < K ? wcol[(size_t)kn * p.AS] : 0.0f;
         }
-      }
-      for (; k < K; ++k) {
-        const float w = wcol[(size_t)k * p.AS];
 #pragma unroll
-        for (int g = 0; g < HEAD_NB / 4; ++g) {
-          const float4 f = f4[k * (HEAD_NB / 4) + g];
-          acc[g * 4 + 0] = fmaf(f.x, w, acc[g * 4 + 0]);
-          acc[g * 4 + 1] = fmaf(f.y, w, acc[g * 4 + 1]);
-          acc[g * 4 + 2] = fmaf(f.z, w, acc[g * 4 + 2]);
-          acc[g * 4 + 3] = fmaf(f.w, w, acc[g * 4 + 3]);
+        for (int u = 0; u < PF; ++u) {
+          if (k + u < K) {
+#pragma unroll
+            for (int g = 0; g < HEAD_NB / 4; ++g) {
+              const float4 f = f4[(k + u) * (HEAD_NB / 4) + g];
+              acc[g * 4 + 0] = fmaf(f.x, w[u], acc[g * 4 + 0]);
+              acc[g * 4 + 1] = fmaf(f.y, w[u], acc[g * 4 + 1]);
+              acc[g * 4 + 2] = fmaf(f.z, w[u], acc[g * 4 + 2]);
+              acc[g * 4 + 3] = fmaf(f.w, w[u], acc[g * 4 + 3]);
+            }
+          }
         }
       }
     }
@@ -190,11 +198,26 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
     const float bo = p.bv1[o];
     float a0 = bo, a1 = bo, a2 = bo, a3 = bo;
     const float4* f4 = reinterpret_cast<const float4*>(s_f + (size_t)4 * HW * HEAD_NB);
-#pragma unroll 4
-    for (int k = 0; k < 2 * HW; ++k) {
-      const float w = p.wv1[k * 64 + o];
-      const float4 f = f4[k * (HEAD_NB / 4) + g];
-      a0 = fmaf(f.x, w, a0); a1 = fmaf(f.y, w, a1); a2 = fmaf(f.z, w, a2); a3 = fmaf(f.w, w, a3);
+    const int K = 2 * HW;
+    constexpr int PF = 8;
+    float wn[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) wn[u] = u < K ? p.wv1[u * 64 + o] : 0.0f;
+    for (int k = 0; k < K; k += PF) {
+      float w[PF];
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        w[u] = wn[u];
+        const int kn = k + PF + u;
+        wn[u] = kn < K ? p.wv1[kn * 64 + o] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (k + u < K) {
+          const float4 f = f4[(k + u) * (HEAD_NB / 4) + g];
+          a0 = fmaf(f.x, w[u], a0); a1 = fmaf(f.y, w[u], a1); a2 = fmaf(f.z, w[u], a2); a3 = fmaf(f.w, w[u], a3);
+        }
+      }
     }
     s_h[(g * 4 + 0) * 64 + o] = fmaxf(a0, 0.0f);
     s_h[(g * 4 + 1) * 64 + o] = fmaxf(a1, 0.0f);

@@ -1,0 +1,232 @@
+// rlzero_b200 -- fused observation encoder + first (stem) convolution of the trunk.
+//
+// Reference ops: GomokuEnv.current_state (rlzero/games/gomoku/gomoku_env.py:95-114) followed by
+// the first nn.Conv2d(4, C, 3, padding=1) + ReLU of the trunk
+// (rlzero/games/gomoku/policy_value_net.py:14,36; stem of the ResNet-N trunk).
+//
+// The 4 observation planes are bits, so the im2col row of a position (9 taps x 4 planes = 36
+// values, padded to K = 64) is built straight from the bitboards in registers and written to
+// shared memory in the 128-byte-swizzled K-major layout tcgen05.mma reads; the planes never
+// exist in HBM.  One 128 x 128 x 64 MMA group per 128 positions, epilogue as in rz_net_tc2.cu
+// (TMEM -> +bias -> ReLU -> pad mask -> bf16 -> staged tile -> TMA store).  The kernel is bound
+// by its 64 KB/board output write; several CTAs per SM overlap build / MMA / drain phases.
+#include <cuda_bf16.h>
+
+#include "rz_common.cuh"
+#include "rz_tc.cuh"
+
+namespace {
+
+constexpr int STEM_THREADS = 128;
+constexpr int OFF_B = 0;                 // [128 cout][64 k] bf16, SW128
+constexpr int OFF_A = 16384;             // [128 pos][64 k] bf16, SW128
+constexpr int OFF_STAGE = 32768;         // 2 x [128 pos][64 cout] bf16, SW128
+constexpr int OFF_CTRL = 65536;
+constexpr int STEM_SMEM = OFF_CTRL + 1024 + 1024;   // + alignment slack
+
+struct StemParams {
+  const uint32_t* rows;   // [n][2][H]
+  const int32_t* meta;    // [n][RZ_META_STRIDE]
+  const float* planes;    // kPlanes: [n][4][H][H] float observation planes instead of bitboards
+  const float* bias;      // [128]
+  int n_tiles;            // 2 per board
+  int H;
+  int relu;
+};
+
+template <bool kPlanes>
+__global__ void __launch_bounds__(STEM_THREADS)
+rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
+                  const StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (rz::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* al = smem_raw + (base - rz::smem_u32(smem_raw));
+  const uint32_t bar_w = base + OFF_CTRL, bar_mma = base + OFF_CTRL + 8;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(al + OFF_CTRL + 16);
+  uint32_t* s_rows = reinterpret_cast<uint32_t*>(al + OFF_CTRL + 32);    // [2][16] + 4 meta words
+  float* s_bias = reinterpret_cast<float*>(al + OFF_CTRL + 256);         // [128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.H;
+
+  if (tid == 0) {
+    rz::tma_prefetch_desc(&tmap_w);
+    rz::tma_prefetch_desc(&tmap_out);
+    rz::mbar_init(bar_w, 1);
+    rz::mbar_init(bar_mma, 1);
+    rz::fence_barrier_init();
+    rz::mbar_expect_tx(bar_w, 16384);
+    rz::tma_load_2d(base + OFF_B, &tmap_w, bar_w, 0, 0);
+  }
+  if (warp == 0) { rz::tmem_alloc(rz::smem_u32(tmem_holder), 128); rz::tmem_relinquish(); }
+  s_bias[tid] = p.bias[tid];
+  rz::tc_fence_before();
+  __syncthreads();
+  rz::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  constexpr uint32_t idesc = rz::umma_idesc_bf16(128, 128);
+  constexpr uint32_t ONE = 0x3F80u;  // bf16 1.0
+
+  uint32_t phase = 0;
+  bool store_pending = false;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int b = tile >> 1;
+    // ---- board of this tile -> shared memory (rows beyond H are zero)
+    if (!kPlanes) {
+      if (tid < 32) {
+        const int c = tid >> 4, y = tid & 15;
+        s_rows[tid] = (y < H) ? p.rows[((size_t)b * 2 + c) * H + y] : 0u;
+      } else if (tid < 36) {
+        const int k = tid - 32;  // player, last_move, stones
+        s_rows[32 + k] = (uint32_t)p.meta[(size_t)b * RZ_META_STRIDE + k];
+      }
+    }
+    if (tid == 0 && store_pending) rz::tma_store_wait_read();  // staging tile free again
+    __syncthreads();
+    // ---- im2col row of position r: k = tap*4 + plane (gomoku_env.py:95-114 per tap)
+    {
+      const int pos = (tile & 1) * 128 + tid;
+      const int y = pos >> 4, x = pos & 15;
+      const int player = (int)s_rows[32] & 1, last = (int)s_rows[33], stones = (int)s_rows[34];
+      const uint32_t colour = (stones & 1) ? 0u : ONE;
+      const bool out_inside = (x < H) && (y < H);
+      uint32_t w[20];  // 5 chunks x 4 words (2 bf16 each): taps 0..8 (+ one empty tap slot)
+#pragma unroll
+      for (int i = 0; i < 20; ++i) w[i] = 0u;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        const bool in = out_inside && yy >= 0 && yy < H && xx >= 0 && xx < H;
+        uint32_t f0 = 0u, f1 = 0u, f2 = 0u, f3 = 0u;
+        if (kPlanes) {
+          if (in) {
+            const float* src = p.planes + (size_t)b * 4 * H * H + yy * H + xx;
+            f0 = __bfloat16_as_ushort(__float2bfloat16_rn(src[0]));
+            f1 = __bfloat16_as_ushort(__float2bfloat16_rn(src[H * H]));
+            f2 = __bfloat16_as_ushort(__float2bfloat16_rn(src[2 * H * H]));
+            f3 = __bfloat16_as_ushort(__float2bfloat16_rn(src[3 * H * H]));
+          }
+        } else {
+          const uint32_t mine = s_rows[player * 16 + (yy & 15)], theirs = s_rows[(player ^ 1) * 16 + (yy & 15)];
+          f0 = in ? ((mine >> (xx & 31)) & 1u) * ONE : 0u;
+          f1 = in ? ((theirs >> (xx & 31)) & 1u) * ONE : 0u;
+          f2 = (in && stones > 0 && last == yy * H + xx) ? ONE : 0u;
+          f3 = in ? colour : 0u;
+        }
+        w[tap * 2 + 0] = f0 | (f1 << 16);
+        w[tap * 2 + 1] = f2 | (f3 << 16);
+      }
+      const uint32_t arow = base + OFF_A + (uint32_t)tid * 128u;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t dst = arow + (((uint32_t)c ^ ((uint32_t)tid & 7u)) << 4);
+        if (c < 5) rz::st_shared_v4(dst, w[c * 4], w[c * 4 + 1], w[c * 4 + 2], w[c * 4 + 3]);
+        else       rz::st_shared_v4(dst, 0u, 0u, 0u, 0u);
+      }
+    }
+    rz::fence_proxy_async();
+    rz::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      rz::tc_fence_after();
+      if (phase == 0) rz::mbar_wait(bar_w, 0);
+      const uint64_t adesc = rz::umma_desc_sw128(base + OFF_A), bdesc = rz::umma_desc_sw128(base + OFF_B);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        rz::umma_bf16(tmem_base, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk > 0 ? 1u : 0u);
+      rz::umma_commit(bar_mma);
+    }
+    rz::mbar_wait(bar_mma, phase & 1u);
+    rz::tc_fence_after();
+    // ---- epilogue: row per thread
+    {
+      const int pos = (tile & 1) * 128 + tid;
+      const bool valid = ((pos & 15) < H) && ((pos >> 4) < H);
+      const uint32_t stage_row = base + OFF_STAGE + (uint32_t)tid * 128u;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t acc[32];
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 32), acc);
+        rz::tmem_ld_wait();
+        const uint32_t srow = stage_row + (uint32_t)(ch >> 1) * 16384u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = j * 8 + e * 2;
+            float v0 = __uint_as_float(acc[c]) + s_bias[ch * 32 + c];
+            float v1 = __uint_as_float(acc[c + 1]) + s_bias[ch * 32 + c + 1];
+            if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+            if (!valid) { v0 = 0.0f; v1 = 0.0f; }
+            const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
+            packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
+          }
+          const uint32_t chunk = (uint32_t)((ch & 1) * 4 + j);
+          rz::st_shared_v4(srow + ((chunk ^ ((uint32_t)tid & 7u)) << 4), packed[0], packed[1], packed[2], packed[3]);
+        }
+      }
+    }
+    rz::fence_proxy_async();
+    rz::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      rz::tma_store_2d(&tmap_out, base + OFF_STAGE, 0, tile * 128);
+      rz::tma_store_2d(&tmap_out, base + OFF_STAGE + 16384, 64, tile * 128);
+      rz::tma_store_commit();
+    }
+    store_pending = true;
+    ++phase;
+  }
+  if (tid == 0 && store_pending) rz::tma_store_wait_all();
+  rz::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { rz::tc_fence_after(); rz::tmem_dealloc(tmem_base, 128); }
+}
+
+}  // namespace
+
+static int stem_launch(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta, const float* planes,
+                       const void* weight, const float* bias, void* act_out, int n_boards, int relu,
+                       int n_ctas, void* stream) {
+  if (n_boards == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rz_stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(rz_stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e != cudaSuccess) { rz_set_error("rz_net_stem_tc: smem attribute: %s", cudaGetErrorString(e)); return -2; }
+    attr_set = true;
+  }
+  CUtensorMap tmap_w, tmap_out;
+  if (rz::make_tmap_2d(&tmap_w, weight, 128, 64, 128)) return -1;
+  if (rz::make_tmap_2d(&tmap_out, act_out, (uint64_t)n_boards * 256, 128, 128)) return -1;
+  StemParams p;
+  p.rows = rows; p.meta = meta; p.planes = planes; p.bias = bias;
+  p.n_tiles = n_boards * 2; p.H = g->board_size; p.relu = relu;
+  int ctas = n_ctas > 0 ? n_ctas : 148 * 3;
+  if (ctas > p.n_tiles) ctas = p.n_tiles;
+  if (planes) rz_stem_tc_kernel<true><<<ctas, STEM_THREADS, STEM_SMEM, (cudaStream_t)stream>>>(tmap_w, tmap_out, p);
+  else        rz_stem_tc_kernel<false><<<ctas, STEM_THREADS, STEM_SMEM, (cudaStream_t)stream>>>(tmap_w, tmap_out, p);
+  RZ_LAUNCH_CHECK("rz_net_stem_tc");
+  return 0;
+}
+
+extern "C" int rz_net_stem_tc(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
+                              const void* weight, const float* bias, void* act_out, int n_boards,
+                              int relu, int n_ctas, void* stream) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(rows && meta && weight && bias && act_out, "rz_net_stem_tc: null argument");
+  RZ_REQUIRE(g->board_size <= 15, "rz_net_stem_tc: the 16x16 tile layout holds boards up to 15x15");
+  RZ_REQUIRE(n_boards >= 0, "rz_net_stem_tc: n_boards %d", n_boards);
+  return stem_launch(g, rows, meta, nullptr, weight, bias, act_out, n_boards, relu, n_ctas, stream);
+}
+
+extern "C" int rz_net_stem_tc_planes(const rz_game_desc* g, const float* planes, const void* weight,
+                                     const float* bias, void* act_out, int n_boards, int relu, int n_ctas,
+                                     void* stream) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(planes && weight && bias && act_out, "rz_net_stem_tc_planes: null argument");
+  RZ_REQUIRE(g->board_size <= 15, "rz_net_stem_tc_planes: the 16x16 tile layout holds boards up to 15x15");
+  RZ_REQUIRE(n_boards >= 0, "rz_net_stem_tc_planes: n_boards %d", n_boards);
+  return stem_launch(g, nullptr, nullptr, planes, weight, bias, act_out, n_boards, relu, n_ctas, stream);
+}

@@ -182,12 +182,13 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       const int pos = (int)(row & 255);
       const bool valid = ((pos & 15) < p.board) && ((pos >> 4) < p.board);
       // residual row: issued before the accumulator is ready, so its latency hides behind the MMAs
-      uint4 res[NCH * 4];
+      // (256-bit loads: each lane fetches whole 32-byte sectors of its row, no sector is read twice)
+      uint32_t res[NCH * 2][8];
       const bool have_res = p.residual != nullptr && valid;
       if (have_res) {
-        const uint4* rrow = reinterpret_cast<const uint4*>(p.residual + row * 128 + col_base);
+        const __nv_bfloat16* rrow = p.residual + row * 128 + col_base;
 #pragma unroll
-        for (int j = 0; j < NCH * 4; ++j) res[j] = rrow[j];
+        for (int j = 0; j < NCH * 2; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
       }
       rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
       rz::tc_fence_after();
@@ -218,7 +219,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
             float v0 = __uint_as_float(acc[c]) + s_bias[col_base + ch * 32 + c];
             float v1 = __uint_as_float(acc[c + 1]) + s_bias[col_base + ch * 32 + c + 1];
             if (have_res) {
-              const uint32_t rw = (&res[ch * 4 + j].x)[e];
+              const uint32_t rw = res[ch * 2 + (j >> 1)][(j & 1) * 4 + e];
               v0 += __uint_as_float(rw << 16);
               v1 += __uint_as_float(rw & 0xffff0000u);
             }

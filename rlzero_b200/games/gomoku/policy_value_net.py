@@ -135,7 +135,7 @@ class NativeForward(object):
     graph_capturable = True
     prior_is_log = True       # the network emits log-probabilities (policy_value_net.py:44)
 
-    def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0, conv_rev=2):
+    def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0, conv_rev=2, fused_stem=True):
         if not torch.cuda.is_available():
             raise L.NativeLibraryError('NativeForward needs a CUDA device (no CPU fallback)')
         self.lib = L.load()
@@ -152,6 +152,7 @@ class NativeForward(object):
             raise ValueError("mode 'tc' needs a 128-channel trunk and board_size <= 15")
         self.mode = mode
         self.n_ctas = int(n_ctas)
+        self.fused_stem = bool(fused_stem)  # encoder + first conv in one kernel (rz_net_stem.cu)
         self.conv_rev = int(conv_rev)   # 2: resident weights + CTA pairs (rz_net_tc2.cu); 1: rz_net_tc.cu
         self.max_batch = 0
         self.refresh_weights()
@@ -176,6 +177,15 @@ class NativeForward(object):
                 wd = w.permute(2, 3, 1, 0).reshape(9, cin, cout).float().contiguous().to(dev)  # [tap][cin][cout]
             self.layers.append(dict(w=wd, b=b.float().contiguous().to(dev), cin=cin_p, cout=cout,
                                     skip=skip, relu=bool(relu)))
+        # fused encoder + stem (rz_net_stem.cu): weight [cout][k = tap*4 + plane], k padded to 64
+        self.stem = None
+        conv0 = m.trunk_layers()[0][0]
+        if self.mode == 'tc' and conv0.in_channels == 4 and m.trunk_layers()[0][1] is None:
+            w0, b0 = _fold_bn(conv0, None)
+            ws = torch.zeros(128, 64, dtype=torch.float64)
+            ws[:, :36] = w0.permute(0, 2, 3, 1).reshape(128, 36)      # [cout][kh][kw][plane]
+            self.stem = dict(w=ws.to(torch.bfloat16).contiguous().to(dev), b=b0.float().contiguous().to(dev),
+                             relu=bool(m.trunk_layers()[0][3]))
         hw, AS = self.A, self.AS
         f32 = torch.float32
         w1 = torch.cat([m.act_conv1.weight.detach().reshape(4, 128), m.val_conv1.weight.detach().reshape(2, 128)])
@@ -217,14 +227,16 @@ class NativeForward(object):
     def _gdesc(self, k=5):
         return L.GameDesc(self.H, min(k, self.H), self.A, self.AS)
 
-    def _trunk_and_heads(self, n, logp, value):
+    def _trunk_and_heads(self, n, logp, value, stem_done=False):
         s = L.stream_ptr()
         lib = self.lib
         if self.mode == 'tc':
             # ping-pong: the residual of a block is the buffer its second conv overwrites
             src, outs = self.act0, self.bufs
-            cur = -1   # index in outs holding the latest activation, -1 = act0
+            cur = 0 if stem_done else -1   # index in outs holding the latest activation, -1 = act0
             for i, l in enumerate(self.layers):
+                if stem_done and i == 0:
+                    continue
                 dst = 0 if cur != 0 else 1
                 res = None
                 if l['skip'] is not None:
@@ -266,13 +278,20 @@ class NativeForward(object):
         logp = self.logp if logp is None else logp
         value = self.value if value is None else value
         g = self._gdesc()
-        if self.mode == 'tc':
+        stem_done = False
+        if self.mode == 'tc' and self.stem is not None and self.fused_stem:
+            st = self.stem
+            L.check(self.lib.rz_net_stem_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(st['w']), L.ptr(st['b']),
+                                            L.ptr(self.bufs[0]), n, int(st['relu']), 0, L.stream_ptr()),
+                    'rz_net_stem_tc')
+            stem_done = True
+        elif self.mode == 'tc':
             L.check(self.lib.rz_gomoku_encode_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(self.act0), n,
                                                  L.stream_ptr()), 'rz_gomoku_encode_tc')
         else:
             L.check(self.lib.rz_gomoku_encode_nhwc_f32(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(self.act0),
                                                        n, L.stream_ptr()), 'rz_gomoku_encode_nhwc_f32')
-        self._trunk_and_heads(n, logp, value)
+        self._trunk_and_heads(n, logp, value, stem_done)
         return logp[:n], value[:n]
 
     def forward_planes(self, planes):
@@ -282,13 +301,23 @@ class NativeForward(object):
         x = torch.as_tensor(planes, dtype=torch.float32, device=self.device)
         n = x.shape[0]
         self._alloc(n)
-        if self.mode == 'tc':
+        stem_done = False
+        if self.mode == 'tc' and self.stem is not None and self.fused_stem:
+            # same kernel (and therefore bit-identical stem outputs) as forward_boards
+            st = self.stem
+            xc = x.contiguous()
+            g = self._gdesc()
+            L.check(self.lib.rz_net_stem_tc_planes(C.byref(g), L.ptr(xc), L.ptr(st['w']), L.ptr(st['b']),
+                                                   L.ptr(self.bufs[0]), n, int(st['relu']), 0, L.stream_ptr()),
+                    'rz_net_stem_tc_planes')
+            stem_done = True
+        elif self.mode == 'tc':
             self.act0[:n].zero_()
             t = self.act0[:n].view(n, 16, 16, 64)
             t[:, :self.H, :self.H, :4] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
         else:
             self.act0[:n] = x.permute(0, 2, 3, 1).reshape(n, self.A, 4)
-        self._trunk_and_heads(n, self.logp, self.value)
+        self._trunk_and_heads(n, self.logp, self.value, stem_done)
         return self.logp[:n, :self.A], self.value[:n]
 
     def __call__(self, forest):

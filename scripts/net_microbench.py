@@ -62,6 +62,15 @@ def main():
     meta = torch.zeros(B, 8, dtype=torch.int32, device='cuda')
     meta[:, 1] = -1
 
+    import ctypes as C
+    g = nf._gdesc()
+    st = nf.stem
+
+    def stem():
+        L.check(lib.rz_net_stem_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(st['w']), L.ptr(st['b']), L.ptr(y), B,
+                                   1, 0, L.stream_ptr()))
+    print(json.dumps({'kernel': 'stem_fused', 'ms': timeit(stem)}))
+
     def fwd():
         nf.forward_boards(rows, meta, B)
     ms = timeit(fwd, iters=5, warm=2)

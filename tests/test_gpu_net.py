@@ -198,3 +198,63 @@ def test_agent_api_shapes():
     assert np.isfinite(loss) and np.isfinite(ent)
     probs2, _ = agent.predict(np.array([env.current_state()]))
     assert not np.allclose(probs2[0], probs[0])   # weights were refreshed after the step
+
+
+@pytest.mark.parametrize('size,n', [(15, 70), (9, 33), (6, 5)])
+def test_fused_stem_matches_encode_plus_conv(size, n):
+    """rz_net_stem_tc (planes built from the bitboards inside the kernel, K = 36) against
+    rz_gomoku_encode_tc + the generic convolution, and against PyTorch on current_state planes."""
+    from oracle import pyoracle
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.games.gomoku.gomoku_env import GomokuEnv
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(size)
+    net = ResNetPolicyValueNet(size, n_blocks=1).cuda().eval()
+    rs = np.random.RandomState(size)
+    envs = []
+    for i in range(n):
+        e = GomokuEnv(size, min(5, size))
+        e.reset()
+        for m in rs.permutation(size * size)[:(0 if i == 0 else rs.randint(0, size * size - 1))]:
+            e.step(int(m))
+            if e.game_end_winner()[0]:
+                break
+        envs.append(e)
+    rows = torch.cat([e.device_state()[0] for e in envs]).cuda()
+    meta = torch.cat([e.device_state()[1] for e in envs]).cuda()
+    nf = NativeForward(net, max_batch=n)
+    lib, g = L.load(), nf._gdesc()
+    st = nf.stem
+    fused = torch.full((n, 256, 128), 3.0, dtype=torch.bfloat16, device='cuda')
+    L.check(lib.rz_net_stem_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(st['w']), L.ptr(st['b']), L.ptr(fused),
+                               n, 1, 0, L.stream_ptr()), 'stem')
+    act0 = torch.zeros(n, 256, 64, dtype=torch.bfloat16, device='cuda')
+    L.check(lib.rz_gomoku_encode_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(act0), n, L.stream_ptr()), 'enc')
+    l0 = nf.layers[0]
+    plain = torch.full((n, 256, 128), 5.0, dtype=torch.bfloat16, device='cuda')
+    L.check(lib.rz_net_conv3x3_tc2(L.ptr(act0), L.ptr(l0['w']), L.ptr(l0['b']), None, L.ptr(plain), n, size, 64, 1,
+                                   2, 0, 0, L.stream_ptr()), 'conv')
+    torch.cuda.synchronize()
+    # same bf16 products, fp32 accumulation in a different order: equal up to one bf16 ulp
+    d = (fused.float() - plain.float()).abs()
+    assert d.max().item() <= 2.0 ** -7 * max(1.0, plain.float().abs().max().item())
+    assert (d == 0).float().mean().item() > 0.98
+    full = fused.reshape(n, 16, 16, 128).float()
+    assert full[:, size:].abs().max().item() == 0.0 and full[:, :, size:].abs().max().item() == 0.0
+    # against PyTorch on the reference's observation planes (weights rounded to bf16 like the kernel's)
+    planes = torch.tensor(np.stack([e.current_state() for e in envs]), dtype=torch.float32, device='cuda')
+    wq = net.stem.weight.detach().to(torch.bfloat16).float()
+    ref = torch.relu(torch.nn.functional.conv2d(planes, wq, net.stem.bias.detach(), padding=1))
+    got = _from_tile(fused, size)
+    assert (got - ref).abs().max().item() <= 2.0 ** -8 * max(1.0, ref.abs().max().item()) + 1e-6
+    # and the whole forward through both routes
+    lp1, v1 = nf.forward_boards(rows, meta, n)
+    lp1, v1 = lp1.clone(), v1.clone()
+    nf2 = NativeForward(net, max_batch=n, fused_stem=False)
+    lp2, v2 = nf2.forward_boards(rows, meta, n)
+    assert (lp1[:, :size * size] - lp2[:, :size * size]).abs().max().item() < 2e-3
+    assert (v1 - v2).abs().max().item() < 2e-3
+    # the planes-fed variant of the kernel (AlphaZeroAgent.policy_value_fn on a host env) is
+    # bit-identical to the bitboard-fed one: search parity with a Python-side evaluator relies on it
+    lp3, v3 = nf.forward_planes(planes.cpu().numpy())
+    assert torch.equal(lp3[:, :size * size], lp1[:, :size * size]) and torch.equal(v3, v1)
