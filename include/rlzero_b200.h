@@ -213,9 +213,9 @@ typedef struct rz_heads_desc {
   int32_t action_stride;         /* AS: row stride of wp / logp */
   const float* w1x1;             /* [6][128]  act_conv1 (4 filters) then val_conv1 (2 filters) */
   const float* b1x1;             /* [6] */
-  const float* wp;               /* [4*HW][AS] act_fc1.weight^T, zero padded */
+  const float* wp;               /* [4*HW + 4][AS] act_fc1.weight^T, zero padded (columns >= HW and the 4 extra rows) */
   const float* bp;               /* [AS] */
-  const float* wv1;              /* [2*HW][64] val_fc1.weight^T */
+  const float* wv1;              /* [2*HW + 2][64] val_fc1.weight^T + 2 zero rows */
   const float* bv1;              /* [64] */
   const float* wv2;              /* [64]       val_fc2.weight */
   const float* bv2;              /* [1] */
@@ -238,6 +238,13 @@ int rz_net_conv3x3_tc(const void* act_in, const void* weight, const float* bias,
 int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias, const void* residual,
                        void* act_out, int n_boards, int board_size, int c_in, int relu, int cta_group,
                        int flags, int n_ctas, void* stream);
+/* the last trunk layer with the heads' two 1x1 convolutions + ReLU (act_conv1 128->4, val_conv1 128->2,
+   policy_value_net.py:41,47) applied in its epilogue: writes ONLY feat f32 [n][6][256] (filter, then
+   position p = y*16+x); the trunk output never reaches HBM.  w1x1_host [6][128] / b1x1_host [6] are
+   HOST float32 arrays (copied into the launch parameters).  Feed feat to rz_net_heads(.., 2, ..). */
+int rz_net_conv3x3_tc2_head(const void* act_in, const void* weight, const float* bias, const void* residual,
+                            int n_boards, int board_size, int c_in, int relu, const float* w1x1_host,
+                            const float* b1x1_host, float* feat, int n_ctas, void* stream);
 /* fused current_state (gomoku_env.py:95-114) + first trunk convolution (policy_value_net.py:14,36):
    the 36-wide im2col row of every position (k = tap*4 + plane) is built from the bitboards in
    registers, so the observation planes never exist in HBM.  weight bf16 [128][64] (k padded with
@@ -254,8 +261,9 @@ int rz_net_conv3x3_f32(const float* in, const float* weight, const float* bias, 
                        float* out, int n_boards, int board_size, int c_in, int c_out, int relu,
                        void* stream);
 /* both heads from the 128-channel trunk output: logp f32 [n][AS] = log_softmax(policy logits)
-   (0 in the padding), value f32 [n] = tanh(...).  act is bf16 tile layout (act_is_tile_bf16 != 0)
-   or f32 [n][HW][128]. */
+   (0 in the padding), value f32 [n] = tanh(...).  act_is_tile_bf16 = 0: act is f32 [n][HW][128];
+   1: bf16 tile layout [n][256][128]; 2: act is the f32 [n][6][256] feature tensor written by
+   rz_net_conv3x3_tc2_head (the 1x1 convolutions are already applied). */
 int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_tile_bf16, float* logp,
                  float* value, int n_boards, void* stream);
 

@@ -64,9 +64,9 @@ struct HeadsParams {
   const void* act;        // trunk output: bf16 [B][256][128] (tile layout) or fp32 [B][HW][128]
   const float* w1x1;      // [6][128]: 4 policy + 2 value 1x1 filters
   const float* b1x1;      // [6]
-  const float* wp;        // [4*HW][AS] policy FC, transposed + padded
+  const float* wp;        // [4*HW + 4][AS] policy FC, transposed + padded (4 zero rows at the end)
   const float* bp;        // [AS]
-  const float* wv1;       // [2*HW][64] value FC1, transposed
+  const float* wv1;       // [2*HW + 2][64] value FC1, transposed (2 zero rows at the end)
   const float* bv1;       // [64]
   const float* wv2;       // [64]
   const float* bv2;       // [1]
@@ -128,69 +128,130 @@ __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos
   }
 }
 
-template <bool kTile>
+// feature (k, board bi) lives at s_f[k*NB + (((bi >> 2) ^ (k & 3)) << 2) + (bi & 3)]: the XOR keeps
+// a float4 of 4 boards together (the FC loops read it as one broadcast LDS.128) while spreading
+// writers that differ only in k over 8 banks
+__device__ __forceinline__ int feat_slot(int k, int bi) {
+  return k * HEAD_NB + ((((bi >> 2) ^ (k & 3)) << 2) | (bi & 3));
+}
+
+enum { SRC_F32 = 0, SRC_TILE = 1, SRC_FEAT = 2 };
+
+template <int kSrc>
 __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsParams p) {
   extern __shared__ __align__(16) float sm[];
   const int HW = p.A;
-  float* s_w = sm;                              // [6][128]
-  float* s_f = s_w + 6 * HEAD_C;                // [6*HW][NB]  k-major features (policy 4*HW, then value 2*HW)
+  float* s_f = sm;                              // [6*HW][NB]  k-major features (policy 4*HW, then value 2*HW)
   float* s_lg = s_f + 6 * HW * HEAD_NB;         // [NB][AS]    logits
   float* s_h = s_lg + HEAD_NB * p.AS;           // [NB][64]    value hidden
+  float* s_w = s_h + HEAD_NB * 64;              // [6][128]    1x1 filters (not for SRC_FEAT)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b0 = blockIdx.x * HEAD_NB;
   const int nb = min(HEAD_NB, p.n_boards - b0);
-  for (int i = tid; i < 6 * HEAD_C; i += HEAD_THREADS) s_w[i] = p.w1x1[i];
-  __syncthreads();
-  // phase 1: 1x1 convolutions + ReLU  (policy_value_net.py:41, 47); boards beyond nb hold zeros
-  for (int i = tid; i < HEAD_NB * HW; i += HEAD_THREADS) {
-    const int bi = i % HEAD_NB, pos = i / HEAD_NB;   // board fastest: conflict-free feature stores
-    float acc[6];
+  if (kSrc == SRC_FEAT) {
+    // phase 1': the 1x1 convolutions were applied by the last trunk layer's epilogue
+    // (rz_net_conv3x3_tc2_head): gather feat[b][f][y*16+x] (coalesced along x) into k-major order
+    const float* feat = reinterpret_cast<const float*>(p.act) + (size_t)b0 * (6 * 256);
+    // iterate over the tile positions t = y*16+x of [bi][f] (coalesced), 4 loads in flight
+    for (int i0 = tid; i0 < HEAD_NB * 6 * 256; i0 += 4 * HEAD_THREADS) {
+      float v[4];
 #pragma unroll
-    for (int f = 0; f < 6; ++f) acc[f] = p.b1x1[f];
-    if (bi < nb) conv1x1_position<kTile>(p.act, b0 + bi, pos, p.H, s_w, acc);
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * HEAD_THREADS;
+        const int bi = i / (6 * 256);
+        v[u] = (i < HEAD_NB * 6 * 256 && bi < nb) ? feat[i] : 0.0f;
+      }
 #pragma unroll
-    for (int f = 0; f < 6; ++f) s_f[(f * HW + pos) * HEAD_NB + bi] = bi < nb ? fmaxf(acc[f], 0.0f) : 0.0f;
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * HEAD_THREADS;
+        const int bi = i / (6 * 256), r = i - bi * (6 * 256);
+        const int f = r >> 8, y = (r >> 4) & 15, x = r & 15;
+        if (i < HEAD_NB * 6 * 256 && x < p.H && y < p.H) s_f[feat_slot(f * HW + y * p.H + x, bi)] = v[u];
+      }
+    }
+  } else {
+    for (int i = tid; i < 6 * HEAD_C; i += HEAD_THREADS) s_w[i] = p.w1x1[i];
+    __syncthreads();
+    // phase 1: 1x1 convolutions + ReLU  (policy_value_net.py:41, 47); boards beyond nb hold zeros
+    for (int i = tid; i < HEAD_NB * HW; i += HEAD_THREADS) {
+      const int bi = i % HEAD_NB, pos = i / HEAD_NB;
+      float acc[6];
+#pragma unroll
+      for (int f = 0; f < 6; ++f) acc[f] = p.b1x1[f];
+      if (bi < nb) conv1x1_position<kSrc == SRC_TILE>(p.act, b0 + bi, pos, p.H, s_w, acc);
+#pragma unroll
+      for (int f = 0; f < 6; ++f) s_f[feat_slot(f * HW + pos, bi)] = bi < nb ? fmaxf(acc[f], 0.0f) : 0.0f;
+    }
   }
   __syncthreads();
-  // phase 2: policy FC (:43): thread j owns output column j for all NB boards
-  for (int j = tid; j < p.AS; j += HEAD_THREADS) {
-    float acc[HEAD_NB];
-    const float bj = j < p.A ? p.bp[j] : 0.0f;
+  // phase 2: policy FC (:43).  Thread (half, t): output columns t and t+128 of every 256-column
+  // group, for all NB boards, over one half of the k range: per k 2 coalesced weight loads
+  // (prefetched 4 k ahead) + NB/4 broadcast LDS.128 feed 2*NB FMAs.
+  {
+    const int khalf = tid >> 7, t = tid & 127;
+    // both halves of the k range are multiples of 4 (K = 4*HW); wp carries 4 zero rows of padding
+    // after row K-1, so the prefetch never needs a bounds check
+    const int K = 4 * HW, k_mid = (K >> 1) & ~3;
+    const int k_lo = khalf ? k_mid : 0, k_hi = khalf ? K : k_mid;
+    const float4* f4 = reinterpret_cast<const float4*>(s_f);
+    for (int jb = 0; jb < p.AS; jb += 256) {
+      const int j0 = jb + t, j1 = jb + 128 + t;
+      const bool c0 = j0 < p.A, c1 = j1 < p.A;
+      float acc0[HEAD_NB], acc1[HEAD_NB];
 #pragma unroll
-    for (int bi = 0; bi < HEAD_NB; ++bi) acc[bi] = bj;
-    if (j < p.A) {
-      const float* wcol = p.wp + j;
-      const float4* f4 = reinterpret_cast<const float4*>(s_f);
-      const int K = 4 * HW;
-      constexpr int PF = 8;  // weights of the next 8 k are in flight while 8 x NB FMAs run
-      float wn[PF];
+      for (int bi = 0; bi < HEAD_NB; ++bi) { acc0[bi] = 0.0f; acc1[bi] = 0.0f; }
+      constexpr int PF = 4;
+      const float* w0p = p.wp + (size_t)k_lo * p.AS + (c0 ? j0 : 0);
+      const float* w1p = p.wp + (size_t)k_lo * p.AS + (c1 ? j1 : 0);
+      const size_t step = (size_t)p.AS;
+      float wn0[PF], wn1[PF];
 #pragma unroll
-      for (int u = 0; u < PF; ++u) wn[u] = u < K ? wcol[(size_t)u * p.AS] : 0.0f;
-      for (int k = 0; k < K; k += PF) {
-        float w[PF];
+      for (int u = 0; u < PF; ++u) { wn0[u] = w0p[u * step]; wn1[u] = w1p[u * step]; }
+      for (int k = k_lo; k < k_hi; k += PF) {
+        float w0[PF], w1[PF];
+        w0p += PF * step;
+        w1p += PF * step;
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-          w[u] = wn[u];
-          const int kn = k + PF + u;
-          wn[u] = kn < K ? wcol[(size_t)kn * p.AS] : 0.0f;
+          w0[u] = wn0[u]; w1[u] = wn1[u];
+          wn0[u] = w0p[u * step];
+          wn1[u] = w1p[u * step];
         }
+        const float4* fk = f4 + k * (HEAD_NB / 4);
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-          if (k + u < K) {
 #pragma unroll
-            for (int g = 0; g < HEAD_NB / 4; ++g) {
-              const float4 f = f4[(k + u) * (HEAD_NB / 4) + g];
-              acc[g * 4 + 0] = fmaf(f.x, w[u], acc[g * 4 + 0]);
-              acc[g * 4 + 1] = fmaf(f.y, w[u], acc[g * 4 + 1]);
-              acc[g * 4 + 2] = fmaf(f.z, w[u], acc[g * 4 + 2]);
-              acc[g * 4 + 3] = fmaf(f.w, w[u], acc[g * 4 + 3]);
-            }
+          for (int g = 0; g < HEAD_NB / 4; ++g) {
+            const float4 f = fk[u * (HEAD_NB / 4) + (g ^ u)];   // k is a multiple of 4: (k+u) & 3 == u
+            acc0[g * 4 + 0] = fmaf(f.x, w0[u], acc0[g * 4 + 0]);
+            acc0[g * 4 + 1] = fmaf(f.y, w0[u], acc0[g * 4 + 1]);
+            acc0[g * 4 + 2] = fmaf(f.z, w0[u], acc0[g * 4 + 2]);
+            acc0[g * 4 + 3] = fmaf(f.w, w0[u], acc0[g * 4 + 3]);
+            acc1[g * 4 + 0] = fmaf(f.x, w1[u], acc1[g * 4 + 0]);
+            acc1[g * 4 + 1] = fmaf(f.y, w1[u], acc1[g * 4 + 1]);
+            acc1[g * 4 + 2] = fmaf(f.z, w1[u], acc1[g * 4 + 2]);
+            acc1[g * 4 + 3] = fmaf(f.w, w1[u], acc1[g * 4 + 3]);
           }
         }
       }
-    }
+      // the upper k half parks its partial sums in s_lg, the lower half adds its own + the bias
+      if (khalf) {
 #pragma unroll
-    for (int bi = 0; bi < HEAD_NB; ++bi) s_lg[bi * p.AS + j] = acc[bi];
+        for (int bi = 0; bi < HEAD_NB; ++bi) {
+          if (j0 < p.AS) s_lg[bi * p.AS + j0] = acc0[bi];
+          if (j1 < p.AS) s_lg[bi * p.AS + j1] = acc1[bi];
+        }
+      }
+      __syncthreads();
+      if (!khalf) {
+        const float bj0 = c0 ? p.bp[j0] : 0.0f, bj1 = c1 ? p.bp[j1] : 0.0f;
+#pragma unroll
+        for (int bi = 0; bi < HEAD_NB; ++bi) {
+          if (j0 < p.AS) s_lg[bi * p.AS + j0] = c0 ? (acc0[bi] + s_lg[bi * p.AS + j0]) + bj0 : 0.0f;
+          if (j1 < p.AS) s_lg[bi * p.AS + j1] = c1 ? (acc1[bi] + s_lg[bi * p.AS + j1]) + bj1 : 0.0f;
+        }
+      }
+    }
   }
   // phase 3a: value FC1 + ReLU (:49): thread = (output o, group of 4 boards)
   for (int i = tid; i < (HEAD_NB / 4) * 64; i += HEAD_THREADS) {
@@ -198,26 +259,19 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
     const float bo = p.bv1[o];
     float a0 = bo, a1 = bo, a2 = bo, a3 = bo;
     const float4* f4 = reinterpret_cast<const float4*>(s_f + (size_t)4 * HW * HEAD_NB);
+    // K = 2*HW is even and the value features start at k = 4*HW (a multiple of 4): unroll by 2,
+    // swizzle phase (4*HW + k) & 3 = k & 3; wv1 carries 2 zero rows of padding for the prefetch
     const int K = 2 * HW;
-    constexpr int PF = 8;
-    float wn[PF];
-#pragma unroll
-    for (int u = 0; u < PF; ++u) wn[u] = u < K ? p.wv1[u * 64 + o] : 0.0f;
-    for (int k = 0; k < K; k += PF) {
-      float w[PF];
-#pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        w[u] = wn[u];
-        const int kn = k + PF + u;
-        wn[u] = kn < K ? p.wv1[kn * 64 + o] : 0.0f;
-      }
-#pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        if (k + u < K) {
-          const float4 f = f4[(k + u) * (HEAD_NB / 4) + g];
-          a0 = fmaf(f.x, w[u], a0); a1 = fmaf(f.y, w[u], a1); a2 = fmaf(f.z, w[u], a2); a3 = fmaf(f.w, w[u], a3);
-        }
-      }
+    const float* wp1 = p.wv1 + o;
+    float wn0 = wp1[0], wn1 = wp1[64];
+    for (int k = 0; k < K; k += 2) {
+      const float w0 = wn0, w1 = wn1;
+      wp1 += 128;
+      wn0 = wp1[0]; wn1 = wp1[64];
+      const float4 fa = f4[k * (HEAD_NB / 4) + (g ^ (k & 3))];
+      const float4 fb = f4[(k + 1) * (HEAD_NB / 4) + (g ^ ((k + 1) & 3))];
+      a0 = fmaf(fa.x, w0, a0); a1 = fmaf(fa.y, w0, a1); a2 = fmaf(fa.z, w0, a2); a3 = fmaf(fa.w, w0, a3);
+      a0 = fmaf(fb.x, w1, a0); a1 = fmaf(fb.y, w1, a1); a2 = fmaf(fb.z, w1, a2); a3 = fmaf(fb.w, w1, a3);
     }
     s_h[(g * 4 + 0) * 64 + o] = fmaxf(a0, 0.0f);
     s_h[(g * 4 + 1) * 64 + o] = fmaxf(a1, 0.0f);
@@ -244,7 +298,16 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
 }
 
 size_t heads_smem(int A, int AS) {
-  return sizeof(float) * (6 * HEAD_C + (size_t)HEAD_NB * 6 * A + (size_t)HEAD_NB * AS + HEAD_NB * 64);
+  return sizeof(float) * ((size_t)HEAD_NB * 6 * A + (size_t)HEAD_NB * AS + HEAD_NB * 64 + 6 * HEAD_C);
+}
+
+template <int kSrc>
+int heads_launch(const HeadsParams& p, size_t smem, int grid, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(rz_heads_kernel<kSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { rz_set_error("rz_net_heads: smem attribute: %s", cudaGetErrorString(e)); return -2; }
+  rz_heads_kernel<kSrc><<<grid, HEAD_THREADS, smem, stream>>>(p);
+  RZ_LAUNCH_CHECK("rz_net_heads");
+  return 0;
 }
 
 }  // namespace
@@ -283,15 +346,7 @@ extern "C" int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_
   p.n_boards = n_boards; p.H = h->board_size; p.A = A; p.AS = h->action_stride;
   const size_t smem = heads_smem(A, p.AS);
   const int grid = (n_boards + HEAD_NB - 1) / HEAD_NB;
-  cudaError_t e;
-  if (act_is_tile_bf16) {
-    e = cudaFuncSetAttribute(rz_heads_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) rz_heads_kernel<true><<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(rz_heads_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) rz_heads_kernel<false><<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>(p);
-  }
-  if (e != cudaSuccess) { rz_set_error("rz_net_heads: smem attribute: %s", cudaGetErrorString(e)); return -2; }
-  RZ_LAUNCH_CHECK("rz_net_heads");
-  return 0;
+  if (act_is_tile_bf16 == 2) return heads_launch<SRC_FEAT>(p, smem, grid, (cudaStream_t)stream);
+  if (act_is_tile_bf16 == 1) return heads_launch<SRC_TILE>(p, smem, grid, (cudaStream_t)stream);
+  return heads_launch<SRC_F32>(p, smem, grid, (cudaStream_t)stream);
 }

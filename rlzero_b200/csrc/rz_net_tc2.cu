@@ -51,11 +51,24 @@ struct Conv2Params {
   int flags;                       // bit 0: set the descriptor base-offset field for shifted A tiles
 };
 
-template <int kCG>
+// kHead: the last trunk layer also applies the heads' two 1x1 convolutions + ReLU
+// (policy_value_net.py:41,47: act_conv1 128->4, val_conv1 128->2) to every output row while it is
+// in registers, and writes ONLY those 6 features: the trunk output never goes to HBM.  The 6x128
+// filter taps ride in the kernel parameters (constant bank): 768 FFMAs with immediate-offset
+// constant operands, no shared-memory or global traffic.
+struct HeadTaps {
+  float w[6 * 128];                // [filter][channel]
+  float b[6];
+  float* feat;                     // [n_boards][6][256] float32, position index p = y*16 + x
+};
+
+template <int kCG, bool kHead>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
                       const __grid_constant__ CUtensorMap tmap_w,
-                      const __grid_constant__ CUtensorMap tmap_out, const Conv2Params p) {
+                      const __grid_constant__ CUtensorMap tmap_out, const Conv2Params p,
+                      const __grid_constant__ HeadTaps head) {
+  static_assert(!kHead || kCG == 2, "the fused 1x1 heads need all 128 channels of a row in one thread");
   constexpr int ACC_N = (kCG == 2) ? 128 : 64;     // accumulator columns per buffer
   constexpr int TMEM_COLS = 2 * ACC_N;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -192,6 +205,11 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       }
       rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
       rz::tc_fence_after();
+      // kHead: nothing is staged, so the A buffer is free as soon as the tile's MMAs are done
+      if (kHead && warp == 2 && lane == 0) rz::mbar_arrive(bar_aempty + 8 * buf);
+      float hacc[6];
+#pragma unroll
+      for (int f = 0; f < 6; ++f) hacc[f] = kHead ? head.b[f] : 0.0f;
       const uint32_t stage_row = a_base + (uint32_t)buf * A_BUF_BYTES + (uint32_t)r_in_tile * 128u;
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
@@ -227,10 +245,26 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
             if (!valid) { v0 = 0.0f; v1 = 0.0f; }
             const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
             packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
+            if (kHead) {
+              // on the bf16-rounded activations, channels in ascending order: the same arithmetic
+              // as a separate heads kernel reading the stored trunk output
+              const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xffff0000u);
+#pragma unroll
+              for (int f = 0; f < 6; ++f)
+                hacc[f] = fmaf(r1, head.w[f * 128 + ch * 32 + c + 1], fmaf(r0, head.w[f * 128 + ch * 32 + c], hacc[f]));
+            }
           }
-          const uint32_t chunk = (uint32_t)((ch & 1) * 4 + j);
-          rz::st_shared_v4(srow + ((chunk ^ ((srow >> 7) & 7u)) << 4), packed[0], packed[1], packed[2], packed[3]);
+          if (!kHead) {
+            const uint32_t chunk = (uint32_t)((ch & 1) * 4 + j);
+            rz::st_shared_v4(srow + ((chunk ^ ((srow >> 7) & 7u)) << 4), packed[0], packed[1], packed[2], packed[3]);
+          }
         }
+      }
+      if (kHead) {
+        float* fo = head.feat + (size_t)(row >> 8) * (6 * 256) + pos;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) fo[f * 256] = fmaxf(hacc[f], 0.0f);
+        continue;
       }
       rz::fence_proxy_async();              // staging writes -> visible to the TMA engine
       rz::named_bar_sync(1, 128);           // the 4 epilogue warps
@@ -256,12 +290,12 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
   }
 }
 
-template <int kCG>
-int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const Conv2Params& p, int ctas,
-           cudaStream_t stream) {
+template <int kCG, bool kHead>
+int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const Conv2Params& p,
+           const HeadTaps& head, int ctas, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rz_conv3x3_tc2_kernel<kCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(rz_conv3x3_tc2_kernel<kCG, kHead>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc2: smem attribute: %s", cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
@@ -277,27 +311,31 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, rz_conv3x3_tc2_kernel<kCG>, ta, tw, to, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, rz_conv3x3_tc2_kernel<kCG, kHead>, ta, tw, to, p, head);
   if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc2: launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
 
 }  // namespace
 
-extern "C" int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias,
-                                  const void* residual, void* act_out, int n_boards, int board_size,
-                                  int c_in, int relu, int cta_group, int flags, int n_ctas, void* stream) {
-  RZ_REQUIRE(act_in && weight && bias && act_out, "rz_net_conv3x3_tc2: null argument");
+static int conv2_entry(const void* act_in, const void* weight, const float* bias, const void* residual,
+                       void* act_out, int n_boards, int board_size, int c_in, int relu, int cta_group,
+                       int flags, int n_ctas, const float* w1x1_host, const float* b1x1_host, float* feat,
+                       void* stream) {
+  RZ_REQUIRE(act_in && weight && bias, "rz_net_conv3x3_tc2: null argument");
   RZ_REQUIRE(n_boards >= 0, "rz_net_conv3x3_tc2: n_boards %d", n_boards);
   RZ_REQUIRE(board_size >= 1 && board_size <= 15, "rz_net_conv3x3_tc2: board_size %d not in [1,15]", board_size);
   RZ_REQUIRE(c_in == 64 || c_in == 128, "rz_net_conv3x3_tc2: c_in %d (64 or 128)", c_in);
   RZ_REQUIRE(cta_group == 1 || cta_group == 2, "rz_net_conv3x3_tc2: cta_group %d (1 or 2)", cta_group);
   RZ_REQUIRE(act_in != act_out, "rz_net_conv3x3_tc2: in-place convolution is not supported");
   if (n_boards == 0) return 0;
+  static HeadTaps head;   // ~3 KB: filled per call, copied into the launch parameters
   CUtensorMap tmap_act, tmap_w, tmap_out;
   if (rz::make_tmap_2d(&tmap_act, act_in, (uint64_t)n_boards * 256, (uint64_t)c_in, A_ROWS)) return -1;
   if (rz::make_tmap_2d(&tmap_w, weight, (uint64_t)9 * 128, (uint64_t)c_in, 64)) return -1;
-  if (rz::make_tmap_2d(&tmap_out, act_out, (uint64_t)n_boards * 256, 128, TILE_M)) return -1;
+  // kHead launches store nothing through this map; it then describes the input tensor's rows
+  if (rz::make_tmap_2d(&tmap_out, feat ? act_in : act_out, (uint64_t)n_boards * 256, feat ? (uint64_t)c_in : 128, TILE_M))
+    return -1;
   Conv2Params p;
   p.bias = bias;
   p.residual = (const __nv_bfloat16*)residual;
@@ -311,6 +349,29 @@ extern "C" int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const 
   ctas &= ~1;                                       // workers are CTA pairs in both modes
   if (ctas < 2) ctas = 2;
   if (ctas / 2 > p.n_items) ctas = 2 * p.n_items;   // every worker gets at least one item
-  return cta_group == 2 ? launch<2>(tmap_act, tmap_w, tmap_out, p, ctas, (cudaStream_t)stream)
-                        : launch<1>(tmap_act, tmap_w, tmap_out, p, ctas, (cudaStream_t)stream);
+  if (feat) {
+    for (int i = 0; i < 6 * 128; ++i) head.w[i] = w1x1_host[i];
+    for (int i = 0; i < 6; ++i) head.b[i] = b1x1_host[i];
+    head.feat = feat;
+    return launch<2, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream);
+  }
+  return cta_group == 2 ? launch<2, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream)
+                        : launch<1, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream);
+}
+
+extern "C" int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias,
+                                  const void* residual, void* act_out, int n_boards, int board_size,
+                                  int c_in, int relu, int cta_group, int flags, int n_ctas, void* stream) {
+  RZ_REQUIRE(act_out, "rz_net_conv3x3_tc2: null output");
+  return conv2_entry(act_in, weight, bias, residual, act_out, n_boards, board_size, c_in, relu, cta_group, flags,
+                     n_ctas, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int rz_net_conv3x3_tc2_head(const void* act_in, const void* weight, const float* bias,
+                                       const void* residual, int n_boards, int board_size, int c_in,
+                                       int relu, const float* w1x1_host, const float* b1x1_host,
+                                       float* feat, int n_ctas, void* stream) {
+  RZ_REQUIRE(w1x1_host && b1x1_host && feat, "rz_net_conv3x3_tc2_head: null head argument");
+  return conv2_entry(act_in, weight, bias, residual, nullptr, n_boards, board_size, c_in, relu, 2, 0, n_ctas,
+                     w1x1_host, b1x1_host, feat, stream);
 }

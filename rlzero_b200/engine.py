@@ -235,7 +235,10 @@ class SearchForest(object):
             for _ in range(n_waves):
                 wave()
             return
-        key = (id(evaluator), prior_is_log, float(noise_eps), float(noise_alpha), int(seed))
+        # weights_version: a captured graph holds the weight pointers (and the fused head's filter
+        # taps) by value, so repacked weights need a new capture
+        key = (id(evaluator), getattr(evaluator, 'weights_version', 0), prior_is_log, float(noise_eps),
+               float(noise_alpha), int(seed))
         graphs = self.__dict__.setdefault('_graphs', {})
         if key not in graphs:
             # warm-up outside capture (lazy module loads etc.), then capture one wave

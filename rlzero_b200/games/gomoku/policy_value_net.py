@@ -16,6 +16,7 @@ the stock network / other shapes.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -135,7 +136,8 @@ class NativeForward(object):
     graph_capturable = True
     prior_is_log = True       # the network emits log-probabilities (policy_value_net.py:44)
 
-    def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0, conv_rev=2, fused_stem=True):
+    def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0, conv_rev=2, fused_stem=True,
+                 fused_head=True):
         if not torch.cuda.is_available():
             raise L.NativeLibraryError('NativeForward needs a CUDA device (no CPU fallback)')
         self.lib = L.load()
@@ -152,6 +154,9 @@ class NativeForward(object):
             raise ValueError("mode 'tc' needs a 128-channel trunk and board_size <= 15")
         self.mode = mode
         self.n_ctas = int(n_ctas)
+        # the heads' 1x1 convolutions inside the last trunk layer's epilogue (rz_net_tc2.cu, kHead)
+        self.fused_head = bool(fused_head) and int(conv_rev) == 2
+        self.weights_version = 0
         self.fused_stem = bool(fused_stem)  # encoder + first conv in one kernel (rz_net_stem.cu)
         self.conv_rev = int(conv_rev)   # 2: resident weights + CTA pairs (rz_net_tc2.cu); 1: rz_net_tc.cu
         self.max_batch = 0
@@ -190,17 +195,21 @@ class NativeForward(object):
         f32 = torch.float32
         w1 = torch.cat([m.act_conv1.weight.detach().reshape(4, 128), m.val_conv1.weight.detach().reshape(2, 128)])
         b1 = torch.cat([m.act_conv1.bias.detach(), m.val_conv1.bias.detach()])
-        wp = torch.zeros(4 * hw, AS, dtype=f32)
-        wp[:, :hw] = m.act_fc1.weight.detach().t().float()
+        wp = torch.zeros(4 * hw + 4, AS, dtype=f32)      # + 4 zero rows: the kernel prefetches past the end
+        wp[:4 * hw, :hw] = m.act_fc1.weight.detach().t().float()
         bp = torch.zeros(AS, dtype=f32)
         bp[:hw] = m.act_fc1.bias.detach().float()
         self.heads = dict(
             w1x1=w1.float().contiguous().to(dev), b1x1=b1.float().contiguous().to(dev),
             wp=wp.contiguous().to(dev), bp=bp.to(dev),
-            wv1=m.val_fc1.weight.detach().t().float().contiguous().to(dev),
+            wv1=torch.cat([m.val_fc1.weight.detach().t().float().cpu(), torch.zeros(2, 64)]).contiguous().to(dev),
             bv1=m.val_fc1.bias.detach().float().contiguous().to(dev),
             wv2=m.val_fc2.weight.detach().reshape(64).float().contiguous().to(dev),
             bv2=m.val_fc2.bias.detach().float().contiguous().to(dev))
+        # host copies of the 1x1 filters: they travel in the launch parameters of the fused last layer
+        self.w1x1_host = np.ascontiguousarray(w1.float().cpu().numpy().reshape(-1))
+        self.b1x1_host = np.ascontiguousarray(b1.float().cpu().numpy().reshape(-1))
+        self.weights_version += 1
         hd = L.HeadsDesc()
         hd.board_size, hd.action_stride = self.H, AS
         for k, v in self.heads.items():
@@ -216,6 +225,7 @@ class NativeForward(object):
             bf = torch.bfloat16
             self.act0 = torch.zeros(n, 256, 64, dtype=bf, device=dev)
             self.bufs = [torch.zeros(n, 256, 128, dtype=bf, device=dev) for _ in range(2)]
+            self.feat = torch.zeros(n, 6, 256, dtype=torch.float32, device=dev)
         else:
             cmax = max(max(l['cin'], l['cout']) for l in self.layers)
             self.act0 = torch.zeros(n, self.A, self.layers[0]['cin'], dtype=torch.float32, device=dev)
@@ -243,6 +253,14 @@ class NativeForward(object):
                     # skip always refers to the activation two layers back = the other buffer
                     res = outs[dst]
                 inp = src if cur < 0 else outs[cur]
+                if self.fused_head and i == len(self.layers) - 1 and l['cin'] == 128:
+                    L.check(lib.rz_net_conv3x3_tc2_head(
+                        L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), n, self.H, l['cin'], int(l['relu']),
+                        self.w1x1_host.ctypes.data_as(C.c_void_p), self.b1x1_host.ctypes.data_as(C.c_void_p),
+                        L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc2_head')
+                    L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(self.feat), 2, L.ptr(logp), L.ptr(value),
+                                             n, s), 'rz_net_heads')
+                    return
                 if self.conv_rev == 2:
                     L.check(lib.rz_net_conv3x3_tc2(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
                                                    L.ptr(outs[dst]), n, self.H, l['cin'], int(l['relu']),
@@ -271,6 +289,12 @@ class NativeForward(object):
                 inp = outs[dst]
             L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(inp), 0, L.ptr(logp), L.ptr(value), n, s),
                     'rz_net_heads')
+
+    def kernels_per_forward(self):
+        """Kernel launches of one forward_boards call (for bench.py's gpu_launches)."""
+        n_conv = len(self.layers)
+        fused = self.mode == 'tc' and self.stem is not None and self.fused_stem
+        return (1 + n_conv - 1 if fused else 1 + n_conv) + 1      # [stem | encode + conv0] + convs + heads
 
     def forward_boards(self, rows, meta, n, logp=None, value=None):
         """Positions in the device board layout -> (logp [n][AS], value [n]) float32 tensors."""

@@ -45,6 +45,7 @@ class BatchedSelfPlay(object):
         self.waves_in_move = 0
         self.moves_played = 0
         self._graph = None
+        self._graph_version = getattr(evaluator, 'weights_version', 0)
         self._pinned = None
 
     # ------------------------------------------------------------------ set-up
@@ -74,9 +75,9 @@ class BatchedSelfPlay(object):
                         self.noise_alpha, self.seed)
 
     def kernels_per_wave(self):
-        n_conv = len(getattr(self.evaluator, 'layers', []))
-        # select + [encode + convs | fused stem + remaining convs] + heads + expand/backup
-        return 1 + (1 + n_conv + 1 if n_conv else 1) + 1
+        # select + evaluator kernels + expand/backup
+        kpf = getattr(self.evaluator, 'kernels_per_forward', None)
+        return 1 + (kpf() if kpf else 1) + 1
 
     def warm_up(self):
         """One eager wave (lazy attribute set-up) and capture of the wave graph."""
@@ -91,8 +92,20 @@ class BatchedSelfPlay(object):
             self._graph = g
         self.waves_in_move += 1
 
+    def _check_weights(self):
+        """A captured wave holds the weight pointers by value: re-capture after refresh_weights()."""
+        v = getattr(self.evaluator, 'weights_version', 0)
+        if self._graph is not None and v != self._graph_version:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._wave()
+            self._graph = g
+        self._graph_version = v
+
     def step_wave(self):
         """One playout for every game; commits the move when ``n_playout`` waves are done."""
+        self._check_weights()
         if self._graph is not None:
             self._graph.replay()
         else:
@@ -135,6 +148,7 @@ class BatchedSelfPlay(object):
         f.root_meta.copy_(p['meta'], non_blocking=True)
         f.reset_trees()
         self.warm_up_for_api()
+        self._check_weights()
         for _ in range(self.n_playout):
             if self._graph is not None:
                 self._graph.replay()

@@ -57,12 +57,24 @@ def main():
 
     def heads():
         L.check(lib.rz_net_heads(nf.hdesc, L.ptr(x), 1, L.ptr(nf.logp), L.ptr(nf.value), B, L.stream_ptr()))
-    print(json.dumps({'kernel': 'heads', 'ms': timeit(heads)}))
+    print(json.dumps({'kernel': 'heads<tile>', 'ms': timeit(heads)}))
+
+    def heads_feat():
+        L.check(lib.rz_net_heads(nf.hdesc, L.ptr(nf.feat), 2, L.ptr(nf.logp), L.ptr(nf.value), B, L.stream_ptr()))
+    print(json.dumps({'kernel': 'heads<feat>', 'ms': timeit(heads_feat)}))
+    import ctypes as C
+
+    def conv_head():
+        L.check(lib.rz_net_conv3x3_tc2_head(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), L.ptr(z), B, H, 128, 1,
+                                            nf.w1x1_host.ctypes.data_as(C.c_void_p),
+                                            nf.b1x1_host.ctypes.data_as(C.c_void_p), L.ptr(nf.feat), ctas,
+                                            L.stream_ptr()))
+    ms = timeit(conv_head)
+    print(json.dumps({'kernel': 'conv3x3_tc2_head+residual', 'ms': ms, 'TFLOPs_issued': flops_issued / ms / 1e9}))
     rows = torch.zeros(B, 2, H, dtype=torch.int32, device='cuda')
     meta = torch.zeros(B, 8, dtype=torch.int32, device='cuda')
     meta[:, 1] = -1
 
-    import ctypes as C
     g = nf._gdesc()
     st = nf.stem
 

@@ -258,3 +258,40 @@ def test_fused_stem_matches_encode_plus_conv(size, n):
     # bit-identical to the bitboard-fed one: search parity with a Python-side evaluator relies on it
     lp3, v3 = nf.forward_planes(planes.cpu().numpy())
     assert torch.equal(lp3[:, :size * size], lp1[:, :size * size]) and torch.equal(v3, v1)
+
+
+@pytest.mark.parametrize('size,blocks,n', [(15, 2, 70), (9, 1, 37), (6, 1, 3)])
+def test_fused_head_matches_separate_heads(size, blocks, n):
+    """The 1x1 head convolutions inside the last layer's epilogue (rz_net_conv3x3_tc2_head) give
+    the same logits / values as storing the trunk output and running the heads kernel on it."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(size + 1)
+    net = ResNetPolicyValueNet(size, n_blocks=blocks).cuda().eval()
+    x = _random_boards(n, size, 3)
+    a = NativeForward(net, max_batch=n, fused_head=True)
+    b = NativeForward(net, max_batch=n, fused_head=False)
+    la, va = (t.clone() for t in a.forward_planes(x))
+    lb, vb = (t.clone() for t in b.forward_planes(x))
+    # same bf16 activations, same fp32 FMA order over channels: identical features; the FC sums are
+    # split over two k halves in both, so the results are bit-identical
+    assert torch.equal(la, lb) and torch.equal(va, vb)
+
+
+def test_graph_recaptured_after_weight_refresh():
+    """A CUDA-graph-captured wave holds weight pointers by value: after AlphaZeroAgent.learn /
+    refresh_weights the self-play driver must capture again (stale weights otherwise)."""
+    from rlzero_b200.games.gomoku.policy_value_net import ResNetPolicyValueNet
+    from rlzero_b200.selfplay import BatchedSelfPlay
+    torch.manual_seed(2)
+    net = ResNetPolicyValueNet(6, n_blocks=1).cuda().eval()
+    sp = BatchedSelfPlay(4, 6, 4, net=net, n_playout=8, add_noise=False, seed=1)
+    rows, meta = sp.forest.boards()
+    _, _, v1 = sp.get_actions(rows, meta)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.5)
+    sp.evaluator.refresh_weights()
+    _, _, v2 = sp.get_actions(rows, meta)
+    sp_new = BatchedSelfPlay(4, 6, 4, net=net, n_playout=8, add_noise=False, seed=1)
+    _, _, v3 = sp_new.get_actions(rows, meta)
+    assert np.array_equal(v2, v3)
