@@ -205,6 +205,25 @@ int rz_tree_advance(const rz_tree_desc* t, const int32_t* moves, int keep_subtre
 int rz_eval_closed_form(const rz_tree_desc* t, int eval_id, float* prior, float* value,
                         void* stream);
 
+/* ---- training-side data path (tools/train_alphazero.py:59-90), SURVEY 8 f1 ----------------------
+   get_equi_data: the 8 symmetric copies of n recorded plies, in the reference's order (for i in
+   1..4: rot90^i, then its fliplr).  rows [n][2][H], info [n][info_stride] int32 (mover, last_move, z,
+   ...: the trajectory ring's records), pi f32 [n][AS]  ->  out_planes f32 [8n][4][H][W] (current_state
+   of the transformed position), out_pi f32 [8n][A], out_z f32 [8n]. */
+int rz_augment_equi(const rz_game_desc* g, const uint32_t* rows, const int32_t* info, int info_stride,
+                    const float* pi, float* out_planes, float* out_pi, float* out_z, int n, void* stream);
+/* dst[i][:] = src[index[i]][:] for a [.][width] float table: mini-batch gather from the replay buffer
+   (random.sample(self.data_buffer, batch_size), tools/train_alphazero.py:94). */
+int rz_gather_rows(const float* src, const long long* index, float* dst, int n, int width, void* stream);
+
+/* ---- pure-MCTS opponent: random playouts (rlzero/mcts/rollout_mcts.py:49-74,96-108) ---------
+   prior: uniform over the leaf's legal moves; value: the reference's _evaluate on a uniformly random
+   playout from the leaf (at most n_limit plies; literal winner == current_player() rule, i.e. -1 for
+   a decisive playout, 0 for a tie).  mode 0: counter-based RNG keyed by (seed, global game id, root
+   visit count, ply); mode 1 / 2: always the lowest / highest legal move (deterministic tests). */
+int rz_eval_rollout(const rz_tree_desc* t, int mode, unsigned long long seed, int n_limit, float* prior,
+                    float* value, void* stream);
+
 /* ---- policy-value network forward (rlzero/games/gomoku/policy_value_net.py:34-52) -------- */
 /* heads weights, all float32 device pointers.  FC weights are stored TRANSPOSED ([in][out]);
    the flatten order of the FC inputs is c*HW + pos (x.view(-1, C*H*W) on NCHW, :42,48). */

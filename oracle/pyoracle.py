@@ -328,3 +328,94 @@ def play_match(board, player0, player1):
         end, winner = board.game_end_winner()
         if end:
             return winner
+
+
+class RolloutSearch(object):
+    """RolloutMCTS restated (rollout_mcts.py:10-108): uniform priors, leaf value from a random
+    playout.  ``rollout`` selects the rollout policy: 'random' draws ``np.random.rand(len(legal))``
+    per ply and plays the argmax exactly like the reference (:96-100, :63-65); 'first' / 'last' play
+    the lowest / highest legal move (deterministic stand-ins for device parity tests).
+
+    Quirk kept on purpose: the winner is compared with ``current_player()`` AFTER the playout
+    (:69-72), and the env flips the player after every move (gomoku_env.py:67-68), so every
+    decisive playout yields -1 and only ties yield 0."""
+
+    def __init__(self, n_playout=1000, c_puct=5.0, n_limit=1000, rollout='random', rng=None):
+        self.root = Node(None, 1.0)
+        self.n_playout = n_playout
+        self.c_puct = c_puct
+        self.n_limit = n_limit
+        self.rollout = rollout
+        self.rng = rng
+
+    def policy_value_fn(self, board):  # :102-108
+        legal = board.leagel_actions()
+        return zip(legal, np.ones(len(legal)) / len(legal))
+
+    def rollout_policy(self, board):  # :96-100
+        legal = board.leagel_actions()
+        if self.rollout == 'random':
+            probs = (self.rng or np.random).rand(len(legal))
+        elif self.rollout == 'first':
+            probs = -np.arange(len(legal), dtype=np.float64)
+        else:
+            probs = np.arange(len(legal), dtype=np.float64)
+        return zip(legal, probs)
+
+    def evaluate(self, board):  # :49-74
+        winner = -1
+        for _ in range(self.n_limit):
+            end, winner = board.game_end_winner()
+            if end:
+                break
+            best = max(self.rollout_policy(board), key=lambda ap: ap[1])[0]
+            board.step(best)
+        if winner == -1:
+            return 0
+        return 1.0 if winner == board.current_player() else -1.0
+
+    def playout(self, board):  # :23-47
+        node = self.root
+        while node.children:
+            action, node = node.select(self.c_puct, RULE_UCT)
+            board.step(action)
+        priors = self.policy_value_fn(board)
+        end, _ = board.game_end_winner()
+        if not end:
+            node.expand(priors)
+        node.backup(-self.evaluate(board))
+
+    def simulate(self, board, temperature=1e-3):  # :76-81
+        for _ in range(self.n_playout):
+            self.playout(copy.deepcopy(board))
+        return max(self.root.children.items(), key=lambda an: an[1].n)[0]
+
+    def update_with_move(self, last_move):  # :83-94
+        if last_move in self.root.children:
+            self.root = self.root.children[last_move]
+            self.root.parent = None
+        else:
+            self.root = Node(None, 1.0)
+
+    def root_visits(self, n_actions):
+        out = np.zeros(n_actions, dtype=np.int32)
+        for a, ch in self.root.children.items():
+            out[a] = ch.n
+        return out
+
+
+class RolloutSearchPlayer(object):
+    """RolloutPlayer restated (rollout_mcts.py:114-140)."""
+
+    def __init__(self, n_playout=1000, c_puct=5, rollout='random', rng=None):
+        self.mcts = RolloutSearch(n_playout, c_puct, rollout=rollout, rng=rng)
+
+    def reset_player(self):
+        self.mcts.update_with_move(-1)
+
+    def get_action(self, board, **kwargs):
+        if len(board.leagel_actions()) > 0:
+            move = self.mcts.simulate(board)
+            self.mcts.update_with_move(-1)
+            return move
+        print('WARNING: the board is full')

@@ -77,6 +77,9 @@ SIGNATURES = {
     'rz_tree_root_policy': (C.c_int, [_TD, C.c_double, _vp, _vp, _vp, _vp, C.c_ulonglong, _vp]),
     'rz_tree_advance': (C.c_int, [_TD, _vp, C.c_int, C.c_int, _TJ, _vp, C.c_int, _vp]),
     'rz_eval_closed_form': (C.c_int, [_TD, C.c_int, _vp, _vp, _vp]),
+    'rz_augment_equi': (C.c_int, [_GD, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_gather_rows': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rz_eval_rollout': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),
     'rz_net_conv3x3_tc': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, _vp]),
     'rz_net_conv3x3_tc2': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -226,6 +226,71 @@ rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* val
   }
 }
 
+// Random-playout evaluator of the pure-MCTS opponent (rlzero/mcts/rollout_mcts.py):
+//   priors  uniform over the legal moves                      policy_value_fn :102-108
+//   value   play uniformly random legal moves to the end      _evaluate :49-74, rollout_policy :96-100
+// The reference compares the winner with current_player() AFTER the playout; the env flips the
+// player after every move (gomoku_env.py:67-68), so a decisive playout is worth -1 and a tie 0.
+// That rule is evaluated literally here.  mode 0: r-th empty square, r uniform from a
+// counter-based RNG keyed by (seed, global game id, root visit count, ply); mode 1 / 2: lowest /
+// highest legal move (deterministic, for bit-exact parity tests of everything but the RNG).
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_eval_rollout_kernel(rz_tree_desc t, int mode, unsigned long long seed, int n_limit, float* prior,
+                       float* value) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  if (t.depth[g] < 0) return;
+  const int lane = rz_lane(), H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  rz_wboard b;
+  rz_board_load(b, t.leaf_rows + (size_t)g * 2 * H, t.leaf_meta + (size_t)g * RZ_META_STRIDE, H);
+  // uniform priors over the leaf's legal moves
+  {
+    const int n_legal = A - b.stones;
+    const float uni = n_legal > 0 ? __fdiv_rn(1.0f, (float)n_legal) : 0.0f;
+    for (int s0 = 0; s0 < AS; s0 += 32) {
+      const int s = s0 + lane;
+      prior[(size_t)g * AS + s] = rz_board_slot_legal(b, s, H, A) ? uni : 0.0f;
+    }
+  }
+  const uint32_t rowmask = (H >= 32) ? 0xffffffffu : ((1u << H) - 1u);
+  const uint32_t visit = (uint32_t)t.root_N[g];
+  int winner = -1;
+  for (int i = 0; i < n_limit; ++i) {
+    const int status = rz_board_status(b, H, t.game.n_in_row, winner);
+    if (status != RZ_ACTIVE) break;
+    const uint32_t empty = lane < H ? (~(b.p[0] | b.p[1]) & rowmask) : 0u;
+    const int cnt = __popc(empty);
+    int inc = cnt;  // inclusive prefix count of empty squares over the rows
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(RZ_FULL, inc, o);
+      if (lane >= o) inc += up;
+    }
+    const int n_legal = __shfl_sync(RZ_FULL, inc, 31);
+    int r;
+    if (mode == 1) r = 0;
+    else if (mode == 2) r = n_legal - 1;
+    else {
+      uint32_t rnd[4];
+      rz_philox4((uint32_t)(t.global_offset + g), visit, (uint32_t)i, 0x7011u, seed, rnd);
+      r = (int)(((unsigned long long)rnd[0] * (unsigned long long)n_legal) >> 32);
+    }
+    // the row holding the r-th empty square, then its column
+    const bool mine = (r >= inc - cnt) && (r < inc);
+    const unsigned who = __ballot_sync(RZ_FULL, mine);
+    const int row = __ffs(who) - 1;
+    int col = 0;
+    if (mine) {
+      uint32_t m = empty;
+      for (int j = r - (inc - cnt); j > 0; --j) m &= m - 1;
+      col = __ffs(m) - 1;
+    }
+    col = __shfl_sync(RZ_FULL, col, row);
+    rz_board_play(b, row * H + col, H);
+  }
+  if (lane == 0) value[g] = (winner == -1) ? 0.0f : (winner == b.player ? 1.0f : -1.0f);
+}
+
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
@@ -307,6 +372,20 @@ extern "C" int rz_gomoku_encode_tc(const rz_game_desc* g, const uint32_t* rows, 
   rz_gomoku_encode_tc_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
                                (cudaStream_t)stream>>>(*g, rows, meta, (__nv_bfloat16*)act_bf16, n_games);
   RZ_LAUNCH_CHECK("rz_gomoku_encode_tc");
+  return 0;
+}
+
+extern "C" int rz_eval_rollout(const rz_tree_desc* t, int mode, unsigned long long seed, int n_limit,
+                               float* prior, float* value, void* stream) {
+  RZ_REQUIRE(t && prior && value, "rz_eval_rollout: null argument");
+  if (rz_check_game(&t->game)) return -1;
+  RZ_REQUIRE(mode >= 0 && mode <= 2, "rz_eval_rollout: mode %d", mode);
+  RZ_REQUIRE(n_limit >= 0, "rz_eval_rollout: n_limit %d", n_limit);
+  RZ_REQUIRE(t->root_N && t->depth && t->leaf_rows && t->leaf_meta, "rz_eval_rollout: null tree array");
+  if (t->n_trees == 0) return 0;
+  rz_eval_rollout_kernel<<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+                           (cudaStream_t)stream>>>(*t, mode, seed, n_limit, prior, value);
+  RZ_LAUNCH_CHECK("rz_eval_rollout");
   return 0;
 }
 

@@ -238,8 +238,10 @@ class SearchForest(object):
         # weights_version: a captured graph holds the weight pointers (and the fused head's filter
         # taps) by value, so repacked weights need a new capture
         key = (id(evaluator), getattr(evaluator, 'weights_version', 0), prior_is_log, float(noise_eps),
-               float(noise_alpha), int(seed))
+               float(noise_alpha), int(seed) if noise_eps > 0 else 0)   # the seed only feeds the noise
         graphs = self.__dict__.setdefault('_graphs', {})
+        if key not in graphs and len(graphs) >= 8:
+            graphs.clear()                                              # bounded cache
         if key not in graphs:
             # warm-up outside capture (lazy module loads etc.), then capture one wave
             wave()
@@ -312,6 +314,19 @@ class SearchForest(object):
                 self.depth.cpu().numpy())
 
     # ------------------------------------------------------------ trajectories
+    def drain_trajectories_device(self):
+        """Like ``drain_trajectories`` but the records stay on the device: dict of CUDA tensors
+        rows int32 [n,2,H], info int32 [n,6], pi float32 [n,AS] (training-side kernels consume them)."""
+        if self.traj is None:
+            raise RuntimeError('forest was built without trajectories')
+        cur = int(self.traj['ring_cursor'].item())
+        lo = max(self._ring_read, cur - self.ring_capacity)
+        dropped = lo - self._ring_read
+        self._ring_read = cur
+        ti = (torch.arange(lo, cur, device=self.device, dtype=torch.int64) % self.ring_capacity)
+        return dict(rows=self.traj['ring_rows'][ti].contiguous(), info=self.traj['ring_info'][ti].contiguous(),
+                    pi=self.traj['ring_pi'][ti].contiguous(), dropped=int(dropped))
+
     def drain_trajectories(self):
         """Finished-episode plies written since the last drain: dict of host arrays
         rows[n,2,H] uint32, info[n,6] (mover,last_move,z,slot,episode,ply), pi[n,A] float32."""
@@ -339,6 +354,24 @@ class ClosedFormEvaluator(object):
 
     def __call__(self, forest):
         forest.eval_closed_form(self.eval_id)
+
+
+class RolloutEvaluator(object):
+    """Device-side random-playout evaluator of the pure-MCTS opponent
+    (rlzero/mcts/rollout_mcts.py:49-74,96-108)."""
+    graph_capturable = True
+    prior_is_log = False
+    MODES = {'random': 0, 'first': 1, 'last': 2}
+
+    def __init__(self, n_limit=1000, seed=0, mode='random'):
+        self.n_limit = int(n_limit)
+        self.seed = int(seed)
+        self.mode = self.MODES[mode]
+
+    def __call__(self, forest):
+        L.check(forest.lib.rz_eval_rollout(C.byref(forest.desc), self.mode, self.seed, self.n_limit,
+                                           L.ptr(forest.prior), L.ptr(forest.value), forest._s()),
+                'rz_eval_rollout')
 
 
 class HostCallbackEvaluator(object):

@@ -1,5 +1,7 @@
 from .alphazero_mcts import AlphaZeroMCTS, AlphaZeroPlayer, softmax
 from .node import TreeNode
 from .player import HumanPlayer, Player
+from .rollout_mcts import RolloutMCTS, RolloutPlayer
 
-__all__ = ['AlphaZeroMCTS', 'AlphaZeroPlayer', 'TreeNode', 'Player', 'HumanPlayer', 'softmax']
+__all__ = ['AlphaZeroMCTS', 'AlphaZeroPlayer', 'RolloutMCTS', 'RolloutPlayer', 'TreeNode', 'Player',
+           'HumanPlayer', 'softmax']

@@ -92,7 +92,9 @@ class AlphaZeroMCTS(object):
         self._forest = SearchForest(1, env.board_size, env.n_in_row, n_playout=self.n_playout,
                                     c_puct=self._c_puct, rule=self.rule, max_carry=carry,
                                     device=self.device)
-        native = getattr(self.policy_value_fn, 'device_evaluator', None)
+        native = getattr(self, '_native_evaluator', None)
+        if native is None:
+            native = getattr(self.policy_value_fn, 'device_evaluator', None)
         if native is not None:
             self._evaluator = native
         else:
