@@ -230,6 +230,7 @@ def run_b200(args):
     ev = sp.evaluator
     lib = L.load()
     roof = None
+    tree_roof = None
     if rank == 0:
         layer = ev.layers[1]
         x, y = ev.bufs[0], ev.bufs[1]
@@ -267,6 +268,35 @@ def run_b200(args):
                 'net_forward_tflops_in_step': net.flops_per_eval() * G / (ms / args.steps) / 1e9,
                 'frac_in_step_of_sustained': net.flops_per_eval() * G / (ms / args.steps) / 1e9 / sustained}
 
+        # tree side (HBM-bound kernels): select is idempotent (it only writes the wave scratch), so it
+        # can be timed back to back on the live trees; algorithmic bytes = one int32 visit-count
+        # sweep (4*AS B) per level descended + the fp64 value sweep (8*AS B) on levels whose children
+        # are all visited (counted as every level but the leaf's parent: a lower bound) + root and
+        # leaf boards + the path record
+        f = sp.forest
+        for _ in range(min(args.playouts // 2, 400)):   # mid-search trees (the timed region ended on a commit)
+            sp.step_wave()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f.select()
+        torch.cuda.synchronize()
+        t0.record()
+        for _ in range(20):
+            f.select()
+        t1.record()
+        torch.cuda.synchronize()
+        sel_ms = t0.elapsed_time(t1) / 20
+        depth = f.depth.clamp(min=0).double()
+        levels = float(depth.sum().item())
+        full_levels = float((depth - 1).clamp(min=0).sum().item())
+        sel_bytes = levels * 4 * f.AS + full_levels * 8 * f.AS + G * (2 * 2 * BOARD * 4 + 2 * 32) + levels * 8
+        hbm = peaks.get('hbm_gbs') or 6650.0
+        tree_roof = {'bound': 'hbm', 'kernel': 'rz_select_kernel (%d trees, mean depth %.2f)' % (G, levels / G),
+                     'achieved': sel_bytes / sel_ms / 1e6, 'peak': hbm, 'unit': 'GB/s',
+                     'frac': sel_bytes / sel_ms / 1e6 / hbm, 'launch_ms': sel_ms,
+                     'algorithmic_bytes_per_launch': sel_bytes,
+                     'share_of_step': sel_ms / (ms / args.steps),
+                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650'}
+
     # end to end through the public API with host buffers (per move: H2D positions, D2H pi/moves)
     e2e = None
     if not args.no_e2e:
@@ -302,7 +332,7 @@ def run_b200(args):
                                        'probe in SURVEY 6)' % (P, ASSUMED_PLIES),
                 'clocks': sampler.summary() if sampler else None,
                 'gpu_launches': args.steps * kpw + commits * 2,
-                'e2e': e2e, 'roofline': roof}
+                'e2e': e2e, 'roofline': roof, 'tree_roofline': tree_roof}
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(args.blocks, P, args.cpu_seconds)
         print(json.dumps(line))

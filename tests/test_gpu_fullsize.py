@@ -1,0 +1,96 @@
+"""Parity at BASELINE.json's full size (config 3: Gomoku 15x15, 8192 games per GPU, ResNet-10 bf16)
+through size-independent properties, plus bit-exact spot checks of individual trees against the
+oracle fed by the same network (batch invariance at batch 8192)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G, H, K, N_PLAYOUT = 8192, 15, 5, 40
+
+
+@pytest.fixture(scope='module')
+def net():
+    from rlzero_b200.games.gomoku.policy_value_net import ResNetPolicyValueNet
+    torch.manual_seed(0)
+    return ResNetPolicyValueNet(H, n_blocks=10).cuda().eval()
+
+
+def _run(net, n_games, offset, ids, noise):
+    from rlzero_b200.selfplay import BatchedSelfPlay
+    sp = BatchedSelfPlay(n_games, H, K, net=net, n_playout=N_PLAYOUT, c_puct=5.0, temperature=1.0,
+                         add_noise=noise, global_offset=offset, seed=4321)
+    sp.set_random_start_positions(global_ids=ids)
+    rows0, meta0 = sp.forest.boards()
+    sp.warm_up()
+    for _ in range(N_PLAYOUT - 1):
+        sp.step_wave()          # the last wave commits the move
+    torch.cuda.synchronize()
+    sp.forest.raise_faults()
+    return sp, rows0, meta0
+
+
+def test_full_size_properties_and_determinism(net):
+    from rlzero_b200 import _lib as L
+    sp, rows0, meta0 = _run(net, G, 0, None, noise=True)
+    f = sp.forest
+    visits = f.visits.cpu().numpy()[:, :H * H]       # root statistics the move was sampled from
+    pi = f.pi.cpu().numpy()[:, :H * H]
+    move = f.move.cpu().numpy()
+    occ = (((rows0[:, 0] | rows0[:, 1])[:, :, None] >> np.arange(H)[None, None, :]) & 1).reshape(G, H * H)
+    # fresh root: the first playout expands it, the other n-1 visit its children
+    assert (visits.sum(1) == N_PLAYOUT - 1).all()
+    assert (visits[occ == 1] == 0).all()
+    np.testing.assert_allclose(pi.sum(1), 1.0, atol=1e-5)
+    assert ((move >= 0) & (move < H * H)).all() and (occ[np.arange(G), move] == 0).all()
+    assert (visits[np.arange(G), move] > 0).all()    # T = 1: only visited children can be sampled
+    # the move was played: one more stone, player flipped, ply advanced
+    rows1, meta1 = f.boards()
+    stones0 = meta0[:, L.META_STONES]
+    cont = meta1[:, L.META_EPISODE] == 0             # games that did not end (ended slots restart)
+    assert (meta1[cont, L.META_STONES] == stones0[cont] + 1).all()
+    assert (meta1[cont, L.META_PLAYER] == 1 - meta0[cont, L.META_PLAYER]).all()
+    assert (meta1[cont, L.META_LAST_MOVE] == move[cont]).all()
+    # kept subtree: root count of the re-rooted tree == visits of the chosen child
+    root_n = f.root_N.cpu().numpy()
+    assert (root_n[cont] == visits[np.arange(G), move][cont]).all()
+    assert (f.n_nodes.cpu().numpy() <= N_PLAYOUT).all()
+    # determinism: an identical second run reproduces every count and every move
+    sp2, _, _ = _run(net, G, 0, None, noise=True)
+    assert torch.equal(sp2.forest.visits, f.visits) and torch.equal(sp2.forest.move, f.move)
+    assert torch.equal(sp2.forest.root_rows, f.root_rows)
+    # shard invariance at full size: global ids 4000..4007 searched alone give the same result
+    ids = np.arange(4000, 4008)
+    sp3, _, _ = _run(net, 8, 4000, ids, noise=True)
+    assert np.array_equal(sp3.forest.visits.cpu().numpy(), f.visits.cpu().numpy()[4000:4008])
+    assert np.array_equal(sp3.forest.move.cpu().numpy(), move[4000:4008])
+
+
+def test_full_batch_trees_equal_the_oracle(net):
+    """Noise off: trees of the 8192-game batch are bit-identical to the oracle's sequential search
+    of the same position with the same network (evaluated board by board: batch invariance)."""
+    from oracle import pyoracle
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.games.gomoku.alphazero_agent import AlphaZeroAgent
+    from rlzero_b200.selfplay import BatchedSelfPlay
+    sp = BatchedSelfPlay(G, H, K, net=net, n_playout=N_PLAYOUT, add_noise=False, seed=1)
+    sp.set_random_start_positions()
+    rows0, meta0 = sp.forest.boards()
+    sp.warm_up()
+    for _ in range(N_PLAYOUT - 2):
+        sp.step_wave()          # stop one wave before the commit: N_PLAYOUT - 1 playouts done
+    torch.cuda.synchronize()
+    visits, w, has, root_n, root_w = sp.forest.root_stats()
+    agent = AlphaZeroAgent(H, net=net)
+    for g in (0, 1, 4095, 8191):
+        b = pyoracle.Board(H, K)
+        b.reset()
+        rs = np.random.RandomState(1000 + g)
+        for m in rs.permutation(H * H)[:(1000 + g) % 31]:
+            b.step(int(m))
+        assert len(b.states) == int(meta0[g, L.META_STONES])
+        s = pyoracle.Search(agent.policy_value_fn, N_PLAYOUT - 1, 5)
+        s.simulate(b, 1.0)
+        assert visits[g].tolist() == s.root_visits(H * H).tolist(), g
+        assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(H * H)], g
+        assert int(root_n[g]) == s.root.n
