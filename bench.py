@@ -240,7 +240,7 @@ def run_b200(args):
             if i == 3:
                 k0.record()
             L.check(lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(layer['w']), L.ptr(layer['b']), None, L.ptr(y), G,
-                                           BOARD, 128, 1, 2, 0, 0, L.stream_ptr()))
+                                           BOARD, BOARD, 128, 1, 2, 0, 0, L.stream_ptr()))
         k1.record()
         torch.cuda.synchronize()
         conv_ms = k0.elapsed_time(k1) / reps

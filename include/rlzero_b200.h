@@ -21,7 +21,8 @@
  *
  * Layouts
  *   board      : per game 2 x H uint32 row bitmasks, rows[g][c][r] bit w set <=>
- *                stone of player c on square r*W+w  (gomoku_env.py: states dict)
+ *                stone of player c on square r*W+w  (gomoku_env.py: states dict);
+ *                meta last_move holds the SQUARE of the last stone (== the action for Gomoku)
  *   meta       : per game RZ_META_STRIDE int32 (enum rz_meta)
  *   edge block : per expanded node A slots indexed BY ACTION (slot a <=> child
  *                reached by move a; children of a reference node are keyed by
@@ -38,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RZ_ABI_VERSION 4
+#define RZ_ABI_VERSION 5
 #define RZ_MAX_BOARD 19          /* rows live one per lane; A = H*W <= 361 */
 #define RZ_META_STRIDE 8
 
@@ -80,11 +81,20 @@ enum rz_child {                  /* values of edge child[] when N >= 1 */
 };
 
 /* ---- game geometry ------------------------------------------------------- */
+enum rz_game {
+  RZ_GAME_GOMOKU = 0,            /* k-in-a-row, action = square r*W+c (gomoku_env.py; TicTacToe = 3x3, k=3) */
+  RZ_GAME_CONNECT4 = 1           /* k-in-a-row with gravity: action = column, the stone drops to the lowest
+                                    empty row (row 0 = bottom).  No reference env exists; same
+                                    duck-typed API, planes and win rule as GomokuEnv */
+};
+
 typedef struct rz_game_desc {
-  int32_t board_size;            /* H == W  (GomokuEnv.board_size) */
-  int32_t n_in_row;              /* k       (GomokuEnv.n_in_row) */
-  int32_t n_actions;             /* A = H*W */
+  int32_t board_size;            /* H: rows      (GomokuEnv.board_size; H == W for Gomoku) */
+  int32_t n_in_row;              /* k            (GomokuEnv.n_in_row) */
+  int32_t n_actions;             /* A = H*W (Gomoku) or W (Connect Four) */
   int32_t action_stride;         /* AS = round_up(A, 32) */
+  int32_t width;                 /* W: columns (0 means W = H) */
+  int32_t game_type;             /* enum rz_game */
 } rz_game_desc;
 
 /* ---- one search forest: G trees, one per game ---------------------------- */
@@ -228,8 +238,10 @@ int rz_eval_rollout(const rz_tree_desc* t, int mode, unsigned long long seed, in
 /* heads weights, all float32 device pointers.  FC weights are stored TRANSPOSED ([in][out]);
    the flatten order of the FC inputs is c*HW + pos (x.view(-1, C*H*W) on NCHW, :42,48). */
 typedef struct rz_heads_desc {
-  int32_t board_size;
+  int32_t board_size;            /* H rows */
   int32_t action_stride;         /* AS: row stride of wp / logp */
+  int32_t width;                 /* W columns (0: W = H) */
+  int32_t n_actions;             /* policy outputs (0: H*W) */
   const float* w1x1;             /* [6][128]  act_conv1 (4 filters) then val_conv1 (2 filters) */
   const float* b1x1;             /* [6] */
   const float* wp;               /* [4*HW + 4][AS] act_fc1.weight^T, zero padded (columns >= HW and the 4 extra rows) */
@@ -255,15 +267,16 @@ int rz_net_conv3x3_tc(const void* act_in, const void* weight, const float* bias,
    (each computes 64 of the 128 output channels).  flags bit 0: set the base-offset field of the
    shifted descriptors.  n_ctas <= 0 picks 148. */
 int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias, const void* residual,
-                       void* act_out, int n_boards, int board_size, int c_in, int relu, int cta_group,
-                       int flags, int n_ctas, void* stream);
+                       void* act_out, int n_boards, int board_size, int board_cols, int c_in, int relu,
+                       int cta_group, int flags, int n_ctas, void* stream);
 /* the last trunk layer with the heads' two 1x1 convolutions + ReLU (act_conv1 128->4, val_conv1 128->2,
    policy_value_net.py:41,47) applied in its epilogue: writes ONLY feat f32 [n][6][256] (filter, then
    position p = y*16+x); the trunk output never reaches HBM.  w1x1_host [6][128] / b1x1_host [6] are
    HOST float32 arrays (copied into the launch parameters).  Feed feat to rz_net_heads(.., 2, ..). */
 int rz_net_conv3x3_tc2_head(const void* act_in, const void* weight, const float* bias, const void* residual,
-                            int n_boards, int board_size, int c_in, int relu, const float* w1x1_host,
-                            const float* b1x1_host, float* feat, int n_ctas, void* stream);
+                            int n_boards, int board_size, int board_cols, int c_in, int relu,
+                            const float* w1x1_host, const float* b1x1_host, float* feat, int n_ctas,
+                            void* stream);
 /* fused current_state (gomoku_env.py:95-114) + first trunk convolution (policy_value_net.py:14,36):
    the 36-wide im2col row of every position (k = tap*4 + plane) is built from the bitboards in
    registers, so the observation planes never exist in HBM.  weight bf16 [128][64] (k padded with

@@ -419,3 +419,91 @@ class RolloutSearchPlayer(object):
             self.mcts.update_with_move(-1)
             return move
         print('WARNING: the board is full')
+
+
+class ConnectFourBoard(object):
+    """Connect Four (k-in-a-row with gravity on a rows x cols board) behind the duck-typed env API
+    of the reference's search.  The reference has no such env; this is the CPU
+    definition the device kernels (RZ_GAME_CONNECT4) are checked against, written independently of
+    ``Board`` (explicit direction scan instead of the reference's window test).  Actions are
+    columns; ``states`` / ``last_move`` use the square index r*cols + c, row 0 at the bottom."""
+
+    def __init__(self, rows=6, cols=7, n_in_row=4):
+        self.board_size = rows          # the attribute the reference's player reads
+        self.board_width = cols
+        self.n_actions = cols
+        self.n_in_row = n_in_row
+        self.players = [0, 1]
+        self._to_move = 0
+        self.legal = list(range(cols))
+
+    def reset(self, start_player_idx=0):
+        self._to_move = self.players[start_player_idx]
+        self.legal = list(range(self.board_width))
+        self.heights = [0] * self.board_width
+        self.states = {}
+        self.last_move = -1
+        self.info = {}
+        return self.current_state()
+
+    def step(self, action):
+        if action not in self.legal:
+            raise AssertionError('illegal action %r' % (action,))
+        mover = self._to_move
+        cell = self.heights[action] * self.board_width + action
+        self.heights[action] += 1
+        self.states[cell] = mover
+        if self.heights[action] == self.board_size:
+            self.legal.remove(action)
+        self.last_move = cell
+        win, winner = self.has_a_winner()
+        reward = (1 if winner == mover else -1) if win else 0
+        self._to_move = 1 - mover
+        return self.current_state(), reward, win, self.info
+
+    def leagel_actions(self):
+        return self.legal
+
+    def legal_actions(self, player=None):
+        return self.legal
+
+    def current_player(self):
+        return self._to_move
+
+    def current_state(self):
+        h, w = self.board_size, self.board_width
+        planes = np.zeros((4, h, w))
+        for m, p in self.states.items():
+            planes[0 if p == self._to_move else 1, m // w, m % w] = 1.0
+        if self.states:
+            planes[2, self.last_move // w, self.last_move % w] = 1.0
+        if len(self.states) % 2 == 0:
+            planes[3, :, :] = 1.0
+        return planes
+
+    def has_a_winner(self):
+        h, w, k = self.board_size, self.board_width, self.n_in_row
+        if len(self.states) < 2 * k - 1:
+            return False, -1
+        for m, p in self.states.items():
+            r, c = divmod(m, w)
+            for dr, dc in ((0, 1), (1, 0), (1, 1), (1, -1)):
+                rr, cc, n = r, c, 0
+                while 0 <= rr < h and 0 <= cc < w and self.states.get(rr * w + cc, -1) == p:
+                    n += 1
+                    rr += dr
+                    cc += dc
+                if n >= k:
+                    return True, p
+        return False, -1
+
+    def game_end_winner(self):
+        win, winner = self.has_a_winner()
+        if win:
+            return True, winner
+        if not self.legal:
+            return True, -1
+        return False, -1
+
+    def is_terminal(self):
+        return self.game_end_winner()[0]

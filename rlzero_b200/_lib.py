@@ -11,7 +11,7 @@ import torch  # noqa: F401  -- loads libcudart.so.12 into the process before our
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'librlzero_b200.so')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 META_STRIDE = 8
 (META_PLAYER, META_LAST_MOVE, META_STONES, META_STATUS, META_WINNER, META_PLY, META_FAULT,
  META_EPISODE) = range(8)
@@ -26,9 +26,13 @@ MAX_BOARD = 19
 _vp = C.c_void_p
 
 
+GAME_GOMOKU, GAME_CONNECT4 = 0, 1
+
+
 class GameDesc(C.Structure):
+    """rz_game_desc: GameDesc(H, k, A, AS[, W, game_type]); W = 0 means a square board."""
     _fields_ = [('board_size', C.c_int32), ('n_in_row', C.c_int32), ('n_actions', C.c_int32),
-                ('action_stride', C.c_int32)]
+                ('action_stride', C.c_int32), ('width', C.c_int32), ('game_type', C.c_int32)]
 
 
 class TreeDesc(C.Structure):
@@ -51,8 +55,8 @@ class TrajDesc(C.Structure):
 
 
 class HeadsDesc(C.Structure):
-    _fields_ = [('board_size', C.c_int32), ('action_stride', C.c_int32),
-                ('w1x1', _vp), ('b1x1', _vp), ('wp', _vp), ('bp', _vp),
+    _fields_ = [('board_size', C.c_int32), ('action_stride', C.c_int32), ('width', C.c_int32),
+                ('n_actions', C.c_int32), ('w1x1', _vp), ('b1x1', _vp), ('wp', _vp), ('bp', _vp),
                 ('wv1', _vp), ('bv1', _vp), ('wv2', _vp), ('bv2', _vp)]
 
 
@@ -82,10 +86,10 @@ SIGNATURES = {
     'rz_eval_rollout': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),
     'rz_net_conv3x3_tc': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, _vp]),
-    'rz_net_conv3x3_tc2': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
+    'rz_net_conv3x3_tc2': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_int, _vp]),
-    'rz_net_conv3x3_tc2_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
-                                          C.c_int, _vp]),
+    'rz_net_conv3x3_tc2_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
+                                          _vp, _vp, C.c_int, _vp]),
     'rz_net_stem_tc': (C.c_int, [_GD, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_net_stem_tc_planes': (C.c_int, [_GD, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_net_conv3x3_f32': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,

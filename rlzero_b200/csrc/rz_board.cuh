@@ -36,19 +36,28 @@ __device__ __forceinline__ void rz_board_store_rows(const rz_wboard& b, uint32_t
   }
 }
 
-// occupied(a) for a warp-uniform action a
-__device__ __forceinline__ bool rz_board_occupied(const rz_wboard& b, int a, int W) {
-  const int r = a / W, c = a - r * W;
+// square an action lands on (warp-uniform a): the square itself, or for a gravity game the lowest
+// empty row of column a (stones of a column are contiguous from row 0, so that row is their count)
+__device__ __forceinline__ int rz_board_action_cell(const rz_wboard& b, int a, const rz_geom& q) {
+  if (!q.gravity) return a;
+  const unsigned col = __ballot_sync(RZ_FULL, ((b.p[0] | b.p[1]) >> a) & 1u);
+  return __popc(col) * q.W + a;
+}
+
+// is action a (warp-uniform, 0 <= a < A) illegal?  occupied square / full column
+__device__ __forceinline__ bool rz_board_occupied(const rz_wboard& b, int a, const rz_geom& q) {
+  const int r = q.gravity ? q.H - 1 : a / q.W, c = q.gravity ? a : a - (a / q.W) * q.W;
   const uint32_t occ = __shfl_sync(RZ_FULL, b.p[0] | b.p[1], r);
   return (occ >> c) & 1u;
 }
 
 // gomoku_env.py:55-57,67-68 -- place the mover's stone and flip the player (a is warp-uniform)
-__device__ __forceinline__ void rz_board_play(rz_wboard& b, int a, int W) {
-  const int r = a / W, c = a - r * W;
+__device__ __forceinline__ void rz_board_play(rz_wboard& b, int a, const rz_geom& q) {
+  const int cell = rz_board_action_cell(b, a, q);
+  const int r = cell / q.W, c = cell - r * q.W;
   if (rz_lane() == r) b.p[b.player] |= (1u << c);
   b.player ^= 1;
-  b.last_move = a;
+  b.last_move = cell;
   b.stones += 1;
 }
 
@@ -68,24 +77,31 @@ __device__ __forceinline__ bool rz_rows_have_line(uint32_t x, int k) {
 
 // game_end_winner (gomoku_env.py:196-203) incl. the stones < 2k-1 early-out of
 // has_a_winner (gomoku_env.py:131-133).  Returns rz_status; winner via reference.
-__device__ __forceinline__ int rz_board_status(const rz_wboard& b, int H, int k, int& winner) {
+__device__ __forceinline__ int rz_board_status(const rz_wboard& b, const rz_geom& q, int& winner) {
   winner = -1;
-  if (b.stones >= 2 * k - 1) {
-    const bool w0 = rz_rows_have_line(b.p[0], k);
-    const bool w1 = rz_rows_have_line(b.p[1], k);
+  if (b.stones >= 2 * q.k - 1) {
+    const bool w0 = rz_rows_have_line(b.p[0], q.k);
+    const bool w1 = rz_rows_have_line(b.p[1], q.k);
     if (w0 || w1) {
       winner = w0 ? 0 : 1;
       return RZ_ENDED_WIN;
     }
   }
-  if (b.stones >= H * H) return RZ_ENDED_TIE;
+  if (b.stones >= q.cells) return RZ_ENDED_TIE;
   return RZ_ACTIVE;
 }
 
-// legality of slot s (per-lane s, all lanes must call): empty square inside the board
-__device__ __forceinline__ bool rz_board_slot_legal(const rz_wboard& b, int s, int W, int A) {
-  const int sc = s < A ? s : 0;
-  const int r = sc / W, c = sc - r * W;
+// legality of action slot s (per-lane s, all lanes must call): empty square / column not full
+__device__ __forceinline__ bool rz_board_slot_legal(const rz_wboard& b, int s, const rz_geom& q) {
+  const int sc = s < q.A ? s : 0;
+  const int r = q.gravity ? q.H - 1 : sc / q.W, c = q.gravity ? sc : sc - (sc / q.W) * q.W;
   const uint32_t occ = __shfl_sync(RZ_FULL, b.p[0] | b.p[1], r);
-  return s < A && !((occ >> c) & 1u);
+  return s < q.A && !((occ >> c) & 1u);
+}
+// the same from the combined occupancy rows (lane r holds row r)
+__device__ __forceinline__ bool rz_occ_slot_legal(uint32_t myocc, int s, const rz_geom& q) {
+  const int sc = s < q.A ? s : 0;
+  const int r = q.gravity ? q.H - 1 : sc / q.W, c = q.gravity ? sc : sc - (sc / q.W) * q.W;
+  const uint32_t occ = __shfl_sync(RZ_FULL, myocc, r);
+  return s < q.A && !((occ >> c) & 1u);
 }

@@ -29,16 +29,37 @@ void rz_set_error(const char* fmt, ...);
     }                                                                   \
   } while (0)
 
+// geometry of a game as the kernels use it
+struct rz_geom {
+  int H, W, k, A, AS, cells, gravity;
+};
+__host__ __device__ inline rz_geom rz_geom_of(const rz_game_desc& d) {
+  rz_geom q;
+  q.H = d.board_size;
+  q.W = d.width > 0 ? d.width : d.board_size;
+  q.k = d.n_in_row;
+  q.A = d.n_actions;
+  q.AS = d.action_stride;
+  q.cells = q.H * q.W;
+  q.gravity = d.game_type == RZ_GAME_CONNECT4;
+  return q;
+}
+
 static inline int rz_check_game(const rz_game_desc* g) {
   if (!g) { rz_set_error("null game desc"); return -1; }
   if (g->board_size < 1 || g->board_size > RZ_MAX_BOARD) {
     rz_set_error("board_size %d outside [1,%d]", g->board_size, RZ_MAX_BOARD); return -1; }
-  if (g->n_actions != g->board_size * g->board_size) {
-    rz_set_error("n_actions %d != board_size^2", g->n_actions); return -1; }
+  const int W = g->width > 0 ? g->width : g->board_size;
+  if (W < 1 || W > RZ_MAX_BOARD) { rz_set_error("width %d outside [1,%d]", W, RZ_MAX_BOARD); return -1; }
+  if (g->game_type != RZ_GAME_GOMOKU && g->game_type != RZ_GAME_CONNECT4) {
+    rz_set_error("game_type %d", g->game_type); return -1; }
+  if (g->n_actions != (g->game_type == RZ_GAME_CONNECT4 ? W : g->board_size * W)) {
+    rz_set_error("n_actions %d does not match the %dx%d board of game %d", g->n_actions, g->board_size, W,
+                 g->game_type); return -1; }
   if (g->action_stride < g->n_actions || (g->action_stride & 31)) {
     rz_set_error("action_stride %d must be a multiple of 32 >= n_actions", g->action_stride); return -1; }
-  if (g->n_in_row < 1 || g->n_in_row > g->board_size) {
-    rz_set_error("n_in_row %d outside [1,board_size]", g->n_in_row); return -1; }
+  if (g->n_in_row < 1 || g->n_in_row > (g->board_size > W ? g->board_size : W)) {
+    rz_set_error("n_in_row %d outside [1,max(H,W)]", g->n_in_row); return -1; }
   return 0;
 }
 

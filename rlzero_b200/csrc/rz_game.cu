@@ -34,20 +34,21 @@ rz_gomoku_step_kernel(rz_game_desc gd, uint32_t* rows, int32_t* meta, const int3
                       int32_t* reward, int32_t* win, int n) {
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= n) return;
+  const rz_geom q = rz_geom_of(gd);
   const int lane = rz_lane(), H = gd.board_size;
   const int a = actions[g];
   if (a < 0) return;
   int32_t* m = meta + (size_t)g * RZ_META_STRIDE;
   rz_wboard b;
   rz_board_load(b, rows + (size_t)g * 2 * H, m, H);
-  if (a >= gd.n_actions || rz_board_occupied(b, a, H)) {  // gomoku_env.py:51
+  if (a >= gd.n_actions || rz_board_occupied(b, a, q)) {  // gomoku_env.py:51
     if (lane == 0) m[RZ_META_FAULT] |= RZ_FAULT_ILLEGAL_MOVE;
     return;
   }
   const int mover = b.player;
-  rz_board_play(b, a, H);
+  rz_board_play(b, a, q);
   int winner;
-  const int status = rz_board_status(b, H, gd.n_in_row, winner);
+  const int status = rz_board_status(b, q, winner);
   rz_board_store_rows(b, rows + (size_t)g * 2 * H, H);
   if (lane == 0) {
     m[RZ_META_PLAYER] = b.player;
@@ -66,14 +67,13 @@ __global__ void __launch_bounds__(RZ_GAME_THREADS)
 rz_gomoku_legal_kernel(rz_game_desc gd, const uint32_t* rows, uint8_t* mask, int n) {
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= n) return;
+  const rz_geom q = rz_geom_of(gd);
   const int lane = rz_lane(), H = gd.board_size, A = gd.n_actions;
   const uint32_t occ = lane < H ? (rows[(size_t)g * 2 * H + lane] | rows[(size_t)g * 2 * H + H + lane]) : 0u;
   for (int s0 = 0; s0 < A; s0 += 32) {
     const int s = s0 + lane;
-    const int sc = s < A ? s : 0;
-    const int r = sc / H, c = sc - r * H;
-    const uint32_t o = __shfl_sync(RZ_FULL, occ, r);
-    if (s < A) mask[(size_t)g * A + s] = ((o >> c) & 1u) ? 0 : 1;
+    const bool legal = rz_occ_slot_legal(occ, s, q);
+    if (s < A) mask[(size_t)g * A + s] = legal ? 1 : 0;
   }
 }
 
@@ -86,7 +86,7 @@ rz_gomoku_winner_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t* me
   rz_wboard b;
   rz_board_load(b, rows + (size_t)g * 2 * H, meta + (size_t)g * RZ_META_STRIDE, H);
   int winner;
-  const int status = rz_board_status(b, H, gd.n_in_row, winner);
+  const int status = rz_board_status(b, rz_geom_of(gd), winner);
   if (rz_lane() == 0) {
     end[g] = status != RZ_ACTIVE;
     winner_out[g] = winner;
@@ -112,7 +112,8 @@ rz_gomoku_encode_f32_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t
                             float* planes, int n) {
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= n) return;
-  const int lane = rz_lane(), H = gd.board_size, A = gd.n_actions;
+  const rz_geom q = rz_geom_of(gd);
+  const int lane = rz_lane(), H = gd.board_size, A = q.cells, W = q.W;
   rz_wboard b;
   rz_board_load(b, rows + (size_t)g * 2 * H, meta + (size_t)g * RZ_META_STRIDE, H);
   const uint32_t mine = b.p[b.player], theirs = b.p[b.player ^ 1];
@@ -121,8 +122,8 @@ rz_gomoku_encode_f32_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t
     const int i = i0 + lane;
     const int ic = i < total ? i : 0;
     const int plane = ic / A, pos = ic - plane * A;
-    const int r = pos / H, c = pos - r * H;
-    const float v = rz_plane_value(b, mine, theirs, plane, r, c, H);
+    const int r = pos / W, c = pos - r * W;
+    const float v = rz_plane_value(b, mine, theirs, plane, r, c, W);
     if (i < total) planes[(size_t)g * total + i] = v;
   }
 }
@@ -133,7 +134,8 @@ rz_gomoku_encode_nhwc_kernel(rz_game_desc gd, const uint32_t* rows, const int32_
                              float* planes, int n) {
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= n) return;
-  const int lane = rz_lane(), H = gd.board_size, A = gd.n_actions;
+  const rz_geom q = rz_geom_of(gd);
+  const int lane = rz_lane(), H = gd.board_size, A = q.cells, W = q.W;
   rz_wboard b;
   rz_board_load(b, rows + (size_t)g * 2 * H, meta + (size_t)g * RZ_META_STRIDE, H);
   const uint32_t mine = b.p[b.player], theirs = b.p[b.player ^ 1];
@@ -142,8 +144,8 @@ rz_gomoku_encode_nhwc_kernel(rz_game_desc gd, const uint32_t* rows, const int32_
     const int i = i0 + lane;
     const int ic = i < total ? i : 0;
     const int pos = ic >> 2, plane = ic & 3;
-    const int r = pos / H, c = pos - r * H;
-    const float v = rz_plane_value(b, mine, theirs, plane, r, c, H);
+    const int r = pos / W, c = pos - r * W;
+    const float v = rz_plane_value(b, mine, theirs, plane, r, c, W);
     if (i < total) planes[(size_t)g * total + i] = v;
   }
 }
@@ -155,7 +157,7 @@ rz_gomoku_encode_tc_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t*
                            __nv_bfloat16* act, int n) {
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= n) return;
-  const int lane = rz_lane(), H = gd.board_size;
+  const int lane = rz_lane(), H = gd.board_size, W = gd.width > 0 ? gd.width : gd.board_size;
   rz_wboard b;
   rz_board_load(b, rows + (size_t)g * 2 * H, meta + (size_t)g * RZ_META_STRIDE, H);
   const uint32_t mine = b.p[b.player], theirs = b.p[b.player ^ 1];
@@ -166,12 +168,12 @@ rz_gomoku_encode_tc_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t*
     const int y = p >> 4, x = p & 15;
     const uint32_t mrow = __shfl_sync(RZ_FULL, mine, y & 31);
     const uint32_t trow = __shfl_sync(RZ_FULL, theirs, y & 31);
-    const bool inside = (y < H) && (x < H);
+    const bool inside = (y < H) && (x < W);
     float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
     if (inside) {
       f0 = (float)((mrow >> x) & 1u);
       f1 = (float)((trow >> x) & 1u);
-      f2 = (b.stones > 0 && b.last_move == y * H + x) ? 1.0f : 0.0f;
+      f2 = (b.stones > 0 && b.last_move == y * W + x) ? 1.0f : 0.0f;
       f3 = colour;
     }
     __nv_bfloat162 lo = __floats2bfloat162_rn(f0, f1), hi = __floats2bfloat162_rn(f2, f3);
@@ -193,7 +195,8 @@ rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* val
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   if (t.depth[g] < 0) return;
-  const int lane = rz_lane(), H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  const rz_geom q = rz_geom_of(t.game);
+  const int lane = rz_lane(), H = t.game.board_size, AS = t.game.action_stride;
   rz_wboard b;
   rz_board_load(b, t.leaf_rows + (size_t)g * 2 * H, t.leaf_meta + (size_t)g * RZ_META_STRIDE, H);
   uint32_t h = 0;
@@ -203,7 +206,7 @@ rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* val
       while (w) {
         const int col = __ffs(w) - 1;
         w &= w - 1;
-        const uint32_t m1 = (uint32_t)(lane * H + col + 1);
+        const uint32_t m1 = (uint32_t)(lane * q.W + col + 1);
         h += m1 * m1 * (3u + 4u * (uint32_t)c);
       }
     }
@@ -215,11 +218,12 @@ rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* val
   if (eval_id == RZ_EVAL_KAT) v = (float)((17 * b.stones + 31 * (b.last_move + 1)) % 13 - 6) / 8.0f;
   else if (eval_id == RZ_EVAL_HASH) v = (float)((int)((h >> 16) % 129u) - 64) / 64.0f;
   if (lane == 0) value[g] = v;
-  const int n_legal = A - b.stones;
+  int n_legal = 0;
+  for (int s0 = 0; s0 < AS; s0 += 32) n_legal += __popc(__ballot_sync(RZ_FULL, rz_board_slot_legal(b, s0 + lane, q)));
   const float uni = n_legal > 0 ? __fdiv_rn(1.0f, (float)n_legal) : 0.0f;
   for (int s0 = 0; s0 < AS; s0 += 32) {
     const int s = s0 + lane;
-    const bool legal = rz_board_slot_legal(b, s, H, A);
+    const bool legal = rz_board_slot_legal(b, s, q);
     float p = 0.0f;
     if (legal) p = (eval_id == RZ_EVAL_HASH) ? (float)(((uint32_t)s * 29u + (h >> 8)) % 32u + 1u) / 256.0f : uni;
     prior[(size_t)g * AS + s] = p;
@@ -240,25 +244,28 @@ rz_eval_rollout_kernel(rz_tree_desc t, int mode, unsigned long long seed, int n_
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   if (t.depth[g] < 0) return;
-  const int lane = rz_lane(), H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  const rz_geom q = rz_geom_of(t.game);
+  const int lane = rz_lane(), H = t.game.board_size, AS = t.game.action_stride;
   rz_wboard b;
   rz_board_load(b, t.leaf_rows + (size_t)g * 2 * H, t.leaf_meta + (size_t)g * RZ_META_STRIDE, H);
   // uniform priors over the leaf's legal moves
   {
-    const int n_legal = A - b.stones;
+    int n_legal = 0;
+    for (int s0 = 0; s0 < AS; s0 += 32) n_legal += __popc(__ballot_sync(RZ_FULL, rz_board_slot_legal(b, s0 + lane, q)));
     const float uni = n_legal > 0 ? __fdiv_rn(1.0f, (float)n_legal) : 0.0f;
     for (int s0 = 0; s0 < AS; s0 += 32) {
       const int s = s0 + lane;
-      prior[(size_t)g * AS + s] = rz_board_slot_legal(b, s, H, A) ? uni : 0.0f;
+      prior[(size_t)g * AS + s] = rz_board_slot_legal(b, s, q) ? uni : 0.0f;
     }
   }
-  const uint32_t rowmask = (H >= 32) ? 0xffffffffu : ((1u << H) - 1u);
+  const uint32_t rowmask = (q.W >= 32) ? 0xffffffffu : ((1u << q.W) - 1u);
   const uint32_t visit = (uint32_t)t.root_N[g];
   int winner = -1;
   for (int i = 0; i < n_limit; ++i) {
-    const int status = rz_board_status(b, H, t.game.n_in_row, winner);
+    const int status = rz_board_status(b, q, winner);
     if (status != RZ_ACTIVE) break;
-    const uint32_t empty = lane < H ? (~(b.p[0] | b.p[1]) & rowmask) : 0u;
+    // candidate squares: every empty square, or (gravity) the empty squares of the top row = open columns
+    const uint32_t empty = (q.gravity ? lane == H - 1 : lane < H) ? (~(b.p[0] | b.p[1]) & rowmask) : 0u;
     const int cnt = __popc(empty);
     int inc = cnt;  // inclusive prefix count of empty squares over the rows
 #pragma unroll
@@ -286,7 +293,7 @@ rz_eval_rollout_kernel(rz_tree_desc t, int mode, unsigned long long seed, int n_
       col = __ffs(m) - 1;
     }
     col = __shfl_sync(RZ_FULL, col, row);
-    rz_board_play(b, row * H + col, H);
+    rz_board_play(b, q.gravity ? col : row * q.W + col, q);
   }
   if (lane == 0) value[g] = (winner == -1) ? 0.0f : (winner == b.player ? 1.0f : -1.0f);
 }

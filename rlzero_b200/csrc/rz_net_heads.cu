@@ -72,7 +72,7 @@ struct HeadsParams {
   const float* bv2;       // [1]
   float* logp;            // [B][AS]
   float* value;           // [B]
-  int n_boards, H, A, AS;
+  int n_boards, H, W, HW, A, AS;   // H x W squares (HW), A policy outputs
 };
 
 // 256-bit read-only global load: one full 32-byte sector per lane (sm_100 LDG.E.256)
@@ -84,11 +84,11 @@ __device__ __forceinline__ void rz_ld_global_nc_v8(const void* p, uint32_t (&r)[
 
 // 6 dot products of one position's 128 channels with the 1x1 filters in shared memory
 template <bool kTile>
-__device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos, int H,
+__device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos, int W, int HW,
                                                  const float* __restrict__ s_w, float (&acc)[6]) {
   const float4* w4 = reinterpret_cast<const float4*>(s_w);
   if constexpr (kTile) {
-    const int y = pos / H, x = pos - y * H;
+    const int y = pos / W, x = pos - y * W;
     const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(act) + ((size_t)b * 256 + y * 16 + x) * HEAD_C;
     uint32_t raw[8][8];  // the whole row: 8 x 32 B, all loads in flight before the first use
 #pragma unroll
@@ -113,7 +113,7 @@ __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos
     }
   } else {
     const float4* src = reinterpret_cast<const float4*>(
-        reinterpret_cast<const float*>(act) + ((size_t)b * H * H + pos) * HEAD_C);
+        reinterpret_cast<const float*>(act) + ((size_t)b * HW + pos) * HEAD_C);
 #pragma unroll 4
     for (int j = 0; j < HEAD_C / 4; ++j) {
       const float4 q = src[j];
@@ -140,7 +140,7 @@ enum { SRC_F32 = 0, SRC_TILE = 1, SRC_FEAT = 2 };
 template <int kSrc>
 __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsParams p) {
   extern __shared__ __align__(16) float sm[];
-  const int HW = p.A;
+  const int HW = p.HW;
   float* s_f = sm;                              // [6*HW][NB]  k-major features (policy 4*HW, then value 2*HW)
   float* s_lg = s_f + 6 * HW * HEAD_NB;         // [NB][AS]    logits
   float* s_h = s_lg + HEAD_NB * p.AS;           // [NB][64]    value hidden
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
         const int i = i0 + u * HEAD_THREADS;
         const int bi = i / (6 * 256), r = i - bi * (6 * 256);
         const int f = r >> 8, y = (r >> 4) & 15, x = r & 15;
-        if (i < HEAD_NB * 6 * 256 && x < p.H && y < p.H) s_f[feat_slot(f * HW + y * p.H + x, bi)] = v[u];
+        if (i < HEAD_NB * 6 * 256 && x < p.W && y < p.H) s_f[feat_slot(f * HW + y * p.W + x, bi)] = v[u];
       }
     }
   } else {
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
       float acc[6];
 #pragma unroll
       for (int f = 0; f < 6; ++f) acc[f] = p.b1x1[f];
-      if (bi < nb) conv1x1_position<kSrc == SRC_TILE>(p.act, b0 + bi, pos, p.H, s_w, acc);
+      if (bi < nb) conv1x1_position<kSrc == SRC_TILE>(p.act, b0 + bi, pos, p.W, HW, s_w, acc);
 #pragma unroll
       for (int f = 0; f < 6; ++f) s_f[feat_slot(f * HW + pos, bi)] = bi < nb ? fmaxf(acc[f], 0.0f) : 0.0f;
     }
@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
   }
 }
 
-size_t heads_smem(int A, int AS) {
-  return sizeof(float) * ((size_t)HEAD_NB * 6 * A + (size_t)HEAD_NB * AS + HEAD_NB * 64 + 6 * HEAD_C);
+size_t heads_smem(int HW, int AS) {
+  return sizeof(float) * ((size_t)HEAD_NB * 6 * HW + (size_t)HEAD_NB * AS + HEAD_NB * 64 + 6 * HEAD_C);
 }
 
 template <int kSrc>
@@ -336,15 +336,18 @@ extern "C" int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_
   RZ_REQUIRE(h->w1x1 && h->b1x1 && h->wp && h->bp && h->wv1 && h->bv1 && h->wv2 && h->bv2,
              "rz_net_heads: null weight pointer");
   RZ_REQUIRE(h->board_size >= 1 && h->board_size <= RZ_MAX_BOARD, "rz_net_heads: board_size %d", h->board_size);
-  RZ_REQUIRE(!act_is_tile_bf16 || h->board_size <= 15, "rz_net_heads: tile layout holds boards up to 15x15");
-  const int A = h->board_size * h->board_size;
+  const int W = h->width > 0 ? h->width : h->board_size;
+  RZ_REQUIRE(W >= 1 && W <= RZ_MAX_BOARD, "rz_net_heads: width %d", W);
+  RZ_REQUIRE(!act_is_tile_bf16 || (h->board_size <= 15 && W <= 15), "rz_net_heads: tile layout holds boards up to 15x15");
+  const int HW = h->board_size * W;
+  const int A = h->n_actions > 0 ? h->n_actions : HW;
   RZ_REQUIRE(h->action_stride >= A && (h->action_stride & 31) == 0, "rz_net_heads: action_stride %d", h->action_stride);
   if (n_boards <= 0) return 0;
   HeadsParams p;
   p.act = act; p.w1x1 = h->w1x1; p.b1x1 = h->b1x1; p.wp = h->wp; p.bp = h->bp; p.wv1 = h->wv1;
   p.bv1 = h->bv1; p.wv2 = h->wv2; p.bv2 = h->bv2; p.logp = logp; p.value = value;
-  p.n_boards = n_boards; p.H = h->board_size; p.A = A; p.AS = h->action_stride;
-  const size_t smem = heads_smem(A, p.AS);
+  p.n_boards = n_boards; p.H = h->board_size; p.W = W; p.HW = HW; p.A = A; p.AS = h->action_stride;
+  const size_t smem = heads_smem(HW, p.AS);
   const int grid = (n_boards + HEAD_NB - 1) / HEAD_NB;
   if (act_is_tile_bf16 == 2) return heads_launch<SRC_FEAT>(p, smem, grid, (cudaStream_t)stream);
   if (act_is_tile_bf16 == 1) return heads_launch<SRC_TILE>(p, smem, grid, (cudaStream_t)stream);

@@ -30,7 +30,8 @@ struct StemParams {
   const float* planes;    // kPlanes: [n][4][H][H] float observation planes instead of bitboards
   const float* bias;      // [128]
   int n_tiles;            // 2 per board
-  int H;
+  int H;                  // rows
+  int W;                  // columns
   int relu;
 };
 
@@ -46,7 +47,7 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint32_t* s_rows = reinterpret_cast<uint32_t*>(al + OFF_CTRL + 32);    // [2][16] + 4 meta words
   float* s_bias = reinterpret_cast<float*>(al + OFF_CTRL + 256);         // [128]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int H = p.H;
+  const int H = p.H, W = p.W;
 
   if (tid == 0) {
     rz::tma_prefetch_desc(&tmap_w);
@@ -88,28 +89,28 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       const int y = pos >> 4, x = pos & 15;
       const int player = (int)s_rows[32] & 1, last = (int)s_rows[33], stones = (int)s_rows[34];
       const uint32_t colour = (stones & 1) ? 0u : ONE;
-      const bool out_inside = (x < H) && (y < H);
+      const bool out_inside = (x < W) && (y < H);
       uint32_t w[20];  // 5 chunks x 4 words (2 bf16 each): taps 0..8 (+ one empty tap slot)
 #pragma unroll
       for (int i = 0; i < 20; ++i) w[i] = 0u;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        const bool in = out_inside && yy >= 0 && yy < H && xx >= 0 && xx < H;
+        const bool in = out_inside && yy >= 0 && yy < H && xx >= 0 && xx < W;
         uint32_t f0 = 0u, f1 = 0u, f2 = 0u, f3 = 0u;
         if (kPlanes) {
           if (in) {
-            const float* src = p.planes + (size_t)b * 4 * H * H + yy * H + xx;
+            const float* src = p.planes + (size_t)b * 4 * H * W + yy * W + xx;
             f0 = __bfloat16_as_ushort(__float2bfloat16_rn(src[0]));
-            f1 = __bfloat16_as_ushort(__float2bfloat16_rn(src[H * H]));
-            f2 = __bfloat16_as_ushort(__float2bfloat16_rn(src[2 * H * H]));
-            f3 = __bfloat16_as_ushort(__float2bfloat16_rn(src[3 * H * H]));
+            f1 = __bfloat16_as_ushort(__float2bfloat16_rn(src[H * W]));
+            f2 = __bfloat16_as_ushort(__float2bfloat16_rn(src[2 * H * W]));
+            f3 = __bfloat16_as_ushort(__float2bfloat16_rn(src[3 * H * W]));
           }
         } else {
           const uint32_t mine = s_rows[player * 16 + (yy & 15)], theirs = s_rows[(player ^ 1) * 16 + (yy & 15)];
           f0 = in ? ((mine >> (xx & 31)) & 1u) * ONE : 0u;
           f1 = in ? ((theirs >> (xx & 31)) & 1u) * ONE : 0u;
-          f2 = (in && stones > 0 && last == yy * H + xx) ? ONE : 0u;
+          f2 = (in && stones > 0 && last == yy * W + xx) ? ONE : 0u;
           f3 = in ? colour : 0u;
         }
         w[tap * 2 + 0] = f0 | (f1 << 16);
@@ -140,7 +141,7 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     // ---- epilogue: row per thread
     {
       const int pos = (tile & 1) * 128 + tid;
-      const bool valid = ((pos & 15) < H) && ((pos >> 4) < H);
+      const bool valid = ((pos & 15) < W) && ((pos >> 4) < H);
       const uint32_t stage_row = base + OFF_STAGE + (uint32_t)tid * 128u;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -202,7 +203,7 @@ static int stem_launch(const rz_game_desc* g, const uint32_t* rows, const int32_
   if (rz::make_tmap_2d(&tmap_out, act_out, (uint64_t)n_boards * 256, 128, 128)) return -1;
   StemParams p;
   p.rows = rows; p.meta = meta; p.planes = planes; p.bias = bias;
-  p.n_tiles = n_boards * 2; p.H = g->board_size; p.relu = relu;
+  p.n_tiles = n_boards * 2; p.H = g->board_size; p.W = g->width > 0 ? g->width : g->board_size; p.relu = relu;
   int ctas = n_ctas > 0 ? n_ctas : 148 * 3;
   if (ctas > p.n_tiles) ctas = p.n_tiles;
   if (planes) rz_stem_tc_kernel<true><<<ctas, STEM_THREADS, STEM_SMEM, (cudaStream_t)stream>>>(tmap_w, tmap_out, p);
@@ -216,7 +217,7 @@ extern "C" int rz_net_stem_tc(const rz_game_desc* g, const uint32_t* rows, const
                               int relu, int n_ctas, void* stream) {
   if (rz_check_game(g)) return -1;
   RZ_REQUIRE(rows && meta && weight && bias && act_out, "rz_net_stem_tc: null argument");
-  RZ_REQUIRE(g->board_size <= 15, "rz_net_stem_tc: the 16x16 tile layout holds boards up to 15x15");
+  RZ_REQUIRE(g->board_size <= 15 && g->width <= 15, "rz_net_stem_tc: the 16x16 tile layout holds boards up to 15x15");
   RZ_REQUIRE(n_boards >= 0, "rz_net_stem_tc: n_boards %d", n_boards);
   return stem_launch(g, rows, meta, nullptr, weight, bias, act_out, n_boards, relu, n_ctas, stream);
 }
@@ -226,7 +227,7 @@ extern "C" int rz_net_stem_tc_planes(const rz_game_desc* g, const float* planes,
                                      void* stream) {
   if (rz_check_game(g)) return -1;
   RZ_REQUIRE(planes && weight && bias && act_out, "rz_net_stem_tc_planes: null argument");
-  RZ_REQUIRE(g->board_size <= 15, "rz_net_stem_tc_planes: the 16x16 tile layout holds boards up to 15x15");
+  RZ_REQUIRE(g->board_size <= 15 && g->width <= 15, "rz_net_stem_tc_planes: the 16x16 tile layout holds boards up to 15x15");
   RZ_REQUIRE(n_boards >= 0, "rz_net_stem_tc_planes: n_boards %d", n_boards);
   return stem_launch(g, nullptr, nullptr, planes, weight, bias, act_out, n_boards, relu, n_ctas, stream);
 }

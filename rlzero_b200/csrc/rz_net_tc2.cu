@@ -45,7 +45,8 @@ struct Conv2Params {
   const __nv_bfloat16* residual;   // [rows][128] or null
   __nv_bfloat16* out;              // [rows][128]
   int n_items;                     // kCG=2: boards; kCG=1: half boards
-  int board;                       // H
+  int board;                       // H (rows)
+  int board_w;                     // W (columns)
   int kblocks;                     // Cin / 64
   int relu;
   int flags;                       // bit 0: set the descriptor base-offset field for shifted A tiles
@@ -193,7 +194,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       const int r_in_tile = q * 32 + lane;
       const size_t row = (size_t)row0 + r_in_tile;
       const int pos = (int)(row & 255);
-      const bool valid = ((pos & 15) < p.board) && ((pos >> 4) < p.board);
+      const bool valid = ((pos & 15) < p.board_w) && ((pos >> 4) < p.board);
       // residual row: issued before the accumulator is ready, so its latency hides behind the MMAs
       // (256-bit loads: each lane fetches whole 32-byte sectors of its row, no sector is read twice)
       uint32_t res[NCH * 2][8];
@@ -319,12 +320,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, 
 }  // namespace
 
 static int conv2_entry(const void* act_in, const void* weight, const float* bias, const void* residual,
-                       void* act_out, int n_boards, int board_size, int c_in, int relu, int cta_group,
+                       void* act_out, int n_boards, int board_size, int board_cols, int c_in, int relu, int cta_group,
                        int flags, int n_ctas, const float* w1x1_host, const float* b1x1_host, float* feat,
                        void* stream) {
   RZ_REQUIRE(act_in && weight && bias, "rz_net_conv3x3_tc2: null argument");
   RZ_REQUIRE(n_boards >= 0, "rz_net_conv3x3_tc2: n_boards %d", n_boards);
   RZ_REQUIRE(board_size >= 1 && board_size <= 15, "rz_net_conv3x3_tc2: board_size %d not in [1,15]", board_size);
+  RZ_REQUIRE(board_cols >= 1 && board_cols <= 15, "rz_net_conv3x3_tc2: board_cols %d not in [1,15]", board_cols);
   RZ_REQUIRE(c_in == 64 || c_in == 128, "rz_net_conv3x3_tc2: c_in %d (64 or 128)", c_in);
   RZ_REQUIRE(cta_group == 1 || cta_group == 2, "rz_net_conv3x3_tc2: cta_group %d (1 or 2)", cta_group);
   RZ_REQUIRE(act_in != act_out, "rz_net_conv3x3_tc2: in-place convolution is not supported");
@@ -342,6 +344,7 @@ static int conv2_entry(const void* act_in, const void* weight, const float* bias
   p.out = (__nv_bfloat16*)act_out;
   p.n_items = cta_group == 2 ? n_boards : n_boards * 2;
   p.board = board_size;
+  p.board_w = board_cols;
   p.kblocks = c_in / 64;
   p.relu = relu;
   p.flags = flags;
@@ -361,17 +364,18 @@ static int conv2_entry(const void* act_in, const void* weight, const float* bias
 
 extern "C" int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias,
                                   const void* residual, void* act_out, int n_boards, int board_size,
-                                  int c_in, int relu, int cta_group, int flags, int n_ctas, void* stream) {
+                                  int board_cols, int c_in, int relu, int cta_group, int flags, int n_ctas,
+                                  void* stream) {
   RZ_REQUIRE(act_out, "rz_net_conv3x3_tc2: null output");
-  return conv2_entry(act_in, weight, bias, residual, act_out, n_boards, board_size, c_in, relu, cta_group, flags,
+  return conv2_entry(act_in, weight, bias, residual, act_out, n_boards, board_size, board_cols, c_in, relu, cta_group, flags,
                      n_ctas, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int rz_net_conv3x3_tc2_head(const void* act_in, const void* weight, const float* bias,
-                                       const void* residual, int n_boards, int board_size, int c_in,
-                                       int relu, const float* w1x1_host, const float* b1x1_host,
+                                       const void* residual, int n_boards, int board_size, int board_cols,
+                                       int c_in, int relu, const float* w1x1_host, const float* b1x1_host,
                                        float* feat, int n_ctas, void* stream) {
   RZ_REQUIRE(w1x1_host && b1x1_host && feat, "rz_net_conv3x3_tc2_head: null head argument");
-  return conv2_entry(act_in, weight, bias, residual, nullptr, n_boards, board_size, c_in, relu, 2, 0, n_ctas,
+  return conv2_entry(act_in, weight, bias, residual, nullptr, n_boards, board_size, board_cols, c_in, relu, 2, 0, n_ctas,
                      w1x1_host, b1x1_host, feat, stream);
 }

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
   const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   const int lane = rz_lane();
+  const rz_geom q = rz_geom_of(t.game);
   const int H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
   const int iters = AS >> 5;
   int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
 
     if (lane == 0) { pnode[depth] = node; pact[depth] = best_slot; }
     depth += 1;
-    rz_board_play(b, best_slot, H);  // game_env.step(action), alphazero_mcts.py:54
+    rz_board_play(b, best_slot, q);  // game_env.step(action), alphazero_mcts.py:54
     if (best_n == 0) break;          // never visited -> unexpanded leaf
     const int child = t.edge_child[base + best_slot];
     if (child < 0) break;            // terminal (or overflowed) leaf, re-evaluated every visit
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
 
   // leaf: game_end_winner() (alphazero_mcts.py:60)
   int winner;
-  const int status = rz_board_status(b, H, t.game.n_in_row, winner);
+  const int status = rz_board_status(b, q, winner);
   rz_board_store_rows(b, t.leaf_rows + (size_t)g * 2 * H, H);
   if (lane == 0) {
     int32_t* lm = t.leaf_meta + (size_t)g * RZ_META_STRIDE;
@@ -203,6 +204,7 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
   const int depth = t.depth[g];
   if (depth < 0) return;
   const int lane = rz_lane();
+  const rz_geom q = rz_geom_of(t.game);
   const int H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
   const int32_t* lm = t.leaf_meta + (size_t)g * RZ_META_STRIDE;
   const int32_t* rm = t.root_meta + (size_t)g * RZ_META_STRIDE;
@@ -236,10 +238,7 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
       for (int i = 0; i < RZ_MAX_ITERS; ++i) {
         if (i >= (AS >> 5)) break;
         const int s = lane + 32 * i;
-        const int sc = s < A ? s : 0;
-        const int r = sc / H, c = sc - r * H;
-        const uint32_t occ = __shfl_sync(RZ_FULL, myocc, r);
-        const bool legal = s < A && !((occ >> c) & 1u);
+        const bool legal = rz_occ_slot_legal(myocc, s, q);
         t.edge_N[nb + s] = legal ? 0 : -1;
         nz[i] = 0.0f;
         if (noisy && legal) {
@@ -479,6 +478,7 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
   const int g = blockIdx.x * RZ_TREE_WARPS + wib;
   if (g >= t.n_trees) return;
   const int lane = rz_lane();
+  const rz_geom q = rz_geom_of(t.game);
   const int H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
   uint32_t* bits = rz_adv_smem + (size_t)wib * 2 * words_per_warp;
   uint32_t* wprefix = bits + words_per_warp;
@@ -492,7 +492,7 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
   rz_wboard b;
   uint32_t* rrows = t.root_rows + (size_t)g * 2 * H;
   rz_board_load(b, rrows, rmeta, H);
-  if (m >= A || rz_board_occupied(b, m, H)) {  // gomoku_env.py:51
+  if (m >= A || rz_board_occupied(b, m, q)) {  // gomoku_env.py:51
     if (lane == 0) rmeta[RZ_META_FAULT] |= RZ_FAULT_ILLEGAL_MOVE;
     return;
   }
@@ -513,9 +513,9 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
     }
   }
   // game.py:117: game_env.step(move)
-  rz_board_play(b, m, H);
+  rz_board_play(b, m, q);
   int winner;
-  const int status = rz_board_status(b, H, t.game.n_in_row, winner);
+  const int status = rz_board_status(b, q, winner);
 
   // alphazero_mcts.py:96-103
   const bool root_expanded = t.n_nodes[g] > 0;

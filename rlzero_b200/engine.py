@@ -46,19 +46,22 @@ class SearchForest(object):
     def __init__(self, n_trees, board_size, n_in_row, n_playout=800, c_puct=5.0,
                  rule=L.RULE_UCT, max_carry=None, max_nodes=None, store_priors=True,
                  device='cuda', global_offset=0, ln_table_len=None, with_trajectories=False,
-                 ring_capacity=None):
+                 ring_capacity=None, board_width=None, game_type=L.GAME_GOMOKU):
         if not torch.cuda.is_available():
             raise L.NativeLibraryError('rlzero_b200 needs a CUDA device (no CPU fallback)')
         self.lib = L.load()
         self.device = torch.device(device)
         self.G = int(n_trees)
         self.H = int(board_size)
+        self.W = self.H if board_width is None else int(board_width)
         self.k = int(n_in_row)
-        if not (1 <= self.H <= L.MAX_BOARD):
+        self.game_type = int(game_type)
+        if not (1 <= self.H <= L.MAX_BOARD and 1 <= self.W <= L.MAX_BOARD):
             raise ValueError('board_size must be in [1, %d]' % L.MAX_BOARD)
-        if self.H < self.k:
+        if max(self.H, self.W) < self.k:
             raise ValueError('Board board_size can not less than %d' % self.k)  # gomoku_env.py:35
-        self.A = self.H * self.H
+        self.cells = self.H * self.W
+        self.A = self.W if self.game_type == L.GAME_CONNECT4 else self.cells      # actions
         self.AS = _round_up(self.A, 32)
         self.n_playout = int(n_playout)
         self.c_puct = float(c_puct)
@@ -69,7 +72,7 @@ class SearchForest(object):
         self.max_nodes = int(max_nodes) if max_nodes else self.n_playout + self.max_carry
         if self.max_nodes > 6144:
             raise ValueError('max_nodes %d > 6144 (re-root bitmap lives in shared memory)' % self.max_nodes)
-        self.max_depth = self.A + 1
+        self.max_depth = self.cells + 1
         self.store_priors = bool(store_priors) or rule == L.RULE_PUCT
         G, AS, H, dev = self.G, self.AS, self.H, self.device
         i32, f64, f32 = torch.int32, torch.float64, torch.float32
@@ -100,7 +103,7 @@ class SearchForest(object):
         self.pi = torch.zeros(G, AS, dtype=f32, device=dev)
         self.move = torch.full((G,), -1, dtype=i32, device=dev)
 
-        self.gdesc = L.GameDesc(self.H, self.k, self.A, self.AS)
+        self.gdesc = L.GameDesc(self.H, self.k, self.A, self.AS, self.W, self.game_type)
         d = L.TreeDesc()
         d.game = self.gdesc
         d.n_trees, d.max_nodes, d.max_depth = G, self.max_nodes, self.max_depth
@@ -122,7 +125,7 @@ class SearchForest(object):
     # ------------------------------------------------------------------ memory
     def _alloc_trajectories(self, ring_capacity):
         G, H, AS, dev = self.G, self.H, self.AS, self.device
-        P = self.A
+        P = self.cells
         cap = int(ring_capacity) if ring_capacity else max(4 * P, 2 * G * 16)
         cap = max(cap, P)
         i32, f32 = torch.int32, torch.float32

@@ -30,8 +30,7 @@ class _PolicyValueFn(object):
     def __call__(self, game_env):
         agent = self._agent
         legal_positions = game_env.leagel_actions()
-        state = np.ascontiguousarray(game_env.current_state().reshape(
-            -1, 4, agent.board_size, agent.board_size))
+        state = np.ascontiguousarray(game_env.current_state()[None])     # [1,4,H,W] (:38-39)
         logp, value = agent.native.forward_planes(state)
         act_probs = np.exp(logp[0].cpu().numpy())
         return zip(legal_positions, act_probs[legal_positions]), float(value[0].item())

@@ -32,21 +32,26 @@ class GomokuEnv(BaseEnv):
         self.players = [0, 1]
         self.start_player_idx = start_player_idx
         self._current_player = self.players[self.start_player_idx]
-        self._leagel_actions = list(range(self.board_size * self.board_size))
+        # geometry extension (SURVEY 7 "square-board assumption"): square k-in-a-row by default
+        self.board_width = board_size
+        self.game_type = L.GAME_GOMOKU
+        self.n_actions = self.board_size * self.board_width
+        self._leagel_actions = list(range(self.n_actions))
         self._device = device
         self._rows = None
         self._meta = None
 
     # ------------------------------------------------------------ device side
     def _gdesc(self):
-        a = self.board_size * self.board_size
-        return L.GameDesc(self.board_size, self.n_in_row, a, (a + 31) // 32 * 32)
+        a = self.n_actions
+        return L.GameDesc(self.board_size, self.n_in_row, a, (a + 31) // 32 * 32, self.board_width,
+                          self.game_type)
 
     def _ensure_device(self):
         if self._rows is None:
             if not torch.cuda.is_available():
                 raise L.NativeLibraryError('GomokuEnv needs a CUDA device (no CPU fallback)')
-            if not 1 <= self.board_size <= L.MAX_BOARD:
+            if not (1 <= self.board_size <= L.MAX_BOARD and 1 <= self.board_width <= L.MAX_BOARD):
                 raise Error('board_size must be in [1, %d]' % L.MAX_BOARD)
             self._lib = L.load()
             self._rows = torch.zeros(1, 2, self.board_size, dtype=torch.int32, device=self._device)
@@ -57,7 +62,7 @@ class GomokuEnv(BaseEnv):
         return self._rows, self._meta
 
     def __deepcopy__(self, memo):
-        new = GomokuEnv.__new__(GomokuEnv)
+        new = type(self).__new__(type(self))
         for k, v in self.__dict__.items():
             if isinstance(v, torch.Tensor):
                 setattr(new, k, v.clone())
@@ -70,14 +75,14 @@ class GomokuEnv(BaseEnv):
     # ------------------------------------------------------------- reference API
     def reset(self, start_player_idx=0):
         """init the board and set some variables (gomoku_env.py:33-47)."""
-        if self.board_size < self.n_in_row:
+        if max(self.board_size, self.board_width) < self.n_in_row:
             raise Error(f'Board board_size can not less than {self.n_in_row}')
         if start_player_idx not in (0, 1):
             raise Error(f'{start_player_idx} should be 0 (player1 first) or 1 (player2 first)')
         self._ensure_device()
         self.start_player_idx = start_player_idx
         self._current_player = self.players[start_player_idx]
-        self._leagel_actions = list(range(self.board_size * self.board_size))
+        self._leagel_actions = list(range(self.n_actions))
         self.states = {}
         self.last_move = -1
         self.info = {}
@@ -99,12 +104,16 @@ class GomokuEnv(BaseEnv):
                                          L.ptr(out[0:1]), L.ptr(out[1:2]), 1, L.stream_ptr()),
                 'rz_gomoku_step')
         reward, win = (int(x) for x in out.cpu().numpy())
-        self.states[action] = self._current_player
-        self._leagel_actions.remove(action)
-        self.last_move = action
+        self._record_move(action)
         self._current_player = (self.players[0] if self._current_player == self.players[1]
                                 else self.players[1])
         return self.current_state(), reward, bool(win), self.info
+
+    def _record_move(self, action):
+        """host mirror of the move: states dict, legal list, last_move (gomoku_env.py:55-57)."""
+        self.states[action] = self._current_player
+        self._leagel_actions.remove(action)
+        self.last_move = action
 
     def leagel_actions(self):
         return self._leagel_actions
@@ -115,7 +124,7 @@ class GomokuEnv(BaseEnv):
     def current_state(self):
         """4 x N x N float64 planes from the mover's perspective (gomoku_env.py:95-114)."""
         n = self.board_size
-        out = torch.empty(1, 4, n, n, dtype=torch.float32, device=self._rows.device)
+        out = torch.empty(1, 4, n, self.board_width, dtype=torch.float32, device=self._rows.device)
         g = self._gdesc()
         L.check(self._lib.rz_gomoku_encode_f32(C.byref(g), L.ptr(self._rows), L.ptr(self._meta),
                                                L.ptr(out), 1, L.stream_ptr()), 'rz_gomoku_encode_f32')
@@ -212,19 +221,26 @@ class LeafEnvView(object):
     ``last_move``, ``current_player()``, ``board_size``, ``game_end_winner()``.  ``states``
     lists stones in ascending square order (play order below the root is not recorded)."""
 
-    def __init__(self, rows, meta, board_size, n_in_row):
+    def __init__(self, rows, meta, board_size, n_in_row, board_width=None, game_type=L.GAME_GOMOKU):
         self.board_size = board_size
+        self.board_width = board_size if board_width is None else board_width
+        self.game_type = game_type
         self.n_in_row = n_in_row
         self.players = [0, 1]
         self._rows = np.asarray(rows, dtype=np.uint32)
         self._meta = np.asarray(meta)
         self.last_move = int(meta[L.META_LAST_MOVE])
         self._current_player = int(meta[L.META_PLAYER])
-        n = board_size
-        bits = ((self._rows[:, :, None] >> np.arange(n, dtype=np.uint32)[None, None, :]) & 1).astype(bool)
-        self._bits = bits  # [2, n, n]
+        n, w = board_size, self.board_width
+        bits = ((self._rows[:, :, None] >> np.arange(w, dtype=np.uint32)[None, None, :]) & 1).astype(bool)
+        self._bits = bits  # [2, n, w]
         occ = bits[0] | bits[1]
-        self._leagel_actions = np.nonzero(~occ.reshape(-1))[0].tolist()
+        if game_type == L.GAME_CONNECT4:
+            self.n_actions = w
+            self._leagel_actions = np.nonzero(~occ[n - 1])[0].tolist()      # columns whose top square is empty
+        else:
+            self.n_actions = n * w
+            self._leagel_actions = np.nonzero(~occ.reshape(-1))[0].tolist()
         self.states = {}
         who = np.where(bits[0], 0, 1).reshape(-1)
         for m in np.nonzero(occ.reshape(-1))[0].tolist():
@@ -240,12 +256,12 @@ class LeafEnvView(object):
         return self._current_player
 
     def current_state(self):
-        n = self.board_size
-        planes = np.zeros((4, n, n))
+        n, w = self.board_size, self.board_width
+        planes = np.zeros((4, n, w))
         planes[0] = self._bits[self._current_player]
         planes[1] = self._bits[1 - self._current_player]
         if self.states:
-            planes[2, self.last_move // n, self.last_move % n] = 1.0
+            planes[2, self.last_move // w, self.last_move % w] = 1.0
         if len(self.states) % 2 == 0:
             planes[3] = 1.0
         return planes

@@ -46,7 +46,7 @@ class PolicyValueNet(nn.Module):
         return F.relu(self.conv3(x))
 
     def heads(self, x):
-        hw = self.board_size * self.board_size
+        hw = self.board_size * getattr(self, 'board_width', self.board_size)
         a = F.relu(self.act_conv1(x)).reshape(-1, 4 * hw)
         logp = F.log_softmax(self.act_fc1(a), dim=1)
         v = F.relu(self.val_conv1(x)).reshape(-1, 2 * hw)
@@ -79,17 +79,21 @@ class _ResBlock(nn.Module):
 class ResNetPolicyValueNet(PolicyValueNet):
     """ResNet-N trunk (C channels) with the reference's heads."""
 
-    def __init__(self, board_size, n_blocks=10, channels=128):
+    def __init__(self, board_size, n_blocks=10, channels=128, board_width=None, n_actions=None):
+        """``board_size`` rows x ``board_width`` columns (square by default, like the reference);
+        ``n_actions`` policy outputs (rows*columns by default; the columns for Connect Four)."""
         nn.Module.__init__(self)
         if channels != 128:
             raise ValueError('the reference heads take 128 trunk channels (policy_value_net.py:19,23)')
         self.board_size = board_size
+        self.board_width = board_size if board_width is None else board_width
         self.n_blocks = n_blocks
-        hw = board_size * board_size
+        hw = self.board_size * self.board_width
+        self.n_actions = hw if n_actions is None else n_actions
         self.stem = nn.Conv2d(4, channels, 3, padding=1)
         self.blocks = nn.ModuleList([_ResBlock(channels) for _ in range(n_blocks)])
         self.act_conv1 = nn.Conv2d(channels, 4, kernel_size=1)
-        self.act_fc1 = nn.Linear(4 * hw, hw)
+        self.act_fc1 = nn.Linear(4 * hw, self.n_actions)
         self.val_conv1 = nn.Conv2d(channels, 2, kernel_size=1)
         self.val_fc1 = nn.Linear(2 * hw, 64)
         self.val_fc2 = nn.Linear(64, 1)
@@ -109,10 +113,10 @@ class ResNetPolicyValueNet(PolicyValueNet):
         return layers
 
     def flops_per_eval(self):
-        hw = self.board_size ** 2
+        hw = self.board_size * self.board_width
         c = 128
         trunk = 2 * hw * (4 * c * 9) + self.n_blocks * 2 * 2 * hw * c * c * 9
-        heads = 2 * hw * c * 6 + 2 * (4 * hw) * hw + 2 * (2 * hw) * 64 + 2 * 64
+        heads = 2 * hw * c * 6 + 2 * (4 * hw) * self.n_actions + 2 * (2 * hw) * 64 + 2 * 64
         return trunk + heads
 
 
@@ -137,21 +141,29 @@ class NativeForward(object):
     prior_is_log = True       # the network emits log-probabilities (policy_value_net.py:44)
 
     def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0, conv_rev=2, fused_stem=True,
-                 fused_head=True):
+                 fused_head=True, game_type=None):
         if not torch.cuda.is_available():
             raise L.NativeLibraryError('NativeForward needs a CUDA device (no CPU fallback)')
         self.lib = L.load()
         self.module = module
         self.device = torch.device(device)
         self.H = int(module.board_size)
-        self.A = self.H * self.H
+        self.W = int(getattr(module, 'board_width', self.H))
+        self.HW = self.H * self.W                      # squares (inputs of the FC heads)
+        self.A = int(getattr(module, 'n_actions', self.HW))   # policy outputs
         self.AS = (self.A + 31) // 32 * 32
+        if game_type is None:   # a policy head over the columns of a non-square board = a gravity game
+            game_type = L.GAME_CONNECT4 if (self.A == self.W and self.A != self.HW) else L.GAME_GOMOKU
+        self.game_type = int(game_type)
         layers = module.trunk_layers()
         all128 = all(l[0].out_channels == 128 for l in layers)
+        fits = self.H <= 15 and self.W <= 15
         if mode is None:
-            mode = 'tc' if (all128 and self.H <= 15) else 'f32'
-        if mode == 'tc' and not (all128 and self.H <= 15):
-            raise ValueError("mode 'tc' needs a 128-channel trunk and board_size <= 15")
+            mode = 'tc' if (all128 and fits) else 'f32'
+        if mode == 'tc' and not (all128 and fits):
+            raise ValueError("mode 'tc' needs a 128-channel trunk and a board of at most 15x15")
+        if mode == 'f32' and self.W != self.H:
+            raise ValueError('the fp32 CUDA-core path handles square boards only')
         self.mode = mode
         self.n_ctas = int(n_ctas)
         # the heads' 1x1 convolutions inside the last trunk layer's epilogue (rz_net_tc2.cu, kHead)
@@ -191,14 +203,14 @@ class NativeForward(object):
             ws[:, :36] = w0.permute(0, 2, 3, 1).reshape(128, 36)      # [cout][kh][kw][plane]
             self.stem = dict(w=ws.to(torch.bfloat16).contiguous().to(dev), b=b0.float().contiguous().to(dev),
                              relu=bool(m.trunk_layers()[0][3]))
-        hw, AS = self.A, self.AS
+        hw, AS = self.HW, self.AS
         f32 = torch.float32
         w1 = torch.cat([m.act_conv1.weight.detach().reshape(4, 128), m.val_conv1.weight.detach().reshape(2, 128)])
         b1 = torch.cat([m.act_conv1.bias.detach(), m.val_conv1.bias.detach()])
         wp = torch.zeros(4 * hw + 4, AS, dtype=f32)      # + 4 zero rows: the kernel prefetches past the end
-        wp[:4 * hw, :hw] = m.act_fc1.weight.detach().t().float()
+        wp[:4 * hw, :self.A] = m.act_fc1.weight.detach().t().float()
         bp = torch.zeros(AS, dtype=f32)
-        bp[:hw] = m.act_fc1.bias.detach().float()
+        bp[:self.A] = m.act_fc1.bias.detach().float()
         self.heads = dict(
             w1x1=w1.float().contiguous().to(dev), b1x1=b1.float().contiguous().to(dev),
             wp=wp.contiguous().to(dev), bp=bp.to(dev),
@@ -211,7 +223,7 @@ class NativeForward(object):
         self.b1x1_host = np.ascontiguousarray(b1.float().cpu().numpy().reshape(-1))
         self.weights_version += 1
         hd = L.HeadsDesc()
-        hd.board_size, hd.action_stride = self.H, AS
+        hd.board_size, hd.action_stride, hd.width, hd.n_actions = self.H, AS, self.W, self.A
         for k, v in self.heads.items():
             setattr(hd, k, v.data_ptr())
         self.hdesc = hd
@@ -228,14 +240,14 @@ class NativeForward(object):
             self.feat = torch.zeros(n, 6, 256, dtype=torch.float32, device=dev)
         else:
             cmax = max(max(l['cin'], l['cout']) for l in self.layers)
-            self.act0 = torch.zeros(n, self.A, self.layers[0]['cin'], dtype=torch.float32, device=dev)
-            self.bufs = [torch.zeros(n, self.A, cmax, dtype=torch.float32, device=dev) for _ in range(3)]
+            self.act0 = torch.zeros(n, self.HW, self.layers[0]['cin'], dtype=torch.float32, device=dev)
+            self.bufs = [torch.zeros(n, self.HW, cmax, dtype=torch.float32, device=dev) for _ in range(3)]
         self.logp = torch.zeros(n, self.AS, dtype=torch.float32, device=dev)
         self.value = torch.zeros(n, dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------ forward
     def _gdesc(self, k=5):
-        return L.GameDesc(self.H, min(k, self.H), self.A, self.AS)
+        return L.GameDesc(self.H, min(k, max(self.H, self.W)), self.A, self.AS, self.W, self.game_type)
 
     def _trunk_and_heads(self, n, logp, value, stem_done=False):
         s = L.stream_ptr()
@@ -255,7 +267,8 @@ class NativeForward(object):
                 inp = src if cur < 0 else outs[cur]
                 if self.fused_head and i == len(self.layers) - 1 and l['cin'] == 128:
                     L.check(lib.rz_net_conv3x3_tc2_head(
-                        L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), n, self.H, l['cin'], int(l['relu']),
+                        L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), n, self.H, self.W, l['cin'],
+                        int(l['relu']),
                         self.w1x1_host.ctypes.data_as(C.c_void_p), self.b1x1_host.ctypes.data_as(C.c_void_p),
                         L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc2_head')
                     L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(self.feat), 2, L.ptr(logp), L.ptr(value),
@@ -263,8 +276,8 @@ class NativeForward(object):
                     return
                 if self.conv_rev == 2:
                     L.check(lib.rz_net_conv3x3_tc2(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
-                                                   L.ptr(outs[dst]), n, self.H, l['cin'], int(l['relu']),
-                                                   2, 0, self.n_ctas, s), 'rz_net_conv3x3_tc2')
+                                                   L.ptr(outs[dst]), n, self.H, self.W, l['cin'],
+                                                   int(l['relu']), 2, 0, self.n_ctas, s), 'rz_net_conv3x3_tc2')
                 else:
                     L.check(lib.rz_net_conv3x3_tc(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
                                                   L.ptr(outs[dst]), n, self.H, l['cin'], int(l['relu']),
@@ -338,9 +351,9 @@ class NativeForward(object):
         elif self.mode == 'tc':
             self.act0[:n].zero_()
             t = self.act0[:n].view(n, 16, 16, 64)
-            t[:, :self.H, :self.H, :4] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+            t[:, :self.H, :self.W, :4] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
         else:
-            self.act0[:n] = x.permute(0, 2, 3, 1).reshape(n, self.A, 4)
+            self.act0[:n] = x.permute(0, 2, 3, 1).reshape(n, self.HW, 4)
         self._trunk_and_heads(n, self.logp, self.value, stem_done)
         return self.logp[:n, :self.A], self.value[:n]
 

@@ -85,13 +85,15 @@ class AlphaZeroMCTS(object):
     # ---------------------------------------------------------------- plumbing
     def _ensure_forest(self, env):
         f = self._forest
-        if (f is not None and f.H == env.board_size and f.k == env.n_in_row
-                and f.n_playout == self.n_playout and f.c_puct == float(self._c_puct)):
-            return f
+        width = getattr(env, 'board_width', env.board_size)
+        game_type = getattr(env, 'game_type', L.GAME_GOMOKU)
+        if (f is not None and f.H == env.board_size and f.W == width and f.game_type == game_type
+                and f.k == env.n_in_row and self.n_playout <= f.n_playout and f.c_puct == float(self._c_puct)):
+            return f     # n_playout may be lowered between moves (the pools were sized for the larger one)
         carry = 64 if self.rule == L.RULE_UCT else self.n_playout
         self._forest = SearchForest(1, env.board_size, env.n_in_row, n_playout=self.n_playout,
                                     c_puct=self._c_puct, rule=self.rule, max_carry=carry,
-                                    device=self.device)
+                                    device=self.device, board_width=width, game_type=game_type)
         native = getattr(self, '_native_evaluator', None)
         if native is None:
             native = getattr(self.policy_value_fn, 'device_evaluator', None)
@@ -100,7 +102,8 @@ class AlphaZeroMCTS(object):
         else:
             h, k = env.board_size, env.n_in_row
             self._evaluator = _NumpyNoiseCallback(
-                self.policy_value_fn, lambda rows, meta: LeafEnvView(rows, meta, h, k), self.add_noise)
+                self.policy_value_fn, lambda rows, meta: LeafEnvView(rows, meta, h, k, width, game_type),
+                self.add_noise)
         return self._forest
 
     def _upload(self, env):
@@ -192,7 +195,8 @@ class AlphaZeroPlayer(Player):
     def get_action(self, game_env, temperature=1e-3, return_prob=False):
         sensible_moves = game_env.leagel_actions()
         # the pi vector returned by MCTS as in the alphaGo Zero paper
-        move_probs = np.zeros(game_env.board_size * game_env.board_size)
+        # board_size**2 in the reference (:144); envs with another action set say so via n_actions
+        move_probs = np.zeros(getattr(game_env, 'n_actions', game_env.board_size * game_env.board_size))
         if len(sensible_moves) == 0:
             print('WARNING: the board is full')
             return None

@@ -26,7 +26,7 @@ class BatchedSelfPlay(object):
     def __init__(self, n_games, board_size=15, n_in_row=5, net=None, n_playout=800, c_puct=5.0,
                  rule=L.RULE_UCT, temperature=1.0, add_noise=True, noise_eps=0.25, noise_alpha=0.3,
                  device='cuda', global_offset=0, seed=0, evaluator=None, ring_capacity=None,
-                 store_priors=True, n_ctas=0):
+                 store_priors=True, n_ctas=0, board_width=None, game_type=L.GAME_GOMOKU):
         self.G = int(n_games)
         self.n_playout = int(n_playout)
         self.temperature = float(temperature)
@@ -36,11 +36,11 @@ class BatchedSelfPlay(object):
         self.forest = SearchForest(self.G, board_size, n_in_row, n_playout=n_playout, c_puct=c_puct,
                                    rule=rule, device=device, global_offset=global_offset,
                                    with_trajectories=True, ring_capacity=ring_capacity,
-                                   store_priors=store_priors)
+                                   store_priors=store_priors, board_width=board_width, game_type=game_type)
         if evaluator is None:
             if net is None:
                 raise ValueError('BatchedSelfPlay needs a policy-value module (net=) or an evaluator')
-            evaluator = NativeForward(net, max_batch=self.G, device=device, n_ctas=n_ctas)
+            evaluator = NativeForward(net, max_batch=self.G, device=device, n_ctas=n_ctas, game_type=game_type)
         self.evaluator = evaluator
         self.waves_in_move = 0
         self.moves_played = 0
@@ -58,7 +58,12 @@ class BatchedSelfPlay(object):
         for gid in ids:
             rs = np.random.RandomState(1000 + int(gid))
             k = (1000 + int(gid)) % max_random_moves
-            lists.append(rs.permutation(f.A)[:k].tolist())
+            if f.game_type == L.GAME_CONNECT4:
+                # k random drops; a column is used at most H times
+                seq = np.repeat(np.arange(f.W), f.H)
+                lists.append(rs.permutation(seq)[:min(k, f.cells - 1)].tolist())
+            else:
+                lists.append(rs.permutation(f.A)[:k].tolist())
         f.set_positions(lists)
         import ctypes as C
         L.check(f.lib.rz_gomoku_reset(C.byref(f.gdesc), L.ptr(f.root_rows), L.ptr(f.root_meta), f.G, 1,
@@ -193,17 +198,17 @@ class BatchedSelfPlay(object):
         f = self.forest
         out = f.drain_trajectories()
         rows, info = out['rows'], out['info']
-        n, H = len(info), f.H
-        states = np.zeros((n, 4, H, H), dtype=np.float32)
+        n, H, W = len(info), f.H, f.W
+        states = np.zeros((n, 4, H, W), dtype=np.float32)
         if n:
-            bits = ((rows[:, :, :, None] >> np.arange(H, dtype=np.uint32)[None, None, None, :]) & 1).astype(np.float32)
+            bits = ((rows[:, :, :, None] >> np.arange(W, dtype=np.uint32)[None, None, None, :]) & 1).astype(np.float32)
             mover = info[:, 0]
             idx = np.arange(n)
             states[:, 0] = bits[idx, mover]
             states[:, 1] = bits[idx, 1 - mover]
             last = info[:, 1]
             has_last = last >= 0
-            states[idx[has_last], 2, last[has_last] // H, last[has_last] % H] = 1.0
+            states[idx[has_last], 2, last[has_last] // W, last[has_last] % W] = 1.0
             stones = bits.sum(axis=(1, 2, 3)).astype(np.int64)
             states[stones % 2 == 0, 3] = 1.0
         return states, out['pi'], info[:, 2].astype(np.float32), info

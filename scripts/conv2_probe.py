@@ -49,7 +49,7 @@ def run_one(cg, flags):
             L.check(lib.rz_net_conv3x3_tc(L.ptr(xt), L.ptr(wt), L.ptr(b), L.ptr(rt), L.ptr(out), n, h, cin, relu,
                                           0, L.stream_ptr()), 'conv v1')
         else:
-            L.check(lib.rz_net_conv3x3_tc2(L.ptr(xt), L.ptr(wt), L.ptr(b), L.ptr(rt), L.ptr(out), n, h, cin, relu,
+            L.check(lib.rz_net_conv3x3_tc2(L.ptr(xt), L.ptr(wt), L.ptr(b), L.ptr(rt), L.ptr(out), n, h, h, cin, relu,
                                            cg, flags, 0, L.stream_ptr()), 'conv v2')
         torch.cuda.synchronize()
         got = out.reshape(n, 16, 16, 128)[:, :h, :h, :].permute(0, 3, 1, 2).double()
@@ -71,7 +71,7 @@ def run_one(cg, flags):
         if cg == 0:
             lib.rz_net_conv3x3_tc(L.ptr(x), L.ptr(w), L.ptr(b), None, L.ptr(y), G, 15, 128, 1, 0, L.stream_ptr())
         else:
-            lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(w), L.ptr(b), None, L.ptr(y), G, 15, 128, 1, cg, flags, 0,
+            lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(w), L.ptr(b), None, L.ptr(y), G, 15, 15, 128, 1, cg, flags, 0,
                                    L.stream_ptr())
     e1.record()
     torch.cuda.synchronize()

@@ -49,7 +49,7 @@ def main():
     z = nf.bufs[1]
     for name, res in (('conv3x3_tc2', None), ('conv3x3_tc2+residual', z)):
         def conv2():
-            L.check(lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), L.ptr(y), B, H,
+            L.check(lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), L.ptr(y), B, H, H,
                                            128, 1, 2, 0, ctas, L.stream_ptr()))
         ms = timeit(conv2)
         print(json.dumps({'kernel': name, 'B': B, 'ms': ms, 'TFLOPs_algorithmic': flops_alg / ms / 1e9,
@@ -65,7 +65,7 @@ def main():
     import ctypes as C
 
     def conv_head():
-        L.check(lib.rz_net_conv3x3_tc2_head(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), L.ptr(z), B, H, 128, 1,
+        L.check(lib.rz_net_conv3x3_tc2_head(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), L.ptr(z), B, H, H, 128, 1,
                                             nf.w1x1_host.ctypes.data_as(C.c_void_p),
                                             nf.b1x1_host.ctypes.data_as(C.c_void_p), L.ptr(nf.feat), ctas,
                                             L.stream_ptr()))

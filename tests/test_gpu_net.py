@@ -53,7 +53,7 @@ def test_conv3x3_tc_matches_torch(n, h, cin, relu, res, rev):
                                       n, h, cin, relu, 0, L.stream_ptr()), 'conv')
     else:
         L.check(lib.rz_net_conv3x3_tc2(L.ptr(xt), L.ptr(wt), L.ptr(b.contiguous()), L.ptr(rt), L.ptr(out),
-                                       n, h, cin, relu, 2 if rev == 'v2_pair' else 1, 0, 0, L.stream_ptr()),
+                                       n, h, h, cin, relu, 2 if rev == 'v2_pair' else 1, 0, 0, L.stream_ptr()),
                 'conv2')
     torch.cuda.synchronize()
     got = _from_tile(out, h).double()
@@ -232,8 +232,8 @@ def test_fused_stem_matches_encode_plus_conv(size, n):
     L.check(lib.rz_gomoku_encode_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(act0), n, L.stream_ptr()), 'enc')
     l0 = nf.layers[0]
     plain = torch.full((n, 256, 128), 5.0, dtype=torch.bfloat16, device='cuda')
-    L.check(lib.rz_net_conv3x3_tc2(L.ptr(act0), L.ptr(l0['w']), L.ptr(l0['b']), None, L.ptr(plain), n, size, 64, 1,
-                                   2, 0, 0, L.stream_ptr()), 'conv')
+    L.check(lib.rz_net_conv3x3_tc2(L.ptr(act0), L.ptr(l0['w']), L.ptr(l0['b']), None, L.ptr(plain), n, size, size,
+                                   64, 1, 2, 0, 0, L.stream_ptr()), 'conv')
     torch.cuda.synchronize()
     # same bf16 products, fp32 accumulation in a different order: equal up to one bf16 ulp
     d = (fused.float() - plain.float()).abs()
