@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Throughput of the parity-case configurations of BASELINE.json (NOT the bench line, which is
+config 3 in bench.py): config 1 TicTacToe / 25 sims / stock net, config 2 Connect Four / 200 sims /
+4096 games / ResNet-6.  One JSON line per configuration."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rlzero_b200 import _lib as L  # noqa: E402
+from rlzero_b200.games.gomoku.policy_value_net import PolicyValueNet, ResNetPolicyValueNet  # noqa: E402
+from rlzero_b200.selfplay import BatchedSelfPlay  # noqa: E402
+
+
+def run(name, sp, waves, warm):
+    sp.set_random_start_positions(max_random_moves=3)
+    sp.warm_up()
+    for _ in range(warm):
+        sp.step_wave()
+    torch.cuda.synchronize()
+    g0 = sp.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(waves):
+        sp.step_wave()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    g1 = sp.stats()
+    sp.forest.raise_faults()
+    games = g1['games_done'] - g0['games_done']
+    print(json.dumps({'config': name, 'games': sp.G, 'n_playout': sp.n_playout, 'waves': waves,
+                      'ms_per_wave': ms / waves, 'simulations_per_s': sp.G * waves / ms * 1e3,
+                      'games_finished': games, 'games_per_hour': games / (ms / 1e3) * 3600.0,
+                      'wall_s': time.time() - t0}), flush=True)
+
+
+def main():
+    torch.manual_seed(0)
+    # config 1: TicTacToe = GomokuEnv(3, 3), 25 simulations/move, stock PolicyValueNet (fp32 path)
+    net1 = PolicyValueNet(3).cuda().eval()
+    for G in (1, 8192):
+        sp = BatchedSelfPlay(G, 3, 3, net=net1, n_playout=25, add_noise=True, seed=1)
+        run('config1 TicTacToe 3x3 k=3, 25 sims/move, stock PolicyValueNet fp32, %d game(s)' % G, sp,
+            25 * 40, 25)
+    # config 2: Connect Four 6x7, 200 simulations/move, 4096 games, ResNet-6 bf16
+    net2 = ResNetPolicyValueNet(6, n_blocks=6, board_width=7, n_actions=7).cuda().eval()
+    sp = BatchedSelfPlay(4096, 6, 4, net=net2, n_playout=200, add_noise=True, seed=2, board_width=7,
+                         game_type=L.GAME_CONNECT4)
+    run('config2 Connect Four 6x7, 200 sims/move, ResNet-6 bf16, 4096 games', sp, 200 * 12, 200)
+
+
+if __name__ == '__main__':
+    main()
