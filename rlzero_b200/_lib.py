@@ -90,6 +90,10 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.c_int, _vp]),
     'rz_net_conv3x3_tc2_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                                           _vp, _vp, C.c_int, _vp]),
+    'rz_net_conv3x3_tc3': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, _vp]),
+    'rz_net_conv3x3_tc3_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
+                                          _vp, _vp, C.c_int, _vp]),
     'rz_net_stem_tc': (C.c_int, [_GD, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_net_stem_tc_planes': (C.c_int, [_GD, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_net_conv3x3_f32': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -73,6 +73,7 @@ struct HeadsParams {
   float* logp;            // [B][AS]
   float* value;           // [B]
   int n_boards, H, W, HW, A, AS;   // H x W squares (HW), A policy outputs
+  int S, P;                        // padded layout of tile / feature sources: row stride S, P = S*S rows per board
 };
 
 // 256-bit read-only global load: one full 32-byte sector per lane (sm_100 LDG.E.256)
@@ -84,12 +85,12 @@ __device__ __forceinline__ void rz_ld_global_nc_v8(const void* p, uint32_t (&r)[
 
 // 6 dot products of one position's 128 channels with the 1x1 filters in shared memory
 template <bool kTile>
-__device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos, int W, int HW,
+__device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos, int W, int HW, int S, int P,
                                                  const float* __restrict__ s_w, float (&acc)[6]) {
   const float4* w4 = reinterpret_cast<const float4*>(s_w);
   if constexpr (kTile) {
     const int y = pos / W, x = pos - y * W;
-    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(act) + ((size_t)b * 256 + y * 16 + x) * HEAD_C;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(act) + ((size_t)b * P + y * S + x) * HEAD_C;
     uint32_t raw[8][8];  // the whole row: 8 x 32 B, all loads in flight before the first use
 #pragma unroll
     for (int j = 0; j < 8; ++j) rz_ld_global_nc_v8(src + j * 16, raw[j]);
@@ -151,22 +152,23 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
   if (kSrc == SRC_FEAT) {
     // phase 1': the 1x1 convolutions were applied by the last trunk layer's epilogue
     // (rz_net_conv3x3_tc2_head): gather feat[b][f][y*16+x] (coalesced along x) into k-major order
-    const float* feat = reinterpret_cast<const float*>(p.act) + (size_t)b0 * (6 * 256);
-    // iterate over the tile positions t = y*16+x of [bi][f] (coalesced), 4 loads in flight
-    for (int i0 = tid; i0 < HEAD_NB * 6 * 256; i0 += 4 * HEAD_THREADS) {
+    const int FP = 6 * p.P;   // floats per board in feat[b][f][y*S+x]
+    const float* feat = reinterpret_cast<const float*>(p.act) + (size_t)b0 * FP;
+    // iterate over the padded positions of [bi][f] (coalesced), 4 loads in flight
+    for (int i0 = tid; i0 < HEAD_NB * FP; i0 += 4 * HEAD_THREADS) {
       float v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * HEAD_THREADS;
-        const int bi = i / (6 * 256);
-        v[u] = (i < HEAD_NB * 6 * 256 && bi < nb) ? feat[i] : 0.0f;
+        const int bi = i / FP;
+        v[u] = (i < HEAD_NB * FP && bi < nb) ? feat[i] : 0.0f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u * HEAD_THREADS;
-        const int bi = i / (6 * 256), r = i - bi * (6 * 256);
-        const int f = r >> 8, y = (r >> 4) & 15, x = r & 15;
-        if (i < HEAD_NB * 6 * 256 && x < p.W && y < p.H) s_f[feat_slot(f * HW + y * p.W + x, bi)] = v[u];
+        const int bi = i / FP, r = i - bi * FP;
+        const int f = r / p.P, t = r - f * p.P, y = t / p.S, x = t - y * p.S;
+        if (i < HEAD_NB * FP && x < p.W && y < p.H) s_f[feat_slot(f * HW + y * p.W + x, bi)] = v[u];
       }
     }
   } else {
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
       float acc[6];
 #pragma unroll
       for (int f = 0; f < 6; ++f) acc[f] = p.b1x1[f];
-      if (bi < nb) conv1x1_position<kSrc == SRC_TILE>(p.act, b0 + bi, pos, p.W, HW, s_w, acc);
+      if (bi < nb) conv1x1_position<kSrc == SRC_TILE>(p.act, b0 + bi, pos, p.W, HW, p.S, p.P, s_w, acc);
 #pragma unroll
       for (int f = 0; f < 6; ++f) s_f[feat_slot(f * HW + pos, bi)] = bi < nb ? fmaxf(acc[f], 0.0f) : 0.0f;
     }
@@ -338,7 +340,7 @@ extern "C" int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_
   RZ_REQUIRE(h->board_size >= 1 && h->board_size <= RZ_MAX_BOARD, "rz_net_heads: board_size %d", h->board_size);
   const int W = h->width > 0 ? h->width : h->board_size;
   RZ_REQUIRE(W >= 1 && W <= RZ_MAX_BOARD, "rz_net_heads: width %d", W);
-  RZ_REQUIRE(!act_is_tile_bf16 || (h->board_size <= 15 && W <= 15), "rz_net_heads: tile layout holds boards up to 15x15");
+  RZ_REQUIRE(!act_is_tile_bf16 || (h->board_size <= 19 && W <= 19), "rz_net_heads: padded layouts hold boards up to 19x19");
   const int HW = h->board_size * W;
   const int A = h->n_actions > 0 ? h->n_actions : HW;
   RZ_REQUIRE(h->action_stride >= A && (h->action_stride & 31) == 0, "rz_net_heads: action_stride %d", h->action_stride);
@@ -347,6 +349,8 @@ extern "C" int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_
   p.act = act; p.w1x1 = h->w1x1; p.b1x1 = h->b1x1; p.wp = h->wp; p.bp = h->bp; p.wv1 = h->wv1;
   p.bv1 = h->bv1; p.wv2 = h->wv2; p.bv2 = h->bv2; p.logp = logp; p.value = value;
   p.n_boards = n_boards; p.H = h->board_size; p.W = W; p.HW = HW; p.A = A; p.AS = h->action_stride;
+  p.S = (h->board_size <= 15 && W <= 15) ? 16 : 20;
+  p.P = p.S * p.S;
   const size_t smem = heads_smem(HW, p.AS);
   const int grid = (n_boards + HEAD_NB - 1) / HEAD_NB;
   if (act_is_tile_bf16 == 2) return heads_launch<SRC_FEAT>(p, smem, grid, (cudaStream_t)stream);

@@ -22,20 +22,23 @@ constexpr int OFF_B = 0;                 // [128 cout][64 k] bf16, SW128
 constexpr int OFF_A = 16384;             // [128 pos][64 k] bf16, SW128
 constexpr int OFF_STAGE = 32768;         // 2 x [128 pos][64 cout] bf16, SW128
 constexpr int OFF_CTRL = 65536;
-constexpr int STEM_SMEM = OFF_CTRL + 1024 + 1024;   // + alignment slack
+constexpr int STEM_SMEM = OFF_CTRL + 2048 + 1024;   // control block + alignment slack
 
 struct StemParams {
   const uint32_t* rows;   // [n][2][H]
   const int32_t* meta;    // [n][RZ_META_STRIDE]
   const float* planes;    // kPlanes: [n][4][H][H] float observation planes instead of bitboards
   const float* bias;      // [128]
-  int n_tiles;            // 2 per board
+  int n_tiles;            // 128-row tiles of the padded position layout
+  int n_boards;
   int H;                  // rows
   int W;                  // columns
   int relu;
 };
 
-template <bool kPlanes>
+// kS: row stride of the padded position layout (16: boards up to 15x15, 20: up to 19x19); a board
+// owns kS*kS consecutive rows, tiles of 128 rows may straddle two boards when kS = 20
+template <bool kPlanes, int kS>
 __global__ void __launch_bounds__(STEM_THREADS)
 rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                   const StemParams p) {
@@ -44,8 +47,9 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint8_t* al = smem_raw + (base - rz::smem_u32(smem_raw));
   const uint32_t bar_w = base + OFF_CTRL, bar_mma = base + OFF_CTRL + 8;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(al + OFF_CTRL + 16);
-  uint32_t* s_rows = reinterpret_cast<uint32_t*>(al + OFF_CTRL + 32);    // [2][16] + 4 meta words
-  float* s_bias = reinterpret_cast<float*>(al + OFF_CTRL + 256);         // [128]
+  uint32_t* s_rows = reinterpret_cast<uint32_t*>(al + OFF_CTRL + 32);    // 2 boards x ([2][32] rows + 4 meta words)
+  float* s_bias = reinterpret_cast<float*>(al + OFF_CTRL + 1024);        // [128]
+  constexpr int P = kS * kS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = p.H, W = p.W;
 
@@ -70,26 +74,26 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   uint32_t phase = 0;
   bool store_pending = false;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const int b = tile >> 1;
-    // ---- board of this tile -> shared memory (rows beyond H are zero)
+    const int b_first = (tile * 128) / P;
+    const int my_row = tile * 128 + tid;
+    const int b = my_row / P, bsel = b - b_first;       // this thread's board (0 or 1 within the tile)
+    // ---- the (at most two) boards of this tile -> shared memory (rows beyond H / boards beyond n are zero)
     if (!kPlanes) {
-      if (tid < 32) {
-        const int c = tid >> 4, y = tid & 15;
-        s_rows[tid] = (y < H) ? p.rows[((size_t)b * 2 + c) * H + y] : 0u;
-      } else if (tid < 36) {
-        const int k = tid - 32;  // player, last_move, stones
-        s_rows[32 + k] = (uint32_t)p.meta[(size_t)b * RZ_META_STRIDE + k];
-      }
+      const int sel = tid >> 6, t = tid & 63, bb = b_first + sel;
+      const int c = t >> 5, y = t & 31;
+      s_rows[sel * 68 + t] = (y < H && bb < p.n_boards) ? p.rows[((size_t)bb * 2 + c) * H + y] : 0u;
+      if (t < 4) s_rows[sel * 68 + 64 + t] = bb < p.n_boards ? (uint32_t)p.meta[(size_t)bb * RZ_META_STRIDE + t] : 0u;
     }
     if (tid == 0 && store_pending) rz::tma_store_wait_read();  // staging tile free again
     __syncthreads();
     // ---- im2col row of position r: k = tap*4 + plane (gomoku_env.py:95-114 per tap)
     {
-      const int pos = (tile & 1) * 128 + tid;
-      const int y = pos >> 4, x = pos & 15;
-      const int player = (int)s_rows[32] & 1, last = (int)s_rows[33], stones = (int)s_rows[34];
+      const int pos = my_row - b * P;
+      const int y = pos / kS, x = pos - y * kS;
+      const uint32_t* brd = s_rows + bsel * 68;
+      const int player = (int)brd[64] & 1, last = (int)brd[65], stones = (int)brd[66];
       const uint32_t colour = (stones & 1) ? 0u : ONE;
-      const bool out_inside = (x < W) && (y < H);
+      const bool out_inside = (x < W) && (y < H) && b < p.n_boards;
       uint32_t w[20];  // 5 chunks x 4 words (2 bf16 each): taps 0..8 (+ one empty tap slot)
 #pragma unroll
       for (int i = 0; i < 20; ++i) w[i] = 0u;
@@ -107,7 +111,7 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             f3 = __bfloat16_as_ushort(__float2bfloat16_rn(src[3 * H * W]));
           }
         } else {
-          const uint32_t mine = s_rows[player * 16 + (yy & 15)], theirs = s_rows[(player ^ 1) * 16 + (yy & 15)];
+          const uint32_t mine = brd[player * 32 + (yy & 31)], theirs = brd[(player ^ 1) * 32 + (yy & 31)];
           f0 = in ? ((mine >> (xx & 31)) & 1u) * ONE : 0u;
           f1 = in ? ((theirs >> (xx & 31)) & 1u) * ONE : 0u;
           f2 = (in && stones > 0 && last == yy * W + xx) ? ONE : 0u;
@@ -140,8 +144,8 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     rz::tc_fence_after();
     // ---- epilogue: row per thread
     {
-      const int pos = (tile & 1) * 128 + tid;
-      const bool valid = ((pos & 15) < W) && ((pos >> 4) < H);
+      const int pos = my_row - b * P;
+      const bool valid = (pos % kS < W) && (pos / kS < H) && b < p.n_boards;
       const uint32_t stage_row = base + OFF_STAGE + (uint32_t)tid * 128u;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -190,24 +194,35 @@ static int stem_launch(const rz_game_desc* g, const uint32_t* rows, const int32_
                        const void* weight, const float* bias, void* act_out, int n_boards, int relu,
                        int n_ctas, void* stream) {
   if (n_boards == 0) return 0;
+  const int H = g->board_size, W = g->width > 0 ? g->width : g->board_size;
+  const int S = (H <= 15 && W <= 15) ? 16 : 20;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rz_stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(rz_stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(rz_stem_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rz_stem_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rz_stem_tc_kernel<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rz_stem_tc_kernel<true, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
     if (e != cudaSuccess) { rz_set_error("rz_net_stem_tc: smem attribute: %s", cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
+  // the output tensor is padded to a multiple of 256 rows (the convolutions work on pairs of 128-row tiles)
+  const long long rows_alloc = ((long long)n_boards * S * S + 255) / 256 * 256;
   CUtensorMap tmap_w, tmap_out;
   if (rz::make_tmap_2d(&tmap_w, weight, 128, 64, 128)) return -1;
-  if (rz::make_tmap_2d(&tmap_out, act_out, (uint64_t)n_boards * 256, 128, 128)) return -1;
+  if (rz::make_tmap_2d(&tmap_out, act_out, (uint64_t)rows_alloc, 128, 128)) return -1;
   StemParams p;
   p.rows = rows; p.meta = meta; p.planes = planes; p.bias = bias;
-  p.n_tiles = n_boards * 2; p.H = g->board_size; p.W = g->width > 0 ? g->width : g->board_size; p.relu = relu;
+  p.n_tiles = (int)(rows_alloc / 128); p.n_boards = n_boards; p.H = H; p.W = W; p.relu = relu;
   int ctas = n_ctas > 0 ? n_ctas : 148 * 3;
   if (ctas > p.n_tiles) ctas = p.n_tiles;
-  if (planes) rz_stem_tc_kernel<true><<<ctas, STEM_THREADS, STEM_SMEM, (cudaStream_t)stream>>>(tmap_w, tmap_out, p);
-  else        rz_stem_tc_kernel<false><<<ctas, STEM_THREADS, STEM_SMEM, (cudaStream_t)stream>>>(tmap_w, tmap_out, p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S == 16) {
+    if (planes) rz_stem_tc_kernel<true, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+    else        rz_stem_tc_kernel<false, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+  } else {
+    if (planes) rz_stem_tc_kernel<true, 20><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+    else        rz_stem_tc_kernel<false, 20><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+  }
   RZ_LAUNCH_CHECK("rz_net_stem_tc");
   return 0;
 }
@@ -217,7 +232,7 @@ extern "C" int rz_net_stem_tc(const rz_game_desc* g, const uint32_t* rows, const
                               int relu, int n_ctas, void* stream) {
   if (rz_check_game(g)) return -1;
   RZ_REQUIRE(rows && meta && weight && bias && act_out, "rz_net_stem_tc: null argument");
-  RZ_REQUIRE(g->board_size <= 15 && g->width <= 15, "rz_net_stem_tc: the 16x16 tile layout holds boards up to 15x15");
+  RZ_REQUIRE(g->board_size <= 19 && g->width <= 19, "rz_net_stem_tc: the padded tile layouts hold boards up to 19x19");
   RZ_REQUIRE(n_boards >= 0, "rz_net_stem_tc: n_boards %d", n_boards);
   return stem_launch(g, rows, meta, nullptr, weight, bias, act_out, n_boards, relu, n_ctas, stream);
 }
@@ -227,7 +242,7 @@ extern "C" int rz_net_stem_tc_planes(const rz_game_desc* g, const float* planes,
                                      void* stream) {
   if (rz_check_game(g)) return -1;
   RZ_REQUIRE(planes && weight && bias && act_out, "rz_net_stem_tc_planes: null argument");
-  RZ_REQUIRE(g->board_size <= 15 && g->width <= 15, "rz_net_stem_tc_planes: the 16x16 tile layout holds boards up to 15x15");
+  RZ_REQUIRE(g->board_size <= 19 && g->width <= 19, "rz_net_stem_tc_planes: the padded tile layouts hold boards up to 19x19");
   RZ_REQUIRE(n_boards >= 0, "rz_net_stem_tc_planes: n_boards %d", n_boards);
   return stem_launch(g, nullptr, nullptr, planes, weight, bias, act_out, n_boards, relu, n_ctas, stream);
 }

@@ -1,0 +1,351 @@
+// rlzero_b200 -- 3x3 convolution of the policy-value trunk, revision 3: the data path of revision 2
+// (rz_net_tc2.cu: weights resident in shared memory over a CTA pair, activation tile loaded once
+// with its halo, row-shifted UMMA descriptors for the 9 taps, cta_group::2 MMAs) for ANY row
+// stride of the padded position layout, so that 19x19 boards run on the tensor cores too.
+//
+// Reference op: nn.Conv2d(128, 128, 3, padding=1) (+ folded BatchNorm, residual, ReLU) of the
+// trunk (rlzero/games/gomoku/policy_value_net.py:14-16,36-38; ResNet-N trunk of SURVEY.md 7;
+// BASELINE.json config 4: 19x19 board, ResNet-20).
+//
+// Layout: act[row][c] bf16 with row = board*P + y*S + x, P = S*S, S = 16 (boards up to 15x15) or
+// 20 (up to 19x19); squares with x >= W or y >= H hold zero, which gives every tap its halo (see
+// rz_net_tc.cu).  Tiles are 128 consecutive rows and need not be aligned to boards (P = 400 is not
+// a multiple of 128); the tensor is padded to a multiple of 256 rows.
+//
+// What changes against revision 2, and why: the halo tile of stride 20 has 128 + 2*21 = 170 rows;
+// two double-buffered 2-k-block tiles (87 KB) + the 147 KB of weights exceed the 227 KB of shared
+// memory.  So
+//   * the MMA loop runs k-block-outer (all 9 taps of input channels 0..63, then 64..127) and the
+//     activation k-block tiles (170 x 128 B = 21.8 KB) cycle through a 3-slot ring: a slot is
+//     released as soon as its 36 MMAs have completed, half a tile early, and refilled with the
+//     next tile's data;
+//   * the epilogue stages the bf16 output tile in two halves of 64 channels through one 16 KB
+//     buffer (TMA store per half) instead of re-using a whole activation buffer.
+// Shared memory: 147456 (weights) + 3*21760 (ring) + 16384 (staging) + 1024 = 230144 B.
+#include <cuda_bf16.h>
+
+#include "rz_common.cuh"
+#include "rz_tc.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int B_TILE_BYTES = 64 * 128;            // 64 output channels x 64 input channels
+constexpr int B_BYTES = 9 * 2 * B_TILE_BYTES;     // 147456
+constexpr int STAGE_BYTES = TILE_M * 128;         // 128 rows x 64 channels bf16
+constexpr int NUM_THREADS = 192;
+constexpr int N_SLOTS = 3;
+
+template <int kS>
+struct Geo {
+  static constexpr int HALO = kS + 1;
+  static constexpr int A_ROWS = TILE_M + 2 * HALO;
+  static constexpr int SLOT_BYTES = A_ROWS * 128;
+  static constexpr int P = kS * kS;
+  static constexpr int OFF_RING = B_BYTES;
+  static constexpr int OFF_STAGE = (OFF_RING + N_SLOTS * SLOT_BYTES + 127) / 128 * 128;
+  static constexpr int OFF_CTRL = OFF_STAGE + STAGE_BYTES;
+  static constexpr int SMEM = OFF_CTRL + 1024;
+};
+
+struct Conv3Params {
+  const float* bias;               // [128]
+  const __nv_bfloat16* residual;   // [rows][128] or null
+  int n_items;                     // pairs of 128-row tiles
+  int total_rows;                  // n_boards * P (rows beyond it are padding)
+  int H, W;
+  int relu;
+};
+
+struct HeadTaps3 {
+  float w[6 * 128];                // [filter][channel]
+  float b[6];
+  float* feat;                     // [n_boards][6][P] float32
+};
+
+template <int kS, bool kHead>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
+                      const __grid_constant__ CUtensorMap tmap_w,
+                      const __grid_constant__ CUtensorMap tmap_out, const Conv3Params p,
+                      const __grid_constant__ HeadTaps3 head) {
+  using G = Geo<kS>;
+  static_assert(G::SMEM <= 232448, "shared memory budget");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = rz::smem_u32(smem_raw);
+  const uint32_t ring = smem_base + G::OFF_RING;
+  const uint32_t stage = smem_base + G::OFF_STAGE;
+  const uint32_t ctrl = smem_base + G::OFF_CTRL;
+  uint8_t* ctrl_ptr = smem_raw + G::OFF_CTRL;
+  const uint32_t bar_bfull = ctrl, bar_afull = ctrl + 8, bar_aempty = ctrl + 32;
+  const uint32_t bar_tfull = ctrl + 56, bar_tempty = ctrl + 72;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ctrl_ptr + 88);
+  float* s_bias = reinterpret_cast<float*>(ctrl_ptr + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = rz::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int worker = blockIdx.x >> 1, n_workers = gridDim.x >> 1;
+
+  if (threadIdx.x == 0 && (smem_base & 1023u)) __trap();
+  if (warp == 0 && lane == 0) {
+    rz::tma_prefetch_desc(&tmap_act);
+    rz::tma_prefetch_desc(&tmap_w);
+    rz::tma_prefetch_desc(&tmap_out);
+    rz::mbar_init(bar_bfull, 1);
+    for (int s = 0; s < N_SLOTS; ++s) {
+      rz::mbar_init(bar_afull + 8 * s, 1);
+      rz::mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      rz::mbar_init(bar_tfull + 8 * b, 1);
+      rz::mbar_init(bar_tempty + 8 * b, 8);     // 4 epilogue warps of each CTA
+    }
+    rz::fence_barrier_init();
+  }
+  if (warp == 1) { rz::tmem_alloc_pair(rz::smem_u32(tmem_holder), 256); rz::tmem_relinquish_pair(); }
+  if (threadIdx.x >= 64) s_bias[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+  rz::tc_fence_before();
+  rz::cluster_sync_all();
+  rz::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer: weights once, then one (tile, k-block) halo tile per ring slot =====
+    if (lane == 0) {
+      const uint32_t l_bfull = rz::mapa_shared(bar_bfull, 0);
+      if (leader) rz::mbar_expect_tx(bar_bfull, (uint32_t)(2 * 18 * B_TILE_BYTES));
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kb = 0; kb < 2; ++kb)
+          rz::tma_load_2d_pair(smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES, &tmap_w, l_bfull, kb * 64,
+                               tap * 128 + (int)rank * 64);
+      int u = 0;   // running (tile, k-block) index
+      for (int item = worker; item < p.n_items; item += n_workers) {
+        const int row0 = item * 256 + (int)rank * TILE_M - G::HALO;
+        for (int kb = 0; kb < 2; ++kb, ++u) {
+          const int slot = u % N_SLOTS;
+          rz::mbar_wait(bar_aempty + 8 * slot, ((uint32_t)(u / N_SLOTS) & 1u) ^ 1u);
+          if (leader) rz::mbar_expect_tx(bar_afull + 8 * slot, (uint32_t)(2 * G::SLOT_BYTES));
+          rz::tma_load_2d_pair(ring + (uint32_t)slot * G::SLOT_BYTES, &tmap_act,
+                               rz::mapa_shared(bar_afull + 8 * slot, 0), kb * 64, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA =====
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = rz::umma_idesc_bf16(256, 128);
+      rz::mbar_wait(bar_bfull, 0);
+      int it = 0, u = 0;
+      for (int item = worker; item < p.n_items; item += n_workers, ++it) {
+        const int buf = it & 1;
+        rz::mbar_wait(bar_tempty + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < 2; ++kb, ++u) {
+          const int slot = u % N_SLOTS;
+          rz::mbar_wait(bar_afull + 8 * slot, (uint32_t)(u / N_SLOTS) & 1u);
+          rz::tc_fence_after();
+          const uint32_t a_slot = ring + (uint32_t)slot * G::SLOT_BYTES;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int shift = G::HALO + (tap / 3 - 1) * kS + (tap % 3 - 1);
+            const uint64_t adesc = rz::umma_desc_sw128(a_slot + (uint32_t)shift * 128u);
+            const uint64_t bdesc = rz::umma_desc_sw128(smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              rz::umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
+              acc = 1;
+            }
+          }
+          rz::umma_commit_pair(bar_aempty + 8 * slot, 3);   // both CTAs may refill this ring slot
+        }
+        rz::umma_commit_pair(bar_tfull + 8 * buf, 3);       // accumulator complete in both CTAs
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4, one output row per thread =====
+    const int q = warp & 3;
+    int it = 0;
+    bool store_pending = false;
+    for (int item = worker; item < p.n_items; item += n_workers, ++it) {
+      const int buf = it & 1;
+      const int row0 = item * 256 + (int)rank * TILE_M;
+      const int r_in_tile = q * 32 + lane;
+      const int row = row0 + r_in_tile;
+      const int board = row / G::P, pos = row - board * G::P;
+      const int y = pos / kS, x = pos - y * kS;
+      const bool in_tensor = row < p.total_rows;
+      const bool valid = in_tensor && x < p.W && y < p.H;
+      uint32_t res[8][8];
+      const bool have_res = p.residual != nullptr && valid;
+      if (have_res) {
+        const __nv_bfloat16* rrow = p.residual + (size_t)row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
+      }
+      rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
+      rz::tc_fence_after();
+      float hacc[6];
+#pragma unroll
+      for (int f = 0; f < 6; ++f) hacc[f] = kHead ? head.b[f] : 0.0f;
+      const uint32_t srow = stage + (uint32_t)r_in_tile * 128u;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t acc[32];
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + ch * 32), acc);
+        rz::tmem_ld_wait();
+        if (ch == 3) {
+          rz::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) rz::mbar_arrive_cluster_relaxed(rz::mapa_shared(bar_tempty + 8 * buf, 0));
+        }
+        if (!kHead && (ch & 1) == 0) {
+          // the staging buffer is free once the previous half's TMA store has read it
+          if (warp == 2 && lane == 0 && store_pending) rz::tma_store_wait_read();
+          rz::named_bar_sync(1, 128);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = j * 8 + e * 2;
+            float v0 = __uint_as_float(acc[c]) + s_bias[ch * 32 + c];
+            float v1 = __uint_as_float(acc[c + 1]) + s_bias[ch * 32 + c + 1];
+            if (have_res) {
+              const uint32_t rw = res[ch * 2 + (j >> 1)][(j & 1) * 4 + e];
+              v0 += __uint_as_float(rw << 16);
+              v1 += __uint_as_float(rw & 0xffff0000u);
+            }
+            if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+            if (!valid) { v0 = 0.0f; v1 = 0.0f; }
+            const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
+            packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
+            if (kHead) {
+              const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xffff0000u);
+#pragma unroll
+              for (int f = 0; f < 6; ++f)
+                hacc[f] = fmaf(r1, head.w[f * 128 + ch * 32 + c + 1], fmaf(r0, head.w[f * 128 + ch * 32 + c], hacc[f]));
+            }
+          }
+          if (!kHead) {
+            const uint32_t chunk = (uint32_t)((ch & 1) * 4 + j);
+            rz::st_shared_v4(srow + ((chunk ^ ((srow >> 7) & 7u)) << 4), packed[0], packed[1], packed[2], packed[3]);
+          }
+        }
+        if (!kHead && (ch & 1) == 1) {
+          rz::fence_proxy_async();
+          rz::named_bar_sync(2, 128);
+          if (warp == 2 && lane == 0) {
+            rz::tma_store_2d(&tmap_out, stage, (ch >> 1) * 64, row0);
+            rz::tma_store_commit();
+          }
+          store_pending = true;
+        }
+      }
+      if (kHead && in_tensor) {
+        float* fo = head.feat + (size_t)board * (6 * G::P) + pos;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) fo[f * G::P] = fmaxf(hacc[f], 0.0f);
+      }
+    }
+    if (warp == 2 && lane == 0 && store_pending) rz::tma_store_wait_all();
+  }
+
+  rz::tc_fence_before();
+  rz::cluster_sync_all();
+  if (warp == 1) {
+    rz::tc_fence_after();
+    rz::tmem_dealloc_pair(tmem_base, 256);
+  }
+}
+
+template <int kS, bool kHead>
+int launch3(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const Conv3Params& p,
+            const HeadTaps3& head, int ctas, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rz_conv3x3_tc3_kernel<kS, kHead>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Geo<kS>::SMEM);
+    if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc3: smem attribute: %s", cudaGetErrorString(e)); return -2; }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Geo<kS>::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, rz_conv3x3_tc3_kernel<kS, kHead>, ta, tw, to, p, head);
+  if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc3: launch failed: %s", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
+}  // namespace
+
+// act_in / act_out / residual: bf16 [rows_alloc][128] with rows_alloc = round_up(n_boards * S*S, 256)
+static int conv3_entry(const void* act_in, const void* weight, const float* bias, const void* residual,
+                       void* act_out, int n_boards, int board_rows, int board_cols, int row_stride, int relu,
+                       int n_ctas, const float* w1x1_host, const float* b1x1_host, float* feat, void* stream) {
+  RZ_REQUIRE(act_in && weight && bias, "rz_net_conv3x3_tc3: null argument");
+  RZ_REQUIRE(n_boards >= 0, "rz_net_conv3x3_tc3: n_boards %d", n_boards);
+  RZ_REQUIRE(row_stride == 16 || row_stride == 20, "rz_net_conv3x3_tc3: row_stride %d (16 or 20)", row_stride);
+  RZ_REQUIRE(board_rows >= 1 && board_rows < row_stride && board_cols >= 1 && board_cols < row_stride,
+             "rz_net_conv3x3_tc3: board %dx%d does not fit row stride %d", board_rows, board_cols, row_stride);
+  RZ_REQUIRE(act_in != act_out, "rz_net_conv3x3_tc3: in-place convolution is not supported");
+  if (n_boards == 0) return 0;
+  const long long total = (long long)n_boards * row_stride * row_stride;
+  const long long rows_alloc = (total + 255) / 256 * 256;
+  static HeadTaps3 head;
+  CUtensorMap tmap_act, tmap_w, tmap_out;
+  const uint32_t a_rows = TILE_M + 2 * (row_stride + 1);
+  if (rz::make_tmap_2d(&tmap_act, act_in, (uint64_t)rows_alloc, 128, a_rows)) return -1;
+  if (rz::make_tmap_2d(&tmap_w, weight, (uint64_t)9 * 128, 128, 64)) return -1;
+  if (rz::make_tmap_2d(&tmap_out, feat ? act_in : act_out, (uint64_t)rows_alloc, 128, TILE_M)) return -1;
+  Conv3Params p;
+  p.bias = bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.n_items = (int)(rows_alloc / 256);
+  p.total_rows = (int)total;
+  p.H = board_rows;
+  p.W = board_cols;
+  p.relu = relu;
+  int ctas = n_ctas > 0 ? n_ctas : 148;
+  ctas &= ~1;
+  if (ctas < 2) ctas = 2;
+  if (ctas / 2 > p.n_items) ctas = 2 * p.n_items;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (feat) {
+    for (int i = 0; i < 6 * 128; ++i) head.w[i] = w1x1_host[i];
+    for (int i = 0; i < 6; ++i) head.b[i] = b1x1_host[i];
+    head.feat = feat;
+    return row_stride == 16 ? launch3<16, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, st)
+                            : launch3<20, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, st);
+  }
+  return row_stride == 16 ? launch3<16, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, st)
+                          : launch3<20, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, st);
+}
+
+extern "C" int rz_net_conv3x3_tc3(const void* act_in, const void* weight, const float* bias,
+                                  const void* residual, void* act_out, int n_boards, int board_rows,
+                                  int board_cols, int row_stride, int relu, int n_ctas, void* stream) {
+  RZ_REQUIRE(act_out, "rz_net_conv3x3_tc3: null output");
+  return conv3_entry(act_in, weight, bias, residual, act_out, n_boards, board_rows, board_cols, row_stride, relu,
+                     n_ctas, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int rz_net_conv3x3_tc3_head(const void* act_in, const void* weight, const float* bias,
+                                       const void* residual, int n_boards, int board_rows, int board_cols,
+                                       int row_stride, int relu, const float* w1x1_host,
+                                       const float* b1x1_host, float* feat, int n_ctas, void* stream) {
+  RZ_REQUIRE(w1x1_host && b1x1_host && feat, "rz_net_conv3x3_tc3_head: null head argument");
+  return conv3_entry(act_in, weight, bias, residual, nullptr, n_boards, board_rows, board_cols, row_stride, relu,
+                     n_ctas, w1x1_host, b1x1_host, feat, stream);
+}

@@ -157,20 +157,24 @@ class NativeForward(object):
         self.game_type = int(game_type)
         layers = module.trunk_layers()
         all128 = all(l[0].out_channels == 128 for l in layers)
-        fits = self.H <= 15 and self.W <= 15
+        fits = self.H <= 19 and self.W <= 19
+        # padded position layout of the tensor-core path: row = board*S*S + y*S + x
+        self.S = 16 if (self.H <= 15 and self.W <= 15) else 20
+        self.P = self.S * self.S
         if mode is None:
             mode = 'tc' if (all128 and fits) else 'f32'
         if mode == 'tc' and not (all128 and fits):
-            raise ValueError("mode 'tc' needs a 128-channel trunk and a board of at most 15x15")
+            raise ValueError("mode 'tc' needs a 128-channel trunk and a board of at most 19x19")
         if mode == 'f32' and self.W != self.H:
             raise ValueError('the fp32 CUDA-core path handles square boards only')
         self.mode = mode
         self.n_ctas = int(n_ctas)
         # the heads' 1x1 convolutions inside the last trunk layer's epilogue (rz_net_tc2.cu, kHead)
-        self.fused_head = bool(fused_head) and int(conv_rev) == 2
+        self.fused_head = bool(fused_head) and int(conv_rev) >= 2
         self.weights_version = 0
         self.fused_stem = bool(fused_stem)  # encoder + first conv in one kernel (rz_net_stem.cu)
-        self.conv_rev = int(conv_rev)   # 2: resident weights + CTA pairs (rz_net_tc2.cu); 1: rz_net_tc.cu
+        # 3: rz_net_tc3.cu (any row stride; forced for 19x19); 2: rz_net_tc2.cu (stride 16); 1: rz_net_tc.cu
+        self.conv_rev = int(conv_rev)
         self.max_batch = 0
         self.refresh_weights()
         self._alloc(max_batch)
@@ -235,9 +239,10 @@ class NativeForward(object):
         self.max_batch = n
         if self.mode == 'tc':
             bf = torch.bfloat16
-            self.act0 = torch.zeros(n, 256, 64, dtype=bf, device=dev)
-            self.bufs = [torch.zeros(n, 256, 128, dtype=bf, device=dev) for _ in range(2)]
-            self.feat = torch.zeros(n, 6, 256, dtype=torch.float32, device=dev)
+            rows = (n * self.P + 255) // 256 * 256          # the convolutions work on pairs of 128-row tiles
+            self.act0 = torch.zeros(n, 256, 64, dtype=bf, device=dev) if self.S == 16 else None
+            self.bufs = [torch.zeros(rows, 128, dtype=bf, device=dev) for _ in range(2)]
+            self.feat = torch.zeros(n, 6, self.P, dtype=torch.float32, device=dev)
         else:
             cmax = max(max(l['cin'], l['cout']) for l in self.layers)
             self.act0 = torch.zeros(n, self.HW, self.layers[0]['cin'], dtype=torch.float32, device=dev)
@@ -265,16 +270,28 @@ class NativeForward(object):
                     # skip always refers to the activation two layers back = the other buffer
                     res = outs[dst]
                 inp = src if cur < 0 else outs[cur]
+                rev3 = (self.conv_rev == 3 or self.S != 16) and l['cin'] == 128
+                w1p = self.w1x1_host.ctypes.data_as(C.c_void_p)
+                b1p = self.b1x1_host.ctypes.data_as(C.c_void_p)
                 if self.fused_head and i == len(self.layers) - 1 and l['cin'] == 128:
-                    L.check(lib.rz_net_conv3x3_tc2_head(
-                        L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), n, self.H, self.W, l['cin'],
-                        int(l['relu']),
-                        self.w1x1_host.ctypes.data_as(C.c_void_p), self.b1x1_host.ctypes.data_as(C.c_void_p),
-                        L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc2_head')
+                    if rev3:
+                        L.check(lib.rz_net_conv3x3_tc3_head(
+                            L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), n, self.H, self.W, self.S,
+                            int(l['relu']), w1p, b1p, L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc3_head')
+                    else:
+                        L.check(lib.rz_net_conv3x3_tc2_head(
+                            L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), n, self.H, self.W, l['cin'],
+                            int(l['relu']), w1p, b1p, L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc2_head')
                     L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(self.feat), 2, L.ptr(logp), L.ptr(value),
                                              n, s), 'rz_net_heads')
                     return
-                if self.conv_rev == 2:
+                if rev3:
+                    L.check(lib.rz_net_conv3x3_tc3(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
+                                                   L.ptr(outs[dst]), n, self.H, self.W, self.S, int(l['relu']),
+                                                   self.n_ctas, s), 'rz_net_conv3x3_tc3')
+                elif self.S != 16:
+                    raise ValueError('19x19 boards need the fused stem (the generic first layer is stride-16 only)')
+                elif self.conv_rev >= 2:
                     L.check(lib.rz_net_conv3x3_tc2(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
                                                    L.ptr(outs[dst]), n, self.H, self.W, l['cin'],
                                                    int(l['relu']), 2, 0, self.n_ctas, s), 'rz_net_conv3x3_tc2')
@@ -323,6 +340,8 @@ class NativeForward(object):
                     'rz_net_stem_tc')
             stem_done = True
         elif self.mode == 'tc':
+            if self.S != 16:
+                raise ValueError('19x19 boards need the fused stem')
             L.check(self.lib.rz_gomoku_encode_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(self.act0), n,
                                                  L.stream_ptr()), 'rz_gomoku_encode_tc')
         else:
@@ -349,6 +368,8 @@ class NativeForward(object):
                     'rz_net_stem_tc_planes')
             stem_done = True
         elif self.mode == 'tc':
+            if self.S != 16:
+                raise ValueError('19x19 boards need the fused stem')
             self.act0[:n].zero_()
             t = self.act0[:n].view(n, 16, 16, 64)
             t[:, :self.H, :self.W, :4] = x.permute(0, 2, 3, 1).to(torch.bfloat16)

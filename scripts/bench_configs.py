@@ -52,6 +52,14 @@ def main():
     sp = BatchedSelfPlay(4096, 6, 4, net=net2, n_playout=200, add_noise=True, seed=2, board_width=7,
                          game_type=L.GAME_CONNECT4)
     run('config2 Connect Four 6x7, 200 sims/move, ResNet-6 bf16, 4096 games', sp, 200 * 12, 200)
+    del sp
+    torch.cuda.empty_cache()
+    # config 4 (board and trunk only): 19x19, 800 simulations/move, ResNet-20 bf16 on the tensor cores.
+    # Go rules are NOT implemented (no runnable oracle): the game is 19x19 five-in-a-row.
+    net4 = ResNetPolicyValueNet(19, n_blocks=20).cuda().eval()
+    sp = BatchedSelfPlay(8192, 19, 5, net=net4, n_playout=800, add_noise=True, seed=3)
+    run('config4-board 19x19 five-in-a-row (Go rules not implemented), 800 sims/move, ResNet-20 bf16, 8192 games',
+        sp, 160, 8)
 
 
 if __name__ == '__main__':

@@ -38,15 +38,25 @@ def main():
     x, y = nf.bufs[0], nf.bufs[1]
     x.normal_()
 
-    def conv():
-        L.check(lib.rz_net_conv3x3_tc(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), None, L.ptr(y), B, H, 128, 1,
-                                      ctas, L.stream_ptr()))
-    ms = timeit(conv)
     flops_alg = 2.0 * B * H * H * 128 * 128 * 9
     flops_issued = 2.0 * B * 256 * 128 * 128 * 9
-    print(json.dumps({'kernel': 'conv3x3_tc', 'B': B, 'ms': ms, 'TFLOPs_algorithmic': flops_alg / ms / 1e9,
-                      'TFLOPs_issued': flops_issued / ms / 1e9}))
+    if nf.S == 16:
+        def conv():
+            L.check(lib.rz_net_conv3x3_tc(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), None, L.ptr(y), B, H, 128, 1,
+                                          ctas, L.stream_ptr()))
+        ms = timeit(conv)
+        print(json.dumps({'kernel': 'conv3x3_tc', 'B': B, 'ms': ms, 'TFLOPs_algorithmic': flops_alg / ms / 1e9,
+                          'TFLOPs_issued': flops_issued / ms / 1e9}))
     z = nf.bufs[1]
+    for name, res in (('conv3x3_tc3', None), ('conv3x3_tc3+residual', z)):
+        def conv3():
+            L.check(lib.rz_net_conv3x3_tc3(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), L.ptr(y), B, H, H,
+                                           nf.S, 1, ctas, L.stream_ptr()))
+        ms = timeit(conv3)
+        print(json.dumps({'kernel': name, 'B': B, 'S': nf.S, 'ms': ms, 'TFLOPs_algorithmic': flops_alg / ms / 1e9,
+                          'TFLOPs_issued': 2.0 * B * nf.P * 128 * 128 * 9 / ms / 1e9}))
+    if nf.S != 16:
+        return
     for name, res in (('conv3x3_tc2', None), ('conv3x3_tc2+residual', z)):
         def conv2():
             L.check(lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), L.ptr(y), B, H, H,

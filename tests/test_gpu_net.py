@@ -24,7 +24,7 @@ def _from_tile(t, h):
     return t.reshape(n, 16, 16, c)[:, :h, :h, :].permute(0, 3, 1, 2).float()
 
 
-@pytest.mark.parametrize('rev', ['v1', 'v2_pair', 'v2_single'])
+@pytest.mark.parametrize('rev', ['v1', 'v2_pair', 'v2_single', 'v3'])
 @pytest.mark.parametrize('n,h,cin,relu,res', [(1, 15, 128, 1, 0), (3, 15, 128, 1, 1), (5, 9, 64, 0, 0),
                                               (300, 15, 128, 1, 1), (2, 3, 64, 1, 0), (37, 15, 64, 1, 0)])
 def test_conv3x3_tc_matches_torch(n, h, cin, relu, res, rev):
@@ -48,7 +48,18 @@ def test_conv3x3_tc_matches_torch(n, h, cin, relu, res, rev):
     if res:
         out.copy_(_to_tile(r))   # residual aliases the output buffer, as in the trunk
         rt = out
-    if rev == 'v1':
+    if rev == 'v3':
+        if cin != 128:
+            pytest.skip('revision 3 is the 128 -> 128 trunk layer')
+        if n % 2:   # tensors padded to a multiple of 256 rows (pairs of 128-row tiles)
+            pad = torch.zeros(1, 256, 128, dtype=torch.bfloat16, device=dev)
+            xt = torch.cat([xt, pad])
+            out = torch.cat([out, pad + 7.0]) if not res else torch.cat([out, pad])
+            rt = out if res else None
+        L.check(lib.rz_net_conv3x3_tc3(L.ptr(xt), L.ptr(wt), L.ptr(b.contiguous()), L.ptr(rt), L.ptr(out),
+                                       n, h, h, 16, relu, 0, L.stream_ptr()), 'conv3')
+        out = out[:n]
+    elif rev == 'v1':
         L.check(lib.rz_net_conv3x3_tc(L.ptr(xt), L.ptr(wt), L.ptr(b.contiguous()), L.ptr(rt), L.ptr(out),
                                       n, h, cin, relu, 0, L.stream_ptr()), 'conv')
     else:
@@ -295,3 +306,81 @@ def test_graph_recaptured_after_weight_refresh():
     sp_new = BatchedSelfPlay(4, 6, 4, net=net, n_playout=8, add_noise=False, seed=1)
     _, _, v3 = sp_new.get_actions(rows, meta)
     assert np.array_equal(v2, v3)
+
+
+def _to_pad(x_nchw, S):
+    """[n,C,H,W] float -> bf16 padded layout [round_up(n*S*S, 256)][C] (row = b*S*S + y*S + x)."""
+    n, c, h, w = x_nchw.shape
+    t = torch.zeros(n, S, S, c, dtype=torch.bfloat16, device=x_nchw.device)
+    t[:, :h, :w, :] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    rows = (n * S * S + 255) // 256 * 256
+    out = torch.zeros(rows, c, dtype=torch.bfloat16, device=x_nchw.device)
+    out[:n * S * S] = t.reshape(n * S * S, c)
+    return out
+
+
+@pytest.mark.parametrize('n,h,w,relu,res', [(1, 19, 19, 1, 0), (5, 19, 19, 1, 1), (131, 19, 19, 1, 1), (3, 17, 18, 0, 0),
+                                            (2, 6, 7, 1, 1)])
+def test_conv3x3_tc3_any_stride_matches_torch(n, h, w, relu, res):
+    """Revision 3 at row stride 20 (19x19 and other boards > 15), tiles straddling boards."""
+    from rlzero_b200 import _lib as L
+    lib = L.load()
+    torch.manual_seed(n * 10 + h)
+    dev = 'cuda'
+    S = 16 if max(h, w) <= 15 else 20
+    x = (torch.randn(n, 128, h, w, device=dev) * 0.5).to(torch.bfloat16).float()
+    wgt = (torch.randn(128, 128, 3, 3, device=dev) / (3.0 * 128 ** 0.5)).to(torch.bfloat16).float()
+    b = torch.randn(128, device=dev) * 0.1
+    r = (torch.randn(n, 128, h, w, device=dev) * 0.5).to(torch.bfloat16).float() if res else None
+    ref = torch.nn.functional.conv2d(x.double(), wgt.double(), b.double(), padding=1)
+    if res:
+        ref = ref + r.double()
+    if relu:
+        ref = torch.relu(ref)
+    xt = _to_pad(x, S)
+    wt = wgt.permute(2, 3, 0, 1).reshape(9, 128, 128).to(torch.bfloat16).contiguous()
+    out = torch.full_like(xt, 7.0)
+    rt = None
+    if res:
+        out.copy_(_to_pad(r, S))
+        rt = out
+    L.check(lib.rz_net_conv3x3_tc3(L.ptr(xt), L.ptr(wt), L.ptr(b.contiguous()), L.ptr(rt), L.ptr(out), n, h, w, S,
+                                   relu, 0, L.stream_ptr()), 'conv3')
+    torch.cuda.synchronize()
+    full = out[:n * S * S].reshape(n, S, S, 128).float()
+    got = full[:, :h, :w, :].permute(0, 3, 1, 2).double()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-2 * max(scale, 1.0), (err, scale)
+    ref_bf = ref.float().to(torch.bfloat16).double()
+    assert ((got - ref_bf).abs() <= 1e-6).double().mean().item() > 0.97
+    assert full[:, h:, :, :].abs().max().item() == 0.0 and full[:, :, w:, :].abs().max().item() == 0.0
+    assert out[n * S * S:].abs().max().item() == 0.0 if out.shape[0] > n * S * S else True
+
+
+@pytest.mark.parametrize('size,blocks,n', [(19, 3, 9), (15, 2, 6)])
+def test_resnet_forward_rev3_vs_torch_and_rev2(size, blocks, n):
+    """Whole forward on the revision-3 convolution: 19x19 against PyTorch fp32 (1e-3), and at 15x15
+    bit-identical to the revision-2 path (same MMAs in a different order of k-blocks would NOT be
+    identical, so this only checks closeness there)."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(size)
+    net = ResNetPolicyValueNet(size, n_blocks=blocks).cuda().eval()
+    nf = NativeForward(net, max_batch=n, conv_rev=3)
+    assert nf.mode == 'tc' and nf.S == (20 if size > 15 else 16)
+    x = _random_boards(n, size, 5)
+    logp, v = (t.cpu() for t in nf.forward_planes(x))
+    ref = ResNetPolicyValueNet(size, n_blocks=blocks).eval()
+    ref.load_state_dict({k: t.cpu() for k, t in net.state_dict().items()})
+    with torch.no_grad():
+        lt, vt = ref(torch.from_numpy(x))
+    assert (logp.exp() - lt.exp()).abs().max().item() < 1e-3
+    assert (v - vt.reshape(-1)).abs().max().item() < 1e-3
+    # fused head on/off agree exactly on this path too
+    nf_b = NativeForward(net, max_batch=n, conv_rev=3, fused_head=False)
+    lb, vb = (t.cpu() for t in nf_b.forward_planes(x))
+    assert torch.equal(lb, logp) and torch.equal(vb, v)
+    if size <= 15:
+        nf2 = NativeForward(net, max_batch=n, conv_rev=2)
+        l2, v2 = (t.cpu() for t in nf2.forward_planes(x))
+        assert (l2.exp() - logp.exp()).abs().max().item() < 1e-4 and (v2 - v).abs().max().item() < 1e-3
