@@ -39,9 +39,10 @@
 extern "C" {
 #endif
 
-#define RZ_ABI_VERSION 5
-#define RZ_MAX_BOARD 19          /* rows live one per lane; A = H*W <= 361 */
-#define RZ_META_STRIDE 8
+#define RZ_ABI_VERSION 6
+#define RZ_MAX_BOARD 19          /* rows live one per lane; A <= 362 (19x19 Go incl. the pass) */
+#define RZ_META_STRIDE 12
+#define RZ_GO_HIST 14            /* history planes a Go position carries besides the current board */
 
 enum rz_meta {                   /* int32 words of a game's meta record */
   RZ_META_PLAYER = 0,            /* player to move, 0/1 (gomoku_env.py:29,67-68) */
@@ -51,8 +52,11 @@ enum rz_meta {                   /* int32 words of a game's meta record */
   RZ_META_WINNER = 4,            /* -1 none/tie, else player id (game_end_winner) */
   RZ_META_PLY = 5,               /* plies played in this episode (trajectory length) */
   RZ_META_FAULT = 6,             /* sticky bit set, enum rz_fault */
-  RZ_META_EPISODE = 7            /* episodes finished in this slot */
-};
+  RZ_META_EPISODE = 7,           /* episodes finished in this slot */
+  RZ_META_KO = 8,                /* Go: square that may not be retaken, -1 none (go_base Position.ko) */
+  RZ_META_PASSES = 9             /* Go: consecutive passes so far (two end the game, go_env.py:185) */
+};                               /* words 10, 11 reserved.  Go also uses LAST_MOVE = last ACTION (the pass
+                                    is H*W) and STONES = moves played (Position.n) */
 
 enum rz_status { RZ_ACTIVE = 0, RZ_ENDED_WIN = 1, RZ_ENDED_TIE = 2, RZ_IDLE = 3 };
 
@@ -83,9 +87,12 @@ enum rz_child {                  /* values of edge child[] when N >= 1 */
 /* ---- game geometry ------------------------------------------------------- */
 enum rz_game {
   RZ_GAME_GOMOKU = 0,            /* k-in-a-row, action = square r*W+c (gomoku_env.py; TicTacToe = 3x3, k=3) */
-  RZ_GAME_CONNECT4 = 1           /* k-in-a-row with gravity: action = column, the stone drops to the lowest
+  RZ_GAME_CONNECT4 = 1,          /* k-in-a-row with gravity: action = column, the stone drops to the lowest
                                     empty row (row 0 = bottom).  No reference env exists; same
                                     duck-typed API, planes and win rule as GomokuEnv */
+  RZ_GAME_GO = 2                 /* Go as rlzero/games/go/go_env.py plays it through pettingzoo's go_base
+                                    (MiniGo rules): captures, no suicide, simple ko, action H*W = pass, two
+                                    passes end the game, Tromp-Taylor area score minus komi; player 0 = black */
 };
 
 typedef struct rz_game_desc {
@@ -95,6 +102,9 @@ typedef struct rz_game_desc {
   int32_t action_stride;         /* AS = round_up(A, 32) */
   int32_t width;                 /* W: columns (0 means W = H) */
   int32_t game_type;             /* enum rz_game */
+  float komi;                    /* Go: points given to white (GoEnv komi, go_env.py:41); 0 otherwise */
+  int32_t max_moves;             /* Go: > 0 ends and scores the game after that many moves (engine-side cap,
+                                    the reference has none); 0 = no cap */
 } rz_game_desc;
 
 /* ---- one search forest: G trees, one per game ---------------------------- */
@@ -130,6 +140,9 @@ typedef struct rz_tree_desc {
   uint32_t* leaf_rows;           /* [G][2][H] */
   int32_t* leaf_meta;            /* [G][RZ_META_STRIDE] (status = terminal state of the leaf) */
   const double* ln_table;        /* ln_table[k] = math.log(k) computed by the HOST libm (k>=1) */
+  /* Go only (NULL otherwise): board_history planes 2..15 of go_env.py:174-178, [G][RZ_GO_HIST][H] */
+  uint32_t* root_hist;
+  uint32_t* leaf_hist;
 } rz_tree_desc;
 
 /* ---- trajectory store (GameControl.start_self_play, game.py:96-134) ------- */
@@ -179,6 +192,32 @@ int rz_gomoku_encode_nhwc_f32(const rz_game_desc* g, const uint32_t* rows, const
    p = y*16+x (x,y < 15 real, else zero), channels 0..3 = planes, 4..63 zero. */
 int rz_gomoku_encode_tc(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
                         void* act_bf16, int n_games, void* stream);
+
+/* ---- game dynamics: GoEnv (rlzero/games/go/go_env.py over pettingzoo go_base = MiniGo rules) ----
+   Positions: rows [n][2][H] (black, white), hist [n][RZ_GO_HIST][H] = board_history planes 2..15
+   (go_env.py:174-178; planes 0,1 are the current stones of the last mover / of the player to move),
+   meta as above (+ KO, PASSES).  hist may be NULL where noted (history not tracked). */
+/* reset (go_env.py:212-230): empty boards, black to move, no ko, zero history. */
+int rz_go_reset(const rz_game_desc* g, uint32_t* rows, uint32_t* hist, int32_t* meta, int n_games,
+                int only_ended, void* stream);
+/* step (go_env.py:168-210): Position.play_move (captures, ko; action H*W = pass), history shift,
+   is_game_over -> status / winner (black iff result() == 1, go_env.py:142-143).  actions[i] < 0
+   skips game i.  reward [n][2] (black, white) = GoEnv.rewards, done [n]; both may be NULL.
+   Illegal move (occupied, ko, suicide, or the game is over) -> RZ_FAULT_ILLEGAL_MOVE.  hist may be NULL. */
+int rz_go_step(const rz_game_desc* g, uint32_t* rows, uint32_t* hist, int32_t* meta, const int32_t* actions,
+               int32_t* reward, int32_t* done, int n_games, void* stream);
+/* Position.all_legal_moves (go_env.py:193-194) as a byte mask [n][H*W + 1] (only the pass once the
+   game is over, go_env.py:192). */
+int rz_go_legal_mask(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta, uint8_t* mask,
+                     int n_games, void* stream);
+/* Position.score() (Tromp-Taylor area, komi subtracted) as float64 [n] and result() in {1,-1,0} [n];
+   either may be NULL. */
+int rz_go_score(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta, double* score,
+                int32_t* result, int n_games, void* stream);
+/* observe (go_env.py:156-166) as float32 [n][17][H][W]: the 16 history planes + the player plane
+   (channels first; the reference's array is [H][W][17]).  hist NULL = zero history. */
+int rz_go_encode_f32(const rz_game_desc* g, const uint32_t* rows, const uint32_t* hist, const int32_t* meta,
+                     float* planes, int n_games, void* stream);
 
 /* ---- search: AlphaZeroMCTS (rlzero/mcts/alphazero_mcts.py, node.py) ------- */
 /* fresh trees: _root = TreeNode(None, 1.0) (alphazero_mcts.py:36).  tree_mask NULL = all. */

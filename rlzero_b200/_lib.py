@@ -11,10 +11,11 @@ import torch  # noqa: F401  -- loads libcudart.so.12 into the process before our
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'librlzero_b200.so')
 
-ABI_VERSION = 5
-META_STRIDE = 8
+ABI_VERSION = 6
+META_STRIDE = 12
 (META_PLAYER, META_LAST_MOVE, META_STONES, META_STATUS, META_WINNER, META_PLY, META_FAULT,
- META_EPISODE) = range(8)
+ META_EPISODE, META_KO, META_PASSES) = range(10)
+GO_HIST = 14
 ACTIVE, ENDED_WIN, ENDED_TIE, IDLE = range(4)
 FAULT_ILLEGAL_MOVE, FAULT_POOL_OVERFLOW, FAULT_DEPTH_OVERFLOW, FAULT_LN_TABLE = 1, 2, 4, 8
 FAULT_NO_CHILDREN, FAULT_CARRY_DROPPED, FAULT_TRAJ_OVERFLOW = 16, 32, 64
@@ -26,13 +27,14 @@ MAX_BOARD = 19
 _vp = C.c_void_p
 
 
-GAME_GOMOKU, GAME_CONNECT4 = 0, 1
+GAME_GOMOKU, GAME_CONNECT4, GAME_GO = 0, 1, 2
 
 
 class GameDesc(C.Structure):
-    """rz_game_desc: GameDesc(H, k, A, AS[, W, game_type]); W = 0 means a square board."""
+    """rz_game_desc: GameDesc(H, k, A, AS[, W, game_type, komi, max_moves]); W = 0 means a square board."""
     _fields_ = [('board_size', C.c_int32), ('n_in_row', C.c_int32), ('n_actions', C.c_int32),
-                ('action_stride', C.c_int32), ('width', C.c_int32), ('game_type', C.c_int32)]
+                ('action_stride', C.c_int32), ('width', C.c_int32), ('game_type', C.c_int32),
+                ('komi', C.c_float), ('max_moves', C.c_int32)]
 
 
 class TreeDesc(C.Structure):
@@ -44,7 +46,8 @@ class TreeDesc(C.Structure):
                 ('n_nodes', _vp), ('root_N', _vp), ('root_W', _vp),
                 ('root_rows', _vp), ('root_meta', _vp),
                 ('path_node', _vp), ('path_action', _vp), ('depth', _vp),
-                ('leaf_rows', _vp), ('leaf_meta', _vp), ('ln_table', _vp)]
+                ('leaf_rows', _vp), ('leaf_meta', _vp), ('ln_table', _vp),
+                ('root_hist', _vp), ('leaf_hist', _vp)]
 
 
 class TrajDesc(C.Structure):
@@ -74,6 +77,11 @@ SIGNATURES = {
     'rz_gomoku_encode_f32': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, _vp]),
     'rz_gomoku_encode_nhwc_f32': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, _vp]),
     'rz_gomoku_encode_tc': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_go_reset': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rz_go_step': (C.c_int, [_GD, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_go_legal_mask': (C.c_int, [_GD, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_go_score': (C.c_int, [_GD, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_go_encode_f32': (C.c_int, [_GD, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     'rz_tree_reset': (C.c_int, [_TD, _vp, _vp]),
     'rz_tree_select': (C.c_int, [_TD, _vp]),
     'rz_tree_expand_backup': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,

@@ -105,3 +105,48 @@ __device__ __forceinline__ bool rz_occ_slot_legal(uint32_t myocc, int s, const r
   const uint32_t occ = __shfl_sync(RZ_FULL, myocc, r);
   return s < q.A && !((occ >> c) & 1u);
 }
+
+// ---- the interface the search kernels (rz_tree.cu) and evaluators are written against -------------
+struct rz_line_game {
+  typedef rz_wboard board;
+  static __device__ __forceinline__ void load_root(board& b, const rz_tree_desc& t, int g) {
+    const int H = t.game.board_size;
+    rz_board_load(b, t.root_rows + (size_t)g * 2 * H, t.root_meta + (size_t)g * RZ_META_STRIDE, H);
+  }
+  static __device__ __forceinline__ void load_leaf(board& b, const rz_tree_desc& t, int g) {
+    const int H = t.game.board_size;
+    rz_board_load(b, t.leaf_rows + (size_t)g * 2 * H, t.leaf_meta + (size_t)g * RZ_META_STRIDE, H);
+  }
+  static __device__ __forceinline__ void store_root(const board& b, const rz_tree_desc& t, int g) {
+    rz_board_store_rows(b, t.root_rows + (size_t)g * 2 * t.game.board_size, t.game.board_size);
+  }
+  static __device__ __forceinline__ void store_leaf(const board& b, const rz_tree_desc& t, int g) {
+    rz_board_store_rows(b, t.leaf_rows + (size_t)g * 2 * t.game.board_size, t.game.board_size);
+  }
+  static __device__ __forceinline__ void store_meta(const board& b, int32_t* m) {   // lane 0
+    m[RZ_META_PLAYER] = b.player;
+    m[RZ_META_LAST_MOVE] = b.last_move;
+    m[RZ_META_STONES] = b.stones;
+  }
+  static __device__ __forceinline__ void play(board& b, int a, const rz_geom& q) { rz_board_play(b, a, q); }
+  static __device__ __forceinline__ int status(const board& b, const rz_geom& q, int& winner) {
+    return rz_board_status(b, q, winner);
+  }
+  static __device__ __forceinline__ bool action_illegal(const board& b, int a, const rz_geom& q) {
+    return a >= q.A || rz_board_occupied(b, a, q);                 // gomoku_env.py:51
+  }
+  // legality of the leaf's action slots (expand): context = this lane's occupancy row
+  static __device__ __forceinline__ uint32_t legal_ctx(const rz_tree_desc& t, int g, const rz_geom& q) {
+    const int lane = rz_lane(), H = q.H;
+    return lane < H ? (t.leaf_rows[(size_t)g * 2 * H + lane] | t.leaf_rows[(size_t)g * 2 * H + H + lane]) : 0u;
+  }
+  static __device__ __forceinline__ uint32_t legal_ctx(const board& b, const rz_geom& q) { return b.p[0] | b.p[1]; }
+  static __device__ __forceinline__ bool slot_legal(uint32_t ctx, int s, const rz_geom& q) {
+    return rz_occ_slot_legal(ctx, s, q);
+  }
+  static __device__ __forceinline__ void clear_root(const rz_tree_desc& t, int g) {  // fresh episode position
+    const int lane = rz_lane(), H = t.game.board_size;
+    if (lane < H) { t.root_rows[(size_t)g * 2 * H + lane] = 0u; t.root_rows[(size_t)g * 2 * H + H + lane] = 0u; }
+  }
+  static __device__ __forceinline__ int stone_count(const board& b) { return b.stones; }
+};

@@ -31,7 +31,8 @@ void rz_set_error(const char* fmt, ...);
 
 // geometry of a game as the kernels use it
 struct rz_geom {
-  int H, W, k, A, AS, cells, gravity;
+  int H, W, k, A, AS, cells, gravity, go, max_moves;
+  double komi;
 };
 __host__ __device__ inline rz_geom rz_geom_of(const rz_game_desc& d) {
   rz_geom q;
@@ -42,6 +43,9 @@ __host__ __device__ inline rz_geom rz_geom_of(const rz_game_desc& d) {
   q.AS = d.action_stride;
   q.cells = q.H * q.W;
   q.gravity = d.game_type == RZ_GAME_CONNECT4;
+  q.go = d.game_type == RZ_GAME_GO;
+  q.max_moves = d.max_moves;
+  q.komi = (double)d.komi;
   return q;
 }
 
@@ -51,9 +55,15 @@ static inline int rz_check_game(const rz_game_desc* g) {
     rz_set_error("board_size %d outside [1,%d]", g->board_size, RZ_MAX_BOARD); return -1; }
   const int W = g->width > 0 ? g->width : g->board_size;
   if (W < 1 || W > RZ_MAX_BOARD) { rz_set_error("width %d outside [1,%d]", W, RZ_MAX_BOARD); return -1; }
-  if (g->game_type != RZ_GAME_GOMOKU && g->game_type != RZ_GAME_CONNECT4) {
+  if (g->game_type != RZ_GAME_GOMOKU && g->game_type != RZ_GAME_CONNECT4 && g->game_type != RZ_GAME_GO) {
     rz_set_error("game_type %d", g->game_type); return -1; }
-  if (g->n_actions != (g->game_type == RZ_GAME_CONNECT4 ? W : g->board_size * W)) {
+  if (g->game_type == RZ_GAME_GO) {
+    if (W != g->board_size) { rz_set_error("Go needs a square board, got %dx%d", g->board_size, W); return -1; }
+    if (g->n_actions != g->board_size * W + 1) {
+      rz_set_error("n_actions %d: Go on %dx%d has %d actions (the pass is the last)", g->n_actions, g->board_size,
+                   W, g->board_size * W + 1); return -1; }
+    if (g->max_moves < 0) { rz_set_error("max_moves %d", g->max_moves); return -1; }
+  } else if (g->n_actions != (g->game_type == RZ_GAME_CONNECT4 ? W : g->board_size * W)) {
     rz_set_error("n_actions %d does not match the %dx%d board of game %d", g->n_actions, g->board_size, W,
                  g->game_type); return -1; }
   if (g->action_stride < g->n_actions || (g->action_stride & 31)) {

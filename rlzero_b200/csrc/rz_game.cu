@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 
 #include "rz_board.cuh"
+#include "rz_go.cuh"
 
 #define RZ_GAME_WARPS 4
 #define RZ_GAME_THREADS (RZ_GAME_WARPS * 32)
@@ -190,15 +191,17 @@ rz_gomoku_encode_tc_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t*
 }
 
 // closed-form evaluators (oracle/evaluators.py) on the leaf positions of a wave
+template <class GM>
 __global__ void __launch_bounds__(RZ_GAME_THREADS)
 rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* value) {
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   if (t.depth[g] < 0) return;
   const rz_geom q = rz_geom_of(t.game);
-  const int lane = rz_lane(), H = t.game.board_size, AS = t.game.action_stride;
-  rz_wboard b;
-  rz_board_load(b, t.leaf_rows + (size_t)g * 2 * H, t.leaf_meta + (size_t)g * RZ_META_STRIDE, H);
+  const int lane = rz_lane(), AS = t.game.action_stride;
+  typename GM::board b;
+  GM::load_leaf(b, t, g);
+  const int n_stones = GM::stone_count(b);     // len(env.states)
   uint32_t h = 0;
   if (eval_id == RZ_EVAL_HASH) {
     for (int c = 0; c < 2; ++c) {
@@ -215,15 +218,16 @@ rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* val
     h *= 2654435761u;
   }
   float v = 0.0f;
-  if (eval_id == RZ_EVAL_KAT) v = (float)((17 * b.stones + 31 * (b.last_move + 1)) % 13 - 6) / 8.0f;
+  if (eval_id == RZ_EVAL_KAT) v = (float)((17 * n_stones + 31 * (b.last_move + 1)) % 13 - 6) / 8.0f;
   else if (eval_id == RZ_EVAL_HASH) v = (float)((int)((h >> 16) % 129u) - 64) / 64.0f;
   if (lane == 0) value[g] = v;
+  const uint32_t lctx = GM::legal_ctx(b, q);
   int n_legal = 0;
-  for (int s0 = 0; s0 < AS; s0 += 32) n_legal += __popc(__ballot_sync(RZ_FULL, rz_board_slot_legal(b, s0 + lane, q)));
+  for (int s0 = 0; s0 < AS; s0 += 32) n_legal += __popc(__ballot_sync(RZ_FULL, GM::slot_legal(lctx, s0 + lane, q)));
   const float uni = n_legal > 0 ? __fdiv_rn(1.0f, (float)n_legal) : 0.0f;
   for (int s0 = 0; s0 < AS; s0 += 32) {
     const int s = s0 + lane;
-    const bool legal = rz_board_slot_legal(b, s, q);
+    const bool legal = GM::slot_legal(lctx, s, q);
     float p = 0.0f;
     if (legal) p = (eval_id == RZ_EVAL_HASH) ? (float)(((uint32_t)s * 29u + (h >> 8)) % 32u + 1u) / 256.0f : uni;
     prior[(size_t)g * AS + s] = p;
@@ -301,11 +305,16 @@ rz_eval_rollout_kernel(rz_tree_desc t, int mode, unsigned long long seed, int n_
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
+static int rz_check_line_game(const rz_game_desc* g) {
+  if (rz_check_game(g)) return -1;
+  RZ_REQUIRE(g->game_type != RZ_GAME_GO, "this entry point serves Gomoku / Connect Four; use the rz_go_* calls for Go");
+  return 0;
+}
 static inline dim3 rz_grid(int n, int warps) { return dim3((unsigned)((n + warps - 1) / warps)); }
 
 extern "C" int rz_gomoku_reset(const rz_game_desc* g, uint32_t* rows, int32_t* meta, int n_games,
                                int only_ended, void* stream) {
-  if (rz_check_game(g)) return -1;
+  if (rz_check_line_game(g)) return -1;
   RZ_REQUIRE(rows && meta && n_games >= 0, "rz_gomoku_reset: bad arguments");
   if (n_games == 0) return 0;
   rz_gomoku_reset_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream>>>(
@@ -317,7 +326,7 @@ extern "C" int rz_gomoku_reset(const rz_game_desc* g, uint32_t* rows, int32_t* m
 extern "C" int rz_gomoku_step(const rz_game_desc* g, uint32_t* rows, int32_t* meta,
                               const int32_t* actions, int32_t* reward, int32_t* win, int n_games,
                               void* stream) {
-  if (rz_check_game(g)) return -1;
+  if (rz_check_line_game(g)) return -1;
   RZ_REQUIRE(rows && meta && actions && n_games >= 0, "rz_gomoku_step: bad arguments");
   if (n_games == 0) return 0;
   rz_gomoku_step_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream>>>(
@@ -328,7 +337,7 @@ extern "C" int rz_gomoku_step(const rz_game_desc* g, uint32_t* rows, int32_t* me
 
 extern "C" int rz_gomoku_legal_mask(const rz_game_desc* g, const uint32_t* rows, uint8_t* mask,
                                     int n_games, void* stream) {
-  if (rz_check_game(g)) return -1;
+  if (rz_check_line_game(g)) return -1;
   RZ_REQUIRE(rows && mask && n_games >= 0, "rz_gomoku_legal_mask: bad arguments");
   if (n_games == 0) return 0;
   rz_gomoku_legal_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream>>>(
@@ -339,7 +348,7 @@ extern "C" int rz_gomoku_legal_mask(const rz_game_desc* g, const uint32_t* rows,
 
 extern "C" int rz_gomoku_winner(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
                                 int32_t* end, int32_t* winner, int n_games, void* stream) {
-  if (rz_check_game(g)) return -1;
+  if (rz_check_line_game(g)) return -1;
   RZ_REQUIRE(rows && meta && end && winner && n_games >= 0, "rz_gomoku_winner: bad arguments");
   if (n_games == 0) return 0;
   rz_gomoku_winner_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream>>>(
@@ -350,7 +359,7 @@ extern "C" int rz_gomoku_winner(const rz_game_desc* g, const uint32_t* rows, con
 
 extern "C" int rz_gomoku_encode_f32(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
                                     float* planes, int n_games, void* stream) {
-  if (rz_check_game(g)) return -1;
+  if (rz_check_line_game(g)) return -1;
   RZ_REQUIRE(rows && meta && planes && n_games >= 0, "rz_gomoku_encode_f32: bad arguments");
   if (n_games == 0) return 0;
   rz_gomoku_encode_f32_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
@@ -361,7 +370,7 @@ extern "C" int rz_gomoku_encode_f32(const rz_game_desc* g, const uint32_t* rows,
 
 extern "C" int rz_gomoku_encode_nhwc_f32(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
                                          float* planes, int n_games, void* stream) {
-  if (rz_check_game(g)) return -1;
+  if (rz_check_line_game(g)) return -1;
   RZ_REQUIRE(rows && meta && planes && n_games >= 0, "rz_gomoku_encode_nhwc_f32: bad arguments");
   if (n_games == 0) return 0;
   rz_gomoku_encode_nhwc_kernel<<<rz_grid(n_games, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
@@ -372,7 +381,7 @@ extern "C" int rz_gomoku_encode_nhwc_f32(const rz_game_desc* g, const uint32_t* 
 
 extern "C" int rz_gomoku_encode_tc(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta,
                                    void* act_bf16, int n_games, void* stream) {
-  if (rz_check_game(g)) return -1;
+  if (rz_check_line_game(g)) return -1;
   RZ_REQUIRE(rows && meta && act_bf16 && n_games >= 0, "rz_gomoku_encode_tc: bad arguments");
   RZ_REQUIRE(g->board_size <= 15, "rz_gomoku_encode_tc: the 16x16 tile layout holds boards up to 15x15");
   if (n_games == 0) return 0;
@@ -389,6 +398,7 @@ extern "C" int rz_eval_rollout(const rz_tree_desc* t, int mode, unsigned long lo
   RZ_REQUIRE(mode >= 0 && mode <= 2, "rz_eval_rollout: mode %d", mode);
   RZ_REQUIRE(n_limit >= 0, "rz_eval_rollout: n_limit %d", n_limit);
   RZ_REQUIRE(t->root_N && t->depth && t->leaf_rows && t->leaf_meta, "rz_eval_rollout: null tree array");
+  RZ_REQUIRE(t->game.game_type != RZ_GAME_GO, "rz_eval_rollout: not implemented for Go");
   if (t->n_trees == 0) return 0;
   rz_eval_rollout_kernel<<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
                            (cudaStream_t)stream>>>(*t, mode, seed, n_limit, prior, value);
@@ -402,8 +412,12 @@ extern "C" int rz_eval_closed_form(const rz_tree_desc* t, int eval_id, float* pr
   if (rz_check_game(&t->game)) return -1;
   RZ_REQUIRE(eval_id >= RZ_EVAL_ZERO && eval_id <= RZ_EVAL_HASH, "rz_eval_closed_form: eval_id %d", eval_id);
   if (t->n_trees == 0) return 0;
-  rz_eval_closed_form_kernel<<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
-                               (cudaStream_t)stream>>>(*t, eval_id, prior, value);
+  if (t->game.game_type == RZ_GAME_GO)
+    rz_eval_closed_form_kernel<rz_go_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+                                             (cudaStream_t)stream>>>(*t, eval_id, prior, value);
+  else
+    rz_eval_closed_form_kernel<rz_line_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+                                               (cudaStream_t)stream>>>(*t, eval_id, prior, value);
   RZ_LAUNCH_CHECK("rz_eval_closed_form");
   return 0;
 }

@@ -22,10 +22,11 @@
 #include <string.h>
 
 #include "rz_board.cuh"
+#include "rz_go.cuh"
 
 #define RZ_TREE_WARPS 4
 #define RZ_TREE_THREADS (RZ_TREE_WARPS * 32)
-#define RZ_MAX_ITERS 12  // AS/32 <= 12  (A <= 361 -> AS <= 384)
+#define RZ_MAX_ITERS 12  // AS/32 <= 12  (A <= 362 -> AS <= 384)
 
 __device__ __forceinline__ size_t rz_edge_base(const rz_tree_desc& t, int g, int node) {
   return ((size_t)g * t.max_nodes + node) * (size_t)t.game.action_stride;
@@ -46,20 +47,21 @@ __device__ __forceinline__ void rz_warp_argmax(double& s, int& slot, int& n) {
 // ---------------------------------------------------------------------------
 // K1: select.  One playout descent per tree + leaf terminal test.
 // ---------------------------------------------------------------------------
+template <class GM>
 __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc t) {
   const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   const int lane = rz_lane();
   const rz_geom q = rz_geom_of(t.game);
-  const int H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  const int AS = t.game.action_stride;
   const int iters = AS >> 5;
   int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
   if (rmeta[RZ_META_STATUS] != RZ_ACTIVE) {
     if (lane == 0) t.depth[g] = -1;
     return;
   }
-  rz_wboard b;
-  rz_board_load(b, t.root_rows + (size_t)g * 2 * H, rmeta, H);
+  typename GM::board b;
+  GM::load_root(b, t, g);
 
   int fault = 0;
   int depth = 0;
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
 
     if (lane == 0) { pnode[depth] = node; pact[depth] = best_slot; }
     depth += 1;
-    rz_board_play(b, best_slot, q);  // game_env.step(action), alphazero_mcts.py:54
+    GM::play(b, best_slot, q);       // game_env.step(action), alphazero_mcts.py:54
     if (best_n == 0) break;          // never visited -> unexpanded leaf
     const int child = t.edge_child[base + best_slot];
     if (child < 0) break;            // terminal (or overflowed) leaf, re-evaluated every visit
@@ -147,13 +149,11 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
 
   // leaf: game_end_winner() (alphazero_mcts.py:60)
   int winner;
-  const int status = rz_board_status(b, q, winner);
-  rz_board_store_rows(b, t.leaf_rows + (size_t)g * 2 * H, H);
+  const int status = GM::status(b, q, winner);
+  GM::store_leaf(b, t, g);
   if (lane == 0) {
     int32_t* lm = t.leaf_meta + (size_t)g * RZ_META_STRIDE;
-    lm[RZ_META_PLAYER] = b.player;
-    lm[RZ_META_LAST_MOVE] = b.last_move;
-    lm[RZ_META_STONES] = b.stones;
+    GM::store_meta(b, lm);
     lm[RZ_META_STATUS] = status;
     lm[RZ_META_WINNER] = winner;
     lm[RZ_META_PLY] = depth;
@@ -162,7 +162,6 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
     t.depth[g] = depth;
     if (fault) rmeta[RZ_META_FAULT] |= fault;
   }
-  (void)A;
 }
 
 // ---------------------------------------------------------------------------
@@ -194,6 +193,7 @@ __device__ float rz_gamma_draw(float alpha, unsigned long long seed, uint32_t c0
 // ---------------------------------------------------------------------------
 // K5+K6: expand the leaf (unless terminal) and back the value up the path.
 // ---------------------------------------------------------------------------
+template <class GM>
 __global__ void __launch_bounds__(RZ_TREE_THREADS)
 rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int prior_is_log,
                         const float* __restrict__ value, const double* __restrict__ value64,
@@ -205,7 +205,7 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
   if (depth < 0) return;
   const int lane = rz_lane();
   const rz_geom q = rz_geom_of(t.game);
-  const int H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  const int AS = t.game.action_stride;
   const int32_t* lm = t.leaf_meta + (size_t)g * RZ_META_STRIDE;
   const int32_t* rm = t.root_meta + (size_t)g * RZ_META_STRIDE;
   const int status = lm[RZ_META_STATUS];
@@ -227,8 +227,7 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
     const int nn = t.n_nodes[g];
     if (nn < t.max_nodes) {
       // node.py:71-73: one child per legal move, in ascending action order
-      const uint32_t myocc = lane < H ? (t.leaf_rows[(size_t)g * 2 * H + lane] |
-                                         t.leaf_rows[(size_t)g * 2 * H + H + lane]) : 0u;
+      const uint32_t lctx = GM::legal_ctx(t, g, q);
       const size_t nb = rz_edge_base(t, g, nn);
       const float* pr = prior + (size_t)g * AS;
       float noise_sum = 0.0f;
@@ -238,7 +237,7 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
       for (int i = 0; i < RZ_MAX_ITERS; ++i) {
         if (i >= (AS >> 5)) break;
         const int s = lane + 32 * i;
-        const bool legal = rz_occ_slot_legal(myocc, s, q);
+        const bool legal = GM::slot_legal(lctx, s, q);
         t.edge_N[nb + s] = legal ? 0 : -1;
         nz[i] = 0.0f;
         if (noisy && legal) {
@@ -470,6 +469,7 @@ __device__ int rz_tree_compact(const rz_tree_desc& t, int g, int c, uint32_t* bi
   return total;
 }
 
+template <class GM>
 __global__ void __launch_bounds__(RZ_TREE_THREADS)
 rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_subtree,
                   int max_carry, rz_traj_desc traj, int have_traj, const float* __restrict__ pi,
@@ -479,7 +479,7 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
   if (g >= t.n_trees) return;
   const int lane = rz_lane();
   const rz_geom q = rz_geom_of(t.game);
-  const int H = t.game.board_size, A = t.game.n_actions, AS = t.game.action_stride;
+  const int H = t.game.board_size, AS = t.game.action_stride;
   uint32_t* bits = rz_adv_smem + (size_t)wib * 2 * words_per_warp;
   uint32_t* wprefix = bits + words_per_warp;
   int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
@@ -489,10 +489,9 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
     return;
   }
   if (rmeta[RZ_META_STATUS] != RZ_ACTIVE) return;
-  rz_wboard b;
-  uint32_t* rrows = t.root_rows + (size_t)g * 2 * H;
-  rz_board_load(b, rrows, rmeta, H);
-  if (m >= A || rz_board_occupied(b, m, q)) {  // gomoku_env.py:51
+  typename GM::board b;
+  GM::load_root(b, t, g);
+  if (GM::action_illegal(b, m, q)) {  // gomoku_env.py:51 / go_base IllegalMove
     if (lane == 0) rmeta[RZ_META_FAULT] |= RZ_FAULT_ILLEGAL_MOVE;
     return;
   }
@@ -501,7 +500,10 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
   if (have_traj) {
     if (ply < traj.max_plies) {
       const size_t so = (size_t)g * traj.max_plies + ply;
-      rz_board_store_rows(b, traj.stage_rows + so * 2 * H, H);
+      if (lane < H) {
+        traj.stage_rows[so * 2 * H + lane] = b.p[0];
+        traj.stage_rows[so * 2 * H + H + lane] = b.p[1];
+      }
       if (lane == 0) {
         int32_t* si = traj.stage_info + so * 4;
         si[0] = b.player; si[1] = b.last_move; si[2] = m; si[3] = b.stones;
@@ -513,9 +515,9 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
     }
   }
   // game.py:117: game_env.step(move)
-  rz_board_play(b, m, q);
+  GM::play(b, m, q);
   int winner;
-  const int status = rz_board_status(b, q, winner);
+  const int status = GM::status(b, q, winner);
 
   // alphazero_mcts.py:96-103
   const bool root_expanded = t.n_nodes[g] > 0;
@@ -539,11 +541,9 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
     }
   }
 
-  rz_board_store_rows(b, rrows, H);
+  GM::store_root(b, t, g);
   if (lane == 0) {
-    rmeta[RZ_META_PLAYER] = b.player;
-    rmeta[RZ_META_LAST_MOVE] = b.last_move;
-    rmeta[RZ_META_STONES] = b.stones;
+    GM::store_meta(b, rmeta);
     rmeta[RZ_META_STATUS] = status;
     rmeta[RZ_META_WINNER] = winner;
     rmeta[RZ_META_PLY] = ply + 1;
@@ -583,7 +583,7 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
   }
   if (lane == 0) rz_tree_fresh(t, g, 0, 0.0);
   if (auto_reset) {
-    if (lane < H) { rrows[lane] = 0u; rrows[H + lane] = 0u; }
+    GM::clear_root(t, g);
     if (lane == 0) {
       rmeta[RZ_META_PLAYER] = 0;
       rmeta[RZ_META_LAST_MOVE] = -1;
@@ -628,6 +628,8 @@ static int rz_check_tree(const rz_tree_desc* t, const char* who) {
   RZ_REQUIRE(t->path_node && t->path_action && t->depth && t->leaf_rows && t->leaf_meta,
              "%s: null wave scratch", who);
   RZ_REQUIRE(t->ln_table && t->ln_table_len >= 2, "%s: ln table missing", who);
+  RZ_REQUIRE(t->game.game_type != RZ_GAME_GO || (t->root_hist && t->leaf_hist),
+             "%s: Go needs the root_hist / leaf_hist planes", who);
   return 0;
 }
 
@@ -644,7 +646,10 @@ extern "C" int rz_tree_reset(const rz_tree_desc* t, const uint8_t* tree_mask, vo
 extern "C" int rz_tree_select(const rz_tree_desc* t, void* stream) {
   if (rz_check_tree(t, "rz_tree_select")) return -1;
   if (t->n_trees == 0) return 0;
-  rz_select_kernel<<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(*t);
+  if (t->game.game_type == RZ_GAME_GO)
+    rz_select_kernel<rz_go_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(*t);
+  else
+    rz_select_kernel<rz_line_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(*t);
   RZ_LAUNCH_CHECK("rz_tree_select");
   return 0;
 }
@@ -659,8 +664,12 @@ extern "C" int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, 
   RZ_REQUIRE(noise_eps >= 0.0f && noise_eps <= 1.0f, "rz_tree_expand_backup: noise_eps %f", noise_eps);
   RZ_REQUIRE(noise_eps == 0.0f || noise_alpha > 0.0f, "rz_tree_expand_backup: noise_alpha %f", noise_alpha);
   if (t->n_trees == 0) return 0;
-  rz_expand_backup_kernel<<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(
-      *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset);
+  if (t->game.game_type == RZ_GAME_GO)
+    rz_expand_backup_kernel<rz_go_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(
+        *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset);
+  else
+    rz_expand_backup_kernel<rz_line_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(
+        *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset);
   RZ_LAUNCH_CHECK("rz_tree_expand_backup");
   return 0;
 }
@@ -696,8 +705,12 @@ extern "C" int rz_tree_advance(const rz_tree_desc* t, const int32_t* moves, int 
   const int words = (t->max_nodes + 31) / 32;
   const size_t smem = (size_t)RZ_TREE_WARPS * 2 * words * sizeof(uint32_t);
   RZ_REQUIRE(smem <= 48 * 1024, "rz_tree_advance: max_nodes %d needs %zu B of shared memory", t->max_nodes, smem);
-  rz_advance_kernel<<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, smem, (cudaStream_t)stream>>>(
-      *t, moves, keep_subtree, max_carry, td, traj != nullptr, pi, auto_reset, words);
+  if (t->game.game_type == RZ_GAME_GO)
+    rz_advance_kernel<rz_go_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, smem, (cudaStream_t)stream>>>(
+        *t, moves, keep_subtree, max_carry, td, traj != nullptr, pi, auto_reset, words);
+  else
+    rz_advance_kernel<rz_line_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, smem, (cudaStream_t)stream>>>(
+        *t, moves, keep_subtree, max_carry, td, traj != nullptr, pi, auto_reset, words);
   RZ_LAUNCH_CHECK("rz_tree_advance");
   return 0;
 }

@@ -82,7 +82,7 @@ def main():
     ms = timeit(conv_head)
     print(json.dumps({'kernel': 'conv3x3_tc2_head+residual', 'ms': ms, 'TFLOPs_issued': flops_issued / ms / 1e9}))
     rows = torch.zeros(B, 2, H, dtype=torch.int32, device='cuda')
-    meta = torch.zeros(B, 8, dtype=torch.int32, device='cuda')
+    meta = torch.zeros(B, 12, dtype=torch.int32, device='cuda')
     meta[:, 1] = -1
 
     g = nf._gdesc()
