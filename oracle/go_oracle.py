@@ -280,3 +280,44 @@ class GoEnvOracle(object):
 
     def is_terminal(self):
         return self._is_terminal
+
+
+class GoSearchBoard(object):
+    """The env duck-type ``pyoracle.Search`` (= the reference's ``AlphaZeroMCTS``,
+    alphazero_mcts.py:42-71) drives -- ``step / game_end_winner / current_player / leagel_actions``,
+    plus the ``states`` / ``last_move`` attributes the closed-form evaluators hash -- over a Go
+    ``Position``.  The reference itself never runs AlphaZeroMCTS on GoEnv (its Go path is
+    DeepMindMCTS); this adapter is what BASELINE.json's config 4 (AlphaZero on a Go board) means in
+    the reference's own search.  Actions ascend with the pass (N*N) last; players 0 = black, 1 = white;
+    ``max_moves`` > 0 ends and scores the game after that many moves (the engine's cap)."""
+
+    def __init__(self, board_size=9, komi=7.5, max_moves=0):
+        self.board_size = board_size
+        self.komi = komi
+        self.max_moves = max_moves
+        self.reset()
+
+    def reset(self):
+        self.pos = Position(self.board_size, self.komi)
+        self.last_move = -1
+
+    def step(self, action):
+        self.pos = self.pos.play_move(from_flat(self.board_size, action))
+        self.last_move = int(action)
+
+    @property
+    def states(self):
+        n = self.board_size
+        return {int(r * n + c): (0 if self.pos.board[r, c] == BLACK else 1)
+                for r, c in zip(*np.nonzero(self.pos.board))}
+
+    def leagel_actions(self):
+        return [int(a) for a in np.where(self.pos.all_legal_moves() == 1)[0]]
+
+    def current_player(self):
+        return 0 if self.pos.to_play == BLACK else 1
+
+    def game_end_winner(self):
+        if self.pos.is_game_over() or (self.max_moves and self.pos.n >= self.max_moves):
+            return True, (0 if self.pos.result() == 1 else 1)      # go_env.py:142-143
+        return False, -1

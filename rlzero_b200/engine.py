@@ -46,7 +46,7 @@ class SearchForest(object):
     def __init__(self, n_trees, board_size, n_in_row, n_playout=800, c_puct=5.0,
                  rule=L.RULE_UCT, max_carry=None, max_nodes=None, store_priors=True,
                  device='cuda', global_offset=0, ln_table_len=None, with_trajectories=False,
-                 ring_capacity=None, board_width=None, game_type=L.GAME_GOMOKU):
+                 ring_capacity=None, board_width=None, game_type=L.GAME_GOMOKU, komi=7.5, max_moves=0):
         if not torch.cuda.is_available():
             raise L.NativeLibraryError('rlzero_b200 needs a CUDA device (no CPU fallback)')
         self.lib = L.load()
@@ -61,7 +61,13 @@ class SearchForest(object):
         if max(self.H, self.W) < self.k:
             raise ValueError('Board board_size can not less than %d' % self.k)  # gomoku_env.py:35
         self.cells = self.H * self.W
-        self.A = self.W if self.game_type == L.GAME_CONNECT4 else self.cells      # actions
+        self.is_go = self.game_type == L.GAME_GO
+        self.komi = float(komi) if self.is_go else 0.0
+        self.max_moves = int(max_moves) if self.is_go else 0
+        if self.is_go and self.W != self.H:
+            raise ValueError('Go needs a square board')
+        # actions: squares; the columns for Connect Four; squares + the pass for Go (go_env.py:74-77)
+        self.A = self.W if self.game_type == L.GAME_CONNECT4 else self.cells + int(self.is_go)
         self.AS = _round_up(self.A, 32)
         self.n_playout = int(n_playout)
         self.c_puct = float(c_puct)
@@ -72,7 +78,8 @@ class SearchForest(object):
         self.max_nodes = int(max_nodes) if max_nodes else self.n_playout + self.max_carry
         if self.max_nodes > 6144:
             raise ValueError('max_nodes %d > 6144 (re-root bitmap lives in shared memory)' % self.max_nodes)
-        self.max_depth = self.cells + 1
+        # a path holds at most one edge per stone (line games) / per expanded node (Go: captures free squares)
+        self.max_depth = self.max_nodes + 1 if self.is_go else self.cells + 1
         self.store_priors = bool(store_priors) or rule == L.RULE_PUCT
         G, AS, H, dev = self.G, self.AS, self.H, self.device
         i32, f64, f32 = torch.int32, torch.float64, torch.float32
@@ -93,6 +100,9 @@ class SearchForest(object):
         self.depth = torch.full((G,), -1, dtype=i32, device=dev)
         self.leaf_rows = torch.zeros(G, 2, H, dtype=i32, device=dev)
         self.leaf_meta = torch.zeros(G, L.META_STRIDE, dtype=i32, device=dev)
+        # Go: board_history planes 2..15 of every root / leaf position (go_env.py:174-178)
+        self.root_hist = torch.zeros(G, L.GO_HIST, H, dtype=i32, device=dev) if self.is_go else None
+        self.leaf_hist = torch.zeros(G, L.GO_HIST, H, dtype=i32, device=dev) if self.is_go else None
         n_ln = int(ln_table_len) if ln_table_len else max(1 << 16, 4 * self.n_playout + 2)
         self.ln_table = torch.from_numpy(ln_table(n_ln)).to(dev)
         # evaluator outputs for one wave
@@ -103,7 +113,7 @@ class SearchForest(object):
         self.pi = torch.zeros(G, AS, dtype=f32, device=dev)
         self.move = torch.full((G,), -1, dtype=i32, device=dev)
 
-        self.gdesc = L.GameDesc(self.H, self.k, self.A, self.AS, self.W, self.game_type)
+        self.gdesc = L.GameDesc(self.H, self.k, self.A, self.AS, self.W, self.game_type, self.komi, self.max_moves)
         d = L.TreeDesc()
         d.game = self.gdesc
         d.n_trees, d.max_nodes, d.max_depth = G, self.max_nodes, self.max_depth
@@ -115,6 +125,8 @@ class SearchForest(object):
                      'depth', 'leaf_rows', 'leaf_meta', 'ln_table'):
             setattr(d, name, getattr(self, name).data_ptr())
         d.edge_P = self.edge_P.data_ptr() if self.edge_P is not None else None
+        d.root_hist = self.root_hist.data_ptr() if self.is_go else None
+        d.leaf_hist = self.leaf_hist.data_ptr() if self.is_go else None
         self.desc = d
         self.traj = None
         self.tdesc = None
@@ -125,7 +137,8 @@ class SearchForest(object):
     # ------------------------------------------------------------------ memory
     def _alloc_trajectories(self, ring_capacity):
         G, H, AS, dev = self.G, self.H, self.AS, self.device
-        P = self.cells
+        # plies one episode can hold: a line game fills the board; Go is capped by max_moves (or 2 * squares)
+        P = (self.max_moves or 2 * self.cells) if self.is_go else self.cells
         cap = int(ring_capacity) if ring_capacity else max(4 * P, 2 * G * 16)
         cap = max(cap, P)
         i32, f32 = torch.int32, torch.float32
@@ -162,8 +175,12 @@ class SearchForest(object):
 
     def reset_games(self):
         """GomokuEnv.reset() for every game + fresh trees (gomoku_env.py:33-47)."""
-        L.check(self.lib.rz_gomoku_reset(C.byref(self.gdesc), L.ptr(self.root_rows),
-                                         L.ptr(self.root_meta), self.G, 0, self._s()), 'rz_gomoku_reset')
+        if self.is_go:
+            L.check(self.lib.rz_go_reset(C.byref(self.gdesc), L.ptr(self.root_rows), L.ptr(self.root_hist),
+                                         L.ptr(self.root_meta), self.G, 0, self._s()), 'rz_go_reset')
+        else:
+            L.check(self.lib.rz_gomoku_reset(C.byref(self.gdesc), L.ptr(self.root_rows),
+                                             L.ptr(self.root_meta), self.G, 0, self._s()), 'rz_gomoku_reset')
         self.reset_trees()
 
     def reset_trees(self, mask=None):
@@ -175,6 +192,10 @@ class SearchForest(object):
     def play_moves(self, actions):
         """env.step for every game (actions[g] < 0 skips); roots only, trees untouched."""
         a = torch.as_tensor(actions, dtype=torch.int32, device=self.device).contiguous()
+        if self.is_go:
+            L.check(self.lib.rz_go_step(C.byref(self.gdesc), L.ptr(self.root_rows), L.ptr(self.root_hist),
+                                        L.ptr(self.root_meta), L.ptr(a), None, None, self.G, self._s()), 'rz_go_step')
+            return
         L.check(self.lib.rz_gomoku_step(C.byref(self.gdesc), L.ptr(self.root_rows), L.ptr(self.root_meta),
                                         L.ptr(a), None, None, self.G, self._s()), 'rz_gomoku_step')
 

@@ -1,0 +1,105 @@
+"""Search parity on Go: the batched CUDA search (SearchForest, RZ_GAME_GO) against the reference's
+AlphaZeroMCTS algorithm (oracle.pyoracle.Search) run over the Go oracle.  With the same closed-form
+evaluator on both sides, visit counts, value sums and tree reuse must be bit-identical -- including
+passes, captures inside the tree, ko and two-pass terminal leaves."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from oracle.evaluators import EVAL_HASH, EVAL_ZERO, make_policy_value_fn
+from oracle.go_oracle import GoSearchBoard
+
+pytestmark = pytest.mark.gpu
+
+
+def _forest(G, n, n_playout, komi=2.5, rule=0, max_moves=0, **kw):
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import SearchForest
+    return SearchForest(G, n, 1, n_playout=n_playout, rule=rule, game_type=L.GAME_GO, komi=komi,
+                        max_moves=max_moves, **kw)
+
+
+def _random_position(n, plies, seed, komi, max_moves=0):
+    rs = np.random.RandomState(seed)
+    b = GoSearchBoard(n, komi, max_moves)
+    moves = []
+    for _ in range(plies):
+        legal = b.leagel_actions()
+        a = legal[rs.randint(len(legal) - 1)] if len(legal) > 1 and rs.rand() > 0.03 else n * n
+        b.step(a)
+        moves.append(a)
+        if b.game_end_winner()[0]:
+            b.reset()
+            moves = []
+    return b, moves
+
+
+@pytest.mark.parametrize('n,n_playout,plies,eval_id,rule', [
+    (3, 80, 4, EVAL_HASH, 0), (5, 120, 12, EVAL_HASH, 0), (5, 150, 30, EVAL_HASH, 1), (5, 60, 20, EVAL_ZERO, 0),
+    (9, 200, 40, EVAL_HASH, 0), (9, 120, 90, EVAL_HASH, 1)])
+def test_visits_match_the_oracle(n, n_playout, plies, eval_id, rule):
+    from rlzero_b200.engine import ClosedFormEvaluator
+    G, komi = 6, 2.5
+    positions = [_random_position(n, (plies * (g + 1)) // G, 17 * g + n, komi) for g in range(G)]
+    f = _forest(G, n, n_playout, komi, rule=rule)
+    f.set_positions([m for _, m in positions])
+    f.search(ClosedFormEvaluator(eval_id))
+    f.raise_faults()
+    visits, w, has, root_n, root_w = f.root_stats()
+    A = n * n + 1
+    for g, (board, _) in enumerate(positions):
+        s = pyoracle.Search(make_policy_value_fn(eval_id), n_playout, 5, rule=rule)
+        s.simulate(board, 1.0)
+        assert np.array_equal(visits[g], s.root_visits(A)), g
+        assert np.array_equal(w[g], s.root_values(A)), g
+        assert root_n[g] == s.root.n and root_w[g] == s.root.w
+        assert sorted(np.nonzero(has[g])[0]) == sorted(s.root.children.keys())
+
+
+def test_tree_reuse_and_passes_to_the_end():
+    """Greedy self-play of one 3x3 game with tree reuse: every move's visit vector matches, through
+    captures, passes and the two-pass end; the winner matches Tromp-Taylor scoring of the oracle."""
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import ClosedFormEvaluator
+    n, n_playout, komi = 3, 60, 0.5
+    f = _forest(1, n, n_playout, komi, max_carry=n_playout)
+    board = GoSearchBoard(n, komi)
+    s = pyoracle.Search(make_policy_value_fn(EVAL_HASH), n_playout, 5)
+    ev = ClosedFormEvaluator(EVAL_HASH)
+    for ply in range(60):
+        f.search(ev)
+        f.raise_faults()
+        visits = f.root_stats()[0][0]
+        s.simulate(board, 1.0)
+        want = s.root_visits(n * n + 1)
+        assert np.array_equal(visits, want), ply
+        move = int(np.argmax(want))
+        f.advance([move], keep_subtree=True)
+        board.step(move)
+        s.update_with_move(move)
+        end, winner = board.game_end_winner()
+        meta = f.boards()[1][0]
+        assert (meta[L.META_STATUS] != L.ACTIVE) == end
+        if end:
+            assert meta[L.META_WINNER] == winner
+            break
+    assert end
+
+
+def test_move_cap_scores_the_game():
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import ClosedFormEvaluator
+    n, cap = 5, 6
+    f = _forest(2, n, 40, 0.5, max_moves=cap)
+    boards = [GoSearchBoard(n, 0.5, cap), GoSearchBoard(n, 0.5, cap)]
+    for g, mv in enumerate([[0, 1, 2], [12, 13, 7, 8]]):
+        for a in mv:
+            boards[g].step(a)
+    f.set_positions([[0, 1, 2], [12, 13, 7, 8]])
+    f.search(ClosedFormEvaluator(EVAL_HASH))
+    f.raise_faults()
+    visits = f.root_stats()[0]
+    for g in range(2):
+        s = pyoracle.Search(make_policy_value_fn(EVAL_HASH), 40, 5)
+        s.simulate(boards[g], 1.0)
+        assert np.array_equal(visits[g], s.root_visits(n * n + 1)), g
