@@ -339,6 +339,15 @@ int rz_net_stem_tc(const rz_game_desc* g, const uint32_t* rows, const int32_t* m
    AlphaZeroAgent.policy_value / predict, alphazero_agent.py:48-57,88-97); planes are rounded to bf16. */
 int rz_net_stem_tc_planes(const rz_game_desc* g, const float* planes, const void* weight, const float* bias,
                           void* act_out, int n_boards, int relu, int n_ctas, void* stream);
+/* Go: fused GoEnv.observe (go_env.py:156-178: 16 history planes + player plane) + stem conv3x3(17->128):
+   the 153-wide im2col row (k = tap*17 + plane) is built from the row bitmasks in registers.  weight bf16
+   [128][192] (k zero padded from 153), bias f32 [128], act_out as rz_net_stem_tc (S = 16 up to 15x15, else 20).
+   rows/hist/meta: the Go position records (rz_go_step).  The _planes variant reads float32 [n][17][H][W]. */
+int rz_net_stem_go_tc(const rz_game_desc* g, const uint32_t* rows, const uint32_t* hist, const int32_t* meta,
+                      const void* weight, const float* bias, void* act_out, int n_boards, int relu, int n_ctas,
+                      void* stream);
+int rz_net_stem_go_tc_planes(const rz_game_desc* g, const float* planes, const void* weight, const float* bias,
+                             void* act_out, int n_boards, int relu, int n_ctas, void* stream);
 /* the same operator in float32 on CUDA cores for the reference's stock network at any board size:
    in [n][HW][c_in], weight [9][c_in][c_out], out [n][HW][c_out] (channels last). */
 int rz_net_conv3x3_f32(const float* in, const float* weight, const float* bias, const float* residual,

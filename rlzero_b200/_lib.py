@@ -104,6 +104,8 @@ SIGNATURES = {
                                           _vp, _vp, C.c_int, _vp]),
     'rz_net_stem_tc': (C.c_int, [_GD, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_net_stem_tc_planes': (C.c_int, [_GD, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_net_stem_go_tc': (C.c_int, [_GD, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_net_stem_go_tc_planes': (C.c_int, [_GD, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_net_conv3x3_f32': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, _vp]),
     'rz_net_heads': (C.c_int, [C.POINTER(HeadsDesc), _vp, C.c_int, _vp, _vp, C.c_int, _vp]),

@@ -79,9 +79,11 @@ class _ResBlock(nn.Module):
 class ResNetPolicyValueNet(PolicyValueNet):
     """ResNet-N trunk (C channels) with the reference's heads."""
 
-    def __init__(self, board_size, n_blocks=10, channels=128, board_width=None, n_actions=None):
+    def __init__(self, board_size, n_blocks=10, channels=128, board_width=None, n_actions=None, in_planes=4):
         """``board_size`` rows x ``board_width`` columns (square by default, like the reference);
-        ``n_actions`` policy outputs (rows*columns by default; the columns for Connect Four)."""
+        ``n_actions`` policy outputs (rows*columns by default; the columns for Connect Four;
+        rows*columns + 1 for Go, whose last action is the pass); ``in_planes`` observation planes
+        (4 = GomokuEnv.current_state, 17 = GoEnv.observe)."""
         nn.Module.__init__(self)
         if channels != 128:
             raise ValueError('the reference heads take 128 trunk channels (policy_value_net.py:19,23)')
@@ -90,7 +92,8 @@ class ResNetPolicyValueNet(PolicyValueNet):
         self.n_blocks = n_blocks
         hw = self.board_size * self.board_width
         self.n_actions = hw if n_actions is None else n_actions
-        self.stem = nn.Conv2d(4, channels, 3, padding=1)
+        self.in_planes = in_planes
+        self.stem = nn.Conv2d(in_planes, channels, 3, padding=1)
         self.blocks = nn.ModuleList([_ResBlock(channels) for _ in range(n_blocks)])
         self.act_conv1 = nn.Conv2d(channels, 4, kernel_size=1)
         self.act_fc1 = nn.Linear(4 * hw, self.n_actions)
@@ -115,7 +118,7 @@ class ResNetPolicyValueNet(PolicyValueNet):
     def flops_per_eval(self):
         hw = self.board_size * self.board_width
         c = 128
-        trunk = 2 * hw * (4 * c * 9) + self.n_blocks * 2 * 2 * hw * c * c * 9
+        trunk = 2 * hw * (self.in_planes * c * 9) + self.n_blocks * 2 * 2 * hw * c * c * 9
         heads = 2 * hw * c * 6 + 2 * (4 * hw) * self.n_actions + 2 * (2 * hw) * 64 + 2 * 64
         return trunk + heads
 
@@ -153,7 +156,8 @@ class NativeForward(object):
         self.A = int(getattr(module, 'n_actions', self.HW))   # policy outputs
         self.AS = (self.A + 31) // 32 * 32
         if game_type is None:   # a policy head over the columns of a non-square board = a gravity game
-            game_type = L.GAME_CONNECT4 if (self.A == self.W and self.A != self.HW) else L.GAME_GOMOKU
+            game_type = L.GAME_CONNECT4 if (self.A == self.W and self.A != self.HW) else (
+                L.GAME_GO if self.A == self.HW + 1 else L.GAME_GOMOKU)
         self.game_type = int(game_type)
         layers = module.trunk_layers()
         all128 = all(l[0].out_channels == 128 for l in layers)
@@ -167,6 +171,8 @@ class NativeForward(object):
             raise ValueError("mode 'tc' needs a 128-channel trunk and a board of at most 19x19")
         if mode == 'f32' and self.W != self.H:
             raise ValueError('the fp32 CUDA-core path handles square boards only')
+        if self.game_type == L.GAME_GO and mode != 'tc':
+            raise ValueError('Go runs on the tensor-core path only (128-channel trunk, 17 input planes)')
         self.mode = mode
         self.n_ctas = int(n_ctas)
         # the heads' 1x1 convolutions inside the last trunk layer's epilogue (rz_net_tc2.cu, kHead)
@@ -201,7 +207,16 @@ class NativeForward(object):
         # fused encoder + stem (rz_net_stem.cu): weight [cout][k = tap*4 + plane], k padded to 64
         self.stem = None
         conv0 = m.trunk_layers()[0][0]
-        if self.mode == 'tc' and conv0.in_channels == 4 and m.trunk_layers()[0][1] is None:
+        if self.game_type == L.GAME_GO:
+            # fused GoEnv.observe + stem (rz_net_stem.cu): weight [cout][k = tap*17 + plane], k padded to 192
+            if conv0.in_channels != 17 or m.trunk_layers()[0][1] is not None:
+                raise ValueError('the Go stem takes the 17 planes of GoEnv.observe (go_env.py:156-166)')
+            w0, b0 = _fold_bn(conv0, None)
+            ws = torch.zeros(128, 192, dtype=torch.float64)
+            ws[:, :153] = w0.permute(0, 2, 3, 1).reshape(128, 153)    # [cout][kh][kw][plane]
+            self.stem = dict(w=ws.to(torch.bfloat16).contiguous().to(dev), b=b0.float().contiguous().to(dev),
+                             relu=bool(m.trunk_layers()[0][3]))
+        elif self.mode == 'tc' and conv0.in_channels == 4 and m.trunk_layers()[0][1] is None:
             w0, b0 = _fold_bn(conv0, None)
             ws = torch.zeros(128, 64, dtype=torch.float64)
             ws[:, :36] = w0.permute(0, 2, 3, 1).reshape(128, 36)      # [cout][kh][kw][plane]
@@ -252,6 +267,8 @@ class NativeForward(object):
 
     # ------------------------------------------------------------------ forward
     def _gdesc(self, k=5):
+        if self.game_type == L.GAME_GO:
+            return L.GameDesc(self.H, 1, self.A, self.AS, self.W, self.game_type)
         return L.GameDesc(self.H, min(k, max(self.H, self.W)), self.A, self.AS, self.W, self.game_type)
 
     def _trunk_and_heads(self, n, logp, value, stem_done=False):
@@ -326,14 +343,23 @@ class NativeForward(object):
         fused = self.mode == 'tc' and self.stem is not None and self.fused_stem
         return (1 + n_conv - 1 if fused else 1 + n_conv) + 1      # [stem | encode + conv0] + convs + heads
 
-    def forward_boards(self, rows, meta, n, logp=None, value=None):
-        """Positions in the device board layout -> (logp [n][AS], value [n]) float32 tensors."""
+    def forward_boards(self, rows, meta, n, logp=None, value=None, hist=None):
+        """Positions in the device board layout -> (logp [n][AS], value [n]) float32 tensors.
+        ``hist``: the Go history planes [n][14][H] (required for Go)."""
         self._alloc(n)
         logp = self.logp if logp is None else logp
         value = self.value if value is None else value
         g = self._gdesc()
         stem_done = False
-        if self.mode == 'tc' and self.stem is not None and self.fused_stem:
+        if self.game_type == L.GAME_GO:
+            st = self.stem
+            if hist is None:
+                raise ValueError('Go positions need their history planes (hist=)')
+            L.check(self.lib.rz_net_stem_go_tc(C.byref(g), L.ptr(rows), L.ptr(hist), L.ptr(meta), L.ptr(st['w']),
+                                               L.ptr(st['b']), L.ptr(self.bufs[0]), n, int(st['relu']), 0,
+                                               L.stream_ptr()), 'rz_net_stem_go_tc')
+            stem_done = True
+        elif self.mode == 'tc' and self.stem is not None and self.fused_stem:
             st = self.stem
             L.check(self.lib.rz_net_stem_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(st['w']), L.ptr(st['b']),
                                             L.ptr(self.bufs[0]), n, int(st['relu']), 0, L.stream_ptr()),
@@ -358,7 +384,15 @@ class NativeForward(object):
         n = x.shape[0]
         self._alloc(n)
         stem_done = False
-        if self.mode == 'tc' and self.stem is not None and self.fused_stem:
+        if self.game_type == L.GAME_GO:
+            st = self.stem
+            xc = x.contiguous()
+            g = self._gdesc()
+            L.check(self.lib.rz_net_stem_go_tc_planes(C.byref(g), L.ptr(xc), L.ptr(st['w']), L.ptr(st['b']),
+                                                      L.ptr(self.bufs[0]), n, int(st['relu']), 0, L.stream_ptr()),
+                    'rz_net_stem_go_tc_planes')
+            stem_done = True
+        elif self.mode == 'tc' and self.stem is not None and self.fused_stem:
             # same kernel (and therefore bit-identical stem outputs) as forward_boards
             st = self.stem
             xc = x.contiguous()
@@ -380,4 +414,5 @@ class NativeForward(object):
 
     def __call__(self, forest):
         """Evaluator protocol of engine.SearchForest.run_waves: evaluate the wave's leaves."""
-        self.forward_boards(forest.leaf_rows, forest.leaf_meta, forest.G, forest.prior, forest.value)
+        self.forward_boards(forest.leaf_rows, forest.leaf_meta, forest.G, forest.prior, forest.value,
+                            hist=getattr(forest, 'leaf_hist', None))

@@ -26,7 +26,10 @@ class BatchedSelfPlay(object):
     def __init__(self, n_games, board_size=15, n_in_row=5, net=None, n_playout=800, c_puct=5.0,
                  rule=L.RULE_UCT, temperature=1.0, add_noise=True, noise_eps=0.25, noise_alpha=0.3,
                  device='cuda', global_offset=0, seed=0, evaluator=None, ring_capacity=None,
-                 store_priors=True, n_ctas=0, board_width=None, game_type=L.GAME_GOMOKU):
+                 store_priors=True, n_ctas=0, board_width=None, game_type=L.GAME_GOMOKU, komi=7.5, max_moves=0):
+        """``game_type = L.GAME_GO``: ``n_in_row`` is ignored, actions are the squares + the pass,
+        ``komi`` as GoEnv's, ``max_moves`` > 0 ends and scores a game after that many moves (the
+        reference has no cap; AlphaGo Zero used 2 * 19 * 19)."""
         self.G = int(n_games)
         self.n_playout = int(n_playout)
         self.temperature = float(temperature)
@@ -36,7 +39,8 @@ class BatchedSelfPlay(object):
         self.forest = SearchForest(self.G, board_size, n_in_row, n_playout=n_playout, c_puct=c_puct,
                                    rule=rule, device=device, global_offset=global_offset,
                                    with_trajectories=True, ring_capacity=ring_capacity,
-                                   store_priors=store_priors, board_width=board_width, game_type=game_type)
+                                   store_priors=store_priors, board_width=board_width, game_type=game_type,
+                                   komi=komi, max_moves=max_moves)
         if evaluator is None:
             if net is None:
                 raise ValueError('BatchedSelfPlay needs a policy-value module (net=) or an evaluator')
@@ -54,6 +58,8 @@ class BatchedSelfPlay(object):
         RandomState(1000+g); positions that happen to be over restart empty."""
         f = self.forest
         ids = np.arange(self.G) + int(f.desc.global_offset) if global_ids is None else np.asarray(global_ids)
+        if f.is_go:
+            return self._set_random_go_positions(ids, max_random_moves)
         lists = []
         for gid in ids:
             rs = np.random.RandomState(1000 + int(gid))
@@ -69,6 +75,36 @@ class BatchedSelfPlay(object):
         L.check(f.lib.rz_gomoku_reset(C.byref(f.gdesc), L.ptr(f.root_rows), L.ptr(f.root_meta), f.G, 1,
                                       L.stream_ptr()), 'rz_gomoku_reset')
         f.root_meta[:, L.META_EPISODE] = 0
+        self.waves_in_move = 0
+
+    def _set_random_go_positions(self, ids, max_random_moves):
+        """Go: the same recipe, but a random square may be illegal (suicide / ko), so the moves are
+        played ply by ply against the device's legal mask: game g plays, k_g times, the first legal
+        square of its RandomState(1000+g) permutation that it has not tried yet."""
+        import ctypes as C
+        f = self.forest
+        f.reset_games()
+        perms = [np.random.RandomState(1000 + int(gid)).permutation(f.cells) for gid in ids]
+        ks = [(1000 + int(gid)) % max_random_moves for gid in ids]
+        ptr = np.zeros(f.G, dtype=np.int64)
+        mask = torch.zeros(f.G, f.A, dtype=torch.uint8, device=f.device)
+        for t in range(max(ks, default=0)):
+            L.check(f.lib.rz_go_legal_mask(C.byref(f.gdesc), L.ptr(f.root_rows), L.ptr(f.root_meta), L.ptr(mask),
+                                           f.G, L.stream_ptr()), 'rz_go_legal_mask')
+            m = mask.cpu().numpy()
+            acts = np.full(f.G, -1, dtype=np.int32)
+            for g in range(f.G):
+                if ks[g] <= t:
+                    continue
+                while ptr[g] < f.cells and not m[g, perms[g][ptr[g]]]:
+                    ptr[g] += 1
+                if ptr[g] < f.cells:
+                    acts[g] = perms[g][ptr[g]]
+                    ptr[g] += 1
+            f.play_moves(acts)
+        f.root_meta[:, L.META_PLY] = 0
+        f.root_meta[:, L.META_EPISODE] = 0
+        f.raise_faults()
         self.waves_in_move = 0
 
     # -------------------------------------------------------------------- waves
@@ -133,11 +169,12 @@ class BatchedSelfPlay(object):
             self.step_wave()
 
     # ------------------------------------------------- host-buffer API (end to end)
-    def get_actions(self, rows_host, meta_host, temperature=None):
+    def get_actions(self, rows_host, meta_host, temperature=None, hist_host=None):
         """Batched ``AlphaZeroPlayer.get_action(env, temperature, return_prob=True)`` with HOST
         buffers: positions come from pinned host memory, the search runs ``n_playout`` playouts
         per game from fresh trees, and (moves [G], pi [G,A], visits [G,A]) come back to the host.
-        ``rows_host``: uint32/int32 [G,2,H]; ``meta_host``: int32 [G,8] (include/rlzero_b200.h)."""
+        ``rows_host``: uint32/int32 [G,2,H]; ``meta_host``: int32 [G,RZ_META_STRIDE]; Go also takes
+        ``hist_host`` [G,14,H], the history planes (include/rlzero_b200.h)."""
         f = self.forest
         if self._pinned is None:
             self._pinned = dict(
@@ -147,6 +184,13 @@ class BatchedSelfPlay(object):
                 pi=torch.empty(f.G, f.AS, dtype=torch.float32).pin_memory(),
                 visits=torch.empty(f.G, f.AS, dtype=torch.int32).pin_memory())
         p = self._pinned
+        if f.is_go:
+            if hist_host is None:
+                raise ValueError('Go positions need their history planes (hist_host=)')
+            if 'hist' not in p:
+                p['hist'] = torch.empty(f.G, L.GO_HIST, f.H, dtype=torch.int32).pin_memory()
+            p['hist'].copy_(torch.as_tensor(np.asarray(hist_host).view(np.int32)))
+            f.root_hist.copy_(p['hist'], non_blocking=True)
         p['rows'].copy_(torch.as_tensor(np.asarray(rows_host).view(np.int32)))
         p['meta'].copy_(torch.as_tensor(np.asarray(meta_host)))
         f.root_rows.copy_(p['rows'], non_blocking=True)
@@ -182,7 +226,7 @@ class BatchedSelfPlay(object):
 
     def api_bytes(self):
         f = self.forest
-        h2d = f.G * (2 * f.H * 4 + L.META_STRIDE * 4)
+        h2d = f.G * ((2 + (L.GO_HIST if f.is_go else 0)) * f.H * 4 + L.META_STRIDE * 4)
         d2h = f.G * (4 + f.AS * 4 + f.AS * 4)
         return h2d, d2h
 

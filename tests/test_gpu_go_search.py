@@ -103,3 +103,92 @@ def test_move_cap_scores_the_game():
         s = pyoracle.Search(make_policy_value_fn(EVAL_HASH), 40, 5)
         s.simulate(boards[g], 1.0)
         assert np.array_equal(visits[g], s.root_visits(n * n + 1)), g
+
+
+# ------------------------------------------------------------------ network + self-play on Go
+def _go_net(n, blocks, seed=0):
+    import torch
+    from rlzero_b200.games.gomoku.policy_value_net import ResNetPolicyValueNet
+    torch.manual_seed(seed)
+    net = ResNetPolicyValueNet(n, n_blocks=blocks, n_actions=n * n + 1, in_planes=17).cuda().eval()
+    # random-init BatchNorm statistics that are not the identity
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    return net
+
+
+@pytest.mark.parametrize('n,blocks,games', [(9, 2, 12), (19, 3, 5)])
+def test_go_net_forward_vs_torch(n, blocks, games):
+    """Fused GoEnv.observe + stem + trunk + heads on Go positions against the fp32 PyTorch forward of
+    the same module on the oracle's 17-plane observation: probabilities and value within 1e-3 (bf16)."""
+    import torch
+    from oracle.go_oracle import GoEnvOracle
+    from rlzero_b200.games.go import GoBoards
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward
+    net = _go_net(n, blocks)
+    rs = np.random.RandomState(3)
+    gb = GoBoards(games, n, 7.5)
+    envs = [GoEnvOracle(n, 7.5) for _ in range(games)]
+    for e in envs:
+        e.reset()
+    for t in range(40):
+        acts = []
+        for g, e in enumerate(envs):
+            if t >= 5 * g + 3 or e.is_terminal():
+                acts.append(-1)
+                continue
+            legal = list(e.legal_actions())
+            a = int(legal[rs.randint(len(legal) - 1)]) if (len(legal) > 1 and rs.rand() > 0.05) else n * n
+            e.step(a)
+            acts.append(a)
+        gb.step(acts)
+    obs = np.stack([e.observe(e.agent_selection)['observation'].transpose(2, 0, 1) for e in envs]).astype(np.float32)
+    nf = NativeForward(net, max_batch=games)
+    logp, v = nf.forward_boards(gb.rows, gb.meta, games, hist=gb.hist)
+    torch.cuda.synchronize()
+    logp, v = logp[:, :n * n + 1].cpu(), v.cpu()
+    with torch.no_grad():
+        lt, vt = net(torch.from_numpy(obs).cuda())
+    lt, vt = lt.cpu(), vt.cpu().reshape(-1)
+    assert (logp.exp() - lt.exp()).abs().max().item() < 1e-3
+    assert (v - vt).abs().max().item() < 1e-3
+    assert torch.allclose(logp.exp().sum(1), torch.ones(games), atol=1e-4)
+    # the plane-fed entry (AlphaZeroAgent.policy_value path) runs the same kernels on the same values
+    l2, v2 = nf.forward_planes(torch.from_numpy(obs))
+    assert torch.equal(l2.cpu(), logp) and torch.equal(v2.cpu(), v)
+
+
+def test_go_selfplay_runs_whole_games_and_is_shard_invariant():
+    """Batched Go self-play with the tensor-core net: games finish (two passes or the move cap), the
+    winners are what Tromp-Taylor scoring says, and sampled moves do not depend on the sharding."""
+    import torch
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.selfplay import BatchedSelfPlay
+    n = 5
+    net = _go_net(n, 1, seed=2)
+
+    def run(G, offset, ids, n_moves):
+        sp = BatchedSelfPlay(G, n, 1, net=net, n_playout=16, temperature=1.0, add_noise=True, global_offset=offset,
+                             seed=31, game_type=L.GAME_GO, komi=0.5, max_moves=40, ring_capacity=4096)
+        sp.set_random_start_positions(global_ids=ids, max_random_moves=5)
+        moves = []
+        for _ in range(n_moves):
+            sp.play(1)
+            torch.cuda.synchronize()
+            moves.append(sp.forest.move.cpu().numpy().copy())
+        sp.forest.raise_faults()
+        return np.stack(moves), sp
+
+    ids = np.arange(6)
+    m_all, sp = run(6, 0, ids, 50)
+    m_lo, _ = run(3, 0, ids[:3], 50)
+    m_hi, _ = run(3, 3, ids[3:], 50)
+    assert np.array_equal(m_all[:, :3], m_lo) and np.array_equal(m_all[:, 3:], m_hi)
+    st = sp.stats()
+    assert st['games_done'] >= 6                       # the 40-move cap guarantees finished episodes
+    out = sp.forest.drain_trajectories()
+    info = out['info']
+    assert len(info) == st['plies_done'] and set(np.unique(info[:, 2])).issubset({-1, 1})
+    assert np.allclose(out['pi'].sum(1), 1.0, atol=1e-5) and out['pi'].shape[1] == n * n + 1
