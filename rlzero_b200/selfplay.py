@@ -243,6 +243,8 @@ class BatchedSelfPlay(object):
         out = f.drain_trajectories()
         rows, info = out['rows'], out['info']
         n, H, W = len(info), f.H, f.W
+        if f.is_go:
+            return self._go_states(rows, info), out['pi'], info[:, 2].astype(np.float32), info
         states = np.zeros((n, 4, H, W), dtype=np.float32)
         if n:
             bits = ((rows[:, :, :, None] >> np.arange(W, dtype=np.uint32)[None, None, None, :]) & 1).astype(np.float32)
@@ -256,3 +258,30 @@ class BatchedSelfPlay(object):
             stones = bits.sum(axis=(1, 2, 3)).astype(np.int64)
             states[stones % 2 == 0, 3] = 1.0
         return states, out['pi'], info[:, 2].astype(np.float32), info
+
+    def _go_states(self, rows, info):
+        """GoEnv.observe planes [n,17,H,W] (go_env.py:156-178) of the drained plies.  The trajectory
+        keeps (black, white) per ply; the 8-position history is rebuilt from the preceding plies of the
+        same episode, which the ring stores consecutively: entry e of ply j is the position before ply
+        j-e as (stones of its last mover, stones of the player to move), zero for j-e < 1.  Exact for
+        episodes recorded from the empty board (self-play); an episode that started from a set-up
+        position, or whose first plies were overwritten in the ring, lacks the older entries."""
+        f = self.forest
+        n, H, W = len(info), f.H, f.W
+        states = np.zeros((n, 17, H, W), dtype=np.float32)
+        if n == 0:
+            return states
+        bits = ((rows[:, :, :, None] >> np.arange(W, dtype=np.uint32)[None, None, None, :]) & 1).astype(np.float32)
+        mover, slot, episode, ply = info[:, 0], info[:, 3], info[:, 4], info[:, 5]
+        idx = np.arange(n)
+        for e in range(8):
+            src = idx - e
+            ok = (src >= 0)
+            srcc = np.where(ok, src, 0)
+            ok &= (slot[srcc] == slot) & (episode[srcc] == episode) & (ply[srcc] == ply - e) & (ply[srcc] >= 1)
+            t = idx[ok]
+            s_ = srcc[ok]
+            states[t, 2 * e] = bits[s_, 1 - mover[s_]]
+            states[t, 2 * e + 1] = bits[s_, mover[s_]]
+        states[mover == 1, 16] = 1.0
+        return states

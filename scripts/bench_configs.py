@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the parity-case configurations of BASELINE.json (NOT the bench line, which is
 config 3 in bench.py): config 1 TicTacToe / 25 sims / stock net, config 2 Connect Four / 200 sims /
-4096 games / ResNet-6.  One JSON line per configuration."""
+4096 games / ResNet-6, config 4 Go 19x19 / 800 sims / ResNet-20.  One JSON line per configuration."""
 import json
 import os
 import sys
@@ -15,8 +15,8 @@ from rlzero_b200.games.gomoku.policy_value_net import PolicyValueNet, ResNetPoli
 from rlzero_b200.selfplay import BatchedSelfPlay  # noqa: E402
 
 
-def run(name, sp, waves, warm):
-    sp.set_random_start_positions(max_random_moves=3)
+def run(name, sp, waves, warm, random_moves=3):
+    sp.set_random_start_positions(max_random_moves=random_moves)
     sp.warm_up()
     for _ in range(warm):
         sp.step_wave()
@@ -40,26 +40,38 @@ def run(name, sp, waves, warm):
 
 
 def main():
+    only = set(sys.argv[1:])           # e.g. `bench_configs.py 4` runs config 4 alone
     torch.manual_seed(0)
-    # config 1: TicTacToe = GomokuEnv(3, 3), 25 simulations/move, stock PolicyValueNet (fp32 path)
-    net1 = PolicyValueNet(3).cuda().eval()
-    for G in (1, 8192):
-        sp = BatchedSelfPlay(G, 3, 3, net=net1, n_playout=25, add_noise=True, seed=1)
-        run('config1 TicTacToe 3x3 k=3, 25 sims/move, stock PolicyValueNet fp32, %d game(s)' % G, sp,
-            25 * 40, 25)
-    # config 2: Connect Four 6x7, 200 simulations/move, 4096 games, ResNet-6 bf16
-    net2 = ResNetPolicyValueNet(6, n_blocks=6, board_width=7, n_actions=7).cuda().eval()
-    sp = BatchedSelfPlay(4096, 6, 4, net=net2, n_playout=200, add_noise=True, seed=2, board_width=7,
-                         game_type=L.GAME_CONNECT4)
-    run('config2 Connect Four 6x7, 200 sims/move, ResNet-6 bf16, 4096 games', sp, 200 * 12, 200)
-    del sp
-    torch.cuda.empty_cache()
-    # config 4 (board and trunk only): 19x19, 800 simulations/move, ResNet-20 bf16 on the tensor cores.
-    # Go rules are NOT implemented (no runnable oracle): the game is 19x19 five-in-a-row.
-    net4 = ResNetPolicyValueNet(19, n_blocks=20).cuda().eval()
-    sp = BatchedSelfPlay(8192, 19, 5, net=net4, n_playout=800, add_noise=True, seed=3)
-    run('config4-board 19x19 five-in-a-row (Go rules not implemented), 800 sims/move, ResNet-20 bf16, 8192 games',
-        sp, 160, 8)
+    if not only or '1' in only:
+        # config 1: TicTacToe = GomokuEnv(3, 3), 25 simulations/move, stock PolicyValueNet (fp32 path)
+        net1 = PolicyValueNet(3).cuda().eval()
+        for G in (1, 8192):
+            sp = BatchedSelfPlay(G, 3, 3, net=net1, n_playout=25, add_noise=True, seed=1)
+            run('config1 TicTacToe 3x3 k=3, 25 sims/move, stock PolicyValueNet fp32, %d game(s)' % G, sp,
+                25 * 40, 25)
+    if not only or '2' in only:
+        # config 2: Connect Four 6x7, 200 simulations/move, 4096 games, ResNet-6 bf16
+        net2 = ResNetPolicyValueNet(6, n_blocks=6, board_width=7, n_actions=7).cuda().eval()
+        sp = BatchedSelfPlay(4096, 6, 4, net=net2, n_playout=200, add_noise=True, seed=2, board_width=7,
+                             game_type=L.GAME_CONNECT4)
+        run('config2 Connect Four 6x7, 200 sims/move, ResNet-6 bf16, 4096 games', sp, 200 * 12, 200)
+        del sp
+        torch.cuda.empty_cache()
+    if not only or '4' in only:
+        # config 4: Go 19x19 (GoEnv rules: captures, ko, suicide, pass, Tromp-Taylor, komi 7.5), 800
+        # simulations/move, ResNet-20 bf16 on the tensor cores, 17-plane observation, 362 actions;
+        # games start after up to 30 random legal moves; engine-side cap of 722 moves per game
+        net4 = ResNetPolicyValueNet(19, n_blocks=20, n_actions=362, in_planes=17).cuda().eval()
+        sp = BatchedSelfPlay(8192, 19, 1, net=net4, n_playout=800, add_noise=True, seed=3, game_type=L.GAME_GO,
+                             komi=7.5, max_moves=722)
+        run('config4 Go 19x19 (komi 7.5), 800 sims/move, ResNet-20 bf16, 8192 games', sp, 160, 8, random_moves=31)
+        del sp
+        torch.cuda.empty_cache()
+    if '4g' in only:
+        # the same board and trunk with five-in-a-row rules (the pre-Go stand-in of earlier runs)
+        net4 = ResNetPolicyValueNet(19, n_blocks=20).cuda().eval()
+        sp = BatchedSelfPlay(8192, 19, 5, net=net4, n_playout=800, add_noise=True, seed=3)
+        run('config4-board 19x19 five-in-a-row, 800 sims/move, ResNet-20 bf16, 8192 games', sp, 160, 8)
 
 
 if __name__ == '__main__':

@@ -192,3 +192,36 @@ def test_go_selfplay_runs_whole_games_and_is_shard_invariant():
     info = out['info']
     assert len(info) == st['plies_done'] and set(np.unique(info[:, 2])).issubset({-1, 1})
     assert np.allclose(out['pi'].sum(1), 1.0, atol=1e-5) and out['pi'].shape[1] == n * n + 1
+
+
+def test_go_drain_rebuilds_the_17_plane_observation():
+    """Drained Go training tuples: the 17 planes rebuilt from the per-ply boards equal GoEnv.observe
+    of the oracle replaying the same episode (moves are the next ply's last_move)."""
+    import torch
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.selfplay import BatchedSelfPlay
+    from oracle.go_oracle import GoEnvOracle
+    n = 5
+    net = _go_net(n, 1, seed=4)
+    sp = BatchedSelfPlay(4, n, 1, net=net, n_playout=12, temperature=1.0, add_noise=True, seed=5,
+                         game_type=L.GAME_GO, komi=0.5, max_moves=30, ring_capacity=4096)
+    sp.play(64)
+    torch.cuda.synchronize()
+    sp.forest.raise_faults()
+    states, pis, zs, info = sp.drain()
+    assert states.shape[1:] == (17, n, n) and len(states) == len(pis) == len(zs) > 0
+    checked = 0
+    keys = sorted(set((int(a), int(b)) for a, b in info[:, 3:5]))
+    for slot, ep in keys:
+        sel = np.nonzero((info[:, 3] == slot) & (info[:, 4] == ep))[0]
+        assert list(info[sel, 5]) == list(range(len(sel)))          # complete episode, plies in order
+        env = GoEnvOracle(n, 0.5)
+        env.reset()
+        for j, i in enumerate(sel):
+            want = env.observe(env.agent_selection)['observation'].transpose(2, 0, 1).astype(np.float32)
+            assert np.array_equal(states[i], want), (slot, ep, j)
+            assert info[i, 0] == env.current_player()
+            if j + 1 < len(sel):
+                env.step(int(info[sel[j + 1], 1]))
+            checked += 1
+    assert checked == len(states)
