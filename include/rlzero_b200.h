@@ -75,6 +75,22 @@ enum rz_rule {
   RZ_RULE_PUCT = 1               /* (n and W/n) + c*P*sqrt(Np)/(n+1) (deepmind_mcts.py:149-151) */
 };
 
+enum rz_flavour {                /* which of the reference's two search drivers the kernels follow */
+  RZ_FLAVOUR_ALPHAZERO = 0,      /* AlphaZeroMCTS (rlzero/mcts/alphazero_mcts.py:42-103): scalar value, sign flip */
+  RZ_FLAVOUR_DEEPMIND = 1        /* DeepMindMCTS (rlzero/mcts/deepmind_mcts.py:384-646, the OpenSpiel bot): returns
+                                    vector indexed by the player who moved, outcome shortcut in the child score
+                                    (:123-124,146-147), terminal outcomes, optional MCTS-Solver backup (:617-642),
+                                    root-only Dirichlet noise (:484-485), search stops once the root is proven */
+};
+
+enum rz_returns {                /* env.returns() of a finished game, indexed by player */
+  RZ_RETURNS_REFERENCE = 0,      /* bug-compatible with GomokuEnv.returns (gomoku_env.py:210-225): it tests winner
+                                    == 1 / == 2 while players are 0 / 1, so a win of player 1 yields [1,-1] and
+                                    everything else [0,0].  Go (go_env.py:142-143,350-354): [1,-1] if black won
+                                    else [-1,1] -- already consistent */
+  RZ_RETURNS_ZERO_SUM = 1        /* the evident intent: +1 for the winner, -1 for the loser, [0,0] for a tie */
+};
+
 enum rz_eval {                   /* closed-form evaluators, oracle/evaluators.py */
   RZ_EVAL_ZERO = 0, RZ_EVAL_KAT = 1, RZ_EVAL_HASH = 2
 };
@@ -143,6 +159,14 @@ typedef struct rz_tree_desc {
   /* Go only (NULL otherwise): board_history planes 2..15 of go_env.py:174-178, [G][RZ_GO_HIST][H] */
   uint32_t* root_hist;
   uint32_t* leaf_hist;
+  /* DeepMindMCTS flavour only (NULL / 0 otherwise) */
+  int32_t flavour;               /* enum rz_flavour */
+  int32_t solve;                 /* DeepMindMCTS(solve=...): back proven outcomes up the path */
+  int32_t returns_mode;          /* enum rz_returns */
+  int32_t noise_root_only;       /* Dirichlet noise only when the expanded node is the root (deepmind_mcts.py:484) */
+  int32_t* edge_O;               /* [G][max_nodes][AS] SearchNode.outcome of each child: 0 = None, else
+                                    0x100 | (outcome[0]+1) | (outcome[1]+1) << 2 */
+  int32_t* root_O;               /* [G] outcome of the root, same encoding */
 } rz_tree_desc;
 
 /* ---- trajectory store (GameControl.start_self_play, game.py:96-134) ------- */
@@ -235,6 +259,18 @@ int rz_tree_select(const rz_tree_desc* t, void* stream);
 int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, int prior_is_log,
                           const float* value, const double* value64, float noise_eps, float noise_alpha,
                           unsigned long long seed, void* stream);
+/* DeepMindMCTS flavour of the same step (deepmind_mcts.py:596-644): `value` is the evaluation for the
+   player to move at the leaf (returns = [v,-v] in player order); ret64 != NULL overrides it with the
+   evaluator's full returns vector, float64 [G][2] (Evaluator.evaluate, :22-24).  Terminal leaves take
+   env.returns() per t->returns_mode and record it as the node's outcome; with t->solve the proven
+   outcomes are backed up (MCTS-Solver). */
+int rz_tree_expand_backup_dm(const rz_tree_desc* t, const float* prior, int prior_is_log, const float* value,
+                             const double* ret64, float noise_eps, float noise_alpha, unsigned long long seed,
+                             void* stream);
+/* SearchNode.best_child (deepmind_mcts.py:153-175): argmax over the root's children of
+   (outcome[player] or 0, explore_count, total_reward), first maximum; best[g] = -1 if the root has no
+   children.  outcome_out (may be NULL) [G] = the root's outcome code (0 = unproven). */
+int rz_tree_best_child(const rz_tree_desc* t, int32_t* best, int32_t* outcome_out, void* stream);
 /* root statistics + move choice (alphazero_mcts.py:86-94, 144-148):
    visits int32 [G][AS] (0 where no child), pi float32 [G][AS] = softmax(log(N+1e-10)/T),
    move[g] sampled from pi with a counter-based RNG (seed, game, ply); u01 != NULL supplies

@@ -507,3 +507,22 @@ class ConnectFourBoard(object):
 
     def is_terminal(self):
         return self.game_end_winner()[0]
+
+
+class DMBoard(Board):
+    """``Board`` with the extra methods ``DeepMindMCTS`` calls (deepmind_mcts.py:497-506,595-597):
+    ``legal_actions()`` without argument and a ``zero_sum`` switch for ``returns`` (the reference's
+    ``GomokuEnv.returns`` tests winner == 1 / == 2 although players are 0 / 1, gomoku_env.py:216-219;
+    ``zero_sum=True`` is the evident intent, RZ_RETURNS_ZERO_SUM on the device)."""
+
+    def __init__(self, board_size=8, n_in_row=5, zero_sum=False):
+        Board.__init__(self, board_size, n_in_row)
+        self.zero_sum = zero_sum
+
+    def returns(self):
+        if not self.zero_sum:
+            return Board.returns(self)
+        win, winner = self.has_a_winner()
+        if not win:
+            return [0, 0]
+        return [1, -1] if winner == 0 else [-1, 1]

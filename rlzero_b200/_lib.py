@@ -20,6 +20,8 @@ ACTIVE, ENDED_WIN, ENDED_TIE, IDLE = range(4)
 FAULT_ILLEGAL_MOVE, FAULT_POOL_OVERFLOW, FAULT_DEPTH_OVERFLOW, FAULT_LN_TABLE = 1, 2, 4, 8
 FAULT_NO_CHILDREN, FAULT_CARRY_DROPPED, FAULT_TRAJ_OVERFLOW = 16, 32, 64
 RULE_UCT, RULE_PUCT = 0, 1
+FLAVOUR_ALPHAZERO, FLAVOUR_DEEPMIND = 0, 1
+RETURNS_REFERENCE, RETURNS_ZERO_SUM = 0, 1
 EVAL_ZERO, EVAL_KAT, EVAL_HASH = 0, 1, 2
 CHILD_TERMINAL, CHILD_OVERFLOW = -1, -2
 MAX_BOARD = 19
@@ -47,7 +49,9 @@ class TreeDesc(C.Structure):
                 ('root_rows', _vp), ('root_meta', _vp),
                 ('path_node', _vp), ('path_action', _vp), ('depth', _vp),
                 ('leaf_rows', _vp), ('leaf_meta', _vp), ('ln_table', _vp),
-                ('root_hist', _vp), ('leaf_hist', _vp)]
+                ('root_hist', _vp), ('leaf_hist', _vp),
+                ('flavour', C.c_int32), ('solve', C.c_int32), ('returns_mode', C.c_int32),
+                ('noise_root_only', C.c_int32), ('edge_O', _vp), ('root_O', _vp)]
 
 
 class TrajDesc(C.Structure):
@@ -86,6 +90,9 @@ SIGNATURES = {
     'rz_tree_select': (C.c_int, [_TD, _vp]),
     'rz_tree_expand_backup': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,
                                         C.c_ulonglong, _vp]),
+    'rz_tree_expand_backup_dm': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,
+                                           C.c_ulonglong, _vp]),
+    'rz_tree_best_child': (C.c_int, [_TD, _vp, _vp, _vp]),
     'rz_tree_root_policy': (C.c_int, [_TD, C.c_double, _vp, _vp, _vp, _vp, C.c_ulonglong, _vp]),
     'rz_tree_advance': (C.c_int, [_TD, _vp, C.c_int, C.c_int, _TJ, _vp, C.c_int, _vp]),
     'rz_eval_closed_form': (C.c_int, [_TD, C.c_int, _vp, _vp, _vp]),

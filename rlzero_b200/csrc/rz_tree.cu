@@ -44,10 +44,23 @@ __device__ __forceinline__ void rz_warp_argmax(double& s, int& slot, int& n) {
   }
 }
 
+// SearchNode.outcome codes (DeepMindMCTS flavour): 0 = None, else 0x100 | (o[0]+1) | (o[1]+1) << 2
+__device__ __forceinline__ int rz_outcome_enc(int o0, int o1) { return 0x100 | (o0 + 1) | ((o1 + 1) << 2); }
+__device__ __forceinline__ int rz_outcome_of(int code, int player) { return ((code >> (2 * player)) & 3) - 1; }
+
+// env.returns() of a finished game (enum rz_returns)
+__device__ __forceinline__ void rz_game_returns(int game_type, int mode, int status, int winner, int& r0, int& r1) {
+  r0 = 0; r1 = 0;
+  if (status != RZ_ENDED_WIN) return;
+  if (game_type == RZ_GAME_GO) { r0 = winner == 0 ? 1 : -1; r1 = -r0; return; }      // go_env.py:142-143
+  if (mode == RZ_RETURNS_REFERENCE) { if (winner == 1) { r0 = 1; r1 = -1; } return; }  // gomoku_env.py:216-219
+  r0 = winner == 0 ? 1 : -1; r1 = -r0;
+}
+
 // ---------------------------------------------------------------------------
 // K1: select.  One playout descent per tree + leaf terminal test.
 // ---------------------------------------------------------------------------
-template <class GM>
+template <class GM, bool DM>
 __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc t) {
   const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
@@ -56,12 +69,14 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
   const int AS = t.game.action_stride;
   const int iters = AS >> 5;
   int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
-  if (rmeta[RZ_META_STATUS] != RZ_ACTIVE) {
+  // a finished game, or (DeepMindMCTS) a proven root: `if root.outcome is not None: break` (:643-644)
+  if (rmeta[RZ_META_STATUS] != RZ_ACTIVE || (DM && t.root_O[g] != 0)) {
     if (lane == 0) t.depth[g] = -1;
     return;
   }
   typename GM::board b;
   GM::load_root(b, t, g);
+  const int root_player = b.player;
 
   int fault = 0;
   int depth = 0;
@@ -82,6 +97,15 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
 
     double best_s = 0.0;
     int best_slot = -1, best_n = 0;
+    // DeepMindMCTS: a child with a known outcome scores outcome[child.player] (deepmind_mcts.py:123-124,
+    // 146-147); the children of a node at this depth were all moved by the same player
+    int oc[RZ_MAX_ITERS];
+    const int mover = root_player ^ (depth & 1);
+    if (DM) {
+      const int32_t* __restrict__ eO = t.edge_O + base;
+#pragma unroll
+      for (int i = 0; i < RZ_MAX_ITERS; ++i) oc[i] = (i < iters && nv[i] > 0) ? eO[lane + 32 * i] : 0;
+    }
     if (t.rule == RZ_RULE_UCT) {
       // node.py:76-80: +inf when the parent or the child is unvisited -> first such child wins
       int first_unvisited = -1;
@@ -111,7 +135,8 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
             const double n = (double)nv[i];
             const double q = __ddiv_rn(wv[i], n);
             const double u = __dsqrt_rn(__ddiv_rn(lnNp, n));
-            const double s = __dadd_rn(q, __dmul_rn(t.c_puct, u));
+            double s = __dadd_rn(q, __dmul_rn(t.c_puct, u));
+            if (DM && oc[i]) s = (double)rz_outcome_of(oc[i], mover);
             if (best_slot < 0 || s > best_s) { best_s = s; best_slot = lane + 32 * i; best_n = nv[i]; }
           }
         }
@@ -129,7 +154,8 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
           const double q = nv[i] > 0 ? __ddiv_rn(eW[slot], (double)nv[i]) : 0.0;
           const double u = __ddiv_rn(__dmul_rn(__dmul_rn(t.c_puct, (double)eP[slot]), sq),
                                      (double)(nv[i] + 1));
-          const double s = __dadd_rn(q, u);
+          double s = __dadd_rn(q, u);
+          if (DM && oc[i]) s = (double)rz_outcome_of(oc[i], mover);
           if (best_slot < 0 || s > best_s) { best_s = s; best_slot = slot; best_n = nv[i]; }
         }
       }
@@ -193,7 +219,7 @@ __device__ float rz_gamma_draw(float alpha, unsigned long long seed, uint32_t c0
 // ---------------------------------------------------------------------------
 // K5+K6: expand the leaf (unless terminal) and back the value up the path.
 // ---------------------------------------------------------------------------
-template <class GM>
+template <class GM, bool DM>
 __global__ void __launch_bounds__(RZ_TREE_THREADS)
 rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int prior_is_log,
                         const float* __restrict__ value, const double* __restrict__ value64,
@@ -232,13 +258,14 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
       const float* pr = prior + (size_t)g * AS;
       float noise_sum = 0.0f;
       float nz[RZ_MAX_ITERS];
-      const bool noisy = noise_eps > 0.0f;
+      const bool noisy = noise_eps > 0.0f && !(DM && t.noise_root_only && depth > 0);
 #pragma unroll
       for (int i = 0; i < RZ_MAX_ITERS; ++i) {
         if (i >= (AS >> 5)) break;
         const int s = lane + 32 * i;
         const bool legal = GM::slot_legal(lctx, s, q);
         t.edge_N[nb + s] = legal ? 0 : -1;
+        if (DM) t.edge_O[nb + s] = 0;
         nz[i] = 0.0f;
         if (noisy && legal) {
           nz[i] = rz_gamma_draw(noise_alpha, seed, (uint32_t)(global_offset + g),
@@ -282,19 +309,89 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
     t.edge_child[rz_edge_base(t, g, pnode[depth - 1]) + pact[depth - 1]] = child_mark;
   }
 
-  // node.py:135-144 with update_recursive(-leaf_value): the leaf gets -v, its parent +v, ...
-  // edge k (0-based from the root) holds the node at depth k+1 and gets (-1)^(depth-k) * v.
-  for (int k = lane; k < depth; k += 32) {
-    const size_t e = rz_edge_base(t, g, pnode[k]) + pact[k];
-    const double x = ((depth - k) & 1) ? -v : v;
-    const int n = t.edge_N[e];
-    t.edge_W[e] = n > 0 ? __dadd_rn(t.edge_W[e], x) : __dadd_rn(0.0, x);
-    t.edge_N[e] = n + 1;
-  }
-  if (lane == 0) {
-    const double x = (depth & 1) ? v : -v;  // root at depth 0: (-1)^(depth+1) * v
-    t.root_W[g] = __dadd_rn(t.root_W[g], x);
-    t.root_N[g] += 1;
+  if (DM) {
+    // deepmind_mcts.py:596-644.  returns: env.returns() at a terminal leaf, else the evaluation
+    // ([v,-v] in the order (player to move at the leaf, the other), or the evaluator's own vector);
+    // every node on the path adds returns[node.player], node.player = who moved into it
+    const int rp = rm[RZ_META_PLAYER];
+    double ret[2];
+    int code = 0;
+    if (status != RZ_ACTIVE) {
+      int r0, r1;
+      rz_game_returns(t.game.game_type, t.returns_mode, status, lm[RZ_META_WINNER], r0, r1);
+      ret[0] = (double)r0; ret[1] = (double)r1;
+      code = rz_outcome_enc(r0, r1);
+    } else if (value64) {                  // here: the evaluator's returns vector [G][2]
+      ret[0] = value64[2 * g]; ret[1] = value64[2 * g + 1];
+    } else {
+      const int pl = lm[RZ_META_PLAYER] & 1;
+      ret[pl] = v; ret[pl ^ 1] = -v;
+    }
+    for (int k = lane; k < depth; k += 32) {
+      const size_t e = rz_edge_base(t, g, pnode[k]) + pact[k];
+      const double x = ret[(rp ^ (k & 1)) & 1];
+      const int n = t.edge_N[e];
+      t.edge_W[e] = n > 0 ? __dadd_rn(t.edge_W[e], x) : __dadd_rn(0.0, x);
+      t.edge_N[e] = n + 1;
+    }
+    if (lane == 0) {
+      t.root_W[g] = __dadd_rn(t.root_W[g], ret[rp & 1]);
+      t.root_N[g] += 1;
+    }
+    if (code) {
+      // visit_path[-1].outcome = returns (:599), then MCTS-Solver up the path (:617-642)
+      if (lane == 0) {
+        if (depth == 0) t.root_O[g] = code;
+        else t.edge_O[rz_edge_base(t, g, pnode[depth - 1]) + pact[depth - 1]] = code;
+      }
+      __syncwarp();
+      bool solved = t.solve != 0;
+      for (int d = depth - 1; solved && d >= 0; --d) {
+        const size_t nb = rz_edge_base(t, g, pnode[d]);
+        const int mover = (rp ^ (d & 1)) & 1;          // node.children[0].player
+        int best_o = -2, best_slot = 0x7fffffff, best_code = 0;
+        bool all_solved = true;
+        for (int s = lane; s < AS; s += 32) {
+          if (t.edge_N[nb + s] < 0) continue;          // not a child
+          const int c = t.edge_O[nb + s];
+          if (c == 0) { all_solved = false; continue; }
+          const int o = rz_outcome_of(c, mover);
+          if (o > best_o) { best_o = o; best_slot = s; best_code = c; }   // first maximum per lane (s ascends)
+        }
+        all_solved = __all_sync(RZ_FULL, all_solved);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const int o2 = __shfl_xor_sync(RZ_FULL, best_o, off);
+          const int s2 = __shfl_xor_sync(RZ_FULL, best_slot, off);
+          const int c2 = __shfl_xor_sync(RZ_FULL, best_code, off);
+          if (o2 > best_o || (o2 == best_o && s2 < best_slot)) { best_o = o2; best_slot = s2; best_code = c2; }
+        }
+        if (best_o > -2 && (all_solved || best_o == 1)) {              // max_utility() == 1
+          if (lane == 0) {
+            if (d == 0) t.root_O[g] = best_code;
+            else t.edge_O[rz_edge_base(t, g, pnode[d - 1]) + pact[d - 1]] = best_code;
+          }
+          __syncwarp();
+        } else {
+          solved = false;
+        }
+      }
+    }
+  } else {
+    // node.py:135-144 with update_recursive(-leaf_value): the leaf gets -v, its parent +v, ...
+    // edge k (0-based from the root) holds the node at depth k+1 and gets (-1)^(depth-k) * v.
+    for (int k = lane; k < depth; k += 32) {
+      const size_t e = rz_edge_base(t, g, pnode[k]) + pact[k];
+      const double x = ((depth - k) & 1) ? -v : v;
+      const int n = t.edge_N[e];
+      t.edge_W[e] = n > 0 ? __dadd_rn(t.edge_W[e], x) : __dadd_rn(0.0, x);
+      t.edge_N[e] = n + 1;
+    }
+    if (lane == 0) {
+      const double x = (depth & 1) ? v : -v;  // root at depth 0: (-1)^(depth+1) * v
+      t.root_W[g] = __dadd_rn(t.root_W[g], x);
+      t.root_N[g] += 1;
+    }
   }
 }
 
@@ -386,6 +483,7 @@ __device__ void rz_tree_fresh(const rz_tree_desc& t, int g, int n, double w) {
   t.n_nodes[g] = 0;
   t.root_N[g] = n;
   t.root_W[g] = w;
+  if (t.root_O) t.root_O[g] = 0;
 }
 
 __device__ __forceinline__ int rz_newidx(const uint32_t* bits, const uint32_t* wprefix, int i) {
@@ -597,6 +695,47 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
 }
 
 // ---------------------------------------------------------------------------
+// SearchNode.best_child (deepmind_mcts.py:153-175): max over the root's children of the key
+// (outcome[player] or 0, explore_count, total_reward); first maximum wins.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(RZ_TREE_THREADS)
+rz_best_child_kernel(rz_tree_desc t, int32_t* __restrict__ best, int32_t* __restrict__ outcome_out) {
+  const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  const int lane = rz_lane();
+  const int AS = t.game.action_stride;
+  const int rp = t.root_meta[(size_t)g * RZ_META_STRIDE + RZ_META_PLAYER] & 1;
+  const size_t base = rz_edge_base(t, g, 0);
+  int bo = -2, bn = -1, bs = 0x7fffffff;
+  double bw = 0.0;
+  if (t.n_nodes[g] > 0) {
+    for (int s = lane; s < AS; s += 32) {
+      const int n = t.edge_N[base + s];
+      if (n < 0) continue;
+      const int c = t.edge_O ? t.edge_O[base + s] : 0;
+      const int o = c ? rz_outcome_of(c, rp) : 0;
+      const double w = n > 0 ? t.edge_W[base + s] : 0.0;
+      if (bs == 0x7fffffff || o > bo || (o == bo && (n > bn || (n == bn && w > bw)))) { bo = o; bn = n; bw = w; bs = s; }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const int o2 = __shfl_xor_sync(RZ_FULL, bo, off);
+    const int n2 = __shfl_xor_sync(RZ_FULL, bn, off);
+    const double w2 = __shfl_xor_sync(RZ_FULL, bw, off);
+    const int s2 = __shfl_xor_sync(RZ_FULL, bs, off);
+    if (s2 == 0x7fffffff) continue;
+    const bool greater = bs == 0x7fffffff || o2 > bo || (o2 == bo && (n2 > bn || (n2 == bn && w2 > bw)));
+    const bool equal = bs != 0x7fffffff && o2 == bo && n2 == bn && w2 == bw;
+    if (greater || (equal && s2 < bs)) { bo = o2; bn = n2; bw = w2; bs = s2; }
+  }
+  if (lane == 0) {
+    best[g] = bs == 0x7fffffff ? -1 : bs;
+    if (outcome_out) outcome_out[g] = t.root_O ? t.root_O[g] : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Utility kernels + C ABI
 // ---------------------------------------------------------------------------
 __global__ void rz_tree_reset_kernel(rz_tree_desc t, const uint8_t* __restrict__ mask) {
@@ -607,6 +746,7 @@ __global__ void rz_tree_reset_kernel(rz_tree_desc t, const uint8_t* __restrict__
   t.root_N[g] = 0;
   t.root_W[g] = 0.0;
   t.depth[g] = -1;
+  if (t.root_O) t.root_O[g] = 0;
 }
 
 static int rz_check_tree(const rz_tree_desc* t, const char* who) {
@@ -630,6 +770,11 @@ static int rz_check_tree(const rz_tree_desc* t, const char* who) {
   RZ_REQUIRE(t->ln_table && t->ln_table_len >= 2, "%s: ln table missing", who);
   RZ_REQUIRE(t->game.game_type != RZ_GAME_GO || (t->root_hist && t->leaf_hist),
              "%s: Go needs the root_hist / leaf_hist planes", who);
+  RZ_REQUIRE(t->flavour == RZ_FLAVOUR_ALPHAZERO || t->flavour == RZ_FLAVOUR_DEEPMIND, "%s: flavour %d", who, t->flavour);
+  RZ_REQUIRE(t->flavour != RZ_FLAVOUR_DEEPMIND || (t->edge_O && t->root_O),
+             "%s: the DeepMindMCTS flavour needs the outcome arrays edge_O / root_O", who);
+  RZ_REQUIRE(t->returns_mode == RZ_RETURNS_REFERENCE || t->returns_mode == RZ_RETURNS_ZERO_SUM,
+             "%s: returns_mode %d", who, t->returns_mode);
   return 0;
 }
 
@@ -646,12 +791,27 @@ extern "C" int rz_tree_reset(const rz_tree_desc* t, const uint8_t* tree_mask, vo
 extern "C" int rz_tree_select(const rz_tree_desc* t, void* stream) {
   if (rz_check_tree(t, "rz_tree_select")) return -1;
   if (t->n_trees == 0) return 0;
-  if (t->game.game_type == RZ_GAME_GO)
-    rz_select_kernel<rz_go_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(*t);
-  else
-    rz_select_kernel<rz_line_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(*t);
+  const dim3 grid = rz_tree_grid(t->n_trees);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool go = t->game.game_type == RZ_GAME_GO, dm = t->flavour == RZ_FLAVOUR_DEEPMIND;
+  if (go && dm) rz_select_kernel<rz_go_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(*t);
+  else if (go) rz_select_kernel<rz_go_game, false><<<grid, RZ_TREE_THREADS, 0, st>>>(*t);
+  else if (dm) rz_select_kernel<rz_line_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(*t);
+  else rz_select_kernel<rz_line_game, false><<<grid, RZ_TREE_THREADS, 0, st>>>(*t);
   RZ_LAUNCH_CHECK("rz_tree_select");
   return 0;
+}
+
+static int rz_expand_backup_launch(const rz_tree_desc* t, const float* prior, int prior_is_log,
+                                   const float* value, const double* value64, float noise_eps,
+                                   float noise_alpha, unsigned long long seed, void* stream);
+
+extern "C" int rz_tree_expand_backup_dm(const rz_tree_desc* t, const float* prior, int prior_is_log,
+                                        const float* value, const double* ret64, float noise_eps,
+                                        float noise_alpha, unsigned long long seed, void* stream) {
+  if (rz_check_tree(t, "rz_tree_expand_backup_dm")) return -1;
+  RZ_REQUIRE(t->flavour == RZ_FLAVOUR_DEEPMIND, "rz_tree_expand_backup_dm: the tree is not in the DeepMindMCTS flavour");
+  return rz_expand_backup_launch(t, prior, prior_is_log, value, ret64, noise_eps, noise_alpha, seed, stream);
 }
 
 extern "C" int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, int prior_is_log,
@@ -659,17 +819,27 @@ extern "C" int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, 
                                      float noise_alpha,
                                      unsigned long long seed, void* stream) {
   if (rz_check_tree(t, "rz_tree_expand_backup")) return -1;
+  RZ_REQUIRE(t->flavour == RZ_FLAVOUR_ALPHAZERO, "rz_tree_expand_backup: DeepMindMCTS trees use rz_tree_expand_backup_dm");
+  return rz_expand_backup_launch(t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, stream);
+}
+
+static int rz_expand_backup_launch(const rz_tree_desc* t, const float* prior, int prior_is_log,
+                                   const float* value, const double* value64, float noise_eps,
+                                   float noise_alpha, unsigned long long seed, void* stream) {
   RZ_REQUIRE(value || value64, "rz_tree_expand_backup: null value");
   RZ_REQUIRE(prior || !t->store_priors, "rz_tree_expand_backup: null prior with store_priors");
   RZ_REQUIRE(noise_eps >= 0.0f && noise_eps <= 1.0f, "rz_tree_expand_backup: noise_eps %f", noise_eps);
   RZ_REQUIRE(noise_eps == 0.0f || noise_alpha > 0.0f, "rz_tree_expand_backup: noise_alpha %f", noise_alpha);
   if (t->n_trees == 0) return 0;
-  if (t->game.game_type == RZ_GAME_GO)
-    rz_expand_backup_kernel<rz_go_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(
-        *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset);
-  else
-    rz_expand_backup_kernel<rz_line_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(
-        *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset);
+  const dim3 grid = rz_tree_grid(t->n_trees);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool go = t->game.game_type == RZ_GAME_GO, dm = t->flavour == RZ_FLAVOUR_DEEPMIND;
+#define RZ_EB_ARGS *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset
+  if (go && dm) rz_expand_backup_kernel<rz_go_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
+  else if (go) rz_expand_backup_kernel<rz_go_game, false><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
+  else if (dm) rz_expand_backup_kernel<rz_line_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
+  else rz_expand_backup_kernel<rz_line_game, false><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
+#undef RZ_EB_ARGS
   RZ_LAUNCH_CHECK("rz_tree_expand_backup");
   return 0;
 }
@@ -712,5 +882,14 @@ extern "C" int rz_tree_advance(const rz_tree_desc* t, const int32_t* moves, int 
     rz_advance_kernel<rz_line_game><<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, smem, (cudaStream_t)stream>>>(
         *t, moves, keep_subtree, max_carry, td, traj != nullptr, pi, auto_reset, words);
   RZ_LAUNCH_CHECK("rz_tree_advance");
+  return 0;
+}
+
+extern "C" int rz_tree_best_child(const rz_tree_desc* t, int32_t* best, int32_t* outcome_out, void* stream) {
+  if (rz_check_tree(t, "rz_tree_best_child")) return -1;
+  RZ_REQUIRE(best, "rz_tree_best_child: null output");
+  if (t->n_trees == 0) return 0;
+  rz_best_child_kernel<<<rz_tree_grid(t->n_trees), RZ_TREE_THREADS, 0, (cudaStream_t)stream>>>(*t, best, outcome_out);
+  RZ_LAUNCH_CHECK("rz_tree_best_child");
   return 0;
 }

@@ -46,7 +46,12 @@ class SearchForest(object):
     def __init__(self, n_trees, board_size, n_in_row, n_playout=800, c_puct=5.0,
                  rule=L.RULE_UCT, max_carry=None, max_nodes=None, store_priors=True,
                  device='cuda', global_offset=0, ln_table_len=None, with_trajectories=False,
-                 ring_capacity=None, board_width=None, game_type=L.GAME_GOMOKU, komi=7.5, max_moves=0):
+                 ring_capacity=None, board_width=None, game_type=L.GAME_GOMOKU, komi=7.5, max_moves=0,
+                 flavour=L.FLAVOUR_ALPHAZERO, solve=False, returns_mode=L.RETURNS_REFERENCE,
+                 noise_root_only=False):
+        """``flavour = L.FLAVOUR_DEEPMIND`` runs the reference's second search driver, DeepMindMCTS
+        (rlzero/mcts/deepmind_mcts.py:384-646): returns vectors, outcome shortcut, terminal outcomes,
+        ``solve`` (MCTS-Solver), root-only noise, early stop on a proven root."""
         if not torch.cuda.is_available():
             raise L.NativeLibraryError('rlzero_b200 needs a CUDA device (no CPU fallback)')
         self.lib = L.load()
@@ -103,6 +108,11 @@ class SearchForest(object):
         # Go: board_history planes 2..15 of every root / leaf position (go_env.py:174-178)
         self.root_hist = torch.zeros(G, L.GO_HIST, H, dtype=i32, device=dev) if self.is_go else None
         self.leaf_hist = torch.zeros(G, L.GO_HIST, H, dtype=i32, device=dev) if self.is_go else None
+        self.flavour = int(flavour)
+        self.is_dm = self.flavour == L.FLAVOUR_DEEPMIND
+        self.edge_O = torch.zeros(n_edges, dtype=i32, device=dev) if self.is_dm else None
+        self.root_O = torch.zeros(G, dtype=i32, device=dev) if self.is_dm else None
+        self.best = torch.full((G,), -1, dtype=i32, device=dev) if self.is_dm else None
         n_ln = int(ln_table_len) if ln_table_len else max(1 << 16, 4 * self.n_playout + 2)
         self.ln_table = torch.from_numpy(ln_table(n_ln)).to(dev)
         # evaluator outputs for one wave
@@ -127,6 +137,10 @@ class SearchForest(object):
         d.edge_P = self.edge_P.data_ptr() if self.edge_P is not None else None
         d.root_hist = self.root_hist.data_ptr() if self.is_go else None
         d.leaf_hist = self.leaf_hist.data_ptr() if self.is_go else None
+        d.flavour, d.solve, d.returns_mode = self.flavour, int(bool(solve)), int(returns_mode)
+        d.noise_root_only = int(bool(noise_root_only))
+        d.edge_O = self.edge_O.data_ptr() if self.is_dm else None
+        d.root_O = self.root_O.data_ptr() if self.is_dm else None
         self.desc = d
         self.traj = None
         self.tdesc = None
@@ -216,6 +230,12 @@ class SearchForest(object):
                       prior=None, value=None, value64=None):
         prior = self.prior if prior is None else prior
         value = self.value if value is None else value
+        if self.is_dm:      # value64 is then the evaluator's returns vector, float64 [G][2]
+            L.check(self.lib.rz_tree_expand_backup_dm(C.byref(self.desc), L.ptr(prior), int(prior_is_log),
+                                                      L.ptr(value), L.ptr(value64), float(noise_eps),
+                                                      float(noise_alpha), int(seed), self._s()),
+                    'rz_tree_expand_backup_dm')
+            return
         L.check(self.lib.rz_tree_expand_backup(C.byref(self.desc), L.ptr(prior), int(prior_is_log),
                                                L.ptr(value), L.ptr(value64), float(noise_eps),
                                                float(noise_alpha), int(seed), self._s()),
@@ -232,6 +252,16 @@ class SearchForest(object):
         L.check(self.lib.rz_tree_root_policy(C.byref(self.desc), float(temperature), L.ptr(self.visits),
                                              L.ptr(self.pi), L.ptr(self.move) if want_move else None,
                                              L.ptr(u), int(seed), self._s()), 'rz_tree_root_policy')
+
+    def best_child(self):
+        """SearchNode.best_child of every root (deepmind_mcts.py:153-175) -> (action [G], root outcome
+        code [G]) host arrays; DeepMindMCTS flavour only."""
+        if not self.is_dm:
+            raise RuntimeError('best_child() belongs to the DeepMindMCTS flavour')
+        oc = torch.zeros(self.G, dtype=torch.int32, device=self.device)
+        L.check(self.lib.rz_tree_best_child(C.byref(self.desc), L.ptr(self.best), L.ptr(oc), self._s()),
+                'rz_tree_best_child')
+        return self.best.cpu().numpy(), oc.cpu().numpy()
 
     def advance(self, moves=None, keep_subtree=True, record=False, auto_reset=False):
         """env.step(move) on the roots + update_with_move (alphazero_mcts.py:96-103)."""
@@ -326,8 +356,12 @@ class SearchForest(object):
         Cc = self.edge_child[sl].cpu().numpy().reshape(-1, AS)[:, :A]
         P = (self.edge_P[sl].cpu().numpy().reshape(-1, AS)[:, :A] if self.edge_P is not None
              else np.ones_like(W, dtype=np.float32))
-        return dict(n_nodes=nn, N=N, W=W, child=Cc, P=P, root_N=int(self.root_N[g]),
-                    root_W=float(self.root_W[g]))
+        out = dict(n_nodes=nn, N=N, W=W, child=Cc, P=P, root_N=int(self.root_N[g]),
+                   root_W=float(self.root_W[g]))
+        if self.is_dm:
+            out['O'] = self.edge_O[sl].cpu().numpy().reshape(-1, AS)[:, :A]
+            out['root_O'] = int(self.root_O[g])
+        return out
 
     def boards(self):
         """Root positions as (rows[G,2,H] uint32, meta[G,8] int32) numpy arrays."""

@@ -101,3 +101,37 @@ def test_selfplay_episode(ep):
         assert sha == rec['state_sha1']
         assert [float(x).hex() for x in pi] == rec['pi']
         assert float(z) == rec['z']
+
+
+# ----------------------------------------------------------------- DeepMindMCTS fixtures
+def _dm_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'dm_mcts.json')) as f:
+        return json.load(f)
+
+
+def test_dm_restatement_matches_reference_fixtures():
+    """oracle.dm_oracle.DMSearch against vectors the live DeepMindMCTS produced
+    (scripts/make_golden_dm.py): visit counts, value sums, priors, outcomes, best child, early stop."""
+    import numpy as np
+    from oracle import dm_oracle, pyoracle
+    cases = _dm_cases()
+    assert len(cases) >= 15 and any(c['root_outcome'] is not None for c in cases)
+    for c in cases:
+        b = pyoracle.DMBoard(c['size'], c['k'])
+        b.reset()
+        for a in c['moves']:
+            b.step(a)
+        kw = {}
+        if c['noise_seed'] is not None:
+            rs = np.random.RandomState(c['noise_seed'])
+            kw = dict(add_exploration_noise=True, dirichlet_noise_epsilon=0.25,
+                      noise_fn=lambda n, rs=rs: rs.dirichlet([0.25] * n))
+        s = dm_oracle.DMSearch(dm_oracle.ClosedFormEvaluator(c['eval_id']), c['sims'], 2, c['method'],
+                               solve=c['solve'], **kw)
+        root = s.search(b)
+        assert root.n == c['root_n'] and root.w == c['root_w'] and root.outcome == c['root_outcome'], c['moves']
+        got = [[ch.action, ch.n, ch.w, ch.outcome, ch.prior] for ch in root.children]
+        assert got == c['children'], c['moves']
+        assert root.best_child().action == c['best']

@@ -84,3 +84,81 @@ def test_env_observation_and_quirks(ref):
         env.step(a)
     with pytest.raises(AssertionError):
         b.step(a)
+
+
+# ----------------------------------------------------------------- DeepMindMCTS (second search driver)
+def _dm_reference():
+    import contextlib
+    import io
+    import sys
+    ref = ref_loader.load()
+    if ref_loader.REFERENCE_ROOT + '/rlzero' not in sys.path:
+        sys.path.insert(0, ref_loader.REFERENCE_ROOT + '/rlzero')   # deepmind_mcts.py:9 `from games.base_env ...`
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        from rlzero.mcts import deepmind_mcts as dm
+
+    class Adapter(ref.GomokuEnv):                 # deepmind_mcts.py:497 calls legal_actions() bare
+        def legal_actions(self, player=None):
+            return list(self.leagel_actions())
+
+    def run(env, **kw):
+        m = dm.DeepMindMCTS(env, **kw)
+        return m
+
+    return dm, Adapter, contextlib, io
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+@pytest.mark.parametrize('size,k,moves,sims,method,solve,eval_id', [
+    (3, 3, [], 60, 'puct', True, 2), (3, 3, [0, 3, 1, 4], 80, 'puct', True, 2), (3, 3, [4, 0], 120, 'uct', True, 2),
+    (3, 3, [0, 3, 1, 4], 80, 'uct', False, 1), (4, 3, [5, 0, 6], 150, 'puct', True, 2), (6, 4, [14, 15, 20], 200, 'puct', False, 2),
+    (5, 4, [12, 7, 13, 8, 11], 300, 'uct', True, 2)])
+def test_dm_restatement_matches_live_reference(size, k, moves, sims, method, solve, eval_id):
+    from oracle import dm_oracle
+    dm, Adapter, contextlib, io = _dm_reference()
+    env = Adapter(size, k)
+    env.reset()
+    mine = pyoracle.DMBoard(size, k)
+    mine.reset()
+    for a in moves:
+        env.step(a)
+        mine.step(a)
+    ev = dm_oracle.ClosedFormEvaluator(eval_id)
+    bot = dm.DeepMindMCTS(env, uct_c=2, max_simulations=sims, evaluator=ev, child_selection_method=method,
+                          solve=solve)
+    bot._random_state = dm_oracle.NoShuffle()
+    with contextlib.redirect_stdout(io.StringIO()):
+        root = bot.mcts_search(env)
+        best = root.best_child().action
+    s = dm_oracle.DMSearch(ev, sims, 2, method, solve=solve)
+    got = s.search(mine)
+    assert got.n == root.explore_count and got.w == root.total_reward
+    assert got.outcome == root.outcome
+    assert [(c.action, c.n, c.w, c.outcome) for c in got.children] == \
+        [(c.action, c.explore_count, c.total_reward, c.outcome) for c in root.children]
+    assert got.best_child().action == best
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference tree not present')
+def test_dm_root_noise_matches_live_reference():
+    from oracle import dm_oracle
+    dm, Adapter, contextlib, io = _dm_reference()
+    env = Adapter(4, 3)
+    env.reset()
+    mine = pyoracle.DMBoard(4, 3)
+    mine.reset()
+    ev = dm_oracle.ClosedFormEvaluator(2)
+    bot = dm.DeepMindMCTS(env, uct_c=2, max_simulations=120, evaluator=ev, child_selection_method='puct',
+                          add_exploration_noise=True, dirichlet_noise_alpha=1.0, dirichlet_noise_epsilon=0.25,
+                          solve=True)
+    bot._random_state = dm_oracle.NoShuffle(np.random.RandomState(11))
+    with contextlib.redirect_stdout(io.StringIO()):
+        root = bot.mcts_search(env)
+    rs = np.random.RandomState(11)
+    s = dm_oracle.DMSearch(ev, 120, 2, 'puct', add_exploration_noise=True, dirichlet_noise_epsilon=0.25,
+                           solve=True, noise_fn=lambda n: rs.dirichlet([0.25] * n))
+    got = s.search(mine)
+    assert [(c.action, c.n, c.w, c.prior) for c in got.children] == \
+        [(c.action, c.explore_count, c.total_reward, c.prior) for c in root.children]
