@@ -309,6 +309,13 @@ int rz_gather_rows(const float* src, const long long* index, float* dst, int n, 
 int rz_eval_rollout(const rz_tree_desc* t, int mode, unsigned long long seed, int n_limit, float* prior,
                     float* value, void* stream);
 
+/* RandomRolloutEvaluator of the DeepMindMCTS driver (rlzero/mcts/deepmind_mcts.py:31-62): uniform priors
+   over the leaf's legal actions and ret64 [G][2] = mean env.returns() (per t->returns_mode) of n_rollouts
+   uniformly random playouts from the leaf (each at most n_limit plies; Go playouts include the pass and
+   end by two passes or the move cap).  Feed ret64 to rz_tree_expand_backup_dm. */
+int rz_eval_rollout_dm(const rz_tree_desc* t, int n_rollouts, unsigned long long seed, int n_limit,
+                       float* prior, double* ret64, void* stream);
+
 /* ---- policy-value network forward (rlzero/games/gomoku/policy_value_net.py:34-52) -------- */
 /* heads weights, all float32 device pointers.  FC weights are stored TRANSPOSED ([in][out]);
    the flatten order of the FC inputs is c*HW + pos (x.view(-1, C*H*W) on NCHW, :42,48). */

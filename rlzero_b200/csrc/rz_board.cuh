@@ -149,4 +149,14 @@ struct rz_line_game {
     if (lane < H) { t.root_rows[(size_t)g * 2 * H + lane] = 0u; t.root_rows[(size_t)g * 2 * H + H + lane] = 0u; }
   }
   static __device__ __forceinline__ int stone_count(const board& b) { return b.stones; }
+  // random playouts: this lane's row of squares a random mover may pick, and the action of (row, col)
+  static __device__ __forceinline__ uint32_t move_candidates(const board& b, const rz_geom& q) {
+    const uint32_t rowmask = (q.W >= 32) ? 0xffffffffu : ((1u << q.W) - 1u);
+    const int lane = rz_lane();
+    return (q.gravity ? lane == q.H - 1 : lane < q.H) ? (~(b.p[0] | b.p[1]) & rowmask) : 0u;
+  }
+  static __device__ __forceinline__ int candidate_action(int row, int col, const rz_geom& q) {
+    return q.gravity ? col : row * q.W + col;
+  }
+  static constexpr bool kHasPass = false;
 };

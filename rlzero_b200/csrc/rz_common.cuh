@@ -147,4 +147,13 @@ __device__ __forceinline__ float rz_u01_24(uint32_t a) {
   return ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
 }
 
+// env.returns() of a finished game (enum rz_returns)
+__device__ __forceinline__ void rz_game_returns(int game_type, int mode, int status, int winner, int& r0, int& r1) {
+  r0 = 0; r1 = 0;
+  if (status != RZ_ENDED_WIN) return;
+  if (game_type == RZ_GAME_GO) { r0 = winner == 0 ? 1 : -1; r1 = -r0; return; }      // go_env.py:142-143
+  if (mode == RZ_RETURNS_REFERENCE) { if (winner == 1) { r0 = 1; r1 = -1; } return; }  // gomoku_env.py:216-219
+  r0 = winner == 0 ? 1 : -1; r1 = -r0;
+}
+
 #endif  // __CUDACC__

@@ -302,6 +302,82 @@ rz_eval_rollout_kernel(rz_tree_desc t, int mode, unsigned long long seed, int n_
   if (lane == 0) value[g] = (winner == -1) ? 0.0f : (winner == b.player ? 1.0f : -1.0f);
 }
 
+// RandomRolloutEvaluator of the DeepMindMCTS driver (rlzero/mcts/deepmind_mcts.py:31-62):
+//   prior     1/len(legal) for every legal action                                  :58-62
+//   evaluate  mean over n_rollouts uniformly random playouts of env.returns()       :43-56
+// returns follow enum rz_returns (the reference's GomokuEnv.returns quirk included).  A playout that
+// is cut by n_limit before the game ends contributes [0,0].  Counter-based RNG keyed by (seed,
+// global game id, root visit count, rollout, ply).
+template <class GM>
+__global__ void __launch_bounds__(RZ_GAME_THREADS)
+rz_eval_rollout_dm_kernel(rz_tree_desc t, int n_rollouts, unsigned long long seed, int n_limit, float* prior,
+                          double* ret64) {
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  if (t.depth[g] < 0) return;
+  const rz_geom q = rz_geom_of(t.game);
+  const int lane = rz_lane(), AS = t.game.action_stride;
+  typename GM::board b0;
+  GM::load_leaf(b0, t, g);
+  {
+    const uint32_t lctx = GM::legal_ctx(b0, q);
+    int n_legal = 0;
+    for (int s0 = 0; s0 < AS; s0 += 32) n_legal += __popc(__ballot_sync(RZ_FULL, GM::slot_legal(lctx, s0 + lane, q)));
+    const float uni = n_legal > 0 ? __fdiv_rn(1.0f, (float)n_legal) : 0.0f;
+    for (int s0 = 0; s0 < AS; s0 += 32) {
+      const int s = s0 + lane;
+      prior[(size_t)g * AS + s] = GM::slot_legal(lctx, s, q) ? uni : 0.0f;
+    }
+  }
+  const uint32_t visit = (uint32_t)t.root_N[g];
+  int sum0 = 0, sum1 = 0;
+  for (int r = 0; r < n_rollouts; ++r) {
+    typename GM::board b = b0;
+    int winner = -1, status = RZ_ACTIVE;
+    for (int i = 0; i <= n_limit; ++i) {
+      status = GM::status(b, q, winner);
+      if (status != RZ_ACTIVE || i == n_limit) break;
+      const uint32_t cand = GM::move_candidates(b, q);
+      const int cnt = __popc(cand);
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(RZ_FULL, inc, o);
+        if (lane >= o) inc += up;
+      }
+      const int n_sq = __shfl_sync(RZ_FULL, inc, 31);
+      const int n_act = n_sq + (GM::kHasPass ? 1 : 0);
+      uint32_t rnd[4];
+      rz_philox4((uint32_t)(t.global_offset + g), visit, ((uint32_t)r << 16) | (uint32_t)i, 0xd311u, seed, rnd);
+      const int pick = (int)(((unsigned long long)rnd[0] * (unsigned long long)n_act) >> 32);
+      int action;
+      if (pick >= n_sq) {
+        action = q.cells;                       // the pass
+      } else {
+        const bool mine = (pick >= inc - cnt) && (pick < inc);
+        const unsigned who = __ballot_sync(RZ_FULL, mine);
+        const int row = __ffs(who) - 1;
+        int col = 0;
+        if (mine) {
+          uint32_t m = cand;
+          for (int j = pick - (inc - cnt); j > 0; --j) m &= m - 1;
+          col = __ffs(m) - 1;
+        }
+        col = __shfl_sync(RZ_FULL, col, row);
+        action = GM::candidate_action(row, col, q);
+      }
+      GM::play(b, action, q);
+    }
+    int r0, r1;
+    rz_game_returns(t.game.game_type, t.returns_mode, status, winner, r0, r1);
+    sum0 += r0; sum1 += r1;
+  }
+  if (lane == 0) {
+    ret64[2 * g] = (double)sum0 / (double)n_rollouts;
+    ret64[2 * g + 1] = (double)sum1 / (double)n_rollouts;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
@@ -419,5 +495,24 @@ extern "C" int rz_eval_closed_form(const rz_tree_desc* t, int eval_id, float* pr
     rz_eval_closed_form_kernel<rz_line_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
                                                (cudaStream_t)stream>>>(*t, eval_id, prior, value);
   RZ_LAUNCH_CHECK("rz_eval_closed_form");
+  return 0;
+}
+
+extern "C" int rz_eval_rollout_dm(const rz_tree_desc* t, int n_rollouts, unsigned long long seed, int n_limit,
+                                  float* prior, double* ret64, void* stream) {
+  RZ_REQUIRE(t && prior && ret64, "rz_eval_rollout_dm: null argument");
+  if (rz_check_game(&t->game)) return -1;
+  RZ_REQUIRE(n_rollouts >= 1, "rz_eval_rollout_dm: n_rollouts %d", n_rollouts);
+  RZ_REQUIRE(n_limit >= 0, "rz_eval_rollout_dm: n_limit %d", n_limit);
+  RZ_REQUIRE(t->root_N && t->depth && t->leaf_rows && t->leaf_meta, "rz_eval_rollout_dm: null tree array");
+  RZ_REQUIRE(t->game.game_type != RZ_GAME_GO || t->leaf_hist, "rz_eval_rollout_dm: Go needs leaf_hist");
+  if (t->n_trees == 0) return 0;
+  if (t->game.game_type == RZ_GAME_GO)
+    rz_eval_rollout_dm_kernel<rz_go_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+                                            (cudaStream_t)stream>>>(*t, n_rollouts, seed, n_limit, prior, ret64);
+  else
+    rz_eval_rollout_dm_kernel<rz_line_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+                                              (cudaStream_t)stream>>>(*t, n_rollouts, seed, n_limit, prior, ret64);
+  RZ_LAUNCH_CHECK("rz_eval_rollout_dm");
   return 0;
 }

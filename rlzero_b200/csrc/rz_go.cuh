@@ -290,4 +290,11 @@ struct rz_go_game {
     }
   }
   static __device__ __forceinline__ int stone_count(const board& b) { return rz_go_count(b.p[0] | b.p[1]); }
+  static __device__ __forceinline__ uint32_t move_candidates(const board& b, const rz_geom& q) {
+    return rz_go_legal_rows(b, q);
+  }
+  static __device__ __forceinline__ int candidate_action(int row, int col, const rz_geom& q) {
+    return row * q.W + col;
+  }
+  static constexpr bool kHasPass = true;      // the pass is one more legal action (go_env.py:193-194)
 };

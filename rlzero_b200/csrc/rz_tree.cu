@@ -48,15 +48,6 @@ __device__ __forceinline__ void rz_warp_argmax(double& s, int& slot, int& n) {
 __device__ __forceinline__ int rz_outcome_enc(int o0, int o1) { return 0x100 | (o0 + 1) | ((o1 + 1) << 2); }
 __device__ __forceinline__ int rz_outcome_of(int code, int player) { return ((code >> (2 * player)) & 3) - 1; }
 
-// env.returns() of a finished game (enum rz_returns)
-__device__ __forceinline__ void rz_game_returns(int game_type, int mode, int status, int winner, int& r0, int& r1) {
-  r0 = 0; r1 = 0;
-  if (status != RZ_ENDED_WIN) return;
-  if (game_type == RZ_GAME_GO) { r0 = winner == 0 ? 1 : -1; r1 = -r0; return; }      // go_env.py:142-143
-  if (mode == RZ_RETURNS_REFERENCE) { if (winner == 1) { r0 = 1; r1 = -1; } return; }  // gomoku_env.py:216-219
-  r0 = winner == 0 ? 1 : -1; r1 = -r0;
-}
-
 // ---------------------------------------------------------------------------
 // K1: select.  One playout descent per tree + leaf terminal test.
 // ---------------------------------------------------------------------------

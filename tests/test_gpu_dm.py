@@ -143,3 +143,70 @@ def test_root_only_noise():
     for node in range(1, d['n_nodes']):
         legal = d['N'][node] >= 0
         assert np.all(d['P'][node][legal] == np.float32(1.0) / np.float32(legal.sum()))   # below: untouched
+
+
+# ------------------------------------------------------------------ the reference-facing classes
+def test_deepmind_mcts_class_with_a_python_evaluator_matches_fixtures():
+    """rlzero_b200.mcts.DeepMindMCTS(env, evaluator=<user Evaluator>) on the GPU GomokuEnv: the root
+    SearchNode view carries the numbers the live reference produced."""
+    from rlzero_b200.games.gomoku import GomokuEnv
+    from rlzero_b200.mcts import DeepMindMCTS
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'dm_mcts.json')) as fh:
+        cases = [c for c in json.load(fh) if c['noise_seed'] is None and c['size'] <= 6][:8]
+    for c in cases:
+        env = GomokuEnv(c['size'], c['k'])
+        env.reset()
+        for a in c['moves']:
+            env.step(a)
+        bot = DeepMindMCTS(env, uct_c=2, max_simulations=c['sims'], evaluator=dm_oracle.ClosedFormEvaluator(c['eval_id']),
+                           child_selection_method=c['method'], solve=c['solve'])
+        root = bot.mcts_search(env)
+        assert root.explore_count == c['root_n'] and root.total_reward == c['root_w'] and root.outcome == c['root_outcome']
+        got = [[ch.action, ch.explore_count, ch.total_reward, ch.outcome] for ch in root.children]
+        assert got == [x[:4] for x in c['children']]
+        assert root.best_child().action == c['best']
+        policy, action = bot.step_with_policy(env)
+        assert action == c['best'] and [a for a, _ in policy] == list(env.legal_actions())
+        assert sum(p for _, p in policy) == 1.0
+
+
+def test_random_rollout_evaluator_on_the_device():
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.games.gomoku import GomokuEnv
+    from rlzero_b200.mcts import DeepMindMCTS, RandomRolloutEvaluator
+    env = GomokuEnv(3, 3)
+    env.reset()
+    for a in [0, 3, 1, 4]:          # player 0 to move, wins at 2; player 1 threatens 5
+        env.step(a)
+    bot = DeepMindMCTS(env, uct_c=2, max_simulations=300, evaluator=RandomRolloutEvaluator(n_rollouts=8, seed=3),
+                       solve=True, returns_mode=L.RETURNS_ZERO_SUM)
+    root = bot.mcts_search(env)
+    kids = {c.action: c for c in root.children}
+    assert sorted(kids) == [2, 5, 6, 7, 8]
+    assert kids[2].outcome == [1, -1] and root.outcome == [1, -1]        # proven win, search stopped early
+    assert root.explore_count < 300
+    assert bot.step(env) == 2
+    for c in root.children:
+        assert abs(c.total_reward) <= c.explore_count
+
+
+def test_mcts_bot_plays_go_like_the_reference_script():
+    """rlzero/games/go/test_mcts_bot.py:9-43: DeepMindMCTS picks moves for black on a Go board,
+    white answers with a random legal move; here on 5x5 to the end of the game."""
+    from rlzero_b200.games.go import GoEnv
+    from rlzero_b200.mcts import DeepMindMCTS, RandomRolloutEvaluator
+    env = GoEnv(board_size=5, komi=0.5)
+    env.seed(1)
+    env.reset()
+    bot = DeepMindMCTS(env, max_simulations=40, evaluator=RandomRolloutEvaluator(n_rollouts=2, n_limit=60, seed=1),
+                       solve=True)
+    for ply in range(60):
+        if env.is_terminal():
+            break
+        if ply % 2 == 0:
+            policy, action = bot.step_with_policy(env)
+            assert action in list(env.legal_actions()) and len(policy) == len(env.legal_actions())
+        else:
+            action = env.random_action()
+        env.step(int(action))
+    assert ply > 4
