@@ -404,6 +404,64 @@ int rz_net_conv3x3_f32(const float* in, const float* weight, const float* bias, 
 int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_tile_bf16, float* logp,
                  float* value, int n_boards, void* stream);
 
+/* ---- MuZero search in latent space (BASELINE.json config 5) ----------------------------------------
+   The reference has no MuZero code: the kernels follow the pseudocode published with the MuZero paper
+   (run_mcts, select_child, ucb_score, expand_node, backpropagate, add_exploration_noise, MinMaxStats) with
+   the two-player value-sign convention; rewards are 0 (board games).  PARITY UNPINNED (oracle/muzero_oracle.py).
+   A node's children live in its edge block as in rz_tree_desc; W is the child's value_sum from the child's own
+   to_play view.  Every simulation expands exactly one node, so node i+1 of every tree is created by simulation
+   i and hidden states are stored node-major: pool[node][tree][S*S][128] bf16. */
+typedef struct rz_mz_desc {
+  int32_t n_trees;               /* G */
+  int32_t n_actions;             /* A: the action space below the root */
+  int32_t action_stride;         /* AS = round_up(A, 32) */
+  int32_t max_nodes;             /* num_simulations + 1 */
+  int32_t max_depth;             /* path capacity (<= max_nodes) */
+  int32_t pbc_table_len;
+  double discount;               /* MuZeroConfig.discount (1 for board games) */
+  double known_min, known_max;   /* MinMaxStats known_bounds; +inf / -inf when unknown */
+  int64_t global_offset;         /* global id of tree 0 (shard-invariant noise) */
+  int32_t* edge_N;               /* [G][max_nodes][AS] visit_count of each child, -1 = no such child */
+  double* edge_W;                /* value_sum */
+  float* edge_P;                 /* prior */
+  int32_t* edge_child;           /* node index once expanded, else -1 */
+  int32_t* n_nodes;              /* [G] */
+  int32_t* root_N;               /* [G] */
+  double* root_W;                /* [G] */
+  double* mm_min;                /* [G] MinMaxStats.minimum */
+  double* mm_max;                /* [G] MinMaxStats.maximum */
+  int32_t* path_node;            /* [G][max_depth] scratch of one simulation */
+  int32_t* path_action;          /* [G][max_depth] */
+  int32_t* depth;                /* [G] length of the search path below the root; -1 = fault */
+  int32_t* leaf_parent;          /* [G] node whose hidden state feeds recurrent_inference */
+  int32_t* leaf_action;          /* [G] history.last_action() */
+  int32_t* fault;                /* [G] sticky bits: 1 = path/pb_c table overflow, 2 = node pool full */
+  const double* pbc_table;       /* pbc_table[n] = log((n + pb_c_base + 1) / pb_c_base) + pb_c_init, HOST libm */
+} rz_mz_desc;
+
+int rz_sizeof_mz_desc(void);
+/* expand_node(root, to_play, legal_actions, initial_inference) + add_exploration_noise: priors =
+   exp(logp) renormalised over the legal actions (legal uint8 [G][A], NULL = all), mixed with
+   Dirichlet(noise_alpha) noise when noise_eps > 0 (counter-based RNG keyed by seed, global tree id and the
+   move counter: move_ids[g] when move_ids != NULL -- a device array, so a captured graph sees fresh counters --
+   else move_id); fresh tree of one node, MinMaxStats reset to the known bounds. */
+int rz_mz_root(const rz_mz_desc* t, const float* logp, const uint8_t* legal, float noise_eps, float noise_alpha,
+               unsigned long long seed, unsigned int move_id, const int32_t* move_ids, void* stream);
+/* the descent of one simulation (select_child until a child that is not expanded): fills path_*, depth,
+   leaf_parent, leaf_action.  ucb_score in float64: pb_c = pbc_table[N] * (sqrt(N) / (n + 1)); score =
+   pb_c * prior + (n > 0 ? normalize(discount * -value_sum / n) : 0); ties go to the HIGHEST action
+   (max over (score, action) tuples). */
+int rz_mz_select(const rz_mz_desc* t, void* stream);
+/* expand_node(leaf, recurrent_inference) + backpropagate: new node n_nodes with priors exp(logp) over the
+   whole action space (logp f32 [G][AS] = log_softmax of the prediction network), value f32 [G] for the
+   player to move at the leaf. */
+int rz_mz_expand_backup(const rz_mz_desc* t, const float* logp, const float* value, void* stream);
+/* input of the dynamics network: stage[g] = pool[parent[g]][g] with channel 127 replaced by the one-hot
+   plane of action[g] (an action >= rows*cols, Go's pass, gives an empty plane).  pool bf16
+   [slots][slot_rows][128] with slot_rows >= n_trees*S*S, stage bf16 [n_trees*S*S][128], S = row_stride. */
+int rz_mz_gather(const void* pool, const int32_t* parent, const int32_t* action, void* stage, int n_trees,
+                 int board_rows, int board_cols, int row_stride, long long slot_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,18 @@ class TrajDesc(C.Structure):
                 ('ring_cursor', _vp), ('games_done', _vp), ('plies_done', _vp)]
 
 
+class MzDesc(C.Structure):
+    """rz_mz_desc: MuZero latent-space trees."""
+    _fields_ = [('n_trees', C.c_int32), ('n_actions', C.c_int32), ('action_stride', C.c_int32),
+                ('max_nodes', C.c_int32), ('max_depth', C.c_int32), ('pbc_table_len', C.c_int32),
+                ('discount', C.c_double), ('known_min', C.c_double), ('known_max', C.c_double),
+                ('global_offset', C.c_int64),
+                ('edge_N', _vp), ('edge_W', _vp), ('edge_P', _vp), ('edge_child', _vp),
+                ('n_nodes', _vp), ('root_N', _vp), ('root_W', _vp), ('mm_min', _vp), ('mm_max', _vp),
+                ('path_node', _vp), ('path_action', _vp), ('depth', _vp), ('leaf_parent', _vp),
+                ('leaf_action', _vp), ('fault', _vp), ('pbc_table', _vp)]
+
+
 class HeadsDesc(C.Structure):
     _fields_ = [('board_size', C.c_int32), ('action_stride', C.c_int32), ('width', C.c_int32),
                 ('n_actions', C.c_int32), ('w1x1', _vp), ('b1x1', _vp), ('wp', _vp), ('bp', _vp),
@@ -100,6 +112,11 @@ SIGNATURES = {
     'rz_gather_rows': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     'rz_eval_rollout': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),
     'rz_eval_rollout_dm': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),
+    'rz_sizeof_mz_desc': (C.c_int, []),
+    'rz_mz_root': (C.c_int, [C.POINTER(MzDesc), _vp, _vp, C.c_float, C.c_float, C.c_ulonglong, C.c_uint, _vp, _vp]),
+    'rz_mz_select': (C.c_int, [C.POINTER(MzDesc), _vp]),
+    'rz_mz_expand_backup': (C.c_int, [C.POINTER(MzDesc), _vp, _vp, _vp]),
+    'rz_mz_gather': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, _vp]),
     'rz_net_conv3x3_tc': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, _vp]),
     'rz_net_conv3x3_tc2': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -146,7 +163,8 @@ def load():
     if lib.rz_abi_version() != ABI_VERSION:
         raise NativeLibraryError('ABI mismatch: library %d, binding %d (rebuild)' % (
             lib.rz_abi_version(), ABI_VERSION))
-    if lib.rz_sizeof_tree_desc() != C.sizeof(TreeDesc) or lib.rz_sizeof_traj_desc() != C.sizeof(TrajDesc):
+    if (lib.rz_sizeof_tree_desc() != C.sizeof(TreeDesc) or lib.rz_sizeof_traj_desc() != C.sizeof(TrajDesc)
+            or lib.rz_sizeof_mz_desc() != C.sizeof(MzDesc)):
         raise NativeLibraryError('descriptor struct size mismatch between header and binding')
     _lib = lib
     return lib
