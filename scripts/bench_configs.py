@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the parity-case configurations of BASELINE.json (NOT the bench line, which is
 config 3 in bench.py): config 1 TicTacToe / 25 sims / stock net, config 2 Connect Four / 200 sims /
-4096 games / ResNet-6, config 4 Go 19x19 / 800 sims / ResNet-20.  One JSON line per configuration."""
+4096 games / ResNet-6, config 4 Go 19x19 / 800 sims / ResNet-20, config 5 MuZero / 50 latent sims.  One JSON line per configuration."""
 import json
 import os
 import sys
@@ -65,6 +65,36 @@ def main():
         sp = BatchedSelfPlay(8192, 19, 1, net=net4, n_playout=800, add_noise=True, seed=3, game_type=L.GAME_GO,
                              komi=7.5, max_moves=722)
         run('config4 Go 19x19 (komi 7.5), 800 sims/move, ResNet-20 bf16, 8192 games', sp, 160, 8, random_moves=31)
+        del sp
+        torch.cuda.empty_cache()
+    if not only or '5' in only:
+        # config 5: MuZero on Gomoku 15x15, 50 simulations/move in latent space, 8192 games: h = stem + 10
+        # blocks on the real position, g = conv + 5 blocks on (hidden state, action plane), f = the heads
+        from rlzero_b200.muzero import BatchedMuZeroSelfPlay, MuZeroConfig, MuZeroNet
+        net5 = MuZeroNet(15, repr_blocks=10, dyn_blocks=5).cuda().eval()
+        G = 8192
+        sp = BatchedMuZeroSelfPlay(G, 15, 5, net=net5, config=MuZeroConfig(num_simulations=50), seed=4)
+        for _ in range(3):
+            sp.play_move()
+        torch.cuda.synchronize()
+        g0, n_moves = sp.games_done, 12
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(n_moves):
+            sp.play_move()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        sp.search.raise_faults()
+        sims = G * 50 * n_moves
+        flops = G * n_moves * (net5.flops('initial') + 50 * net5.flops('recurrent'))
+        print(json.dumps({'config': 'config5 MuZero Gomoku 15x15, 50 latent sims/move, h=ResNet-10 g=ResNet-5 bf16, '
+                                    '%d games' % G, 'games': G, 'n_playout': 50, 'moves': n_moves,
+                          'ms_per_move': ms / n_moves, 'simulations_per_s': sims / ms * 1e3,
+                          'moves_per_s': G * n_moves / ms * 1e3, 'net_tflops': flops / ms / 1e9,
+                          'hbm_gb': sp.search.hbm_bytes() / 1e9, 'kernels_per_move': sp.search.kernels_per_move(),
+                          'games_finished': sp.games_done - g0, 'wall_s': time.time() - t0}), flush=True)
         del sp
         torch.cuda.empty_cache()
     if '4g' in only:
