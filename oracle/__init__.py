@@ -14,8 +14,13 @@ Contents
                  (``rlzero/mcts/node.py``, ``rlzero/mcts/alphazero_mcts.py``,
                  ``rlzero/games/gomoku/gomoku_env.py``,
                  ``rlzero/games/gomoku/game.py``).
-``c/``           (planned) plain-C restatement of the same search for large cases
-                 (``oracle/build_oracle.py``; absent until written).
+``c/``           plain-C restatement of the same search (board, win scan, UCT / PUCT selection,
+                 expansion, sign-flipping backup, tree reuse, closed-form evaluators), OpenMP over
+                 games, for parity at BASELINE size (8192 games x 800 playouts in seconds);
+                 built by ``oracle/build_oracle.py`` into ``oracle/_build/`` (git-ignored).
+``go_oracle``    Go rules (MiniGo / pettingzoo ``go_base`` restated) + the ``GoEnv`` wrapper; PARITY UNPINNED.
+``dm_oracle``    the reference's second search driver ``DeepMindMCTS``, pinned by the live class.
+``muzero_oracle`` the MuZero paper's search pseudocode; PARITY UNPINNED (no reference code).
 ``evaluators``   closed-form evaluators shared by both sides of a parity test.
 
 Pinning: the reference's own tests hold no golden vector for this path

@@ -1,0 +1,97 @@
+"""TEST INFRASTRUCTURE ONLY -- builds oracle/c/rz_oracle.c (the plain-C restatement of the reference
+search) into oracle/_build/librz_oracle.so with gcc, and loads it through ctypes.
+
+    python -m oracle.build_oracle
+
+The shared object is git-ignored and travels to the GPU box with the repository snapshot; building
+the checker is not using it: only tests/ load it."""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'c', 'rz_oracle.c')
+OUT_DIR = os.path.join(HERE, '_build')
+LIB = os.path.join(OUT_DIR, 'librz_oracle.so')
+
+
+def build(force=False):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) > os.path.getmtime(SRC):
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ['gcc', '-O2', '-ffp-contract=off', '-fopenmp', '-shared', '-fPIC', '-o', LIB + '.tmp', SRC, '-lm']
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if out.returncode != 0:
+        raise RuntimeError('gcc failed:\n' + out.stdout.decode())
+    os.replace(LIB + '.tmp', LIB)
+    return LIB
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        lib = C.CDLL(LIB)
+        i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        lib.rzo_search_game.restype = C.c_int
+        lib.rzo_search_game.argtypes = [C.c_int, C.c_int, i32p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                        C.c_int, i32p, i32p, f64p, i32p, f64p]
+        lib.rzo_search_batch.restype = C.c_int
+        lib.rzo_search_batch.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
+                                         C.c_int, C.c_int, i32p, f64p, i32p, f64p]
+        _lib = lib
+    return _lib
+
+
+def search_game(size, k, moves, n_playout, cpuct=5.0, rule=0, eval_id=2, follow=()):
+    """Search a position (after ``moves``), then again after each move of ``follow`` with the subtree
+    kept.  Returns (visits [n,A] int32, W [n,A] float64, root_N [n], root_W [n])."""
+    import numpy as np
+    lib = load()
+    A = size * size
+    n = len(follow) + 1
+    mv = np.ascontiguousarray(np.asarray(list(moves) + [0], dtype=np.int32))
+    fl = np.ascontiguousarray(np.asarray(list(follow) + [0], dtype=np.int32))
+    visits = np.zeros((n, A), dtype=np.int32)
+    w = np.zeros((n, A), dtype=np.float64)
+    rn = np.zeros(n, dtype=np.int32)
+    rw = np.zeros(n, dtype=np.float64)
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    rc = lib.rzo_search_game(size, k, mv.ctypes.data_as(i32p), len(moves), n_playout, float(cpuct), int(rule),
+                             int(eval_id), n, fl.ctypes.data_as(i32p), visits.ctypes.data_as(i32p),
+                             w.ctypes.data_as(f64p), rn.ctypes.data_as(i32p), rw.ctypes.data_as(f64p))
+    if rc:
+        raise RuntimeError('rzo_search_game failed (%d)' % rc)
+    return visits, w, rn, rw
+
+
+def search_batch(size, k, move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2):
+    """One fresh search per game, all host cores.  Returns (visits [G,A], W [G,A], root_N [G], root_W [G])."""
+    import numpy as np
+    lib = load()
+    G, A = len(move_lists), size * size
+    mx = max(1, max((len(m) for m in move_lists), default=0))
+    mv = np.zeros((G, mx), dtype=np.int32)
+    nm = np.zeros(G, dtype=np.int32)
+    for g, m in enumerate(move_lists):
+        mv[g, :len(m)] = m
+        nm[g] = len(m)
+    visits = np.zeros((G, A), dtype=np.int32)
+    w = np.zeros((G, A), dtype=np.float64)
+    rn = np.zeros(G, dtype=np.int32)
+    rw = np.zeros(G, dtype=np.float64)
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    rc = lib.rzo_search_batch(G, size, k, mv.ctypes.data_as(i32p), nm.ctypes.data_as(i32p), mx, n_playout,
+                              float(cpuct), int(rule), int(eval_id), visits.ctypes.data_as(i32p),
+                              w.ctypes.data_as(f64p), rn.ctypes.data_as(i32p), rw.ctypes.data_as(f64p))
+    if rc:
+        raise RuntimeError('rzo_search_batch failed (%d)' % rc)
+    return visits, w, rn, rw
+
+
+if __name__ == '__main__':
+    print(build(force=True))

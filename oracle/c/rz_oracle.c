@@ -1,0 +1,227 @@
+/* TEST INFRASTRUCTURE ONLY -- plain-C restatement of the reference's AlphaZero search on k-in-a-row
+ * boards, for parity checks at sizes the Python oracle cannot finish (8192 games x 800 playouts).
+ *
+ * Follows, function by function (paths under /root/reference):
+ *   board / step / legal list     rlzero/games/gomoku/gomoku_env.py:19-70
+ *   has_a_winner                  rlzero/games/gomoku/gomoku_env.py:116-170
+ *   game_end_winner               rlzero/games/gomoku/gomoku_env.py:196-203
+ *   TreeNode select / uct_value   rlzero/mcts/node.py:32-42,75-88   (PUCT: deepmind_mcts.py:149-151)
+ *   TreeNode expand               rlzero/mcts/node.py:44-73 (no noise)
+ *   update_recursive              rlzero/mcts/node.py:119-144
+ *   _playout / simulate           rlzero/mcts/alphazero_mcts.py:42-94
+ *   update_with_move              rlzero/mcts/alphazero_mcts.py:96-103
+ * with the closed-form evaluators of oracle/evaluators.py as policy_value_fn.  It shares no code with
+ * the CUDA library and none with the Python oracle; tests/test_oracle_c.py pins it against the Python
+ * restatement and the golden vectors generated from the live reference (tests/golden/mcts_kat.json).
+ *
+ * Build: gcc -O2 -ffp-contract=off (no FMA contraction: Python evaluates W/n + c*sqrt(ln(Np)/n) with
+ * separately rounded operations) -fopenmp -shared -fPIC; see oracle/build_oracle.py.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define MAXC 361
+
+typedef struct {
+  int n, k;
+  int8_t cell[MAXC];      /* -1 empty, 0 / 1 */
+  int stones, last_move, to_move;
+} board_t;
+
+typedef struct node_s {
+  struct node_s* parent;
+  struct node_s** child;  /* [A] by action, NULL = no such child; allocated on expand */
+  int expanded;
+  int n;                  /* explore_count */
+  double w;               /* total_reward */
+  double prior;
+} node_t;
+
+/* simple arena so a search frees everything at once */
+typedef struct { char* base; size_t used, cap; } arena_t;
+static void* arena_alloc(arena_t* a, size_t sz) {
+  sz = (sz + 15) & ~(size_t)15;
+  if (a->used + sz > a->cap) {
+    size_t nc = a->cap * 2 + sz;
+    /* chunks are never moved: allocate a new block and chain it through the first bytes */
+    char* nb = (char*)malloc(nc + 16);
+    if (!nb) return NULL;
+    *(char**)nb = a->base;
+    a->base = nb; a->used = 16; a->cap = nc + 16;
+  }
+  void* p = a->base + a->used;
+  a->used += sz;
+  return p;
+}
+static void arena_free(arena_t* a) {
+  char* b = a->base;
+  while (b) { char* nx = *(char**)b; free(b); b = nx; }
+  a->base = NULL;
+}
+static int arena_init(arena_t* a, size_t cap) {
+  a->base = (char*)malloc(cap + 16);
+  if (!a->base) return -1;
+  *(char**)a->base = NULL;
+  a->used = 16; a->cap = cap + 16;
+  return 0;
+}
+
+static void board_reset(board_t* b, int n, int k) {
+  b->n = n; b->k = k;
+  memset(b->cell, -1, sizeof(b->cell));
+  b->stones = 0; b->last_move = -1; b->to_move = 0;
+}
+static void board_step(board_t* b, int a) {
+  b->cell[a] = (int8_t)b->to_move;
+  b->stones += 1; b->last_move = a; b->to_move ^= 1;
+}
+/* gomoku_env.py:116-170: for every stone, the four directions with the reference's edge guards */
+static int board_winner(const board_t* b) {
+  const int n = b->n, k = b->k;
+  if (b->stones < 2 * k - 1) return -1;
+  for (int m = 0; m < n * n; ++m) {
+    const int p = b->cell[m];
+    if (p < 0) continue;
+    const int h = m / n, w = m % n;
+    int ok;
+    if (w <= n - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i] == p; if (ok) return p; }
+    if (h <= n - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i * n] == p; if (ok) return p; }
+    if (w <= n - k && h <= n - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i * (n + 1)] == p; if (ok) return p; }
+    if (w >= k - 1 && h <= n - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i * (n - 1)] == p; if (ok) return p; }
+  }
+  return -1;
+}
+/* game_end_winner: 1 = ended; *winner = player or -1 (tie) */
+static int board_end(const board_t* b, int* winner) {
+  *winner = board_winner(b);
+  if (*winner >= 0) return 1;
+  return b->stones >= b->n * b->n;
+}
+
+/* oracle/evaluators.py */
+static uint32_t board_hash(const board_t* b) {
+  uint32_t h = 0;
+  for (int m = 0; m < b->n * b->n; ++m)
+    if (b->cell[m] >= 0) h += (uint32_t)(m + 1) * (uint32_t)(m + 1) * (3u + 4u * (uint32_t)b->cell[m]);
+  h += 7u * (uint32_t)(b->last_move + 1);
+  return h * 2654435761u;
+}
+static double eval_value(const board_t* b, int eval_id) {
+  if (eval_id == 1) return (double)((17 * b->stones + 31 * (b->last_move + 1)) % 13 - 6) / 8.0;
+  if (eval_id == 2) return (double)((int)((board_hash(b) >> 16) % 129u) - 64) / 64.0;
+  return 0.0;
+}
+static double eval_prior(const board_t* b, int eval_id, int action, int n_legal, uint32_t h) {
+  if (eval_id == 2) return (double)(((uint32_t)action * 29u + (h >> 8)) % 32u + 1u) / 256.0;
+  return (double)(1.0f / (float)n_legal);    /* np.float32(1) / np.float32(len(legal)) */
+}
+
+static double node_score(const node_t* c, double cpuct, int rule) {
+  if (rule == 1)   /* deepmind_mcts.py:149-151 */
+    return (c->n ? c->w / (double)c->n : 0.0) + cpuct * c->prior * sqrt((double)c->parent->n) / (double)(c->n + 1);
+  if (c->parent->n == 0 || c->n == 0) return INFINITY;      /* node.py:76-80 */
+  return c->w / (double)c->n + cpuct * sqrt(log((double)c->parent->n) / (double)c->n);
+}
+
+static int playout(arena_t* ar, node_t* root, board_t b, int A, double cpuct, int rule, int eval_id) {
+  node_t* node = root;
+  while (node->expanded) {
+    int best_a = -1; double best_s = 0.0;
+    for (int a = 0; a < A; ++a) {                 /* children in ascending action order, first maximum */
+      node_t* c = node->child[a];
+      if (!c) continue;
+      const double s = node_score(c, cpuct, rule);
+      if (best_a < 0 || s > best_s) { best_a = a; best_s = s; }
+    }
+    if (best_a < 0) return -2;                    /* ValueError('Node has no children.') */
+    node = node->child[best_a];
+    board_step(&b, best_a);
+  }
+  double v = eval_value(&b, eval_id);             /* evaluated on terminal leaves too (:59) */
+  int winner;
+  if (!board_end(&b, &winner)) {
+    node->child = (node_t**)arena_alloc(ar, sizeof(node_t*) * (size_t)A);
+    if (!node->child) return -1;
+    const uint32_t h = eval_id == 2 ? board_hash(&b) : 0u;
+    const int n_legal = A - b.stones;
+    for (int a = 0; a < A; ++a) {
+      node->child[a] = NULL;
+      if (b.cell[a] >= 0) continue;
+      node_t* c = (node_t*)arena_alloc(ar, sizeof(node_t));
+      if (!c) return -1;
+      c->parent = node; c->child = NULL; c->expanded = 0; c->n = 0; c->w = 0.0;
+      c->prior = eval_prior(&b, eval_id, a, n_legal, h);
+      node->child[a] = c;
+    }
+    node->expanded = 1;
+  } else if (winner < 0) {
+    v = 0.0;
+  } else {
+    v = winner == b.to_move ? 1.0 : -1.0;
+  }
+  v = -v;                                          /* update_recursive(-leaf_value) */
+  for (node_t* p = node; p; p = p->parent) { p->n += 1; p->w += v; v = -v; }
+  return 0;
+}
+
+/* One game: play `moves`, then for each of n_searches: n_playout playouts, report the root children's
+ * visits / value sums, then commit follow[j] (keeping the subtree, update_with_move) if j < n_follow.
+ * visits/w: [n_searches][A]; root_n/root_w: [n_searches].  Returns 0, or <0 on error. */
+int rzo_search_game(int size, int k, const int32_t* moves, int n_moves, int n_playout, double cpuct, int rule,
+                    int eval_id, int n_searches, const int32_t* follow, int32_t* visits, double* w,
+                    int32_t* root_n, double* root_w) {
+  if (size < 1 || size * size > MAXC) return -3;
+  const int A = size * size;
+  board_t b;
+  board_reset(&b, size, k);
+  for (int i = 0; i < n_moves; ++i) {
+    if (moves[i] < 0 || moves[i] >= A || b.cell[moves[i]] >= 0) return -4;
+    board_step(&b, moves[i]);
+  }
+  arena_t ar;
+  if (arena_init(&ar, (size_t)1 << 22)) return -1;
+  node_t* root = (node_t*)arena_alloc(&ar, sizeof(node_t));
+  memset(root, 0, sizeof(*root));
+  root->prior = 1.0;
+  int rc = 0;
+  for (int j = 0; j < n_searches && rc == 0; ++j) {
+    for (int i = 0; i < n_playout && rc == 0; ++i) rc = playout(&ar, root, b, A, cpuct, rule, eval_id);
+    if (rc) break;
+    for (int a = 0; a < A; ++a) {
+      node_t* c = root->expanded ? root->child[a] : NULL;
+      visits[(size_t)j * A + a] = c ? c->n : 0;
+      w[(size_t)j * A + a] = c ? c->w : 0.0;
+    }
+    root_n[j] = root->n; root_w[j] = root->w;
+    if (j + 1 < n_searches) {
+      const int m = follow[j];
+      if (m < 0 || m >= A || b.cell[m] >= 0) { rc = -4; break; }
+      board_step(&b, m);
+      if (root->expanded && root->child[m]) { root = root->child[m]; root->parent = NULL; }
+      else { root = (node_t*)arena_alloc(&ar, sizeof(node_t)); memset(root, 0, sizeof(*root)); root->prior = 1.0; }
+    }
+  }
+  arena_free(&ar);
+  return rc;
+}
+
+/* G independent games in parallel over the host cores (OpenMP): moves [G][max_moves] with n_moves[G]. */
+int rzo_search_batch(int G, int size, int k, const int32_t* moves, const int32_t* n_moves, int max_moves,
+                     int n_playout, double cpuct, int rule, int eval_id, int32_t* visits, double* w,
+                     int32_t* root_n, double* root_w) {
+  const int A = size * size;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int g = 0; g < G; ++g) {
+    const int rc = rzo_search_game(size, k, moves + (size_t)g * max_moves, n_moves[g], n_playout, cpuct, rule,
+                                   eval_id, 1, NULL, visits + (size_t)g * A, w + (size_t)g * A, root_n + g,
+                                   root_w + g);
+    if (rc) {
+#pragma omp atomic write
+      bad = rc;
+    }
+  }
+  return bad;
+}

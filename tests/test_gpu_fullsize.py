@@ -1,6 +1,7 @@
 """Parity at BASELINE.json's full size (config 3: Gomoku 15x15, 8192 games per GPU, ResNet-10 bf16)
-through size-independent properties, plus bit-exact spot checks of individual trees against the
-oracle fed by the same network (batch invariance at batch 8192)."""
+through size-independent properties, bit-exact spot checks of individual trees against the Python
+oracle fed by the same network (batch invariance at batch 8192), and -- with a closed-form evaluator
+on both sides -- bit-exact comparison of ALL 8192 trees after 800 playouts with the plain-C oracle."""
 import numpy as np
 import pytest
 import torch
@@ -94,3 +95,36 @@ def test_full_batch_trees_equal_the_oracle(net):
         assert visits[g].tolist() == s.root_visits(H * H).tolist(), g
         assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(H * H)], g
         assert int(root_n[g]) == s.root.n
+
+
+@pytest.mark.parametrize('rule', [0, 1])
+def test_all_8192_trees_at_800_playouts_equal_the_c_oracle(rule):
+    """BASELINE config-3 size, every tree checked: 8192 games from the bench start positions, 800
+    playouts each, closed-form HASH evaluator on both sides -- visit counts, fp64 value sums and root
+    statistics of ALL trees are bit-identical to the plain-C restatement of the reference search
+    (oracle/c/rz_oracle.c, itself pinned to the live-reference fixtures in tests/test_oracle_c.py)."""
+    from oracle import build_oracle
+    from oracle.evaluators import EVAL_HASH
+    from rlzero_b200.engine import ClosedFormEvaluator, SearchForest
+    n_playout = 800
+    lists = []
+    for g in range(G):
+        rs = np.random.RandomState(1000 + g)
+        lists.append([int(m) for m in rs.permutation(H * H)[:(1000 + g) % 31]])
+    f = SearchForest(G, H, K, n_playout=n_playout, c_puct=5.0, rule=rule, max_carry=0)
+    f.set_positions(lists)
+    meta = f.boards()[1]
+    from rlzero_b200 import _lib as L
+    live = meta[:, L.META_STATUS] == L.ACTIVE          # a random start may already be decided: skipped by both
+    f.search(ClosedFormEvaluator(EVAL_HASH))
+    torch.cuda.synchronize()
+    f.raise_faults()
+    visits, w, has, root_n, root_w = f.root_stats()
+    cv, cw, crn, crw = build_oracle.search_batch(H, K, lists, n_playout, 5.0, rule, EVAL_HASH)
+    assert live.sum() > G - 64
+    assert np.array_equal(visits[live], cv[live])
+    assert np.array_equal(w[live].view(np.int64), cw[live].view(np.int64))        # bit patterns of the fp64 sums
+    assert np.array_equal(root_n[live], crn[live])
+    # the root's own sum: the engine keeps the reference's sign convention (root gets -v of the leaf chain)
+    assert np.array_equal(root_w[live].view(np.int64), crw[live].view(np.int64))
+    assert (visits[live].sum(1) == n_playout - 1).all()

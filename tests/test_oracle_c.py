@@ -1,0 +1,54 @@
+"""The plain-C oracle (oracle/c/rz_oracle.c, built by oracle/build_oracle.py) against the golden vectors the
+LIVE reference produced (tests/golden/mcts_kat.json: KAT A-F of SURVEY.md section 4 and more, UCT and PUCT, tree
+reuse, terminal leaves, ties) and against the Python restatement on random positions.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import build_oracle, pyoracle
+from oracle.evaluators import make_policy_value_fn
+
+
+def test_c_oracle_matches_live_reference_fixtures(golden_dir):
+    with open(os.path.join(golden_dir, 'mcts_kat.json')) as f:
+        cases = json.load(f)['cases']
+    assert len(cases) >= 16
+    for c in cases:
+        rule = 1 if c['rule'] == 'puct' else 0
+        visits, w, rn, rw = build_oracle.search_game(c['board_size'], c['n_in_row'], c['pre_moves'], c['n_playout'],
+                                                     c['c_puct'], rule, c['eval_id'], follow=c['chain'])
+        assert len(c['stages']) == len(c['chain']) + 1
+        for j, st in enumerate(c['stages']):
+            assert visits[j].tolist() == st['visits'], (c['name'], j)
+            assert [float(x).hex() for x in w[j]] == [float.fromhex(x).hex() for x in st['W']], (c['name'], j)
+            assert int(rn[j]) == st['root_N'] and float(rw[j]).hex() == float.fromhex(st['root_W']).hex()
+
+
+@pytest.mark.parametrize('size,k,n_playout,rule,eval_id,cpuct', [(3, 3, 150, 0, 2, 5.0), (4, 3, 200, 1, 2, 2.0),
+                                                                 (6, 4, 250, 0, 1, 5.0), (8, 5, 300, 1, 2, 5.0),
+                                                                 (5, 4, 120, 0, 0, 5.0)])
+def test_c_oracle_matches_python_restatement_on_random_positions(size, k, n_playout, rule, eval_id, cpuct):
+    rs = np.random.RandomState(size * 7 + n_playout)
+    lists, boards = [], []
+    while len(lists) < 10:
+        b = pyoracle.Board(size, k)
+        b.reset()
+        mv = [int(x) for x in rs.permutation(size * size)[:rs.randint(0, size * size - 1)]]
+        ok = True
+        for a in mv:
+            b.step(a)
+            if b.game_end_winner()[0]:
+                ok = False
+                break
+        if ok:
+            lists.append(mv)
+            boards.append(b)
+    visits, w, rn, rw = build_oracle.search_batch(size, k, lists, n_playout, cpuct, rule, eval_id)
+    for g, b in enumerate(boards):
+        s = pyoracle.Search(make_policy_value_fn(eval_id), n_playout, cpuct, rule=rule)
+        s.simulate(b, 1.0)
+        assert visits[g].tolist() == s.root_visits(size * size).tolist(), g
+        assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(size * size)], g
+        assert int(rn[g]) == s.root.n and float(rw[g]) == float(s.root.w)
