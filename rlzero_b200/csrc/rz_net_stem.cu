@@ -197,8 +197,9 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 constexpr int GO_PLANES = 17;
 constexpr int GO_OFF_B = 0;               // 3 x [128 cout][64 k] bf16, SW128
 constexpr int GO_OFF_A = 49152;           // 3 x [128 pos][64 k]
-constexpr int GO_OFF_STAGE = 98304;       // 2 x [128 pos][64 cout]
-constexpr int GO_OFF_CTRL = 131072;
+constexpr int GO_OFF_STAGE = GO_OFF_A;    // 2 x [128 pos][64 cout]: the A tile is dead once its MMAs are done, so
+                                          // the output is staged over it (105 KB per CTA -> two CTAs per SM)
+constexpr int GO_OFF_CTRL = 98304;
 constexpr int GO_BOARD_WORDS = 16 * 32 + 4;                 // 16 planes x 32 rows + (player, pad)
 constexpr int GO_STEM_SMEM = GO_OFF_CTRL + 8192 + 1024;
 
@@ -452,7 +453,7 @@ static int go_stem_launch(const rz_game_desc* g, const uint32_t* rows, const uin
   GoStemParams p;
   p.rows = rows; p.hist = hist; p.meta = meta; p.planes = planes; p.bias = bias;
   p.n_tiles = (int)(rows_alloc / 128); p.n_boards = n_boards; p.H = H; p.W = W; p.relu = relu;
-  int ctas = n_ctas > 0 ? n_ctas : 148;
+  int ctas = n_ctas > 0 ? n_ctas : 148 * 2;
   if (ctas > p.n_tiles) ctas = p.n_tiles;
   cudaStream_t st = (cudaStream_t)stream;
   if (S == 16) {
