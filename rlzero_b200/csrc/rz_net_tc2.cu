@@ -38,7 +38,8 @@ constexpr int B_TILE_BYTES = 64 * 128;            // 64 output channels x 64 inp
 constexpr int B_BYTES = 9 * 2 * B_TILE_BYTES;     // 147456
 constexpr int CTRL_OFF = B_BYTES + 2 * A_BUF_BYTES;  // 230400
 constexpr int SMEM_BYTES = CTRL_OFF + 1024;       // 231424 <= 232448
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;                  // producer warp, MMA warp, 8 epilogue warps
+constexpr int EPI_WARPS_HEAD = 4;                 // the fused-heads layer keeps one warp per TMEM lane quarter
 
 struct Conv2Params {
   const float* bias;               // [128]
@@ -63,7 +64,11 @@ struct HeadTaps {
   float* feat;                     // [n_boards][6][256] float32, position index p = y*16 + x
 };
 
-template <int kCG, bool kHead>
+// kDirect: the epilogue writes its output rows straight from registers with 256-bit global stores (one full
+// 32-byte sector per lane and instruction) instead of staging them in the A buffer for a TMA store, so the A
+// buffer goes back to the producer as soon as the tile's MMAs are done: the reload of the next-but-one tile
+// starts one epilogue earlier and has a whole MMA period to land.
+template <int kCG, bool kHead, bool kDirect>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
                       const __grid_constant__ CUtensorMap tmap_w,
@@ -82,8 +87,10 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ctrl_ptr + 72);
   float* s_bias = reinterpret_cast<float*>(ctrl_ptr + 128);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = (kCG == 2) ? rz::cluster_ctarank() : 0u;
+  // warp index and cluster rank through a shuffle: values the compiler can prove warp-uniform, so the
+  // role branches below are uniform and the MMA issuer's operands live in uniform registers
+  const int warp = rz::uniform_i32((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+  const uint32_t rank = (kCG == 2) ? rz::uniform_u32(rz::cluster_ctarank()) : 0u;
   const int half = (kCG == 2) ? (int)rank : (int)(blockIdx.x & 1);   // which 64 output channels live here
   const bool leader = rank == 0;
   const int worker = blockIdx.x >> 1, n_workers = gridDim.x >> 1;
@@ -98,7 +105,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       rz::mbar_init(bar_afull + 8 * b, 1);
       rz::mbar_init(bar_aempty + 8 * b, 1);
       rz::mbar_init(bar_tfull + 8 * b, 1);
-      rz::mbar_init(bar_tempty + 8 * b, 4 * kCG);
+      rz::mbar_init(bar_tempty + 8 * b, (kHead ? EPI_WARPS_HEAD : 8) * kCG);
     }
     rz::fence_barrier_init();
   }
@@ -106,7 +113,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
     if (kCG == 2) { rz::tmem_alloc_pair(rz::smem_u32(tmem_holder), TMEM_COLS); rz::tmem_relinquish_pair(); }
     else          { rz::tmem_alloc(rz::smem_u32(tmem_holder), TMEM_COLS); rz::tmem_relinquish(); }
   }
-  if (threadIdx.x >= 64) s_bias[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+  if (threadIdx.x >= 64 && threadIdx.x < 192) s_bias[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
   rz::tc_fence_before();
   if (kCG == 2) rz::cluster_sync_all(); else __syncthreads();
   rz::tc_fence_after();
@@ -143,9 +150,12 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread of the leader CTA =====
-    if (lane == 0 && leader) {
+    // ===== MMA issuer: the whole warp of the leader CTA runs the loop (converged, uniform operands);
+    // one elected lane issues each tcgen05.mma / commit =====
+    if (leader) {
       constexpr uint32_t idesc = rz::umma_idesc_bf16(kCG == 2 ? 256 : 128, ACC_N);
+      const uint32_t issue = rz::elect_one();
+      const uint32_t tmem_u = rz::uniform_u32(tmem_base);
       rz::mbar_wait(bar_bfull, 0);
       int it = 0;
       for (int item = worker; item < p.n_items; item += n_workers, ++it) {
@@ -154,7 +164,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
         rz::mbar_wait(bar_tempty + 8 * buf, par ^ 1u);
         rz::mbar_wait(bar_afull + 8 * buf, par);
         rz::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_N);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(buf * ACC_N);
         const uint32_t a_buf = a_base + (uint32_t)buf * A_BUF_BYTES;
         uint32_t acc = 0;
 #pragma unroll 1
@@ -167,20 +177,131 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
             const uint64_t bdesc = rz::umma_desc_sw128(b_addr);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              if (kCG == 2) rz::umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
-              else          rz::umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
+              if (kCG == 2) rz::umma_bf16_pair_pred(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc, issue);
+              else          rz::umma_bf16_pred(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc, issue);
               acc = 1;
             }
           }
         }
         // accumulator complete: both CTAs drain their half; the A buffers are recycled by the
         // epilogues (they stage the output tile in them), not here
-        if (kCG == 2) rz::umma_commit_pair(bar_tfull + 8 * buf, 3);
-        else          rz::umma_commit(bar_tfull + 8 * buf);
+        if (kCG == 2) rz::umma_commit_pair_pred(bar_tfull + 8 * buf, 3, issue);
+        else          rz::umma_commit_pred(bar_tfull + 8 * buf, issue);
       }
     }
-  } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4, one output row per thread =====
+  } else if (!kHead) {
+    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4: one output
+    // row x half the channels per thread.  Two warps per scheduler and half the serial work per thread:
+    // with a single warp per quarter the epilogue (TMEM drain, bias/residual/ReLU, bf16 packing, staging)
+    // took longer than the tile's 72 MMAs and set the pace of the kernel (profiles/r1_run24_*).
+    // TMEM -> registers -> (+bias, +residual, ReLU, pad mask, bf16) -> shared-memory staging in the
+    // A buffer the tile's MMAs have just finished with -> TMA store.  The A buffer is handed back
+    // to the producer (a_empty) once the store has read it.
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    constexpr int HALF = ACC_N / 2;                 // columns per thread: 64 (pair) / 32 (single CTA)
+    constexpr int NCHH = HALF / 32;                 // 32-column TMEM chunks per thread
+    const int col0 = ((kCG == 2) ? 0 : half * 64) + hsel * HALF;   // first output channel of this thread
+    int it = 0;
+    for (int item = worker; item < p.n_items; item += n_workers, ++it) {
+      const int buf = it & 1;
+      const int row0 = row_of(item);
+      const int r_in_tile = q * 32 + lane;
+      const size_t row = (size_t)row0 + r_in_tile;
+      const int pos = (int)(row & 255);
+      const bool valid = ((pos & 15) < p.board_w) && ((pos >> 4) < p.board);
+      uint32_t res[NCHH * 2][8];
+      const bool have_res = p.residual != nullptr && valid;
+      if (have_res) {
+        const __nv_bfloat16* rrow = p.residual + row * 128 + col0;
+#pragma unroll
+        for (int j = 0; j < NCHH * 2; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
+      }
+      // the NEXT tile's residual segment of this thread -> L2 now, so that its loads (issued one tile from
+      // now, when the accumulator is usually already waiting) do not pay the DRAM latency in the open
+      if (p.residual != nullptr && item + n_workers < p.n_items)
+        rz::prefetch_l2(p.residual + ((size_t)row_of(item + n_workers) + r_in_tile) * 128 + col0);
+      rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
+      rz::tc_fence_after();
+      if (p.flags & 4) {   // PROBE ONLY (scripts/conv_overhead_probe.py): no epilogue work at all -> MMA-side floor
+        rz::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCG == 2) rz::mbar_arrive_cluster_relaxed(rz::mapa_shared(bar_tempty + 8 * buf, 0));
+          else          rz::mbar_arrive(bar_tempty + 8 * buf);
+          if (warp == 2) rz::mbar_arrive(bar_aempty + 8 * buf);
+        }
+        continue;
+      }
+      if (kDirect && warp == 2 && lane == 0) rz::mbar_arrive(bar_aempty + 8 * buf);   // MMAs done: A tile is dead
+      // all of this thread's accumulator columns in flight at once, one wait
+      uint32_t acc[NCHH][32];
+#pragma unroll
+      for (int ch = 0; ch < NCHH; ++ch)
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_N + hsel * HALF + ch * 32), acc[ch]);
+      rz::tmem_ld_wait();
+      // accumulator drained: the MMA issuer may overwrite it (no memory payload -> relaxed)
+      rz::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kCG == 2) rz::mbar_arrive_cluster_relaxed(rz::mapa_shared(bar_tempty + 8 * buf, 0));
+        else          rz::mbar_arrive(bar_tempty + 8 * buf);
+      }
+      // staging row: k-block (64 columns) `kbs` is a [128 rows][128 B] tile with the 128-byte swizzle of the
+      // absolute shared-memory address, as the TMA store expects; this thread owns 16-byte chunks c0.. of it
+      const int kbs = (hsel * HALF) >> 6;
+      const uint32_t chunk0 = (uint32_t)(((hsel * HALF) & 63) >> 3);
+      const uint32_t srow = a_base + (uint32_t)buf * A_BUF_BYTES + (uint32_t)kbs * (TILE_M * 128u) + (uint32_t)r_in_tile * 128u;
+      const uint32_t sw = (srow >> 7) & 7u;
+      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + col0);
+      uint32_t pair8[8];
+#pragma unroll
+      for (int ch = 0; ch < NCHH; ++ch) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = bias4[ch * 8 + j * 2], b1 = bias4[ch * 8 + j * 2 + 1];
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t packed[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = j * 8 + e * 2;
+            float v0 = __uint_as_float(acc[ch][c]) + bb[e * 2];
+            float v1 = __uint_as_float(acc[ch][c + 1]) + bb[e * 2 + 1];
+            if (have_res) {
+              const uint32_t rw = res[ch * 2 + (j >> 1)][(j & 1) * 4 + e];
+              v0 += __uint_as_float(rw << 16);
+              v1 += __uint_as_float(rw & 0xffff0000u);
+            }
+            packed[e] = p.relu ? rz::pack_bf16x2_relu(v0, v1) : rz::pack_bf16x2(v0, v1);
+            if (!valid) packed[e] = 0u;
+          }
+          if (kDirect) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pair8[(j & 1) * 4 + e] = packed[e];
+            if (j & 1) rz::st_global_v8(p.out + row * 128 + col0 + ch * 32 + (j - 1) * 8, pair8);
+          } else {
+            const uint32_t chunk = chunk0 + (uint32_t)(ch * 4 + j);
+            rz::st_shared_v4(srow + ((chunk ^ sw) << 4), packed[0], packed[1], packed[2], packed[3]);
+          }
+        }
+      }
+      if (kDirect) continue;
+      rz::fence_proxy_async();              // staging writes -> visible to the TMA engine
+      rz::named_bar_sync(1, 256);           // the 8 epilogue warps
+      if (warp == 2 && lane == 0) {
+        const uint32_t stage = a_base + (uint32_t)buf * A_BUF_BYTES;
+        const int cb = (kCG == 2) ? 0 : half * 64;
+#pragma unroll
+        for (int kb = 0; kb < ACC_N / 64; ++kb)
+          rz::tma_store_2d(&tmap_out, stage + (uint32_t)kb * (TILE_M * 128u), cb + kb * 64, row0);
+        rz::tma_store_commit();
+        rz::tma_store_wait_read();
+        rz::mbar_arrive(bar_aempty + 8 * buf);   // this CTA's producer may refill the buffer
+      }
+    }
+    if (warp == 2 && lane == 0) rz::tma_store_wait_all();
+  } else if (warp < 2 + EPI_WARPS_HEAD) {
+    // ===== fused-heads layer: epilogue warps 2..5, TMEM lane quarter = warp % 4, one output row per thread =====
     // TMEM -> registers -> (+bias, +residual, ReLU, pad mask, bf16) -> shared-memory staging in the
     // A buffer the tile's MMAs have just finished with -> TMA store.  The A buffer is handed back
     // to the producer (a_empty) once the store has read it.
@@ -291,12 +412,12 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
   }
 }
 
-template <int kCG, bool kHead>
+template <int kCG, bool kHead, bool kDirect>
 int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const Conv2Params& p,
            const HeadTaps& head, int ctas, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rz_conv3x3_tc2_kernel<kCG, kHead>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(rz_conv3x3_tc2_kernel<kCG, kHead, kDirect>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc2: smem attribute: %s", cudaGetErrorString(e)); return -2; }
     attr_set = true;
   }
@@ -312,7 +433,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, rz_conv3x3_tc2_kernel<kCG, kHead>, ta, tw, to, p, head);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, rz_conv3x3_tc2_kernel<kCG, kHead, kDirect>, ta, tw, to, p, head);
   if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc2: launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
 }
@@ -356,10 +477,11 @@ static int conv2_entry(const void* act_in, const void* weight, const float* bias
     for (int i = 0; i < 6 * 128; ++i) head.w[i] = w1x1_host[i];
     for (int i = 0; i < 6; ++i) head.b[i] = b1x1_host[i];
     head.feat = feat;
-    return launch<2, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream);
+    return launch<2, true, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream);
   }
-  return cta_group == 2 ? launch<2, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream)
-                        : launch<1, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream);
+  if (cta_group == 2 && (flags & 2)) return launch<2, false, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream);
+  return cta_group == 2 ? launch<2, false, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream)
+                        : launch<1, false, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, (cudaStream_t)stream);
 }
 
 extern "C" int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias,

@@ -181,6 +181,10 @@ class NativeForward(object):
         self.fused_stem = bool(fused_stem)  # encoder + first conv in one kernel (rz_net_stem.cu)
         # 3: rz_net_tc3.cu (any row stride; forced for 19x19); 2: rz_net_tc2.cu (stride 16); 1: rz_net_tc.cu
         self.conv_rev = int(conv_rev)
+        # rz_net_conv3x3_tc2 flags: bit 1 = direct-store epilogue, the default (853 k vs 840 k sims/s sustained on
+        # one box, profiles/r1_run24_bench_ab.log; bit-identical tensors); RZ_CONV_FLAGS=0 selects the staged TMA store
+        import os
+        self.conv_flags = int(os.environ.get('RZ_CONV_FLAGS', '2'))
         self.max_batch = 0
         self.refresh_weights()
         self._alloc(max_batch)
@@ -311,7 +315,7 @@ class NativeForward(object):
                 elif self.conv_rev >= 2:
                     L.check(lib.rz_net_conv3x3_tc2(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
                                                    L.ptr(outs[dst]), n, self.H, self.W, l['cin'],
-                                                   int(l['relu']), 2, 0, self.n_ctas, s), 'rz_net_conv3x3_tc2')
+                                                   int(l['relu']), 2, self.conv_flags, self.n_ctas, s), 'rz_net_conv3x3_tc2')
                 else:
                     L.check(lib.rz_net_conv3x3_tc(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
                                                   L.ptr(outs[dst]), n, self.H, l['cin'], int(l['relu']),

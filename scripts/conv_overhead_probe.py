@@ -18,6 +18,7 @@ def main():
     torch.manual_seed(0)
     w = (torch.randn(9, 128, 128, device='cuda') * 0.03).to(torch.bfloat16).contiguous()
     b = torch.zeros(128, device='cuda')
+    flags = (4 if 'noepilogue' in sys.argv else 0) | (2 if 'direct' in sys.argv else 0)
     pts = []
     for rounds in (4, 8, 16, 32, 64, 110):
         B = 74 * rounds
@@ -27,7 +28,7 @@ def main():
         for res in (None, r):
             def run():
                 L.check(lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(res) if res is not None else None,
-                                               L.ptr(y), B, 15, 15, 128, 1, 2, 0, 0, L.stream_ptr()))
+                                               L.ptr(y), B, 15, 15, 128, 1, 2, flags, 0, L.stream_ptr()))
             for _ in range(5):
                 run()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
