@@ -33,7 +33,7 @@ constexpr int TILE_M = 128;
 constexpr int B_TILE_BYTES = 64 * 128;            // 64 output channels x 64 input channels
 constexpr int B_BYTES = 9 * 2 * B_TILE_BYTES;     // 147456
 constexpr int STAGE_BYTES = TILE_M * 128;         // 128 rows x 64 channels bf16
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;    // producer warp, MMA warp, 8 epilogue warps (4 in the fused-heads layer)
 constexpr int N_SLOTS = 3;
 
 template <int kS>
@@ -51,6 +51,7 @@ struct Geo {
 struct Conv3Params {
   const float* bias;               // [128]
   const __nv_bfloat16* residual;   // [rows][128] or null
+  void* out;                       // [rows][128] bf16 (null in the fused-heads layer)
   int n_items;                     // pairs of 128-row tiles
   int total_rows;                  // n_boards * P (rows beyond it are padding)
   int H, W;
@@ -82,8 +83,10 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ctrl_ptr + 88);
   float* s_bias = reinterpret_cast<float*>(ctrl_ptr + 128);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = rz::cluster_ctarank();
+  // warp index / cluster rank through a shuffle: provably warp-uniform, so the role branches are uniform and
+  // the MMA issuer's operands live in uniform registers (see rz_tc.cuh, "warp-converged issue")
+  const int warp = rz::uniform_i32((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+  const uint32_t rank = rz::uniform_u32(rz::cluster_ctarank());
   const bool leader = rank == 0;
   const int worker = blockIdx.x >> 1, n_workers = gridDim.x >> 1;
 
@@ -99,12 +102,12 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
     }
     for (int b = 0; b < 2; ++b) {
       rz::mbar_init(bar_tfull + 8 * b, 1);
-      rz::mbar_init(bar_tempty + 8 * b, 8);     // 4 epilogue warps of each CTA
+      rz::mbar_init(bar_tempty + 8 * b, kHead ? 8 : 16);     // 4 / 8 epilogue warps of each CTA
     }
     rz::fence_barrier_init();
   }
   if (warp == 1) { rz::tmem_alloc_pair(rz::smem_u32(tmem_holder), 256); rz::tmem_relinquish_pair(); }
-  if (threadIdx.x >= 64) s_bias[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
+  if (threadIdx.x >= 64 && threadIdx.x < 192) s_bias[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
   rz::tc_fence_before();
   rz::cluster_sync_all();
   rz::tc_fence_after();
@@ -132,15 +135,17 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: one thread of the leader CTA =====
-    if (lane == 0 && leader) {
+    // ===== MMA issuer: the whole warp of the leader CTA runs the loop converged; one elected lane issues =====
+    if (leader) {
       constexpr uint32_t idesc = rz::umma_idesc_bf16(256, 128);
+      const uint32_t issue = rz::elect_one();
+      const uint32_t tmem_u = rz::uniform_u32(tmem_base);
       rz::mbar_wait(bar_bfull, 0);
       int it = 0, u = 0;
       for (int item = worker; item < p.n_items; item += n_workers, ++it) {
         const int buf = it & 1;
         rz::mbar_wait(bar_tempty + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(buf * 128);
         uint32_t acc = 0;
         for (int kb = 0; kb < 2; ++kb, ++u) {
           const int slot = u % N_SLOTS;
@@ -154,17 +159,76 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
             const uint64_t bdesc = rz::umma_desc_sw128(smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              rz::umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
+              rz::umma_bf16_pair_pred(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc, issue);
               acc = 1;
             }
           }
-          rz::umma_commit_pair(bar_aempty + 8 * slot, 3);   // both CTAs may refill this ring slot
+          rz::umma_commit_pair_pred(bar_aempty + 8 * slot, 3, issue);   // both CTAs may refill this ring slot
         }
-        rz::umma_commit_pair(bar_tfull + 8 * buf, 3);       // accumulator complete in both CTAs
+        rz::umma_commit_pair_pred(bar_tfull + 8 * buf, 3, issue);       // accumulator complete in both CTAs
       }
     }
-  } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4, one output row per thread =====
+  } else if (!kHead) {
+    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; one output row x
+    // 64 channels per thread, written with 256-bit global stores straight from registers (rz_net_tc2.cu) =====
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int col0 = hsel * 64;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    int it = 0;
+    for (int item = worker; item < p.n_items; item += n_workers, ++it) {
+      const int buf = it & 1;
+      const int row0 = item * 256 + (int)rank * TILE_M;
+      const int r_in_tile = q * 32 + lane;
+      const int row = row0 + r_in_tile;
+      const int board = row / G::P, pos = row - board * G::P;
+      const int y = pos / kS, x = pos - y * kS;
+      const bool valid = row < p.total_rows && x < p.W && y < p.H;
+      uint32_t res[4][8];
+      const bool have_res = p.residual != nullptr && valid;
+      if (have_res) {
+        const __nv_bfloat16* rrow = p.residual + (size_t)row * 128 + col0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
+      }
+      rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
+      rz::tc_fence_after();
+      uint32_t acc[2][32];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch)
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + col0 + ch * 32), acc[ch]);
+      rz::tmem_ld_wait();
+      rz::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) rz::mbar_arrive_cluster_relaxed(rz::mapa_shared(bar_tempty + 8 * buf, 0));
+      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + col0);
+      uint32_t pair8[8];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = bias4[ch * 8 + j * 2], b1 = bias4[ch * 8 + j * 2 + 1];
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = j * 8 + e * 2;
+            float v0 = __uint_as_float(acc[ch][c]) + bb[e * 2];
+            float v1 = __uint_as_float(acc[ch][c + 1]) + bb[e * 2 + 1];
+            if (have_res) {
+              const uint32_t rw = res[ch * 2 + (j >> 1)][(j & 1) * 4 + e];
+              v0 += __uint_as_float(rw << 16);
+              v1 += __uint_as_float(rw & 0xffff0000u);
+            }
+            uint32_t pk = p.relu ? rz::pack_bf16x2_relu(v0, v1) : rz::pack_bf16x2(v0, v1);
+            if (!valid) pk = 0u;
+            pair8[(j & 1) * 4 + e] = pk;
+          }
+          if (j & 1) rz::st_global_v8(out + (size_t)row * 128 + col0 + ch * 32 + (j - 1) * 8, pair8);
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== fused-heads layer: epilogue warps 2..5, TMEM lane quarter = warp % 4, one output row per thread =====
     const int q = warp & 3;
     int it = 0;
     bool store_pending = false;
@@ -312,6 +376,7 @@ static int conv3_entry(const void* act_in, const void* weight, const float* bias
   Conv3Params p;
   p.bias = bias;
   p.residual = (const __nv_bfloat16*)residual;
+  p.out = act_out;
   p.n_items = (int)(rows_alloc / 256);
   p.total_rows = (int)total;
   p.H = board_rows;
