@@ -205,7 +205,7 @@ def run_b200(args):
             if i == 3:
                 k0.record()
             L.check(lib.rz_net_conv3x3_tc2(L.ptr(x), L.ptr(layer['w']), L.ptr(layer['b']), None, L.ptr(y), G,
-                                           BOARD, BOARD, 128, 1, 2, 0, 0, L.stream_ptr()))
+                                           BOARD, BOARD, 128, 1, 2, getattr(ev, 'conv_flags', 0), 0, L.stream_ptr()))
         k1.record()
         torch.cuda.synchronize()
         return k0.elapsed_time(k1) / reps
@@ -268,7 +268,7 @@ def run_b200(args):
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'conv3x3_tc_traffic.json')))['dram_bytes_per_launch']
         except Exception:
             pass
-        roof = {'bound': 'tensor', 'kernel': 'rz_conv3x3_tc2_kernel<2> (128->128, %d boards)' % G,
+        roof = {'bound': 'tensor', 'kernel': 'rz_conv3x3_tc2_kernel<2> (128->128, %d boards, flags %d)' % (G, getattr(ev, 'conv_flags', 0)),
                 'achieved': flops / conv_ms / 1e9, 'peak': peak, 'unit': 'TFLOP/s',
                 'frac': flops / conv_ms / 1e9 / peak,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst, of measured)' if peaks else 'fallback 1590',

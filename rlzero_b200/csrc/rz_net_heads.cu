@@ -83,11 +83,14 @@ __device__ __forceinline__ void rz_ld_global_nc_v8(const void* p, uint32_t (&r)[
                : "l"(p));
 }
 
-// 6 dot products of one position's 128 channels with the 1x1 filters in shared memory
+// 6 dot products of one position's 128 channels with the 1x1 filters in shared memory.  Summation order
+// (shared with the fused epilogue of rz_net_tc2.cu, which splits a row over two warps): channels 0..63
+// ascending onto the bias, channels 64..127 ascending onto zero, then the two partial sums are added.
 template <bool kTile>
 __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos, int W, int HW, int S, int P,
                                                  const float* __restrict__ s_w, float (&acc)[6]) {
   const float4* w4 = reinterpret_cast<const float4*>(s_w);
+  float hi[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   if constexpr (kTile) {
     const int y = pos / W, x = pos - y * W;
     const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(act) + ((size_t)b * P + y * S + x) * HEAD_C;
@@ -106,10 +109,10 @@ __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos
 #pragma unroll
       for (int f = 0; f < 6; ++f) {
         const float4 wa = w4[f * (HEAD_C / 4) + j * 2], wb = w4[f * (HEAD_C / 4) + j * 2 + 1];
-        float a = acc[f];
+        float a = j < 8 ? acc[f] : hi[f];
         a = fmaf(v[0], wa.x, a); a = fmaf(v[1], wa.y, a); a = fmaf(v[2], wa.z, a); a = fmaf(v[3], wa.w, a);
         a = fmaf(v[4], wb.x, a); a = fmaf(v[5], wb.y, a); a = fmaf(v[6], wb.z, a); a = fmaf(v[7], wb.w, a);
-        acc[f] = a;
+        if (j < 8) acc[f] = a; else hi[f] = a;
       }
     }
   } else {
@@ -121,12 +124,14 @@ __device__ __forceinline__ void conv1x1_position(const void* act, int b, int pos
 #pragma unroll
       for (int f = 0; f < 6; ++f) {
         const float4 w = w4[f * (HEAD_C / 4) + j];
-        float a = acc[f];
+        float a = j < HEAD_C / 8 ? acc[f] : hi[f];
         a = fmaf(q.x, w.x, a); a = fmaf(q.y, w.y, a); a = fmaf(q.z, w.z, a); a = fmaf(q.w, w.w, a);
-        acc[f] = a;
+        if (j < HEAD_C / 8) acc[f] = a; else hi[f] = a;
       }
     }
   }
+#pragma unroll
+  for (int f = 0; f < 6; ++f) acc[f] += hi[f];
 }
 
 // feature (k, board bi) lives at s_f[k*NB + (((bi >> 2) ^ (k & 3)) << 2) + (bi & 3)]: the XOR keeps

@@ -39,7 +39,7 @@ constexpr int B_BYTES = 9 * 2 * B_TILE_BYTES;     // 147456
 constexpr int CTRL_OFF = B_BYTES + 2 * A_BUF_BYTES;  // 230400
 constexpr int SMEM_BYTES = CTRL_OFF + 1024;       // 231424 <= 232448
 constexpr int NUM_THREADS = 320;                  // producer warp, MMA warp, 8 epilogue warps
-constexpr int EPI_WARPS_HEAD = 4;                 // the fused-heads layer keeps one warp per TMEM lane quarter
+
 
 struct Conv2Params {
   const float* bias;               // [128]
@@ -103,9 +103,9 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
     rz::mbar_init(bar_bfull, 1);
     for (int b = 0; b < 2; ++b) {
       rz::mbar_init(bar_afull + 8 * b, 1);
-      rz::mbar_init(bar_aempty + 8 * b, 1);
+      rz::mbar_init(bar_aempty + 8 * b, kHead ? 4 : 1);   // fused-heads layer: the 4 warps that read the scratch
       rz::mbar_init(bar_tfull + 8 * b, 1);
-      rz::mbar_init(bar_tempty + 8 * b, (kHead ? EPI_WARPS_HEAD : 8) * kCG);
+      rz::mbar_init(bar_tempty + 8 * b, 8 * kCG);
     }
     rz::fence_barrier_init();
   }
@@ -300,14 +300,15 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       }
     }
     if (warp == 2 && lane == 0) rz::tma_store_wait_all();
-  } else if (warp < 2 + EPI_WARPS_HEAD) {
-    // ===== fused-heads layer: epilogue warps 2..5, TMEM lane quarter = warp % 4, one output row per thread =====
-    // TMEM -> registers -> (+bias, +residual, ReLU, pad mask, bf16) -> shared-memory staging in the
-    // A buffer the tile's MMAs have just finished with -> TMA store.  The A buffer is handed back
-    // to the producer (a_empty) once the store has read it.
+  } else {
+    // ===== fused-heads layer (kHead): the same 8 epilogue warps; every thread turns its 64 channels of a row
+    // into bf16 activations (never stored) and 6 partial dot products with the heads' 1x1 filters; the warp
+    // holding channels 64..127 hands its partial sums to its partner through the tile's A buffer (dead once the
+    // MMAs are done), which adds them, applies ReLU and writes the 6 features.  Summation order = that of
+    // rz_net_heads.cu's conv1x1_position, so the fused and the separate path agree bit for bit. =====
     const int q = warp & 3;
-    const int col_base = (kCG == 2) ? 0 : half * 64;
-    constexpr int NCH = ACC_N / 32;
+    const int hsel = (warp - 2) >> 2;
+    const int col0 = hsel * 64;
     int it = 0;
     for (int item = worker; item < p.n_items; item += n_workers, ++it) {
       const int buf = it & 1;
@@ -316,91 +317,72 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       const size_t row = (size_t)row0 + r_in_tile;
       const int pos = (int)(row & 255);
       const bool valid = ((pos & 15) < p.board_w) && ((pos >> 4) < p.board);
-      // residual row: issued before the accumulator is ready, so its latency hides behind the MMAs
-      // (256-bit loads: each lane fetches whole 32-byte sectors of its row, no sector is read twice)
-      uint32_t res[NCH * 2][8];
+      uint32_t res[4][8];
       const bool have_res = p.residual != nullptr && valid;
       if (have_res) {
-        const __nv_bfloat16* rrow = p.residual + row * 128 + col_base;
+        const __nv_bfloat16* rrow = p.residual + row * 128 + col0;
 #pragma unroll
-        for (int j = 0; j < NCH * 2; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
+        for (int j = 0; j < 4; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
       }
       rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
       rz::tc_fence_after();
-      // kHead: nothing is staged, so the A buffer is free as soon as the tile's MMAs are done
-      if (kHead && warp == 2 && lane == 0) rz::mbar_arrive(bar_aempty + 8 * buf);
+      uint32_t acc[2][32];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch)
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_N + col0 + ch * 32), acc[ch]);
+      rz::tmem_ld_wait();
+      rz::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) rz::mbar_arrive_cluster_relaxed(rz::mapa_shared(bar_tempty + 8 * buf, 0));
       float hacc[6];
 #pragma unroll
-      for (int f = 0; f < 6; ++f) hacc[f] = kHead ? head.b[f] : 0.0f;
-      const uint32_t stage_row = a_base + (uint32_t)buf * A_BUF_BYTES + (uint32_t)r_in_tile * 128u;
+      for (int f = 0; f < 6; ++f) hacc[f] = hsel == 0 ? head.b[f] : 0.0f;
+      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + col0);
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        uint32_t acc[32];
-        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_N + ch * 32), acc);
-        rz::tmem_ld_wait();
-        if (ch == NCH - 1) {
-          // accumulator drained: the MMA issuer may overwrite it (no memory payload -> relaxed)
-          rz::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (kCG == 2) rz::mbar_arrive_cluster_relaxed(rz::mapa_shared(bar_tempty + 8 * buf, 0));
-            else          rz::mbar_arrive(bar_tempty + 8 * buf);
-          }
-        }
-        // staging: k-block (64 columns) `ch / 2` is a [128 rows][128 B] tile with the 128-byte
-        // swizzle of the absolute shared-memory address, as the TMA store expects
-        const uint32_t srow = stage_row + (uint32_t)(ch >> 1) * (TILE_M * 128u);
+      for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t packed[4];
+          const float4 b0 = bias4[ch * 8 + j * 2], b1 = bias4[ch * 8 + j * 2 + 1];
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = j * 8 + e * 2;
-            float v0 = __uint_as_float(acc[c]) + s_bias[col_base + ch * 32 + c];
-            float v1 = __uint_as_float(acc[c + 1]) + s_bias[col_base + ch * 32 + c + 1];
+            float v0 = __uint_as_float(acc[ch][c]) + bb[e * 2];
+            float v1 = __uint_as_float(acc[ch][c + 1]) + bb[e * 2 + 1];
             if (have_res) {
               const uint32_t rw = res[ch * 2 + (j >> 1)][(j & 1) * 4 + e];
               v0 += __uint_as_float(rw << 16);
               v1 += __uint_as_float(rw & 0xffff0000u);
             }
-            if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
-            if (!valid) { v0 = 0.0f; v1 = 0.0f; }
-            const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
-            packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
-            if (kHead) {
-              // on the bf16-rounded activations, channels in ascending order: the same arithmetic
-              // as a separate heads kernel reading the stored trunk output
-              const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xffff0000u);
+            uint32_t pk = p.relu ? rz::pack_bf16x2_relu(v0, v1) : rz::pack_bf16x2(v0, v1);
+            if (!valid) pk = 0u;
+            // on the bf16-rounded activations, channels in ascending order
+            const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+            const int cc = ch * 32 + c;                 // channel within this thread's half
 #pragma unroll
-              for (int f = 0; f < 6; ++f)
-                hacc[f] = fmaf(r1, head.w[f * 128 + ch * 32 + c + 1], fmaf(r0, head.w[f * 128 + ch * 32 + c], hacc[f]));
+            for (int f = 0; f < 6; ++f) {
+              hacc[f] = fmaf(r1, head.w[f * 128 + col0 + cc + 1], fmaf(r0, head.w[f * 128 + col0 + cc], hacc[f]));
             }
-          }
-          if (!kHead) {
-            const uint32_t chunk = (uint32_t)((ch & 1) * 4 + j);
-            rz::st_shared_v4(srow + ((chunk ^ ((srow >> 7) & 7u)) << 4), packed[0], packed[1], packed[2], packed[3]);
           }
         }
       }
-      if (kHead) {
+      // partial sums of channels 64..127 -> scratch rows of 8 floats in the (dead) A buffer of this tile
+      float* scratch = reinterpret_cast<float*>(smem_raw + B_BYTES + buf * A_BUF_BYTES) + r_in_tile * 8;
+      if (hsel == 1) {
+#pragma unroll
+        for (int f = 0; f < 6; ++f) scratch[f] = hacc[f];
+      }
+      rz::named_bar_sync(1, 256);
+      if (hsel == 0) {
         float* fo = head.feat + (size_t)(row >> 8) * (6 * 256) + pos;
 #pragma unroll
-        for (int f = 0; f < 6; ++f) fo[f * 256] = fmaxf(hacc[f], 0.0f);
-        continue;
-      }
-      rz::fence_proxy_async();              // staging writes -> visible to the TMA engine
-      rz::named_bar_sync(1, 128);           // the 4 epilogue warps
-      if (warp == 2 && lane == 0) {
-        const uint32_t stage = a_base + (uint32_t)buf * A_BUF_BYTES;
-#pragma unroll
-        for (int kb = 0; kb < ACC_N / 64; ++kb)
-          rz::tma_store_2d(&tmap_out, stage + (uint32_t)kb * (TILE_M * 128u), col_base + kb * 64, row0);
-        rz::tma_store_commit();
-        rz::tma_store_wait_read();
-        rz::mbar_arrive(bar_aempty + 8 * buf);   // this CTA's producer may refill the buffer
+        for (int f = 0; f < 6; ++f) fo[f * 256] = fmaxf(hacc[f] + scratch[f], 0.0f);
+        // the scratch has been read: the A buffer may be refilled (generic -> async proxy hand-over)
+        rz::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) rz::mbar_arrive(bar_aempty + 8 * buf);
       }
     }
-    if (warp == 2 && lane == 0) rz::tma_store_wait_all();
   }
 
   rz::tc_fence_before();

@@ -250,9 +250,10 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
       }
       rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
       rz::tc_fence_after();
-      float hacc[6];
+      // summation order of rz_net_heads.cu's conv1x1_position: channels 0..63 onto the bias, 64..127 onto zero
+      float hacc[6], hacc_hi[6];
 #pragma unroll
-      for (int f = 0; f < 6; ++f) hacc[f] = kHead ? head.b[f] : 0.0f;
+      for (int f = 0; f < 6; ++f) { hacc[f] = kHead ? head.b[f] : 0.0f; hacc_hi[f] = 0.0f; }
       const uint32_t srow = stage + (uint32_t)r_in_tile * 128u;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -289,8 +290,11 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
             if (kHead) {
               const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xffff0000u);
 #pragma unroll
-              for (int f = 0; f < 6; ++f)
-                hacc[f] = fmaf(r1, head.w[f * 128 + ch * 32 + c + 1], fmaf(r0, head.w[f * 128 + ch * 32 + c], hacc[f]));
+              for (int f = 0; f < 6; ++f) {
+                const float a0 = ch < 2 ? hacc[f] : hacc_hi[f];
+                const float a1 = fmaf(r1, head.w[f * 128 + ch * 32 + c + 1], fmaf(r0, head.w[f * 128 + ch * 32 + c], a0));
+                if (ch < 2) hacc[f] = a1; else hacc_hi[f] = a1;
+              }
             }
           }
           if (!kHead) {
@@ -311,7 +315,7 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
       if (kHead && in_tensor) {
         float* fo = head.feat + (size_t)board * (6 * G::P) + pos;
 #pragma unroll
-        for (int f = 0; f < 6; ++f) fo[f * G::P] = fmaxf(hacc[f], 0.0f);
+        for (int f = 0; f < 6; ++f) fo[f * G::P] = fmaxf(hacc[f] + hacc_hi[f], 0.0f);
       }
     }
     if (warp == 2 && lane == 0 && store_pending) rz::tma_store_wait_all();

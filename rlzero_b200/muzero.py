@@ -172,7 +172,7 @@ class MuZeroNative(object):
         s = L.stream_ptr()
         if self.S == 16:
             L.check(self.lib.rz_net_conv3x3_tc2(L.ptr(inp), L.ptr(layer['w']), L.ptr(layer['b']), L.ptr(res),
-                                                L.ptr(out), self.G, self.H, self.W, 128, int(layer['relu']), 2, 0,
+                                                L.ptr(out), self.G, self.H, self.W, 128, int(layer['relu']), 2, self.h.conv_flags,
                                                 self.n_ctas, s), 'rz_net_conv3x3_tc2')
         else:
             L.check(self.lib.rz_net_conv3x3_tc3(L.ptr(inp), L.ptr(layer['w']), L.ptr(layer['b']), L.ptr(res),
