@@ -202,25 +202,40 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
     constexpr int HALF = ACC_N / 2;                 // columns per thread: 64 (pair) / 32 (single CTA)
     constexpr int NCHH = HALF / 32;                 // 32-column TMEM chunks per thread
     const int col0 = ((kCG == 2) ? 0 : half * 64) + hsel * HALF;   // first output channel of this thread
+    const int r_in_tile = q * 32 + lane;
+    auto row_valid = [&](int item_) {
+      const int pos_ = (row_of(item_) + r_in_tile) & 255;
+      return ((pos_ & 15) < p.board_w) && ((pos_ >> 4) < p.board);
+    };
+    // residual segment of this thread's row, double-buffered in registers: the loads for tile i+1 are issued
+    // while tile i is processed.  (With the loads at the top of their own iteration the epilogue -- usually
+    // behind the MMAs, so the accumulator is already waiting -- paid their latency in the open: 77 % against
+    // 94 % tensor-pipe activity for layers with / without a residual input, profiles/r1_run26_*.)
+    uint32_t res[NCHH * 2][8], resn[NCHH * 2][8];
+    bool next_res = false;
+    auto load_res = [&](int item_) {
+      next_res = p.residual != nullptr && row_valid(item_);
+      if (next_res) {
+        const __nv_bfloat16* rrow = p.residual + ((size_t)row_of(item_) + r_in_tile) * 128 + col0;
+#pragma unroll
+        for (int j = 0; j < NCHH * 2; ++j) rz::ld_global_v8_stream(rrow + j * 16, resn[j]);
+      }
+    };
+    if (worker < p.n_items) load_res(worker);
     int it = 0;
     for (int item = worker; item < p.n_items; item += n_workers, ++it) {
       const int buf = it & 1;
       const int row0 = row_of(item);
-      const int r_in_tile = q * 32 + lane;
       const size_t row = (size_t)row0 + r_in_tile;
-      const int pos = (int)(row & 255);
-      const bool valid = ((pos & 15) < p.board_w) && ((pos >> 4) < p.board);
-      uint32_t res[NCHH * 2][8];
-      const bool have_res = p.residual != nullptr && valid;
+      const bool valid = row_valid(item);
+      const bool have_res = next_res;
       if (have_res) {
-        const __nv_bfloat16* rrow = p.residual + row * 128 + col0;
 #pragma unroll
-        for (int j = 0; j < NCHH * 2; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
+        for (int j = 0; j < NCHH * 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) res[j][e] = resn[j][e];
       }
-      // the NEXT tile's residual segment of this thread -> L2 now, so that its loads (issued one tile from
-      // now, when the accumulator is usually already waiting) do not pay the DRAM latency in the open
-      if (p.residual != nullptr && item + n_workers < p.n_items)
-        rz::prefetch_l2(p.residual + ((size_t)row_of(item + n_workers) + r_in_tile) * 128 + col0);
+      if (item + n_workers < p.n_items) load_res(item + n_workers); else next_res = false;
       rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
       rz::tc_fence_after();
       if (p.flags & 4) {   // PROBE ONLY (scripts/conv_overhead_probe.py): no epilogue work at all -> MMA-side floor
@@ -309,20 +324,28 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
     const int col0 = hsel * 64;
+    const int r_in_tile = q * 32 + lane;
+    const int pos = (row_of(worker) + r_in_tile) & 255;       // the same square in every tile (see above)
+    const bool valid = ((pos & 15) < p.board_w) && ((pos >> 4) < p.board);
+    const bool have_res = p.residual != nullptr && valid;
+    uint32_t res[4][8], resn[4][8];                            // residual double-buffered in registers
+    auto load_res = [&](int item_) {
+      const __nv_bfloat16* rrow = p.residual + ((size_t)row_of(item_) + r_in_tile) * 128 + col0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rz::ld_global_v8_stream(rrow + j * 16, resn[j]);
+    };
+    if (have_res && worker < p.n_items) load_res(worker);
     int it = 0;
     for (int item = worker; item < p.n_items; item += n_workers, ++it) {
       const int buf = it & 1;
       const int row0 = row_of(item);
-      const int r_in_tile = q * 32 + lane;
       const size_t row = (size_t)row0 + r_in_tile;
-      const int pos = (int)(row & 255);
-      const bool valid = ((pos & 15) < p.board_w) && ((pos >> 4) < p.board);
-      uint32_t res[4][8];
-      const bool have_res = p.residual != nullptr && valid;
       if (have_res) {
-        const __nv_bfloat16* rrow = p.residual + row * 128 + col0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) res[j][e] = resn[j][e];
+        if (item + n_workers < p.n_items) load_res(item + n_workers);
       }
       rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
       rz::tc_fence_after();

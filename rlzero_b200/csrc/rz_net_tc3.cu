@@ -175,22 +175,39 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
     const int hsel = (warp - 2) >> 2;
     const int col0 = hsel * 64;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    const int r_in_tile = q * 32 + lane;
+    auto row_valid = [&](int row_) {
+      const int board_ = row_ / G::P, pos_ = row_ - board_ * G::P;
+      const int y_ = pos_ / kS, x_ = pos_ - y_ * kS;
+      return row_ < p.total_rows && x_ < p.W && y_ < p.H;
+    };
+    // residual segment double-buffered in registers: tile i+1's loads fly while tile i is processed
+    uint32_t res[4][8], resn[4][8];
+    bool next_res = false;
+    auto load_res = [&](int item_) {
+      const int row_ = item_ * 256 + (int)rank * TILE_M + r_in_tile;
+      next_res = p.residual != nullptr && row_valid(row_);
+      if (next_res) {
+        const __nv_bfloat16* rrow = p.residual + (size_t)row_ * 128 + col0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rz::ld_global_v8_stream(rrow + j * 16, resn[j]);
+      }
+    };
+    if (worker < p.n_items) load_res(worker);
     int it = 0;
     for (int item = worker; item < p.n_items; item += n_workers, ++it) {
       const int buf = it & 1;
       const int row0 = item * 256 + (int)rank * TILE_M;
-      const int r_in_tile = q * 32 + lane;
       const int row = row0 + r_in_tile;
-      const int board = row / G::P, pos = row - board * G::P;
-      const int y = pos / kS, x = pos - y * kS;
-      const bool valid = row < p.total_rows && x < p.W && y < p.H;
-      uint32_t res[4][8];
-      const bool have_res = p.residual != nullptr && valid;
+      const bool valid = row_valid(row);
+      const bool have_res = next_res;
       if (have_res) {
-        const __nv_bfloat16* rrow = p.residual + (size_t)row * 128 + col0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) res[j][e] = resn[j][e];
       }
+      if (item + n_workers < p.n_items) load_res(item + n_workers); else next_res = false;
       rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
       rz::tc_fence_after();
       uint32_t acc[2][32];

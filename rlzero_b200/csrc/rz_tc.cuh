@@ -89,12 +89,21 @@ __device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&r)[8]) {
                : "l"(p)
                : "memory");
 }
+// the same load without allocating the line in L1: the L1 data array is the shared-memory array the tensor
+// pipe fetches its operands from (96 of 128 B/clk in the trunk convolution), so streaming data that is used
+// once should not be written into it
+__device__ __forceinline__ void ld_global_v8_stream(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p)
+               : "memory");
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 // 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per lane
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
