@@ -276,6 +276,11 @@ def run_b200(args):
                 'frac_after_sustained_run_of_sustained_peak': flops / conv_ms_hot / 1e9 / sustained,
                 'launches_per_step': n_conv, 'share_of_step': in_step,
                 'traffic': traffic,
+                'issued_tflops': flops * 256.0 / 225.0 / conv_ms / 1e9,
+                'issued_frac_of_nominal_2250': flops * 256.0 / 225.0 / conv_ms / 1e9 / 2250.0,
+                'note': ('algorithmic FLOPs count the 225 squares of a board; the kernel issues MMAs for the 256 rows '
+                         'of its padded 16x16 tile.  frac may exceed 1: the MEASURED_PEAKS burst figure is cuBLAS '
+                         'at its own power-limited clock (about 0.76 of the nominal 2250 TFLOP/s)'),
                 'net_forward_tflops_in_step': net.flops_per_eval() * G / (ms / args.steps) / 1e9,
                 'frac_in_step_of_sustained': net.flops_per_eval() * G / (ms / args.steps) / 1e9 / sustained}
 
