@@ -76,3 +76,44 @@ def test_no_gpu_means_loud_failure():
         SearchForest(1, 3, 3, n_playout=10)
     with pytest.raises(_lib.NativeLibraryError):
         GomokuEnv(3, 3).reset()
+
+
+def test_new_entry_points_validate_arguments(lib):
+    """Go / DeepMindMCTS / MuZero entry points: host-side validation without a GPU."""
+    from rlzero_b200 import _lib
+    assert lib.rz_sizeof_mz_desc() == C.sizeof(_lib.MzDesc)
+    go = _lib.GameDesc(19, 1, 361, 384, 19, _lib.GAME_GO, 7.5, 0)          # the pass action is missing
+    rc = lib.rz_go_reset(C.byref(go), None, None, None, 1, 0, None)
+    assert rc != 0 and b'362' in lib.rz_last_error()
+    gomoku = _lib.GameDesc(15, 5, 225, 256)
+    rc = lib.rz_go_step(C.byref(gomoku), None, None, None, None, None, None, 1, None)
+    assert rc != 0 and b'RZ_GAME_GO' in lib.rz_last_error()
+    go = _lib.GameDesc(19, 1, 362, 384, 19, _lib.GAME_GO, 7.5, 0)
+    rc = lib.rz_gomoku_step(C.byref(go), None, None, None, None, None, 1, None)
+    assert rc != 0 and b'rz_go_' in lib.rz_last_error()
+    t = _lib.TreeDesc()
+    t.game = _lib.GameDesc(15, 5, 225, 256)
+    t.n_trees, t.max_nodes, t.max_depth, t.rule, t.flavour = 1, 8, 226, 0, 3
+    rc = lib.rz_tree_select(C.byref(t), None)
+    assert rc != 0
+    m = _lib.MzDesc()
+    m.n_trees, m.n_actions, m.action_stride, m.max_nodes, m.max_depth = 1, 225, 230, 51, 51
+    rc = lib.rz_mz_select(C.byref(m), None)
+    assert rc != 0 and b'action_stride' in lib.rz_last_error()
+    rc = lib.rz_mz_gather(None, None, None, None, 1, 15, 15, 16, 256, None)
+    assert rc != 0 and b'null' in lib.rz_last_error()
+
+
+def test_new_host_classes_fail_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from rlzero_b200 import _lib
+    from rlzero_b200.games.go import GoBoards, GoEnv
+    from rlzero_b200.muzero import MuZeroNet, MuZeroSearch
+    with pytest.raises(_lib.NativeLibraryError):
+        GoBoards(1, 9)
+    with pytest.raises(_lib.NativeLibraryError):
+        GoEnv(9).reset()
+    with pytest.raises(_lib.NativeLibraryError):
+        MuZeroSearch(1, MuZeroNet(6, 0, 0))
