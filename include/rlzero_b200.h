@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RZ_ABI_VERSION 6
+#define RZ_ABI_VERSION 7
 #define RZ_MAX_BOARD 19          /* rows live one per lane; A <= 362 (19x19 Go incl. the pass) */
 #define RZ_META_STRIDE 12
 #define RZ_GO_HIST 14            /* history planes a Go position carries besides the current board */
@@ -121,6 +121,9 @@ typedef struct rz_game_desc {
   float komi;                    /* Go: points given to white (GoEnv komi, go_env.py:41); 0 otherwise */
   int32_t max_moves;             /* Go: > 0 ends and scores the game after that many moves (engine-side cap,
                                     the reference has none); 0 = no cap */
+  int32_t row_stride;            /* network kernels only: row stride S of the padded position layout the trunk
+                                    activations use (a board owns S*S rows, square (y,x) at row y*S+x).
+                                    0 = the smallest of 8 / 16 / 20 with max(H,W) < S; else exactly 8, 16 or 20 */
 } rz_game_desc;
 
 /* ---- one search forest: G trees, one per game ---------------------------- */
@@ -324,6 +327,8 @@ typedef struct rz_heads_desc {
   int32_t action_stride;         /* AS: row stride of wp / logp */
   int32_t width;                 /* W columns (0: W = H) */
   int32_t n_actions;             /* policy outputs (0: H*W) */
+  int32_t row_stride;            /* S of the padded layout the features / trunk output use (0: automatic, as in
+                                    rz_game_desc.row_stride) */
   const float* w1x1;             /* [6][128]  act_conv1 (4 filters) then val_conv1 (2 filters) */
   const float* b1x1;             /* [6] */
   const float* wp;               /* [4*HW + 4][AS] act_fc1.weight^T, zero padded (columns >= HW and the 4 extra rows) */

@@ -11,7 +11,7 @@ import torch  # noqa: F401  -- loads libcudart.so.12 into the process before our
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'librlzero_b200.so')
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 META_STRIDE = 12
 (META_PLAYER, META_LAST_MOVE, META_STONES, META_STATUS, META_WINNER, META_PLY, META_FAULT,
  META_EPISODE, META_KO, META_PASSES) = range(10)
@@ -33,10 +33,11 @@ GAME_GOMOKU, GAME_CONNECT4, GAME_GO = 0, 1, 2
 
 
 class GameDesc(C.Structure):
-    """rz_game_desc: GameDesc(H, k, A, AS[, W, game_type, komi, max_moves]); W = 0 means a square board."""
+    """rz_game_desc: GameDesc(H, k, A, AS[, W, game_type, komi, max_moves, row_stride]); W = 0 means a square
+    board, row_stride = 0 the automatic padded layout of the network kernels (see row_stride())."""
     _fields_ = [('board_size', C.c_int32), ('n_in_row', C.c_int32), ('n_actions', C.c_int32),
                 ('action_stride', C.c_int32), ('width', C.c_int32), ('game_type', C.c_int32),
-                ('komi', C.c_float), ('max_moves', C.c_int32)]
+                ('komi', C.c_float), ('max_moves', C.c_int32), ('row_stride', C.c_int32)]
 
 
 class TreeDesc(C.Structure):
@@ -75,7 +76,7 @@ class MzDesc(C.Structure):
 
 class HeadsDesc(C.Structure):
     _fields_ = [('board_size', C.c_int32), ('action_stride', C.c_int32), ('width', C.c_int32),
-                ('n_actions', C.c_int32), ('w1x1', _vp), ('b1x1', _vp), ('wp', _vp), ('bp', _vp),
+                ('n_actions', C.c_int32), ('row_stride', C.c_int32), ('w1x1', _vp), ('b1x1', _vp), ('wp', _vp), ('bp', _vp),
                 ('wv1', _vp), ('bv1', _vp), ('wv2', _vp), ('bv2', _vp)]
 
 
@@ -141,6 +142,16 @@ _lib = None
 
 class NativeLibraryError(RuntimeError):
     pass
+
+
+def row_stride(H, W, requested=0):
+    """Row stride S of the padded position layout of the tensor-core network path (rz_row_stride in
+    rz_common.cuh): the smallest of 8 / 16 / 20 that leaves a zero column and a zero row, or the explicit
+    request; 0 if the board does not fit."""
+    m = max(int(H), int(W))
+    if requested:
+        return int(requested) if requested in (8, 16, 20) and m < requested else 0
+    return 8 if m <= 7 else (16 if m <= 15 else (20 if m <= 19 else 0))
 
 
 def load():

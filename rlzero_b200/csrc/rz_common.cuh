@@ -70,7 +70,19 @@ static inline int rz_check_game(const rz_game_desc* g) {
     rz_set_error("action_stride %d must be a multiple of 32 >= n_actions", g->action_stride); return -1; }
   if (g->n_in_row < 1 || g->n_in_row > (g->board_size > W ? g->board_size : W)) {
     rz_set_error("n_in_row %d outside [1,max(H,W)]", g->n_in_row); return -1; }
+  if (g->row_stride != 0 && g->row_stride != 8 && g->row_stride != 16 && g->row_stride != 20) {
+    rz_set_error("row_stride %d (0 = automatic, 8, 16 or 20)", g->row_stride); return -1; }
   return 0;
+}
+
+// Row stride S of the padded position layout of the tensor-core network path (a board owns S*S rows of
+// [128 channels] bf16, square (y, x) at row y*S + x, squares with x >= W or y >= H hold zero): the smallest of
+// 8 / 16 / 20 that leaves one zero column and one zero row, or the caller's explicit choice.  Returns 0 when
+// the board does not fit.  Mirrored by rlzero_b200._lib.row_stride.
+static inline int rz_row_stride(int H, int W, int requested) {
+  const int m = H > W ? H : W;
+  if (requested != 0) return (requested == 8 || requested == 16 || requested == 20) && m < requested ? requested : 0;
+  return m <= 7 ? 8 : (m <= 15 ? 16 : (m <= 19 ? 20 : 0));
 }
 
 // ---- device helpers --------------------------------------------------------

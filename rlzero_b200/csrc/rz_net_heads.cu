@@ -354,7 +354,9 @@ extern "C" int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_
   p.act = act; p.w1x1 = h->w1x1; p.b1x1 = h->b1x1; p.wp = h->wp; p.bp = h->bp; p.wv1 = h->wv1;
   p.bv1 = h->bv1; p.wv2 = h->wv2; p.bv2 = h->bv2; p.logp = logp; p.value = value;
   p.n_boards = n_boards; p.H = h->board_size; p.W = W; p.HW = HW; p.A = A; p.AS = h->action_stride;
-  p.S = (h->board_size <= 15 && W <= 15) ? 16 : 20;
+  p.S = rz_row_stride(h->board_size, W, h->row_stride);
+  RZ_REQUIRE(!act_is_tile_bf16 || p.S != 0, "rz_net_heads: row_stride %d does not hold a %dx%d board", h->row_stride,
+             h->board_size, W);
   p.P = p.S * p.S;
   const size_t smem = heads_smem(HW, p.AS);
   const int grid = (n_boards + HEAD_NB - 1) / HEAD_NB;

@@ -36,12 +36,14 @@ struct StemParams {
   int relu;
 };
 
-// kS: row stride of the padded position layout (16: boards up to 15x15, 20: up to 19x19); a board
-// owns kS*kS consecutive rows, tiles of 128 rows may straddle two boards when kS = 20
+// kS: row stride of the padded position layout (8: boards up to 7x7 such as Connect Four 6x7, 16: up to 15x15,
+// 20: up to 19x19); a board owns kS*kS consecutive rows; a tile of 128 rows holds exactly two boards when kS = 8
+// and may straddle two boards when kS = 20
 template <bool kPlanes, int kS>
 __global__ void __launch_bounds__(STEM_THREADS)
 rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                   const StemParams p) {
+  static_assert(kS * kS >= 64, "a 128-row tile must not touch more than two boards");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (rz::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* al = smem_raw + (base - rz::smem_u32(smem_raw));
@@ -379,10 +381,13 @@ static int stem_launch(const rz_game_desc* g, const uint32_t* rows, const int32_
                        int n_ctas, void* stream) {
   if (n_boards == 0) return 0;
   const int H = g->board_size, W = g->width > 0 ? g->width : g->board_size;
-  const int S = (H <= 15 && W <= 15) ? 16 : 20;
+  const int S = rz_row_stride(H, W, g->row_stride);
+  RZ_REQUIRE(S != 0, "rz_net_stem_tc: row_stride %d does not hold a %dx%d board", g->row_stride, H, W);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(rz_stem_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(rz_stem_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rz_stem_tc_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(rz_stem_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rz_stem_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rz_stem_tc_kernel<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(rz_stem_tc_kernel<true, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
@@ -400,7 +405,10 @@ static int stem_launch(const rz_game_desc* g, const uint32_t* rows, const int32_
   int ctas = n_ctas > 0 ? n_ctas : 148 * 3;
   if (ctas > p.n_tiles) ctas = p.n_tiles;
   cudaStream_t st = (cudaStream_t)stream;
-  if (S == 16) {
+  if (S == 8) {
+    if (planes) rz_stem_tc_kernel<true, 8><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+    else        rz_stem_tc_kernel<false, 8><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+  } else if (S == 16) {
     if (planes) rz_stem_tc_kernel<true, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
     else        rz_stem_tc_kernel<false, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
   } else {
@@ -436,7 +444,9 @@ static int go_stem_launch(const rz_game_desc* g, const uint32_t* rows, const uin
                           int relu, int n_ctas, void* stream) {
   if (n_boards == 0) return 0;
   const int H = g->board_size, W = H;
-  const int S = H <= 15 ? 16 : 20;
+  const int S = H <= 15 ? 16 : 20;   // the Go stem keeps at most two boards per tile in its plane staging: 16 / 20 only
+  RZ_REQUIRE(g->row_stride == 0 || g->row_stride == S, "rz_net_stem_go_tc: row_stride %d (a %dx%d Go board uses %d)",
+             g->row_stride, H, W, S);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(rz_stem_go_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GO_STEM_SMEM);

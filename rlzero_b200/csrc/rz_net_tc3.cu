@@ -381,7 +381,8 @@ static int conv3_entry(const void* act_in, const void* weight, const float* bias
                        int n_ctas, const float* w1x1_host, const float* b1x1_host, float* feat, void* stream) {
   RZ_REQUIRE(act_in && weight && bias, "rz_net_conv3x3_tc3: null argument");
   RZ_REQUIRE(n_boards >= 0, "rz_net_conv3x3_tc3: n_boards %d", n_boards);
-  RZ_REQUIRE(row_stride == 16 || row_stride == 20, "rz_net_conv3x3_tc3: row_stride %d (16 or 20)", row_stride);
+  RZ_REQUIRE(row_stride == 8 || row_stride == 16 || row_stride == 20, "rz_net_conv3x3_tc3: row_stride %d (8, 16 or 20)",
+             row_stride);
   RZ_REQUIRE(board_rows >= 1 && board_rows < row_stride && board_cols >= 1 && board_cols < row_stride,
              "rz_net_conv3x3_tc3: board %dx%d does not fit row stride %d", board_rows, board_cols, row_stride);
   RZ_REQUIRE(act_in != act_out, "rz_net_conv3x3_tc3: in-place convolution is not supported");
@@ -412,11 +413,13 @@ static int conv3_entry(const void* act_in, const void* weight, const float* bias
     for (int i = 0; i < 6 * 128; ++i) head.w[i] = w1x1_host[i];
     for (int i = 0; i < 6; ++i) head.b[i] = b1x1_host[i];
     head.feat = feat;
-    return row_stride == 16 ? launch3<16, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, st)
-                            : launch3<20, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, st);
+    return row_stride == 8    ? launch3<8, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, st)
+           : row_stride == 16 ? launch3<16, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, st)
+                              : launch3<20, true>(tmap_act, tmap_w, tmap_out, p, head, ctas, st);
   }
-  return row_stride == 16 ? launch3<16, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, st)
-                          : launch3<20, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, st);
+  return row_stride == 8    ? launch3<8, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, st)
+         : row_stride == 16 ? launch3<16, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, st)
+                            : launch3<20, false>(tmap_act, tmap_w, tmap_out, p, head, ctas, st);
 }
 
 extern "C" int rz_net_conv3x3_tc3(const void* act_in, const void* weight, const float* bias,

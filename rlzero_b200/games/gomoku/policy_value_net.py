@@ -144,7 +144,7 @@ class NativeForward(object):
     prior_is_log = True       # the network emits log-probabilities (policy_value_net.py:44)
 
     def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0, conv_rev=2, fused_stem=True,
-                 fused_head=True, game_type=None):
+                 fused_head=True, game_type=None, row_stride=None):
         if not torch.cuda.is_available():
             raise L.NativeLibraryError('NativeForward needs a CUDA device (no CPU fallback)')
         self.lib = L.load()
@@ -162,8 +162,16 @@ class NativeForward(object):
         layers = module.trunk_layers()
         all128 = all(l[0].out_channels == 128 for l in layers)
         fits = self.H <= 19 and self.W <= 19
-        # padded position layout of the tensor-core path: row = board*S*S + y*S + x
-        self.S = 16 if (self.H <= 15 and self.W <= 15) else 20
+        # padded position layout of the tensor-core path: row = board*S*S + y*S + x, S the smallest of 8 / 16 / 20
+        # with a zero column and a zero row left (Connect Four 6x7 and other boards up to 7x7: S = 8, 64 rows per
+        # board instead of 256); the Go stem stages at most two boards per tile and keeps 16 / 20
+        auto = L.row_stride(self.H, self.W)
+        if self.game_type == L.GAME_GO:
+            auto = max(auto, 16)
+        self.S = int(row_stride) if row_stride else (auto or 20)
+        if fits and L.row_stride(self.H, self.W, self.S) != self.S:
+            raise ValueError('row_stride %r does not hold a %dx%d board (8, 16 or 20, > max(H, W))' % (
+                row_stride, self.H, self.W))
         self.P = self.S * self.S
         if mode is None:
             mode = 'tc' if (all128 and fits) else 'f32'
@@ -247,6 +255,7 @@ class NativeForward(object):
         self.weights_version += 1
         hd = L.HeadsDesc()
         hd.board_size, hd.action_stride, hd.width, hd.n_actions = self.H, AS, self.W, self.A
+        hd.row_stride = self.S if self.mode == 'tc' else 0
         for k, v in self.heads.items():
             setattr(hd, k, v.data_ptr())
         self.hdesc = hd
@@ -271,9 +280,10 @@ class NativeForward(object):
 
     # ------------------------------------------------------------------ forward
     def _gdesc(self, k=5):
+        rs = self.S if self.mode == 'tc' else 0
         if self.game_type == L.GAME_GO:
-            return L.GameDesc(self.H, 1, self.A, self.AS, self.W, self.game_type)
-        return L.GameDesc(self.H, min(k, max(self.H, self.W)), self.A, self.AS, self.W, self.game_type)
+            return L.GameDesc(self.H, 1, self.A, self.AS, self.W, self.game_type, 0.0, 0, rs)
+        return L.GameDesc(self.H, min(k, max(self.H, self.W)), self.A, self.AS, self.W, self.game_type, 0.0, 0, rs)
 
     def _trunk_and_heads(self, n, logp, value, stem_done=False):
         s = L.stream_ptr()

@@ -117,3 +117,22 @@ def test_new_host_classes_fail_loudly_without_a_gpu():
         GoEnv(9).reset()
     with pytest.raises(_lib.NativeLibraryError):
         MuZeroSearch(1, MuZeroNet(6, 0, 0))
+
+
+def test_row_stride_rule_and_validation(lib):
+    """Padded position layout of the network kernels: S = the smallest of 8 / 16 / 20 above max(H, W) (ABI 7);
+    the Python mirror and the C validation agree."""
+    from rlzero_b200 import _lib as L
+    assert [L.row_stride(h, w) for h, w in [(3, 3), (6, 7), (7, 7), (8, 8), (6, 8), (15, 15), (16, 16), (19, 19)]] == \
+        [8, 8, 8, 16, 16, 16, 20, 20]
+    assert L.row_stride(20, 20) == 0 and L.row_stride(9, 9, 8) == 0 and L.row_stride(6, 7, 16) == 16
+    g = L.GameDesc(6, 4, 7, 32, 7, L.GAME_CONNECT4, 0.0, 0, 12)
+    rc = lib.rz_gomoku_reset(C.byref(g), None, None, 1, 0, None)
+    assert rc != 0 and b'row_stride' in lib.rz_last_error()
+    # a 9x9 board does not fit the 8-stride layout: rejected on the host before any launch
+    g = L.GameDesc(9, 5, 81, 96, 9, L.GAME_GOMOKU, 0.0, 0, 8)
+    dummy = C.c_void_p(16)
+    rc = lib.rz_net_stem_tc(C.byref(g), dummy, dummy, dummy, dummy, dummy, 1, 1, 0, None)
+    assert rc != 0 and b'row_stride' in lib.rz_last_error()
+    rc = lib.rz_net_conv3x3_tc3(dummy, dummy, dummy, None, C.c_void_p(32), 1, 6, 7, 12, 1, 0, None)
+    assert rc != 0 and b'row_stride' in lib.rz_last_error()

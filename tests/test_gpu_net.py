@@ -233,7 +233,9 @@ def test_fused_stem_matches_encode_plus_conv(size, n):
         envs.append(e)
     rows = torch.cat([e.device_state()[0] for e in envs]).cuda()
     meta = torch.cat([e.device_state()[1] for e in envs]).cuda()
-    nf = NativeForward(net, max_batch=n)
+    # row_stride=16: this test compares against the legacy stride-16 encode + conv route (a 6x6 board would
+    # otherwise use the 8-stride layout, covered by test_row_stride_8_*)
+    nf = NativeForward(net, max_batch=n, row_stride=16)
     lib, g = L.load(), nf._gdesc()
     st = nf.stem
     fused = torch.full((n, 256, 128), 3.0, dtype=torch.bfloat16, device='cuda')
@@ -261,7 +263,7 @@ def test_fused_stem_matches_encode_plus_conv(size, n):
     # and the whole forward through both routes
     lp1, v1 = nf.forward_boards(rows, meta, n)
     lp1, v1 = lp1.clone(), v1.clone()
-    nf2 = NativeForward(net, max_batch=n, fused_stem=False)
+    nf2 = NativeForward(net, max_batch=n, fused_stem=False, row_stride=16)
     lp2, v2 = nf2.forward_boards(rows, meta, n)
     assert (lp1[:, :size * size] - lp2[:, :size * size]).abs().max().item() < 2e-3
     assert (v1 - v2).abs().max().item() < 2e-3
@@ -319,15 +321,18 @@ def _to_pad(x_nchw, S):
     return out
 
 
-@pytest.mark.parametrize('n,h,w,relu,res', [(1, 19, 19, 1, 0), (5, 19, 19, 1, 1), (131, 19, 19, 1, 1), (3, 17, 18, 0, 0),
-                                            (2, 6, 7, 1, 1)])
-def test_conv3x3_tc3_any_stride_matches_torch(n, h, w, relu, res):
-    """Revision 3 at row stride 20 (19x19 and other boards > 15), tiles straddling boards."""
+@pytest.mark.parametrize('n,h,w,relu,res,S', [(1, 19, 19, 1, 0, 20), (5, 19, 19, 1, 1, 20), (131, 19, 19, 1, 1, 20),
+                                              (3, 17, 18, 0, 0, 20), (2, 6, 7, 1, 1, 16), (2, 6, 7, 1, 1, 8),
+                                              (1, 7, 7, 0, 0, 8), (301, 6, 7, 1, 1, 8), (9, 3, 3, 1, 0, 8),
+                                              (1200, 6, 7, 1, 1, 8)])
+def test_conv3x3_tc3_any_stride_matches_torch(n, h, w, relu, res, S):
+    """Revision 3 at row stride 20 (19x19 and other boards > 15: tiles straddling boards), 16, and 8 (Connect
+    Four 6x7 and other boards up to 7x7: two whole boards per 128-row tile, 4 per CTA-pair item)."""
     from rlzero_b200 import _lib as L
     lib = L.load()
     torch.manual_seed(n * 10 + h)
     dev = 'cuda'
-    S = 16 if max(h, w) <= 15 else 20
+    assert L.row_stride(h, w, S) == S
     x = (torch.randn(n, 128, h, w, device=dev) * 0.5).to(torch.bfloat16).float()
     wgt = (torch.randn(128, 128, 3, 3, device=dev) / (3.0 * 128 ** 0.5)).to(torch.bfloat16).float()
     b = torch.randn(128, device=dev) * 0.1
@@ -384,3 +389,87 @@ def test_resnet_forward_rev3_vs_torch_and_rev2(size, blocks, n):
         nf2 = NativeForward(net, max_batch=n, conv_rev=2)
         l2, v2 = (t.cpu() for t in nf2.forward_planes(x))
         assert (l2.exp() - logp.exp()).abs().max().item() < 1e-4 and (v2 - v).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize('h,w,a,blocks,n', [(6, 7, 7, 3, 300), (6, 6, None, 2, 5), (3, 3, None, 1, 17), (7, 7, None, 1, 130)])
+def test_row_stride_8_forward_vs_torch_and_stride_16(h, w, a, blocks, n):
+    """Boards up to 7x7 (Connect Four 6x7 = BASELINE config 2, TicTacToe 3x3) run on the 8-stride padded layout
+    (64 rows per board instead of 256): whole forward within 1e-3 of PyTorch fp32, fused head on/off and
+    planes-/bitboard-fed stems bit-identical, and the same network forced onto the 16-stride layout agrees (same
+    bf16 products; the accumulation order inside one MMA chain is the same, so the trunk is in fact identical)."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(h * 10 + w)
+    kw = dict(board_width=w, n_actions=a) if a is not None else dict(board_width=w)
+    net = ResNetPolicyValueNet(h, n_blocks=blocks, **kw).cuda().eval()
+    nf = NativeForward(net, max_batch=n)
+    assert nf.mode == 'tc' and nf.S == 8 and nf.P == 64
+    rs = np.random.RandomState(n)
+    x = rs.randint(0, 2, size=(n, 4, h, w)).astype(np.float32)
+    logp, v = (t.cpu().clone() for t in nf.forward_planes(x))
+    ref = ResNetPolicyValueNet(h, n_blocks=blocks, **kw).eval()
+    ref.load_state_dict({k: t.cpu() for k, t in net.state_dict().items()})
+    with torch.no_grad():
+        lt, vt = ref(torch.from_numpy(x))
+    A = nf.A
+    assert (logp[:, :A].exp() - lt.exp()).abs().max().item() < 1e-3
+    assert (v - vt.reshape(-1)).abs().max().item() < 1e-3
+    nf_b = NativeForward(net, max_batch=n, fused_head=False)
+    assert nf_b.S == 8
+    lb, vb = (t.cpu() for t in nf_b.forward_planes(x))
+    assert torch.equal(lb[:, :A], logp[:, :A]) and torch.equal(vb, v)
+    nf16 = NativeForward(net, max_batch=n, row_stride=16, conv_rev=3)
+    assert nf16.S == 16
+    l16, v16 = (t.cpu() for t in nf16.forward_planes(x))
+    assert (l16[:, :A].exp() - logp[:, :A].exp()).abs().max().item() < 1e-4 and (v16 - v).abs().max().item() < 1e-3
+    # padding squares and the rows beyond the last board stay zero (they are every tap's halo)
+    full = nf_b.bufs[0][:n * 64].reshape(n, 8, 8, 128).float()
+    assert full[:, h:].abs().max().item() == 0.0 and full[:, :, w:].abs().max().item() == 0.0
+    with pytest.raises(ValueError):
+        NativeForward(ResNetPolicyValueNet(9, n_blocks=1).cuda().eval(), row_stride=8)
+
+
+@pytest.mark.parametrize('size,n', [(6, 37), (3, 4)])
+def test_row_stride_8_stem_bitboards_vs_planes_and_torch(size, n):
+    """The fused encoder + stem on the 8-stride layout: positions fed as device bitboards and as current_state
+    planes give bit-identical outputs, equal to PyTorch's conv on the reference's planes (bf16 weights)."""
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.games.gomoku.gomoku_env import GomokuEnv
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(size)
+    net = ResNetPolicyValueNet(size, n_blocks=1).cuda().eval()
+    rs = np.random.RandomState(size)
+    envs = []
+    for i in range(n):
+        e = GomokuEnv(size, min(4, size))
+        e.reset()
+        for m in rs.permutation(size * size)[:(0 if i == 0 else rs.randint(0, size * size - 1))]:
+            e.step(int(m))
+            if e.game_end_winner()[0]:
+                break
+        envs.append(e)
+    rows = torch.cat([e.device_state()[0] for e in envs]).cuda()
+    meta = torch.cat([e.device_state()[1] for e in envs]).cuda()
+    nf = NativeForward(net, max_batch=n)
+    assert nf.S == 8
+    lib, g = L.load(), nf._gdesc()
+    st = nf.stem
+    rows_alloc = (n * 64 + 255) // 256 * 256
+    fused = torch.full((rows_alloc, 128), 3.0, dtype=torch.bfloat16, device='cuda')
+    L.check(lib.rz_net_stem_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(st['w']), L.ptr(st['b']), L.ptr(fused),
+                               n, 1, 0, L.stream_ptr()), 'stem')
+    planes = torch.tensor(np.stack([e.current_state() for e in envs]), dtype=torch.float32, device='cuda')
+    fused_p = torch.full((rows_alloc, 128), 5.0, dtype=torch.bfloat16, device='cuda')
+    L.check(lib.rz_net_stem_tc_planes(C.byref(g), L.ptr(planes.contiguous()), L.ptr(st['w']), L.ptr(st['b']),
+                                      L.ptr(fused_p), n, 1, 0, L.stream_ptr()), 'stem planes')
+    torch.cuda.synchronize()
+    assert torch.equal(fused, fused_p)
+    assert fused[n * 64:].abs().max().item() == 0.0 if rows_alloc > n * 64 else True
+    full = fused[:n * 64].reshape(n, 8, 8, 128).float()
+    assert full[:, size:].abs().max().item() == 0.0 and full[:, :, size:].abs().max().item() == 0.0
+    wq = net.stem.weight.detach().to(torch.bfloat16).float()
+    ref = torch.relu(torch.nn.functional.conv2d(planes, wq, net.stem.bias.detach(), padding=1))
+    got = full[:, :size, :size].permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() <= 2.0 ** -8 * max(1.0, ref.abs().max().item()) + 1e-6
+    lp1, v1 = (t.clone() for t in nf.forward_boards(rows, meta, n))
+    lp3, v3 = nf.forward_planes(planes.cpu().numpy())
+    assert torch.equal(lp3[:, :size * size], lp1[:, :size * size]) and torch.equal(v3, v1)
