@@ -365,8 +365,8 @@ int rz_net_conv3x3_tc2_head(const void* act_in, const void* weight, const float*
                             const float* w1x1_host, const float* b1x1_host, float* feat, int n_ctas,
                             void* stream);
 /* revision 3 of the convolution: the same data path for any row stride of the padded position
-   layout (row = board*S*S + y*S + x; S = row_stride = 16 for boards up to 15x15, 20 up to 19x19), tiles of
-   128 rows that may straddle boards, a 3-slot ring of k-block halo tiles and a half-staged TMA-store
+   layout (row = board*S*S + y*S + x; S = row_stride = 8 for boards up to 7x7 such as Connect Four 6x7, 16 up
+   to 15x15, 20 up to 19x19), tiles of 128 rows that may straddle boards (S = 20) or hold two boards (S = 8), a 3-slot ring of k-block halo tiles and a half-staged TMA-store
    epilogue (shared-memory budget of the 170-row halo at S = 20).  c_in = c_out = 128.  Tensors are
    bf16 [round_up(n_boards*S*S, 256)][128].  The _head variant writes feat f32 [n_boards][6][S*S]. */
 int rz_net_conv3x3_tc3(const void* act_in, const void* weight, const float* bias, const void* residual,
@@ -379,8 +379,9 @@ int rz_net_conv3x3_tc3_head(const void* act_in, const void* weight, const float*
 /* fused current_state (gomoku_env.py:95-114) + first trunk convolution (policy_value_net.py:14,36):
    the 36-wide im2col row of every position (k = tap*4 + plane) is built from the bitboards in
    registers, so the observation planes never exist in HBM.  weight bf16 [128][64] (k padded with
-   zeros from 36), bias f32 [128], act_out bf16 [round_up(n*S*S, 256)][128] padded layout, S = 16 for
-   boards up to 15x15 (then [n][256][128]) and 20 up to 19x19. */
+   zeros from 36), bias f32 [128], act_out bf16 [round_up(n*S*S, 256)][128] padded layout, S =
+   g->row_stride, or when that is 0 the smallest of 8 (boards up to 7x7), 16 (up to 15x15, then
+   [n][256][128]) and 20 (up to 19x19). */
 int rz_net_stem_tc(const rz_game_desc* g, const uint32_t* rows, const int32_t* meta, const void* weight,
                    const float* bias, void* act_out, int n_boards, int relu, int n_ctas, void* stream);
 /* the same kernel fed from float32 observation planes [n][4][H][W] (the current_state format,
@@ -404,8 +405,8 @@ int rz_net_conv3x3_f32(const float* in, const float* weight, const float* bias, 
 /* both heads from the 128-channel trunk output: logp f32 [n][AS] = log_softmax(policy logits)
    (0 in the padding), value f32 [n] = tanh(...).  act_is_tile_bf16 = 0: act is f32 [n][HW][128];
    1: bf16 padded layout [n][S*S][128]; 2: act is the f32 [n][6][S*S] feature tensor written by
-   rz_net_conv3x3_tc2_head / _tc3_head (the 1x1 convolutions are already applied); S = 16 for boards
-   up to 15x15, else 20. */
+   rz_net_conv3x3_tc2_head / _tc3_head (the 1x1 convolutions are already applied); S = h->row_stride, or
+   when that is 0 the smallest of 8 / 16 / 20 above max(H, W). */
 int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_tile_bf16, float* logp,
                  float* value, int n_boards, void* stream);
 
