@@ -337,6 +337,12 @@ typedef struct rz_heads_desc {
   const float* bv1;              /* [64] */
   const float* wv2;              /* [64]       val_fc2.weight */
   const float* bv2;              /* [1] */
+  /* rz_net_heads_tc only (may be NULL otherwise): both FC weight matrices as ONE bf16 K-major matrix
+     [AS + 64][KP], KP = round_up(6*S*S, 64), split into a high and a low part (w = hi + lo, lo = the bf16
+     rounding error of hi).  Row a < AS: act_fc1.weight[a] at column f*S*S + y*S + x (f < 4; zero at padding
+     squares and for a >= A); row AS + o: val_fc1.weight[o] at column (4 + f)*S*S + y*S + x (f < 2). */
+  const void* wtc_hi;
+  const void* wtc_lo;
 } rz_heads_desc;
 
 /* 3x3 convolution (padding 1) + bias (+ residual) (+ ReLU) on the tensor cores (tcgen05/TMEM/TMA):
@@ -409,6 +415,16 @@ int rz_net_conv3x3_f32(const float* in, const float* weight, const float* bias, 
    when that is 0 the smallest of 8 / 16 / 20 above max(H, W). */
 int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_tile_bf16, float* logp,
                  float* value, int n_boards, void* stream);
+/* the heads' two 1x1 convolutions + ReLU alone (policy_value_net.py:41,47): act bf16 padded layout
+   [n*S*S][128] -> feat f32 [n][6][S*S], the tensor rz_net_conv3x3_tc2_head / _tc3_head write from their
+   epilogue (same summation order: bit-identical at the board's squares). */
+int rz_net_head_features(const rz_heads_desc* h, const void* act, float* feat, int n_boards, void* stream);
+/* the fully connected layers of both heads on the tensor cores (act_fc1 + log_softmax, val_fc1 + ReLU +
+   val_fc2 + tanh; policy_value_net.py:42-44,48-51) from feat f32 [n][6][S*S]: one tcgen05 GEMM per 128 boards
+   over the padded feature row, bf16 hi/lo split of features and weights (3 MMAs per k-step) for float32-level
+   accuracy, accumulators and the softmax in TMEM.  Needs h->wtc_hi / wtc_lo; logp f32 [n][AS], value f32 [n]. */
+int rz_net_heads_tc(const rz_heads_desc* h, const float* feat, float* logp, float* value, int n_boards,
+                    void* stream);
 
 /* ---- MuZero search in latent space (BASELINE.json config 5) ----------------------------------------
    The reference has no MuZero code: the kernels follow the pseudocode published with the MuZero paper

@@ -77,7 +77,7 @@ class MzDesc(C.Structure):
 class HeadsDesc(C.Structure):
     _fields_ = [('board_size', C.c_int32), ('action_stride', C.c_int32), ('width', C.c_int32),
                 ('n_actions', C.c_int32), ('row_stride', C.c_int32), ('w1x1', _vp), ('b1x1', _vp), ('wp', _vp), ('bp', _vp),
-                ('wv1', _vp), ('bv1', _vp), ('wv2', _vp), ('bv2', _vp)]
+                ('wv1', _vp), ('bv1', _vp), ('wv2', _vp), ('bv2', _vp), ('wtc_hi', _vp), ('wtc_lo', _vp)]
 
 
 # name -> (restype, argtypes); every symbol include/rlzero_b200.h declares
@@ -135,6 +135,8 @@ SIGNATURES = {
     'rz_net_conv3x3_f32': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, _vp]),
     'rz_net_heads': (C.c_int, [C.POINTER(HeadsDesc), _vp, C.c_int, _vp, _vp, C.c_int, _vp]),
+    'rz_net_head_features': (C.c_int, [C.POINTER(HeadsDesc), _vp, _vp, C.c_int, _vp]),
+    'rz_net_heads_tc': (C.c_int, [C.POINTER(HeadsDesc), _vp, _vp, _vp, C.c_int, _vp]),
 }
 
 _lib = None

@@ -11,6 +11,7 @@
 // (3 layers, <= 64 input channels) at any board size; the benchmark trunk runs on the tensor
 // cores (rz_net_tc.cu).  The heads kernel serves both (template on the activation layout).
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "rz_common.cuh"
 
@@ -304,6 +305,26 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
   }
 }
 
+// the heads' 1x1 convolutions + ReLU alone: bf16 trunk output (padded layout) -> feat[b][f][y*S+x], the tensor the
+// fused last trunk layer writes from its epilogue (same summation order, conv1x1_position).  Padding squares hold
+// relu(bias), as there (their activations are zero); the FC weights are zero at those columns.
+__global__ void __launch_bounds__(256) rz_head_features_kernel(const HeadsParams p, float* __restrict__ feat) {
+  __shared__ __align__(16) float s_w[6 * HEAD_C];
+  for (int i = threadIdx.x; i < 6 * HEAD_C; i += blockDim.x) s_w[i] = p.w1x1[i];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)p.n_boards * p.P) return;
+  const int b = (int)(idx / p.P), t = (int)(idx - (long long)b * p.P);
+  const int y = t / p.S, x = t - y * p.S;
+  float acc[6];
+#pragma unroll
+  for (int f = 0; f < 6; ++f) acc[f] = p.b1x1[f];
+  if (x < p.W && y < p.H) conv1x1_position<true>(p.act, b, y * p.W + x, p.W, p.HW, p.S, p.P, s_w, acc);
+  float* fo = feat + (size_t)b * (6 * p.P) + t;
+#pragma unroll
+  for (int f = 0; f < 6; ++f) fo[f * p.P] = fmaxf(acc[f], 0.0f);
+}
+
 size_t heads_smem(int HW, int AS) {
   return sizeof(float) * ((size_t)HEAD_NB * 6 * HW + (size_t)HEAD_NB * AS + HEAD_NB * 64 + 6 * HEAD_C);
 }
@@ -363,4 +384,24 @@ extern "C" int rz_net_heads(const rz_heads_desc* h, const void* act, int act_is_
   if (act_is_tile_bf16 == 2) return heads_launch<SRC_FEAT>(p, smem, grid, (cudaStream_t)stream);
   if (act_is_tile_bf16 == 1) return heads_launch<SRC_TILE>(p, smem, grid, (cudaStream_t)stream);
   return heads_launch<SRC_F32>(p, smem, grid, (cudaStream_t)stream);
+}
+
+extern "C" int rz_net_head_features(const rz_heads_desc* h, const void* act, float* feat, int n_boards,
+                                    void* stream) {
+  RZ_REQUIRE(h && act && feat, "rz_net_head_features: null argument");
+  RZ_REQUIRE(h->w1x1 && h->b1x1, "rz_net_head_features: null weight pointer");
+  RZ_REQUIRE(h->board_size >= 1 && h->board_size <= RZ_MAX_BOARD, "rz_net_head_features: board_size %d", h->board_size);
+  const int W = h->width > 0 ? h->width : h->board_size;
+  RZ_REQUIRE(W >= 1 && W <= RZ_MAX_BOARD, "rz_net_head_features: width %d", W);
+  const int S = rz_row_stride(h->board_size, W, h->row_stride);
+  RZ_REQUIRE(S != 0, "rz_net_head_features: row_stride %d does not hold a %dx%d board", h->row_stride, h->board_size, W);
+  if (n_boards <= 0) return 0;
+  HeadsParams p;
+  memset(&p, 0, sizeof(p));
+  p.act = act; p.w1x1 = h->w1x1; p.b1x1 = h->b1x1;
+  p.n_boards = n_boards; p.H = h->board_size; p.W = W; p.HW = h->board_size * W; p.S = S; p.P = S * S;
+  const long long total = (long long)n_boards * p.P;
+  rz_head_features_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, feat);
+  RZ_LAUNCH_CHECK("rz_net_head_features");
+  return 0;
 }

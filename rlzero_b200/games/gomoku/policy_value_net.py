@@ -144,7 +144,7 @@ class NativeForward(object):
     prior_is_log = True       # the network emits log-probabilities (policy_value_net.py:44)
 
     def __init__(self, module, mode=None, max_batch=1, device='cuda', n_ctas=0, conv_rev=2, fused_stem=True,
-                 fused_head=True, game_type=None, row_stride=None):
+                 fused_head=True, game_type=None, row_stride=None, heads_tc=True):
         if not torch.cuda.is_available():
             raise L.NativeLibraryError('NativeForward needs a CUDA device (no CPU fallback)')
         self.lib = L.load()
@@ -187,6 +187,9 @@ class NativeForward(object):
         self.fused_head = bool(fused_head) and int(conv_rev) >= 2
         self.weights_version = 0
         self.fused_stem = bool(fused_stem)  # encoder + first conv in one kernel (rz_net_stem.cu)
+        # the heads' fully connected layers on the tensor cores (rz_net_heads_tc.cu; bf16 hi/lo split, fp32-level
+        # accuracy); False keeps the CUDA-core heads kernel
+        self.heads_tc = bool(heads_tc) and mode == 'tc'
         # 3: rz_net_tc3.cu (any row stride; forced for 19x19); 2: rz_net_tc2.cu (stride 16); 1: rz_net_tc.cu
         self.conv_rev = int(conv_rev)
         # rz_net_conv3x3_tc2 flags: bit 1 = direct-store epilogue, the default (853 k vs 840 k sims/s sustained on
@@ -249,6 +252,21 @@ class NativeForward(object):
             bv1=m.val_fc1.bias.detach().float().contiguous().to(dev),
             wv2=m.val_fc2.weight.detach().reshape(64).float().contiguous().to(dev),
             bv2=m.val_fc2.bias.detach().float().contiguous().to(dev))
+        if self.heads_tc:
+            # both FCs as one K-major matrix over the padded feature row k' = f*P + y*S + x (rz_heads_desc.wtc_hi)
+            S, Pp, A = self.S, self.P, self.A
+            KP = (6 * Pp + 63) // 64 * 64
+            wall = torch.zeros(AS + 64, KP, dtype=torch.float32)
+            wpol = torch.zeros(A, 4, S, S, dtype=torch.float32)
+            wpol[:, :, :self.H, :self.W] = m.act_fc1.weight.detach().float().cpu().reshape(A, 4, self.H, self.W)
+            wall[:A, :4 * Pp] = wpol.reshape(A, 4 * Pp)
+            wval = torch.zeros(64, 2, S, S, dtype=torch.float32)
+            wval[:, :, :self.H, :self.W] = m.val_fc1.weight.detach().float().cpu().reshape(64, 2, self.H, self.W)
+            wall[AS:AS + 64, 4 * Pp:6 * Pp] = wval.reshape(64, 2 * Pp)
+            whi = wall.to(torch.bfloat16)
+            wlo = (wall - whi.float()).to(torch.bfloat16)
+            self.heads['wtc_hi'] = whi.contiguous().to(dev)
+            self.heads['wtc_lo'] = wlo.contiguous().to(dev)
         # host copies of the 1x1 filters: they travel in the launch parameters of the fused last layer
         self.w1x1_host = np.ascontiguousarray(w1.float().cpu().numpy().reshape(-1))
         self.b1x1_host = np.ascontiguousarray(b1.float().cpu().numpy().reshape(-1))
@@ -313,8 +331,12 @@ class NativeForward(object):
                         L.check(lib.rz_net_conv3x3_tc2_head(
                             L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), n, self.H, self.W, l['cin'],
                             int(l['relu']), w1p, b1p, L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc2_head')
-                    L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(self.feat), 2, L.ptr(logp), L.ptr(value),
-                                             n, s), 'rz_net_heads')
+                    if self.heads_tc:
+                        L.check(lib.rz_net_heads_tc(C.byref(self.hdesc), L.ptr(self.feat), L.ptr(logp), L.ptr(value),
+                                                    n, s), 'rz_net_heads_tc')
+                    else:
+                        L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(self.feat), 2, L.ptr(logp),
+                                                 L.ptr(value), n, s), 'rz_net_heads')
                     return
                 if rev3:
                     L.check(lib.rz_net_conv3x3_tc3(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
@@ -331,8 +353,14 @@ class NativeForward(object):
                                                   L.ptr(outs[dst]), n, self.H, l['cin'], int(l['relu']),
                                                   self.n_ctas, s), 'rz_net_conv3x3_tc')
                 cur = dst
-            L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(outs[cur]), 1, L.ptr(logp), L.ptr(value), n, s),
-                    'rz_net_heads')
+            if self.heads_tc:
+                L.check(lib.rz_net_head_features(C.byref(self.hdesc), L.ptr(outs[cur]), L.ptr(self.feat), n, s),
+                        'rz_net_head_features')
+                L.check(lib.rz_net_heads_tc(C.byref(self.hdesc), L.ptr(self.feat), L.ptr(logp), L.ptr(value), n, s),
+                        'rz_net_heads_tc')
+            else:
+                L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(outs[cur]), 1, L.ptr(logp), L.ptr(value), n, s),
+                        'rz_net_heads')
         else:
             outs = self.bufs
             hist = []   # buffer index holding the output of layer i
@@ -355,7 +383,8 @@ class NativeForward(object):
         """Kernel launches of one forward_boards call (for bench.py's gpu_launches)."""
         n_conv = len(self.layers)
         fused = self.mode == 'tc' and self.stem is not None and self.fused_stem
-        return (1 + n_conv - 1 if fused else 1 + n_conv) + 1      # [stem | encode + conv0] + convs + heads
+        heads = 2 if (self.heads_tc and not self.fused_head) else 1   # [1x1 features +] FC heads
+        return (1 + n_conv - 1 if fused else 1 + n_conv) + heads  # [stem | encode + conv0] + convs + heads
 
     def forward_boards(self, rows, meta, n, logp=None, value=None, hist=None):
         """Positions in the device board layout -> (logp [n][AS], value [n]) float32 tensors.

@@ -156,6 +156,8 @@ class MuZeroNative(object):
         bf = torch.bfloat16
         self.pool = torch.zeros(int(n_slots), self.slot_rows, 128, dtype=bf, device=self.device)
         self.bufs = [torch.zeros(self.slot_rows, 128, dtype=bf, device=self.device) for _ in range(2)]
+        # head features [G][6][P] (rz_net_head_features -> rz_net_heads_tc: the FCs of f on the tensor cores)
+        self.feat = torch.zeros(self.G, 6, self.P, dtype=torch.float32, device=self.device)
         self.logp = torch.zeros(self.G, self.AS, dtype=torch.float32, device=self.device)
         self.value = torch.zeros(self.G, dtype=torch.float32, device=self.device)
         self.weights_version = 0
@@ -215,12 +217,18 @@ class MuZeroNative(object):
         """f(pool[slot]) -> (log-probabilities [G][AS], value [G])."""
         logp = self.logp if logp is None else logp
         value = self.value if value is None else value
-        L.check(self.lib.rz_net_heads(C.byref(self.h.hdesc), L.ptr(self.pool[slot]), 1, L.ptr(logp), L.ptr(value),
-                                      self.G, L.stream_ptr()), 'rz_net_heads')
+        if self.h.heads_tc:
+            L.check(self.lib.rz_net_head_features(C.byref(self.h.hdesc), L.ptr(self.pool[slot]), L.ptr(self.feat),
+                                                  self.G, L.stream_ptr()), 'rz_net_head_features')
+            L.check(self.lib.rz_net_heads_tc(C.byref(self.h.hdesc), L.ptr(self.feat), L.ptr(logp), L.ptr(value),
+                                             self.G, L.stream_ptr()), 'rz_net_heads_tc')
+        else:
+            L.check(self.lib.rz_net_heads(C.byref(self.h.hdesc), L.ptr(self.pool[slot]), 1, L.ptr(logp),
+                                          L.ptr(value), self.G, L.stream_ptr()), 'rz_net_heads')
         return logp, value
 
     def kernels_per_simulation(self):
-        return 1 + len(self.g.layers) + 1      # gather + convolutions + heads
+        return 1 + len(self.g.layers) + (2 if self.h.heads_tc else 1)      # gather + convolutions + heads
 
     def hidden_state(self, slot):
         """pool[slot] as float32 [G, 128, H, W] (tests)."""
@@ -316,7 +324,7 @@ class MuZeroSearch(object):
 
     def kernels_per_move(self):
         nat = self.native
-        return (len(nat.h.layers) + 2) + self.cfg.num_simulations * (2 + nat.kernels_per_simulation())
+        return (len(nat.h.layers) + (3 if nat.h.heads_tc else 2)) + self.cfg.num_simulations * (2 + nat.kernels_per_simulation())
 
     # ------------------------------------------------------------------- search
     def run(self, rows, meta, legal=None, add_noise=True, use_graph=True, move_ids=None):

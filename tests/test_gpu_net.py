@@ -473,3 +473,47 @@ def test_row_stride_8_stem_bitboards_vs_planes_and_torch(size, n):
     lp1, v1 = (t.clone() for t in nf.forward_boards(rows, meta, n))
     lp3, v3 = nf.forward_planes(planes.cpu().numpy())
     assert torch.equal(lp3[:, :size * size], lp1[:, :size * size]) and torch.equal(v3, v1)
+
+
+@pytest.mark.parametrize('h,w,a,planes,n', [(15, 15, None, 4, 300), (15, 15, None, 4, 1), (19, 19, 362, 17, 131),
+                                            (6, 7, 7, 4, 257), (3, 3, None, 4, 5), (9, 9, None, 4, 128)])
+def test_heads_on_the_tensor_cores_match_the_fp32_heads(h, w, a, planes, n):
+    """rz_net_heads_tc (both FCs as one tcgen05 GEMM over the padded feature row, bf16 hi/lo split) against the
+    CUDA-core fp32 heads kernel on the same features: float32-level agreement (the split drops only the lo*lo
+    term), for every padded layout (S = 8 / 16 / 20), AS = 32 ... 384 (two N pieces for Go), partial last tile;
+    fused-head and separate-feature routes are bit-identical."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(h * 31 + n)
+    kw = dict(board_width=w, in_planes=planes)
+    if a is not None:
+        kw['n_actions'] = a
+    net = ResNetPolicyValueNet(h, n_blocks=1, **kw).cuda().eval()
+    with torch.no_grad():   # heads with some dynamic range: a peaked policy, a value away from 0
+        net.act_fc1.weight.mul_(8.0)
+        net.val_fc1.weight.mul_(4.0)
+        net.val_fc2.weight.mul_(4.0)
+    x = np.random.RandomState(n).randint(0, 2, size=(n, planes, h, w)).astype(np.float32)
+    tc = NativeForward(net, max_batch=n, heads_tc=True)
+    cc = NativeForward(net, max_batch=n, heads_tc=False)
+    assert tc.heads_tc and not cc.heads_tc
+    lt, vt = (t.clone() for t in tc.forward_planes(x))
+    lc, vc = (t.clone() for t in cc.forward_planes(x))
+    A = tc.A
+    assert torch.isfinite(lt).all() and torch.isfinite(vt).all()
+    # a few float32 ulps of the largest |log p| (the scaled heads reach ~30): two fp32 summation orders differ by that
+    assert (lt[:, :A] - lc[:, :A]).abs().max().item() < 1e-4, (lt[:, :A] - lc[:, :A]).abs().max().item()
+    assert (lt[:, :A].exp() - lc[:, :A].exp()).abs().max().item() < 1e-5
+    assert (vt - vc).abs().max().item() < 1e-5
+    assert torch.allclose(lt[:, :A].exp().sum(1), torch.ones(n, device='cuda'), atol=1e-4)
+    assert tc.logp[:n, A:].abs().max().item() == 0.0 if tc.AS > A else True
+    tb = NativeForward(net, max_batch=n, heads_tc=True, fused_head=False)
+    lb, vb = tb.forward_planes(x)
+    assert torch.equal(lb, lt) and torch.equal(vb, vt)
+    # against PyTorch fp32 end to end
+    ref = ResNetPolicyValueNet(h, n_blocks=1, **kw).eval()
+    ref.load_state_dict({k: t.cpu() for k, t in net.state_dict().items()})
+    with torch.no_grad():
+        lr, vr = ref(torch.from_numpy(x))
+    # (the scaled-up head weights amplify the bf16 error of the trunk: looser than the 1e-3 of the stock scale)
+    assert (lt[:, :A].exp().cpu() - lr.exp()).abs().max().item() < 1e-2
+    assert (vt.cpu() - vr.reshape(-1)).abs().max().item() < 2e-2
