@@ -97,7 +97,9 @@ enum rz_eval {                   /* closed-form evaluators, oracle/evaluators.py
 
 enum rz_child {                  /* values of edge child[] when N >= 1 */
   RZ_CHILD_TERMINAL = -1,        /* visited, game over there: never expanded (alphazero_mcts.py:60-68) */
-  RZ_CHILD_OVERFLOW = -2         /* visited, pool was full: re-evaluated like a leaf */
+  RZ_CHILD_OVERFLOW = -2,        /* visited, pool was full: re-evaluated like a leaf */
+  RZ_CHILD_PENDING = -3          /* leaf-parallel mode only: a playout of the current wave is in flight through
+                                    this never-visited edge (its visit count is virtual) */
 };
 
 /* ---- game geometry ------------------------------------------------------- */
@@ -170,6 +172,20 @@ typedef struct rz_tree_desc {
   int32_t* edge_O;               /* [G][max_nodes][AS] SearchNode.outcome of each child: 0 = None, else
                                     0x100 | (outcome[0]+1) | (outcome[1]+1) << 2 */
   int32_t* root_O;               /* [G] outcome of the root, same encoding */
+  /* leaf-parallel waves with virtual loss (opt-in, AlphaZero flavour; NOT the reference's sequential order --
+     leaves_per_tree <= 1 is the parity mode and ignores the other three fields).  Every tree runs up to K
+     playouts per wave: the warp that owns the tree descends K times in a row, and after each descent adds one
+     virtual visit and subtracts virtual_loss from the value sum of every edge on that path (no atomics needed:
+     one warp per tree), so the next descent is steered elsewhere.  rz_tree_expand_backup first restores the
+     edges exactly (saved value sums, reverse order), then expands and backs up the K leaves in order; a leaf
+     reached twice in one wave is expanded once and backed up twice.  All per-wave arrays (path_node,
+     path_action, depth, leaf_rows, leaf_meta, leaf_hist, the evaluator's prior / value) then hold G*K entries,
+     leaf slot = tree*K + k. */
+  int32_t leaves_per_tree;       /* K */
+  int32_t* target_N;             /* [G] or NULL: a tree takes no playout once root_N reaches target_N (so the last
+                                    wave of a search may be partial); a tree whose root is unexpanded takes one */
+  double* vl_saved_W;            /* [G*K][max_depth] scratch: the value sums the virtual losses overwrote */
+  double virtual_loss;           /* subtracted per in-flight playout (1.0 = a lost game for the mover) */
 } rz_tree_desc;
 
 /* ---- trajectory store (GameControl.start_self_play, game.py:96-134) ------- */

@@ -213,7 +213,13 @@ class Search(object):
     """AlphaZeroMCTS restated (alphazero_mcts.py:17-103)."""
 
     def __init__(self, policy_value_fn, n_playout=1000, c_puct=5,
-                 add_noise=False, rule=RULE_UCT, rng=None):
+                 add_noise=False, rule=RULE_UCT, rng=None, leaves_per_wave=1, virtual_loss=1.0):
+        # leaves_per_wave > 1: the product's opt-in leaf-parallel mode (rz_tree_desc.leaves_per_tree).  The
+        # reference has no such mode -- PARITY UNPINNED for it: `wave` below restates the product's own
+        # definition (include/rlzero_b200.h) so that the kernels can be checked bit for bit; with
+        # leaves_per_wave == 1 this class is the reference's sequential search.
+        self.leaves_per_wave = leaves_per_wave
+        self.virtual_loss = virtual_loss
         self.root = Node(None, 1.0)
         self.policy_value_fn = policy_value_fn
         self.n_playout = n_playout
@@ -237,9 +243,49 @@ class Search(object):
             v = 1.0 if winner == board.current_player() else -1.0
         node.backup(-v)
 
+    def wave(self, board, budget):
+        """`budget` playouts that share one evaluation batch: descend, put a virtual visit and a virtual loss on the
+        path, descend again ...; then take the virtual statistics off in reverse order (restoring the saved sums)
+        and expand / back up the leaves in order; a leaf reached twice is expanded once and backed up twice."""
+        leaves, undo = [], []
+        for _ in range(budget):
+            b = copy.deepcopy(board)
+            node, path = self.root, []
+            while node.children:
+                a, node = node.select(self.c_puct, self.rule)
+                b.step(a)
+                path.append(node)
+            leaves.append((b, node))
+            for nd in path:
+                undo.append((nd, nd.w))
+                nd.w = (nd.w - self.virtual_loss) if nd.n > 0 else -self.virtual_loss
+                nd.n += 1
+            self.root.n += 1
+        for nd, w in reversed(undo):
+            nd.w = w
+            nd.n -= 1
+        self.root.n -= budget
+        for b, node in leaves:
+            priors, v = self.policy_value_fn(b)
+            end, winner = b.game_end_winner()
+            if not end:
+                if not node.children:
+                    node.expand(priors, self.add_noise, self.rng)
+            elif winner == -1:
+                v = 0.0
+            else:
+                v = 1.0 if winner == b.current_player() else -1.0
+            node.backup(-v)
+
     def simulate(self, board, temperature=1e-3):  # alphazero_mcts.py:73-94
-        for _ in range(self.n_playout):
-            self.playout(copy.deepcopy(board))
+        if self.leaves_per_wave > 1:
+            target = self.root.n + self.n_playout
+            while self.root.n < target:
+                budget = min(self.leaves_per_wave, target - self.root.n)
+                self.wave(board, budget if self.root.children else 1)
+        else:
+            for _ in range(self.n_playout):
+                self.playout(copy.deepcopy(board))
         acts = tuple(self.root.children.keys())
         visits = np.array([ch.n for ch in self.root.children.values()])
         return acts, softmax(1.0 / temperature * np.log(visits + 1e-10))

@@ -23,7 +23,7 @@ RULE_UCT, RULE_PUCT = 0, 1
 FLAVOUR_ALPHAZERO, FLAVOUR_DEEPMIND = 0, 1
 RETURNS_REFERENCE, RETURNS_ZERO_SUM = 0, 1
 EVAL_ZERO, EVAL_KAT, EVAL_HASH = 0, 1, 2
-CHILD_TERMINAL, CHILD_OVERFLOW = -1, -2
+CHILD_TERMINAL, CHILD_OVERFLOW, CHILD_PENDING = -1, -2, -3
 MAX_BOARD = 19
 
 _vp = C.c_void_p
@@ -52,7 +52,9 @@ class TreeDesc(C.Structure):
                 ('leaf_rows', _vp), ('leaf_meta', _vp), ('ln_table', _vp),
                 ('root_hist', _vp), ('leaf_hist', _vp),
                 ('flavour', C.c_int32), ('solve', C.c_int32), ('returns_mode', C.c_int32),
-                ('noise_root_only', C.c_int32), ('edge_O', _vp), ('root_O', _vp)]
+                ('noise_root_only', C.c_int32), ('edge_O', _vp), ('root_O', _vp),
+                ('leaves_per_tree', C.c_int32), ('target_N', _vp), ('vl_saved_W', _vp),
+                ('virtual_loss', C.c_double)]
 
 
 class TrajDesc(C.Structure):

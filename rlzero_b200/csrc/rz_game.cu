@@ -194,8 +194,8 @@ rz_gomoku_encode_tc_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t*
 template <class GM>
 __global__ void __launch_bounds__(RZ_GAME_THREADS)
 rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* value) {
-  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
-  if (g >= t.n_trees) return;
+  const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);     // a leaf slot (tree*K + k in leaf-parallel mode)
+  if (g >= t.n_trees * (t.leaves_per_tree > 1 ? t.leaves_per_tree : 1)) return;
   if (t.depth[g] < 0) return;
   const rz_geom q = rz_geom_of(t.game);
   const int lane = rz_lane(), AS = t.game.action_stride;
@@ -475,6 +475,7 @@ extern "C" int rz_eval_rollout(const rz_tree_desc* t, int mode, unsigned long lo
   RZ_REQUIRE(n_limit >= 0, "rz_eval_rollout: n_limit %d", n_limit);
   RZ_REQUIRE(t->root_N && t->depth && t->leaf_rows && t->leaf_meta, "rz_eval_rollout: null tree array");
   RZ_REQUIRE(t->game.game_type != RZ_GAME_GO, "rz_eval_rollout: not implemented for Go");
+  RZ_REQUIRE(t->leaves_per_tree <= 1, "rz_eval_rollout: leaf-parallel waves are not supported by the rollout evaluator");
   if (t->n_trees == 0) return 0;
   rz_eval_rollout_kernel<<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
                            (cudaStream_t)stream>>>(*t, mode, seed, n_limit, prior, value);
@@ -488,11 +489,12 @@ extern "C" int rz_eval_closed_form(const rz_tree_desc* t, int eval_id, float* pr
   if (rz_check_game(&t->game)) return -1;
   RZ_REQUIRE(eval_id >= RZ_EVAL_ZERO && eval_id <= RZ_EVAL_HASH, "rz_eval_closed_form: eval_id %d", eval_id);
   if (t->n_trees == 0) return 0;
+  const int n_leaves = t->n_trees * (t->leaves_per_tree > 1 ? t->leaves_per_tree : 1);
   if (t->game.game_type == RZ_GAME_GO)
-    rz_eval_closed_form_kernel<rz_go_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+    rz_eval_closed_form_kernel<rz_go_game><<<rz_grid(n_leaves, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
                                              (cudaStream_t)stream>>>(*t, eval_id, prior, value);
   else
-    rz_eval_closed_form_kernel<rz_line_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
+    rz_eval_closed_form_kernel<rz_line_game><<<rz_grid(n_leaves, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
                                                (cudaStream_t)stream>>>(*t, eval_id, prior, value);
   RZ_LAUNCH_CHECK("rz_eval_closed_form");
   return 0;
@@ -506,6 +508,7 @@ extern "C" int rz_eval_rollout_dm(const rz_tree_desc* t, int n_rollouts, unsigne
   RZ_REQUIRE(n_limit >= 0, "rz_eval_rollout_dm: n_limit %d", n_limit);
   RZ_REQUIRE(t->root_N && t->depth && t->leaf_rows && t->leaf_meta, "rz_eval_rollout_dm: null tree array");
   RZ_REQUIRE(t->game.game_type != RZ_GAME_GO || t->leaf_hist, "rz_eval_rollout_dm: Go needs leaf_hist");
+  RZ_REQUIRE(t->leaves_per_tree <= 1, "rz_eval_rollout_dm: leaf-parallel waves are not supported by the rollout evaluator");
   if (t->n_trees == 0) return 0;
   if (t->game.game_type == RZ_GAME_GO)
     rz_eval_rollout_dm_kernel<rz_go_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,

@@ -19,7 +19,8 @@ namespace {
 
 // ---------------------------------------------------------------------------
 // fp32 conv3x3, NHWC: in [B][HW][Cin], w [9][Cin][Cout], out [B][HW][Cout]
-// one block per board; the input board sits in shared memory.
+// blockIdx.x = board, blockIdx.y = slice of the board's (position, output channel) pairs: a single game (the
+// reference API, batch 1) is spread over gridDim.y blocks instead of one SM; the input board sits in shared memory.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 rz_conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
@@ -30,7 +31,10 @@ rz_conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
   const float* ib = in + (size_t)b * HW * Cin;
   for (int i = threadIdx.x; i < HW * Cin; i += blockDim.x) s_in[i] = ib[i];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < HW * Cout; idx += blockDim.x) {
+  const int total = HW * Cout;
+  const int per = (total + gridDim.y - 1) / gridDim.y;
+  const int lo = blockIdx.y * per, hi = min(total, lo + per);
+  for (int idx = lo + threadIdx.x; idx < hi; idx += blockDim.x) {
     const int co = idx % Cout, pos = idx / Cout;
     const int y = pos / H, x = pos - y * H;
     float acc = bias[co];
@@ -352,8 +356,14 @@ extern "C" int rz_net_conv3x3_f32(const float* in, const float* weight, const fl
   if (n_boards == 0) return 0;
   cudaError_t e = cudaFuncSetAttribute(rz_conv3x3_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_f32: smem attribute: %s", cudaGetErrorString(e)); return -2; }
-  rz_conv3x3_f32_kernel<<<n_boards, 256, smem, (cudaStream_t)stream>>>(in, weight, bias, residual, out,
-                                                                      board_size, c_in, c_out, relu);
+  // few boards (the single-game API): split each board over several blocks so that the grid covers the 148 SMs
+  int split = (2 * 148 + n_boards - 1) / n_boards;
+  const int max_split = (board_size * board_size * c_out + 255) / 256;
+  if (split > max_split) split = max_split;
+  if (split > 64) split = 64;
+  if (split < 1) split = 1;
+  rz_conv3x3_f32_kernel<<<dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream>>>(
+      in, weight, bias, residual, out, board_size, c_in, c_out, relu);
   RZ_LAUNCH_CHECK("rz_net_conv3x3_f32");
   return 0;
 }

@@ -51,20 +51,13 @@ __device__ __forceinline__ int rz_outcome_of(int code, int player) { return ((co
 // ---------------------------------------------------------------------------
 // K1: select.  One playout descent per tree + leaf terminal test.
 // ---------------------------------------------------------------------------
+// one descent of tree g; its path / leaf go to wave slot L (= g in the parity mode, g*K + k in leaf-parallel mode)
 template <class GM, bool DM>
-__global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc t) {
-  const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
-  if (g >= t.n_trees) return;
+__device__ __forceinline__ void rz_select_one(const rz_tree_desc& t, const int g, const int L, const rz_geom& q,
+                                              int32_t* rmeta) {
   const int lane = rz_lane();
-  const rz_geom q = rz_geom_of(t.game);
   const int AS = t.game.action_stride;
   const int iters = AS >> 5;
-  int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
-  // a finished game, or (DeepMindMCTS) a proven root: `if root.outcome is not None: break` (:643-644)
-  if (rmeta[RZ_META_STATUS] != RZ_ACTIVE || (DM && t.root_O[g] != 0)) {
-    if (lane == 0) t.depth[g] = -1;
-    return;
-  }
   typename GM::board b;
   GM::load_root(b, t, g);
   const int root_player = b.player;
@@ -74,13 +67,13 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
   int node = 0;
   int Np = t.root_N[g];
   bool descend = t.n_nodes[g] > 0;
-  int32_t* pnode = t.path_node + (size_t)g * t.max_depth;
-  int32_t* pact = t.path_action + (size_t)g * t.max_depth;
+  int32_t* pnode = t.path_node + (size_t)L * t.max_depth;
+  int32_t* pact = t.path_action + (size_t)L * t.max_depth;
 
   while (descend) {
     if (depth >= t.max_depth) { fault |= RZ_FAULT_DEPTH_OVERFLOW; break; }
     const size_t base = rz_edge_base(t, g, node);
-    const int32_t* __restrict__ eN = t.edge_N + base;
+    const int32_t* eN = t.edge_N + base;
     // pass 1: visit counts (coalesced, all loads in flight at once)
     int nv[RZ_MAX_ITERS];
 #pragma unroll
@@ -93,7 +86,7 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
     int oc[RZ_MAX_ITERS];
     const int mover = root_player ^ (depth & 1);
     if (DM) {
-      const int32_t* __restrict__ eO = t.edge_O + base;
+      const int32_t* eO = t.edge_O + base;
 #pragma unroll
       for (int i = 0; i < RZ_MAX_ITERS; ++i) oc[i] = (i < iters && nv[i] > 0) ? eO[lane + 32 * i] : 0;
     }
@@ -112,7 +105,7 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
         best_n = eN[cand];
       } else {
         // every child visited: W/n + c*sqrt(ln(Np)/n)   (node.py:82-88)
-        const double* __restrict__ eW = t.edge_W + base;
+        const double* eW = t.edge_W + base;
         double wv[RZ_MAX_ITERS];
 #pragma unroll
         for (int i = 0; i < RZ_MAX_ITERS; ++i)
@@ -135,8 +128,8 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
       }
     } else {
       // deepmind_mcts.py:149-151: (n and W/n) + ((c*P)*sqrt(Np))/(n+1)
-      const double* __restrict__ eW = t.edge_W + base;
-      const float* __restrict__ eP = t.edge_P + base;
+      const double* eW = t.edge_W + base;
+      const float* eP = t.edge_P + base;
       const double sq = __dsqrt_rn((double)Np);
 #pragma unroll
       for (int i = 0; i < RZ_MAX_ITERS; ++i) {
@@ -167,17 +160,64 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc
   // leaf: game_end_winner() (alphazero_mcts.py:60)
   int winner;
   const int status = GM::status(b, q, winner);
-  GM::store_leaf(b, t, g);
+  GM::store_leaf(b, t, L);
   if (lane == 0) {
-    int32_t* lm = t.leaf_meta + (size_t)g * RZ_META_STRIDE;
+    int32_t* lm = t.leaf_meta + (size_t)L * RZ_META_STRIDE;
     GM::store_meta(b, lm);
     lm[RZ_META_STATUS] = status;
     lm[RZ_META_WINNER] = winner;
     lm[RZ_META_PLY] = depth;
     lm[RZ_META_FAULT] = fault;
     lm[RZ_META_EPISODE] = rmeta[RZ_META_EPISODE];
-    t.depth[g] = depth;
+    t.depth[L] = depth;
     if (fault) rmeta[RZ_META_FAULT] |= fault;
+  }
+}
+
+template <class GM, bool DM>
+__global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc t) {
+  const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  const int lane = rz_lane();
+  const rz_geom q = rz_geom_of(t.game);
+  const int K = t.leaves_per_tree > 1 ? t.leaves_per_tree : 1;
+  int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
+  // a finished game, or (DeepMindMCTS) a proven root: `if root.outcome is not None: break` (:643-644)
+  if (rmeta[RZ_META_STATUS] != RZ_ACTIVE || (DM && t.root_O[g] != 0)) {
+    for (int k = lane; k < K; k += 32) t.depth[(size_t)g * K + k] = -1;
+    return;
+  }
+  if (K == 1) {                      // the parity mode: the reference's strictly sequential playouts
+    rz_select_one<GM, DM>(t, g, g, q, rmeta);
+    return;
+  }
+  // leaf-parallel wave: up to K descents, each followed by its virtual loss (see rz_tree_desc.leaves_per_tree)
+  int budget = K;
+  if (t.target_N) budget = min(budget, t.target_N[g] - t.root_N[g]);
+  if (t.n_nodes[g] == 0) budget = min(budget, 1);      // the first playout only expands the root
+  for (int k = 0; k < K; ++k) {
+    const int L = g * K + k;
+    if (k >= budget) {
+      if (lane == 0) t.depth[L] = -1;
+      continue;
+    }
+    rz_select_one<GM, DM>(t, g, L, q, rmeta);
+    __syncwarp();
+    const int depth = t.depth[L];
+    const int32_t* pnode = t.path_node + (size_t)L * t.max_depth;
+    const int32_t* pact = t.path_action + (size_t)L * t.max_depth;
+    double* saved = t.vl_saved_W + (size_t)L * t.max_depth;
+    for (int i = lane; i < depth; i += 32) {
+      const size_t e = rz_edge_base(t, g, pnode[i]) + pact[i];
+      const int n = t.edge_N[e];
+      const double w = t.edge_W[e];
+      saved[i] = w;
+      t.edge_W[e] = n > 0 ? __dadd_rn(w, -t.virtual_loss) : -t.virtual_loss;
+      t.edge_N[e] = n + 1;
+      if (n == 0) t.edge_child[e] = RZ_CHILD_PENDING;   // visited only virtually: a later descent stops here
+    }
+    if (lane == 0) t.root_N[g] += 1;
+    __syncwarp();
   }
 }
 
@@ -210,24 +250,22 @@ __device__ float rz_gamma_draw(float alpha, unsigned long long seed, uint32_t c0
 // ---------------------------------------------------------------------------
 // K5+K6: expand the leaf (unless terminal) and back the value up the path.
 // ---------------------------------------------------------------------------
+// leaf slot L of tree g (L = g in the parity mode).  `dedup`: leaf-parallel mode, where a leaf may have been
+// expanded by an earlier playout of the same wave.
 template <class GM, bool DM>
-__global__ void __launch_bounds__(RZ_TREE_THREADS)
-rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int prior_is_log,
-                        const float* __restrict__ value, const double* __restrict__ value64,
-                        float noise_eps, float noise_alpha,
-                        unsigned long long seed, long long global_offset) {
-  const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
-  if (g >= t.n_trees) return;
-  const int depth = t.depth[g];
+__device__ __forceinline__ void
+rz_expand_backup_one(const rz_tree_desc& t, const int g, const int L, const bool dedup, const rz_geom& q,
+                     const float* prior, int prior_is_log, const float* value, const double* value64,
+                     float noise_eps, float noise_alpha, unsigned long long seed, long long global_offset) {
+  const int depth = t.depth[L];
   if (depth < 0) return;
   const int lane = rz_lane();
-  const rz_geom q = rz_geom_of(t.game);
   const int AS = t.game.action_stride;
-  const int32_t* lm = t.leaf_meta + (size_t)g * RZ_META_STRIDE;
+  const int32_t* lm = t.leaf_meta + (size_t)L * RZ_META_STRIDE;
   const int32_t* rm = t.root_meta + (size_t)g * RZ_META_STRIDE;
   const int status = lm[RZ_META_STATUS];
-  int32_t* pnode = t.path_node + (size_t)g * t.max_depth;
-  int32_t* pact = t.path_action + (size_t)g * t.max_depth;
+  int32_t* pnode = t.path_node + (size_t)L * t.max_depth;
+  int32_t* pact = t.path_action + (size_t)L * t.max_depth;
 
   // alphazero_mcts.py:59-68: network value unless the game is over at the leaf
   double v;
@@ -240,13 +278,18 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
     v = 0.0;
     child_mark = RZ_CHILD_TERMINAL; have_mark = true;
   } else {
-    v = value64 ? value64[g] : (double)value[g];
+    v = value64 ? value64[L] : (double)value[L];
     const int nn = t.n_nodes[g];
-    if (nn < t.max_nodes) {
+    // leaf-parallel mode: an earlier playout of this wave reached the same leaf and expanded it already
+    const bool expanded_already =
+        dedup && (depth > 0 ? t.edge_child[rz_edge_base(t, g, pnode[depth - 1]) + pact[depth - 1]] >= 0 : nn > 0);
+    if (expanded_already) {
+      // back the (identical) evaluation up once more, nothing to create
+    } else if (nn < t.max_nodes) {
       // node.py:71-73: one child per legal move, in ascending action order
-      const uint32_t lctx = GM::legal_ctx(t, g, q);
+      const uint32_t lctx = GM::legal_ctx(t, L, q);
       const size_t nb = rz_edge_base(t, g, nn);
-      const float* pr = prior + (size_t)g * AS;
+      const float* pr = prior + (size_t)L * AS;
       float noise_sum = 0.0f;
       float nz[RZ_MAX_ITERS];
       const bool noisy = noise_eps > 0.0f && !(DM && t.noise_root_only && depth > 0);
@@ -313,7 +356,7 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
       ret[0] = (double)r0; ret[1] = (double)r1;
       code = rz_outcome_enc(r0, r1);
     } else if (value64) {                  // here: the evaluator's returns vector [G][2]
-      ret[0] = value64[2 * g]; ret[1] = value64[2 * g + 1];
+      ret[0] = value64[2 * L]; ret[1] = value64[2 * L + 1];
     } else {
       const int pl = lm[RZ_META_PLAYER] & 1;
       ret[pl] = v; ret[pl ^ 1] = -v;
@@ -383,6 +426,46 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
       t.root_W[g] = __dadd_rn(t.root_W[g], x);
       t.root_N[g] += 1;
     }
+  }
+}
+
+template <class GM, bool DM>
+__global__ void __launch_bounds__(RZ_TREE_THREADS)
+rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int prior_is_log,
+                        const float* __restrict__ value, const double* __restrict__ value64,
+                        float noise_eps, float noise_alpha,
+                        unsigned long long seed, long long global_offset) {
+  const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  const rz_geom q = rz_geom_of(t.game);
+  const int K = t.leaves_per_tree > 1 ? t.leaves_per_tree : 1;
+  if (K == 1) {
+    rz_expand_backup_one<GM, DM>(t, g, g, false, q, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed,
+                                 global_offset);
+    return;
+  }
+  // leaf-parallel wave: take the virtual losses off again -- the saved value sums in reverse order of application,
+  // so every edge returns to its exact pre-wave bits -- then expand and back up the K leaves in order
+  const int lane = rz_lane();
+  for (int k = K - 1; k >= 0; --k) {
+    const int L = g * K + k;
+    const int depth = t.depth[L];
+    if (depth < 0) continue;
+    const int32_t* pnode = t.path_node + (size_t)L * t.max_depth;
+    const int32_t* pact = t.path_action + (size_t)L * t.max_depth;
+    const double* saved = t.vl_saved_W + (size_t)L * t.max_depth;
+    for (int i = lane; i < depth; i += 32) {
+      const size_t e = rz_edge_base(t, g, pnode[i]) + pact[i];
+      t.edge_W[e] = saved[i];
+      t.edge_N[e] -= 1;
+    }
+    if (lane == 0) t.root_N[g] -= 1;
+    __syncwarp();
+  }
+  for (int k = 0; k < K; ++k) {
+    rz_expand_backup_one<GM, DM>(t, g, g * K + k, true, q, prior, prior_is_log, value, value64, noise_eps, noise_alpha,
+                                 seed, global_offset);
+    __syncwarp();
   }
 }
 
@@ -766,6 +849,14 @@ static int rz_check_tree(const rz_tree_desc* t, const char* who) {
              "%s: the DeepMindMCTS flavour needs the outcome arrays edge_O / root_O", who);
   RZ_REQUIRE(t->returns_mode == RZ_RETURNS_REFERENCE || t->returns_mode == RZ_RETURNS_ZERO_SUM,
              "%s: returns_mode %d", who, t->returns_mode);
+  RZ_REQUIRE(t->leaves_per_tree >= 0 && t->leaves_per_tree <= 256, "%s: leaves_per_tree %d outside [0,256]", who,
+             t->leaves_per_tree);
+  if (t->leaves_per_tree > 1) {
+    RZ_REQUIRE(t->flavour == RZ_FLAVOUR_ALPHAZERO, "%s: leaf-parallel waves (leaves_per_tree %d) need the AlphaZero flavour",
+               who, t->leaves_per_tree);
+    RZ_REQUIRE(t->vl_saved_W, "%s: leaves_per_tree %d needs the vl_saved_W scratch", who, t->leaves_per_tree);
+    RZ_REQUIRE(t->virtual_loss >= 0.0, "%s: virtual_loss %f", who, t->virtual_loss);
+  }
   return 0;
 }
 

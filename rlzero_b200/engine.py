@@ -48,8 +48,13 @@ class SearchForest(object):
                  device='cuda', global_offset=0, ln_table_len=None, with_trajectories=False,
                  ring_capacity=None, board_width=None, game_type=L.GAME_GOMOKU, komi=7.5, max_moves=0,
                  flavour=L.FLAVOUR_ALPHAZERO, solve=False, returns_mode=L.RETURNS_REFERENCE,
-                 noise_root_only=False):
-        """``flavour = L.FLAVOUR_DEEPMIND`` runs the reference's second search driver, DeepMindMCTS
+                 noise_root_only=False, leaves_per_tree=1, virtual_loss=1.0):
+        """``leaves_per_tree = K > 1`` switches to leaf-parallel waves with virtual loss (opt-in; not the
+        reference's sequential order, see ``rz_tree_desc.leaves_per_tree``): every wave runs up to K playouts per
+        tree and the evaluator sees ``n_leaves = G*K`` positions -- for a handful of games (the single-game API)
+        this is what fills the network batch.  ``K = 1`` is the parity mode.
+
+        ``flavour = L.FLAVOUR_DEEPMIND`` runs the reference's second search driver, DeepMindMCTS
         (rlzero/mcts/deepmind_mcts.py:384-646): returns vectors, outcome shortcut, terminal outcomes,
         ``solve`` (MCTS-Solver), root-only noise, early stop on a proven root."""
         if not torch.cuda.is_available():
@@ -57,6 +62,11 @@ class SearchForest(object):
         self.lib = L.load()
         self.device = torch.device(device)
         self.G = int(n_trees)
+        self.K = max(1, int(leaves_per_tree))
+        self.n_leaves = self.G * self.K
+        self.virtual_loss = float(virtual_loss)
+        if self.K > 1 and int(flavour) != L.FLAVOUR_ALPHAZERO:
+            raise ValueError('leaf-parallel waves (leaves_per_tree > 1) need the AlphaZero flavour')
         self.H = int(board_size)
         self.W = self.H if board_width is None else int(board_width)
         self.k = int(n_in_row)
@@ -100,14 +110,17 @@ class SearchForest(object):
         self.root_W = torch.zeros(G, dtype=f64, device=dev)
         self.root_rows = torch.zeros(G, 2, H, dtype=i32, device=dev)
         self.root_meta = torch.zeros(G, L.META_STRIDE, dtype=i32, device=dev)
-        self.path_node = torch.zeros(G, self.max_depth, dtype=i32, device=dev)
-        self.path_action = torch.zeros(G, self.max_depth, dtype=i32, device=dev)
-        self.depth = torch.full((G,), -1, dtype=i32, device=dev)
-        self.leaf_rows = torch.zeros(G, 2, H, dtype=i32, device=dev)
-        self.leaf_meta = torch.zeros(G, L.META_STRIDE, dtype=i32, device=dev)
+        NL = self.n_leaves      # wave slots: one per tree, or K per tree in leaf-parallel mode
+        self.path_node = torch.zeros(NL, self.max_depth, dtype=i32, device=dev)
+        self.path_action = torch.zeros(NL, self.max_depth, dtype=i32, device=dev)
+        self.depth = torch.full((NL,), -1, dtype=i32, device=dev)
+        self.leaf_rows = torch.zeros(NL, 2, H, dtype=i32, device=dev)
+        self.leaf_meta = torch.zeros(NL, L.META_STRIDE, dtype=i32, device=dev)
+        self.vl_saved_W = torch.zeros(NL * self.max_depth, dtype=f64, device=dev) if self.K > 1 else None
+        self.target_N = torch.full((G,), 2 ** 31 - 1, dtype=i32, device=dev) if self.K > 1 else None
         # Go: board_history planes 2..15 of every root / leaf position (go_env.py:174-178)
         self.root_hist = torch.zeros(G, L.GO_HIST, H, dtype=i32, device=dev) if self.is_go else None
-        self.leaf_hist = torch.zeros(G, L.GO_HIST, H, dtype=i32, device=dev) if self.is_go else None
+        self.leaf_hist = torch.zeros(NL, L.GO_HIST, H, dtype=i32, device=dev) if self.is_go else None
         self.flavour = int(flavour)
         self.is_dm = self.flavour == L.FLAVOUR_DEEPMIND
         self.edge_O = torch.zeros(n_edges, dtype=i32, device=dev) if self.is_dm else None
@@ -116,8 +129,8 @@ class SearchForest(object):
         n_ln = int(ln_table_len) if ln_table_len else max(1 << 16, 4 * self.n_playout + 2)
         self.ln_table = torch.from_numpy(ln_table(n_ln)).to(dev)
         # evaluator outputs for one wave
-        self.prior = torch.zeros(G, AS, dtype=f32, device=dev)
-        self.value = torch.zeros(G, dtype=f32, device=dev)
+        self.prior = torch.zeros(NL, AS, dtype=f32, device=dev)
+        self.value = torch.zeros(NL, dtype=f32, device=dev)
         # root policy outputs
         self.visits = torch.zeros(G, AS, dtype=i32, device=dev)
         self.pi = torch.zeros(G, AS, dtype=f32, device=dev)
@@ -141,6 +154,10 @@ class SearchForest(object):
         d.noise_root_only = int(bool(noise_root_only))
         d.edge_O = self.edge_O.data_ptr() if self.is_dm else None
         d.root_O = self.root_O.data_ptr() if self.is_dm else None
+        d.leaves_per_tree = self.K
+        d.target_N = self.target_N.data_ptr() if self.K > 1 else None
+        d.vl_saved_W = self.vl_saved_W.data_ptr() if self.K > 1 else None
+        d.virtual_loss = self.virtual_loss
         self.desc = d
         self.traj = None
         self.tdesc = None
@@ -311,7 +328,16 @@ class SearchForest(object):
             g.replay()
 
     def search(self, evaluator, n_playout=None, **kw):
-        self.run_waves(self.n_playout if n_playout is None else n_playout, evaluator, **kw)
+        """``n_playout`` playouts for every tree (``AlphaZeroMCTS.simulate``, alphazero_mcts.py:83-85).  In
+        leaf-parallel mode each tree stops at exactly ``n_playout`` more root visits: the first wave of a fresh
+        tree only expands the root, the last wave may be partial."""
+        n = self.n_playout if n_playout is None else int(n_playout)
+        if self.K == 1:
+            self.run_waves(n, evaluator, **kw)
+            return
+        torch.add(self.root_N, n, out=self.target_N)
+        self.run_waves(1 + (max(n - 1, 0) + self.K - 1) // self.K, evaluator, **kw)
+        self.target_N.fill_(2 ** 31 - 1)
 
     # ---------------------------------------------------------------- readback
     def faults(self):
@@ -447,11 +473,11 @@ class HostCallbackEvaluator(object):
 
     def __call__(self, forest):
         rows, meta, depth = forest.leaf_boards()
-        prior = np.zeros((forest.G, forest.AS), dtype=np.float32)
-        value = np.zeros(forest.G, dtype=np.float64)
+        prior = np.zeros((forest.n_leaves, forest.AS), dtype=np.float32)
+        value = np.zeros(forest.n_leaves, dtype=np.float64)
         if self.value64 is None:
-            self.value64 = torch.zeros(forest.G, dtype=torch.float64, device=forest.device)
-        for g in range(forest.G):
+            self.value64 = torch.zeros(forest.n_leaves, dtype=torch.float64, device=forest.device)
+        for g in range(forest.n_leaves):
             if depth[g] < 0:
                 continue
             env = self.env_factory(rows[g], meta[g])

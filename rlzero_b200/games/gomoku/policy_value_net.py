@@ -457,5 +457,5 @@ class NativeForward(object):
 
     def __call__(self, forest):
         """Evaluator protocol of engine.SearchForest.run_waves: evaluate the wave's leaves."""
-        self.forward_boards(forest.leaf_rows, forest.leaf_meta, forest.G, forest.prior, forest.value,
+        self.forward_boards(forest.leaf_rows, forest.leaf_meta, forest.n_leaves, forest.prior, forest.value,
                             hist=getattr(forest, 'leaf_hist', None))

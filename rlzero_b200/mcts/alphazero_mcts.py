@@ -41,11 +41,11 @@ class _NumpyNoiseCallback(HostCallbackEvaluator):
 
     def __call__(self, forest):
         rows, meta, depth = forest.leaf_boards()
-        prior = np.zeros((forest.G, forest.AS), dtype=np.float32)
-        value = np.zeros(forest.G, dtype=np.float64)
+        prior = np.zeros((forest.n_leaves, forest.AS), dtype=np.float32)
+        value = np.zeros(forest.n_leaves, dtype=np.float64)
         if self.value64 is None:
-            self.value64 = torch.zeros(forest.G, dtype=torch.float64, device=forest.device)
-        for g in range(forest.G):
+            self.value64 = torch.zeros(forest.n_leaves, dtype=torch.float64, device=forest.device)
+        for g in range(forest.n_leaves):
             if depth[g] < 0:
                 continue
             env = self.env_factory(rows[g], meta[g])
@@ -69,7 +69,12 @@ class AlphaZeroMCTS(object):
     """An implementation of Monte Carlo Tree Search (GPU trees, reference API)."""
 
     def __init__(self, policy_value_fn, n_playout=1000, c_puct=5, add_noise=False,
-                 rule=L.RULE_UCT, device='cuda'):
+                 rule=L.RULE_UCT, device='cuda', leaves_per_wave=1, virtual_loss=1.0):
+        """``leaves_per_wave = K > 1`` (an extension, not in the reference): leaf-parallel search with virtual loss --
+        K playouts of this one tree share a network batch.  Faster for a single game, but no longer the reference's
+        sequential playout order (visit counts differ); the default 1 is bit-exact."""
+        self.leaves_per_wave = max(1, int(leaves_per_wave))
+        self.virtual_loss = float(virtual_loss)
         self.policy_value_fn = policy_value_fn
         self.n_playout = n_playout
         self._c_puct = c_puct
@@ -88,12 +93,14 @@ class AlphaZeroMCTS(object):
         width = getattr(env, 'board_width', env.board_size)
         game_type = getattr(env, 'game_type', L.GAME_GOMOKU)
         if (f is not None and f.H == env.board_size and f.W == width and f.game_type == game_type
-                and f.k == env.n_in_row and self.n_playout <= f.n_playout and f.c_puct == float(self._c_puct)):
+                and f.k == env.n_in_row and self.n_playout <= f.n_playout and f.c_puct == float(self._c_puct)
+                and f.K == self.leaves_per_wave):
             return f     # n_playout may be lowered between moves (the pools were sized for the larger one)
         carry = 64 if self.rule == L.RULE_UCT else self.n_playout
         self._forest = SearchForest(1, env.board_size, env.n_in_row, n_playout=self.n_playout,
                                     c_puct=self._c_puct, rule=self.rule, max_carry=carry,
-                                    device=self.device, board_width=width, game_type=game_type)
+                                    device=self.device, board_width=width, game_type=game_type,
+                                    leaves_per_tree=self.leaves_per_wave, virtual_loss=self.virtual_loss)
         native = getattr(self, '_native_evaluator', None)
         if native is None:
             native = getattr(self.policy_value_fn, 'device_evaluator', None)
@@ -138,7 +145,7 @@ class AlphaZeroMCTS(object):
         native = getattr(self._evaluator, 'graph_capturable', False)
         eps = 0.25 if (self.add_noise and native) else 0.0  # callback path mixes noise on the host
         self._seed += 1
-        f.run_waves(n, self._evaluator, noise_eps=eps, noise_alpha=0.3, seed=self._seed)
+        f.search(self._evaluator, n, noise_eps=eps, noise_alpha=0.3, seed=self._seed)
         self._snap = None
         f.raise_faults()
 
@@ -181,12 +188,14 @@ class AlphaZeroPlayer(Player):
     """AI player based on MCTS (alphazero_mcts.py:109-165)."""
 
     def __init__(self, policy_value_fn, n_playout=1000, c_puct=5, is_selfplay=False,
-                 player_id=0, player_name='', rule=L.RULE_UCT, device='cuda'):
+                 player_id=0, player_name='', rule=L.RULE_UCT, device='cuda', leaves_per_wave=1,
+                 virtual_loss=1.0):
         super().__init__(player_id, player_name)
         self.is_selfplay = is_selfplay
         self.add_noise = is_selfplay
         self.mcts = AlphaZeroMCTS(policy_value_fn, n_playout=n_playout, c_puct=c_puct,
-                                  add_noise=self.add_noise, rule=rule, device=device)
+                                  add_noise=self.add_noise, rule=rule, device=device,
+                                  leaves_per_wave=leaves_per_wave, virtual_loss=virtual_loss)
 
     def reset_player(self):
         """reset, reconstructing the MCTS Tree for next simulation."""

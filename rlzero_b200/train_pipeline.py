@@ -105,7 +105,9 @@ def augment_equi_device(forest_or_desc, rows, info, pi):
 class TrainPipeline(object):
 
     def __init__(self, board_size=6, n_in_row=4, n_playout=400, n_parallel_games=1, device='cuda', net=None,
-                 game_batch_num=64, check_freq=50, pure_mcts_playout_num=100):
+                 game_batch_num=64, check_freq=50, pure_mcts_playout_num=100, leaves_per_wave=1):
+        # leaves_per_wave > 1: leaf-parallel self-play search of the single-game path (an extension; the default is
+        # the reference's sequential search)
         # params of the board and the game (tools/train_alphazero.py:19-26)
         self.board_size = board_size
         self.n_in_row = n_in_row
@@ -130,7 +132,7 @@ class TrainPipeline(object):
         self.pure_mcts_playout_num = pure_mcts_playout_num
         self.alphazero_agent = AlphaZeroAgent(self.board_size, device=self.device, net=net)
         self.mcts_player = AlphaZeroPlayer(self.alphazero_agent.policy_value_fn, n_playout=self.n_playout,
-                                           c_puct=self.c_puct, is_selfplay=True)
+                                           c_puct=self.c_puct, is_selfplay=True, leaves_per_wave=leaves_per_wave)
         # batched collection
         self.n_parallel_games = int(n_parallel_games)
         self.selfplay = None
