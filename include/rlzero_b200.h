@@ -266,7 +266,9 @@ int rz_go_encode_f32(const rz_game_desc* g, const uint32_t* rows, const uint32_t
 /* fresh trees: _root = TreeNode(None, 1.0) (alphazero_mcts.py:36).  tree_mask NULL = all. */
 int rz_tree_reset(const rz_tree_desc* t, const uint8_t* tree_mask, void* stream);
 /* descent of one playout per tree (alphazero_mcts.py:48-54 + node.py:32-42,75-88 +
-   gomoku_env.py:49-70), then game_end_winner on the leaf (alphazero_mcts.py:60). */
+   gomoku_env.py:49-70), then game_end_winner on the leaf (alphazero_mcts.py:60).  With
+   t->leaves_per_tree = K > 1: up to K descents per tree, each followed by its virtual loss
+   (see rz_tree_desc); the wave arrays hold G*K slots. */
 int rz_tree_select(const rz_tree_desc* t, void* stream);
 /* expand (node.py:44-73) + terminal value rule (alphazero_mcts.py:60-68) + sign-flipping
    backup (node.py:135-144).  prior: [G][AS] float32; prior_is_log != 0 means it holds
@@ -274,7 +276,8 @@ int rz_tree_select(const rz_tree_desc* t, void* stream);
    network's output type); value64 != NULL overrides it with [G] float64 (a Python
    policy_value_fn returns a Python float, alphazero_mcts.py:59).
    noise_eps > 0 mixes Dirichlet(noise_alpha) noise into every expanded node
-   (node.py:63-69, eps = 0.25, alpha = 0.3), counter-based RNG keyed by (seed, game, node). */
+   (node.py:63-69, eps = 0.25, alpha = 0.3), counter-based RNG keyed by (seed, game, node).
+   Leaf-parallel mode: prior [G*K][AS], value [G*K]; the virtual losses of the wave are taken off first. */
 int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, int prior_is_log,
                           const float* value, const double* value64, float noise_eps, float noise_alpha,
                           unsigned long long seed, void* stream);
