@@ -54,6 +54,17 @@ class AlphaZeroAgent(object):
         logp, value = self.native.forward_planes(np.array(state_batch))
         return np.exp(logp.cpu().numpy()), value.cpu().numpy().reshape(-1, 1)
 
+    def policy_value_device(self, state_batch):
+        """``policy_value`` for a device tensor [B,4,H,W], results left on the device (the batched training
+        path: mini-batches gathered from the device replay buffer never visit the host)."""
+        logp, value = self.native.forward_planes(state_batch)
+        return torch.exp(logp).clone(), value.reshape(-1, 1).clone()
+
+    def _f32(self, x):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=torch.float32)
+        return torch.FloatTensor(np.array(x)).to(self.device)
+
     def predict(self, state_batch):
         """(:88-97)"""
         return self.policy_value(state_batch)
@@ -63,9 +74,9 @@ class AlphaZeroAgent(object):
         net = self.policy_value_net
         net.train()
         dev = self.device
-        state_batch = torch.FloatTensor(np.array(state_batch)).to(dev)
-        mcts_probs = torch.FloatTensor(np.array(mcts_probs)).to(dev)
-        target_batch = torch.FloatTensor(np.array(target_vs)).to(dev)
+        state_batch = self._f32(state_batch)          # lists / numpy as in the reference, or device tensors
+        mcts_probs = self._f32(mcts_probs)
+        target_batch = self._f32(target_vs)
         log_act_probs, value = net(state_batch)
         value_loss = F.mse_loss(value.view(-1), target_batch)
         policy_loss = -torch.mean(torch.sum(mcts_probs * log_act_probs, dim=1))

@@ -193,8 +193,7 @@ class TrainPipeline(object):
     def policy_update(self):
         """update the policy-value net (:92-137)."""
         if self.n_parallel_games > 1:
-            sb, pb, zb = self.device_buffer.sample(self.batch_size)
-            state_batch, mcts_probs_batch, winner_batch = sb.cpu().numpy(), pb.cpu().numpy(), zb.cpu().numpy()
+            return self._policy_update_device()
         else:
             mini_batch = random.sample(self.data_buffer, self.batch_size)
             state_batch = [data[0] for data in mini_batch]
@@ -219,6 +218,32 @@ class TrainPipeline(object):
                'explained_var_new:{:.3f}').format(kl, self.lr_multiplier, loss, entropy, explained_var_old,
                                                   explained_var_new))
         self.last_kl = float(kl)
+        return loss, entropy
+
+    def _policy_update_device(self):
+        """The same update (:92-137) on a mini-batch gathered from the device replay buffer: states, targets, the
+        KL early-stop test and the explained variances stay in HBM; only the printed scalars reach the host."""
+        agent = self.alphazero_agent
+        state_batch, mcts_probs_batch, winner_batch = self.device_buffer.sample(self.batch_size)
+        old_probs, old_v = agent.policy_value_device(state_batch)
+        for i in range(self.epochs):
+            loss, entropy = agent.learn(state_batch, mcts_probs_batch, winner_batch)
+            new_probs, new_v = agent.policy_value_device(state_batch)
+            kl = float(torch.mean(torch.sum(old_probs * (torch.log(old_probs + 1e-10) - torch.log(new_probs + 1e-10)),
+                                            dim=1)).item())
+            if kl > self.kl_targ * 4:  # early stopping if D_KL diverges badly
+                break
+        if kl > self.kl_targ * 2 and self.lr_multiplier > 0.1:
+            self.lr_multiplier /= 1.5
+        elif kl < self.kl_targ / 2 and self.lr_multiplier < 10:
+            self.lr_multiplier *= 1.5
+        var_z = torch.var(winner_batch, unbiased=False)      # np.var is the population variance
+        explained_var_old = float((1 - torch.var(winner_batch - old_v.flatten(), unbiased=False) / var_z).item())
+        explained_var_new = float((1 - torch.var(winner_batch - new_v.flatten(), unbiased=False) / var_z).item())
+        print(('kl:{:.5f},lr_multiplier:{:.3f},loss:{},entropy:{},explained_var_old:{:.3f},'
+               'explained_var_new:{:.3f}').format(kl, self.lr_multiplier, loss, entropy, explained_var_old,
+                                                  explained_var_new))
+        self.last_kl = kl
         return loss, entropy
 
     def policy_evaluate(self, n_games=10):

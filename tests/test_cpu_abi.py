@@ -136,3 +136,24 @@ def test_row_stride_rule_and_validation(lib):
     assert rc != 0 and b'row_stride' in lib.rz_last_error()
     rc = lib.rz_net_conv3x3_tc3(dummy, dummy, dummy, None, C.c_void_p(32), 1, 6, 7, 12, 1, 0, None)
     assert rc != 0 and b'row_stride' in lib.rz_last_error()
+
+
+def test_leaf_parallel_descriptor_is_validated(lib):
+    """rz_tree_desc.leaves_per_tree > 1 needs its scratch and the AlphaZero flavour (host-side validation)."""
+    from rlzero_b200 import _lib
+    t = _lib.TreeDesc()
+    t.game = _lib.GameDesc(15, 5, 225, 256)
+    t.n_trees, t.max_nodes, t.max_depth, t.rule, t.ln_table_len = 1, 8, 226, 0, 16
+    dummy = 64
+    for name in ('edge_N', 'edge_W', 'edge_child', 'node_parent', 'node_paction', 'n_nodes', 'root_N', 'root_W',
+                 'root_rows', 'root_meta', 'path_node', 'path_action', 'depth', 'leaf_rows', 'leaf_meta', 'ln_table'):
+        setattr(t, name, dummy)
+    t.leaves_per_tree = 4
+    rc = lib.rz_tree_select(C.byref(t), None)
+    assert rc != 0 and b'vl_saved_W' in lib.rz_last_error()
+    t.leaves_per_tree = 1000
+    rc = lib.rz_tree_select(C.byref(t), None)
+    assert rc != 0 and b'leaves_per_tree' in lib.rz_last_error()
+    t.leaves_per_tree, t.vl_saved_W, t.flavour, t.edge_O, t.root_O = 4, dummy, _lib.FLAVOUR_DEEPMIND, dummy, dummy
+    rc = lib.rz_tree_select(C.byref(t), None)
+    assert rc != 0 and b'AlphaZero flavour' in lib.rz_last_error()

@@ -135,3 +135,80 @@ def test_single_game_api_with_leaves_per_wave():
         env.step(move)
         if env.game_end_winner()[0]:
             break
+
+
+@pytest.mark.parametrize('n,n_playout,plies,K', [(5, 150, 12, 8), (9, 200, 40, 16), (3, 90, 4, 4)])
+def test_leaf_parallel_on_go_matches_the_oracle_wave(n, n_playout, plies, K):
+    """The same wave over the Go rules (captures, ko, passes and two-pass terminal leaves inside the tree)."""
+    from oracle import pyoracle
+    from oracle.evaluators import EVAL_HASH, make_policy_value_fn
+    from oracle.go_oracle import GoSearchBoard
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import ClosedFormEvaluator, SearchForest
+    G, komi = 6, 2.5
+    positions = []
+    for g in range(G):
+        rs = np.random.RandomState(17 * g + n)
+        b = GoSearchBoard(n, komi, 0)
+        moves = []
+        for _ in range((plies * (g + 1)) // G):
+            legal = b.leagel_actions()
+            a = legal[rs.randint(len(legal) - 1)] if len(legal) > 1 and rs.rand() > 0.03 else n * n
+            b.step(a)
+            moves.append(a)
+            if b.game_end_winner()[0]:
+                b.reset()
+                moves = []
+        positions.append((b, moves))
+    f = SearchForest(G, n, 1, n_playout=n_playout, game_type=L.GAME_GO, komi=komi, leaves_per_tree=K)
+    f.set_positions([m for _, m in positions])
+    f.search(ClosedFormEvaluator(EVAL_HASH))
+    f.raise_faults()
+    visits, w, has, root_n, root_w = f.root_stats()
+    A = n * n + 1
+    for g, (board, _) in enumerate(positions):
+        s = pyoracle.Search(make_policy_value_fn(EVAL_HASH), n_playout, 5, leaves_per_wave=K)
+        s.simulate(board, 1.0)
+        assert np.array_equal(visits[g], s.root_visits(A)), g
+        assert np.array_equal(w[g], s.root_values(A)), g
+        assert root_n[g] == s.root.n and root_w[g] == s.root.w
+
+
+def test_leaf_parallel_on_connect_four_matches_the_oracle_wave():
+    from oracle import pyoracle
+    from oracle.evaluators import EVAL_HASH, make_policy_value_fn
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import ClosedFormEvaluator, SearchForest
+    G, n_playout, K = 8, 300, 8
+    boards, move_lists = [], []
+    for g in range(G):
+        rs = np.random.RandomState(1000 + g)
+        seq = [int(m) for m in rs.permutation(np.repeat(np.arange(7), 6))[:g * 2]]
+        b = pyoracle.ConnectFourBoard()
+        b.reset()
+        ok = []
+        for m in seq:
+            b.step(m)
+            ok.append(m)
+            if b.game_end_winner()[0]:
+                b.reset()
+                ok = []
+        boards.append(b)
+        move_lists.append(ok)
+    f = SearchForest(G, 6, 4, n_playout=n_playout, board_width=7, game_type=L.GAME_CONNECT4, leaves_per_tree=K)
+    f.set_positions(move_lists)
+    f.search(ClosedFormEvaluator(EVAL_HASH))
+    f.raise_faults()
+    visits, w, has, root_n, root_w = f.root_stats()
+    for g in range(G):
+        s = pyoracle.Search(make_policy_value_fn(EVAL_HASH), n_playout, 5, leaves_per_wave=K)
+        s.simulate(boards[g], 1.0)
+        assert visits[g].tolist() == s.root_visits(7).tolist(), g
+        assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(7)], g
+
+
+def test_leaf_parallel_rejects_the_deepmind_flavour():
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import SearchForest
+    with pytest.raises(ValueError):
+        SearchForest(1, 6, 4, n_playout=10, flavour=L.FLAVOUR_DEEPMIND, leaves_per_tree=4)

@@ -114,3 +114,25 @@ def test_train_pipeline_runs_in_both_modes(tmp_path, monkeypatch):
     tp2.collect_selfplay_data(4)
     ratio = tp2.policy_evaluate(n_games=2)
     assert 0.0 <= ratio <= 1.0
+
+
+def test_learn_and_policy_value_accept_device_tensors():
+    """AlphaZeroAgent.learn / policy_value_device on CUDA tensors (the batched pipeline's mini-batches, which never
+    visit the host) give exactly what the reference-style list / numpy inputs give."""
+    from rlzero_b200.games.gomoku.alphazero_agent import AlphaZeroAgent
+    rs = np.random.RandomState(0)
+    states = rs.randint(0, 2, size=(24, 4, 6, 6)).astype(np.float32)
+    pis = rs.dirichlet(np.ones(36), size=24).astype(np.float32)
+    zs = rs.choice([-1.0, 0.0, 1.0], size=24).astype(np.float32)
+    torch.manual_seed(1)
+    a = AlphaZeroAgent(6)
+    torch.manual_seed(1)
+    b = AlphaZeroAgent(6)
+    la = a.learn([s for s in states], [p for p in pis], [z for z in zs])
+    lb = b.learn(torch.from_numpy(states).cuda(), torch.from_numpy(pis).cuda(), torch.from_numpy(zs).cuda())
+    assert la == lb
+    for pa, pb in zip(a.policy_value_net.parameters(), b.policy_value_net.parameters()):
+        assert torch.equal(pa, pb)
+    pa, va = a.policy_value(states)
+    pb, vb = b.policy_value_device(torch.from_numpy(states).cuda())
+    assert np.array_equal(pa, pb.cpu().numpy()) and np.array_equal(va, vb.cpu().numpy())
