@@ -312,6 +312,26 @@ def run_b200(args):
                      'algorithmic_bytes_per_launch': sel_bytes,
                      'share_of_step': sel_ms / (ms / args.steps),
                      'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650'}
+        # expand + backup mutates the trees, so it is timed inside live (un-graphed) waves, CUDA events around the
+        # launch.  Algorithmic bytes per tree: the leaf's log-priors (4*AS read), the new edge block's visit
+        # counts (4*AS written; + 4*AS priors when they are stored), the leaf occupancy rows, and a read-modify-write
+        # of (N int32, W fp64) per edge of the path plus the root
+        eb_ms, n_eb = 0.0, 10
+        for _ in range(n_eb):
+            f.select()
+            sp.evaluator(f)
+            t0.record()
+            f.expand_backup(bool(getattr(sp.evaluator, 'prior_is_log', False)), sp.noise_eps, sp.noise_alpha, sp.seed)
+            t1.record()
+            torch.cuda.synchronize()
+            eb_ms += t0.elapsed_time(t1) / n_eb
+        sp.waves_in_move += n_eb
+        eb_bytes = G * (4 * f.AS + 4 * f.AS * (2 if f.store_priors else 1) + 2 * BOARD * 4) + (levels + G) * 24
+        tree_roof['expand_backup'] = {
+            'kernel': 'rz_expand_backup_kernel (%d trees, Dirichlet noise %s)' % (G, 'on' if sp.noise_eps > 0 else 'off'),
+            'achieved': eb_bytes / eb_ms / 1e6, 'peak': hbm, 'unit': 'GB/s', 'frac': eb_bytes / eb_ms / 1e6 / hbm,
+            'launch_ms': eb_ms, 'algorithmic_bytes_per_launch': eb_bytes, 'share_of_step': eb_ms / (ms / args.steps),
+            'note': 'latency- and ALU-bound (one warp per tree: %d Gamma draws per expansion), not bandwidth-bound' % f.A}
 
     # end to end through the public API with host buffers (per move: H2D positions, D2H pi/moves)
     e2e = None
