@@ -8,7 +8,8 @@
 // values, padded to K = 64) is built straight from the bitboards in registers and written to
 // shared memory in the 128-byte-swizzled K-major layout tcgen05.mma reads; the planes never
 // exist in HBM.  One 128 x 128 x 64 MMA group per 128 positions, epilogue as in rz_net_tc2.cu
-// (TMEM -> +bias -> ReLU -> pad mask -> bf16 -> staged tile -> TMA store).  The kernel is bound
+// (TMEM -> +bias -> ReLU -> pad mask -> bf16 -> 256-bit global stores from registers; the Go stem
+// below still stages its tile for a TMA store).  The kernel is bound
 // by its 64 KB/board output write; several CTAs per SM overlap build / MMA / drain phases.
 #include <cuda_bf16.h>
 
@@ -20,8 +21,7 @@ namespace {
 constexpr int STEM_THREADS = 128;
 constexpr int OFF_B = 0;                 // [128 cout][64 k] bf16, SW128
 constexpr int OFF_A = 16384;             // [128 pos][64 k] bf16, SW128
-constexpr int OFF_STAGE = 32768;         // 2 x [128 pos][64 cout] bf16, SW128
-constexpr int OFF_CTRL = 65536;
+constexpr int OFF_CTRL = 32768;          // (the output goes to HBM straight from registers: no staging tile)
 constexpr int STEM_SMEM = OFF_CTRL + 2048 + 1024;   // control block + alignment slack
 
 struct StemParams {
@@ -29,6 +29,8 @@ struct StemParams {
   const int32_t* meta;    // [n][RZ_META_STRIDE]
   const float* planes;    // kPlanes: [n][4][H][H] float observation planes instead of bitboards
   const float* bias;      // [128]
+  __nv_bfloat16* out;     // [rows_alloc][128]
+  long long rows_alloc;   // n_tiles * 128
   int n_tiles;            // 128-row tiles of the padded position layout
   int n_boards;
   int H;                  // rows
@@ -41,8 +43,7 @@ struct StemParams {
 // and may straddle two boards when kS = 20
 template <bool kPlanes, int kS>
 __global__ void __launch_bounds__(STEM_THREADS)
-rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
-                  const StemParams p) {
+rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p) {
   static_assert(kS * kS >= 64, "a 128-row tile must not touch more than two boards");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (rz::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -57,7 +58,6 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   if (tid == 0) {
     rz::tma_prefetch_desc(&tmap_w);
-    rz::tma_prefetch_desc(&tmap_out);
     rz::mbar_init(bar_w, 1);
     rz::mbar_init(bar_mma, 1);
     rz::fence_barrier_init();
@@ -74,7 +74,6 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   constexpr uint32_t ONE = 0x3F80u;  // bf16 1.0
 
   uint32_t phase = 0;
-  bool store_pending = false;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int b_first = (tile * 128) / P;
     const int my_row = tile * 128 + tid;
@@ -86,7 +85,6 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       s_rows[sel * 68 + t] = (y < H && bb < p.n_boards) ? p.rows[((size_t)bb * 2 + c) * H + y] : 0u;
       if (t < 4) s_rows[sel * 68 + 64 + t] = bb < p.n_boards ? (uint32_t)p.meta[(size_t)bb * RZ_META_STRIDE + t] : 0u;
     }
-    if (tid == 0 && store_pending) rz::tma_store_wait_read();  // staging tile free again
     __syncthreads();
     // ---- im2col row of position r: k = tap*4 + plane (gomoku_env.py:95-114 per tap)
     {
@@ -144,23 +142,23 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     }
     rz::mbar_wait(bar_mma, phase & 1u);
     rz::tc_fence_after();
-    // ---- epilogue: row per thread
+    // ---- epilogue: row per thread, 256-bit global stores straight from registers (L1::no_allocate, as in the
+    // trunk convolution): no staging tile, no TMA store to wait for before the next tile
     {
       const int pos = my_row - b * P;
       const bool valid = (pos % kS < W) && (pos / kS < H) && b < p.n_boards;
-      const uint32_t stage_row = base + OFF_STAGE + (uint32_t)tid * 128u;
+      __nv_bfloat16* orow = p.out + (size_t)my_row * 128;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t acc[32];
         rz::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 32), acc);
         rz::tmem_ld_wait();
-        const uint32_t srow = stage_row + (uint32_t)(ch >> 1) * 16384u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t packed[4];
+        for (int j = 0; j < 2; ++j) {
+          uint32_t packed[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = j * 8 + e * 2;
+          for (int e = 0; e < 8; ++e) {
+            const int c = j * 16 + e * 2;
             float v0 = __uint_as_float(acc[c]) + s_bias[ch * 32 + c];
             float v1 = __uint_as_float(acc[c + 1]) + s_bias[ch * 32 + c + 1];
             if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
@@ -168,23 +166,14 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
             packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
           }
-          const uint32_t chunk = (uint32_t)((ch & 1) * 4 + j);
-          rz::st_shared_v4(srow + ((chunk ^ ((uint32_t)tid & 7u)) << 4), packed[0], packed[1], packed[2], packed[3]);
+          if (my_row < p.rows_alloc) rz::st_global_v8(orow + ch * 32 + j * 16, packed);
         }
       }
     }
-    rz::fence_proxy_async();
     rz::tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      rz::tma_store_2d(&tmap_out, base + OFF_STAGE, 0, tile * 128);
-      rz::tma_store_2d(&tmap_out, base + OFF_STAGE + 16384, 64, tile * 128);
-      rz::tma_store_commit();
-    }
-    store_pending = true;
+    __syncthreads();          // every warp has read its accumulator rows: the next tile's MMAs may overwrite TMEM
     ++phase;
   }
-  if (tid == 0 && store_pending) rz::tma_store_wait_all();
   rz::tc_fence_before();
   __syncthreads();
   if (warp == 0) { rz::tc_fence_after(); rz::tmem_dealloc(tmem_base, 128); }
@@ -396,24 +385,24 @@ static int stem_launch(const rz_game_desc* g, const uint32_t* rows, const int32_
   }
   // the output tensor is padded to a multiple of 256 rows (the convolutions work on pairs of 128-row tiles)
   const long long rows_alloc = ((long long)n_boards * S * S + 255) / 256 * 256;
-  CUtensorMap tmap_w, tmap_out;
+  CUtensorMap tmap_w;
   if (rz::make_tmap_2d(&tmap_w, weight, 128, 64, 128)) return -1;
-  if (rz::make_tmap_2d(&tmap_out, act_out, (uint64_t)rows_alloc, 128, 128)) return -1;
   StemParams p;
   p.rows = rows; p.meta = meta; p.planes = planes; p.bias = bias;
+  p.out = reinterpret_cast<__nv_bfloat16*>(act_out); p.rows_alloc = rows_alloc;
   p.n_tiles = (int)(rows_alloc / 128); p.n_boards = n_boards; p.H = H; p.W = W; p.relu = relu;
-  int ctas = n_ctas > 0 ? n_ctas : 148 * 3;
+  int ctas = n_ctas > 0 ? n_ctas : 148 * 4;   // 35 KB of shared memory and 128 TMEM columns per CTA: four per SM
   if (ctas > p.n_tiles) ctas = p.n_tiles;
   cudaStream_t st = (cudaStream_t)stream;
   if (S == 8) {
-    if (planes) rz_stem_tc_kernel<true, 8><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
-    else        rz_stem_tc_kernel<false, 8><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+    if (planes) rz_stem_tc_kernel<true, 8><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
+    else        rz_stem_tc_kernel<false, 8><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
   } else if (S == 16) {
-    if (planes) rz_stem_tc_kernel<true, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
-    else        rz_stem_tc_kernel<false, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+    if (planes) rz_stem_tc_kernel<true, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
+    else        rz_stem_tc_kernel<false, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
   } else {
-    if (planes) rz_stem_tc_kernel<true, 20><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
-    else        rz_stem_tc_kernel<false, 20><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+    if (planes) rz_stem_tc_kernel<true, 20><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
+    else        rz_stem_tc_kernel<false, 20><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
   }
   RZ_LAUNCH_CHECK("rz_net_stem_tc");
   return 0;

@@ -26,8 +26,13 @@ class BatchedSelfPlay(object):
     def __init__(self, n_games, board_size=15, n_in_row=5, net=None, n_playout=800, c_puct=5.0,
                  rule=L.RULE_UCT, temperature=1.0, add_noise=True, noise_eps=0.25, noise_alpha=0.3,
                  device='cuda', global_offset=0, seed=0, evaluator=None, ring_capacity=None,
-                 store_priors=True, n_ctas=0, board_width=None, game_type=L.GAME_GOMOKU, komi=7.5, max_moves=0):
-        """``game_type = L.GAME_GO``: ``n_in_row`` is ignored, actions are the squares + the pass,
+                 store_priors=True, n_ctas=0, board_width=None, game_type=L.GAME_GOMOKU, komi=7.5, max_moves=0,
+                 leaves_per_tree=1, virtual_loss=1.0):
+        """``leaves_per_tree = K > 1``: leaf-parallel waves with virtual loss (``SearchForest``): a move is
+        ``1 + ceil((n_playout - 1) / K)`` waves of up to K playouts per game and the network sees G*K leaves per
+        wave -- for batches too small to fill the GPU.  Not the reference's sequential search order; 1 = parity mode.
+
+        ``game_type = L.GAME_GO``: ``n_in_row`` is ignored, actions are the squares + the pass,
         ``komi`` as GoEnv's, ``max_moves`` > 0 ends and scores a game after that many moves (the
         reference has no cap; AlphaGo Zero used 2 * 19 * 19)."""
         self.G = int(n_games)
@@ -40,17 +45,27 @@ class BatchedSelfPlay(object):
                                    rule=rule, device=device, global_offset=global_offset,
                                    with_trajectories=True, ring_capacity=ring_capacity,
                                    store_priors=store_priors, board_width=board_width, game_type=game_type,
-                                   komi=komi, max_moves=max_moves)
+                                   komi=komi, max_moves=max_moves, leaves_per_tree=leaves_per_tree,
+                                   virtual_loss=virtual_loss)
+        self.K = self.forest.K
+        self.waves_per_move = self.n_playout if self.K == 1 else 1 + (max(self.n_playout - 1, 0) + self.K - 1) // self.K
         if evaluator is None:
             if net is None:
                 raise ValueError('BatchedSelfPlay needs a policy-value module (net=) or an evaluator')
-            evaluator = NativeForward(net, max_batch=self.G, device=device, n_ctas=n_ctas, game_type=game_type)
+            evaluator = NativeForward(net, max_batch=self.forest.n_leaves, device=device, n_ctas=n_ctas,
+                                      game_type=game_type)
         self.evaluator = evaluator
+        self._arm_budget()
         self.waves_in_move = 0
         self.moves_played = 0
         self._graph = None
         self._graph_version = getattr(evaluator, 'weights_version', 0)
         self._pinned = None
+
+    def _arm_budget(self):
+        """Leaf-parallel mode: every tree takes exactly n_playout more playouts (rz_tree_desc.target_N)."""
+        if self.K > 1:
+            torch.add(self.forest.root_N, self.n_playout, out=self.forest.target_N)
 
     # ------------------------------------------------------------------ set-up
     def set_random_start_positions(self, global_ids=None, max_random_moves=31):
@@ -76,6 +91,7 @@ class BatchedSelfPlay(object):
                                       L.stream_ptr()), 'rz_gomoku_reset')
         f.root_meta[:, L.META_EPISODE] = 0
         self.waves_in_move = 0
+        self._arm_budget()
 
     def _set_random_go_positions(self, ids, max_random_moves):
         """Go: the same recipe, but a random square may be illegal (suicide / ko), so the moves are
@@ -106,6 +122,7 @@ class BatchedSelfPlay(object):
         f.root_meta[:, L.META_EPISODE] = 0
         f.raise_faults()
         self.waves_in_move = 0
+        self._arm_budget()
 
     # -------------------------------------------------------------------- waves
     def _wave(self):
@@ -152,7 +169,7 @@ class BatchedSelfPlay(object):
         else:
             self._wave()
         self.waves_in_move += 1
-        if self.waves_in_move >= self.n_playout:
+        if self.waves_in_move >= self.waves_per_move:
             self.commit_move()
 
     def commit_move(self):
@@ -162,10 +179,11 @@ class BatchedSelfPlay(object):
         f.advance(keep_subtree=True, record=True, auto_reset=True)
         self.waves_in_move = 0
         self.moves_played += 1
+        self._arm_budget()
 
     def play(self, n_moves):
         self.warm_up()
-        for _ in range(n_moves * self.n_playout):
+        for _ in range(n_moves * self.waves_per_move):
             self.step_wave()
 
     # ------------------------------------------------- host-buffer API (end to end)
@@ -198,7 +216,8 @@ class BatchedSelfPlay(object):
         f.reset_trees()
         self.warm_up_for_api()
         self._check_weights()
-        for _ in range(self.n_playout):
+        self._arm_budget()
+        for _ in range(self.waves_per_move):
             if self._graph is not None:
                 self._graph.replay()
             else:

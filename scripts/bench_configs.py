@@ -97,6 +97,30 @@ def main():
                           'games_finished': sp.games_done - g0, 'wall_s': time.time() - t0}), flush=True)
         del sp
         torch.cuda.empty_cache()
+    if '2vl' in only:
+        # config 2 again with leaf-parallel waves (opt-in, not the parity mode): K playouts per game and wave make
+        # the launches K times longer, which amortises the fixed cost of a short convolution launch
+        net2 = ResNetPolicyValueNet(6, n_blocks=6, board_width=7, n_actions=7).cuda().eval()
+        for K in (1, 2, 4):
+            sp = BatchedSelfPlay(4096, 6, 4, net=net2, n_playout=200, add_noise=True, seed=2, board_width=7,
+                                 game_type=L.GAME_CONNECT4, leaves_per_tree=K)
+            sp.set_random_start_positions(max_random_moves=3)
+            sp.play(2)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_moves = 10
+            e0.record()
+            for _ in range(n_moves * sp.waves_per_move):
+                sp.step_wave()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            sp.forest.raise_faults()
+            print(json.dumps({'config': 'config2 Connect Four, 4096 games, ResNet-6, leaves_per_tree=%d' % K,
+                              'waves_per_move': sp.waves_per_move, 'ms_per_move': ms / n_moves,
+                              'simulations_per_s': 4096 * 200 * n_moves / ms * 1e3}), flush=True)
+            del sp
+            torch.cuda.empty_cache()
     if '4g' in only:
         # the same board and trunk with five-in-a-row rules (the pre-Go stand-in of earlier runs)
         net4 = ResNetPolicyValueNet(19, n_blocks=20).cuda().eval()

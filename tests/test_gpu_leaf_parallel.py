@@ -212,3 +212,44 @@ def test_leaf_parallel_rejects_the_deepmind_flavour():
     from rlzero_b200.engine import SearchForest
     with pytest.raises(ValueError):
         SearchForest(1, 6, 4, n_playout=10, flavour=L.FLAVOUR_DEEPMIND, leaves_per_tree=4)
+
+
+def test_batched_selfplay_with_leaf_parallel_waves():
+    """BatchedSelfPlay(leaves_per_tree=K): a move is 1 + ceil((n-1)/K) waves, every game gets exactly n_playout
+    playouts per move (the root's child visits sum to n_playout - 1 on a fresh tree), games finish, drain works."""
+    import torch
+    from rlzero_b200.games.gomoku.policy_value_net import ResNetPolicyValueNet
+    from rlzero_b200.selfplay import BatchedSelfPlay
+    torch.manual_seed(0)
+    net = ResNetPolicyValueNet(6, n_blocks=1).cuda().eval()
+    G, n, K = 24, 50, 8
+    sp = BatchedSelfPlay(G, 6, 4, net=net, n_playout=n, add_noise=True, seed=3, leaves_per_tree=K)
+    assert sp.waves_per_move == 1 + (n - 1 + K - 1) // K and sp.evaluator.max_batch >= G * K
+    sp.warm_up()
+    for _ in range(sp.waves_per_move - 2):
+        sp.step_wave()
+    # one wave before the commit: n_playout - (last wave's share) visits so far; after it exactly n_playout
+    if sp._graph is not None:
+        sp._graph.replay()
+    else:
+        sp._wave()
+    torch.cuda.synchronize()
+    sp.forest.raise_faults()
+    visits, _, _, root_n, _ = sp.forest.root_stats()
+    assert (root_n == n).all() and (visits.sum(1) == n - 1).all()
+    sp.waves_in_move += 1
+    sp.commit_move()
+    sp.play(40)
+    sp.forest.raise_faults()
+    st = sp.stats()
+    assert st['games_done'] >= G
+    states, pis, zs, info = sp.drain()
+    assert len(zs) > 0 and set(np.unique(zs)).issubset({-1.0, 0.0, 1.0})
+    assert np.allclose(pis.sum(1), 1.0, atol=1e-5)
+    # the host-buffer API in the same mode
+    rows, meta = sp.forest.boards()
+    meta = meta.copy()
+    from rlzero_b200 import _lib as L
+    meta[:, L.META_STATUS] = L.ACTIVE
+    moves, pi, v = sp.get_actions(rows, meta)
+    assert (v.sum(1) == n - 1).all() and np.allclose(pi.sum(1), 1.0, atol=1e-5)
