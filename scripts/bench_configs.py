@@ -97,6 +97,16 @@ def main():
                           'games_finished': sp.games_done - g0, 'wall_s': time.time() - t0}), flush=True)
         del sp
         torch.cuda.empty_cache()
+    if 'stock15' in only:
+        # the reference's OWN network (PolicyValueNet 4 -> 32 -> 64 -> 128) at 15x15 / 800 sims / 8192 games: the
+        # fp32 CUDA-core path (1e-5 parity, the default for this net) against the same weights zero-padded onto the
+        # bf16 tensor-core trunk (mode 'tc', 1e-3)
+        net = PolicyValueNet(15).cuda().eval()
+        for mode, waves in (('f32', 24), ('tc', 400)):
+            sp = BatchedSelfPlay(8192, 15, 5, net=net, n_playout=800, add_noise=True, seed=1, net_mode=mode)
+            run('stock PolicyValueNet 15x15, 800 sims/move, 8192 games, mode %s' % mode, sp, waves, 4)
+            del sp
+            torch.cuda.empty_cache()
     if '2vl' in only:
         # config 2 again with leaf-parallel waves (opt-in, not the parity mode): K playouts per game and wave make
         # the launches K times longer, which amortises the fixed cost of a short convolution launch

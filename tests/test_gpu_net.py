@@ -517,3 +517,37 @@ def test_heads_on_the_tensor_cores_match_the_fp32_heads(h, w, a, planes, n):
     # (the scaled-up head weights amplify the bf16 error of the trunk: looser than the 1e-3 of the stock scale)
     assert (lt[:, :A].exp().cpu() - lr.exp()).abs().max().item() < 1e-2
     assert (vt.cpu() - vr.reshape(-1)).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize('size,n', [(15, 37), (9, 5), (6, 130)])
+def test_stock_net_on_the_tensor_core_path(size, n):
+    """The reference's PolicyValueNet (4 -> 32 -> 64 -> 128) zero-padded onto the bf16 tensor-core trunk (mode 'tc',
+    opt-in): within the north star's bf16 tolerance (1e-3) of PyTorch fp32, padding channels exactly zero, search
+    through the reference API works with it."""
+    from rlzero_b200.games.gomoku import GomokuEnv
+    from rlzero_b200.games.gomoku.alphazero_agent import AlphaZeroAgent
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, PolicyValueNet
+    from rlzero_b200.mcts import AlphaZeroMCTS
+    torch.manual_seed(size)
+    net = PolicyValueNet(size).cuda().eval()
+    nf = NativeForward(net, max_batch=n, mode='tc')
+    assert nf.mode == 'tc' and all(l['cout'] == 128 for l in nf.layers)
+    assert NativeForward(net, max_batch=1).mode == 'f32'        # the default for this network stays fp32
+    x = _random_boards(n, size, 9)
+    logp, v = (t.cpu() for t in nf.forward_planes(x))
+    ref = PolicyValueNet(size).eval()
+    ref.load_state_dict({k: t.cpu() for k, t in net.state_dict().items()})
+    with torch.no_grad():
+        lt, vt = ref(torch.from_numpy(x))
+    assert (logp.exp() - lt.exp()).abs().max().item() < 1e-3
+    assert (v - vt.reshape(-1)).abs().max().item() < 1e-3
+    nb = NativeForward(net, max_batch=n, mode='tc', fused_head=False)
+    nb.forward_planes(x)
+    P = nb.P
+    mid = nb.bufs[1][:n * P].float()           # output of the padded 32 -> 64 layer (ping-pong buffer 1): channels 64.. are zero
+    assert mid[:, 64:].abs().max().item() == 0.0 and mid[:, :64].abs().max().item() > 0.0
+    agent = AlphaZeroAgent(size, net=net, mode='tc')
+    env = GomokuEnv(size, min(5, size))
+    env.reset()
+    acts, probs = AlphaZeroMCTS(agent.policy_value_fn, n_playout=40).simulate(env, 1.0)
+    assert len(acts) == size * size and abs(probs.sum() - 1.0) < 1e-9
