@@ -52,6 +52,79 @@ rz_conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
   }
 }
 
+// The same operator register-tiled: a thread owns TP consecutive positions x 4 consecutive output channels, so one
+// 128-bit weight load and TP shared-memory reads feed 4*TP FMAs (the kernel above issues two loads per FMA).  Every
+// output accumulates bias, then taps 0..8 (in-board only), input channels ascending, with the same fmaf operand order
+// as above: the results are bit-identical to it (tests compare the fp32 path with live-reference fixtures).
+template <int TP>
+__global__ void __launch_bounds__(256)
+rz_conv3x3_f32_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                            const float* __restrict__ bias, const float* __restrict__ residual,
+                            float* __restrict__ out, int H, int Cin, int Cout, int relu) {
+  extern __shared__ float s_in[];  // [HW][Cin]
+  const int b = blockIdx.x, HW = H * H;
+  const float* ib = in + (size_t)b * HW * Cin;
+  for (int i = threadIdx.x; i < HW * Cin; i += blockDim.x) s_in[i] = ib[i];
+  __syncthreads();
+  const int ct = Cout >> 2, pt = (HW + TP - 1) / TP;
+  const int total = ct * pt;
+  const int per = (total + gridDim.y - 1) / gridDim.y;
+  const int lo = blockIdx.y * per, hi = min(total, lo + per);
+  for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+    const int co0 = (t % ct) << 2, pos0 = (t / ct) * TP;
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + co0);
+    float acc[TP][4];
+    int py[TP], px[TP];
+#pragma unroll
+    for (int p = 0; p < TP; ++p) {
+      acc[p][0] = b4.x; acc[p][1] = b4.y; acc[p][2] = b4.z; acc[p][3] = b4.w;
+      const int pos = pos0 + p;
+      py[p] = pos < HW ? pos / H : -4;          // -4: every tap of a position beyond the board is out of range
+      px[p] = pos - (pos / H) * H;
+    }
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      int base[TP];
+      bool ok[TP], any = false;
+#pragma unroll
+      for (int p = 0; p < TP; ++p) {
+        const int yy = py[p] + dy, xx = px[p] + dx;
+        ok[p] = yy >= 0 && yy < H && xx >= 0 && xx < H;
+        base[p] = ok[p] ? (yy * H + xx) * Cin : 0;
+        any |= ok[p];
+      }
+      if (!any) continue;
+      const float* wt = w + (size_t)tap * Cin * Cout + co0;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)ci * Cout);
+#pragma unroll
+        for (int p = 0; p < TP; ++p) {
+          if (ok[p]) {
+            const float x = s_in[base[p] + ci];
+            acc[p][0] = fmaf(x, w4.x, acc[p][0]);
+            acc[p][1] = fmaf(x, w4.y, acc[p][1]);
+            acc[p][2] = fmaf(x, w4.z, acc[p][2]);
+            acc[p][3] = fmaf(x, w4.w, acc[p][3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < TP; ++p) {
+      const int pos = pos0 + p;
+      if (pos >= HW) continue;
+      const size_t o = ((size_t)b * HW + pos) * Cout + co0;
+      float4 r = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+      if (residual) {
+        const float4 q = *reinterpret_cast<const float4*>(residual + o);
+        r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+      }
+      if (relu) { r.x = fmaxf(r.x, 0.0f); r.y = fmaxf(r.y, 0.0f); r.z = fmaxf(r.z, 0.0f); r.w = fmaxf(r.w, 0.0f); }
+      *reinterpret_cast<float4*>(out + o) = r;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // heads: NB boards per block.
 //
@@ -354,7 +427,17 @@ extern "C" int rz_net_conv3x3_f32(const float* in, const float* weight, const fl
   const size_t smem = sizeof(float) * (size_t)board_size * board_size * c_in;
   RZ_REQUIRE(smem <= 200 * 1024, "rz_net_conv3x3_f32: input board needs %zu B of shared memory", smem);
   if (n_boards == 0) return 0;
-  cudaError_t e = cudaFuncSetAttribute(rz_conv3x3_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the register-tiled kernel needs output channels in groups of 4 and 16-byte aligned tensors, and pays off when a
+  // board keeps a 256-thread block busy (>= 512 thread tiles: 15x15 with 32+ channels, not 3x3) and there are enough
+  // boards to fill the GPU; a handful of boards (the single-game API) stay on the scalar kernel, split over blocks
+  const int HWs = board_size * board_size, ct4 = c_out >> 2;
+  const bool vec_ok = (c_out & 3) == 0 && ((((uintptr_t)weight) | ((uintptr_t)bias) | ((uintptr_t)out) |
+                                            ((uintptr_t)residual)) & 15) == 0;
+  const int tp = !(vec_ok && n_boards >= 64) ? 0 : (ct4 * ((HWs + 3) / 4) >= 512 ? 4 : (ct4 * HWs >= 512 ? 1 : 0));
+  const bool tiled = tp != 0;
+  cudaError_t e = !tiled ? cudaFuncSetAttribute(rz_conv3x3_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : tp == 1 ? cudaFuncSetAttribute(rz_conv3x3_f32_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(rz_conv3x3_f32_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_f32: smem attribute: %s", cudaGetErrorString(e)); return -2; }
   // few boards (the single-game API): split each board over several blocks so that the grid covers the 148 SMs
   int split = (2 * 148 + n_boards - 1) / n_boards;
@@ -362,8 +445,19 @@ extern "C" int rz_net_conv3x3_f32(const float* in, const float* weight, const fl
   if (split > max_split) split = max_split;
   if (split > 64) split = 64;
   if (split < 1) split = 1;
-  rz_conv3x3_f32_kernel<<<dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream>>>(
-      in, weight, bias, residual, out, board_size, c_in, c_out, relu);
+  if (tiled) {
+    const int tiles = (c_out >> 2) * ((board_size * board_size + tp - 1) / tp);
+    if (split > (tiles + 255) / 256) split = (tiles + 255) / 256;
+    if (tp == 1)
+      rz_conv3x3_f32_tiled_kernel<1><<<dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream>>>(
+          in, weight, bias, residual, out, board_size, c_in, c_out, relu);
+    else
+      rz_conv3x3_f32_tiled_kernel<4><<<dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream>>>(
+          in, weight, bias, residual, out, board_size, c_in, c_out, relu);
+  } else {
+    rz_conv3x3_f32_kernel<<<dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream>>>(
+        in, weight, bias, residual, out, board_size, c_in, c_out, relu);
+  }
   RZ_LAUNCH_CHECK("rz_net_conv3x3_f32");
   return 0;
 }
