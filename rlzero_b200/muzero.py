@@ -227,6 +227,29 @@ class MuZeroNative(object):
                                           L.ptr(value), self.G, L.stream_ptr()), 'rz_net_heads')
         return logp, value
 
+    def unroll(self, rows, meta, actions):
+        """Batched K-step unroll (BASELINE config 5; the MuZero paper's training / reanalysis unroll, forward
+        side): s0 = h(position g), s_k = g(s_{k-1}, actions[g][k-1]), (p_k, v_k) = f(s_k) for every position of the
+        batch at once.  ``actions``: int [G][K] (device or host).  Returns (logp [K+1][G][AS], value [K+1][G]) float32
+        device tensors; hidden state k stays in pool slot k (needs K + 1 <= n_slots).  Positions are independent, so
+        across GPUs the batch is simply sharded (no collective)."""
+        a = torch.as_tensor(actions, dtype=torch.int32, device=self.device).contiguous()
+        if a.dim() != 2 or a.shape[0] != self.G:
+            raise ValueError('actions must be [G][K] with G = %d' % self.G)
+        K = int(a.shape[1])
+        if K + 1 > self.pool.shape[0]:
+            raise ValueError('unroll of %d steps needs %d hidden-state slots, the pool has %d' % (K, K + 1, self.pool.shape[0]))
+        logp = torch.zeros(K + 1, self.G, self.AS, dtype=torch.float32, device=self.device)
+        value = torch.zeros(K + 1, self.G, dtype=torch.float32, device=self.device)
+        at = a.t().contiguous()                       # [K][G]: one contiguous action vector per step
+        self.representation(rows, meta, 0)
+        self.prediction(0, logp[0], value[0])
+        for k in range(K):
+            parent = torch.full((self.G,), k, dtype=torch.int32, device=self.device)
+            self.dynamics(parent, at[k], k + 1)
+            self.prediction(k + 1, logp[k + 1], value[k + 1])
+        return logp, value
+
     def kernels_per_simulation(self):
         return 1 + len(self.g.layers) + (2 if self.h.heads_tc else 1)      # gather + convolutions + heads
 

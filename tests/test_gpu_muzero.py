@@ -156,3 +156,40 @@ def test_selfplay_loop_plays_legal_moves_and_finishes_games():
     from rlzero_b200 import _lib as L
     assert not (sp.meta[:, L.META_FAULT].cpu().numpy() & L.FAULT_ILLEGAL_MOVE).any()
     assert sp.games_done >= 16 and sp.moves_played == 40
+
+
+@pytest.mark.parametrize('size,K,n', [(6, 5, 9), (9, 3, 130)])
+def test_batched_unroll_matches_torch(size, K, n):
+    """MuZeroNative.unroll: h, then K times g + f along given action sequences for a whole batch, against the fp32
+    PyTorch module unrolled the same way (errors accumulate over the steps: 1e-3 per step on probabilities / values), and against the step-by-step device calls (bit-identical)."""
+    from rlzero_b200.muzero import MuZeroNative
+    net = _net(size, 1, 1)
+    f, boards = _positions(n, size, min(5, size), 5)
+    nat = MuZeroNative(net, n, K + 1, n_in_row=min(5, size))
+    A = size * size
+    rs = np.random.RandomState(K)
+    actions = rs.randint(0, A, size=(n, K)).astype(np.int32)
+    logp, value = nat.unroll(f.root_rows, f.root_meta, actions)
+    assert logp.shape == (K + 1, n, nat.AS) and value.shape == (K + 1, n)
+    obs = torch.from_numpy(np.stack([b.current_state() for b in boards])).float().cuda()
+    with torch.no_grad():
+        s, lt, vt = net.initial_inference(obs)
+        outs = [(lt, vt)]
+        for k in range(K):
+            s, lt, vt = net.recurrent_inference(s, torch.from_numpy(actions[:, k]).cuda())
+            outs.append((lt, vt))
+    for k, (lt, vt) in enumerate(outs):
+        tol = 1e-3 * (k + 1)          # the bf16 error of every further dynamics step adds up
+        assert (logp[k][:, :A].exp() - lt.exp()).abs().max().item() < tol, k
+        assert (value[k] - vt.reshape(-1)).abs().max().item() < tol, k
+    # the same through the single-step calls
+    nat2 = MuZeroNative(net, n, K + 1, n_in_row=min(5, size))
+    nat2.representation(f.root_rows, f.root_meta, 0)
+    l0, v0 = (x.clone() for x in nat2.prediction(0))
+    assert torch.equal(l0, logp[0]) and torch.equal(v0, value[0])
+    for k in range(K):
+        nat2.dynamics(torch.full((n,), k, dtype=torch.int32, device='cuda'), torch.from_numpy(actions[:, k]).cuda(), k + 1)
+        lk, vk = nat2.prediction(k + 1)
+        assert torch.equal(lk, logp[k + 1]) and torch.equal(vk, value[k + 1])
+    with pytest.raises(ValueError):
+        nat.unroll(f.root_rows, f.root_meta, np.zeros((n, K + 3), dtype=np.int32))
