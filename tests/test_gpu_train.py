@@ -137,3 +137,23 @@ def test_learn_and_policy_value_accept_device_tensors():
     pb, vb = a.policy_value_device(torch.from_numpy(states).cuda())
     # same log-probabilities; exp is numpy's on one side and CUDA's on the other (last-ulp differences)
     assert np.allclose(pa, pb.cpu().numpy(), rtol=1e-6, atol=0) and np.array_equal(va, vb.cpu().numpy())
+
+
+def test_train_pipeline_single_game_loop_with_leaf_parallel_search(tmp_path, monkeypatch):
+    """TrainPipeline(leaves_per_wave=K): the reference-style one-game-at-a-time loop with the leaf-parallel search
+    (GameControl.start_self_play -> AlphaZeroPlayer.get_action): episodes finish, 8-fold augmented records land in
+    the buffer with pi vectors that sum to 1, and an update step runs."""
+    from rlzero_b200.train_pipeline import TrainPipeline
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(1)
+    random.seed(1)
+    torch.manual_seed(1)
+    tp = TrainPipeline(board_size=5, n_in_row=4, n_playout=24, game_batch_num=1, leaves_per_wave=4)
+    assert tp.mcts_player.mcts.leaves_per_wave == 4
+    tp.batch_size = 16
+    tp.collect_selfplay_data(2)
+    assert tp.episode_len > 0 and len(tp.data_buffer) >= 8 * tp.episode_len
+    for state, pi, z in list(tp.data_buffer)[:16]:
+        assert state.shape == (4, 5, 5) and abs(float(np.sum(pi)) - 1.0) < 1e-6 and z in (-1.0, 0.0, 1.0)
+    loss, entropy = tp.policy_update()
+    assert np.isfinite(loss) and np.isfinite(entropy)
