@@ -82,7 +82,9 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
   const uint32_t a_base = smem_base + B_BYTES;
   const uint32_t ctrl = smem_base + CTRL_OFF;
   uint8_t* ctrl_ptr = smem_raw + CTRL_OFF;
-  const uint32_t bar_bfull = ctrl, bar_afull = ctrl + 8, bar_aempty = ctrl + 24;
+  // weights: one barrier per tap (ctrl + 640 .. 711), so the first tile's MMAs of tap t start as soon as tap t has
+  // landed instead of waiting for all 147 KB; the first activation tile is requested BEFORE the weights
+  const uint32_t bar_btap = ctrl + 640, bar_afull = ctrl + 8, bar_aempty = ctrl + 24;
   const uint32_t bar_tfull = ctrl + 40, bar_tempty = ctrl + 56;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ctrl_ptr + 72);
   float* s_bias = reinterpret_cast<float*>(ctrl_ptr + 128);
@@ -100,7 +102,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
     rz::tma_prefetch_desc(&tmap_act);
     rz::tma_prefetch_desc(&tmap_w);
     rz::tma_prefetch_desc(&tmap_out);
-    rz::mbar_init(bar_bfull, 1);
+    for (int tap = 0; tap < 9; ++tap) rz::mbar_init(bar_btap + 8 * tap, 1);
     for (int b = 0; b < 2; ++b) {
       rz::mbar_init(bar_afull + 8 * b, 1);
       rz::mbar_init(bar_aempty + 8 * b, kHead ? 4 : 1);   // fused-heads layer: the 4 warps that read the scratch
@@ -127,14 +129,17 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
   if (warp == 0) {
     // ===== TMA producer (every CTA loads its own operands; completion is credited to the leader) =====
     if (lane == 0) {
-      const uint32_t l_bfull = (kCG == 2) ? rz::mapa_shared(bar_bfull, 0) : bar_bfull;
-      if (leader) rz::mbar_expect_tx(bar_bfull, (uint32_t)(kCG * 9 * p.kblocks * B_TILE_BYTES));
-      for (int tap = 0; tap < 9; ++tap)
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          const uint32_t dst = smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES;
-          if (kCG == 2) rz::tma_load_2d_pair(dst, &tmap_w, l_bfull, kb * 64, tap * 128 + half * 64);
-          else          rz::tma_load_2d(dst, &tmap_w, l_bfull, kb * 64, tap * 128 + half * 64);
+      auto load_weights = [&]() {
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t l_btap = (kCG == 2) ? rz::mapa_shared(bar_btap + 8 * tap, 0) : bar_btap + 8 * tap;
+          if (leader) rz::mbar_expect_tx(bar_btap + 8 * tap, (uint32_t)(kCG * p.kblocks * B_TILE_BYTES));
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            const uint32_t dst = smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES;
+            if (kCG == 2) rz::tma_load_2d_pair(dst, &tmap_w, l_btap, kb * 64, tap * 128 + half * 64);
+            else          rz::tma_load_2d(dst, &tmap_w, l_btap, kb * 64, tap * 128 + half * 64);
+          }
         }
+      };
       int it = 0;
       for (int item = worker; item < p.n_items; item += n_workers, ++it) {
         const int buf = it & 1;
@@ -147,6 +152,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
           if (kCG == 2) rz::tma_load_2d_pair(dst, &tmap_act, l_afull, kb * 64, row0);
           else          rz::tma_load_2d(dst, &tmap_act, l_afull, kb * 64, row0);
         }
+        if (it == 0) load_weights();      // right behind the first activation tile
       }
     }
   } else if (warp == 1) {
@@ -156,7 +162,6 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       constexpr uint32_t idesc = rz::umma_idesc_bf16(kCG == 2 ? 256 : 128, ACC_N);
       const uint32_t issue = rz::elect_one();
       const uint32_t tmem_u = rz::uniform_u32(tmem_base);
-      rz::mbar_wait(bar_bfull, 0);
       int it = 0;
       for (int item = worker; item < p.n_items; item += n_workers, ++it) {
         const int buf = it & 1;
@@ -170,6 +175,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           const int shift = HALO + (tap / 3 - 1) * 16 + (tap % 3 - 1);   // 0..34 rows into the halo tile
+          if (it == 0) { rz::mbar_wait(bar_btap + 8 * tap, 0); rz::tc_fence_after(); }   // this tap's weights have landed
           for (int kb = 0; kb < p.kblocks; ++kb) {
             const uint32_t a_addr = a_buf + (uint32_t)kb * A_KB_BYTES + (uint32_t)shift * 128u;
             const uint32_t b_addr = smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES;

@@ -78,7 +78,9 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
   const uint32_t stage = smem_base + G::OFF_STAGE;
   const uint32_t ctrl = smem_base + G::OFF_CTRL;
   uint8_t* ctrl_ptr = smem_raw + G::OFF_CTRL;
-  const uint32_t bar_bfull = ctrl, bar_afull = ctrl + 8, bar_aempty = ctrl + 32;
+  // weights: one barrier per (k-block, tap) at ctrl + 640 .. 783, loaded in the order the MMA loop consumes them and
+  // right behind the first activation k-block, so the first tile starts after 16 KB of weights instead of 147 KB
+  const uint32_t bar_btap = ctrl + 640, bar_afull = ctrl + 8, bar_aempty = ctrl + 32;
   const uint32_t bar_tfull = ctrl + 56, bar_tempty = ctrl + 72;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ctrl_ptr + 88);
   float* s_bias = reinterpret_cast<float*>(ctrl_ptr + 128);
@@ -95,7 +97,7 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
     rz::tma_prefetch_desc(&tmap_act);
     rz::tma_prefetch_desc(&tmap_w);
     rz::tma_prefetch_desc(&tmap_out);
-    rz::mbar_init(bar_bfull, 1);
+    for (int j = 0; j < 18; ++j) rz::mbar_init(bar_btap + 8 * j, 1);
     for (int s = 0; s < N_SLOTS; ++s) {
       rz::mbar_init(bar_afull + 8 * s, 1);
       rz::mbar_init(bar_aempty + 8 * s, 1);
@@ -116,12 +118,14 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
   if (warp == 0) {
     // ===== TMA producer: weights once, then one (tile, k-block) halo tile per ring slot =====
     if (lane == 0) {
-      const uint32_t l_bfull = rz::mapa_shared(bar_bfull, 0);
-      if (leader) rz::mbar_expect_tx(bar_bfull, (uint32_t)(2 * 18 * B_TILE_BYTES));
-      for (int tap = 0; tap < 9; ++tap)
-        for (int kb = 0; kb < 2; ++kb)
-          rz::tma_load_2d_pair(smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES, &tmap_w, l_bfull, kb * 64,
-                               tap * 128 + (int)rank * 64);
+      auto load_weights = [&](int kb) {
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t bar = bar_btap + 8 * (uint32_t)(kb * 9 + tap);
+          if (leader) rz::mbar_expect_tx(bar, (uint32_t)(2 * B_TILE_BYTES));
+          rz::tma_load_2d_pair(smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES, &tmap_w, rz::mapa_shared(bar, 0),
+                               kb * 64, tap * 128 + (int)rank * 64);
+        }
+      };
       int u = 0;   // running (tile, k-block) index
       for (int item = worker; item < p.n_items; item += n_workers) {
         const int row0 = item * 256 + (int)rank * TILE_M - G::HALO;
@@ -131,6 +135,7 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
           if (leader) rz::mbar_expect_tx(bar_afull + 8 * slot, (uint32_t)(2 * G::SLOT_BYTES));
           rz::tma_load_2d_pair(ring + (uint32_t)slot * G::SLOT_BYTES, &tmap_act,
                                rz::mapa_shared(bar_afull + 8 * slot, 0), kb * 64, row0);
+          if (u < 2) load_weights(u);     // first tile only: k-block u's weights right behind its activations
         }
       }
     }
@@ -140,7 +145,6 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
       constexpr uint32_t idesc = rz::umma_idesc_bf16(256, 128);
       const uint32_t issue = rz::elect_one();
       const uint32_t tmem_u = rz::uniform_u32(tmem_base);
-      rz::mbar_wait(bar_bfull, 0);
       int it = 0, u = 0;
       for (int item = worker; item < p.n_items; item += n_workers, ++it) {
         const int buf = it & 1;
@@ -155,6 +159,7 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             const int shift = G::HALO + (tap / 3 - 1) * kS + (tap % 3 - 1);
+            if (u < 2) { rz::mbar_wait(bar_btap + 8 * (uint32_t)(u * 9 + tap), 0); rz::tc_fence_after(); }
             const uint64_t adesc = rz::umma_desc_sw128(a_slot + (uint32_t)shift * 128u);
             const uint64_t bdesc = rz::umma_desc_sw128(smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES);
 #pragma unroll
