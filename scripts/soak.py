@@ -79,8 +79,43 @@ def soak_muzero(G=8192, moves=120):
     assert bad == 0
 
 
+def soak_line(name, G, size, k, moves, n_playout, blocks=2, **kw):
+    """Full-width self-play of a line game (Gomoku / Connect Four) through many committed moves: re-rooting, refills,
+    trajectories; every game must finish and drain cleanly, no fault bits."""
+    from rlzero_b200.selfplay import BatchedSelfPlay
+    torch.manual_seed(0)
+    net = ResNetPolicyValueNet(size, n_blocks=blocks, **{k_: v for k_, v in kw.items() if k_ in ('board_width', 'n_actions')}).cuda().eval()
+    spkw = {k_: v for k_, v in kw.items() if k_ not in ('n_actions',)}
+    sp = BatchedSelfPlay(G, size, k, net=net, n_playout=n_playout, add_noise=True, seed=9, ring_capacity=G * 96, **spkw)
+    sp.set_random_start_positions(max_random_moves=5)
+    t0 = time.time()
+    for m in range(moves):
+        sp.play(1)
+        if m % 10 == 9:
+            torch.cuda.synchronize()
+            sp.forest.raise_faults()
+    torch.cuda.synchronize()
+    sp.forest.raise_faults()
+    st = sp.stats()
+    states, pis, zs, info = sp.drain()
+    assert np.allclose(pis.sum(1), 1.0, atol=1e-4) and set(np.unique(zs)).issubset({-1.0, 0.0, 1.0})
+    print(json.dumps({'soak': name, 'games': G, 'moves': moves, 'n_playout': n_playout, 'leaves_per_tree': sp.K,
+                      'games_done': st['games_done'], 'plies_done': st['plies_done'], 'records_drained': int(len(zs)),
+                      'mean_episode_plies': float(st['plies_done']) / max(1, st['games_done']),
+                      'first_player_win_share': float((zs[info[:, 0] == 0] == 1).mean()) if len(zs) else None,
+                      'wall_s': time.time() - t0}), flush=True)
+    assert st['games_done'] >= G
+
+
 if __name__ == '__main__':
     which = sys.argv[1:] or ['go', 'dm', 'muzero']
+    if 'gomoku' in which:
+        soak_line('gomoku 15x15', 8192, 15, 5, 160, 32)
+    if 'c4' in which:
+        soak_line('connect four 6x7 (8-stride layout)', 4096, 6, 4, 60, 32, board_width=7, n_actions=7,
+                  game_type=L.GAME_CONNECT4)
+    if 'leafpar' in which:
+        soak_line('gomoku 9x9, leaf-parallel K=4', 2048, 9, 5, 100, 33, leaves_per_tree=4)
     if 'go' in which:
         soak_go()
     if 'dm' in which:
