@@ -454,7 +454,9 @@ rz_expand_backup_one(const rz_tree_desc& t, const int g, const int L, const bool
 }
 
 template <class GM, bool DM>
-__global__ void __launch_bounds__(RZ_TREE_THREADS)
+// 6 blocks (24 warps) per SM: 80 registers instead of 116; the kernel is latency-bound (16 warps/SM kept the issue
+// slots 42 % busy), a few bytes of spill are the price
+__global__ void __launch_bounds__(RZ_TREE_THREADS, 6)
 rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int prior_is_log,
                         const float* __restrict__ value, const double* __restrict__ value64,
                         float noise_eps, float noise_alpha,
