@@ -124,3 +124,62 @@ def test_random_games_terminate_and_stay_consistent():
                 if b[r, c] != 0:
                     chain, border = find_reached(b, (r, c))
                     assert any(b[p] == 0 for p in border)
+
+
+def test_one_move_captures_two_groups_and_sets_no_ko():
+    """White stones at (1,1) and (1,3) share their last liberty (1,2): black playing there removes both; two captured
+    stones never make a ko."""
+    n = 5
+    pos = play(Position(n), [(0, 1), (1, 1), (2, 1), (1, 3), (1, 0), (4, 4), (0, 3), (4, 3), (2, 3), (4, 2), (1, 4),
+                             (4, 1)], n)
+    assert pos.to_play == BLACK and pos.board[1, 1] == WHITE and pos.board[1, 3] == WHITE
+    pos = pos.play_move((1, 2))
+    assert pos.board[1, 1] == 0 and pos.board[1, 3] == 0 and pos.board[1, 2] == BLACK
+    assert pos.caps == (2, 0) and pos.ko is None
+    # both points are playable for white again (each has empty neighbours now? (1,1): no -- all four neighbours are
+    # black, and the black stones around it keep liberties, so it is suicide)
+    legal = pos.all_legal_moves()
+    assert legal[1 * n + 1] == 0 and legal[1 * n + 3] == 0
+
+
+def test_corner_capture_and_multi_stone_chain_capture():
+    n = 5
+    # a corner stone has two liberties
+    pos = play(Position(n), [(4, 4), (0, 0), (0, 1), (4, 0), (1, 0)], n)
+    assert pos.board[0, 0] == 0 and pos.caps == (1, 0)
+    assert pos.ko is None            # (1,0) is not enclosed by white stones
+    # a two-stone chain on the edge: white (0,1),(0,2); black needs (0,0),(1,1),(1,2),(0,3)
+    pos = play(Position(n), [(0, 0), (0, 1), (1, 1), (0, 2), (1, 2), (4, 4), (0, 3)], n)
+    assert pos.board[0, 1] == 0 and pos.board[0, 2] == 0 and pos.caps == (2, 0) and pos.ko is None
+
+
+def test_suicide_of_a_chain_is_illegal():
+    """Black (0,0) + a stone at (0,1) would form a two-stone chain with no liberty and capture nothing."""
+    n = 5
+    pos = play(Position(n), [(0, 0), (1, 0), (4, 4), (1, 1), (4, 3), (0, 2)], n)
+    assert pos.to_play == BLACK
+    assert not pos.is_move_legal((0, 1)) and pos.all_legal_moves()[1] == 0
+    with pytest.raises(IllegalMove):
+        pos.play_move((0, 1))
+    # once the white stone at (0,2) is itself in atari on that point, the same move captures it and is legal:
+    # black takes (0,3) and (1,2), white passes
+    pos = play(pos, [(0, 3), None, (1, 2), None], n)
+    assert pos.to_play == BLACK and pos.is_move_legal((0, 1))
+    pos = pos.play_move((0, 1))
+    assert pos.board[0, 2] == 0 and pos.caps[0] == 1 and pos.board[0, 0] == BLACK and pos.board[0, 1] == BLACK
+
+
+def test_tromp_taylor_counts_only_single_coloured_regions():
+    """5x5: a black wall on column 1 and a white wall on column 3: column 0 is black territory, column 4 white
+    territory, column 2 touches both (dame).  Black 5 + 5, white 5 + 5, komi decides."""
+    n = 5
+    moves = []
+    for r in range(n):
+        moves += [(r, 1), (r, 3)]
+    pos = play(Position(n, komi=0.5), moves, n)
+    assert pos.score() == -0.5 and pos.result() == -1
+    pos2 = play(Position(n, komi=0.0), moves, n)
+    assert pos2.score() == 0.0 and pos2.result() == 0
+    # a black stone inside the white territory that white does not bother to capture makes column 4 dame too
+    pos3 = play(Position(n, komi=0.5), moves + [(2, 4), None], n)
+    assert pos3.score() == 10 + 1 - 5 - 0.5

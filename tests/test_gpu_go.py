@@ -130,3 +130,45 @@ def test_goenv_reference_smoke_test():
         if len(illegal):
             with pytest.raises(ValueError):
                 env.step(int(illegal[0]))
+
+
+def test_hand_derived_positions_on_the_device():
+    """The known-answer sequences of tests/test_go_oracle.py (hand-derived: two groups captured by one move, corner
+    and chain captures, suicide of a chain, ko, Tromp-Taylor with dame) replayed through rz_go_step: boards, ko, legal
+    masks and scores on the device equal the hand-derived answers, not just the oracle's."""
+    from rlzero_b200 import _lib as L
+    GoBoards, _ = _go()
+    n = 5
+    P = n * n   # the pass
+    col_walls = [a for r in range(n) for a in (r * n + 1, r * n + 3)]
+    seqs = [
+        [1, 6, 11, 8, 5, 24, 3, 23, 13, 22, 9, 21, 7],              # (1,2) captures (1,1) and (1,3)
+        [24, 0, 1, 20, 5],                                            # corner capture
+        [0, 1, 6, 2, 7, 24, 3],                                       # two-stone chain captured on the edge
+        [0, 5, 24, 6, 23, 2],                                         # black (0,1) would be suicide
+        [1, 2, 5, 8, 11, 12, 24, 6, 7],                               # ko: black retakes at (1,2), ko at (1,1)
+        col_walls,                                                    # walls on columns 1 and 3
+        col_walls + [14, P],                                          # + a black stone inside white's column
+    ]
+    gb = GoBoards(len(seqs), n, 0.5)
+    for t in range(max(len(s) for s in seqs)):
+        gb.step([s[t] if t < len(s) else -1 for s in seqs])
+    assert not gb.faults().any()
+    boards = gb.boards()
+    meta = gb.meta.cpu().numpy()
+    legal = gb.legal_mask().cpu().numpy()
+    score, result = (x.cpu().numpy() for x in gb.score())
+    # 0: both white stones gone, no ko, (1,1) / (1,3) are suicide for white
+    assert boards[0][1, 1] == 0 and boards[0][1, 3] == 0 and boards[0][1, 2] != 0 and meta[0, L.META_KO] == -1
+    assert legal[0][6] == 0 and legal[0][8] == 0
+    # 1: the corner stone is gone, no ko
+    assert boards[1][0, 0] == 0 and meta[1, L.META_KO] == -1
+    # 2: the chain (0,1),(0,2) is gone
+    assert boards[2][0, 1] == 0 and boards[2][0, 2] == 0 and meta[2, L.META_KO] == -1
+    # 3: black to move, (0,1) is illegal (suicide of the chain), the pass is legal
+    assert meta[3, L.META_PLAYER] == 0 and legal[3][1] == 0 and legal[3][P] == 1
+    # 4: white stone at (1,1) captured, ko at (1,1): white may not retake
+    assert boards[4][1, 1] == 0 and meta[4, L.META_KO] == 6 and legal[4][6] == 0
+    # 5 / 6: Tromp-Taylor with komi 0.5: 10 - 10 - 0.5; 11 - 5 - 0.5
+    assert score[5] == -0.5 and result[5] == -1
+    assert score[6] == 5.5 and result[6] == 1
