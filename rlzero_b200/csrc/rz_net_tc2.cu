@@ -17,7 +17,9 @@
 //     17-row halo (162 rows x 128 channels = 41 KB, double buffered); tap (dy,dx) is the same
 //     tile read 16*dy+dx rows further on, i.e. only the UMMA descriptor start address moves.
 // L2->SM traffic drops to 41 KB per 128x128x1152 tile (14x less); the MMA issuer never waits
-// for operands inside a tile (72 back-to-back tcgen05.mma per tile).
+// for operands inside a tile (72 back-to-back tcgen05.mma per tile).  At the start of a launch the
+// first activation tile is requested before the weights, which complete on one mbarrier per tap, so
+// the first tile's MMAs begin after 16 KB of weights instead of all 147 KB.
 //
 // kCG = 2: the production kernel (cluster of 2).  kCG = 1: the same data path on a single CTA
 // (UMMA 128x64, each CTA computes one half of the output channels) -- kept as a bisecting aid

@@ -116,7 +116,8 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
   const uint32_t tmem_base = *tmem_holder;
 
   if (warp == 0) {
-    // ===== TMA producer: weights once, then one (tile, k-block) halo tile per ring slot =====
+    // ===== TMA producer: one (tile, k-block) halo tile per ring slot; the weights once, k-block-major, right behind
+    // the first tile's two activation k-blocks =====
     if (lane == 0) {
       auto load_weights = [&](int kb) {
         for (int tap = 0; tap < 9; ++tap) {
