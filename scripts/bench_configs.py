@@ -107,6 +107,15 @@ def main():
             run('stock PolicyValueNet 15x15, 800 sims/move, 8192 games, mode %s' % mode, sp, waves, 4)
             del sp
             torch.cuda.empty_cache()
+    if 'stock3' in only:
+        # config 1's network and board (TicTacToe, stock PolicyValueNet) with 8192 games on the tensor-core path
+        # (8-stride layout, layers zero-padded to 128 channels) against the fp32 default
+        net = PolicyValueNet(3).cuda().eval()
+        for mode in ('f32', 'tc'):
+            sp = BatchedSelfPlay(8192, 3, 3, net=net, n_playout=25, add_noise=True, seed=1, net_mode=mode)
+            run('config1 TicTacToe, stock PolicyValueNet, 8192 games, mode %s' % mode, sp, 25 * 40, 25)
+            del sp
+            torch.cuda.empty_cache()
     if '2vl' in only:
         # config 2 again with leaf-parallel waves (opt-in, not the parity mode): K playouts per game and wave make
         # the launches K times longer, which amortises the fixed cost of a short convolution launch
