@@ -43,6 +43,9 @@ def load():
         lib.rzo_search_batch.restype = C.c_int
         lib.rzo_search_batch.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
                                          C.c_int, C.c_int, i32p, f64p, i32p, f64p]
+        lib.rzo_search_batch_vl.restype = C.c_int
+        lib.rzo_search_batch_vl.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
+                                            C.c_int, C.c_int, C.c_int, C.c_double, i32p, f64p, i32p, f64p]
         _lib = lib
     return _lib
 
@@ -90,6 +93,32 @@ def search_batch(size, k, move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2):
                               w.ctypes.data_as(f64p), rn.ctypes.data_as(i32p), rw.ctypes.data_as(f64p))
     if rc:
         raise RuntimeError('rzo_search_batch failed (%d)' % rc)
+    return visits, w, rn, rw
+
+
+def search_batch_vl(size, k, move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2, leaves_per_wave=8, virtual_loss=1.0):
+    """``search_batch`` in the product's leaf-parallel mode (waves of up to ``leaves_per_wave`` playouts with virtual
+    loss; parity unpinned: the reference has no such mode)."""
+    import numpy as np
+    lib = load()
+    G, A = len(move_lists), size * size
+    mx = max(1, max((len(m) for m in move_lists), default=0))
+    mv = np.zeros((G, mx), dtype=np.int32)
+    nm = np.zeros(G, dtype=np.int32)
+    for g, m in enumerate(move_lists):
+        mv[g, :len(m)] = m
+        nm[g] = len(m)
+    visits = np.zeros((G, A), dtype=np.int32)
+    w = np.zeros((G, A), dtype=np.float64)
+    rn = np.zeros(G, dtype=np.int32)
+    rw = np.zeros(G, dtype=np.float64)
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    rc = lib.rzo_search_batch_vl(G, size, k, mv.ctypes.data_as(i32p), nm.ctypes.data_as(i32p), mx, n_playout,
+                                 float(cpuct), int(rule), int(eval_id), int(leaves_per_wave), float(virtual_loss),
+                                 visits.ctypes.data_as(i32p), w.ctypes.data_as(f64p), rn.ctypes.data_as(i32p),
+                                 rw.ctypes.data_as(f64p))
+    if rc:
+        raise RuntimeError('rzo_search_batch_vl failed (%d)' % rc)
     return visits, w, rn, rw
 
 

@@ -207,6 +207,138 @@ int rzo_search_game(int size, int k, const int32_t* moves, int n_moves, int n_pl
   return rc;
 }
 
+/* ---- the product's opt-in leaf-parallel wave (include/rlzero_b200.h, rz_tree_desc.leaves_per_tree) -------------
+ * NOT a reference algorithm (the reference has no virtual loss: PARITY UNPINNED for this mode); restated here, as in
+ * oracle/pyoracle.py Search.wave, so that the kernels can be checked at full size.  `budget` descents, each followed
+ * by one virtual visit and -vl on the value sum of every node of its path (+1 visit on the root); then the virtual
+ * statistics are taken off in reverse order (saved sums restored), and the leaves are expanded / backed up in order;
+ * a leaf reached twice is expanded once and backed up twice. */
+typedef struct { node_t* node; double w; } undo_t;
+
+static int expand_and_backup(arena_t* ar, node_t* node, board_t* b, int A, int eval_id) {
+  double v = eval_value(b, eval_id);
+  int winner;
+  if (!board_end(b, &winner)) {
+    if (!node->expanded) {
+      node->child = (node_t**)arena_alloc(ar, sizeof(node_t*) * (size_t)A);
+      if (!node->child) return -1;
+      const uint32_t h = eval_id == 2 ? board_hash(b) : 0u;
+      const int n_legal = A - b->stones;
+      for (int a = 0; a < A; ++a) {
+        node->child[a] = NULL;
+        if (b->cell[a] >= 0) continue;
+        node_t* c = (node_t*)arena_alloc(ar, sizeof(node_t));
+        if (!c) return -1;
+        c->parent = node; c->child = NULL; c->expanded = 0; c->n = 0; c->w = 0.0;
+        c->prior = eval_prior(b, eval_id, a, n_legal, h);
+        node->child[a] = c;
+      }
+      node->expanded = 1;
+    }
+  } else if (winner < 0) {
+    v = 0.0;
+  } else {
+    v = winner == b->to_move ? 1.0 : -1.0;
+  }
+  v = -v;
+  for (node_t* p = node; p; p = p->parent) { p->n += 1; p->w += v; v = -v; }
+  return 0;
+}
+
+static int wave(arena_t* ar, node_t* root, const board_t* board, int A, double cpuct, int rule, int eval_id,
+                int budget, double vl, node_t** leaf_node, board_t* leaf_board, undo_t* undo) {
+  int n_undo = 0;
+  for (int k = 0; k < budget; ++k) {
+    board_t b = *board;
+    node_t* node = root;
+    const int first = n_undo;
+    while (node->expanded) {
+      int best_a = -1; double best_s = 0.0;
+      for (int a = 0; a < A; ++a) {
+        node_t* c = node->child[a];
+        if (!c) continue;
+        const double s = node_score(c, cpuct, rule);
+        if (best_a < 0 || s > best_s) { best_a = a; best_s = s; }
+      }
+      if (best_a < 0) return -2;
+      node = node->child[best_a];
+      board_step(&b, best_a);
+      undo[n_undo].node = node; n_undo += 1;
+    }
+    leaf_node[k] = node; leaf_board[k] = b;
+    for (int i = first; i < n_undo; ++i) {
+      node_t* nd = undo[i].node;
+      undo[i].w = nd->w;
+      nd->w = nd->n > 0 ? nd->w - vl : -vl;
+      nd->n += 1;
+    }
+    root->n += 1;
+  }
+  for (int i = n_undo - 1; i >= 0; --i) { undo[i].node->w = undo[i].w; undo[i].node->n -= 1; }
+  root->n -= budget;
+  for (int k = 0; k < budget; ++k) {
+    const int rc = expand_and_backup(ar, leaf_node[k], &leaf_board[k], A, eval_id);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+/* one fresh search of n_playout playouts in waves of up to K leaves (the first wave of a fresh root takes one) */
+static int search_game_vl(int size, int k, const int32_t* moves, int n_moves, int n_playout, double cpuct, int rule,
+                          int eval_id, int K, double vl, int32_t* visits, double* w, int32_t* root_n, double* root_w) {
+  if (size < 1 || size * size > MAXC || K < 1 || K > 256) return -3;
+  const int A = size * size;
+  board_t b;
+  board_reset(&b, size, k);
+  for (int i = 0; i < n_moves; ++i) {
+    if (moves[i] < 0 || moves[i] >= A || b.cell[moves[i]] >= 0) return -4;
+    board_step(&b, moves[i]);
+  }
+  arena_t ar;
+  if (arena_init(&ar, (size_t)1 << 22)) return -1;
+  node_t* root = (node_t*)arena_alloc(&ar, sizeof(node_t));
+  memset(root, 0, sizeof(*root));
+  root->prior = 1.0;
+  node_t** leaf_node = (node_t**)malloc(sizeof(node_t*) * (size_t)K);
+  board_t* leaf_board = (board_t*)malloc(sizeof(board_t) * (size_t)K);
+  undo_t* undo = (undo_t*)malloc(sizeof(undo_t) * (size_t)K * (size_t)(A + 1));
+  int rc = (leaf_node && leaf_board && undo) ? 0 : -1;
+  const int target = root->n + n_playout;
+  while (rc == 0 && root->n < target) {
+    int budget = target - root->n < K ? target - root->n : K;
+    if (!root->expanded) budget = 1;
+    rc = wave(&ar, root, &b, A, cpuct, rule, eval_id, budget, vl, leaf_node, leaf_board, undo);
+  }
+  if (rc == 0) {
+    for (int a = 0; a < A; ++a) {
+      node_t* c = root->expanded ? root->child[a] : NULL;
+      visits[a] = c ? c->n : 0;
+      w[a] = c ? c->w : 0.0;
+    }
+    *root_n = root->n; *root_w = root->w;
+  }
+  free(leaf_node); free(leaf_board); free(undo);
+  arena_free(&ar);
+  return rc;
+}
+
+int rzo_search_batch_vl(int G, int size, int k, const int32_t* moves, const int32_t* n_moves, int max_moves,
+                        int n_playout, double cpuct, int rule, int eval_id, int K, double vl, int32_t* visits,
+                        double* w, int32_t* root_n, double* root_w) {
+  const int A = size * size;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int g = 0; g < G; ++g) {
+    const int rc = search_game_vl(size, k, moves + (size_t)g * max_moves, n_moves[g], n_playout, cpuct, rule, eval_id,
+                                  K, vl, visits + (size_t)g * A, w + (size_t)g * A, root_n + g, root_w + g);
+    if (rc) {
+#pragma omp atomic write
+      bad = rc;
+    }
+  }
+  return bad;
+}
+
 /* G independent games in parallel over the host cores (OpenMP): moves [G][max_moves] with n_moves[G]. */
 int rzo_search_batch(int G, int size, int k, const int32_t* moves, const int32_t* n_moves, int max_moves,
                      int n_playout, double cpuct, int rule, int eval_id, int32_t* visits, double* w,

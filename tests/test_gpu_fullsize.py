@@ -128,3 +128,34 @@ def test_all_8192_trees_at_800_playouts_equal_the_c_oracle(rule):
     # the root's own sum: the engine keeps the reference's sign convention (root gets -v of the leaf chain)
     assert np.array_equal(root_w[live].view(np.int64), crw[live].view(np.int64))
     assert (visits[live].sum(1) == n_playout - 1).all()
+
+
+@pytest.mark.parametrize('rule,leaves', [(0, 8), (1, 16)])
+def test_all_8192_trees_leaf_parallel_equal_the_c_oracle_wave(rule, leaves):
+    """The opt-in leaf-parallel mode at BASELINE config-3 size, every tree checked: 8192 games, 800 playouts in waves
+    of up to `leaves` playouts per tree with virtual loss -- bit-identical to the plain-C restatement of that wave
+    (oracle/c/rz_oracle.c rzo_search_batch_vl; parity unpinned against the reference, which has no such mode)."""
+    from oracle import build_oracle
+    from oracle.evaluators import EVAL_HASH
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import ClosedFormEvaluator, SearchForest
+    n_playout = 800
+    lists = []
+    for g in range(G):
+        rs = np.random.RandomState(1000 + g)
+        lists.append([int(m) for m in rs.permutation(H * H)[:(1000 + g) % 31]])
+    f = SearchForest(G, H, K, n_playout=n_playout, c_puct=5.0, rule=rule, max_carry=0, leaves_per_tree=leaves)
+    f.set_positions(lists)
+    meta = f.boards()[1]
+    live = meta[:, L.META_STATUS] == L.ACTIVE
+    f.search(ClosedFormEvaluator(EVAL_HASH))
+    torch.cuda.synchronize()
+    f.raise_faults()
+    visits, w, has, root_n, root_w = f.root_stats()
+    cv, cw, crn, crw = build_oracle.search_batch_vl(H, K, lists, n_playout, 5.0, rule, EVAL_HASH, leaves, 1.0)
+    assert live.sum() > G - 64
+    assert np.array_equal(visits[live], cv[live])
+    assert np.array_equal(w[live].view(np.int64), cw[live].view(np.int64))
+    assert np.array_equal(root_n[live], crn[live]) and (root_n[live] == n_playout).all()
+    assert np.array_equal(root_w[live].view(np.int64), crw[live].view(np.int64))
+    assert (visits[live].sum(1) == n_playout - 1).all()

@@ -52,3 +52,32 @@ def test_c_oracle_matches_python_restatement_on_random_positions(size, k, n_play
         assert visits[g].tolist() == s.root_visits(size * size).tolist(), g
         assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(size * size)], g
         assert int(rn[g]) == s.root.n and float(rw[g]) == float(s.root.w)
+
+
+@pytest.mark.parametrize('size,k,n_playout,rule,K,vl', [(3, 3, 90, 0, 4, 1.0), (6, 4, 200, 0, 8, 1.0),
+                                                        (8, 5, 250, 1, 16, 1.0), (5, 4, 300, 0, 32, 0.5)])
+def test_c_oracle_leaf_parallel_wave_matches_python_restatement(size, k, n_playout, rule, K, vl):
+    """The leaf-parallel wave (the product's opt-in mode, parity unpinned) restated twice -- oracle/c/rz_oracle.c and
+    pyoracle.Search.wave -- must agree bit for bit; the C one checks the kernels at full size."""
+    rs = np.random.RandomState(size * 11 + K)
+    lists, boards = [], []
+    while len(lists) < 8:
+        b = pyoracle.Board(size, k)
+        b.reset()
+        mv = [int(x) for x in rs.permutation(size * size)[:rs.randint(0, size * size - 1)]]
+        ok = True
+        for a in mv:
+            b.step(a)
+            if b.game_end_winner()[0]:
+                ok = False
+                break
+        if ok:
+            lists.append(mv)
+            boards.append(b)
+    visits, w, rn, rw = build_oracle.search_batch_vl(size, k, lists, n_playout, 2.5, rule, 2, K, vl)
+    for g, b in enumerate(boards):
+        s = pyoracle.Search(make_policy_value_fn(2), n_playout, 2.5, rule=rule, leaves_per_wave=K, virtual_loss=vl)
+        s.simulate(b, 1.0)
+        assert visits[g].tolist() == s.root_visits(size * size).tolist(), g
+        assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(size * size)], g
+        assert int(rn[g]) == s.root.n and float(rw[g]) == float(s.root.w)
