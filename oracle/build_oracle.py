@@ -46,6 +46,9 @@ def load():
         lib.rzo_search_batch_vl.restype = C.c_int
         lib.rzo_search_batch_vl.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
                                             C.c_int, C.c_int, C.c_int, C.c_double, i32p, f64p, i32p, f64p]
+        lib.rzo_search_batch_c4.restype = C.c_int
+        lib.rzo_search_batch_c4.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
+                                            C.c_int, C.c_int, C.c_int, C.c_double, i32p, f64p, i32p, f64p]
         _lib = lib
     return _lib
 
@@ -119,6 +122,33 @@ def search_batch_vl(size, k, move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2
                                  rw.ctypes.data_as(f64p))
     if rc:
         raise RuntimeError('rzo_search_batch_vl failed (%d)' % rc)
+    return visits, w, rn, rw
+
+
+def search_batch_c4(move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2, rows=6, cols=7, k=4, leaves_per_wave=1,
+                    virtual_loss=1.0):
+    """Connect Four (actions = columns): one fresh search per game; ``leaves_per_wave = 1`` is the reference's
+    sequential search over that game.  Returns (visits [G,cols], W [G,cols], root_N [G], root_W [G])."""
+    import numpy as np
+    lib = load()
+    G = len(move_lists)
+    mx = max(1, max((len(m) for m in move_lists), default=0))
+    mv = np.zeros((G, mx), dtype=np.int32)
+    nm = np.zeros(G, dtype=np.int32)
+    for g, m in enumerate(move_lists):
+        mv[g, :len(m)] = m
+        nm[g] = len(m)
+    visits = np.zeros((G, cols), dtype=np.int32)
+    w = np.zeros((G, cols), dtype=np.float64)
+    rn = np.zeros(G, dtype=np.int32)
+    rw = np.zeros(G, dtype=np.float64)
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    rc = lib.rzo_search_batch_c4(G, rows, cols, k, mv.ctypes.data_as(i32p), nm.ctypes.data_as(i32p), mx, n_playout,
+                                 float(cpuct), int(rule), int(eval_id), int(leaves_per_wave), float(virtual_loss),
+                                 visits.ctypes.data_as(i32p), w.ctypes.data_as(f64p), rn.ctypes.data_as(i32p),
+                                 rw.ctypes.data_as(f64p))
+    if rc:
+        raise RuntimeError('rzo_search_batch_c4 failed (%d)' % rc)
     return visits, w, rn, rw
 
 

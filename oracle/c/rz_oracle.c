@@ -25,8 +25,12 @@
 #define MAXC 361
 
 typedef struct {
-  int n, k;
-  int8_t cell[MAXC];      /* -1 empty, 0 / 1 */
+  int rows, cols, k;
+  int gravity;            /* 0: an action is a square (Gomoku, gomoku_env.py); 1: an action is a column and the stone
+                             drops to the lowest empty row (Connect Four: oracle/pyoracle.py ConnectFourBoard, the CPU
+                             definition of RZ_GAME_CONNECT4 -- the reference has no such game) */
+  int8_t cell[MAXC];      /* -1 empty, 0 / 1; square index r * cols + c (row 0 at the bottom for gravity games) */
+  int8_t height[19];      /* gravity: stones in each column */
   int stones, last_move, to_move;
 } board_t;
 
@@ -68,28 +72,39 @@ static int arena_init(arena_t* a, size_t cap) {
   return 0;
 }
 
-static void board_reset(board_t* b, int n, int k) {
-  b->n = n; b->k = k;
+static void board_reset(board_t* b, int rows, int cols, int k, int gravity) {
+  b->rows = rows; b->cols = cols; b->k = k; b->gravity = gravity;
   memset(b->cell, -1, sizeof(b->cell));
+  memset(b->height, 0, sizeof(b->height));
   b->stones = 0; b->last_move = -1; b->to_move = 0;
 }
+static int board_actions(const board_t* b) { return b->gravity ? b->cols : b->rows * b->cols; }
+static int board_legal(const board_t* b, int a) { return b->gravity ? b->height[a] < b->rows : b->cell[a] < 0; }
+static int board_n_legal(const board_t* b) {
+  if (!b->gravity) return b->rows * b->cols - b->stones;
+  int n = 0;
+  for (int c = 0; c < b->cols; ++c) n += b->height[c] < b->rows;
+  return n;
+}
 static void board_step(board_t* b, int a) {
-  b->cell[a] = (int8_t)b->to_move;
-  b->stones += 1; b->last_move = a; b->to_move ^= 1;
+  int cell = a;
+  if (b->gravity) { cell = b->height[a] * b->cols + a; b->height[a] += 1; }
+  b->cell[cell] = (int8_t)b->to_move;
+  b->stones += 1; b->last_move = cell; b->to_move ^= 1;
 }
 /* gomoku_env.py:116-170: for every stone, the four directions with the reference's edge guards */
 static int board_winner(const board_t* b) {
-  const int n = b->n, k = b->k;
+  const int n = b->cols, nr = b->rows, k = b->k;     /* square boards: n == nr, the reference's width == height */
   if (b->stones < 2 * k - 1) return -1;
-  for (int m = 0; m < n * n; ++m) {
+  for (int m = 0; m < nr * n; ++m) {
     const int p = b->cell[m];
     if (p < 0) continue;
     const int h = m / n, w = m % n;
     int ok;
     if (w <= n - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i] == p; if (ok) return p; }
-    if (h <= n - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i * n] == p; if (ok) return p; }
-    if (w <= n - k && h <= n - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i * (n + 1)] == p; if (ok) return p; }
-    if (w >= k - 1 && h <= n - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i * (n - 1)] == p; if (ok) return p; }
+    if (h <= nr - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i * n] == p; if (ok) return p; }
+    if (w <= n - k && h <= nr - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i * (n + 1)] == p; if (ok) return p; }
+    if (w >= k - 1 && h <= nr - k) { ok = 1; for (int i = 1; i < k && ok; ++i) ok = b->cell[m + i * (n - 1)] == p; if (ok) return p; }
   }
   return -1;
 }
@@ -97,13 +112,13 @@ static int board_winner(const board_t* b) {
 static int board_end(const board_t* b, int* winner) {
   *winner = board_winner(b);
   if (*winner >= 0) return 1;
-  return b->stones >= b->n * b->n;
+  return b->stones >= b->rows * b->cols;
 }
 
 /* oracle/evaluators.py */
 static uint32_t board_hash(const board_t* b) {
   uint32_t h = 0;
-  for (int m = 0; m < b->n * b->n; ++m)
+  for (int m = 0; m < b->rows * b->cols; ++m)
     if (b->cell[m] >= 0) h += (uint32_t)(m + 1) * (uint32_t)(m + 1) * (3u + 4u * (uint32_t)b->cell[m]);
   h += 7u * (uint32_t)(b->last_move + 1);
   return h * 2654435761u;
@@ -145,10 +160,10 @@ static int playout(arena_t* ar, node_t* root, board_t b, int A, double cpuct, in
     node->child = (node_t**)arena_alloc(ar, sizeof(node_t*) * (size_t)A);
     if (!node->child) return -1;
     const uint32_t h = eval_id == 2 ? board_hash(&b) : 0u;
-    const int n_legal = A - b.stones;
+    const int n_legal = board_n_legal(&b);
     for (int a = 0; a < A; ++a) {
       node->child[a] = NULL;
-      if (b.cell[a] >= 0) continue;
+      if (!board_legal(&b, a)) continue;
       node_t* c = (node_t*)arena_alloc(ar, sizeof(node_t));
       if (!c) return -1;
       c->parent = node; c->child = NULL; c->expanded = 0; c->n = 0; c->w = 0.0;
@@ -175,7 +190,7 @@ int rzo_search_game(int size, int k, const int32_t* moves, int n_moves, int n_pl
   if (size < 1 || size * size > MAXC) return -3;
   const int A = size * size;
   board_t b;
-  board_reset(&b, size, k);
+  board_reset(&b, size, size, k, 0);
   for (int i = 0; i < n_moves; ++i) {
     if (moves[i] < 0 || moves[i] >= A || b.cell[moves[i]] >= 0) return -4;
     board_step(&b, moves[i]);
@@ -223,10 +238,10 @@ static int expand_and_backup(arena_t* ar, node_t* node, board_t* b, int A, int e
       node->child = (node_t**)arena_alloc(ar, sizeof(node_t*) * (size_t)A);
       if (!node->child) return -1;
       const uint32_t h = eval_id == 2 ? board_hash(b) : 0u;
-      const int n_legal = A - b->stones;
+      const int n_legal = board_n_legal(b);
       for (int a = 0; a < A; ++a) {
         node->child[a] = NULL;
-        if (b->cell[a] >= 0) continue;
+        if (!board_legal(b, a)) continue;
         node_t* c = (node_t*)arena_alloc(ar, sizeof(node_t));
         if (!c) return -1;
         c->parent = node; c->child = NULL; c->expanded = 0; c->n = 0; c->w = 0.0;
@@ -284,14 +299,15 @@ static int wave(arena_t* ar, node_t* root, const board_t* board, int A, double c
 }
 
 /* one fresh search of n_playout playouts in waves of up to K leaves (the first wave of a fresh root takes one) */
-static int search_game_vl(int size, int k, const int32_t* moves, int n_moves, int n_playout, double cpuct, int rule,
-                          int eval_id, int K, double vl, int32_t* visits, double* w, int32_t* root_n, double* root_w) {
-  if (size < 1 || size * size > MAXC || K < 1 || K > 256) return -3;
-  const int A = size * size;
+static int search_game_vl(int rows, int cols, int gravity, int k, const int32_t* moves, int n_moves, int n_playout,
+                          double cpuct, int rule, int eval_id, int K, double vl, int32_t* visits, double* w,
+                          int32_t* root_n, double* root_w) {
+  if (rows < 1 || cols < 1 || cols > 19 || rows * cols > MAXC || K < 1 || K > 256) return -3;
   board_t b;
-  board_reset(&b, size, k);
+  board_reset(&b, rows, cols, k, gravity);
+  const int A = board_actions(&b);
   for (int i = 0; i < n_moves; ++i) {
-    if (moves[i] < 0 || moves[i] >= A || b.cell[moves[i]] >= 0) return -4;
+    if (moves[i] < 0 || moves[i] >= A || !board_legal(&b, moves[i])) return -4;
     board_step(&b, moves[i]);
   }
   arena_t ar;
@@ -301,10 +317,11 @@ static int search_game_vl(int size, int k, const int32_t* moves, int n_moves, in
   root->prior = 1.0;
   node_t** leaf_node = (node_t**)malloc(sizeof(node_t*) * (size_t)K);
   board_t* leaf_board = (board_t*)malloc(sizeof(board_t) * (size_t)K);
-  undo_t* undo = (undo_t*)malloc(sizeof(undo_t) * (size_t)K * (size_t)(A + 1));
+  undo_t* undo = (undo_t*)malloc(sizeof(undo_t) * (size_t)K * (size_t)(rows * cols + 1));
   int rc = (leaf_node && leaf_board && undo) ? 0 : -1;
   const int target = root->n + n_playout;
   while (rc == 0 && root->n < target) {
+    if (K == 1) { rc = playout(&ar, root, b, A, cpuct, rule, eval_id); continue; }   /* the sequential reference search */
     int budget = target - root->n < K ? target - root->n : K;
     if (!root->expanded) budget = 1;
     rc = wave(&ar, root, &b, A, cpuct, rule, eval_id, budget, vl, leaf_node, leaf_board, undo);
@@ -329,8 +346,27 @@ int rzo_search_batch_vl(int G, int size, int k, const int32_t* moves, const int3
   int bad = 0;
 #pragma omp parallel for schedule(dynamic, 8)
   for (int g = 0; g < G; ++g) {
-    const int rc = search_game_vl(size, k, moves + (size_t)g * max_moves, n_moves[g], n_playout, cpuct, rule, eval_id,
-                                  K, vl, visits + (size_t)g * A, w + (size_t)g * A, root_n + g, root_w + g);
+    const int rc = search_game_vl(size, size, 0, k, moves + (size_t)g * max_moves, n_moves[g], n_playout, cpuct, rule,
+                                  eval_id, K, vl, visits + (size_t)g * A, w + (size_t)g * A, root_n + g, root_w + g);
+    if (rc) {
+#pragma omp atomic write
+      bad = rc;
+    }
+  }
+  return bad;
+}
+
+/* Connect Four (gravity, rows x cols, actions = columns): K = 1 is the reference's sequential search over that game,
+ * K > 1 the leaf-parallel wave.  visits / w: [G][cols]. */
+int rzo_search_batch_c4(int G, int rows, int cols, int k, const int32_t* moves, const int32_t* n_moves, int max_moves,
+                        int n_playout, double cpuct, int rule, int eval_id, int K, double vl, int32_t* visits,
+                        double* w, int32_t* root_n, double* root_w) {
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int g = 0; g < G; ++g) {
+    const int rc = search_game_vl(rows, cols, 1, k, moves + (size_t)g * max_moves, n_moves[g], n_playout, cpuct, rule,
+                                  eval_id, K, vl, visits + (size_t)g * cols, w + (size_t)g * cols, root_n + g,
+                                  root_w + g);
     if (rc) {
 #pragma omp atomic write
       bad = rc;

@@ -159,3 +159,36 @@ def test_all_8192_trees_leaf_parallel_equal_the_c_oracle_wave(rule, leaves):
     assert np.array_equal(root_n[live], crn[live]) and (root_n[live] == n_playout).all()
     assert np.array_equal(root_w[live].view(np.int64), crw[live].view(np.int64))
     assert (visits[live].sum(1) == n_playout - 1).all()
+
+
+@pytest.mark.parametrize('rule,leaves', [(0, 1), (1, 1), (0, 8)])
+def test_config2_all_4096_connect_four_trees_equal_the_c_oracle(rule, leaves):
+    """BASELINE config-2 size, every tree checked: 4096 Connect Four games (6x7, gravity, 7 actions), 200 playouts
+    each, closed-form HASH evaluator on both sides: visit counts, fp64 value sums and root statistics of ALL trees are
+    bit-identical to the C oracle's search over that game (sequential = the reference's MCTS algorithm, pinned through
+    tests/golden/connect4.json and tests/test_oracle_c.py; leaves = 8: the leaf-parallel wave)."""
+    from oracle import build_oracle
+    from oracle.evaluators import EVAL_HASH
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import ClosedFormEvaluator, SearchForest
+    G2, n_playout = 4096, 200
+    lists = []
+    for g in range(G2):
+        rs = np.random.RandomState(1000 + g)
+        lists.append([int(m) for m in rs.permutation(np.repeat(np.arange(7), 6))[:(1000 + g) % 13]])
+    f = SearchForest(G2, 6, 4, n_playout=n_playout, c_puct=5.0, rule=rule, max_carry=0, board_width=7,
+                     game_type=L.GAME_CONNECT4, leaves_per_tree=leaves)
+    f.set_positions(lists)
+    live = f.boards()[1][:, L.META_STATUS] == L.ACTIVE
+    f.search(ClosedFormEvaluator(EVAL_HASH))
+    torch.cuda.synchronize()
+    f.raise_faults()
+    visits, w, has, root_n, root_w = f.root_stats()
+    # the C oracle refuses a move list that runs into a finished game; search only the live ones
+    idx = np.nonzero(live)[0]
+    cv, cw, crn, crw = build_oracle.search_batch_c4([lists[i] for i in idx], n_playout, 5.0, rule, EVAL_HASH,
+                                                    leaves_per_wave=leaves)
+    assert len(idx) > G2 - 256
+    assert np.array_equal(visits[idx], cv)
+    assert np.array_equal(w[idx].view(np.int64), cw.view(np.int64))
+    assert np.array_equal(root_n[idx], crn) and np.array_equal(root_w[idx].view(np.int64), crw.view(np.int64))

@@ -81,3 +81,31 @@ def test_c_oracle_leaf_parallel_wave_matches_python_restatement(size, k, n_playo
         assert visits[g].tolist() == s.root_visits(size * size).tolist(), g
         assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(size * size)], g
         assert int(rn[g]) == s.root.n and float(rw[g]) == float(s.root.w)
+
+
+@pytest.mark.parametrize('n_playout,rule,K', [(200, 0, 1), (300, 1, 1), (250, 0, 8)])
+def test_c_oracle_connect_four_matches_python_restatement(n_playout, rule, K):
+    """Connect Four in the C oracle (gravity, 6x7, actions = columns) against pyoracle.ConnectFourBoard -- which the
+    live reference MCTS pins through tests/golden/connect4.json -- for the sequential search and the leaf-parallel wave."""
+    rs = np.random.RandomState(n_playout + K)
+    lists, boards = [], []
+    while len(lists) < 10:
+        b = pyoracle.ConnectFourBoard()
+        b.reset()
+        mv = [int(x) for x in rs.permutation(np.repeat(np.arange(7), 6))[:rs.randint(0, 30)]]
+        ok = True
+        for a in mv:
+            b.step(a)
+            if b.game_end_winner()[0]:
+                ok = False
+                break
+        if ok:
+            lists.append(mv)
+            boards.append(b)
+    visits, w, rn, rw = build_oracle.search_batch_c4(lists, n_playout, 5.0, rule, 2, leaves_per_wave=K)
+    for g, b in enumerate(boards):
+        s = pyoracle.Search(make_policy_value_fn(2), n_playout, 5.0, rule=rule, leaves_per_wave=K)
+        s.simulate(b, 1.0)
+        assert visits[g].tolist() == s.root_visits(7).tolist(), g
+        assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(7)], g
+        assert int(rn[g]) == s.root.n and float(rw[g]) == float(s.root.w)
