@@ -38,6 +38,13 @@ CASES = [
     (3, 3, [4, 0, 8, 2], 400, 'uct', True, 2, None),
     (3, 3, [4, 0, 8, 2, 1], 400, 'puct', True, 2, None),
     (4, 3, [0, 4, 1, 5, 8, 2, 9, 7, 12, 10, 3], 600, 'puct', True, 2, None),
+    # larger boards and budgets (added at the end of round 1)
+    (9, 5, [40, 41, 31, 32, 49], 400, 'uct', False, 2, None),
+    (9, 5, [40, 41, 31, 32, 49, 22], 600, 'puct', True, 2, 3),
+    (15, 5, [112, 113, 97, 98, 127], 500, 'uct', True, 2, None),
+    (15, 5, [], 400, 'puct', False, 1, None),
+    (7, 4, [24, 25, 17, 18, 31], 500, 'puct', True, 2, None),
+    (6, 4, [14, 15, 20, 21, 8, 9], 300, 'uct', True, 2, 7),
 ]
 
 
