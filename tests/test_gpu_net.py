@@ -551,3 +551,37 @@ def test_stock_net_on_the_tensor_core_path(size, n):
     env.reset()
     acts, probs = AlphaZeroMCTS(agent.policy_value_fn, n_playout=40).simulate(env, 1.0)
     assert len(acts) == size * size and abs(probs.sum() - 1.0) < 1e-9
+
+
+@pytest.mark.parametrize('h,cin,cout,relu,res', [(15, 64, 128, 1, 0), (15, 4, 32, 1, 0), (9, 32, 64, 0, 1), (19, 64, 128, 1, 1)])
+def test_fp32_conv_tiled_and_scalar_kernels_are_bit_identical(h, cin, cout, relu, res):
+    """rz_net_conv3x3_f32 picks the register-tiled kernel for batches (>= 64 boards) and the scalar one for a handful
+    of boards: the same boards through both give the same bits (same fmaf order per output), and match PyTorch."""
+    from rlzero_b200 import _lib as L
+    lib = L.load()
+    torch.manual_seed(h + cin)
+    n = 96
+    x = torch.randn(n, h * h, cin, device='cuda')
+    w = (torch.randn(9, cin, cout, device='cuda') / (3.0 * cin ** 0.5)).contiguous()
+    b = torch.randn(cout, device='cuda') * 0.1
+    r = torch.randn(n, h * h, cout, device='cuda') if res else None
+    big = torch.full((n, h * h, cout), 7.0, device='cuda')
+    L.check(lib.rz_net_conv3x3_f32(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(r), L.ptr(big), n, h, cin, cout, relu,
+                                   L.stream_ptr()), 'tiled')
+    small = torch.full((n, h * h, cout), 5.0, device='cuda')
+    for i in range(0, n, 32):
+        rr = r[i:i + 32].contiguous() if res else None
+        xi, oi = x[i:i + 32].contiguous(), torch.empty(32, h * h, cout, device='cuda')
+        L.check(lib.rz_net_conv3x3_f32(L.ptr(xi), L.ptr(w), L.ptr(b), L.ptr(rr), L.ptr(oi), 32, h, cin, cout, relu,
+                                       L.stream_ptr()), 'scalar')
+        small[i:i + 32] = oi
+    torch.cuda.synchronize()
+    assert torch.equal(big, small)
+    xt = x.reshape(n, h, h, cin).permute(0, 3, 1, 2).double()
+    wt = w.reshape(3, 3, cin, cout).permute(3, 2, 0, 1).double()
+    ref = torch.nn.functional.conv2d(xt, wt, b.double(), padding=1).permute(0, 2, 3, 1).reshape(n, h * h, cout)
+    if res:
+        ref = ref + r.double()
+    if relu:
+        ref = torch.relu(ref)
+    assert (big.double() - ref).abs().max().item() < 1e-4
