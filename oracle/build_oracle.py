@@ -49,6 +49,9 @@ def load():
         lib.rzo_search_batch_c4.restype = C.c_int
         lib.rzo_search_batch_c4.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
                                             C.c_int, C.c_int, C.c_int, C.c_double, i32p, f64p, i32p, f64p]
+        lib.rzo_dm_search_batch.restype = C.c_int
+        lib.rzo_dm_search_batch.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double, C.c_int,
+                                            C.c_int, C.c_int, C.c_int, i32p, f64p, i32p, i32p, f64p, i32p, i32p]
         _lib = lib
     return _lib
 
@@ -150,6 +153,35 @@ def search_batch_c4(move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2, rows=6,
     if rc:
         raise RuntimeError('rzo_search_batch_c4 failed (%d)' % rc)
     return visits, w, rn, rw
+
+
+def dm_search_batch(size, k, move_lists, sims, uct_c=2.0, method='puct', solve=True, returns_mode=0, eval_id=2):
+    """The reference's DeepMindMCTS (no shuffle, no noise) on every position.  Returns a dict of arrays: visits [G,A]
+    (-1 = not a root child), w [G,A], outcome [G,A] (0 none, else 0x100 | (o0+1) | (o1+1) << 2), root_n, root_w,
+    root_outcome, best [G]."""
+    import numpy as np
+    lib = load()
+    G, A = len(move_lists), size * size
+    mx = max(1, max((len(m) for m in move_lists), default=0))
+    mv = np.zeros((G, mx), dtype=np.int32)
+    nm = np.zeros(G, dtype=np.int32)
+    for g, m in enumerate(move_lists):
+        mv[g, :len(m)] = m
+        nm[g] = len(m)
+    out = dict(visits=np.zeros((G, A), dtype=np.int32), w=np.zeros((G, A), dtype=np.float64),
+               outcome=np.zeros((G, A), dtype=np.int32), root_n=np.zeros(G, dtype=np.int32),
+               root_w=np.zeros(G, dtype=np.float64), root_outcome=np.zeros(G, dtype=np.int32),
+               best=np.zeros(G, dtype=np.int32))
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    rc = lib.rzo_dm_search_batch(G, size, k, mv.ctypes.data_as(i32p), nm.ctypes.data_as(i32p), mx, int(sims),
+                                 float(uct_c), 1 if method == 'puct' else 0, int(bool(solve)), int(returns_mode),
+                                 int(eval_id), out['visits'].ctypes.data_as(i32p), out['w'].ctypes.data_as(f64p),
+                                 out['outcome'].ctypes.data_as(i32p), out['root_n'].ctypes.data_as(i32p),
+                                 out['root_w'].ctypes.data_as(f64p), out['root_outcome'].ctypes.data_as(i32p),
+                                 out['best'].ctypes.data_as(i32p))
+    if rc:
+        raise RuntimeError('rzo_dm_search_batch failed (%d)' % rc)
+    return out
 
 
 if __name__ == '__main__':

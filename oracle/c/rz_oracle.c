@@ -356,6 +356,155 @@ int rzo_search_batch_vl(int G, int size, int k, const int32_t* moves, const int3
   return bad;
 }
 
+/* ---- the reference's second search driver, DeepMindMCTS (rlzero/mcts/deepmind_mcts.py:65-175,384-646) -------------
+ *   SearchNode.uct_value / puct_value with the outcome shortcut   :106-151
+ *   sort_key / best_child                                         :153-175
+ *   _apply_tree_policy (children created on a node's second visit, first maximum; no shuffle, no noise here) :477-528
+ *   mcts_search (returns indexed by the player who moved, terminal outcomes, MCTS-Solver, early stop)       :554-646
+ * returns_mode 0: GomokuEnv.returns() literally (gomoku_env.py:216-219 tests winner == 1 / == 2 although the players
+ * are 0 / 1: a win of player 1 yields [1,-1], everything else [0,0]); 1: the zero-sum intent. */
+typedef struct dnode_s {
+  int action, player, n, n_children, has_outcome;
+  int o[2];
+  double prior, w;
+  struct dnode_s* children;
+} dnode_t;
+
+static double dnode_score(const dnode_t* c, int parent_n, double uct_c, int rule) {
+  if (c->has_outcome) return (double)c->o[c->player];
+  if (rule == 1) return (c->n ? c->w / (double)c->n : 0.0) + uct_c * c->prior * sqrt((double)parent_n) / (double)(c->n + 1);
+  if (c->n == 0) return INFINITY;
+  return c->w / (double)c->n + uct_c * sqrt(log((double)parent_n) / (double)c->n);
+}
+
+static void board_returns(const board_t* b, int mode, int winner, int* r) {
+  r[0] = 0; r[1] = 0;
+  if (winner < 0) return;
+  if (mode == 0) { if (winner == 1) { r[0] = 1; r[1] = -1; } return; }
+  r[0] = winner == 0 ? 1 : -1; r[1] = -r[0];
+  (void)b;
+}
+
+/* One search; outputs per action a: visits[a] (-1 = not a root child), w[a], outcome code[a] (0 none, else
+ * 0x100 | (o0+1) | (o1+1) << 2), and root_n, root_w, root outcome code, best_child action. */
+static int dm_search_game(int size, int k, const int32_t* moves, int n_moves, int sims, double uct_c, int rule,
+                          int solve, int returns_mode, int eval_id, int32_t* visits, double* w, int32_t* outcome,
+                          int32_t* root_n, double* root_w, int32_t* root_o, int32_t* best_a) {
+  if (size < 1 || size * size > MAXC) return -3;
+  const int A = size * size;
+  board_t b0;
+  board_reset(&b0, size, size, k, 0);
+  for (int i = 0; i < n_moves; ++i) {
+    if (moves[i] < 0 || moves[i] >= A || b0.cell[moves[i]] >= 0) return -4;
+    board_step(&b0, moves[i]);
+  }
+  arena_t ar;
+  if (arena_init(&ar, (size_t)1 << 22)) return -1;
+  dnode_t* root = (dnode_t*)arena_alloc(&ar, sizeof(dnode_t));
+  memset(root, 0, sizeof(*root));
+  root->action = -1; root->player = b0.to_move; root->prior = 1.0;
+  dnode_t** path = (dnode_t**)malloc(sizeof(dnode_t*) * (size_t)(A + 2));
+  int rc = path ? 0 : -1;
+  for (int s = 0; s < sims && rc == 0; ++s) {
+    board_t work = b0;
+    dnode_t* node = root;
+    int depth = 0, winner = -1, ended;
+    path[depth++] = node;
+    while (!(ended = board_end(&work, &winner)) && node->n > 0) {
+      if (!node->children) {
+        const int nl = board_n_legal(&work);
+        node->children = (dnode_t*)arena_alloc(&ar, sizeof(dnode_t) * (size_t)nl);
+        if (!node->children) { rc = -1; break; }
+        const uint32_t h = eval_id == 2 ? board_hash(&work) : 0u;
+        int j = 0;
+        for (int a = 0; a < A; ++a) {
+          if (!board_legal(&work, a)) continue;
+          dnode_t* c = &node->children[j++];
+          memset(c, 0, sizeof(*c));
+          c->action = a; c->player = work.to_move; c->prior = eval_prior(&work, eval_id, a, nl, h);
+        }
+        node->n_children = nl;
+      }
+      dnode_t* best = NULL; double best_s = 0.0;
+      for (int j = 0; j < node->n_children; ++j) {
+        const double sc = dnode_score(&node->children[j], node->n, uct_c, rule);
+        if (!best || sc > best_s) { best = &node->children[j]; best_s = sc; }
+      }
+      board_step(&work, best->action);
+      node = best;
+      path[depth++] = node;
+    }
+    if (rc) break;
+    double ret[2];
+    int solved = 0;
+    if (ended) {
+      int r[2];
+      board_returns(&work, returns_mode, winner, r);
+      ret[0] = (double)r[0]; ret[1] = (double)r[1];
+      dnode_t* leaf = path[depth - 1];
+      leaf->has_outcome = 1; leaf->o[0] = r[0]; leaf->o[1] = r[1];
+      solved = solve;
+    } else {
+      const double v = eval_value(&work, eval_id);
+      ret[work.to_move] = v; ret[1 - work.to_move] = -v;
+    }
+    while (depth > 0) {
+      dnode_t* nd = path[--depth];
+      nd->w += ret[nd->player];
+      nd->n += 1;
+      if (solved && nd->children) {
+        const int player = nd->children[0].player;
+        dnode_t* best = NULL; int all_solved = 1;
+        for (int j = 0; j < nd->n_children; ++j) {
+          dnode_t* c = &nd->children[j];
+          if (!c->has_outcome) all_solved = 0;
+          else if (!best || c->o[player] > best->o[player]) best = c;
+        }
+        if (best && (all_solved || best->o[player] == 1)) { nd->has_outcome = 1; nd->o[0] = best->o[0]; nd->o[1] = best->o[1]; }
+        else solved = 0;
+      }
+    }
+    if (root->has_outcome) break;
+  }
+  if (rc == 0) {
+    for (int a = 0; a < A; ++a) { visits[a] = -1; w[a] = 0.0; outcome[a] = 0; }
+    dnode_t* best = NULL;
+    for (int j = 0; j < root->n_children; ++j) {
+      dnode_t* c = &root->children[j];
+      visits[c->action] = c->n; w[c->action] = c->w;
+      outcome[c->action] = c->has_outcome ? (0x100 | (c->o[0] + 1) | ((c->o[1] + 1) << 2)) : 0;
+      if (!best) { best = c; continue; }
+      /* sort_key (:153-171): (outcome[player] or 0, explore_count, total_reward), first maximum */
+      const int ko = c->has_outcome ? c->o[c->player] : 0, kb = best->has_outcome ? best->o[best->player] : 0;
+      if (ko > kb || (ko == kb && (c->n > best->n || (c->n == best->n && c->w > best->w)))) best = c;
+    }
+    *root_n = root->n; *root_w = root->w;
+    *root_o = root->has_outcome ? (0x100 | (root->o[0] + 1) | ((root->o[1] + 1) << 2)) : 0;
+    *best_a = best ? best->action : -1;
+  }
+  free(path);
+  arena_free(&ar);
+  return rc;
+}
+
+int rzo_dm_search_batch(int G, int size, int k, const int32_t* moves, const int32_t* n_moves, int max_moves, int sims,
+                        double uct_c, int rule, int solve, int returns_mode, int eval_id, int32_t* visits, double* w,
+                        int32_t* outcome, int32_t* root_n, double* root_w, int32_t* root_o, int32_t* best_a) {
+  const int A = size * size;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int g = 0; g < G; ++g) {
+    const int rc = dm_search_game(size, k, moves + (size_t)g * max_moves, n_moves[g], sims, uct_c, rule, solve,
+                                  returns_mode, eval_id, visits + (size_t)g * A, w + (size_t)g * A,
+                                  outcome + (size_t)g * A, root_n + g, root_w + g, root_o + g, best_a + g);
+    if (rc) {
+#pragma omp atomic write
+      bad = rc;
+    }
+  }
+  return bad;
+}
+
 /* Connect Four (gravity, rows x cols, actions = columns): K = 1 is the reference's sequential search over that game,
  * K > 1 the leaf-parallel wave.  visits / w: [G][cols]. */
 int rzo_search_batch_c4(int G, int rows, int cols, int k, const int32_t* moves, const int32_t* n_moves, int max_moves,

@@ -192,3 +192,42 @@ def test_config2_all_4096_connect_four_trees_equal_the_c_oracle(rule, leaves):
     assert np.array_equal(visits[idx], cv)
     assert np.array_equal(w[idx].view(np.int64), cw.view(np.int64))
     assert np.array_equal(root_n[idx], crn) and np.array_equal(root_w[idx].view(np.int64), crw.view(np.int64))
+
+
+@pytest.mark.parametrize('method,solve,returns_mode,sims', [('puct', True, 1, 300), ('uct', True, 0, 200)])
+def test_all_8192_deepmind_mcts_trees_equal_the_c_oracle(method, solve, returns_mode, sims):
+    """The DeepMindMCTS flavour (rlzero/mcts/deepmind_mcts.py) at full width: 8192 Gomoku 15x15 positions, every tree
+    checked against the C restatement of the reference class (oracle/c/rz_oracle.c dm_search_game, pinned on the CPU to
+    the live-reference fixtures and to oracle.dm_oracle): root children's visit counts, value-sum bits and outcomes,
+    the root's N / W / outcome, best_child."""
+    from oracle import build_oracle
+    from oracle.evaluators import EVAL_HASH
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import ClosedFormEvaluator, SearchForest
+    lists = []
+    for g in range(G):
+        rs = np.random.RandomState(1000 + g)
+        lists.append([int(m) for m in rs.permutation(H * H)[:(1000 + g) % 31]])
+    f = SearchForest(G, H, K, n_playout=sims, c_puct=2.0, rule=L.RULE_PUCT if method == 'puct' else L.RULE_UCT,
+                     flavour=L.FLAVOUR_DEEPMIND, solve=solve, returns_mode=returns_mode, max_carry=0)
+    f.set_positions(lists)
+    live = f.boards()[1][:, L.META_STATUS] == L.ACTIVE
+    f.search(ClosedFormEvaluator(EVAL_HASH))
+    torch.cuda.synchronize()
+    f.raise_faults()
+    visits, w, has, root_n, root_w = f.root_stats()
+    A = H * H
+    edge_o = f.edge_O.view(G, f.max_nodes, f.AS)[:, 0, :A].cpu().numpy()
+    root_o = f.root_O.cpu().numpy()
+    best, _ = f.best_child()
+    idx = np.nonzero(live)[0]
+    r = build_oracle.dm_search_batch(H, K, [lists[i] for i in idx], sims, 2.0, method, solve, returns_mode, EVAL_HASH)
+    assert len(idx) > G - 64
+    child = r['visits'] >= 0
+    assert np.array_equal(has[idx], child)
+    assert np.array_equal(visits[idx], np.where(child, r['visits'], 0))
+    wc = np.where(child & (r['visits'] > 0), r['w'], 0.0)
+    assert np.array_equal(w[idx].view(np.int64), wc.view(np.int64))
+    assert np.array_equal(np.where(child, edge_o[idx], 0), r['outcome'])
+    assert np.array_equal(root_n[idx], r['root_n']) and np.array_equal(root_w[idx].view(np.int64), r['root_w'].view(np.int64))
+    assert np.array_equal(root_o[idx], r['root_outcome']) and np.array_equal(best[idx], r['best'])

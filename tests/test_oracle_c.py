@@ -109,3 +109,59 @@ def test_c_oracle_connect_four_matches_python_restatement(n_playout, rule, K):
         assert visits[g].tolist() == s.root_visits(7).tolist(), g
         assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(7)], g
         assert int(rn[g]) == s.root.n and float(rw[g]) == float(s.root.w)
+
+
+def _enc(o):
+    return 0 if o is None else (0x100 | (int(o[0]) + 1) | ((int(o[1]) + 1) << 2))
+
+
+def test_c_oracle_deepmind_mcts_matches_live_reference_fixtures(golden_dir):
+    """The C restatement of DeepMindMCTS against the vectors the LIVE reference class produced (all fixtures without
+    root noise): root children's N / W / outcome, the root's N / W / outcome (solver, early stop), best_child."""
+    with open(os.path.join(golden_dir, 'dm_mcts.json')) as f:
+        cases = [c for c in json.load(f) if c['noise_seed'] is None]
+    assert len(cases) >= 18
+    for c in cases:
+        r = build_oracle.dm_search_batch(c['size'], c['k'], [c['moves']], c['sims'], 2.0, c['method'], c['solve'], 0,
+                                         c['eval_id'])
+        want = {int(ch[0]): ch for ch in c['children']}
+        for a in range(c['size'] ** 2):
+            if a in want:
+                _, n, w, o, _ = want[a]
+                assert int(r['visits'][0, a]) == n and float(r['w'][0, a]).hex() == float(w).hex(), (c['moves'], a)
+                assert int(r['outcome'][0, a]) == _enc(o)
+            else:
+                assert int(r['visits'][0, a]) == -1
+        assert int(r['root_n'][0]) == c['root_n'] and float(r['root_w'][0]).hex() == float(c['root_w']).hex()
+        assert int(r['root_outcome'][0]) == _enc(c['root_outcome']) and int(r['best'][0]) == c['best']
+
+
+@pytest.mark.parametrize('size,k,sims,method,solve,mode', [(3, 3, 200, 'puct', True, 1), (4, 3, 300, 'uct', True, 0),
+                                                           (5, 4, 300, 'puct', True, 1), (6, 4, 250, 'uct', False, 1)])
+def test_c_oracle_deepmind_mcts_matches_python_restatement(size, k, sims, method, solve, mode):
+    from oracle import dm_oracle
+    rs = np.random.RandomState(size * 13 + sims)
+    lists, boards = [], []
+    while len(lists) < 10:
+        b = pyoracle.DMBoard(size, k, zero_sum=bool(mode))
+        b.reset()
+        mv = [int(x) for x in rs.permutation(size * size)[:rs.randint(0, size * size - 2)]]
+        ok = True
+        for a in mv:
+            b.step(a)
+            if b.game_end_winner()[0]:
+                ok = False
+                break
+        if ok:
+            lists.append(mv)
+            boards.append(b)
+    r = build_oracle.dm_search_batch(size, k, lists, sims, 2.0, method, solve, mode, 2)
+    for g, b in enumerate(boards):
+        s = dm_oracle.DMSearch(dm_oracle.ClosedFormEvaluator(2), sims, 2, method, solve=solve)
+        root = s.search(b)
+        for ch in root.children:
+            assert int(r['visits'][g, ch.action]) == ch.n and float(r['w'][g, ch.action]).hex() == float(ch.w).hex()
+            assert int(r['outcome'][g, ch.action]) == _enc(ch.outcome)
+        assert int(r['root_n'][g]) == root.n and float(r['root_w'][g]).hex() == float(root.w).hex()
+        assert int(r['root_outcome'][g]) == _enc(root.outcome)
+        assert int(r['best'][g]) == root.best_child().action
