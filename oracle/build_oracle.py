@@ -49,6 +49,9 @@ def load():
         lib.rzo_search_batch_c4.restype = C.c_int
         lib.rzo_search_batch_c4.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
                                             C.c_int, C.c_int, C.c_int, C.c_double, i32p, f64p, i32p, f64p]
+        lib.rzo_search_batch_reuse.restype = C.c_int
+        lib.rzo_search_batch_reuse.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
+                                               C.c_int, C.c_int, i32p, i32p, f64p, i32p, f64p]
         lib.rzo_dm_search_batch.restype = C.c_int
         lib.rzo_dm_search_batch.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double, C.c_int,
                                             C.c_int, C.c_int, C.c_int, i32p, f64p, i32p, i32p, f64p, i32p, i32p]
@@ -153,6 +156,34 @@ def search_batch_c4(move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2, rows=6,
     if rc:
         raise RuntimeError('rzo_search_batch_c4 failed (%d)' % rc)
     return visits, w, rn, rw
+
+
+def search_batch_reuse(size, k, move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2):
+    """Search, play the most visited move (lowest action on ties), search again with the subtree kept
+    (update_with_move).  Returns (move [G], visits [G,A], W [G,A], root_N [G], root_W [G]) of the SECOND search;
+    games that the move ends report zeros."""
+    import numpy as np
+    lib = load()
+    G, A = len(move_lists), size * size
+    mx = max(1, max((len(m) for m in move_lists), default=0))
+    mv = np.zeros((G, mx), dtype=np.int32)
+    nm = np.zeros(G, dtype=np.int32)
+    for g, m in enumerate(move_lists):
+        mv[g, :len(m)] = m
+        nm[g] = len(m)
+    move = np.zeros(G, dtype=np.int32)
+    visits = np.zeros((G, A), dtype=np.int32)
+    w = np.zeros((G, A), dtype=np.float64)
+    rn = np.zeros(G, dtype=np.int32)
+    rw = np.zeros(G, dtype=np.float64)
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    rc = lib.rzo_search_batch_reuse(G, size, k, mv.ctypes.data_as(i32p), nm.ctypes.data_as(i32p), mx, n_playout,
+                                    float(cpuct), int(rule), int(eval_id), move.ctypes.data_as(i32p),
+                                    visits.ctypes.data_as(i32p), w.ctypes.data_as(f64p), rn.ctypes.data_as(i32p),
+                                    rw.ctypes.data_as(f64p))
+    if rc:
+        raise RuntimeError('rzo_search_batch_reuse failed (%d)' % rc)
+    return move, visits, w, rn, rw
 
 
 def dm_search_batch(size, k, move_lists, sims, uct_c=2.0, method='puct', solve=True, returns_mode=0, eval_id=2):

@@ -222,6 +222,54 @@ int rzo_search_game(int size, int k, const int32_t* moves, int n_moves, int n_pl
   return rc;
 }
 
+/* Two searches per game with the subtree kept in between (update_with_move, alphazero_mcts.py:96-103): after the
+ * first search the most visited root child is played (lowest action on ties, numpy argmax), then n_playout more
+ * playouts from the re-rooted tree.  Outputs the SECOND stage and the move played; games whose position after the move
+ * is over report move and zeros. */
+int rzo_search_batch_reuse(int G, int size, int k, const int32_t* moves, const int32_t* n_moves, int max_moves,
+                           int n_playout, double cpuct, int rule, int eval_id, int32_t* move_out, int32_t* visits,
+                           double* w, int32_t* root_n, double* root_w) {
+  const int A = size * size;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int g = 0; g < G; ++g) {
+    int32_t* v1 = (int32_t*)malloc(sizeof(int32_t) * (size_t)A * 2);
+    double* w1 = (double*)malloc(sizeof(double) * (size_t)A * 2);
+    int32_t rn[2]; double rw[2]; int32_t follow[1];
+    int rc = (v1 && w1) ? rzo_search_game(size, k, moves + (size_t)g * max_moves, n_moves[g], n_playout, cpuct, rule,
+                                          eval_id, 1, NULL, v1, w1, rn, rw) : -1;
+    if (rc == 0) {
+      int best = 0;
+      for (int a = 1; a < A; ++a) if (v1[a] > v1[best]) best = a;
+      move_out[g] = best;
+      follow[0] = best;
+      /* is the game over after that move?  replay on a scratch board */
+      board_t b; board_reset(&b, size, size, k, 0);
+      for (int i = 0; i < n_moves[g]; ++i) board_step(&b, moves[(size_t)g * max_moves + i]);
+      board_step(&b, best);
+      int winner;
+      if (board_end(&b, &winner)) {
+        for (int a = 0; a < A; ++a) { visits[(size_t)g * A + a] = 0; w[(size_t)g * A + a] = 0.0; }
+        root_n[g] = 0; root_w[g] = 0.0;
+      } else {
+        rc = rzo_search_game(size, k, moves + (size_t)g * max_moves, n_moves[g], n_playout, cpuct, rule, eval_id, 2,
+                             follow, v1, w1, rn, rw);
+        if (rc == 0) {
+          memcpy(visits + (size_t)g * A, v1 + A, sizeof(int32_t) * (size_t)A);
+          memcpy(w + (size_t)g * A, w1 + A, sizeof(double) * (size_t)A);
+          root_n[g] = rn[1]; root_w[g] = rw[1];
+        }
+      }
+    }
+    free(v1); free(w1);
+    if (rc) {
+#pragma omp atomic write
+      bad = rc;
+    }
+  }
+  return bad;
+}
+
 /* ---- the product's opt-in leaf-parallel wave (include/rlzero_b200.h, rz_tree_desc.leaves_per_tree) -------------
  * NOT a reference algorithm (the reference has no virtual loss: PARITY UNPINNED for this mode); restated here, as in
  * oracle/pyoracle.py Search.wave, so that the kernels can be checked at full size.  `budget` descents, each followed

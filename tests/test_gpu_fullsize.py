@@ -231,3 +231,45 @@ def test_all_8192_deepmind_mcts_trees_equal_the_c_oracle(method, solve, returns_
     assert np.array_equal(np.where(child, edge_o[idx], 0), r['outcome'])
     assert np.array_equal(root_n[idx], r['root_n']) and np.array_equal(root_w[idx].view(np.int64), r['root_w'].view(np.int64))
     assert np.array_equal(root_o[idx], r['root_outcome']) and np.array_equal(best[idx], r['best'])
+
+
+@pytest.mark.parametrize('rule', [0, 1])
+def test_all_8192_trees_after_a_committed_move_equal_the_c_oracle(rule):
+    """Tree reuse at full width (update_with_move, alphazero_mcts.py:96-103 = rz_tree_advance with subtree compaction):
+    search 400 playouts, play every game's most visited move keeping its subtree, search 400 more -- every re-rooted
+    tree equals the C oracle's (which the Python restatement pins on the CPU, tests/test_oracle_c.py)."""
+    from oracle import build_oracle
+    from oracle.evaluators import EVAL_HASH
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import ClosedFormEvaluator, SearchForest
+    n_playout = 400
+    lists = []
+    for g in range(G):
+        rs = np.random.RandomState(1000 + g)
+        lists.append([int(m) for m in rs.permutation(H * H)[:(1000 + g) % 31]])
+    f = SearchForest(G, H, K, n_playout=n_playout, c_puct=5.0, rule=rule, max_carry=n_playout)
+    f.set_positions(lists)
+    live0 = f.boards()[1][:, L.META_STATUS] == L.ACTIVE
+    ev = ClosedFormEvaluator(EVAL_HASH)
+    f.search(ev)
+    f.raise_faults()
+    visits1 = f.root_stats()[0]
+    moves = np.argmax(visits1, axis=1).astype(np.int32)
+    moves[~live0] = -1
+    f.advance(moves, keep_subtree=True)
+    f.raise_faults()
+    live = live0 & (f.boards()[1][:, L.META_STATUS] == L.ACTIVE)
+    f.search(ev)
+    torch.cuda.synchronize()
+    f.raise_faults()
+    visits, w, has, root_n, root_w = f.root_stats()
+    idx = np.nonzero(live0)[0]
+    cm, cv, cw, crn, crw = build_oracle.search_batch_reuse(H, K, [lists[i] for i in idx], n_playout, 5.0, rule, EVAL_HASH)
+    assert np.array_equal(moves[idx], cm)
+    sel = live[idx]
+    assert sel.sum() > G - 128
+    assert np.array_equal(visits[idx][sel], cv[sel])
+    assert np.array_equal(w[idx][sel].view(np.int64), cw[sel].view(np.int64))
+    assert np.array_equal(root_n[idx][sel], crn[sel])
+    assert np.array_equal(root_w[idx][sel].view(np.int64), crw[sel].view(np.int64))
+    assert (crn[~sel] == 0).all()            # the games the move ended: nothing searched on either side

@@ -165,3 +165,37 @@ def test_c_oracle_deepmind_mcts_matches_python_restatement(size, k, sims, method
         assert int(r['root_n'][g]) == root.n and float(r['root_w'][g]).hex() == float(root.w).hex()
         assert int(r['root_outcome'][g]) == _enc(root.outcome)
         assert int(r['best'][g]) == root.best_child().action
+
+
+@pytest.mark.parametrize('size,k,n_playout,rule', [(6, 4, 150, 0), (8, 5, 200, 1)])
+def test_c_oracle_tree_reuse_batch_matches_python_restatement(size, k, n_playout, rule):
+    rs = np.random.RandomState(size + n_playout)
+    lists, boards = [], []
+    while len(lists) < 8:
+        b = pyoracle.Board(size, k)
+        b.reset()
+        mv = [int(x) for x in rs.permutation(size * size)[:rs.randint(0, size * size // 2)]]
+        ok = True
+        for a in mv:
+            b.step(a)
+            if b.game_end_winner()[0]:
+                ok = False
+                break
+        if ok:
+            lists.append(mv)
+            boards.append(b)
+    move, visits, w, rn, rw = build_oracle.search_batch_reuse(size, k, lists, n_playout, 5.0, rule, 2)
+    for g, b in enumerate(boards):
+        s = pyoracle.Search(make_policy_value_fn(2), n_playout, 5.0, rule=rule)
+        s.simulate(b, 1.0)
+        m = int(np.argmax(s.root_visits(size * size)))
+        assert int(move[g]) == m
+        b.step(m)
+        if b.game_end_winner()[0]:
+            assert int(rn[g]) == 0
+            continue
+        s.update_with_move(m)
+        s.simulate(b, 1.0)
+        assert visits[g].tolist() == s.root_visits(size * size).tolist(), g
+        assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(size * size)], g
+        assert int(rn[g]) == s.root.n and float(rw[g]) == float(s.root.w)
