@@ -273,3 +273,44 @@ def test_all_8192_trees_after_a_committed_move_equal_the_c_oracle(rule):
     assert np.array_equal(root_n[idx][sel], crn[sel])
     assert np.array_equal(root_w[idx][sel].view(np.int64), crw[sel].view(np.int64))
     assert (crn[~sel] == 0).all()            # the games the move ended: nothing searched on either side
+
+
+def test_root_policy_and_move_sampling_at_full_width():
+    """AlphaZeroPlayer.get_action's pi = softmax(log(N + 1e-10) / T) and np.random.choice(acts, p=pi)
+    (alphazero_mcts.py:86-94,144-148) for all 8192 trees after an 800-playout search: pi against numpy in fp64, the
+    sampled move against numpy's rule (first index whose normalised cumulative probability exceeds u) for the same
+    uniforms, T -> 0 picks a most-visited child."""
+    from oracle.evaluators import EVAL_HASH
+    from rlzero_b200.engine import ClosedFormEvaluator, SearchForest
+    lists = []
+    for g in range(G):
+        rs = np.random.RandomState(1000 + g)
+        lists.append([int(m) for m in rs.permutation(H * H)[:(1000 + g) % 31]])
+    f = SearchForest(G, H, K, n_playout=800)
+    f.set_positions(lists)
+    f.search(ClosedFormEvaluator(EVAL_HASH))
+    f.raise_faults()
+    A = H * H
+    u = np.random.RandomState(5).random_sample(G)
+    f.root_policy(temperature=1.0, u01=u)
+    pi = f.pi.cpu().numpy()[:, :A].astype(np.float64)
+    mv = f.move.cpu().numpy()
+    visits = f.visits.cpu().numpy()[:, :A].astype(np.float64)
+    has = f.root_stats()[2]
+    live = has.any(1)
+    assert live.sum() > G - 64
+    logits = np.where(has, np.log(visits + 1e-10), -np.inf)
+    with np.errstate(invalid='ignore'):                    # rows of finished games are all -inf
+        p = np.exp(logits - logits.max(1, keepdims=True))
+    p = np.where(live[:, None], p / np.maximum(np.nan_to_num(p).sum(1, keepdims=True), 1e-300), 0.0)
+    assert np.abs(pi[live] - p[live]).max() < 1e-6
+    assert np.abs(pi[live].sum(1) - 1.0).max() < 1e-5
+    cdf = np.cumsum(p, axis=1)
+    cdf /= np.maximum(cdf[:, -1:], 1e-300)
+    want = (cdf <= u[:, None]).sum(1)                       # searchsorted(u, side='right') per row
+    near = np.abs(cdf[np.arange(G), np.minimum(want, mv).clip(0, A - 1)] - u) < 1e-6   # fp32 pi on the device: a boundary case
+    assert ((mv == want) | near)[live].all()
+    assert (mv[live] >= 0).all() and has[np.arange(G), mv.clip(0)][live].all()
+    f.root_policy(temperature=1e-3, u01=u)
+    mv0 = f.move.cpu().numpy()
+    assert (visits[np.arange(G), mv0.clip(0)] == visits.max(1))[live].all()
