@@ -49,6 +49,8 @@ def load():
         lib.rzo_search_batch_c4.restype = C.c_int
         lib.rzo_search_batch_c4.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
                                             C.c_int, C.c_int, C.c_int, C.c_double, i32p, f64p, i32p, f64p]
+        lib.rzo_replay_games.restype = C.c_int
+        lib.rzo_replay_games.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, i32p, i32p, i32p]
         lib.rzo_search_batch_reuse.restype = C.c_int
         lib.rzo_search_batch_reuse.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
                                                C.c_int, C.c_int, i32p, i32p, f64p, i32p, f64p]
@@ -156,6 +158,23 @@ def search_batch_c4(move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2, rows=6,
     if rc:
         raise RuntimeError('rzo_search_batch_c4 failed (%d)' % rc)
     return visits, w, rn, rw
+
+
+def replay_games(size, k, moves):
+    """GomokuEnv.step until game_end_winner for every row of ``moves`` [G, T] (int32).  Returns (end_ply, winner,
+    ended) int32 [G]."""
+    import numpy as np
+    lib = load()
+    mv = np.ascontiguousarray(moves, dtype=np.int32)
+    G, T = mv.shape
+    nm = np.full(G, T, dtype=np.int32)
+    end_ply, winner, ended = (np.zeros(G, dtype=np.int32) for _ in range(3))
+    i32p = C.POINTER(C.c_int32)
+    rc = lib.rzo_replay_games(G, size, k, mv.ctypes.data_as(i32p), nm.ctypes.data_as(i32p), T,
+                              end_ply.ctypes.data_as(i32p), winner.ctypes.data_as(i32p), ended.ctypes.data_as(i32p))
+    if rc:
+        raise RuntimeError('rzo_replay_games failed (%d)' % rc)
+    return end_ply, winner, ended
 
 
 def search_batch_reuse(size, k, move_lists, n_playout, cpuct=5.0, rule=0, eval_id=2):

@@ -222,6 +222,33 @@ int rzo_search_game(int size, int k, const int32_t* moves, int n_moves, int n_pl
   return rc;
 }
 
+/* GomokuEnv.step / game_end_winner (gomoku_env.py:49-70,196-203) over whole games: play moves[g][0..] until the game
+ * is over; end_ply[g] = number of moves played (n_moves[g] if it never ended), winner[g] = the winner, -1 for a tie
+ * or an unfinished game, ended[g] = 1 if it ended. */
+int rzo_replay_games(int G, int size, int k, const int32_t* moves, const int32_t* n_moves, int max_moves,
+                     int32_t* end_ply, int32_t* winner, int32_t* ended) {
+  if (size < 1 || size * size > MAXC) return -3;
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int g = 0; g < G; ++g) {
+    board_t b;
+    board_reset(&b, size, size, k, 0);
+    int t = 0, w = -1, e = 0;
+    for (; t < n_moves[g]; ++t) {
+      const int a = moves[(size_t)g * max_moves + t];
+      if (a < 0 || a >= size * size || b.cell[a] >= 0) {
+#pragma omp atomic write
+        bad = -4;
+        break;
+      }
+      board_step(&b, a);
+      if (board_end(&b, &w)) { e = 1; t += 1; break; }
+    }
+    end_ply[g] = t; winner[g] = e ? w : -1; ended[g] = e;
+  }
+  return bad;
+}
+
 /* Two searches per game with the subtree kept in between (update_with_move, alphazero_mcts.py:96-103): after the
  * first search the most visited root child is played (lowest action on ties, numpy argmax), then n_playout more
  * playouts from the re-rooted tree.  Outputs the SECOND stage and the move played; games whose position after the move

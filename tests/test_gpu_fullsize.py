@@ -314,3 +314,45 @@ def test_root_policy_and_move_sampling_at_full_width():
     f.root_policy(temperature=1e-3, u01=u)
     mv0 = f.move.cpu().numpy()
     assert (visits[np.arange(G), mv0.clip(0)] == visits.max(1))[live].all()
+
+
+@pytest.mark.parametrize('size,k', [(15, 5), (9, 4)])
+def test_8192_random_games_to_the_end_equal_the_c_oracle(size, k):
+    """The game kernels at full width (GomokuEnv.step / has_a_winner / game_end_winner, gomoku_env.py:49-70,116-170,
+    196-203): 8192 random games played to the end, every game ends at the same ply with the same winner as in the C
+    restatement (itself pinned to pyoracle.Board and through it to the live reference's env games); the legal mask of
+    every final position equals the empty squares."""
+    from oracle import build_oracle
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import SearchForest
+    Gn, A = 8192, size * size
+    rs = np.random.RandomState(size * 7)
+    moves = np.stack([rs.permutation(A) for _ in range(Gn)]).astype(np.int32)
+    f = SearchForest(Gn, size, k, n_playout=2)
+    end_ply = np.zeros(Gn, dtype=np.int32)
+    winner = np.full(Gn, -1, dtype=np.int32)
+    active = np.ones(Gn, dtype=bool)
+    for t in range(A):
+        f.play_moves(np.where(active, moves[:, t], -1))
+        meta = f.root_meta.cpu().numpy()
+        over = active & (meta[:, L.META_STATUS] != L.ACTIVE)
+        end_ply[over] = t + 1
+        winner[over] = meta[over, L.META_WINNER]
+        active &= ~over
+        if not active.any():
+            break
+    f.raise_faults()
+    assert not active.any()
+    c_end, c_win, c_ended = build_oracle.replay_games(size, k, moves)
+    assert c_ended.all() and np.array_equal(end_ply, c_end) and np.array_equal(winner, c_win)
+    assert (winner == -1).sum() >= 0 and set(np.unique(winner)).issubset({-1, 0, 1})
+    # final positions: stones on the board = plies played; legal mask = empty squares
+    import ctypes as C
+    mask = torch.zeros(Gn, A, dtype=torch.uint8, device='cuda')
+    L.check(f.lib.rz_gomoku_legal_mask(C.byref(f.gdesc), L.ptr(f.root_rows), L.ptr(mask), Gn, L.stream_ptr()), 'legal')
+    legal = mask.cpu().numpy().astype(bool)
+    played = np.zeros((Gn, A), dtype=bool)
+    for g in range(0, Gn, 257):
+        played[g, moves[g, :end_ply[g]]] = True
+        assert np.array_equal(legal[g], ~played[g]), g
+    assert (legal.sum(1) == A - end_ply).all()

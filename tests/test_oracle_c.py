@@ -199,3 +199,25 @@ def test_c_oracle_tree_reuse_batch_matches_python_restatement(size, k, n_playout
         assert visits[g].tolist() == s.root_visits(size * size).tolist(), g
         assert [float(x).hex() for x in w[g]] == [float(x).hex() for x in s.root_values(size * size)], g
         assert int(rn[g]) == s.root.n and float(rw[g]) == float(s.root.w)
+
+
+@pytest.mark.parametrize('size,k', [(3, 3), (6, 4), (15, 5), (19, 5)])
+def test_c_oracle_game_replay_matches_python_board(size, k):
+    """GomokuEnv.step / game_end_winner in the C oracle against pyoracle.Board (pinned to the live reference's env games
+    by tests/test_oracle_golden.py) on random full games: same ending ply, same winner, ties included."""
+    rs = np.random.RandomState(size)
+    G = 40
+    moves = np.stack([rs.permutation(size * size) for _ in range(G)]).astype(np.int32)
+    end_ply, winner, ended = build_oracle.replay_games(size, k, moves)
+    for g in range(G):
+        b = pyoracle.Board(size, k)
+        b.reset()
+        t, w, e = 0, -1, False
+        for a in moves[g]:
+            b.step(int(a))
+            t += 1
+            e, w = b.game_end_winner()
+            if e:
+                break
+        assert (int(end_ply[g]), int(winner[g]), bool(ended[g])) == (t, int(w), bool(e)), g
+    assert ended.all()
