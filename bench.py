@@ -91,9 +91,10 @@ def _cpu_worker(args):
     import torch
     torch.set_num_threads(1)
     from oracle import pyoracle
-    from rlzero_b200.games.gomoku.policy_value_net import ResNetPolicyValueNet
+    from rlzero_b200.games.gomoku.policy_value_net import PolicyValueNet, ResNetPolicyValueNet
     torch.manual_seed(0)
-    net = ResNetPolicyValueNet(BOARD, n_blocks=blocks).eval()
+    # blocks < 0: the reference's own stock PolicyValueNet (what tools/train_alphazero.py runs) instead of the ResNet
+    net = (PolicyValueNet(BOARD) if blocks < 0 else ResNetPolicyValueNet(BOARD, n_blocks=blocks)).eval()
     if state is not None:
         net.load_state_dict(state)
 
@@ -113,14 +114,19 @@ def _cpu_worker(args):
         if board.game_end_winner()[0]:
             board.reset()
             break
-    s = pyoracle.Search(pvf, n_playout, C_PUCT, add_noise=True)
     import copy
-    s.playout(copy.deepcopy(board))  # warm-up (expands the root)
+    pyoracle.Search(pvf, n_playout, C_PUCT, add_noise=True).playout(copy.deepcopy(board))  # warm-up (lazy imports)
     t0 = time.time()
     n = 0
-    while time.time() - t0 < seconds and n < n_playout - 1:
-        s.playout(copy.deepcopy(board))
-        n += 1
+    while time.time() - t0 < seconds:
+        # one move's search of at most n_playout playouts (alphazero_mcts.py:83-85), then a fresh tree, until the
+        # time sample is used up
+        s = pyoracle.Search(pvf, n_playout, C_PUCT, add_noise=True)
+        k = 0
+        while k < n_playout and time.time() - t0 < seconds:
+            s.playout(copy.deepcopy(board))
+            k += 1
+            n += 1
     return n, time.time() - t0
 
 
@@ -135,11 +141,12 @@ def cpu_baseline(blocks, n_playout, seconds):
         res = pool.map(_cpu_worker, [(i, blocks, n_playout, seconds, None, None) for i in range(cores)])
     sims = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
+    netname = 'the stock PolicyValueNet' if blocks < 0 else 'ResNet-%d' % blocks
     return {'value': sims / wall, 'unit': 'simulations/s', 'cores': cores, 'kind': 'port',
             'sample': '%d host processes x up to %.0f s of AlphaZeroMCTS playouts (oracle port of '
-                      'rlzero/mcts + GomokuEnv, ResNet-%d fp32 on the CPU, batch 1, noise on), '
+                      'rlzero/mcts + GomokuEnv, %s fp32 on the CPU, batch 1, noise on), '
                       '15x15 from the bench start positions; %d playouts in %.1f s' % (
-                          cores, seconds, blocks, sims, wall)}
+                          cores, seconds, netname, sims, wall)}
 
 
 def run_reference(args):
@@ -371,6 +378,10 @@ def run_b200(args):
                 'e2e': e2e, 'roofline': roof, 'tree_roofline': tree_roof}
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(args.blocks, P, args.cpu_seconds)
+            # the same CPU search with the reference's own stock network as evaluator, a shorter sample
+            stock = cpu_baseline(-1, P, min(8.0, args.cpu_seconds))
+            line['cpu_baseline']['stock_net'] = {'value': stock['value'], 'unit': stock['unit'], 'cores': stock['cores'],
+                                                 'sample': stock['sample']}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
