@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RZ_ABI_VERSION 7
+#define RZ_ABI_VERSION 8
 #define RZ_MAX_BOARD 19          /* rows live one per lane; A <= 362 (19x19 Go incl. the pass) */
 #define RZ_META_STRIDE 12
 #define RZ_GO_HIST 14            /* history planes a Go position carries besides the current board */
@@ -186,6 +186,24 @@ typedef struct rz_tree_desc {
                                     wave of a search may be partial); a tree whose root is unexpanded takes one */
   double* vl_saved_W;            /* [G*K][max_depth] scratch: the value sums the virtual losses overwrote */
   double virtual_loss;           /* subtracted per in-flight playout (1.0 = a lost game for the mover) */
+  /* optional pools / inputs (ABI 8; every one may be NULL) */
+  double* edge_P64;              /* [G][max_nodes][AS] the priors in float64.  TreeNode.prior is a Python float: with
+                                    Dirichlet noise the reference forms 0.75 * p + 0.25 * noise in float64
+                                    (node.py:66-69), which a float32 pool cannot hold.  When non-NULL the PUCT rule
+                                    reads this pool instead of edge_P, expand writes both */
+  const unsigned long long* seed_dev; /* [1] device scalar added to the `seed` argument of rz_tree_expand_backup* and
+                                    rz_eval_rollout*: a captured CUDA graph holds `seed` by value, the host bumps this
+                                    word between searches instead of re-capturing */
+  int32_t* edge_R;               /* [G][max_nodes][AS] DeepMindMCTS flavour: position of each child in its parent's
+                                    `children` list, which the reference shuffles (deepmind_mcts.py:508) -- `max()`
+                                    returns the FIRST maximum, so the list order is the tie-break of the child
+                                    selection (:513-517) and of best_child (:173-175).  NULL = unshuffled (ties go to
+                                    the lowest action).  Expansion fills it with counter-based random keys
+                                    (shuffle_mode 1) or with the slot index (shuffle_mode 0: the host overwrites a
+                                    node's ranks with the permutation numpy's RandomState.shuffle drew, the seeded
+                                    parity path of rlzero_b200.mcts.DeepMindMCTS) */
+  int32_t shuffle_mode;
+  int32_t reserved0;
 } rz_tree_desc;
 
 /* ---- trajectory store (GameControl.start_self_play, game.py:96-134) ------- */
@@ -281,6 +299,17 @@ int rz_tree_select(const rz_tree_desc* t, void* stream);
 int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, int prior_is_log,
                           const float* value, const double* value64, float noise_eps, float noise_alpha,
                           unsigned long long seed, void* stream);
+/* the same step with host-supplied randomness (seeded parity with the reference, whose noise comes from the global
+   numpy stream, node.py:63-69; SURVEY 8 b2 `noise*|NULL`).  Either of
+     noise64 [G*K][AS] float64: a Dirichlet sample per leaf, entry s = the noise of the child reached by action s
+                                 (the reference indexes it by position in the legal-move list): the priors become
+                                 (double)((1 - eps)_f32 * p_f32) + eps * noise64[s], numpy's arithmetic for a float32 p
+                                 (eps = noise_eps; no device draw);
+     prior64 [G*K][AS] float64: the finished float64 priors of the new node, stored verbatim (prior / noise_* ignored);
+   both NULL = rz_tree_expand_backup.  With t->edge_P64 the float64 values are kept, else rounded to float32. */
+int rz_tree_expand_backup_ex(const rz_tree_desc* t, const float* prior, int prior_is_log,
+                             const float* value, const double* value64, float noise_eps, float noise_alpha,
+                             unsigned long long seed, const double* noise64, const double* prior64, void* stream);
 /* DeepMindMCTS flavour of the same step (deepmind_mcts.py:596-644): `value` is the evaluation for the
    player to move at the leaf (returns = [v,-v] in player order); ret64 != NULL overrides it with the
    evaluator's full returns vector, float64 [G][2] (Evaluator.evaluate, :22-24).  Terminal leaves take

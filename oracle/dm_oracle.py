@@ -64,7 +64,7 @@ class DMSearch(object):
 
     def __init__(self, evaluator, max_simulations=2000, uct_c=2, child_selection_method='puct',
                  add_exploration_noise=False, dirichlet_noise_epsilon=0.25, solve=True, max_utility=1,
-                 noise_fn=None):
+                 noise_fn=None, shuffle_fn=None):
         self.evaluator = evaluator
         self.max_simulations = max_simulations
         self.uct_c = uct_c
@@ -75,6 +75,7 @@ class DMSearch(object):
         self.solve = solve
         self.max_utility = max_utility
         self.noise_fn = noise_fn or (lambda k: np.random.dirichlet([self.alpha] * k))
+        self.shuffle_fn = shuffle_fn          # in-place list shuffle (deepmind_mcts.py:508); None = keep the order
 
     def _score(self, ch, parent_n):
         return ch.puct(parent_n, self.uct_c) if self.rule == 'puct' else ch.uct(parent_n, self.uct_c)
@@ -89,6 +90,8 @@ class DMSearch(object):
                 if node is root and self.add_noise:
                     noise = self.noise_fn(len(pri))
                     pri = [(a, self.eps * z + (1 - self.eps) * p) for (a, p), z in zip(pri, noise)]
+                if self.shuffle_fn is not None:
+                    self.shuffle_fn(pri)                  # "Reduce bias from move generation order" (:508)
                 mover = work.current_player()
                 node.children = [Node(a, mover, p) for a, p in pri]
             best, best_s = None, None

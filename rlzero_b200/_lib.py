@@ -11,7 +11,7 @@ import torch  # noqa: F401  -- loads libcudart.so.12 into the process before our
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'librlzero_b200.so')
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 META_STRIDE = 12
 (META_PLAYER, META_LAST_MOVE, META_STONES, META_STATUS, META_WINNER, META_PLY, META_FAULT,
  META_EPISODE, META_KO, META_PASSES) = range(10)
@@ -54,7 +54,9 @@ class TreeDesc(C.Structure):
                 ('flavour', C.c_int32), ('solve', C.c_int32), ('returns_mode', C.c_int32),
                 ('noise_root_only', C.c_int32), ('edge_O', _vp), ('root_O', _vp),
                 ('leaves_per_tree', C.c_int32), ('target_N', _vp), ('vl_saved_W', _vp),
-                ('virtual_loss', C.c_double)]
+                ('virtual_loss', C.c_double),
+                ('edge_P64', _vp), ('seed_dev', _vp), ('edge_R', _vp), ('shuffle_mode', C.c_int32),
+                ('reserved0', C.c_int32)]
 
 
 class TrajDesc(C.Structure):
@@ -105,6 +107,8 @@ SIGNATURES = {
     'rz_tree_select': (C.c_int, [_TD, _vp]),
     'rz_tree_expand_backup': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,
                                         C.c_ulonglong, _vp]),
+    'rz_tree_expand_backup_ex': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,
+                                           C.c_ulonglong, _vp, _vp, _vp]),
     'rz_tree_expand_backup_dm': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,
                                            C.c_ulonglong, _vp]),
     'rz_tree_best_child': (C.c_int, [_TD, _vp, _vp, _vp]),

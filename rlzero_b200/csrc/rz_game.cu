@@ -264,6 +264,10 @@ rz_eval_rollout_kernel(rz_tree_desc t, int mode, unsigned long long seed, int n_
   }
   const uint32_t rowmask = (q.W >= 32) ? 0xffffffffu : ((1u << q.W) - 1u);
   const uint32_t visit = (uint32_t)t.root_N[g];
+  // the stream also depends on the root position (stones on the board) and on the host's search counter
+  // (rz_tree_desc.seed_dev), so that playout #v of different moves / games does not repeat the same numbers
+  const uint32_t c3 = 0x7011u + ((uint32_t)t.root_meta[(size_t)g * RZ_META_STRIDE + RZ_META_STONES] << 16);
+  if (t.seed_dev) seed += *t.seed_dev;
   int winner = -1;
   for (int i = 0; i < n_limit; ++i) {
     const int status = rz_board_status(b, q, winner);
@@ -283,7 +287,7 @@ rz_eval_rollout_kernel(rz_tree_desc t, int mode, unsigned long long seed, int n_
     else if (mode == 2) r = n_legal - 1;
     else {
       uint32_t rnd[4];
-      rz_philox4((uint32_t)(t.global_offset + g), visit, (uint32_t)i, 0x7011u, seed, rnd);
+      rz_philox4((uint32_t)(t.global_offset + g), visit, (uint32_t)i, c3, seed, rnd);
       r = (int)(((unsigned long long)rnd[0] * (unsigned long long)n_legal) >> 32);
     }
     // the row holding the r-th empty square, then its column
@@ -330,6 +334,7 @@ rz_eval_rollout_dm_kernel(rz_tree_desc t, int n_rollouts, unsigned long long see
     }
   }
   const uint32_t visit = (uint32_t)t.root_N[g];
+  if (t.seed_dev) seed += *t.seed_dev;   // the host's search counter (rz_tree_desc.seed_dev)
   int sum0 = 0, sum1 = 0;
   for (int r = 0; r < n_rollouts; ++r) {
     typename GM::board b = b0;

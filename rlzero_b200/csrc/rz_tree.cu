@@ -43,6 +43,20 @@ __device__ __forceinline__ void rz_warp_argmax(double& s, int& slot, int& n) {
     if (take) { s = s2; slot = slot2; n = n2; }
   }
 }
+// the same over (score desc, rank asc, slot asc): `rank` is the child's position in the parent's shuffled
+// `children` list (deepmind_mcts.py:508), the order Python's max() breaks ties in
+__device__ __forceinline__ void rz_warp_argmax_ranked(double& s, int& rank, int& slot, int& n) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double s2 = __shfl_xor_sync(RZ_FULL, s, o);
+    const int r2 = __shfl_xor_sync(RZ_FULL, rank, o);
+    const int slot2 = __shfl_xor_sync(RZ_FULL, slot, o);
+    const int n2 = __shfl_xor_sync(RZ_FULL, n, o);
+    const bool take = (slot2 >= 0) && (slot < 0 || s2 > s ||
+                                       (s2 == s && (r2 < rank || (r2 == rank && slot2 < slot))));
+    if (take) { s = s2; rank = r2; slot = slot2; n = n2; }
+  }
+}
 
 // SearchNode.outcome codes (DeepMindMCTS flavour): 0 = None, else 0x100 | (o[0]+1) | (o[1]+1) << 2
 __device__ __forceinline__ int rz_outcome_enc(int o0, int o1) { return 0x100 | (o0 + 1) | ((o1 + 1) << 2); }
@@ -80,7 +94,15 @@ __device__ __forceinline__ void rz_select_one(const rz_tree_desc& t, const int g
     for (int i = 0; i < RZ_MAX_ITERS; ++i) nv[i] = (i < iters) ? eN[lane + 32 * i] : -1;
 
     double best_s = 0.0;
-    int best_slot = -1, best_n = 0;
+    int best_slot = -1, best_n = 0, best_r = 0;
+    // DeepMindMCTS with the child shuffle: ties go to the child that comes first in the shuffled list
+    const bool ranked = DM && t.edge_R != nullptr;
+    int rk[RZ_MAX_ITERS];
+    if (ranked) {
+      const int32_t* eR = t.edge_R + base;
+#pragma unroll
+      for (int i = 0; i < RZ_MAX_ITERS; ++i) rk[i] = (i < iters && nv[i] >= 0) ? eR[lane + 32 * i] : 0x7fffffff;
+    }
     // DeepMindMCTS: a child with a known outcome scores outcome[child.player] (deepmind_mcts.py:123-124,
     // 146-147); the children of a node at this depth were all moved by the same player
     int oc[RZ_MAX_ITERS];
@@ -98,8 +120,25 @@ __device__ __forceinline__ void rz_select_one(const rz_tree_desc& t, const int g
         if (i < iters && (nv[i] == 0 || (nv[i] > 0 && Np == 0))) first_unvisited = lane + 32 * i;
       // lowest slot over the warp
       int cand = first_unvisited < 0 ? 0x7fffffff : first_unvisited;
+      if (ranked) {
+        // every unvisited child scores +inf: the first of them in list order wins
+        long long key = 0x7fffffffffffffffll;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(RZ_FULL, cand, o));
+        for (int i = 0; i < RZ_MAX_ITERS; ++i)
+          if (i < iters && (nv[i] == 0 || (nv[i] > 0 && Np == 0))) {
+            const long long k2 = ((long long)rk[i] << 32) | (unsigned)(lane + 32 * i);
+            key = k2 < key ? k2 : key;
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const long long k2 = __shfl_xor_sync(RZ_FULL, key, o);
+          key = k2 < key ? k2 : key;
+        }
+        cand = key == 0x7fffffffffffffffll ? 0x7fffffff : (int)(key & 0xffffffffll);
+      } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(RZ_FULL, cand, o));
+      }
       if (cand != 0x7fffffff) {
         best_slot = cand;
         best_n = eN[cand];
@@ -121,29 +160,36 @@ __device__ __forceinline__ void rz_select_one(const rz_tree_desc& t, const int g
             const double u = __dsqrt_rn(__ddiv_rn(lnNp, n));
             double s = __dadd_rn(q, __dmul_rn(t.c_puct, u));
             if (DM && oc[i]) s = (double)rz_outcome_of(oc[i], mover);
-            if (best_slot < 0 || s > best_s) { best_s = s; best_slot = lane + 32 * i; best_n = nv[i]; }
+            if (best_slot < 0 || s > best_s || (ranked && s == best_s && rk[i] < best_r)) {
+              best_s = s; best_slot = lane + 32 * i; best_n = nv[i]; best_r = ranked ? rk[i] : 0;
+            }
           }
         }
-        rz_warp_argmax(best_s, best_slot, best_n);
+        if (ranked) rz_warp_argmax_ranked(best_s, best_r, best_slot, best_n);
+        else rz_warp_argmax(best_s, best_slot, best_n);
       }
     } else {
       // deepmind_mcts.py:149-151: (n and W/n) + ((c*P)*sqrt(Np))/(n+1)
       const double* eW = t.edge_W + base;
       const float* eP = t.edge_P + base;
+      const double* eP64 = t.edge_P64 ? t.edge_P64 + base : nullptr;   // float64 priors (noise mixed in float64)
       const double sq = __dsqrt_rn((double)Np);
 #pragma unroll
       for (int i = 0; i < RZ_MAX_ITERS; ++i) {
         if (i < iters && nv[i] >= 0) {
           const int slot = lane + 32 * i;
           const double q = nv[i] > 0 ? __ddiv_rn(eW[slot], (double)nv[i]) : 0.0;
-          const double u = __ddiv_rn(__dmul_rn(__dmul_rn(t.c_puct, (double)eP[slot]), sq),
-                                     (double)(nv[i] + 1));
+          const double pr = eP64 ? eP64[slot] : (double)eP[slot];
+          const double u = __ddiv_rn(__dmul_rn(__dmul_rn(t.c_puct, pr), sq), (double)(nv[i] + 1));
           double s = __dadd_rn(q, u);
           if (DM && oc[i]) s = (double)rz_outcome_of(oc[i], mover);
-          if (best_slot < 0 || s > best_s) { best_s = s; best_slot = slot; best_n = nv[i]; }
+          if (best_slot < 0 || s > best_s || (ranked && s == best_s && rk[i] < best_r)) {
+            best_s = s; best_slot = slot; best_n = nv[i]; best_r = ranked ? rk[i] : 0;
+          }
         }
       }
-      rz_warp_argmax(best_s, best_slot, best_n);
+      if (ranked) rz_warp_argmax_ranked(best_s, best_r, best_slot, best_n);
+      else rz_warp_argmax(best_s, best_slot, best_n);
     }
     if (best_slot < 0) { fault |= RZ_FAULT_NO_CHILDREN; break; }  // node.py:38-39
 
@@ -280,7 +326,8 @@ template <class GM, bool DM>
 __device__ __forceinline__ void
 rz_expand_backup_one(const rz_tree_desc& t, const int g, const int L, const bool dedup, const rz_geom& q,
                      const float* prior, int prior_is_log, const float* value, const double* value64,
-                     float noise_eps, float noise_alpha, unsigned long long seed, long long global_offset) {
+                     float noise_eps, float noise_alpha, unsigned long long seed, long long global_offset,
+                     const double* noise64, const double* prior64) {
   const int depth = t.depth[L];
   if (depth < 0) return;
   const int lane = rz_lane();
@@ -313,10 +360,18 @@ rz_expand_backup_one(const rz_tree_desc& t, const int g, const int L, const bool
       // node.py:71-73: one child per legal move, in ascending action order
       const uint32_t lctx = GM::legal_ctx(t, L, q);
       const size_t nb = rz_edge_base(t, g, nn);
-      const float* pr = prior + (size_t)L * AS;
+      const float* pr = prior ? prior + (size_t)L * AS : nullptr;
       float noise_sum = 0.0f;
       float nz[RZ_MAX_ITERS];
-      const bool noisy = noise_eps > 0.0f && !(DM && t.noise_root_only && depth > 0);
+      // host-supplied randomness (rz_tree_expand_backup_ex): no device draw
+      const double* hn = noise64 ? noise64 + (size_t)L * AS : nullptr;
+      const double* hp = prior64 ? prior64 + (size_t)L * AS : nullptr;
+      // the UCB1 rule never reads a prior: with no prior pool there is nothing the noise could change
+      const bool noisy = noise_eps > 0.0f && !(DM && t.noise_root_only && depth > 0) && !hp && t.store_priors;
+      const bool draw = noisy && !hn;
+      // noise stream of this node: Philox counter (global game, episode | slot << 20, ply << 16 | node, attempt)
+      const uint32_t c1 = (uint32_t)rm[RZ_META_EPISODE] & 0xfffffu;
+      const uint32_t c2 = ((uint32_t)rm[RZ_META_PLY] << 16) | (uint32_t)nn;
 #pragma unroll
       for (int i = 0; i < RZ_MAX_ITERS; ++i) {
         if (i >= (AS >> 5)) break;
@@ -324,31 +379,57 @@ rz_expand_backup_one(const rz_tree_desc& t, const int g, const int L, const bool
         const bool legal = GM::slot_legal(lctx, s, q);
         t.edge_N[nb + s] = legal ? 0 : -1;
         if (DM) t.edge_O[nb + s] = 0;
+        if (DM && t.edge_R) {
+          // children order: a random key per child (a uniformly random order, ties broken by the action), or the
+          // slot itself when the host supplies numpy's permutation afterwards (rz_tree_desc.edge_R)
+          int r = s;
+          if (t.shuffle_mode == 1) {
+            uint32_t rr[4];
+            rz_philox4((uint32_t)(global_offset + g), c1 | ((uint32_t)s << 20), c2, 0xffffu,
+                       seed ^ 0x517cc1b727220a95ull, rr);
+            r = (int)(rr[0] >> 1);
+          }
+          t.edge_R[nb + s] = legal ? r : 0x7fffffff;
+        }
         nz[i] = 0.0f;
-        if (noisy && legal) {
-          nz[i] = rz_gamma_draw(noise_alpha, seed, (uint32_t)(global_offset + g),
-                                (uint32_t)rm[RZ_META_EPISODE],
-                                ((uint32_t)rm[RZ_META_PLY] << 21) | ((uint32_t)nn << 9) | (uint32_t)s);
+        if (draw && legal) {
+          nz[i] = rz_gamma_draw(noise_alpha, seed, (uint32_t)(global_offset + g), c1 | ((uint32_t)s << 20), c2);
           noise_sum += nz[i];
         }
-        if (t.store_priors && !noisy) {
+        if (hp) {
+          const double p = legal ? hp[s] : 0.0;
+          if (t.store_priors) t.edge_P[nb + s] = (float)p;
+          if (t.edge_P64) t.edge_P64[nb + s] = p;
+        } else if (t.store_priors && !noisy) {
           float p = legal ? pr[s] : 0.0f;
           if (legal && prior_is_log) p = expf(p);
           t.edge_P[nb + s] = p;
+          if (t.edge_P64) t.edge_P64[nb + s] = (double)p;
         }
       }
       if (noisy) {
-        noise_sum = rz_warp_sum_f32(noise_sum);
-        const float inv = noise_sum > 0.0f ? 1.0f / noise_sum : 0.0f;
-        if (t.store_priors) {
+        float inv = 0.0f;
+        if (draw) {
+          noise_sum = rz_warp_sum_f32(noise_sum);
+          inv = noise_sum > 0.0f ? 1.0f / noise_sum : 0.0f;
+        }
 #pragma unroll
-          for (int i = 0; i < RZ_MAX_ITERS; ++i) {
-            if (i >= (AS >> 5)) break;
-            const int s = lane + 32 * i;
-            const bool legal = t.edge_N[nb + s] == 0;
-            float p = legal ? pr[s] : 0.0f;
-            if (legal && prior_is_log) p = expf(p);
-            t.edge_P[nb + s] = legal ? (1.0f - noise_eps) * p + noise_eps * nz[i] * inv : 0.0f;
+        for (int i = 0; i < RZ_MAX_ITERS; ++i) {
+          if (i >= (AS >> 5)) break;
+          const int s = lane + 32 * i;
+          const bool legal = t.edge_N[nb + s] == 0;
+          float p = legal ? pr[s] : 0.0f;
+          if (legal && prior_is_log) p = expf(p);
+          if (hn) {
+            // numpy: float32 * python float stays float32, float32 + float64 is float64 (node.py:68)
+            const double mixed = legal ? __dadd_rn((double)__fmul_rn(1.0f - noise_eps, p),
+                                                   __dmul_rn((double)noise_eps, hn[s])) : 0.0;
+            t.edge_P[nb + s] = (float)mixed;
+            if (t.edge_P64) t.edge_P64[nb + s] = mixed;
+          } else {
+            const float mixed = legal ? (1.0f - noise_eps) * p + noise_eps * nz[i] * inv : 0.0f;
+            t.edge_P[nb + s] = mixed;
+            if (t.edge_P64) t.edge_P64[nb + s] = (double)mixed;
           }
         }
       }
@@ -460,14 +541,16 @@ __global__ void __launch_bounds__(RZ_TREE_THREADS, 6)
 rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int prior_is_log,
                         const float* __restrict__ value, const double* __restrict__ value64,
                         float noise_eps, float noise_alpha,
-                        unsigned long long seed, long long global_offset) {
+                        unsigned long long seed, long long global_offset,
+                        const double* __restrict__ noise64, const double* __restrict__ prior64) {
   const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   const rz_geom q = rz_geom_of(t.game);
   const int K = t.leaves_per_tree > 1 ? t.leaves_per_tree : 1;
+  if (t.seed_dev) seed += *t.seed_dev;       // a captured graph draws fresh noise on every replay
   if (K == 1) {
     rz_expand_backup_one<GM, DM>(t, g, g, false, q, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed,
-                                 global_offset);
+                                 global_offset, noise64, prior64);
     return;
   }
   // leaf-parallel wave: take the virtual losses off again -- the saved value sums in reverse order of application,
@@ -490,7 +573,7 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
   }
   for (int k = 0; k < K; ++k) {
     rz_expand_backup_one<GM, DM>(t, g, g * K + k, true, q, prior, prior_is_log, value, value64, noise_eps, noise_alpha,
-                                 seed, global_offset);
+                                 seed, global_offset, noise64, prior64);
     __syncwarp();
   }
 }
@@ -654,6 +737,9 @@ __device__ int rz_tree_compact(const rz_tree_desc& t, int g, int c, uint32_t* bi
         t.edge_W[db + s] = wv;
         t.edge_child[db + s] = ch;
         if (t.store_priors) t.edge_P[db + s] = t.edge_P[sb + s];
+        if (t.edge_P64) t.edge_P64[db + s] = t.edge_P64[sb + s];
+        if (t.edge_O) t.edge_O[db + s] = t.edge_O[sb + s];
+        if (t.edge_R) t.edge_R[db + s] = t.edge_R[sb + s];
       }
       if (lane == 0) {
         const int p = parent[src];
@@ -723,10 +809,11 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
   const int cn = root_expanded ? t.edge_N[rb + m] : -1;  // -1: move not among the children
   const double cw = (cn > 0) ? t.edge_W[rb + m] : 0.0;
   const int cc = (cn > 0) ? t.edge_child[rb + m] : -1;
+  const int co = (cn > 0 && t.edge_O) ? t.edge_O[rb + m] : 0;   // SearchNode.outcome of the child that becomes the root
   if (!keep_subtree || cn < 0) {
     if (lane == 0) rz_tree_fresh(t, g, 0, 0.0);
   } else if (cc < 0) {  // child exists but was never expanded: it keeps its own counts
-    if (lane == 0) rz_tree_fresh(t, g, cn, cw);
+    if (lane == 0) { rz_tree_fresh(t, g, cn, cw); if (t.root_O) t.root_O[g] = co; }
   } else {
     const int kept = rz_tree_compact(t, g, cc, bits, wprefix, max_carry);
     if (lane == 0) {
@@ -735,6 +822,7 @@ rz_advance_kernel(rz_tree_desc t, const int32_t* __restrict__ moves, int keep_su
         rmeta[RZ_META_FAULT] |= RZ_FAULT_CARRY_DROPPED;
       } else {
         t.n_nodes[g] = kept; t.root_N[g] = cn; t.root_W[g] = cw;
+        if (t.root_O) t.root_O[g] = co;
       }
     }
   }
@@ -806,7 +894,7 @@ rz_best_child_kernel(rz_tree_desc t, int32_t* __restrict__ best, int32_t* __rest
   const int AS = t.game.action_stride;
   const int rp = t.root_meta[(size_t)g * RZ_META_STRIDE + RZ_META_PLAYER] & 1;
   const size_t base = rz_edge_base(t, g, 0);
-  int bo = -2, bn = -1, bs = 0x7fffffff;
+  int bo = -2, bn = -1, bs = 0x7fffffff, br = 0;   // br: position in the (shuffled) children list, 0 if unshuffled
   double bw = 0.0;
   if (t.n_nodes[g] > 0) {
     for (int s = lane; s < AS; s += 32) {
@@ -815,7 +903,10 @@ rz_best_child_kernel(rz_tree_desc t, int32_t* __restrict__ best, int32_t* __rest
       const int c = t.edge_O ? t.edge_O[base + s] : 0;
       const int o = c ? rz_outcome_of(c, rp) : 0;
       const double w = n > 0 ? t.edge_W[base + s] : 0.0;
-      if (bs == 0x7fffffff || o > bo || (o == bo && (n > bn || (n == bn && w > bw)))) { bo = o; bn = n; bw = w; bs = s; }
+      const int r = t.edge_R ? t.edge_R[base + s] : 0;
+      if (bs == 0x7fffffff || o > bo || (o == bo && (n > bn || (n == bn && (w > bw || (w == bw && r < br)))))) {
+        bo = o; bn = n; bw = w; bs = s; br = r;
+      }
     }
   }
 #pragma unroll
@@ -824,10 +915,11 @@ rz_best_child_kernel(rz_tree_desc t, int32_t* __restrict__ best, int32_t* __rest
     const int n2 = __shfl_xor_sync(RZ_FULL, bn, off);
     const double w2 = __shfl_xor_sync(RZ_FULL, bw, off);
     const int s2 = __shfl_xor_sync(RZ_FULL, bs, off);
+    const int r2 = __shfl_xor_sync(RZ_FULL, br, off);
     if (s2 == 0x7fffffff) continue;
     const bool greater = bs == 0x7fffffff || o2 > bo || (o2 == bo && (n2 > bn || (n2 == bn && w2 > bw)));
     const bool equal = bs != 0x7fffffff && o2 == bo && n2 == bn && w2 == bw;
-    if (greater || (equal && s2 < bs)) { bo = o2; bn = n2; bw = w2; bs = s2; }
+    if (greater || (equal && (r2 < br || (r2 == br && s2 < bs)))) { bo = o2; bn = n2; bw = w2; bs = s2; br = r2; }
   }
   if (lane == 0) {
     best[g] = bs == 0x7fffffff ? -1 : bs;
@@ -877,6 +969,9 @@ static int rz_check_tree(const rz_tree_desc* t, const char* who) {
              "%s: returns_mode %d", who, t->returns_mode);
   RZ_REQUIRE(t->leaves_per_tree >= 0 && t->leaves_per_tree <= 256, "%s: leaves_per_tree %d outside [0,256]", who,
              t->leaves_per_tree);
+  RZ_REQUIRE(!t->edge_P64 || t->store_priors, "%s: edge_P64 needs store_priors", who);
+  RZ_REQUIRE(!t->edge_R || t->flavour == RZ_FLAVOUR_DEEPMIND, "%s: edge_R (child shuffle) belongs to the DeepMindMCTS flavour", who);
+  RZ_REQUIRE(t->shuffle_mode == 0 || t->shuffle_mode == 1, "%s: shuffle_mode %d", who, t->shuffle_mode);
   if (t->leaves_per_tree > 1) {
     RZ_REQUIRE(t->flavour == RZ_FLAVOUR_ALPHAZERO, "%s: leaf-parallel waves (leaves_per_tree %d) need the AlphaZero flavour",
                who, t->leaves_per_tree);
@@ -912,7 +1007,8 @@ extern "C" int rz_tree_select(const rz_tree_desc* t, void* stream) {
 
 static int rz_expand_backup_launch(const rz_tree_desc* t, const float* prior, int prior_is_log,
                                    const float* value, const double* value64, float noise_eps,
-                                   float noise_alpha, unsigned long long seed, void* stream);
+                                   float noise_alpha, unsigned long long seed, void* stream,
+                                   const double* noise64 = nullptr, const double* prior64 = nullptr);
 
 extern "C" int rz_tree_expand_backup_dm(const rz_tree_desc* t, const float* prior, int prior_is_log,
                                         const float* value, const double* ret64, float noise_eps,
@@ -931,18 +1027,30 @@ extern "C" int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, 
   return rz_expand_backup_launch(t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, stream);
 }
 
+extern "C" int rz_tree_expand_backup_ex(const rz_tree_desc* t, const float* prior, int prior_is_log,
+                                        const float* value, const double* value64, float noise_eps,
+                                        float noise_alpha, unsigned long long seed, const double* noise64,
+                                        const double* prior64, void* stream) {
+  if (rz_check_tree(t, "rz_tree_expand_backup_ex")) return -1;
+  RZ_REQUIRE(!(noise64 && prior64), "rz_tree_expand_backup_ex: give noise64 or prior64, not both");
+  RZ_REQUIRE(!noise64 || (noise_eps > 0.0f && prior), "rz_tree_expand_backup_ex: noise64 needs noise_eps > 0 and a prior");
+  return rz_expand_backup_launch(t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, stream, noise64,
+                                 prior64);
+}
+
 static int rz_expand_backup_launch(const rz_tree_desc* t, const float* prior, int prior_is_log,
                                    const float* value, const double* value64, float noise_eps,
-                                   float noise_alpha, unsigned long long seed, void* stream) {
+                                   float noise_alpha, unsigned long long seed, void* stream,
+                                   const double* noise64, const double* prior64) {
   RZ_REQUIRE(value || value64, "rz_tree_expand_backup: null value");
-  RZ_REQUIRE(prior || !t->store_priors, "rz_tree_expand_backup: null prior with store_priors");
+  RZ_REQUIRE(prior || prior64 || !t->store_priors, "rz_tree_expand_backup: null prior with store_priors");
   RZ_REQUIRE(noise_eps >= 0.0f && noise_eps <= 1.0f, "rz_tree_expand_backup: noise_eps %f", noise_eps);
   RZ_REQUIRE(noise_eps == 0.0f || noise_alpha > 0.0f, "rz_tree_expand_backup: noise_alpha %f", noise_alpha);
   if (t->n_trees == 0) return 0;
   const dim3 grid = rz_tree_grid(t->n_trees);
   cudaStream_t st = (cudaStream_t)stream;
   const bool go = t->game.game_type == RZ_GAME_GO, dm = t->flavour == RZ_FLAVOUR_DEEPMIND;
-#define RZ_EB_ARGS *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset
+#define RZ_EB_ARGS *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset, noise64, prior64
   if (go && dm) rz_expand_backup_kernel<rz_go_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
   else if (go) rz_expand_backup_kernel<rz_go_game, false><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
   else if (dm) rz_expand_backup_kernel<rz_line_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);

@@ -48,11 +48,18 @@ class SearchForest(object):
                  device='cuda', global_offset=0, ln_table_len=None, with_trajectories=False,
                  ring_capacity=None, board_width=None, game_type=L.GAME_GOMOKU, komi=7.5, max_moves=0,
                  flavour=L.FLAVOUR_ALPHAZERO, solve=False, returns_mode=L.RETURNS_REFERENCE,
-                 noise_root_only=False, leaves_per_tree=1, virtual_loss=1.0):
+                 noise_root_only=False, leaves_per_tree=1, virtual_loss=1.0, prior_f64=False,
+                 child_shuffle=None):
         """``leaves_per_tree = K > 1`` switches to leaf-parallel waves with virtual loss (opt-in; not the
         reference's sequential order, see ``rz_tree_desc.leaves_per_tree``): every wave runs up to K playouts per
         tree and the evaluator sees ``n_leaves = G*K`` positions -- for a handful of games (the single-game API)
         this is what fills the network batch.  ``K = 1`` is the parity mode.
+
+        ``prior_f64``: keep the priors in float64 as well (``rz_tree_desc.edge_P64``): ``TreeNode.prior`` is a Python
+        float, and with Dirichlet noise the reference forms it in float64 (node.py:66-69), so the PUCT rule is only
+        bit-exact under noise with this pool.  ``child_shuffle`` (DeepMindMCTS flavour): ``'random'`` = the children of
+        every new node in a counter-based random order, ``'host'`` = the host writes numpy's permutation
+        (``set_child_order``), ``None`` = unshuffled, ties to the lowest action (deepmind_mcts.py:508).
 
         ``flavour = L.FLAVOUR_DEEPMIND`` runs the reference's second search driver, DeepMindMCTS
         (rlzero/mcts/deepmind_mcts.py:384-646): returns vectors, outcome shortcut, terminal outcomes,
@@ -88,7 +95,11 @@ class SearchForest(object):
         self.c_puct = float(c_puct)
         self.rule = int(rule)
         if max_carry is None:
-            max_carry = 64 if rule == L.RULE_UCT else self.n_playout
+            # nodes of the chosen child's subtree that update_with_move keeps (alphazero_mcts.py:96-103).  Under
+            # UCB1 with c = 5 the visits of a 15x15 search are spread almost evenly, so the kept subtree is a handful
+            # of nodes and 64 bounds the pool (20 B x AS per node x thousands of games); small boards concentrate
+            # them (a 4x4 / 400-playout search carries 70 nodes), and their blocks are small: carry everything
+            max_carry = self.n_playout if (rule != L.RULE_UCT or self.AS <= 64) else 64
         self.max_carry = int(max_carry)
         self.max_nodes = int(max_nodes) if max_nodes else self.n_playout + self.max_carry
         if self.max_nodes > 6144:
@@ -103,6 +114,11 @@ class SearchForest(object):
         self.edge_W = torch.empty(n_edges, dtype=f64, device=dev)
         self.edge_child = torch.empty(n_edges, dtype=i32, device=dev)
         self.edge_P = torch.empty(n_edges, dtype=f32, device=dev) if self.store_priors else None
+        self.edge_P64 = torch.empty(n_edges, dtype=f64, device=dev) if (prior_f64 and self.store_priors) else None
+        # search counter the captured wave graph reads (rz_tree_desc.seed_dev): bumped per search instead of
+        # re-capturing the graph with a new by-value seed
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.carry_dropped = 0       # re-roots whose kept subtree exceeded max_carry (tree restarted instead)
         self.node_parent = torch.empty(G * self.max_nodes, dtype=i32, device=dev)
         self.node_paction = torch.empty(G * self.max_nodes, dtype=i32, device=dev)
         self.n_nodes = torch.zeros(G, dtype=i32, device=dev)
@@ -126,6 +142,12 @@ class SearchForest(object):
         self.edge_O = torch.zeros(n_edges, dtype=i32, device=dev) if self.is_dm else None
         self.root_O = torch.zeros(G, dtype=i32, device=dev) if self.is_dm else None
         self.best = torch.full((G,), -1, dtype=i32, device=dev) if self.is_dm else None
+        if child_shuffle not in (None, 'random', 'host'):
+            raise ValueError("child_shuffle must be None, 'random' or 'host'")
+        if child_shuffle and not self.is_dm:
+            raise ValueError('the child shuffle belongs to the DeepMindMCTS flavour')
+        self.child_shuffle = child_shuffle
+        self.edge_R = torch.zeros(n_edges, dtype=i32, device=dev) if child_shuffle else None
         n_ln = int(ln_table_len) if ln_table_len else max(1 << 16, 4 * self.n_playout + 2)
         self.ln_table = torch.from_numpy(ln_table(n_ln)).to(dev)
         # evaluator outputs for one wave
@@ -158,6 +180,10 @@ class SearchForest(object):
         d.target_N = self.target_N.data_ptr() if self.K > 1 else None
         d.vl_saved_W = self.vl_saved_W.data_ptr() if self.K > 1 else None
         d.virtual_loss = self.virtual_loss
+        d.edge_P64 = self.edge_P64.data_ptr() if self.edge_P64 is not None else None
+        d.seed_dev = self.seed_dev.data_ptr()
+        d.edge_R = self.edge_R.data_ptr() if self.edge_R is not None else None
+        d.shuffle_mode = 1 if child_shuffle == 'random' else 0
         self.desc = d
         self.traj = None
         self.tdesc = None
@@ -244,9 +270,17 @@ class SearchForest(object):
         L.check(self.lib.rz_tree_select(C.byref(self.desc), self._s()), 'rz_tree_select')
 
     def expand_backup(self, prior_is_log=False, noise_eps=0.0, noise_alpha=0.3, seed=0,
-                      prior=None, value=None, value64=None):
+                      prior=None, value=None, value64=None, noise64=None, prior64=None):
+        """``noise64`` / ``prior64`` (float64 [n_leaves][AS] device tensors): host-supplied Dirichlet noise / finished
+        float64 priors of the new nodes (rz_tree_expand_backup_ex), the seeded-parity inputs."""
         prior = self.prior if prior is None else prior
         value = self.value if value is None else value
+        if noise64 is not None or prior64 is not None:
+            L.check(self.lib.rz_tree_expand_backup_ex(C.byref(self.desc), L.ptr(prior), int(prior_is_log),
+                                                      L.ptr(value), L.ptr(value64), float(noise_eps),
+                                                      float(noise_alpha), int(seed), L.ptr(noise64), L.ptr(prior64),
+                                                      self._s()), 'rz_tree_expand_backup_ex')
+            return
         if self.is_dm:      # value64 is then the evaluator's returns vector, float64 [G][2]
             L.check(self.lib.rz_tree_expand_backup_dm(C.byref(self.desc), L.ptr(prior), int(prior_is_log),
                                                       L.ptr(value), L.ptr(value64), float(noise_eps),
@@ -296,20 +330,26 @@ class SearchForest(object):
         prior_is_log = bool(getattr(evaluator, 'prior_is_log', False))
         capturable = bool(getattr(evaluator, 'graph_capturable', False))
 
+        # the per-search seed travels through the device word the kernels add to their by-value seed
+        # (rz_tree_desc.seed_dev), so one captured graph serves every search
+        self.seed_dev.fill_(int(seed))
+
         def wave():
             self.select()
             evaluator(self)
-            self.expand_backup(prior_is_log, noise_eps, noise_alpha, seed,
-                               value64=getattr(evaluator, 'value64', None))
+            self.expand_backup(prior_is_log, noise_eps, noise_alpha, 0,
+                               value64=getattr(evaluator, 'value64', None),
+                               prior64=getattr(evaluator, 'prior64', None))
 
         if not (use_graph and capturable) or n_waves < 4:
             for _ in range(n_waves):
                 wave()
             return
-        # weights_version: a captured graph holds the weight pointers (and the fused head's filter
-        # taps) by value, so repacked weights need a new capture
+        # weights_version: a captured graph holds the weight pointers (and the fused head's filter taps) and the
+        # evaluator's activation buffers by value, so repacked weights or re-allocated buffers need a new capture
+        # (NativeForward bumps it in both cases).  The cache entry keeps the evaluator alive: its id() is the key
         key = (id(evaluator), getattr(evaluator, 'weights_version', 0), prior_is_log, float(noise_eps),
-               float(noise_alpha), int(seed) if noise_eps > 0 else 0)   # the seed only feeds the noise
+               float(noise_alpha))
         graphs = self.__dict__.setdefault('_graphs', {})
         if key not in graphs and len(graphs) >= 8:
             graphs.clear()                                              # bounded cache
@@ -321,9 +361,9 @@ class SearchForest(object):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 wave()
-            graphs[key] = g
+            graphs[key] = (g, evaluator)
             # the capture itself did not run the wave
-        g = graphs[key]
+        g = graphs[key][0]
         for _ in range(n_waves):
             g.replay()
 
@@ -348,9 +388,16 @@ class SearchForest(object):
         f = self.faults()
         if not f.any():
             return
+        self.root_meta[:, L.META_FAULT] = 0
+        # a kept subtree larger than max_carry is not an error of the caller: the tree restarted from a fresh root
+        # (what update_with_move does for an unknown move, alphazero_mcts.py:102-103); count it
+        dropped = (f & L.FAULT_CARRY_DROPPED) != 0
+        self.carry_dropped += int(dropped.sum())
+        f = f & ~np.int32(L.FAULT_CARRY_DROPPED)
+        if not f.any():
+            return
         g = int(np.nonzero(f)[0][0])
         bits = int(f[g])
-        self.root_meta[:, L.META_FAULT] = 0
         if bits & L.FAULT_ILLEGAL_MOVE:
             raise AssertionError('You input illegal action (game %d)' % g)  # gomoku_env.py:51
         if bits & L.FAULT_NO_CHILDREN:
@@ -382,12 +429,24 @@ class SearchForest(object):
         Cc = self.edge_child[sl].cpu().numpy().reshape(-1, AS)[:, :A]
         P = (self.edge_P[sl].cpu().numpy().reshape(-1, AS)[:, :A] if self.edge_P is not None
              else np.ones_like(W, dtype=np.float32))
+        if self.edge_P64 is not None:
+            P = self.edge_P64[sl].cpu().numpy().reshape(-1, AS)[:, :A]
         out = dict(n_nodes=nn, N=N, W=W, child=Cc, P=P, root_N=int(self.root_N[g]),
                    root_W=float(self.root_W[g]))
+        if self.edge_R is not None:
+            out['R'] = self.edge_R[sl].cpu().numpy().reshape(-1, AS)[:, :A]
         if self.is_dm:
             out['O'] = self.edge_O[sl].cpu().numpy().reshape(-1, AS)[:, :A]
             out['root_O'] = int(self.root_O[g])
         return out
+
+    def set_child_order(self, g, node, order):
+        """DeepMindMCTS child shuffle, host mode: ``order`` = the legal actions of ``node`` of tree ``g`` in the
+        order of the reference's shuffled ``children`` list (deepmind_mcts.py:508-513)."""
+        base = (g * self.max_nodes + int(node)) * self.AS
+        rank = torch.full((self.AS,), 2 ** 31 - 1, dtype=torch.int32)
+        rank[torch.as_tensor(list(order), dtype=torch.int64)] = torch.arange(len(order), dtype=torch.int32)
+        self.edge_R[base:base + self.AS] = rank.to(self.device)
 
     def boards(self):
         """Root positions as (rows[G,2,H] uint32, meta[G,8] int32) numpy arrays."""
@@ -470,20 +529,31 @@ class HostCallbackEvaluator(object):
         self.fn = policy_value_fn
         self.env_factory = env_factory
         self.value64 = None
+        self.prior64 = None     # float64 priors for forests that keep them (SearchForest(prior_f64=True))
+
+    def _mix(self, act_probs, meta):
+        """[(action, prior)] of the node to create; subclasses add the noise."""
+        return act_probs
 
     def __call__(self, forest):
         rows, meta, depth = forest.leaf_boards()
-        prior = np.zeros((forest.n_leaves, forest.AS), dtype=np.float32)
+        prior = np.zeros((forest.n_leaves, forest.AS), dtype=np.float64)
         value = np.zeros(forest.n_leaves, dtype=np.float64)
         if self.value64 is None:
             self.value64 = torch.zeros(forest.n_leaves, dtype=torch.float64, device=forest.device)
+        if self.prior64 is None and forest.edge_P64 is not None:
+            self.prior64 = torch.zeros(forest.n_leaves, forest.AS, dtype=torch.float64, device=forest.device)
         for g in range(forest.n_leaves):
             if depth[g] < 0:
                 continue
             env = self.env_factory(rows[g], meta[g])
             act_probs, v = self.fn(env)
-            for a, p in act_probs:
-                prior[g, int(a)] = p
             value[g] = v
-        forest.prior.copy_(torch.from_numpy(prior))
+            if meta[g][L.META_STATUS] != L.ACTIVE:
+                continue  # terminal leaf: evaluated (alphazero_mcts.py:59) but never expanded (:61-62)
+            for a, p in self._mix(act_probs, meta[g]):
+                prior[g, int(a)] = p
+        forest.prior.copy_(torch.from_numpy(prior.astype(np.float32)))
+        if self.prior64 is not None:
+            self.prior64.copy_(torch.from_numpy(prior))   # TreeNode.prior is a Python float: keep every bit
         self.value64.copy_(torch.from_numpy(value))  # python floats are fp64: keep them exact

@@ -298,6 +298,10 @@ class NativeForward(object):
         if n <= self.max_batch:
             return
         dev = self.device
+        if self.max_batch:
+            # a captured wave graph holds the old buffers' addresses by value: growing them invalidates it, exactly
+            # like repacked weights do, so the same version word makes every holder re-capture
+            self.weights_version += 1
         self.max_batch = n
         if self.mode == 'tc':
             bf = torch.bfloat16

@@ -33,36 +33,20 @@ def softmax(x):
 class _NumpyNoiseCallback(HostCallbackEvaluator):
     """Host-callback evaluator that also draws the per-node Dirichlet noise from the global
     numpy RNG in the reference's order (node.py:63-69), keeping the RNG stream -- and hence
-    every later ``np.random.choice`` -- aligned with the reference."""
+    every later ``np.random.choice`` -- aligned with the reference.  The mix is formed with the
+    reference's own expression on the evaluator's own number types, so a forest that keeps
+    float64 priors (PUCT rule) holds ``TreeNode.prior`` bit for bit."""
 
     def __init__(self, policy_value_fn, env_factory, add_noise):
         super().__init__(policy_value_fn, env_factory)
         self.add_noise = add_noise
 
-    def __call__(self, forest):
-        rows, meta, depth = forest.leaf_boards()
-        prior = np.zeros((forest.n_leaves, forest.AS), dtype=np.float32)
-        value = np.zeros(forest.n_leaves, dtype=np.float64)
-        if self.value64 is None:
-            self.value64 = torch.zeros(forest.n_leaves, dtype=torch.float64, device=forest.device)
-        for g in range(forest.n_leaves):
-            if depth[g] < 0:
-                continue
-            env = self.env_factory(rows[g], meta[g])
-            act_probs, v = self.fn(env)
-            value[g] = v
-            if meta[g][L.META_STATUS] != L.ACTIVE:
-                continue  # terminal leaf: evaluated (:59) but never expanded (:61-62)
-            act_probs = list(act_probs)
-            if self.add_noise:
-                noise = np.random.dirichlet(0.3 * np.ones(len(act_probs)))
-                for i, (a, p) in enumerate(act_probs):
-                    prior[g, int(a)] = 0.75 * p + 0.25 * noise[i]
-            else:
-                for a, p in act_probs:
-                    prior[g, int(a)] = p
-        forest.prior.copy_(torch.from_numpy(prior))
-        self.value64.copy_(torch.from_numpy(value))
+    def _mix(self, act_probs, meta):
+        act_probs = list(act_probs)
+        if not self.add_noise:
+            return act_probs
+        noise = np.random.dirichlet(0.3 * np.ones(len(act_probs)))
+        return [(a, 0.75 * p + 0.25 * noise[i]) for i, (a, p) in enumerate(act_probs)]
 
 
 class AlphaZeroMCTS(object):
@@ -96,14 +80,18 @@ class AlphaZeroMCTS(object):
                 and f.k == env.n_in_row and self.n_playout <= f.n_playout and f.c_puct == float(self._c_puct)
                 and f.K == self.leaves_per_wave):
             return f     # n_playout may be lowered between moves (the pools were sized for the larger one)
-        carry = 64 if self.rule == L.RULE_UCT else self.n_playout
-        self._forest = SearchForest(1, env.board_size, env.n_in_row, n_playout=self.n_playout,
-                                    c_puct=self._c_puct, rule=self.rule, max_carry=carry,
-                                    device=self.device, board_width=width, game_type=game_type,
-                                    leaves_per_tree=self.leaves_per_wave, virtual_loss=self.virtual_loss)
         native = getattr(self, '_native_evaluator', None)
         if native is None:
             native = getattr(self.policy_value_fn, 'device_evaluator', None)
+        # update_with_move keeps the whole subtree of the move played (alphazero_mcts.py:96-103), which a search
+        # can grow to any size over a game: one tree costs little, so the pool takes everything the re-root kernel
+        # can compact (6144 nodes); a kept subtree beyond that restarts the tree (counted in forest.carry_dropped)
+        carry = max(0, min(6144 - int(self.n_playout), max(4 * int(self.n_playout), 1024)))
+        self._forest = SearchForest(1, env.board_size, env.n_in_row, n_playout=self.n_playout,
+                                    c_puct=self._c_puct, rule=self.rule, max_carry=carry,
+                                    device=self.device, board_width=width, game_type=game_type,
+                                    leaves_per_tree=self.leaves_per_wave, virtual_loss=self.virtual_loss,
+                                    prior_f64=(self.rule == L.RULE_PUCT and native is None))
         if native is not None:
             self._evaluator = native
         else:

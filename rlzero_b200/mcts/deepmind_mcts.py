@@ -12,9 +12,21 @@ MCTS-Solver backup (``solve``), root-only Dirichlet noise, early stop once the r
 * through ``evaluator.evaluate(env)`` / ``evaluator.prior(env)`` themselves (the reference's
   ``Evaluator`` contract, :14-28) per leaf on the host -- slow, but it accepts any user evaluator.
 
-Two things differ from the reference on purpose, both only in randomised tie-breaking: a new node's
-children are not shuffled (:508; ties go to the lowest action) and the root noise comes from the
-device's counter-based generator.  The reference's quirks that change results are kept: the noise
+Randomness.  The reference owns a private ``np.random.RandomState`` (:444) that shuffles every new
+node's ``children`` list (:508 -- ``max()`` takes the first maximum, so the list order is the tie-break
+of the descent and of ``best_child``) and draws the root's Dirichlet noise (:539).  Three modes:
+
+* ``random_state=np.random.RandomState(seed)`` -- the seeded parity path: the host walks the search one
+  simulation at a time, draws noise and shuffle from that very stream in the reference's order (at a
+  node's SECOND visit, when the reference creates its children) and hands the kernels the resulting
+  float64 priors and child order: visit counts, value sums and the move equal the reference's for the
+  same seed, bit for bit (``tests/golden/dm_mcts_shuffle.json``).  One tree, three small device-host
+  copies per simulation: a checker, not the fast path;
+* ``child_shuffle=True`` (default, like the reference) without a ``random_state`` -- counter-based random
+  child order and root noise on the device, inside the captured wave graph (same distribution);
+* ``child_shuffle=False`` -- no shuffle, ties to the lowest action (the deterministic fixtures).
+
+The reference's quirks that change results are kept: the noise
 concentration is ``dirichlet_noise_epsilon`` (:439 stores epsilon as alpha), and ``returns`` of a
 finished Gomoku game follow ``GomokuEnv.returns`` literally unless ``returns_mode`` says otherwise.
 """
@@ -89,11 +101,14 @@ class _HostEvaluator(object):
         self.evaluator = evaluator
         self.env_factory = env_factory
         self.value64 = None
+        self.prior64 = None       # float64 priors for a forest that keeps them (the seeded parity path)
 
     def __call__(self, forest):
         rows, meta, depth = forest.leaf_boards()
         hist = forest.leaf_hist.cpu().numpy() if forest.is_go else None
-        prior = np.zeros((forest.G, forest.AS), dtype=np.float32)
+        prior = np.zeros((forest.G, forest.AS), dtype=np.float64)
+        if self.prior64 is None and forest.edge_P64 is not None:
+            self.prior64 = torch.zeros(forest.G, forest.AS, dtype=torch.float64, device=forest.device)
         ret = np.zeros((forest.G, 2), dtype=np.float64)
         if self.value64 is None:
             self.value64 = torch.zeros(forest.G, 2, dtype=torch.float64, device=forest.device)
@@ -104,7 +119,9 @@ class _HostEvaluator(object):
             ret[g] = np.asarray(self.evaluator.evaluate(env), dtype=np.float64)[:2]
             for a, p in self.evaluator.prior(env):
                 prior[g, int(a)] = p
-        forest.prior.copy_(torch.from_numpy(prior))
+        forest.prior.copy_(torch.from_numpy(prior.astype(np.float32)))
+        if self.prior64 is not None:
+            self.prior64.copy_(torch.from_numpy(prior))
         self.value64.copy_(torch.from_numpy(ret))
 
 
@@ -150,6 +167,8 @@ class SearchNode(object):
                     kids.append(SearchNode(a, mover, float(s['P'][i, a]), n, float(s['W'][i, a]) if n >= 1 else 0.0,
                                            self._decode(int(s['O'][i, a])) if 'O' in s else None, _snap=s,
                                            _node=ch if ch >= 0 else -1))
+                if 'R' in s:      # the shuffled list order (deepmind_mcts.py:508), which max() breaks ties in
+                    kids.sort(key=lambda c: (int(s['R'][i, c.action]), c.action))
             self._kids = kids
         return self._kids
 
@@ -194,7 +213,8 @@ class DeepMindMCTS(object):
 
     def __init__(self, game_env, uct_c=2, max_simulations=2000, evaluator=None, child_selection_method='puct',
                  add_exploration_noise=False, dirichlet_noise_alpha=1.0, dirichlet_noise_epsilon=0.25, solve=True,
-                 verbose=False, returns_mode=L.RETURNS_REFERENCE, device='cuda', seed=0):
+                 verbose=False, returns_mode=L.RETURNS_REFERENCE, device='cuda', seed=0, child_shuffle=True,
+                 random_state=None):
         self.game_env = game_env
         self.uct_c = uct_c
         self.max_simulations = max_simulations
@@ -214,6 +234,8 @@ class DeepMindMCTS(object):
         self.returns_mode = int(returns_mode)
         self.device = device
         self._seed = int(seed)
+        self.child_shuffle = bool(child_shuffle)
+        self._random_state = random_state        # np.random.RandomState: the seeded parity path
         self._forest = None
         self._dev_eval = None
 
@@ -233,10 +255,13 @@ class DeepMindMCTS(object):
                 and self.max_simulations <= f.n_playout and f.c_puct == float(self.uct_c)):
             return f
         rule = L.RULE_PUCT if self.child_selection_method == 'puct' else L.RULE_UCT
+        seeded = self._random_state is not None
+        shuffle = None if not self.child_shuffle else ('host' if seeded else 'random')
         self._forest = SearchForest(1, H, k, n_playout=self.max_simulations, c_puct=self.uct_c, rule=rule,
                                     max_carry=0, device=self.device, board_width=W, game_type=game_type,
                                     komi=komi, flavour=L.FLAVOUR_DEEPMIND, solve=self.solve,
-                                    returns_mode=self.returns_mode, noise_root_only=True)
+                                    returns_mode=self.returns_mode, noise_root_only=True,
+                                    child_shuffle=shuffle, prior_f64=seeded)
         native = getattr(self.evaluator, 'device_evaluator', None)
         if native is not None:
             self._dev_eval = native
@@ -268,11 +293,55 @@ class DeepMindMCTS(object):
         f = self._ensure_forest(game_env)
         self._upload(game_env)
         self._seed += 1
-        eps = float(self.dirichlet_noise_epsilon) if self.add_exploration_noise else 0.0
-        f.run_waves(self.max_simulations, self._dev_eval, noise_eps=eps,
-                    noise_alpha=float(self.dirichlet_noide_alpha), seed=self._seed)
+        if self._random_state is not None:
+            self._search_seeded(f)
+        else:
+            eps = float(self.dirichlet_noise_epsilon) if self.add_exploration_noise else 0.0
+            f.run_waves(self.max_simulations, self._dev_eval, noise_eps=eps,
+                        noise_alpha=float(self.dirichlet_noide_alpha), seed=self._seed)
         f.raise_faults()
         return SearchNode.from_snapshot(f.dump_tree(0), int(game_env.current_player()))
+
+    def _search_seeded(self, f):
+        """The search with noise and child order drawn from ``self._random_state`` exactly when and how the
+        reference draws them (deepmind_mcts.py:499-513): at the second visit of a node -- the kernels created its
+        edge block at the first visit, with the evaluator's priors in action order -- the root's priors are mixed
+        with Dirichlet noise (:484-485,530-552; float64, ``eps * noise + (1 - eps) * p``), then the (action,
+        prior) list is shuffled, and the descent is repeated with that order as the tie-break."""
+        rs = self._random_state
+        ev = self._dev_eval
+        prior_is_log = bool(getattr(ev, 'prior_is_log', False))
+        AS, A = f.AS, f.A
+        ordered = set()                   # edge blocks whose children the reference has created
+        eps = float(self.dirichlet_noise_epsilon)
+        for _ in range(self.max_simulations):
+            f.select()
+            depth = int(f.depth[0].item())
+            if depth < 0:
+                break                      # proven root (:643-644) or a finished game
+            if depth > 0:
+                node = int(f.path_node[0, depth - 1].item())
+                if node not in ordered:
+                    base = node * AS
+                    legal = np.nonzero(f.edge_N[base:base + A].cpu().numpy() >= 0)[0]
+                    pri = f.edge_P64[base:base + A].cpu().numpy()
+                    pairs = [(int(a), float(pri[a])) for a in legal]
+                    if node == 0 and self.add_exploration_noise:
+                        noise = rs.dirichlet([self.dirichlet_noide_alpha] * len(pairs))
+                        pairs = [(a, eps * z + (1 - eps) * p) for (a, p), z in zip(pairs, noise)]
+                        new = np.zeros(AS, dtype=np.float64)
+                        for a, p in pairs:
+                            new[a] = p
+                        f.edge_P64[base:base + AS] = torch.from_numpy(new).to(f.device)
+                        f.edge_P[base:base + AS] = torch.from_numpy(new.astype(np.float32)).to(f.device)
+                    if self.child_shuffle:
+                        rs.shuffle(pairs)
+                        f.set_child_order(0, node, [a for a, _ in pairs])
+                    ordered.add(node)
+                    f.select()             # the same descent, ties now broken in list order
+            ev(f)
+            f.expand_backup(prior_is_log, 0.0, 1.0, 0, value64=getattr(ev, 'value64', None),
+                            prior64=getattr(ev, 'prior64', None))
 
     def step_with_policy(self, game_env):
         """Returns bot's policy and action at given state (deepmind_mcts.py:447-472)."""

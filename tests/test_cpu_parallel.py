@@ -52,12 +52,38 @@ def _worker(rank, world, port, out_dir):
             assert np.array_equal(g_pis, np.concatenate([e[1] for e in exp]))
             assert np.array_equal(g_zs, np.concatenate([e[2] for e in exp]))
             assert np.array_equal(g_info, np.concatenate([e[3] for e in exp]))
+        # compact device-record gather (the NCCL path's function on gloo/CPU tensors): ragged, one rank empty,
+        # local slot -> global game id, pi travels bit-cast and comes back bit for bit
+        for counts in ([3, 5], [0, 4], [0, 0]):
+            n = counts[rank]
+            rs = np.random.RandomState(200 + rank)
+            rows = torch.from_numpy(rs.randint(0, 1 << 15, size=(n, 2, 15)).astype(np.int32))
+            info = torch.from_numpy(rs.randint(0, 50, size=(n, 6)).astype(np.int32))
+            pi = torch.from_numpy(rs.rand(n, 256).astype(np.float32))
+            g_rows, g_info, g_pi, got = parallel.gather_records_device(rows, info, pi, global_offset=1000 * rank)
+            assert got == counts
+            if sum(counts) == 0:
+                continue
+            exp = []
+            for r in range(world):
+                rr = np.random.RandomState(200 + r)
+                m = counts[r]
+                e_rows = rr.randint(0, 1 << 15, size=(m, 2, 15)).astype(np.int32)
+                e_info = rr.randint(0, 50, size=(m, 6)).astype(np.int32)
+                e_info[:, 3] += 1000 * r
+                exp.append((e_rows, e_info, rr.rand(m, 256).astype(np.float32)))
+            assert np.array_equal(g_rows.numpy(), np.concatenate([e[0] for e in exp]))
+            assert np.array_equal(g_info.numpy(), np.concatenate([e[1] for e in exp]))
+            assert np.array_equal(g_pi.numpy(), np.concatenate([e[2] for e in exp]))
+        p_rows, p_info, p_pi = parallel.unpack_records(parallel.pack_records(rows, info, pi), 15)
+        assert torch.equal(p_rows, rows) and torch.equal(p_info, info) and torch.equal(p_pi, pi)
         # weight broadcast: every rank ends with rank 0's parameters, bit for bit
         torch.manual_seed(1234 + rank)
         net = PolicyValueNet(6)
         torch.manual_seed(1234)
         ref = PolicyValueNet(6)
-        parallel.broadcast_weights(net, src=0)
+        moved = parallel.broadcast_weights(net, src=0)
+        assert moved == sum(p.numel() * p.element_size() for p in ref.parameters())
         for (k, a), (_, b) in zip(net.state_dict().items(), ref.state_dict().items()):
             assert torch.equal(a, b), k
         open(os.path.join(out_dir, 'ok%d' % rank), 'w').write('ok')

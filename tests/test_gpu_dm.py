@@ -159,7 +159,7 @@ def test_deepmind_mcts_class_with_a_python_evaluator_matches_fixtures():
         for a in c['moves']:
             env.step(a)
         bot = DeepMindMCTS(env, uct_c=2, max_simulations=c['sims'], evaluator=dm_oracle.ClosedFormEvaluator(c['eval_id']),
-                           child_selection_method=c['method'], solve=c['solve'])
+                           child_selection_method=c['method'], solve=c['solve'], child_shuffle=False)
         root = bot.mcts_search(env)
         assert root.explore_count == c['root_n'] and root.total_reward == c['root_w'] and root.outcome == c['root_outcome']
         got = [[ch.action, ch.explore_count, ch.total_reward, ch.outcome] for ch in root.children]
