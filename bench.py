@@ -432,14 +432,16 @@ def config_block(args, peaks):
         return e
 
     torch.manual_seed(0)
-    # config 1: TicTacToe = GomokuEnv(3, 3), 25 simulations/move, the stock PolicyValueNet (fp32 path)
+    # config 1: TicTacToe = GomokuEnv(3, 3), 25 simulations/move, the stock PolicyValueNet on its default
+    # path (mode 'tc32': tensor cores at float32-level accuracy, 16-stride layout)
     net1 = PolicyValueNet(3).cuda().eval()
     for G in (1, 8192):
         sp = BatchedSelfPlay(G, 3, 3, net=net1, n_playout=25, add_noise=True, seed=1)
-        entry('config1: TicTacToe 3x3 k=3, 25 sims/move, stock PolicyValueNet fp32 CUDA-core path, %d game(s)' % G, sp,
-              stock_flops(3), 25 * 20, 25, 3, cpu='config1' if G == 1 else None, dtype='f32',
+        entry('config1: TicTacToe 3x3 k=3, 25 sims/move, stock PolicyValueNet (mode %s), %d game(s)' % (
+            sp.evaluator.mode, G), sp, stock_flops(3), 25 * 20, 25, 3, cpu='config1' if G == 1 else None, dtype='bf16x3',
               note='one game = one board per launch: launch-latency bound, the tensor roofline does not apply'
-              if G == 1 else 'fp32 CUDA-core convolutions by design (1e-5 parity path)')
+              if G == 1 else 'a 3x3 board occupies 9 of the 256 rows of its 16-stride tile: the issued MMAs are 28x the '
+                             'algorithmic FLOPs counted here')
         del sp
     # config 2: Connect Four 6x7, 200 simulations/move, 4096 games, ResNet-6 bf16
     net2 = ResNetPolicyValueNet(6, n_blocks=6, board_width=7, n_actions=7).cuda().eval()
@@ -459,10 +461,11 @@ def config_block(args, peaks):
     torch.cuda.empty_cache()
     # the reference's OWN network at config 3's size: fp32 default path and the tensor-core path
     net = PolicyValueNet(15).cuda().eval()
-    for mode, waves in (('f32', 16), ('tc', 200)):
+    for mode, waves in (('tc32', 200), ('f32', 16), ('tc', 200)):
         sp = BatchedSelfPlay(8192, 15, 5, net=net, n_playout=800, add_noise=True, seed=1, net_mode=mode)
-        entry('stock PolicyValueNet 15x15, 800 sims/move, 8192 games, mode %s' % mode, sp, stock_flops(15), waves, 4,
-              31, dtype='f32' if mode == 'f32' else 'bf16',
+        entry('stock PolicyValueNet 15x15, 800 sims/move, 8192 games, mode %s%s' % (
+            mode, ' (the default: float32-level accuracy on the tensor cores)' if mode == 'tc32' else ''), sp,
+              stock_flops(15), waves, 4, 31, dtype={'f32': 'f32', 'tc': 'bf16', 'tc32': 'bf16x3'}[mode],
               note='the CPU sample of this search is cpu_baseline.stock_net of the headline')
         del sp
         torch.cuda.empty_cache()

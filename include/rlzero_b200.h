@@ -418,6 +418,18 @@ int rz_net_conv3x3_tc2_head(const void* act_in, const void* weight, const float*
                             int n_boards, int board_size, int board_cols, int c_in, int relu,
                             const float* w1x1_host, const float* b1x1_host, float* feat, int n_ctas,
                             void* stream);
+/* the same with the kernel's mode flags: 16 = split input (act_in = [hi 0..63 | lo 0..63], the bf16 high parts and
+   rounding residues of a 64-channel float32-accurate activation; weight = [tap][128][Whi 0..63 | Wlo 0..63]; three
+   products per tap: hi*Whi + lo*Whi + hi*Wlo), 32 = the 1x1 head convolutions read the float32 accumulators instead
+   of bf16-rounded activations.  Together: conv3 (64 -> 128) + act_conv1 / val_conv1 of the reference's own
+   PolicyValueNet at float32-level accuracy on the tensor cores.  Likewise rz_net_conv3x3_tc2 accepts flags 8 =
+   split output (64 real output channels written as [hi 0..63 | lo 0..63]; needs flag 2), and the `relu` argument of
+   rz_net_stem_tc / rz_net_stem_tc_planes bit 1 = 32-channel float32-accurate stem: weight rows 0..31 / 32..63 hold
+   the high parts / residues of the 32 filters, the output row is [hi 0..31 | lo 0..31 | hi 0..31 | lo 0..31]. */
+int rz_net_conv3x3_tc2_head_ex(const void* act_in, const void* weight, const float* bias, const void* residual,
+                               int n_boards, int board_size, int board_cols, int c_in, int relu, int flags,
+                               const float* w1x1_host, const float* b1x1_host, float* feat, int n_ctas,
+                               void* stream);
 /* revision 3 of the convolution: the same data path for any row stride of the padded position
    layout (row = board*S*S + y*S + x; S = row_stride = 8 for boards up to 7x7 such as Connect Four 6x7, 16 up
    to 15x15, 20 up to 19x19), tiles of 128 rows that may straddle boards (S = 20) or hold two boards (S = 8), a 3-slot ring of k-block halo tiles and a half-staged TMA-store

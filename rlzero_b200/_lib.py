@@ -130,6 +130,8 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.c_int, _vp]),
     'rz_net_conv3x3_tc2_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                                           _vp, _vp, C.c_int, _vp]),
+    'rz_net_conv3x3_tc2_head_ex': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             _vp, _vp, _vp, C.c_int, _vp]),
     'rz_net_conv3x3_tc3': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, _vp]),
     'rz_net_conv3x3_tc3_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,

@@ -144,7 +144,47 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p
     rz::tc_fence_after();
     // ---- epilogue: row per thread, 256-bit global stores straight from registers (L1::no_allocate, as in the
     // trunk convolution): no staging tile, no TMA store to wait for before the next tile
-    {
+    if (p.relu & 2) {
+      // float32-accurate 32-channel stem (the reference's own conv1 4 -> 32, policy_value_net.py:14): the weight
+      // rows hold the bf16 high parts of the 32 filters (rows 0..31) and the rounding residues (rows 32..63), the
+      // inputs are 0/1, so acc[c] + acc[32 + c] is the float32 convolution.  The activation leaves as a bf16
+      // (high, low) pair per channel in the layout the next layer's single K = 128 pass consumes:
+      // [hi 0..31 | lo 0..31 | hi 0..31 | lo 0..31] against weights [Whi | Whi | Wlo | Wlo].
+      const int pos = my_row - b * P;
+      const bool valid = (pos % kS < W) && (pos / kS < H) && b < p.n_boards;
+      __nv_bfloat16* orow = p.out + (size_t)my_row * 128;
+      uint32_t a_hi[32], a_lo[32];
+      rz::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16), a_hi);
+      rz::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + 32u, a_lo);
+      rz::tmem_ld_wait();
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float v0 = (__uint_as_float(a_hi[2 * e]) + __uint_as_float(a_lo[2 * e])) + s_bias[2 * e];
+        float v1 = (__uint_as_float(a_hi[2 * e + 1]) + __uint_as_float(a_lo[2 * e + 1])) + s_bias[2 * e + 1];
+        if (p.relu & 1) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+        if (!valid) { v0 = 0.0f; v1 = 0.0f; }
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+        hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - __low2float(h2), v1 - __high2float(h2));
+        lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      if (my_row < p.rows_alloc) {
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+          uint32_t v8[8];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v8[e] = hi[j * 8 + e];
+            rz::st_global_v8(orow + rep * 64 + j * 16, v8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v8[e] = lo[j * 8 + e];
+            rz::st_global_v8(orow + rep * 64 + 32 + j * 16, v8);
+          }
+        }
+      }
+    } else {
       const int pos = my_row - b * P;
       const bool valid = (pos % kS < W) && (pos / kS < H) && b < p.n_boards;
       __nv_bfloat16* orow = p.out + (size_t)my_row * 128;
@@ -161,7 +201,7 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p
             const int c = j * 16 + e * 2;
             float v0 = __uint_as_float(acc[c]) + s_bias[ch * 32 + c];
             float v1 = __uint_as_float(acc[c + 1]) + s_bias[ch * 32 + c + 1];
-            if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+            if (p.relu & 1) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
             if (!valid) { v0 = 0.0f; v1 = 0.0f; }
             const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
             packed[e] = *reinterpret_cast<const uint32_t*>(&o2);

@@ -178,9 +178,14 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
         for (int tap = 0; tap < 9; ++tap) {
           const int shift = HALO + (tap / 3 - 1) * 16 + (tap % 3 - 1);   // 0..34 rows into the halo tile
           if (it == 0) { rz::mbar_wait(bar_btap + 8 * tap, 0); rz::tc_fence_after(); }   // this tap's weights have landed
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            const uint32_t a_addr = a_buf + (uint32_t)kb * A_KB_BYTES + (uint32_t)shift * 128u;
-            const uint32_t b_addr = smem_base + (uint32_t)(tap * 2 + kb) * B_TILE_BYTES;
+          // flags bit 4 (split input, c_in = 128 = [hi 0..63 | lo 0..63] of a 64-channel float32-accurate
+          // activation against weights [Whi | Wlo]): three products per tap -- hi*Whi, lo*Whi, hi*Wlo
+          const int n_prod = (p.flags & 16) ? 3 : p.kblocks;
+          for (int pr = 0; pr < n_prod; ++pr) {
+            const int ka = (p.flags & 16) ? (pr == 1 ? 1 : 0) : pr;      // k-block of the activation tile
+            const int kw = (p.flags & 16) ? (pr == 2 ? 1 : 0) : pr;      // k-block of the weights
+            const uint32_t a_addr = a_buf + (uint32_t)ka * A_KB_BYTES + (uint32_t)shift * 128u;
+            const uint32_t b_addr = smem_base + (uint32_t)(tap * 2 + kw) * B_TILE_BYTES;
             const uint64_t adesc = rz::umma_desc_sw128_bo(a_addr, (p.flags & 1) ? (a_addr >> 7) & 7u : 0u);
             const uint64_t bdesc = rz::umma_desc_sw128(b_addr);
 #pragma unroll
@@ -210,6 +215,11 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
     constexpr int HALF = ACC_N / 2;                 // columns per thread: 64 (pair) / 32 (single CTA)
     constexpr int NCHH = HALF / 32;                 // 32-column TMEM chunks per thread
     const int col0 = ((kCG == 2) ? 0 : half * 64) + hsel * HALF;   // first output channel of this thread
+    // flags bit 3 (split output, pair kernel): the layer has 64 real output channels (accumulator columns 0..63);
+    // the row leaves as [hi 0..63 | lo 0..63], hi = bf16(x), lo = bf16(x - hi): warps with hsel = 0 write the high
+    // parts, their partners read the SAME columns and write the rounding residues
+    const bool split_out = (kCG == 2) && (p.flags & 8);
+    const int csrc = split_out ? 0 : hsel * HALF;                    // first accumulator column this thread reads
     const int r_in_tile = q * 32 + lane;
     auto row_valid = [&](int item_) {
       const int pos_ = (row_of(item_) + r_in_tile) & 255;
@@ -261,7 +271,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       uint32_t acc[NCHH][32];
 #pragma unroll
       for (int ch = 0; ch < NCHH; ++ch)
-        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_N + hsel * HALF + ch * 32), acc[ch]);
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_N + csrc + ch * 32), acc[ch]);
       rz::tmem_ld_wait();
       // accumulator drained: the MMA issuer may overwrite it (no memory payload -> relaxed)
       rz::tc_fence_before();
@@ -276,7 +286,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       const uint32_t chunk0 = (uint32_t)(((hsel * HALF) & 63) >> 3);
       const uint32_t srow = a_base + (uint32_t)buf * A_BUF_BYTES + (uint32_t)kbs * (TILE_M * 128u) + (uint32_t)r_in_tile * 128u;
       const uint32_t sw = (srow >> 7) & 7u;
-      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + col0);
+      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + (split_out ? csrc : col0));
       uint32_t pair8[8];
 #pragma unroll
       for (int ch = 0; ch < NCHH; ++ch) {
@@ -296,6 +306,10 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
               v1 += __uint_as_float(rw & 0xffff0000u);
             }
             packed[e] = p.relu ? rz::pack_bf16x2_relu(v0, v1) : rz::pack_bf16x2(v0, v1);
+            if (split_out && hsel == 1) {      // the residue of the (ReLU'd) float32 value after its bf16 high part
+              if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+              packed[e] = rz::pack_bf16x2(v0 - __uint_as_float(packed[e] << 16), v1 - __uint_as_float(packed[e] & 0xffff0000u));
+            }
             if (!valid) packed[e] = 0u;
           }
           if (kDirect) {
@@ -387,8 +401,13 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
             }
             uint32_t pk = p.relu ? rz::pack_bf16x2_relu(v0, v1) : rz::pack_bf16x2(v0, v1);
             if (!valid) pk = 0u;
-            // on the bf16-rounded activations, channels in ascending order
-            const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+            // on the bf16-rounded activations, channels in ascending order; flags bit 5: on the float32
+            // activations themselves (the float32-accurate path of the stock network)
+            float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+            if (p.flags & 32) {
+              r0 = valid ? (p.relu ? fmaxf(v0, 0.0f) : v0) : 0.0f;
+              r1 = valid ? (p.relu ? fmaxf(v1, 0.0f) : v1) : 0.0f;
+            }
             const int cc = ch * 32 + c;                 // channel within this thread's half
 #pragma unroll
             for (int f = 0; f < 6; ++f) {
@@ -464,6 +483,9 @@ static int conv2_entry(const void* act_in, const void* weight, const float* bias
   RZ_REQUIRE(c_in == 64 || c_in == 128, "rz_net_conv3x3_tc2: c_in %d (64 or 128)", c_in);
   RZ_REQUIRE(cta_group == 1 || cta_group == 2, "rz_net_conv3x3_tc2: cta_group %d (1 or 2)", cta_group);
   RZ_REQUIRE(act_in != act_out, "rz_net_conv3x3_tc2: in-place convolution is not supported");
+  RZ_REQUIRE(!(flags & (8 | 16)) || (cta_group == 2 && c_in == 128),
+             "rz_net_conv3x3_tc2: the split modes (flags 8 / 16) need the pair kernel and c_in = 128");
+  RZ_REQUIRE(!(flags & 8) || (flags & 2) || feat, "rz_net_conv3x3_tc2: split output (flag 8) needs the direct-store epilogue (flag 2)");
   if (n_boards == 0) return 0;
   static HeadTaps head;   // ~3 KB: filled per call, copied into the launch parameters
   CUtensorMap tmap_act, tmap_w, tmap_out;
@@ -512,5 +534,15 @@ extern "C" int rz_net_conv3x3_tc2_head(const void* act_in, const void* weight, c
                                        float* feat, int n_ctas, void* stream) {
   RZ_REQUIRE(w1x1_host && b1x1_host && feat, "rz_net_conv3x3_tc2_head: null head argument");
   return conv2_entry(act_in, weight, bias, residual, nullptr, n_boards, board_size, board_cols, c_in, relu, 2, 0, n_ctas,
+                     w1x1_host, b1x1_host, feat, stream);
+}
+
+extern "C" int rz_net_conv3x3_tc2_head_ex(const void* act_in, const void* weight, const float* bias,
+                                          const void* residual, int n_boards, int board_size, int board_cols,
+                                          int c_in, int relu, int flags, const float* w1x1_host,
+                                          const float* b1x1_host, float* feat, int n_ctas, void* stream) {
+  RZ_REQUIRE(w1x1_host && b1x1_host && feat, "rz_net_conv3x3_tc2_head_ex: null head argument");
+  RZ_REQUIRE((flags & ~(16 | 32)) == 0, "rz_net_conv3x3_tc2_head_ex: flags %d (16 = split input, 32 = float32 features)", flags);
+  return conv2_entry(act_in, weight, bias, residual, nullptr, n_boards, board_size, board_cols, c_in, relu, 2, flags, n_ctas,
                      w1x1_host, b1x1_host, feat, stream);
 }

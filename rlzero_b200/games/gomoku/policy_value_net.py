@@ -143,6 +143,14 @@ class NativeForward(object):
                  boards up to 19x19; outputs within 1e-3 of fp32.  Opt-in for the stock network, whose default
                  stays 'f32')
     mode 'f32' : fp32 CUDA-core trunk (any channel counts, any board <= 19)
+    mode 'tc32': the reference's own PolicyValueNet (4 -> 32 -> 64 -> 128, policy_value_net.py:14-16) on the tensor
+                 cores at float32-level accuracy: every activation and weight travels as a bf16 (high, low) pair
+                 (x = hi + lo, 16 mantissa bits) and every convolution forms hi*Whi + lo*Whi + hi*Wlo (+ lo*Wlo
+                 where it is free) in the fp32 accumulators -- the recipe of the tensor-core heads.  conv1 is the
+                 fused encoder/stem kernel with the filters' high parts and residues as separate output columns;
+                 conv2 is ONE ordinary K = 128 pass over [hi | lo | hi | lo] x [Whi | Whi | Wlo | Wlo]; conv3 runs
+                 three products per tap and feeds the heads' 1x1 convolutions from the fp32 accumulators.  Boards
+                 up to 15x15 (16-stride layout).  The default for the stock network on such boards.
     """
     graph_capturable = True
     prior_is_log = True       # the network emits log-probabilities (policy_value_net.py:44)
@@ -180,8 +188,17 @@ class NativeForward(object):
             raise ValueError('row_stride %r does not hold a %dx%d board (8, 16 or 20, > max(H, W))' % (
                 row_stride, self.H, self.W))
         self.P = self.S * self.S
+        stock = (len(layers) == 3 and [l[0].in_channels for l in layers] == [4, 32, 64]
+                 and [l[0].out_channels for l in layers] == [32, 64, 128] and all(l[1] is None and l[2] is None for l in layers)
+                 and self.game_type != L.GAME_GO)
         if mode is None:
-            mode = 'tc' if (all128 and fits) else 'f32'
+            mode = 'tc' if (all128 and fits) else ('tc32' if (stock and max(self.H, self.W) <= 15) else 'f32')
+        if mode == 'tc32':
+            if not (stock and max(self.H, self.W) <= 15):
+                raise ValueError("mode 'tc32' serves the stock 4 -> 32 -> 64 -> 128 PolicyValueNet on boards up to 15x15")
+            if row_stride not in (None, 0, 16):
+                raise ValueError("mode 'tc32' uses the 16-stride layout")
+            self.S, self.P = 16, 256
         if mode == 'tc' and not (tc_able and fits):
             raise ValueError("mode 'tc' needs trunk layers of at most 128 channels (the last one 128) and a board of "
                              "at most 19x19")
@@ -197,7 +214,7 @@ class NativeForward(object):
         self.fused_stem = bool(fused_stem)  # encoder + first conv in one kernel (rz_net_stem.cu)
         # the heads' fully connected layers on the tensor cores (rz_net_heads_tc.cu; bf16 hi/lo split, fp32-level
         # accuracy); False keeps the CUDA-core heads kernel
-        self.heads_tc = bool(heads_tc) and mode == 'tc'
+        self.heads_tc = (bool(heads_tc) and mode == 'tc') or mode == 'tc32'
         # 3: rz_net_tc3.cu (any row stride; forced for 19x19); 2: rz_net_tc2.cu (stride 16); 1: rz_net_tc.cu
         self.conv_rev = int(conv_rev)
         # rz_net_conv3x3_tc2 flags: bit 1 = direct-store epilogue, the default (853 k vs 840 k sims/s sustained on
@@ -214,7 +231,9 @@ class NativeForward(object):
         dev = self.device
         m = self.module
         self.layers = []
-        for conv, bn, skip, relu in m.trunk_layers():
+        if self.mode == 'tc32':
+            self._pack_tc32()
+        for conv, bn, skip, relu in (m.trunk_layers() if self.mode != 'tc32' else []):
             w, b = _fold_bn(conv, bn)                      # [Cout][Cin][3][3]
             cout, cin = w.shape[0], w.shape[1]
             if self.mode == 'tc':
@@ -233,9 +252,12 @@ class NativeForward(object):
             self.layers.append(dict(w=wd, b=b.float().contiguous().to(dev), cin=cin_p, cout=cout,
                                     skip=skip, relu=bool(relu)))
         # fused encoder + stem (rz_net_stem.cu): weight [cout][k = tap*4 + plane], k padded to 64
-        self.stem = None
         conv0 = m.trunk_layers()[0][0]
-        if self.game_type == L.GAME_GO:
+        if self.mode != 'tc32':
+            self.stem = None
+        if self.mode == 'tc32':
+            pass
+        elif self.game_type == L.GAME_GO:
             # fused GoEnv.observe + stem (rz_net_stem.cu): weight [cout][k = tap*17 + plane], k padded to 192
             if conv0.in_channels != 17 or m.trunk_layers()[0][1] is not None:
                 raise ValueError('the Go stem takes the 17 planes of GoEnv.observe (go_env.py:156-166)')
@@ -289,10 +311,47 @@ class NativeForward(object):
         self.weights_version += 1
         hd = L.HeadsDesc()
         hd.board_size, hd.action_stride, hd.width, hd.n_actions = self.H, AS, self.W, self.A
-        hd.row_stride = self.S if self.mode == 'tc' else 0
+        hd.row_stride = self.S if self.mode in ('tc', 'tc32') else 0
         for k, v in self.heads.items():
             setattr(hd, k, v.data_ptr())
         self.hdesc = hd
+
+    @staticmethod
+    def _split(w):
+        """float64/float32 tensor -> (hi, lo) bf16 with hi + lo = w to 16 mantissa bits."""
+        w = w.float()
+        hi = w.to(torch.bfloat16)
+        lo = (w - hi.float()).to(torch.bfloat16)
+        return hi, lo
+
+    def _pack_tc32(self):
+        """Weights of the float32-accurate tensor-core path (mode 'tc32', see the class docstring)."""
+        dev = self.device
+        (c1, _, _, r1), (c2, _, _, r2), (c3, _, _, r3) = self.module.trunk_layers()
+        # conv1 through the fused stem: weight [128 rows][64 k], k = tap*4 + plane; rows 0..31 = high parts, rows
+        # 32..63 = residues of the 32 filters
+        w1 = c1.weight.detach().cpu().double().permute(0, 2, 3, 1).reshape(32, 36)
+        hi, lo = self._split(w1)
+        ws = torch.zeros(128, 64, dtype=torch.bfloat16)
+        ws[:32, :36], ws[32:64, :36] = hi, lo
+        b1 = torch.zeros(128)
+        b1[:32] = c1.bias.detach().cpu().float()
+        self.stem = dict(w=ws.contiguous().to(dev), b=b1.to(dev), relu=int(bool(r1)) | 2)
+        # conv2: [tap][cout (64 real of 128)][cin = hi | lo | hi | lo of the 32 inputs] x [Whi | Whi | Wlo | Wlo]
+        w2 = c2.weight.detach().cpu().double().permute(2, 3, 0, 1).reshape(9, 64, 32)
+        hi, lo = self._split(w2)
+        wt = torch.zeros(9, 128, 128, dtype=torch.bfloat16)
+        wt[:, :64, 0:32], wt[:, :64, 32:64], wt[:, :64, 64:96], wt[:, :64, 96:128] = hi, hi, lo, lo
+        b2 = torch.zeros(128)
+        b2[:64] = c2.bias.detach().cpu().float()
+        # conv3: [tap][cout 128][cin = Whi (64) | Wlo (64)], three products per tap in the kernel
+        w3 = c3.weight.detach().cpu().double().permute(2, 3, 0, 1).reshape(9, 128, 64)
+        hi, lo = self._split(w3)
+        wt3 = torch.cat([hi, lo], dim=2).contiguous()
+        self.layers = [dict(w=None, b=None, cin=64, cout=128, skip=None, relu=bool(r1)),      # the stem
+                       dict(w=wt.contiguous().to(dev), b=b2.to(dev), cin=128, cout=128, skip=None, relu=bool(r2)),
+                       dict(w=wt3.to(dev), b=c3.bias.detach().float().contiguous().to(dev), cin=128, cout=128,
+                            skip=None, relu=bool(r3))]
 
     def _alloc(self, n):
         if n <= self.max_batch:
@@ -303,7 +362,7 @@ class NativeForward(object):
             # like repacked weights do, so the same version word makes every holder re-capture
             self.weights_version += 1
         self.max_batch = n
-        if self.mode == 'tc':
+        if self.mode in ('tc', 'tc32'):
             bf = torch.bfloat16
             rows = (n * self.P + 255) // 256 * 256          # the convolutions work on pairs of 128-row tiles
             self.act0 = torch.zeros(n, 256, 64, dtype=bf, device=dev) if self.S == 16 else None
@@ -318,7 +377,7 @@ class NativeForward(object):
 
     # ------------------------------------------------------------------ forward
     def _gdesc(self, k=5):
-        rs = self.S if self.mode == 'tc' else 0
+        rs = self.S if self.mode in ('tc', 'tc32') else 0
         if self.game_type == L.GAME_GO:
             return L.GameDesc(self.H, 1, self.A, self.AS, self.W, self.game_type, 0.0, 0, rs)
         return L.GameDesc(self.H, min(k, max(self.H, self.W)), self.A, self.AS, self.W, self.game_type, 0.0, 0, rs)
@@ -326,6 +385,19 @@ class NativeForward(object):
     def _trunk_and_heads(self, n, logp, value, stem_done=False):
         s = L.stream_ptr()
         lib = self.lib
+        if self.mode == 'tc32':
+            # conv2 (one K = 128 pass, split output) and conv3 (three products per tap, fp32 features), then the heads
+            l2, l3 = self.layers[1], self.layers[2]
+            L.check(lib.rz_net_conv3x3_tc2(L.ptr(self.bufs[0]), L.ptr(l2['w']), L.ptr(l2['b']), None, L.ptr(self.bufs[1]),
+                                           n, self.H, self.W, 128, int(l2['relu']), 2, 2 | 8, self.n_ctas, s),
+                    'rz_net_conv3x3_tc2')
+            L.check(lib.rz_net_conv3x3_tc2_head_ex(
+                L.ptr(self.bufs[1]), L.ptr(l3['w']), L.ptr(l3['b']), None, n, self.H, self.W, 128, int(l3['relu']),
+                16 | 32, self.w1x1_host.ctypes.data_as(C.c_void_p), self.b1x1_host.ctypes.data_as(C.c_void_p),
+                L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc2_head_ex')
+            L.check(lib.rz_net_heads_tc(C.byref(self.hdesc), L.ptr(self.feat), L.ptr(logp), L.ptr(value), n, s),
+                    'rz_net_heads_tc')
+            return
         if self.mode == 'tc':
             # ping-pong: the residual of a block is the buffer its second conv overwrites
             src, outs = self.act0, self.bufs
@@ -401,6 +473,8 @@ class NativeForward(object):
 
     def kernels_per_forward(self):
         """Kernel launches of one forward_boards call (for bench.py's gpu_launches)."""
+        if self.mode == 'tc32':
+            return 4                                        # stem, conv2, conv3 + 1x1 heads, FC heads
         n_conv = len(self.layers)
         fused = self.mode == 'tc' and self.stem is not None and self.fused_stem
         heads = 2 if (self.heads_tc and not self.fused_head) else 1   # [1x1 features +] FC heads
@@ -422,7 +496,7 @@ class NativeForward(object):
                                                L.ptr(st['b']), L.ptr(self.bufs[0]), n, int(st['relu']), 0,
                                                L.stream_ptr()), 'rz_net_stem_go_tc')
             stem_done = True
-        elif self.mode == 'tc' and self.stem is not None and self.fused_stem:
+        elif self.mode in ('tc', 'tc32') and self.stem is not None and self.fused_stem:
             st = self.stem
             L.check(self.lib.rz_net_stem_tc(C.byref(g), L.ptr(rows), L.ptr(meta), L.ptr(st['w']), L.ptr(st['b']),
                                             L.ptr(self.bufs[0]), n, int(st['relu']), 0, L.stream_ptr()),
@@ -455,7 +529,7 @@ class NativeForward(object):
                                                       L.ptr(self.bufs[0]), n, int(st['relu']), 0, L.stream_ptr()),
                     'rz_net_stem_go_tc_planes')
             stem_done = True
-        elif self.mode == 'tc' and self.stem is not None and self.fused_stem:
+        elif self.mode in ('tc', 'tc32') and self.stem is not None and self.fused_stem:
             # same kernel (and therefore bit-identical stem outputs) as forward_boards
             st = self.stem
             xc = x.contiguous()

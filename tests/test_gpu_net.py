@@ -81,19 +81,63 @@ def test_conv3x3_tc_matches_torch(n, h, cin, relu, res, rev):
     assert full[:, :, h:, :].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize('mode', ['tc32', 'f32'])
 @pytest.mark.parametrize('size', [3, 6])
-def test_stock_net_matches_reference_golden(size):
-    """PolicyValueNet through the fp32 CUDA path == the reference's outputs (1e-5)."""
+def test_stock_net_matches_reference_golden(size, mode):
+    """PolicyValueNet == the reference's own outputs (tests/golden/net_pvn_*.npz) within 1e-5: through the default
+    path -- the tensor cores at float32-level accuracy (mode 'tc32': bf16 high/low pairs, three products per
+    convolution) -- and through the fp32 CUDA-core path."""
     from rlzero_b200.games.gomoku.policy_value_net import NativeForward, PolicyValueNet
     z = np.load(os.path.join(HERE, 'golden', 'net_pvn_%d.npz' % size))
     net = PolicyValueNet(size)
     net.load_state_dict({k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('w_')})
     net.cuda().eval()
-    nf = NativeForward(net)
-    assert nf.mode == 'f32'
+    assert NativeForward(net).mode == 'tc32'           # the default for the reference's network
+    nf = NativeForward(net, mode=mode)
     logp, v = nf.forward_planes(z['x'])
     np.testing.assert_allclose(logp.cpu().numpy(), z['logp'], atol=1e-5, rtol=0)
     np.testing.assert_allclose(v.cpu().numpy().reshape(-1, 1), z['v'], atol=1e-5, rtol=0)
+
+
+@pytest.mark.parametrize('size,n,scale', [(15, 70, 1.0), (15, 300, 4.0), (15, 64, 30.0), (9, 5, 1.0), (6, 130, 2.0),
+                                          (3, 9, 1.0)])
+def test_stock_net_float32_accurate_tensor_core_path(size, n, scale):
+    """mode 'tc32' against PyTorch fp32 on the CPU (cuDNN would use TF32): action probabilities and values within 1e-5
+    (the north star's fp32 tolerance), also with the weights scaled up (trained-like logit ranges), and the same
+    numbers from bitboards as from planes; the search through the reference API runs on it."""
+    from rlzero_b200.games.gomoku import GomokuEnv
+    from rlzero_b200.games.gomoku.alphazero_agent import AlphaZeroAgent
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, PolicyValueNet
+    from rlzero_b200.mcts import AlphaZeroMCTS
+    torch.manual_seed(size)
+    net = PolicyValueNet(size)
+    with torch.no_grad():
+        for prm in net.parameters():
+            prm.mul_(scale ** 0.25)
+        if scale > 1.0:                      # trained-like heads: logits and value pre-activations spread out
+            net.act_fc1.weight.mul_(scale)
+            net.val_fc2.weight.mul_(scale)
+    ref = PolicyValueNet(size).eval()
+    ref.load_state_dict(net.state_dict())
+    net.cuda().eval()
+    nf = NativeForward(net, max_batch=n)
+    assert nf.mode == 'tc32' and nf.kernels_per_forward() == 4
+    x = _random_boards(n, size, 9)
+    logp, v = (t.cpu() for t in nf.forward_planes(x))
+    with torch.no_grad():
+        lt, vt = ref(torch.from_numpy(x))
+    p_err = (logp.exp() - lt.exp()).abs().max().item()
+    v_err = (v - vt.reshape(-1)).abs().max().item()
+    l_err = (logp - lt).abs().max().item()
+    print('tc32 %dx%d n=%d scale %.1f: max |dp| %.2e  |dv| %.2e  |dlogp| %.2e (logp range %.2f)' % (
+        size, size, n, scale, p_err, v_err, l_err, float(lt.max() - lt.min())))
+    assert p_err < 1e-5 and v_err < 1e-5 and l_err < (1e-5 if scale == 1.0 else 1e-4)
+    if scale == 1.0:
+        agent = AlphaZeroAgent(size, net=net)
+        env = GomokuEnv(size, min(5, size))
+        env.reset()
+        acts, probs = AlphaZeroMCTS(agent.policy_value_fn, n_playout=40).simulate(env, 1.0)
+        assert len(acts) == size * size and abs(probs.sum() - 1.0) < 1e-9
 
 
 def _random_boards(n, size, seed):
@@ -532,7 +576,7 @@ def test_stock_net_on_the_tensor_core_path(size, n):
     net = PolicyValueNet(size).cuda().eval()
     nf = NativeForward(net, max_batch=n, mode='tc')
     assert nf.mode == 'tc' and all(l['cout'] == 128 for l in nf.layers)
-    assert NativeForward(net, max_batch=1).mode == 'f32'        # the default for this network stays fp32
+    assert NativeForward(net, max_batch=1).mode == 'tc32'       # the default: float32-accurate tensor-core path
     x = _random_boards(n, size, 9)
     logp, v = (t.cpu() for t in nf.forward_planes(x))
     ref = PolicyValueNet(size).eval()

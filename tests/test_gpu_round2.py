@@ -272,17 +272,20 @@ def test_one_graph_serves_every_seed():
 
 
 def test_rollout_streams_differ_between_moves():
-    """RolloutPlayer used the same random numbers for playout #v of every move and game."""
+    """RolloutPlayer used the same random numbers for playout #v of every move and game.  The same
+    position searched repeatedly by one player must not replay the same playouts: on 3x3 a random playout ends in a
+    tie (0) or a win (-1 by the reference's literal rule), so the value sums tell the streams apart."""
     from rlzero_b200.games.gomoku import GomokuEnv
     from rlzero_b200.mcts import RolloutPlayer
-    env = GomokuEnv(6, 4)
+    env = GomokuEnv(3, 3)
     env.reset()
-    p = RolloutPlayer(n_playout=64, seed=9)
-    moves = []
+    p = RolloutPlayer(n_playout=40, seed=9)
+    seen = set()
     for _ in range(6):
-        env.reset()
-        moves.append(p.get_action(env))
-    assert len(set(moves)) > 1                      # same position, same player: the searches are not replays
+        p.mcts.simulate(env)
+        seen.add(tuple(p.mcts._forest.root_stats()[1][0].tolist()))
+        p.reset_player()
+    assert len(seen) > 1
 
 
 # ------------------------------------------------------------------ the reference's own training script
