@@ -352,6 +352,52 @@ int rz_augment_equi(const rz_game_desc* g, const uint32_t* rows, const int32_t* 
    (random.sample(self.data_buffer, batch_size), tools/train_alphazero.py:94). */
 int rz_gather_rows(const float* src, const long long* index, float* dst, int n, int width, void* stream);
 
+/* ---- the training step: AlphaZeroAgent.learn (rlzero/games/gomoku/alphazero_agent.py:59-86), SURVEY 8 f1 ----------
+   Hand-written forward-with-saved-activations / analytic backward / loss / Adam in float32 (rz_learn.cu): no autograd,
+   no cuDNN, no cuBLAS; every batch reduction in a fixed order (deterministic).  Activations are channels-last
+   [n][HW][C] float32 (the layout of rz_net_conv3x3_f32, which is the forward convolution and -- with the weights
+   rz_learn_pack_conv writes -- the data gradient); parameter gradients come out in the state_dict layouts.  The host
+   mirror is rlzero_b200/learn.py::NativeTrainer; the oracle is oracle/train_oracle.py. */
+/* C[M][N] = alpha * sum_k A(m,k) B(k,n) (+ C if accumulate); A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]: every
+   fully connected layer and its two gradients (nn.Linear, policy_value_net.py:20,24,25) */
+int rz_learn_sgemm(int M, int N, int K, const float* A, long long sam, long long sak, const float* B, long long sbk,
+                   long long sbn, float* C, long long ldc, float alpha, int accumulate, void* stream);
+/* out[c] = alpha * sum_r in[r*ld + c] (bias gradients); scratch: n_slices * cols floats */
+int rz_learn_colsum(const float* in, long long rows, int cols, long long ld, float* out, float alpha, float* scratch,
+                    int n_slices, void* stream);
+/* nn.Conv2d weight [cout][cin][3][3] -> w_fwd [tap][cin][cout] (rz_net_conv3x3_f32's layout) and w_bwd
+   [8-tap][cout][cin]: rz_net_conv3x3_f32(dz, w_bwd, zero bias, ..., c_in = cout, c_out = cin) is the data gradient.
+   Either output may be NULL. */
+int rz_learn_pack_conv(const float* w_oihw, float* w_fwd, float* w_bwd, int c_in, int c_out, void* stream);
+/* grad[i] = act[i] > 0 ? grad[i] : 0  (F.relu backward) */
+int rz_learn_relu_bwd(const float* act, float* grad, long long n, void* stream);
+/* [n][C][HW] -> [n][HW][C] */
+int rz_learn_nchw_to_nhwc(const float* in, float* out, int n, int channels, int hw, void* stream);
+/* dw [cout][cin][3][3] = sum over boards and squares of x (shifted by the tap) * dz, db [cout] = sum dz; x [n][HW][cin],
+   dz [n][HW][cout]; c_in <= 64, c_out <= 128; scratch: 96 * 9 * c_in * c_out floats */
+int rz_learn_conv_wgrad(const float* x, const float* dz, float* dw_oihw, float* db, float* scratch,
+                        long long scratch_floats, int n_boards, int board_size, int c_in, int c_out, void* stream);
+/* feat [n][6][HW] = relu(act_conv1 / val_conv1 (a3)) (policy_value_net.py:41,47); a3 [n][HW][128], w1x1 [6][128] */
+int rz_learn_head_feat_fwd(const float* a3, const float* w1x1, const float* b1x1, float* feat, int n_boards, int hw,
+                           void* stream);
+/* logits[b][:] <- log_softmax(logits[b][:n_actions] + bias) in place, 0 in the padding (policy_value_net.py:43-44) */
+int rz_learn_logsoftmax(float* logits, const float* bias, int n, int n_actions, int action_stride, void* stream);
+/* h [n][64] <- relu(h + bv1) in place; v[b] = tanh(h[b] . wv2 + bv2) (policy_value_net.py:49-51) */
+int rz_learn_value_fwd(float* h, const float* bv1, const float* wv2, const float* bv2, float* v, int n, void* stream);
+/* loss and the gradients at the outputs (alphazero_agent.py:70-75,83-85): dlogits [n][AS] = (softmax * sum(pi) - pi) / n,
+   dpre2 [n] = 2 (v - z) / n * (1 - v^2), dh [n][64] = dpre2 * wv2 * (h > 0); loss3 = (mse(v, z), -mean sum pi log p,
+   -mean sum p log p).  terms: [n][3] scratch, scratch: 24 floats */
+int rz_learn_loss_bwd(const float* logp, const float* pi, int pi_stride, const float* v, const float* z, const float* h,
+                      const float* wv2, float* dlogits, float* dpre2, float* dh, float* terms, float* loss3,
+                      float* scratch, int n, int n_actions, int action_stride, void* stream);
+/* backward of the two 1x1 head convolutions: da3 [n][HW][128] = dfeat . w1x1, dw1x1 [6][128], db1x1 [6]; dfeat
+   [n][6][HW] must already carry the ReLU mask; scratch: (ceil(n*HW/64) + 64) * 774 floats */
+int rz_learn_head_feat_bwd(const float* dfeat, const float* a3, const float* w1x1, float* da3, float* dw1x1, float* db1x1,
+                           float* scratch, long long scratch_floats, int n_boards, int hw, void* stream);
+/* torch.optim.Adam on one flat buffer (L2 weight decay folded into the gradient, bias-corrected moments); step >= 1 */
+int rz_learn_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* ---- pure-MCTS opponent: random playouts (rlzero/mcts/rollout_mcts.py:49-74,96-108) ---------
    prior: uniform over the leaf's legal moves; value: the reference's _evaluate on a uniformly random
    playout from the leaf (at most n_limit plies; literal winner == current_player() rule, i.e. -1 for

@@ -117,6 +117,21 @@ SIGNATURES = {
     'rz_eval_closed_form': (C.c_int, [_TD, C.c_int, _vp, _vp, _vp]),
     'rz_augment_equi': (C.c_int, [_GD, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     'rz_gather_rows': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rz_learn_sgemm': (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.c_longlong, C.c_longlong, _vp, C.c_longlong,
+                                 C.c_longlong, _vp, C.c_longlong, C.c_float, C.c_int, _vp]),
+    'rz_learn_colsum': (C.c_int, [_vp, C.c_longlong, C.c_int, C.c_longlong, _vp, C.c_float, _vp, C.c_int, _vp]),
+    'rz_learn_pack_conv': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rz_learn_relu_bwd': (C.c_int, [_vp, _vp, C.c_longlong, _vp]),
+    'rz_learn_nchw_to_nhwc': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_learn_conv_wgrad': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_learn_head_feat_fwd': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rz_learn_logsoftmax': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_learn_value_fwd': (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    'rz_learn_loss_bwd': (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int,
+                                    C.c_int, C.c_int, _vp]),
+    'rz_learn_head_feat_bwd': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_int, _vp]),
+    'rz_learn_adam': (C.c_int, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_float, C.c_int, _vp]),
     'rz_eval_rollout': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),
     'rz_eval_rollout_dm': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),
     'rz_sizeof_mz_desc': (C.c_int, []),

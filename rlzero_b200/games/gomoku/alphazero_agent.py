@@ -3,9 +3,11 @@
 Inference (``policy_value_fn``, ``policy_value``, ``predict``) runs on the hand-written CUDA
 forward (``NativeForward``); ``policy_value_fn`` additionally carries a ``device_evaluator`` so
 that ``AlphaZeroMCTS`` evaluates whole waves of leaves on the device without the per-leaf
-host round trip the reference makes (alphazero_agent.py:41-45).  ``learn`` is the reference's
-training step in plain PyTorch (the training side is outside this round's hot path); the packed
-inference weights are refreshed after every step.
+host round trip the reference makes (alphazero_agent.py:41-45).  ``learn`` (:59-86) runs on the
+hand-written training kernels (``rlzero_b200.learn.NativeTrainer``: forward with saved activations,
+analytic backward, loss / entropy, Adam -- no autograd, cuDNN or cuBLAS) for the reference's own
+``PolicyValueNet``; ``learn_autograd`` is the same step in plain PyTorch, kept as the checker and for
+other modules.  The packed inference weights are refreshed after every step.
 """
 import os
 
@@ -14,6 +16,7 @@ import torch
 import torch.nn.functional as F
 import torch.optim as optim
 
+from ...learn import NativeTrainer
 from .policy_value_net import NativeForward, PolicyValueNet
 
 
@@ -39,13 +42,24 @@ class _PolicyValueFn(object):
 class AlphaZeroAgent(object):
 
     def __init__(self, board_size, learning_rate=0.001, weight_decay=1e-4, device='cuda',
-                 net=None, mode=None):
+                 net=None, mode=None, trainer=None):
+        """``trainer``: 'native' (hand-written kernels; the default for the reference's PolicyValueNet) or
+        'autograd' (plain PyTorch; the default for any other module)."""
         self.board_size = board_size
         self.policy_value_net = net if net is not None else PolicyValueNet(board_size)
         self.policy_value_net.to(device)
         self.optimizer = optim.Adam(self.policy_value_net.parameters(), lr=learning_rate,
                                     weight_decay=weight_decay)
         self.device = device
+        if trainer is None:
+            trainer = 'native' if type(self.policy_value_net) is PolicyValueNet else 'autograd'
+        if trainer not in ('native', 'autograd'):
+            raise ValueError("trainer must be 'native' or 'autograd'")
+        self.trainer = None
+        if trainer == 'native':
+            # re-points the module's parameters at one flat device buffer (state_dict / optimizer see the same tensors)
+            self.trainer = NativeTrainer(self.policy_value_net, learning_rate=learning_rate, weight_decay=weight_decay,
+                                         device=device)
         self.native = NativeForward(self.policy_value_net, mode=mode, device=device)
         self.policy_value_fn = _PolicyValueFn(self)
 
@@ -71,6 +85,14 @@ class AlphaZeroAgent(object):
 
     def learn(self, state_batch, mcts_probs, target_vs):
         """perform a training step: loss = (z - v)^2 - pi^T log p (+ L2 in the optimizer) (:59-86)."""
+        if self.trainer is None:
+            return self.learn_autograd(state_batch, mcts_probs, target_vs)
+        loss, entropy = self.trainer.learn(self._f32(state_batch), self._f32(mcts_probs), self._f32(target_vs))
+        self.native.refresh_weights()
+        return loss, entropy
+
+    def learn_autograd(self, state_batch, mcts_probs, target_vs):
+        """The same step through PyTorch autograd (the checker of the native trainer; other network modules)."""
         net = self.policy_value_net
         net.train()
         dev = self.device
@@ -94,7 +116,8 @@ class AlphaZeroAgent(object):
         if not os.path.exists(save_dir):
             os.mkdir(save_dir)
         torch.save(self.policy_value_net.state_dict(), os.path.join(save_dir, model_name))
-        torch.save(self.optimizer.state_dict(), os.path.join(save_dir, opt_name))
+        opt_state = self.trainer.optimizer_state_dict() if self.trainer is not None else self.optimizer.state_dict()
+        torch.save(opt_state, os.path.join(save_dir, opt_name))
         print('save model successfully!')
 
     def restore(self, save_dir, model_name='model.th', opt_name='optimizer.th'):
@@ -102,6 +125,11 @@ class AlphaZeroAgent(object):
         if not os.path.exists(save_dir):
             os.mkdir(save_dir)
         self.policy_value_net.load_state_dict(torch.load(os.path.join(save_dir, model_name)))
-        self.optimizer.load_state_dict(torch.load(os.path.join(save_dir, opt_name)))
+        opt_state = torch.load(os.path.join(save_dir, opt_name))
+        if self.trainer is not None:
+            self.trainer.load_optimizer_state_dict(opt_state)
+            self.trainer.weights_changed()
+        else:
+            self.optimizer.load_state_dict(opt_state)
         self.native.refresh_weights()
         print('restore model successfully!')

@@ -1,0 +1,240 @@
+"""``NativeTrainer``: the training step of ``AlphaZeroAgent.learn``
+(rlzero/games/gomoku/alphazero_agent.py:59-86) on the hand-written kernels of ``csrc/rz_learn.cu``.
+
+    forward (activations saved) -> loss / entropy -> analytic backward -> Adam(weight_decay)
+
+for the reference's own ``PolicyValueNet`` (policy_value_net.py:6-52) in float32: no autograd, no
+cuDNN, no cuBLAS on the path.  The module stays the parameter container -- its parameters are re-pointed
+at slices of ONE flat device buffer, so ``state_dict()``, ``save_model`` / ``restore`` and the inference
+path's ``refresh_weights`` see every update, and Adam is a single launch over the flat buffer.  Gradients
+and both Adam moments are flat buffers with the same offsets; ``optimizer_state_dict()`` hands them out in
+``torch.optim.Adam``'s format (alphazero_agent.py:104-111 saves exactly that).
+
+PyTorch is used for device memory only.  The checker is ``oracle/train_oracle.py`` (numpy float64, pinned
+to autograd and to the live reference agent): ``tests/test_gpu_learn.py``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+class NativeTrainer(object):
+
+    def __init__(self, module, learning_rate=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, device='cuda'):
+        if not torch.cuda.is_available():
+            raise L.NativeLibraryError('NativeTrainer needs a CUDA device (no CPU fallback)')
+        self.lib = L.load()
+        self.module = module
+        self.device = torch.device(device)
+        self.H = int(module.board_size)
+        self.HW = self.H * self.H
+        self.A = self.HW
+        self.AS = (self.A + 31) // 32 * 32
+        self.lr, self.wd, self.betas, self.eps = float(learning_rate), float(weight_decay), tuple(betas), float(eps)
+        self.step = 0
+        names = ['conv1', 'conv2', 'conv3', 'act_conv1', 'act_fc1', 'val_conv1', 'val_fc1', 'val_fc2']
+        for n in names:
+            if not hasattr(module, n):
+                raise ValueError('NativeTrainer trains the reference PolicyValueNet (missing %s)' % n)
+        self.chan = [(module.conv1.in_channels, module.conv1.out_channels),
+                     (module.conv2.in_channels, module.conv2.out_channels),
+                     (module.conv3.in_channels, module.conv3.out_channels)]
+        if self.chan != [(4, 32), (32, 64), (64, 128)]:
+            raise ValueError('NativeTrainer trains the 4 -> 32 -> 64 -> 128 trunk of the reference')
+        # ---- one flat buffer for the parameters, in parameters() order (= torch.optim.Adam's param order)
+        params = list(module.parameters())
+        self.names = [n for n, _ in module.named_parameters()]
+        sizes = [p.numel() for p in params]
+        self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        n_total = int(self.offsets[-1])
+        f32 = torch.float32
+        self.flat = torch.empty(n_total, dtype=f32, device=self.device)
+        self.grad = torch.zeros(n_total, dtype=f32, device=self.device)
+        self.exp_avg = torch.zeros(n_total, dtype=f32, device=self.device)
+        self.exp_avg_sq = torch.zeros(n_total, dtype=f32, device=self.device)
+        for p, o in zip(params, self.offsets[:-1]):
+            view = self.flat[int(o):int(o) + p.numel()].view(p.shape)
+            view.copy_(p.data.to(self.device, f32))
+            p.data = view                                   # the module's tensors ARE the flat buffer from here on
+        self._views = {n: (self.flat[int(o):int(o) + s], self.grad[int(o):int(o) + s])
+                       for n, o, s in zip(self.names, self.offsets[:-1], sizes)}
+        self._shapes = {n: tuple(p.shape) for n, p in zip(self.names, params)}
+        # packed convolution weights (forward and data-gradient layouts), refreshed after every update
+        self.wf = [torch.empty(9 * ci * co, dtype=f32, device=self.device) for ci, co in self.chan]
+        self.wb = [torch.empty(9 * ci * co, dtype=f32, device=self.device) for ci, co in self.chan]
+        self.zero_bias = torch.zeros(128, dtype=f32, device=self.device)
+        self.B = 0
+        self._repack()
+
+    # ------------------------------------------------------------------ plumbing
+    def _p(self, name):
+        return self._views[name][0]
+
+    def _g(self, name):
+        return self._views[name][1]
+
+    def _repack(self):
+        s = L.stream_ptr()
+        for i, (ci, co) in enumerate(self.chan):
+            L.check(self.lib.rz_learn_pack_conv(L.ptr(self._p('conv%d.weight' % (i + 1))), L.ptr(self.wf[i]),
+                                                L.ptr(self.wb[i]), ci, co, s), 'rz_learn_pack_conv')
+
+    def _alloc(self, B):
+        if B == self.B:
+            return
+        dev, f32, HW, AS = self.device, torch.float32, self.HW, self.AS
+        self.B = B
+        z = lambda *shape: torch.zeros(*shape, dtype=f32, device=dev)
+        self.x = z(B, HW, 4)
+        self.a = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]
+        self.d = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]     # gradients at the activations
+        self.feat, self.dfeat = z(B, 6, HW), z(B, 6, HW)
+        self.logp, self.dlogits = z(B, AS), z(B, AS)
+        self.h, self.dh = z(B, 64), z(B, 64)
+        self.v, self.dpre2 = z(B), z(B)
+        self.terms, self.loss3 = z(B, 3), z(3)
+        self.pi, self.z = z(B, self.A), z(B)
+        rows = B * HW
+        n_scr = max(96 * 9 * 64 * 128, ((rows + 63) // 64 + 64) * 774, 96 * AS, 1024)
+        self.scratch = z(n_scr)
+
+    def _sgemm(self, M, N, K, A, sam, sak, Bm, sbk, sbn, Cm, ldc, alpha=1.0, accumulate=False):
+        L.check(self.lib.rz_learn_sgemm(M, N, K, L.ptr(A), sam, sak, L.ptr(Bm), sbk, sbn, L.ptr(Cm), ldc, float(alpha),
+                                        int(accumulate), L.stream_ptr()), 'rz_learn_sgemm')
+
+    def _colsum(self, t, rows, cols, ld, out, slices=32):
+        L.check(self.lib.rz_learn_colsum(L.ptr(t), rows, cols, ld, L.ptr(out), 1.0, L.ptr(self.scratch), slices,
+                                         L.stream_ptr()), 'rz_learn_colsum')
+
+    def _conv(self, inp, w, b, out, ci, co, relu):
+        L.check(self.lib.rz_net_conv3x3_f32(L.ptr(inp), L.ptr(w), L.ptr(b), None, L.ptr(out), self.B, self.H, ci, co,
+                                            int(relu), L.stream_ptr()), 'rz_net_conv3x3_f32')
+
+    # ------------------------------------------------------------------ the step
+    def forward(self, states):
+        """states [B,4,H,W] float32 device tensor -> (logp [B,AS], v [B]); activations are kept for backward()."""
+        B = int(states.shape[0])
+        self._alloc(B)
+        s = L.stream_ptr()
+        lib, HW, AS, A = self.lib, self.HW, self.AS, self.A
+        st = states.to(self.device, torch.float32).contiguous()
+        L.check(lib.rz_learn_nchw_to_nhwc(L.ptr(st), L.ptr(self.x), B, 4, HW, s), 'rz_learn_nchw_to_nhwc')
+        inp = self.x
+        for i, (ci, co) in enumerate(self.chan):
+            self._conv(inp, self.wf[i], self._p('conv%d.bias' % (i + 1)), self.a[i], ci, co, True)
+            inp = self.a[i]
+        # the two 1x1 head convolutions, stacked: rows 0..3 act_conv1, 4..5 val_conv1
+        w1 = torch.cat([self._p('act_conv1.weight'), self._p('val_conv1.weight')])
+        b1 = torch.cat([self._p('act_conv1.bias'), self._p('val_conv1.bias')])
+        self._w1x1 = w1
+        L.check(lib.rz_learn_head_feat_fwd(L.ptr(self.a[2]), L.ptr(w1), L.ptr(b1), L.ptr(self.feat), B, HW, s),
+                'rz_learn_head_feat_fwd')
+        # logits = pf . Wp^T (pf = feat[b][0:4HW]), log_softmax
+        self._sgemm(B, A, 4 * HW, self.feat, 6 * HW, 1, self._p('act_fc1.weight'), 1, 4 * HW, self.logp, AS)
+        L.check(lib.rz_learn_logsoftmax(L.ptr(self.logp), L.ptr(self._p('act_fc1.bias')), B, A, AS, s),
+                'rz_learn_logsoftmax')
+        # hidden = relu(vf . Wv1^T + bv1) (vf = feat[b][4HW:6HW]), v = tanh(h . wv2 + bv2)
+        vf = self.feat.view(-1)[4 * HW:]
+        self._sgemm(B, 64, 2 * HW, vf, 6 * HW, 1, self._p('val_fc1.weight'), 1, 2 * HW, self.h, 64)
+        L.check(lib.rz_learn_value_fwd(L.ptr(self.h), L.ptr(self._p('val_fc1.bias')), L.ptr(self._p('val_fc2.weight')),
+                                       L.ptr(self._p('val_fc2.bias')), L.ptr(self.v), B, s), 'rz_learn_value_fwd')
+        return self.logp, self.v
+
+    def backward(self, mcts_probs, target_vs):
+        """Loss, entropy and every parameter gradient (into ``self.grad``) for the batch of the last forward()."""
+        B, HW, AS, A = self.B, self.HW, self.AS, self.A
+        lib, s = self.lib, L.stream_ptr()
+        self.pi.copy_(mcts_probs.to(self.device, torch.float32).reshape(B, -1)[:, :A])
+        self.z.copy_(target_vs.to(self.device, torch.float32).reshape(B))
+        L.check(lib.rz_learn_loss_bwd(L.ptr(self.logp), L.ptr(self.pi), A, L.ptr(self.v), L.ptr(self.z), L.ptr(self.h),
+                                      L.ptr(self._p('val_fc2.weight')), L.ptr(self.dlogits), L.ptr(self.dpre2),
+                                      L.ptr(self.dh), L.ptr(self.terms), L.ptr(self.loss3), L.ptr(self.scratch), B, A, AS,
+                                      s), 'rz_learn_loss_bwd')
+        vf = self.feat.view(-1)[4 * HW:]
+        # value head: val_fc2 (weight [1][64], bias [1]), val_fc1 (weight [64][2HW])
+        self._sgemm(1, 64, B, self.dpre2, 0, 1, self.h, 64, 1, self._g('val_fc2.weight'), 64)
+        self._colsum(self.dpre2, B, 1, 1, self._g('val_fc2.bias'))
+        self._sgemm(64, 2 * HW, B, self.dh, 1, 64, vf, 6 * HW, 1, self._g('val_fc1.weight'), 2 * HW)
+        self._colsum(self.dh, B, 64, 64, self._g('val_fc1.bias'))
+        # policy head: act_fc1 (weight [A][4HW])
+        self._sgemm(A, 4 * HW, B, self.dlogits, 1, AS, self.feat, 6 * HW, 1, self._g('act_fc1.weight'), 4 * HW)
+        self._colsum(self.dlogits, B, A, AS, self._g('act_fc1.bias'))
+        # gradients at the head features: dpf = dlogits . Wp, dvf = dh . Wv1, then the ReLU mask of the 1x1 convolutions
+        self._sgemm(B, 4 * HW, A, self.dlogits, AS, 1, self._p('act_fc1.weight'), 4 * HW, 1, self.dfeat, 6 * HW)
+        dvf = self.dfeat.view(-1)[4 * HW:]
+        self._sgemm(B, 2 * HW, 64, self.dh, 64, 1, self._p('val_fc1.weight'), 2 * HW, 1, dvf, 6 * HW)
+        L.check(lib.rz_learn_relu_bwd(L.ptr(self.feat), L.ptr(self.dfeat), B * 6 * HW, s), 'rz_learn_relu_bwd')
+        dw1 = torch.empty(6 * 128, dtype=torch.float32, device=self.device)
+        db1 = torch.empty(6, dtype=torch.float32, device=self.device)
+        L.check(lib.rz_learn_head_feat_bwd(L.ptr(self.dfeat), L.ptr(self.a[2]), L.ptr(self._w1x1), L.ptr(self.d[2]),
+                                           L.ptr(dw1), L.ptr(db1), L.ptr(self.scratch), self.scratch.numel(), B, HW, s),
+                'rz_learn_head_feat_bwd')
+        self._g('act_conv1.weight').copy_(dw1[:4 * 128])
+        self._g('val_conv1.weight').copy_(dw1[4 * 128:])
+        self._g('act_conv1.bias').copy_(db1[:4])
+        self._g('val_conv1.bias').copy_(db1[4:])
+        # trunk, last layer first: ReLU mask, weight/bias gradient, data gradient
+        inputs = [self.x, self.a[0], self.a[1]]
+        for i in (2, 1, 0):
+            ci, co = self.chan[i]
+            L.check(lib.rz_learn_relu_bwd(L.ptr(self.a[i]), L.ptr(self.d[i]), B * HW * co, s), 'rz_learn_relu_bwd')
+            L.check(lib.rz_learn_conv_wgrad(L.ptr(inputs[i]), L.ptr(self.d[i]), L.ptr(self._g('conv%d.weight' % (i + 1))),
+                                            L.ptr(self._g('conv%d.bias' % (i + 1))), L.ptr(self.scratch),
+                                            self.scratch.numel(), B, self.H, ci, co, s), 'rz_learn_conv_wgrad')
+            if i > 0:
+                self._conv(self.d[i], self.wb[i], self.zero_bias, self.d[i - 1], co, ci, False)
+        return self.loss3
+
+    def adam_step(self):
+        self.step += 1
+        L.check(self.lib.rz_learn_adam(L.ptr(self.flat), L.ptr(self.grad), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                                       self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                                       self.step, L.stream_ptr()), 'rz_learn_adam')
+        self._repack()
+
+    def learn(self, state_batch, mcts_probs, target_vs):
+        """One training step; returns (loss, entropy) as Python floats (alphazero_agent.py:86)."""
+        self.forward(state_batch)
+        loss3 = self.backward(mcts_probs, target_vs)
+        self.adam_step()
+        vl, pl, ent = loss3.tolist()          # the one device -> host read of the step
+        return vl + pl, ent
+
+    # ------------------------------------------------------------------ views for callers and tests
+    def grads(self):
+        """{parameter name: gradient tensor in the state_dict's shape} (views of the flat gradient buffer)."""
+        return {n: self._g(n).view(self._shapes[n]) for n in self.names}
+
+    def optimizer_state_dict(self):
+        """``torch.optim.Adam.state_dict()`` format (alphazero_agent.py:108-111 saves it)."""
+        state = {}
+        for i, n in enumerate(self.names):
+            o, e = int(self.offsets[i]), int(self.offsets[i + 1])
+            if self.step > 0:
+                state[i] = {'step': torch.tensor(float(self.step)), 'exp_avg': self.exp_avg[o:e].view(self._shapes[n]).clone(),
+                            'exp_avg_sq': self.exp_avg_sq[o:e].view(self._shapes[n]).clone()}
+        group = {'lr': self.lr, 'betas': self.betas, 'eps': self.eps, 'weight_decay': self.wd, 'amsgrad': False,
+                 'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None,
+                 'params': list(range(len(self.names)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        g = sd['param_groups'][0]
+        self.lr, self.wd, self.eps = float(g['lr']), float(g['weight_decay']), float(g['eps'])
+        self.betas = tuple(g['betas'])
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step = 0
+        for i, st in sd['state'].items():
+            i = int(i)
+            o, e = int(self.offsets[i]), int(self.offsets[i + 1])
+            self.exp_avg[o:e].copy_(st['exp_avg'].reshape(-1))
+            self.exp_avg_sq[o:e].copy_(st['exp_avg_sq'].reshape(-1))
+            self.step = int(float(st['step']))
+
+    def weights_changed(self):
+        """Call after the module's parameters were written from outside (load_state_dict, a broadcast)."""
+        self._repack()
