@@ -533,6 +533,22 @@ def exchange_block(sp, net, world, rank, dist):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ag_ms = float(t.item())
     recv_bytes = rec_bytes * n_rec * (world - 1)       # what every GPU receives over NVLink
+    # the collective alone on a larger pre-packed payload (262144 records per rank): NVLink bandwidth, no pack / count
+    big = parallel.pack_records(rows, info, pi).repeat(8, 1)
+    recv = torch.empty(world * big.shape[0], big.shape[1], dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(recv, big)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    for _ in range(5):
+        dist.all_gather_into_tensor(recv, big)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    coll_ms = float(t.item())
+    coll_bytes = big.numel() * 4 * (world - 1)
+    del recv, big
     # -- weight broadcast + re-pack + graph re-capture
     dist.barrier()
     torch.cuda.synchronize()
@@ -580,6 +596,10 @@ def exchange_block(sp, net, world, rank, dist):
                                       'gb_per_s_per_gpu': recv_bytes / ag_ms / 1e6,
                                       'vs_nvlink_770_gb_s_measured_peer_copy': recv_bytes / ag_ms / 1e6 / 770.0,
                                       'payload_ok': ok_gather,
+                                      'collective_only': {'records_per_rank': 8 * n_rec, 'bytes_received_per_gpu': coll_bytes,
+                                                          'ms': coll_ms, 'gb_per_s_per_gpu': coll_bytes / coll_ms / 1e6,
+                                                          'vs_nvlink_770_gb_s_measured_peer_copy':
+                                                              coll_bytes / coll_ms / 1e6 / 770.0},
                                       'how': 'pack + NCCL all_gather_into_tensor + unpack of device tensors, CUDA '
                                              'events, max over ranks (includes the 8-byte count collective)'},
             'weight_broadcast': {'bytes': moved, 'ms': float(t[0].item()),

@@ -106,7 +106,10 @@ def test_native_step_equals_the_autograd_step():
         lb, eb = b.learn(x, pi, z)
         assert abs(la - lb) < 1e-5 and abs(ea - eb) < 1e-5
     for (k, ta), (_, tb) in zip(a.policy_value_net.state_dict().items(), b.policy_value_net.state_dict().items()):
-        assert (ta - tb).abs().max().item() < 5e-5, k
+        d = (ta - tb).abs().flatten().float()
+        # two float32 implementations: Adam turns rounding noise on near-zero gradient components into steps of up to
+        # a learning rate (see test_adam_steps_match_the_oracle), everything else agrees to 1e-5
+        assert torch.quantile(d, 0.99).item() < 1e-5 and d.max().item() < 3.1e-3, k
     new_a, newv_a = a.policy_value(x)
     new_b, newv_b = b.policy_value(x)
     kl = lambda o, n: np.mean(np.sum(o * (np.log(o + 1e-10) - np.log(n + 1e-10)), axis=1))
