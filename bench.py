@@ -501,6 +501,60 @@ def config_block(args, peaks):
     return out
 
 
+# ------------------------------------------------------------------- the training step (N = 1)
+def train_block(peaks):
+    """AlphaZeroAgent.learn (alphazero_agent.py:59-86) on synthetic batches: the hand-written step (tensor-core trunk for
+    ResNet-10, float32 CUDA-core kernels for the reference's own network) next to the same step through PyTorch autograd
+    (cuDNN / cuBLAS, PyTorch's default TF32 convolutions) on the same GPU.  FLOPs per step = 3 x forward (forward, data
+    gradient, weight gradient); frac = achieved / the measured sustained bf16 peak."""
+    import numpy as np
+    import torch
+    from rlzero_b200.games.gomoku.alphazero_agent import AlphaZeroAgent
+    from rlzero_b200.games.gomoku.policy_value_net import PolicyValueNet, ResNetPolicyValueNet
+    sustained = peaks.get('bf16_tflops_sustained') or 1400.0
+    out = []
+    rs = np.random.RandomState(0)
+
+    def stock_flops(H):
+        hw = H * H
+        return 2 * hw * 9 * (4 * 32 + 32 * 64 + 64 * 128) + 2 * hw * 128 * 6 + 2 * 4 * hw * hw + 2 * 2 * hw * 64 + 128
+
+    for name, make, B, flops, steps in (
+            ('ResNet-10/128ch 15x15, batch 4096', lambda: ResNetPolicyValueNet(15, n_blocks=10), 4096, None, 6),
+            ('stock PolicyValueNet 15x15, batch 512', lambda: PolicyValueNet(15), 512, stock_flops(15), 10)):
+        x = torch.from_numpy((rs.rand(B, 4, 15, 15) < 0.2).astype(np.float32)).cuda()
+        pi = torch.from_numpy(rs.dirichlet(0.3 * np.ones(225), size=B).astype(np.float32)).cuda()
+        z = torch.from_numpy(rs.choice([-1.0, 0.0, 1.0], size=B).astype(np.float32)).cuda()
+        entry = {'step': 'AlphaZeroAgent.learn, ' + name}
+        for kind in ('native', 'autograd'):
+            torch.manual_seed(0)
+            net = make()
+            agent = AlphaZeroAgent(15, net=net, trainer=kind)
+            if flops is None:
+                flops = net.flops_per_eval()
+            for _ in range(2):
+                agent.learn(x, pi, z)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss, ent = agent.learn(x, pi, z)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            tf = 3.0 * flops * B / ms / 1e9
+            entry[kind] = {'ms_per_step': ms, 'steps_per_s': 1e3 / ms, 'samples_per_s': B * 1e3 / ms, 'tflops': tf,
+                           'frac_of_sustained_bf16_peak': tf / sustained, 'loss_after': loss,
+                           'path': ('hand-written kernels (%s)' % type(agent.trainer).__name__) if agent.trainer is not None
+                           else 'PyTorch autograd, cuDNN/cuBLAS, fp32 tensors with TF32 convolutions (PyTorch default)'}
+            del agent, net
+            torch.cuda.empty_cache()
+        entry['speedup_vs_autograd'] = entry['autograd']['ms_per_step'] / entry['native']['ms_per_step']
+        entry['includes'] = 'forward, loss, backward, Adam, and the re-pack of the inference weights (refresh_weights)'
+        out.append(entry)
+    return out
+
+
 # ------------------------------------------------------------------- off-path exchange (N > 1)
 def exchange_block(sp, net, world, rank, dist):
     """The two collectives of a generation, off the search path, on NCCL: all-gather of compact trajectory records
@@ -766,6 +820,7 @@ def run_b200(args):
         torch.cuda.empty_cache()
         if world == 1 and not args.no_configs:
             line['configs'] = config_block(args, peaks)
+            line['train'] = train_block(peaks)
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline('config3', args.cpu_seconds, args.blocks, P)
             # the same CPU search with the reference's own stock network as evaluator, a shorter sample

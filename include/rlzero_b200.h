@@ -398,6 +398,38 @@ int rz_learn_head_feat_bwd(const float* dfeat, const float* a3, const float* w1x
 int rz_learn_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* ---- the same step for the 128-channel ResNet trunk on the tensor cores (rz_learn_tc.cu) -------------------------
+   bf16 activations / gradients in the padded 16-stride layout [n*256][128] of the inference path (boards up to 15x15),
+   fp32 statistics and parameter gradients.  Forward convolution and data gradient are rz_net_conv3x3_tc2 (the latter
+   with w_bwd below); the heads run through the float32 kernels above after rz_learn_tile_to_nhwc. */
+/* dw [128][128][3][3] fp32 = sum over positions of dy[p][co] * x[p + d(tap)][ci]: tcgen05 GEMM with MN-major operands
+   (the reduction index is the tile row), accumulators in TMEM for the whole launch, CTA triples (one per filter row)
+   sharing position tiles through L2.  x, dy: bf16 [n*256][128] with zero pad squares.  scratch: 49 * 9 * 128 * 128
+   floats (per-split partials, folded in a fixed order).  n_ctas <= 0 picks 147. */
+int rz_learn_conv_wgrad_tc(const void* x, const void* dy, float* dw_oihw, float* scratch, long long scratch_floats,
+                           int n_boards, int n_ctas, void* stream);
+/* nn.Conv2d weight fp32 [128][128][3][3] -> bf16 w_fwd [tap][cout][cin] (rz_net_conv3x3_tc2's layout) and w_bwd
+   [8-tap][cin][cout]: rz_net_conv3x3_tc2(dy, w_bwd, zero bias, residual = skip gradient, ...) is the data gradient */
+int rz_learn_pack_conv_tc(const float* w_oihw, void* w_fwd, void* w_bwd, void* stream);
+/* stem weight fp32 [128][4][3][3] -> bf16 [128][64] (k = tap*4 + plane, rz_net_stem_tc's layout) */
+int rz_learn_pack_stem_tc(const float* w_oihw, void* w_stem, void* stream);
+/* nn.BatchNorm2d in training mode + skip + ReLU: batch statistics of y over the board squares (biased variance),
+   running_mean / running_var updated (momentum, unbiased variance; may be NULL), out = relu((y - mean) * invstd *
+   gamma + beta (+ skip)), zero off the board.  stats [4][128] receives mean, invstd, gamma * invstd, beta - mean *
+   gamma * invstd (kept for the backward pass).  scratch: 148 * 4 * 256 + 256 floats. */
+int rz_learn_bn_forward(const void* y, const void* skip, void* out, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, float eps, float momentum, float* stats, float* scratch,
+                        int n_boards, int board_rows, int board_cols, void* stream);
+/* its backward pass: dz = dout * (act > 0); dgamma = sum dz * xhat, dbeta = sum dz; dy = gamma * invstd * (dz - dbeta / N -
+   xhat * dgamma / N) (bf16, zero off the board); dz_out (may be NULL) receives dz, the gradient into the skip */
+int rz_learn_bn_backward(const void* dout, const void* act, const void* y, const float* stats, float* dgamma, float* dbeta,
+                         void* dy, void* dz_out, float* scratch, int n_boards, int board_rows, int board_cols, void* stream);
+/* grad = dout * (act > 0) on bf16 tiles (ReLU without BatchNorm: the stem) */
+int rz_learn_relu_bwd_bf16(const void* dout, const void* act, void* grad, int n_boards, void* stream);
+/* bf16 padded tile layout [n*256][128] <-> float32 [n][HW][128] */
+int rz_learn_tile_to_nhwc(const void* tile, float* out, int n_boards, int board_rows, int board_cols, void* stream);
+int rz_learn_nhwc_to_tile(const float* in, void* tile, int n_boards, int board_rows, int board_cols, void* stream);
+
 /* ---- pure-MCTS opponent: random playouts (rlzero/mcts/rollout_mcts.py:49-74,96-108) ---------
    prior: uniform over the leaf's legal moves; value: the reference's _evaluate on a uniformly random
    playout from the leaf (at most n_limit plies; literal winner == current_player() rule, i.e. -1 for

@@ -132,6 +132,15 @@ SIGNATURES = {
     'rz_learn_head_feat_bwd': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_int, _vp]),
     'rz_learn_adam': (C.c_int, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_int, _vp]),
+    'rz_learn_conv_wgrad_tc': (C.c_int, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_int, _vp]),
+    'rz_learn_pack_conv_tc': (C.c_int, [_vp, _vp, _vp, _vp]),
+    'rz_learn_pack_stem_tc': (C.c_int, [_vp, _vp, _vp]),
+    'rz_learn_bn_forward': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, C.c_int, C.c_int,
+                                      C.c_int, _vp]),
+    'rz_learn_bn_backward': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_learn_relu_bwd_bf16': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    'rz_learn_tile_to_nhwc': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_learn_nhwc_to_tile': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_eval_rollout': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),
     'rz_eval_rollout_dm': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),
     'rz_sizeof_mz_desc': (C.c_int, []),

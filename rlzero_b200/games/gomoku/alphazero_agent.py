@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 import torch.optim as optim
 
-from ...learn import NativeTrainer
+from ...learn import make_trainer
 from .policy_value_net import NativeForward, PolicyValueNet
 
 
@@ -43,23 +43,24 @@ class AlphaZeroAgent(object):
 
     def __init__(self, board_size, learning_rate=0.001, weight_decay=1e-4, device='cuda',
                  net=None, mode=None, trainer=None):
-        """``trainer``: 'native' (hand-written kernels; the default for the reference's PolicyValueNet) or
-        'autograd' (plain PyTorch; the default for any other module)."""
+        """``trainer``: 'native' (hand-written kernels: the float32 step for the reference's PolicyValueNet, the
+        tensor-core step for ResNetPolicyValueNet on square boards up to 15x15; the default where one fits) or
+        'autograd' (plain PyTorch: the checker, and any other module)."""
         self.board_size = board_size
         self.policy_value_net = net if net is not None else PolicyValueNet(board_size)
         self.policy_value_net.to(device)
         self.optimizer = optim.Adam(self.policy_value_net.parameters(), lr=learning_rate,
                                     weight_decay=weight_decay)
         self.device = device
-        if trainer is None:
-            trainer = 'native' if type(self.policy_value_net) is PolicyValueNet else 'autograd'
-        if trainer not in ('native', 'autograd'):
+        if trainer not in (None, 'native', 'autograd'):
             raise ValueError("trainer must be 'native' or 'autograd'")
         self.trainer = None
-        if trainer == 'native':
+        if trainer != 'autograd':
             # re-points the module's parameters at one flat device buffer (state_dict / optimizer see the same tensors)
-            self.trainer = NativeTrainer(self.policy_value_net, learning_rate=learning_rate, weight_decay=weight_decay,
-                                         device=device)
+            self.trainer = make_trainer(self.policy_value_net, learning_rate=learning_rate, weight_decay=weight_decay,
+                                        device=device)
+            if self.trainer is None and trainer == 'native':
+                raise ValueError('no native trainer fits this module (use trainer="autograd")')
         self.native = NativeForward(self.policy_value_net, mode=mode, device=device)
         self.policy_value_fn = _PolicyValueFn(self)
 

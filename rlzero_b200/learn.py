@@ -22,6 +22,9 @@ from . import _lib as L
 
 
 class NativeTrainer(object):
+    """The reference's PolicyValueNet (conv 4 -> 32 -> 64 -> 128, float32 on CUDA cores).  The heads, the loss, the
+    flat parameter buffers and Adam are shared with ``ResNetTrainer`` (tensor-core trunk) through the ``_trunk_*``
+    hooks."""
 
     def __init__(self, module, learning_rate=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, device='cuda'):
         if not torch.cuda.is_available():
@@ -35,15 +38,10 @@ class NativeTrainer(object):
         self.AS = (self.A + 31) // 32 * 32
         self.lr, self.wd, self.betas, self.eps = float(learning_rate), float(weight_decay), tuple(betas), float(eps)
         self.step = 0
-        names = ['conv1', 'conv2', 'conv3', 'act_conv1', 'act_fc1', 'val_conv1', 'val_fc1', 'val_fc2']
-        for n in names:
+        for n in ['act_conv1', 'act_fc1', 'val_conv1', 'val_fc1', 'val_fc2']:
             if not hasattr(module, n):
-                raise ValueError('NativeTrainer trains the reference PolicyValueNet (missing %s)' % n)
-        self.chan = [(module.conv1.in_channels, module.conv1.out_channels),
-                     (module.conv2.in_channels, module.conv2.out_channels),
-                     (module.conv3.in_channels, module.conv3.out_channels)]
-        if self.chan != [(4, 32), (32, 64), (64, 128)]:
-            raise ValueError('NativeTrainer trains the 4 -> 32 -> 64 -> 128 trunk of the reference')
+                raise ValueError('the native trainers need the reference heads (missing %s)' % n)
+        self._check_module(module)
         # ---- one flat buffer for the parameters, in parameters() order (= torch.optim.Adam's param order)
         params = list(module.parameters())
         self.names = [n for n, _ in module.named_parameters()]
@@ -62,12 +60,62 @@ class NativeTrainer(object):
         self._views = {n: (self.flat[int(o):int(o) + s], self.grad[int(o):int(o) + s])
                        for n, o, s in zip(self.names, self.offsets[:-1], sizes)}
         self._shapes = {n: tuple(p.shape) for n, p in zip(self.names, params)}
+        self.zero_bias = torch.zeros(128, dtype=f32, device=self.device)
+        self.B = 0
+        self._init_trunk()
+        self._repack()
+
+    # ------------------------------------------------------------------ the stock trunk (float32, CUDA cores)
+    def _check_module(self, module):
+        for n in ['conv1', 'conv2', 'conv3']:
+            if not hasattr(module, n):
+                raise ValueError('NativeTrainer trains the reference PolicyValueNet (missing %s)' % n)
+        self.chan = [(module.conv1.in_channels, module.conv1.out_channels),
+                     (module.conv2.in_channels, module.conv2.out_channels),
+                     (module.conv3.in_channels, module.conv3.out_channels)]
+        if self.chan != [(4, 32), (32, 64), (64, 128)]:
+            raise ValueError('NativeTrainer trains the 4 -> 32 -> 64 -> 128 trunk of the reference')
+
+    def _init_trunk(self):
+        f32 = torch.float32
         # packed convolution weights (forward and data-gradient layouts), refreshed after every update
         self.wf = [torch.empty(9 * ci * co, dtype=f32, device=self.device) for ci, co in self.chan]
         self.wb = [torch.empty(9 * ci * co, dtype=f32, device=self.device) for ci, co in self.chan]
-        self.zero_bias = torch.zeros(128, dtype=f32, device=self.device)
-        self.B = 0
-        self._repack()
+
+    def _repack(self):
+        s = L.stream_ptr()
+        for i, (ci, co) in enumerate(self.chan):
+            L.check(self.lib.rz_learn_pack_conv(L.ptr(self._p('conv%d.weight' % (i + 1))), L.ptr(self.wf[i]),
+                                                L.ptr(self.wb[i]), ci, co, s), 'rz_learn_pack_conv')
+
+    def _alloc_trunk(self, B):
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        HW = self.HW
+        self.x = z(B, HW, 4)
+        self.a = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]
+        self.d = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]     # gradients at the activations
+        self.a_last, self.d_last = self.a[2], self.d[2]
+
+    def _trunk_forward(self, st):
+        L.check(self.lib.rz_learn_nchw_to_nhwc(L.ptr(st), L.ptr(self.x), self.B, 4, self.HW, L.stream_ptr()),
+                'rz_learn_nchw_to_nhwc')
+        inp = self.x
+        for i, (ci, co) in enumerate(self.chan):
+            self._conv(inp, self.wf[i], self._p('conv%d.bias' % (i + 1)), self.a[i], ci, co, True)
+            inp = self.a[i]
+
+    def _trunk_backward(self):
+        # last layer first: ReLU mask, weight/bias gradient, data gradient
+        lib, s, B, HW = self.lib, L.stream_ptr(), self.B, self.HW
+        inputs = [self.x, self.a[0], self.a[1]]
+        for i in (2, 1, 0):
+            ci, co = self.chan[i]
+            L.check(lib.rz_learn_relu_bwd(L.ptr(self.a[i]), L.ptr(self.d[i]), B * HW * co, s), 'rz_learn_relu_bwd')
+            L.check(lib.rz_learn_conv_wgrad(L.ptr(inputs[i]), L.ptr(self.d[i]), L.ptr(self._g('conv%d.weight' % (i + 1))),
+                                            L.ptr(self._g('conv%d.bias' % (i + 1))), L.ptr(self.scratch),
+                                            self.scratch.numel(), B, self.H, ci, co, s), 'rz_learn_conv_wgrad')
+            if i > 0:
+                self._conv(self.d[i], self.wb[i], self.zero_bias, self.d[i - 1], co, ci, False)
 
     # ------------------------------------------------------------------ plumbing
     def _p(self, name):
@@ -76,21 +124,13 @@ class NativeTrainer(object):
     def _g(self, name):
         return self._views[name][1]
 
-    def _repack(self):
-        s = L.stream_ptr()
-        for i, (ci, co) in enumerate(self.chan):
-            L.check(self.lib.rz_learn_pack_conv(L.ptr(self._p('conv%d.weight' % (i + 1))), L.ptr(self.wf[i]),
-                                                L.ptr(self.wb[i]), ci, co, s), 'rz_learn_pack_conv')
-
     def _alloc(self, B):
         if B == self.B:
             return
         dev, f32, HW, AS = self.device, torch.float32, self.HW, self.AS
         self.B = B
         z = lambda *shape: torch.zeros(*shape, dtype=f32, device=dev)
-        self.x = z(B, HW, 4)
-        self.a = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]
-        self.d = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]     # gradients at the activations
+        self._alloc_trunk(B)
         self.feat, self.dfeat = z(B, 6, HW), z(B, 6, HW)
         self.logp, self.dlogits = z(B, AS), z(B, AS)
         self.h, self.dh = z(B, 64), z(B, 64)
@@ -98,8 +138,11 @@ class NativeTrainer(object):
         self.terms, self.loss3 = z(B, 3), z(3)
         self.pi, self.z = z(B, self.A), z(B)
         rows = B * HW
-        n_scr = max(96 * 9 * 64 * 128, ((rows + 63) // 64 + 64) * 774, 96 * AS, 1024)
+        n_scr = max(96 * 9 * 64 * 128, ((rows + 63) // 64 + 64) * 774, 96 * AS, 1024, self._trunk_scratch_floats())
         self.scratch = z(n_scr)
+
+    def _trunk_scratch_floats(self):
+        return 0
 
     def _sgemm(self, M, N, K, A, sam, sak, Bm, sbk, sbn, Cm, ldc, alpha=1.0, accumulate=False):
         L.check(self.lib.rz_learn_sgemm(M, N, K, L.ptr(A), sam, sak, L.ptr(Bm), sbk, sbn, L.ptr(Cm), ldc, float(alpha),
@@ -121,16 +164,12 @@ class NativeTrainer(object):
         s = L.stream_ptr()
         lib, HW, AS, A = self.lib, self.HW, self.AS, self.A
         st = states.to(self.device, torch.float32).contiguous()
-        L.check(lib.rz_learn_nchw_to_nhwc(L.ptr(st), L.ptr(self.x), B, 4, HW, s), 'rz_learn_nchw_to_nhwc')
-        inp = self.x
-        for i, (ci, co) in enumerate(self.chan):
-            self._conv(inp, self.wf[i], self._p('conv%d.bias' % (i + 1)), self.a[i], ci, co, True)
-            inp = self.a[i]
+        self._trunk_forward(st)
         # the two 1x1 head convolutions, stacked: rows 0..3 act_conv1, 4..5 val_conv1
         w1 = torch.cat([self._p('act_conv1.weight'), self._p('val_conv1.weight')])
         b1 = torch.cat([self._p('act_conv1.bias'), self._p('val_conv1.bias')])
         self._w1x1 = w1
-        L.check(lib.rz_learn_head_feat_fwd(L.ptr(self.a[2]), L.ptr(w1), L.ptr(b1), L.ptr(self.feat), B, HW, s),
+        L.check(lib.rz_learn_head_feat_fwd(L.ptr(self.a_last), L.ptr(w1), L.ptr(b1), L.ptr(self.feat), B, HW, s),
                 'rz_learn_head_feat_fwd')
         # logits = pf . Wp^T (pf = feat[b][0:4HW]), log_softmax
         self._sgemm(B, A, 4 * HW, self.feat, 6 * HW, 1, self._p('act_fc1.weight'), 1, 4 * HW, self.logp, AS)
@@ -169,23 +208,14 @@ class NativeTrainer(object):
         L.check(lib.rz_learn_relu_bwd(L.ptr(self.feat), L.ptr(self.dfeat), B * 6 * HW, s), 'rz_learn_relu_bwd')
         dw1 = torch.empty(6 * 128, dtype=torch.float32, device=self.device)
         db1 = torch.empty(6, dtype=torch.float32, device=self.device)
-        L.check(lib.rz_learn_head_feat_bwd(L.ptr(self.dfeat), L.ptr(self.a[2]), L.ptr(self._w1x1), L.ptr(self.d[2]),
+        L.check(lib.rz_learn_head_feat_bwd(L.ptr(self.dfeat), L.ptr(self.a_last), L.ptr(self._w1x1), L.ptr(self.d_last),
                                            L.ptr(dw1), L.ptr(db1), L.ptr(self.scratch), self.scratch.numel(), B, HW, s),
                 'rz_learn_head_feat_bwd')
         self._g('act_conv1.weight').copy_(dw1[:4 * 128])
         self._g('val_conv1.weight').copy_(dw1[4 * 128:])
         self._g('act_conv1.bias').copy_(db1[:4])
         self._g('val_conv1.bias').copy_(db1[4:])
-        # trunk, last layer first: ReLU mask, weight/bias gradient, data gradient
-        inputs = [self.x, self.a[0], self.a[1]]
-        for i in (2, 1, 0):
-            ci, co = self.chan[i]
-            L.check(lib.rz_learn_relu_bwd(L.ptr(self.a[i]), L.ptr(self.d[i]), B * HW * co, s), 'rz_learn_relu_bwd')
-            L.check(lib.rz_learn_conv_wgrad(L.ptr(inputs[i]), L.ptr(self.d[i]), L.ptr(self._g('conv%d.weight' % (i + 1))),
-                                            L.ptr(self._g('conv%d.bias' % (i + 1))), L.ptr(self.scratch),
-                                            self.scratch.numel(), B, self.H, ci, co, s), 'rz_learn_conv_wgrad')
-            if i > 0:
-                self._conv(self.d[i], self.wb[i], self.zero_bias, self.d[i - 1], co, ci, False)
+        self._trunk_backward()
         return self.loss3
 
     def adam_step(self):
@@ -238,3 +268,131 @@ class NativeTrainer(object):
     def weights_changed(self):
         """Call after the module's parameters were written from outside (load_state_dict, a broadcast)."""
         self._repack()
+
+
+class ResNetTrainer(NativeTrainer):
+    """The same step for ``ResNetPolicyValueNet`` (stem conv3x3(4 -> 128) + ReLU, N blocks of 2 x [conv3x3 +
+    BatchNorm2d] + skip + ReLU, the reference heads) with the trunk on the tensor cores (``csrc/rz_learn_tc.cu``):
+    bf16 activations / gradients in the padded 16-stride layout, forward convolution and data gradient through
+    ``rz_net_conv3x3_tc2``, weight gradient through the tcgen05 MN-major kernel, BatchNorm in training mode with
+    float32 statistics.  Heads, loss and Adam are the float32 kernels of ``NativeTrainer`` (the trunk output crosses
+    into float32 channels-last once per step).  Square boards up to 15x15, 4 input planes."""
+
+    def _check_module(self, module):
+        if not (hasattr(module, 'stem') and hasattr(module, 'blocks')):
+            raise ValueError('ResNetTrainer trains ResNetPolicyValueNet')
+        W = int(getattr(module, 'board_width', module.board_size))
+        if W != self.H or self.H > 15 or module.stem.in_channels != 4 or int(getattr(module, 'n_actions', self.HW)) != self.HW:
+            raise ValueError('ResNetTrainer: square Gomoku-style boards up to 15x15 with 4 input planes')
+        self.n_blocks = len(module.blocks)
+
+    def _init_trunk(self):
+        dev, bf = self.device, torch.bfloat16
+        self.w_stem = torch.empty(128 * 64, dtype=bf, device=dev)
+        n_conv = 2 * self.n_blocks
+        self.wf = [torch.empty(9 * 128 * 128, dtype=bf, device=dev) for _ in range(n_conv)]
+        self.wb = [torch.empty(9 * 128 * 128, dtype=bf, device=dev) for _ in range(n_conv)]
+        self.stats = [torch.zeros(4 * 128, dtype=torch.float32, device=dev) for _ in range(n_conv)]
+        self.gdesc = L.GameDesc(self.H, min(5, self.H), self.HW, self.AS, self.H, L.GAME_GOMOKU, 0.0, 0, 16)
+        self.conv_names = []
+        for i in range(self.n_blocks):
+            self.conv_names += [('blocks.%d.conv1' % i, 'blocks.%d.bn1' % i), ('blocks.%d.conv2' % i, 'blocks.%d.bn2' % i)]
+        self.bns = []
+        for blk in self.module.blocks:
+            self.bns += [blk.bn1, blk.bn2]
+
+    def _repack(self):
+        s = L.stream_ptr()
+        L.check(self.lib.rz_learn_pack_stem_tc(L.ptr(self._p('stem.weight')), L.ptr(self.w_stem), s), 'rz_learn_pack_stem_tc')
+        for j, (cn, _) in enumerate(self.conv_names):
+            L.check(self.lib.rz_learn_pack_conv_tc(L.ptr(self._p(cn + '.weight')), L.ptr(self.wf[j]), L.ptr(self.wb[j]), s),
+                    'rz_learn_pack_conv_tc')
+
+    def _trunk_scratch_floats(self):
+        return max(49 * 9 * 128 * 128, 148 * 4 * 256 + 256, 96 * 9 * 4 * 128)
+
+    def _alloc_trunk(self, B):
+        dev, bf, HW = self.device, torch.bfloat16, self.HW
+        rows = B * 256
+        t = lambda: torch.zeros(rows, 128, dtype=bf, device=dev)
+        n_conv = 2 * self.n_blocks
+        self.act0 = t()                                  # stem output
+        self.ybuf = [t() for _ in range(n_conv)]         # raw convolution outputs (inputs of the BatchNorms)
+        self.abuf = [t() for _ in range(n_conv)]         # activations after BatchNorm (+ skip) + ReLU
+        self.gbuf = [t() for _ in range(4)]              # gradient ping-pong
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)
+        self.x = z(B, HW, 4)
+        self.a_last, self.d_last = z(B, HW, 128), z(B, HW, 128)
+        self.planes = None
+
+    def _tc_conv(self, inp, w, bias, res, out):
+        L.check(self.lib.rz_net_conv3x3_tc2(L.ptr(inp), L.ptr(w), L.ptr(bias), L.ptr(res), L.ptr(out), self.B, self.H, self.H,
+                                            128, 0, 2, 2, 0, L.stream_ptr()), 'rz_net_conv3x3_tc2')
+
+    def _trunk_forward(self, st):
+        lib, s, B, H = self.lib, L.stream_ptr(), self.B, self.H
+        self.planes = st
+        L.check(lib.rz_net_stem_tc_planes(C.byref(self.gdesc), L.ptr(st), L.ptr(self.w_stem), L.ptr(self._p('stem.bias')),
+                                          L.ptr(self.act0), B, 1, 0, s), 'rz_net_stem_tc_planes')
+        cur = self.act0
+        for j, (cn, bn) in enumerate(self.conv_names):
+            self._tc_conv(cur if j % 2 == 0 else self.abuf[j - 1], self.wf[j], self._p(cn + '.bias'), None, self.ybuf[j])
+            m = self.bns[j]
+            L.check(lib.rz_learn_bn_forward(L.ptr(self.ybuf[j]), L.ptr(cur) if j % 2 == 1 else None, L.ptr(self.abuf[j]),
+                                            L.ptr(self._p(bn + '.weight')), L.ptr(self._p(bn + '.bias')),
+                                            L.ptr(m.running_mean), L.ptr(m.running_var), float(m.eps),
+                                            float(m.momentum if m.momentum is not None else 0.1), L.ptr(self.stats[j]),
+                                            L.ptr(self.scratch), B, H, H, s), 'rz_learn_bn_forward')
+            if j % 2 == 1:
+                cur = self.abuf[j]
+                m.num_batches_tracked += 1
+            else:
+                m.num_batches_tracked += 1
+        self.trunk_out = cur
+        L.check(lib.rz_learn_tile_to_nhwc(L.ptr(cur), L.ptr(self.a_last), B, H, H, s), 'rz_learn_tile_to_nhwc')
+
+    def _trunk_backward(self):
+        lib, s, B, H = self.lib, L.stream_ptr(), self.B, self.H
+        g, dy, dz, da = self.gbuf
+        L.check(lib.rz_learn_nhwc_to_tile(L.ptr(self.d_last), L.ptr(g), B, H, H, s), 'rz_learn_nhwc_to_tile')
+        scr, nscr = L.ptr(self.scratch), self.scratch.numel()
+        for i in reversed(range(self.n_blocks)):
+            j1, j2 = 2 * i, 2 * i + 1
+            block_in = self.act0 if i == 0 else self.abuf[j1 - 1]
+            (c1, b1), (c2, b2) = self.conv_names[j1], self.conv_names[j2]
+            # second half of the block: BatchNorm2 + skip + ReLU, conv2
+            L.check(lib.rz_learn_bn_backward(L.ptr(g), L.ptr(self.abuf[j2]), L.ptr(self.ybuf[j2]), L.ptr(self.stats[j2]),
+                                             L.ptr(self._g(b2 + '.weight')), L.ptr(self._g(b2 + '.bias')), L.ptr(dy), L.ptr(dz),
+                                             scr, B, H, H, s), 'rz_learn_bn_backward')
+            L.check(lib.rz_learn_conv_wgrad_tc(L.ptr(self.abuf[j1]), L.ptr(dy), L.ptr(self._g(c2 + '.weight')), scr, nscr, B, 0, s),
+                    'rz_learn_conv_wgrad_tc')
+            self._tc_conv(dy, self.wb[j2], self.zero_bias, None, da)
+            # first half: BatchNorm1 + ReLU, conv1; the skip gradient dz joins the data gradient
+            L.check(lib.rz_learn_bn_backward(L.ptr(da), L.ptr(self.abuf[j1]), L.ptr(self.ybuf[j1]), L.ptr(self.stats[j1]),
+                                             L.ptr(self._g(b1 + '.weight')), L.ptr(self._g(b1 + '.bias')), L.ptr(dy), None,
+                                             scr, B, H, H, s), 'rz_learn_bn_backward')
+            L.check(lib.rz_learn_conv_wgrad_tc(L.ptr(block_in), L.ptr(dy), L.ptr(self._g(c1 + '.weight')), scr, nscr, B, 0, s),
+                    'rz_learn_conv_wgrad_tc')
+            self._tc_conv(dy, self.wb[j1], self.zero_bias, dz, g)
+            # a convolution bias in front of a BatchNorm has no gradient (the batch mean absorbs it)
+            self._g(c1 + '.bias').zero_()
+            self._g(c2 + '.bias').zero_()
+        # stem: ReLU mask on the tile, then the float32 weight-gradient kernel on channels-last copies (c_in = 4)
+        L.check(lib.rz_learn_relu_bwd_bf16(L.ptr(g), L.ptr(self.act0), L.ptr(dy), B, s), 'rz_learn_relu_bwd_bf16')
+        L.check(lib.rz_learn_tile_to_nhwc(L.ptr(dy), L.ptr(self.d_last), B, H, H, s), 'rz_learn_tile_to_nhwc')
+        L.check(lib.rz_learn_nchw_to_nhwc(L.ptr(self.planes), L.ptr(self.x), B, 4, self.HW, s), 'rz_learn_nchw_to_nhwc')
+        L.check(lib.rz_learn_conv_wgrad(L.ptr(self.x), L.ptr(self.d_last), L.ptr(self._g('stem.weight')),
+                                        L.ptr(self._g('stem.bias')), scr, nscr, B, H, 4, 128, s), 'rz_learn_conv_wgrad')
+
+
+def make_trainer(module, **kw):
+    """The native trainer that fits ``module``, or None (the caller then falls back to its autograd path)."""
+    from .games.gomoku.policy_value_net import PolicyValueNet, ResNetPolicyValueNet
+    if type(module) is PolicyValueNet:
+        return NativeTrainer(module, **kw)
+    if isinstance(module, ResNetPolicyValueNet):
+        W = int(getattr(module, 'board_width', module.board_size))
+        if (W == module.board_size and module.board_size <= 15 and module.stem.in_channels == 4
+                and int(module.n_actions) == module.board_size ** 2):
+            return ResNetTrainer(module, **kw)
+    return None
