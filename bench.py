@@ -519,17 +519,22 @@ def train_block(peaks):
         hw = H * H
         return 2 * hw * 9 * (4 * 32 + 32 * 64 + 64 * 128) + 2 * hw * 128 * 6 + 2 * 4 * hw * hw + 2 * 2 * hw * 64 + 128
 
-    for name, make, B, flops, steps in (
-            ('ResNet-10/128ch 15x15, batch 4096', lambda: ResNetPolicyValueNet(15, n_blocks=10), 4096, None, 6),
-            ('stock PolicyValueNet 15x15, batch 512', lambda: PolicyValueNet(15), 512, stock_flops(15), 10)):
-        x = torch.from_numpy((rs.rand(B, 4, 15, 15) < 0.2).astype(np.float32)).cuda()
-        pi = torch.from_numpy(rs.dirichlet(0.3 * np.ones(225), size=B).astype(np.float32)).cuda()
+    for name, H, make, B, flops, steps in (
+            ('ResNet-10/128ch 15x15, batch 4096', 15, lambda: ResNetPolicyValueNet(15, n_blocks=10), 4096, None, 6),
+            ('stock PolicyValueNet 15x15, batch 512', 15, lambda: PolicyValueNet(15), 512, stock_flops(15), 10),
+            ('stock PolicyValueNet 6x6, batch 32 (the sizes of tools/train_alphazero.py:19-33)', 6,
+             lambda: PolicyValueNet(6), 32, stock_flops(6), 30)):
+        x = torch.from_numpy((rs.rand(B, 4, H, H) < 0.2).astype(np.float32)).cuda()
+        pi = torch.from_numpy(rs.dirichlet(0.3 * np.ones(H * H), size=B).astype(np.float32)).cuda()
         z = torch.from_numpy(rs.choice([-1.0, 0.0, 1.0], size=B).astype(np.float32)).cuda()
         entry = {'step': 'AlphaZeroAgent.learn, ' + name}
-        for kind in ('native', 'autograd'):
+        for kind in ('native', 'autograd', 'autograd_fp32_strict'):
             torch.manual_seed(0)
             net = make()
-            agent = AlphaZeroAgent(15, net=net, trainer=kind)
+            strict = kind == 'autograd_fp32_strict'
+            torch.backends.cudnn.allow_tf32 = not strict
+            torch.backends.cuda.matmul.allow_tf32 = False
+            agent = AlphaZeroAgent(H, net=net, trainer='native' if kind == 'native' else 'autograd')
             if flops is None:
                 flops = net.flops_per_eval()
             for _ in range(2):
@@ -546,10 +551,49 @@ def train_block(peaks):
             entry[kind] = {'ms_per_step': ms, 'steps_per_s': 1e3 / ms, 'samples_per_s': B * 1e3 / ms, 'tflops': tf,
                            'frac_of_sustained_bf16_peak': tf / sustained, 'loss_after': loss,
                            'path': ('hand-written kernels (%s)' % type(agent.trainer).__name__) if agent.trainer is not None
-                           else 'PyTorch autograd, cuDNN/cuBLAS, fp32 tensors with TF32 convolutions (PyTorch default)'}
+                           else ('PyTorch autograd, cuDNN/cuBLAS, true fp32 convolutions (cudnn.allow_tf32 = False): the '
+                                 'accuracy class of the float32 native step' if strict else
+                                 'PyTorch autograd, cuDNN/cuBLAS, fp32 tensors with TF32 convolutions (PyTorch default)')}
             del agent, net
             torch.cuda.empty_cache()
+        torch.backends.cudnn.allow_tf32 = True
+        # the strongest stock-PyTorch variant of the same step: bf16 autocast, channels_last, fused Adam
+        import torch.nn.functional as F
+        torch.manual_seed(0)
+        net = make().cuda().to(memory_format=torch.channels_last)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+        if flops is None:
+            flops = net.flops_per_eval()
+        xc = x.contiguous(memory_format=torch.channels_last)
+
+        def ac_step():
+            net.train()
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                lp, v = net(xc)
+            loss = F.mse_loss(v.float().view(-1), z) - torch.mean(torch.sum(pi * lp.float(), dim=1))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(2):
+            ac_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = ac_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        entry['autograd_bf16_autocast'] = {'ms_per_step': ms, 'steps_per_s': 1e3 / ms, 'tflops': 3.0 * flops * B / ms / 1e9,
+                                           'loss_after': float(loss.item()),
+                                           'path': 'PyTorch autograd, torch.autocast(bf16), channels_last, fused Adam; no '
+                                                   'inference re-pack (not part of that path)'}
+        del net, opt
+        torch.cuda.empty_cache()
         entry['speedup_vs_autograd'] = entry['autograd']['ms_per_step'] / entry['native']['ms_per_step']
+        entry['speedup_vs_autograd_bf16_autocast'] = entry['autograd_bf16_autocast']['ms_per_step'] / entry['native']['ms_per_step']
+        entry['speedup_vs_autograd_fp32_strict'] = entry['autograd_fp32_strict']['ms_per_step'] / entry['native']['ms_per_step']
         entry['includes'] = 'forward, loss, backward, Adam, and the re-pack of the inference weights (refresh_weights)'
         out.append(entry)
     return out

@@ -424,6 +424,17 @@ int rz_learn_bn_forward(const void* y, const void* skip, void* out, const float*
    xhat * dgamma / N) (bf16, zero off the board); dz_out (may be NULL) receives dz, the gradient into the skip */
 int rz_learn_bn_backward(const void* dout, const void* act, const void* y, const float* stats, float* dgamma, float* dbeta,
                          void* dy, void* dz_out, float* scratch, int n_boards, int board_rows, int board_cols, void* stream);
+/* float32 observation planes [n][4][H][W] -> bf16 tile [n*256][128] (channels 0..3, rest zero): the stem's input as the
+   x operand of rz_learn_conv_wgrad_tc (its result's input channels 0..3 are the stem's weight gradient) */
+int rz_learn_planes_to_tile(const float* planes, void* tile, int n_boards, int board_rows, int board_cols, void* stream);
+/* float32 channels-last [n][HW][C] -> bf16 tiles holding the values as (high, low) pairs (hi = bf16(x), lo = bf16(x - hi)):
+   mode 0: tile_a[:, 0:C] = hi, tile_a[:, C:2C] = lo (2C <= 128; the layer input); mode 1: tile_a[:, 0:C] = hi,
+   tile_b[:, 0:C] = lo (the output gradient).  Two rz_learn_conv_wgrad_tc launches (x pair-tile against the high and the
+   low gradient tile) then hold all four partial products of the float32 weight gradient. */
+int rz_learn_nhwc_to_tile_hilo(const float* in, int channels, void* tile_a, void* tile_b, int mode, int n_boards,
+                               int board_rows, int board_cols, void* stream);
+/* out[c] = sum over the rows of a bf16 tile [n*256][128] (a bias gradient); scratch: 148 * 2 * 256 floats */
+int rz_learn_tile_colsum(const void* tile, float* out, float* scratch, int n_boards, void* stream);
 /* grad = dout * (act > 0) on bf16 tiles (ReLU without BatchNorm: the stem) */
 int rz_learn_relu_bwd_bf16(const void* dout, const void* act, void* grad, int n_boards, void* stream);
 /* bf16 padded tile layout [n*256][128] <-> float32 [n][HW][128] */

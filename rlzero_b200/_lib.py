@@ -139,6 +139,9 @@ SIGNATURES = {
                                       C.c_int, _vp]),
     'rz_learn_bn_backward': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_learn_relu_bwd_bf16': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    'rz_learn_planes_to_tile': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_learn_tile_colsum': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    'rz_learn_nhwc_to_tile_hilo': (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_learn_tile_to_nhwc': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_learn_nhwc_to_tile': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_eval_rollout': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),

@@ -255,14 +255,24 @@ rz_bn_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __
 //   mode 0: mean, invstd, scale = gamma * invstd, shift = beta - mean * scale; running statistics updated
 //           (nn.BatchNorm2d in training mode: momentum 0.1, unbiased variance for running_var)
 //   mode 1: dgamma, dbeta, c1 = dbeta / N, c2 = dgamma / N
-__global__ void rz_bn_finalize_kernel(const float* __restrict__ part, int n_blocks, double count, int mode,
-                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                      float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
-                                      float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2,
-                                      float* __restrict__ o3) {
-  const int c = threadIdx.x;
+//   mode 2: o0 = column sums
+__global__ void __launch_bounds__(1024)
+rz_bn_finalize_kernel(const float* __restrict__ part, int n_blocks, double count, int mode,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                      float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2,
+                      float* __restrict__ o3) {
+  // 8 slices of the partials are folded in parallel (fixed assignment and order: deterministic), then combined
+  __shared__ double red[8][2][128];
+  const int c = threadIdx.x & 127, sl = threadIdx.x >> 7;
   double s0 = 0.0, s1 = 0.0;
-  for (int b = 0; b < n_blocks; ++b) { s0 += part[((size_t)b * 2) * 128 + c]; s1 += part[((size_t)b * 2 + 1) * 128 + c]; }
+  for (int b = sl; b < n_blocks; b += 8) { s0 += part[((size_t)b * 2) * 128 + c]; s1 += part[((size_t)b * 2 + 1) * 128 + c]; }
+  red[sl][0][c] = s0; red[sl][1][c] = s1;
+  __syncthreads();
+  if (sl != 0) return;
+  s0 = 0.0; s1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s0 += red[i][0][c]; s1 += red[i][1][c]; }
   if (mode == 0) {
     const double mean = s0 / count;
     double var = s1 / count - mean * mean;
@@ -275,11 +285,13 @@ __global__ void rz_bn_finalize_kernel(const float* __restrict__ part, int n_bloc
       running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
       running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)(var * count / (count - 1.0));
     }
-  } else {
+  } else if (mode == 1) {
     o0[c] = (float)s1;            // dgamma
     o1[c] = (float)s0;            // dbeta
     o2[c] = (float)(s0 / count);
     o3[c] = (float)(s1 / count);
+  } else {
+    o0[c] = (float)s0;            // plain column sums (a bias gradient)
   }
 }
 
@@ -383,11 +395,63 @@ rz_nhwc_to_tile_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__
   }
 }
 
+// float32 observation planes [n][4][H][W] -> bf16 tile layout [n*256][128], channels 0..3 (the rest zero): the stem's
+// input as an operand of the tensor-core weight-gradient kernel (planes are 0/1: exact in bf16)
+__global__ void __launch_bounds__(256)
+rz_planes_to_tile_kernel(const float* __restrict__ planes, __nv_bfloat16* __restrict__ tile, int n, int H, int W) {
+  const int lane = threadIdx.x & 31, c0 = lane * 4, HW = H * W;
+  const long long rows = (long long)n * 256;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    f4 o;
+    o.v[0] = o.v[1] = o.v[2] = o.v[3] = 0.0f;
+    if (lane == 0 && row_on_board(r, H, W)) {
+      const int pos = (int)(r & 255);
+      const float* src = planes + (r >> 8) * 4 * HW + (pos >> 4) * W + (pos & 15);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o.v[e] = src[e * HW];
+    }
+    st_bf16x4(tile + r * 128 + c0, o);
+  }
+}
+
+// float32 channels-last [n][HW][C] -> bf16 tiles carrying the value as a (high, low) pair, x = hi + lo to 16 mantissa
+// bits: the operands of the float32-accurate weight gradient of the reference's own network on the tensor cores.
+//   mode 0 (the layer input, 2C <= 128): tile_a[:, 0:C] = hi, tile_a[:, C:2C] = lo
+//   mode 1 (the output gradient, C <= 128): tile_a[:, 0:C] = hi, tile_b[:, 0:C] = lo
+__global__ void __launch_bounds__(256)
+rz_nhwc_to_tile_hilo_kernel(const float* __restrict__ in, int C, __nv_bfloat16* __restrict__ tile_a,
+                            __nv_bfloat16* __restrict__ tile_b, int mode, int n, int H, int W) {
+  const int lane = threadIdx.x & 31, c0 = lane * 4, HW = H * W;
+  const long long rows = (long long)n * 256;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    f4 a, b;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { a.v[e] = 0.0f; b.v[e] = 0.0f; }
+    if (row_on_board(r, H, W)) {
+      const int pos = (int)(r & 255);
+      const float* src = in + ((r >> 8) * HW + (pos >> 4) * W + (pos & 15)) * C;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + e;
+        const int cs = c < C ? c : c - C;
+        if (c < C || (mode == 0 && c < 2 * C)) {
+          const float x = src[cs];
+          const float hi = __bfloat162float(__float2bfloat16_rn(x));
+          if (c < C) { a.v[e] = hi; b.v[e] = x - hi; }
+          else a.v[e] = x - hi;
+        }
+      }
+    }
+    st_bf16x4(tile_a + r * 128 + c0, a);
+    if (mode == 1) st_bf16x4(tile_b + r * 128 + c0, b);
+  }
+}
+
 inline int row_grid(long long rows) {
   long long b = (rows + 7) / 8;
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
 }
-constexpr int BN_BLOCKS = 148 * 4;
+constexpr int BN_BLOCKS = 148 * 2;
 
 }  // namespace
 
@@ -448,7 +512,7 @@ extern "C" int rz_learn_bn_forward(const void* y, const void* skip, void* out, c
   cudaStream_t st = (cudaStream_t)stream;
   rz_bn_reduce_kernel<0><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, rows, scratch);
   // stats: [4][128] = mean, invstd, scale, shift
-  rz_bn_finalize_kernel<<<1, 128, 0, st>>>(scratch, blocks, (double)n_boards * board_rows * board_cols, 0, gamma, beta, eps,
+  rz_bn_finalize_kernel<<<1, 1024, 0, st>>>(scratch, blocks, (double)n_boards * board_rows * board_cols, 0, gamma, beta, eps,
                                           momentum, running_mean, running_var, stats, stats + 128, stats + 256, stats + 384);
   rz_bn_apply_kernel<<<row_grid(rows), 256, 0, st>>>((const __nv_bfloat16*)y, stats + 256, stats + 384,
                                                     (const __nv_bfloat16*)skip, (__nv_bfloat16*)out, rows, board_rows, board_cols);
@@ -466,12 +530,45 @@ extern "C" int rz_learn_bn_backward(const void* dout, const void* act, const voi
   rz_bn_reduce_kernel<1><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)dout, (const __nv_bfloat16*)act,
                                                 stats, stats + 128, rows, scratch);
   float* coef = scratch + (size_t)BN_BLOCKS * 256;        // c1, c2
-  rz_bn_finalize_kernel<<<1, 128, 0, st>>>(scratch, blocks, (double)n_boards * board_rows * board_cols, 1, nullptr, nullptr, 0.0f,
+  rz_bn_finalize_kernel<<<1, 1024, 0, st>>>(scratch, blocks, (double)n_boards * board_rows * board_cols, 1, nullptr, nullptr, 0.0f,
                                           0.0f, nullptr, nullptr, dgamma, dbeta, coef, coef + 128);
   rz_bn_bwd_apply_kernel<<<row_grid(rows), 256, 0, st>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)act,
                                                         (const __nv_bfloat16*)y, stats, stats + 128, stats + 256, coef, coef + 128,
                                                         (__nv_bfloat16*)dy, (__nv_bfloat16*)dz_out, rows, board_rows, board_cols);
   RZ_LAUNCH_CHECK("rz_learn_bn_backward");
+  return 0;
+}
+
+extern "C" int rz_learn_planes_to_tile(const float* planes, void* tile, int n_boards, int board_rows, int board_cols,
+                                       void* stream) {
+  RZ_REQUIRE(planes && tile && n_boards >= 1 && board_rows <= 15 && board_cols <= 15, "rz_learn_planes_to_tile: bad arguments");
+  rz_planes_to_tile_kernel<<<row_grid((long long)n_boards * 256), 256, 0, (cudaStream_t)stream>>>(
+      planes, (__nv_bfloat16*)tile, n_boards, board_rows, board_cols);
+  RZ_LAUNCH_CHECK("rz_learn_planes_to_tile");
+  return 0;
+}
+
+extern "C" int rz_learn_nhwc_to_tile_hilo(const float* in, int channels, void* tile_a, void* tile_b, int mode, int n_boards,
+                                          int board_rows, int board_cols, void* stream) {
+  RZ_REQUIRE(in && tile_a && (mode == 0 || tile_b) && n_boards >= 1 && board_rows <= 15 && board_cols <= 15,
+             "rz_learn_nhwc_to_tile_hilo: bad arguments");
+  RZ_REQUIRE((mode == 0 && channels >= 1 && 2 * channels <= 128) || (mode == 1 && channels >= 1 && channels <= 128),
+             "rz_learn_nhwc_to_tile_hilo: mode %d with %d channels", mode, channels);
+  rz_nhwc_to_tile_hilo_kernel<<<row_grid((long long)n_boards * 256), 256, 0, (cudaStream_t)stream>>>(
+      in, channels, (__nv_bfloat16*)tile_a, (__nv_bfloat16*)tile_b, mode, n_boards, board_rows, board_cols);
+  RZ_LAUNCH_CHECK("rz_learn_nhwc_to_tile_hilo");
+  return 0;
+}
+
+extern "C" int rz_learn_tile_colsum(const void* tile, float* out, float* scratch, int n_boards, void* stream) {
+  RZ_REQUIRE(tile && out && scratch && n_boards >= 1, "rz_learn_tile_colsum: bad arguments");
+  const long long rows = (long long)n_boards * 256;
+  const int blocks = row_grid(rows) < BN_BLOCKS ? row_grid(rows) : BN_BLOCKS;
+  cudaStream_t st = (cudaStream_t)stream;
+  rz_bn_reduce_kernel<0><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)tile, nullptr, nullptr, nullptr, nullptr, rows, scratch);
+  rz_bn_finalize_kernel<<<1, 1024, 0, st>>>(scratch, blocks, 1.0, 2, nullptr, nullptr, 0.0f, 0.0f, nullptr, nullptr, out, nullptr,
+                                           nullptr, nullptr);
+  RZ_LAUNCH_CHECK("rz_learn_tile_colsum");
   return 0;
 }
 

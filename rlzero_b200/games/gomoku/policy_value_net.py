@@ -126,7 +126,8 @@ class ResNetPolicyValueNet(PolicyValueNet):
 def _fold_bn(conv, bn):
     """Conv weight/bias with an eval-mode BatchNorm folded in (float64 arithmetic)."""
     w = conv.weight.detach().double()
-    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64,
+                                                                              device=w.device)
     if bn is not None:
         s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
         w = w * s[:, None, None, None]
@@ -239,11 +240,12 @@ class NativeForward(object):
             if self.mode == 'tc':
                 # [tap][cout][cin], zero-padded to 128 output channels (a narrower layer's extra channels come
                 # out as relu(0) = 0) and to the 128 channels the previous layer wrote (64 for the plane input)
+                # (packed where the parameters live: after a training step that is the device -- no host round trip)
                 cin_p = 128 if len(self.layers) > 0 else (64 if cin <= 64 else 128)
-                wt = torch.zeros(9, 128, cin_p, dtype=torch.float64)
+                wt = torch.zeros(9, 128, cin_p, dtype=torch.float64, device=w.device)
                 wt[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
                 wd = wt.to(torch.bfloat16).contiguous().to(dev)
-                bpad = torch.zeros(128, dtype=b.dtype)
+                bpad = torch.zeros(128, dtype=b.dtype, device=b.device)
                 bpad[:cout] = b
                 b, cout = bpad, 128
             else:
@@ -262,16 +264,16 @@ class NativeForward(object):
             if conv0.in_channels != 17 or m.trunk_layers()[0][1] is not None:
                 raise ValueError('the Go stem takes the 17 planes of GoEnv.observe (go_env.py:156-166)')
             w0, b0 = _fold_bn(conv0, None)
-            ws = torch.zeros(128, 192, dtype=torch.float64)
+            ws = torch.zeros(128, 192, dtype=torch.float64, device=w0.device)
             ws[:, :153] = w0.permute(0, 2, 3, 1).reshape(128, 153)    # [cout][kh][kw][plane]
             self.stem = dict(w=ws.to(torch.bfloat16).contiguous().to(dev), b=b0.float().contiguous().to(dev),
                              relu=bool(m.trunk_layers()[0][3]))
         elif self.mode == 'tc' and conv0.in_channels == 4 and m.trunk_layers()[0][1] is None:
             w0, b0 = _fold_bn(conv0, None)
             c0 = w0.shape[0]
-            ws = torch.zeros(128, 64, dtype=torch.float64)
+            ws = torch.zeros(128, 64, dtype=torch.float64, device=w0.device)
             ws[:c0, :36] = w0.permute(0, 2, 3, 1).reshape(c0, 36)     # [cout][kh][kw][plane], cout padded to 128
-            bs = torch.zeros(128, dtype=b0.dtype)
+            bs = torch.zeros(128, dtype=b0.dtype, device=b0.device)
             bs[:c0] = b0
             self.stem = dict(w=ws.to(torch.bfloat16).contiguous().to(dev), b=bs.float().contiguous().to(dev),
                              relu=bool(m.trunk_layers()[0][3]))
@@ -279,14 +281,15 @@ class NativeForward(object):
         f32 = torch.float32
         w1 = torch.cat([m.act_conv1.weight.detach().reshape(4, 128), m.val_conv1.weight.detach().reshape(2, 128)])
         b1 = torch.cat([m.act_conv1.bias.detach(), m.val_conv1.bias.detach()])
-        wp = torch.zeros(4 * hw + 4, AS, dtype=f32)      # + 4 zero rows: the kernel prefetches past the end
+        pdev = m.act_fc1.weight.device
+        wp = torch.zeros(4 * hw + 4, AS, dtype=f32, device=pdev)      # + 4 zero rows: the kernel prefetches past the end
         wp[:4 * hw, :self.A] = m.act_fc1.weight.detach().t().float()
-        bp = torch.zeros(AS, dtype=f32)
+        bp = torch.zeros(AS, dtype=f32, device=pdev)
         bp[:self.A] = m.act_fc1.bias.detach().float()
         self.heads = dict(
             w1x1=w1.float().contiguous().to(dev), b1x1=b1.float().contiguous().to(dev),
             wp=wp.contiguous().to(dev), bp=bp.to(dev),
-            wv1=torch.cat([m.val_fc1.weight.detach().t().float().cpu(), torch.zeros(2, 64)]).contiguous().to(dev),
+            wv1=torch.cat([m.val_fc1.weight.detach().t().float(), torch.zeros(2, 64, device=pdev)]).contiguous().to(dev),
             bv1=m.val_fc1.bias.detach().float().contiguous().to(dev),
             wv2=m.val_fc2.weight.detach().reshape(64).float().contiguous().to(dev),
             bv2=m.val_fc2.bias.detach().float().contiguous().to(dev))
@@ -294,12 +297,12 @@ class NativeForward(object):
             # both FCs as one K-major matrix over the padded feature row k' = f*P + y*S + x (rz_heads_desc.wtc_hi)
             S, Pp, A = self.S, self.P, self.A
             KP = (6 * Pp + 63) // 64 * 64
-            wall = torch.zeros(AS + 64, KP, dtype=torch.float32)
-            wpol = torch.zeros(A, 4, S, S, dtype=torch.float32)
-            wpol[:, :, :self.H, :self.W] = m.act_fc1.weight.detach().float().cpu().reshape(A, 4, self.H, self.W)
+            wall = torch.zeros(AS + 64, KP, dtype=torch.float32, device=pdev)
+            wpol = torch.zeros(A, 4, S, S, dtype=torch.float32, device=pdev)
+            wpol[:, :, :self.H, :self.W] = m.act_fc1.weight.detach().float().reshape(A, 4, self.H, self.W)
             wall[:A, :4 * Pp] = wpol.reshape(A, 4 * Pp)
-            wval = torch.zeros(64, 2, S, S, dtype=torch.float32)
-            wval[:, :, :self.H, :self.W] = m.val_fc1.weight.detach().float().cpu().reshape(64, 2, self.H, self.W)
+            wval = torch.zeros(64, 2, S, S, dtype=torch.float32, device=pdev)
+            wval[:, :, :self.H, :self.W] = m.val_fc1.weight.detach().float().reshape(64, 2, self.H, self.W)
             wall[AS:AS + 64, 4 * Pp:6 * Pp] = wval.reshape(64, 2 * Pp)
             whi = wall.to(torch.bfloat16)
             wlo = (wall - whi.float()).to(torch.bfloat16)
@@ -325,27 +328,29 @@ class NativeForward(object):
         return hi, lo
 
     def _pack_tc32(self):
-        """Weights of the float32-accurate tensor-core path (mode 'tc32', see the class docstring)."""
+        """Weights of the float32-accurate tensor-core path (mode 'tc32', see the class docstring); packed where the
+        parameters live (the device after a training step)."""
         dev = self.device
         (c1, _, _, r1), (c2, _, _, r2), (c3, _, _, r3) = self.module.trunk_layers()
+        pdev = c1.weight.device
         # conv1 through the fused stem: weight [128 rows][64 k], k = tap*4 + plane; rows 0..31 = high parts, rows
         # 32..63 = residues of the 32 filters
-        w1 = c1.weight.detach().cpu().double().permute(0, 2, 3, 1).reshape(32, 36)
+        w1 = c1.weight.detach().double().permute(0, 2, 3, 1).reshape(32, 36)
         hi, lo = self._split(w1)
-        ws = torch.zeros(128, 64, dtype=torch.bfloat16)
+        ws = torch.zeros(128, 64, dtype=torch.bfloat16, device=pdev)
         ws[:32, :36], ws[32:64, :36] = hi, lo
-        b1 = torch.zeros(128)
-        b1[:32] = c1.bias.detach().cpu().float()
+        b1 = torch.zeros(128, device=pdev)
+        b1[:32] = c1.bias.detach().float()
         self.stem = dict(w=ws.contiguous().to(dev), b=b1.to(dev), relu=int(bool(r1)) | 2)
         # conv2: [tap][cout (64 real of 128)][cin = hi | lo | hi | lo of the 32 inputs] x [Whi | Whi | Wlo | Wlo]
-        w2 = c2.weight.detach().cpu().double().permute(2, 3, 0, 1).reshape(9, 64, 32)
+        w2 = c2.weight.detach().double().permute(2, 3, 0, 1).reshape(9, 64, 32)
         hi, lo = self._split(w2)
-        wt = torch.zeros(9, 128, 128, dtype=torch.bfloat16)
+        wt = torch.zeros(9, 128, 128, dtype=torch.bfloat16, device=pdev)
         wt[:, :64, 0:32], wt[:, :64, 32:64], wt[:, :64, 64:96], wt[:, :64, 96:128] = hi, hi, lo, lo
-        b2 = torch.zeros(128)
-        b2[:64] = c2.bias.detach().cpu().float()
+        b2 = torch.zeros(128, device=pdev)
+        b2[:64] = c2.bias.detach().float()
         # conv3: [tap][cout 128][cin = Whi (64) | Wlo (64)], three products per tap in the kernel
-        w3 = c3.weight.detach().cpu().double().permute(2, 3, 0, 1).reshape(9, 128, 64)
+        w3 = c3.weight.detach().double().permute(2, 3, 0, 1).reshape(9, 128, 64)
         hi, lo = self._split(w3)
         wt3 = torch.cat([hi, lo], dim=2).contiguous()
         self.layers = [dict(w=None, b=None, cin=64, cout=128, skip=None, relu=bool(r1)),      # the stem

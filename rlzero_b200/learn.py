@@ -76,6 +76,8 @@ class NativeTrainer(object):
         if self.chan != [(4, 32), (32, 64), (64, 128)]:
             raise ValueError('NativeTrainer trains the 4 -> 32 -> 64 -> 128 trunk of the reference')
 
+    use_tc_wgrad = True        # False: the float32 CUDA-core weight-gradient kernel (any board size)
+
     def _init_trunk(self):
         f32 = torch.float32
         # packed convolution weights (forward and data-gradient layouts), refreshed after every update
@@ -95,6 +97,13 @@ class NativeTrainer(object):
         self.a = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]
         self.d = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]     # gradients at the activations
         self.a_last, self.d_last = self.a[2], self.d[2]
+        # operands of the tensor-core weight gradient: one [hi | lo] input tile, the high and the low gradient tile
+        self.wg_tiles = None
+        if self.H <= 15 and self.use_tc_wgrad:
+            bf = torch.bfloat16
+            self.wg_tiles = [torch.zeros(B * 256, 128, dtype=bf, device=self.device) for _ in range(3)]
+            self.dw_a = torch.zeros(128 * 128 * 9, dtype=torch.float32, device=self.device)
+            self.dw_b = torch.zeros(128 * 128 * 9, dtype=torch.float32, device=self.device)
 
     def _trunk_forward(self, st):
         L.check(self.lib.rz_learn_nchw_to_nhwc(L.ptr(st), L.ptr(self.x), self.B, 4, self.HW, L.stream_ptr()),
@@ -104,6 +113,23 @@ class NativeTrainer(object):
             self._conv(inp, self.wf[i], self._p('conv%d.bias' % (i + 1)), self.a[i], ci, co, True)
             inp = self.a[i]
 
+    def _wgrad_tc_split(self, x, dz, ci, co, gw, gb):
+        """The float32 weight gradient of a 3x3 convolution on the tensor cores: input and output gradient travel as
+        bf16 (high, low) pairs (16 mantissa bits), two launches of the tcgen05 weight-gradient kernel form all four
+        partial products in fp32 accumulators (a [hi | lo] input tile against the high and the low gradient tile).
+        Boards up to 15x15; the CUDA-core kernel serves larger ones."""
+        lib, s, B, H = self.lib, L.stream_ptr(), self.B, self.H
+        xt, dhi, dlo = self.wg_tiles
+        L.check(lib.rz_learn_nhwc_to_tile_hilo(L.ptr(x), ci, L.ptr(xt), None, 0, B, H, H, s), 'rz_learn_nhwc_to_tile_hilo')
+        L.check(lib.rz_learn_nhwc_to_tile_hilo(L.ptr(dz), co, L.ptr(dhi), L.ptr(dlo), 1, B, H, H, s), 'rz_learn_nhwc_to_tile_hilo')
+        scr, nscr = L.ptr(self.scratch), self.scratch.numel()
+        L.check(lib.rz_learn_conv_wgrad_tc(L.ptr(xt), L.ptr(dhi), L.ptr(self.dw_a), scr, nscr, B, 0, s), 'rz_learn_conv_wgrad_tc')
+        L.check(lib.rz_learn_conv_wgrad_tc(L.ptr(xt), L.ptr(dlo), L.ptr(self.dw_b), scr, nscr, B, 0, s), 'rz_learn_conv_wgrad_tc')
+        da, db = self.dw_a.view(128, 128, 9), self.dw_b.view(128, 128, 9)
+        # fixed order of the four partial products: (hi*hi + hi*lo) + (lo*hi + lo*lo)
+        torch.add(da[:co, :ci] + da[:co, ci:2 * ci], db[:co, :ci] + db[:co, ci:2 * ci], out=gw.view(co, ci, 9))
+        self._colsum(dz, B * self.HW, co, co, gb, slices=96)
+
     def _trunk_backward(self):
         # last layer first: ReLU mask, weight/bias gradient, data gradient
         lib, s, B, HW = self.lib, L.stream_ptr(), self.B, self.HW
@@ -111,9 +137,12 @@ class NativeTrainer(object):
         for i in (2, 1, 0):
             ci, co = self.chan[i]
             L.check(lib.rz_learn_relu_bwd(L.ptr(self.a[i]), L.ptr(self.d[i]), B * HW * co, s), 'rz_learn_relu_bwd')
-            L.check(lib.rz_learn_conv_wgrad(L.ptr(inputs[i]), L.ptr(self.d[i]), L.ptr(self._g('conv%d.weight' % (i + 1))),
-                                            L.ptr(self._g('conv%d.bias' % (i + 1))), L.ptr(self.scratch),
-                                            self.scratch.numel(), B, self.H, ci, co, s), 'rz_learn_conv_wgrad')
+            gw, gb = self._g('conv%d.weight' % (i + 1)), self._g('conv%d.bias' % (i + 1))
+            if self.wg_tiles is not None:
+                self._wgrad_tc_split(inputs[i], self.d[i], ci, co, gw, gb)
+            else:
+                L.check(lib.rz_learn_conv_wgrad(L.ptr(inputs[i]), L.ptr(self.d[i]), L.ptr(gw), L.ptr(gb), L.ptr(self.scratch),
+                                                self.scratch.numel(), B, self.H, ci, co, s), 'rz_learn_conv_wgrad')
             if i > 0:
                 self._conv(self.d[i], self.wb[i], self.zero_bias, self.d[i - 1], co, ci, False)
 
@@ -138,7 +167,8 @@ class NativeTrainer(object):
         self.terms, self.loss3 = z(B, 3), z(3)
         self.pi, self.z = z(B, self.A), z(B)
         rows = B * HW
-        n_scr = max(96 * 9 * 64 * 128, ((rows + 63) // 64 + 64) * 774, 96 * AS, 1024, self._trunk_scratch_floats())
+        n_scr = max(96 * 9 * 64 * 128, ((rows + 63) // 64 + 64) * 774, 96 * AS, 1024, 49 * 9 * 128 * 128,
+                    self._trunk_scratch_floats())
         self.scratch = z(n_scr)
 
     def _trunk_scratch_floats(self):
@@ -293,6 +323,7 @@ class ResNetTrainer(NativeTrainer):
         self.wf = [torch.empty(9 * 128 * 128, dtype=bf, device=dev) for _ in range(n_conv)]
         self.wb = [torch.empty(9 * 128 * 128, dtype=bf, device=dev) for _ in range(n_conv)]
         self.stats = [torch.zeros(4 * 128, dtype=torch.float32, device=dev) for _ in range(n_conv)]
+        self.dw_full = torch.zeros(128 * 128 * 9, dtype=torch.float32, device=dev)
         self.gdesc = L.GameDesc(self.H, min(5, self.H), self.HW, self.AS, self.H, L.GAME_GOMOKU, 0.0, 0, 16)
         self.conv_names = []
         for i in range(self.n_blocks):
@@ -377,12 +408,14 @@ class ResNetTrainer(NativeTrainer):
             # a convolution bias in front of a BatchNorm has no gradient (the batch mean absorbs it)
             self._g(c1 + '.bias').zero_()
             self._g(c2 + '.bias').zero_()
-        # stem: ReLU mask on the tile, then the float32 weight-gradient kernel on channels-last copies (c_in = 4)
+        # stem: ReLU mask on the tile; its weight gradient through the same tensor-core kernel with the observation
+        # planes as channels 0..3 of a tile (0/1 values: exact), its bias gradient = the column sums of dz
         L.check(lib.rz_learn_relu_bwd_bf16(L.ptr(g), L.ptr(self.act0), L.ptr(dy), B, s), 'rz_learn_relu_bwd_bf16')
-        L.check(lib.rz_learn_tile_to_nhwc(L.ptr(dy), L.ptr(self.d_last), B, H, H, s), 'rz_learn_tile_to_nhwc')
-        L.check(lib.rz_learn_nchw_to_nhwc(L.ptr(self.planes), L.ptr(self.x), B, 4, self.HW, s), 'rz_learn_nchw_to_nhwc')
-        L.check(lib.rz_learn_conv_wgrad(L.ptr(self.x), L.ptr(self.d_last), L.ptr(self._g('stem.weight')),
-                                        L.ptr(self._g('stem.bias')), scr, nscr, B, H, 4, 128, s), 'rz_learn_conv_wgrad')
+        L.check(lib.rz_learn_planes_to_tile(L.ptr(self.planes), L.ptr(da), B, H, H, s), 'rz_learn_planes_to_tile')
+        L.check(lib.rz_learn_conv_wgrad_tc(L.ptr(da), L.ptr(dy), L.ptr(self.dw_full), scr, nscr, B, 0, s),
+                'rz_learn_conv_wgrad_tc')
+        self._g('stem.weight').view(128, 4, 9).copy_(self.dw_full.view(128, 128, 9)[:, :4, :])
+        L.check(lib.rz_learn_tile_colsum(L.ptr(dy), L.ptr(self._g('stem.bias')), scr, B, s), 'rz_learn_tile_colsum')
 
 
 def make_trainer(module, **kw):

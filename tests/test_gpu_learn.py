@@ -30,14 +30,18 @@ def _oracle_params(net):
     return {k: v.detach().cpu().double().numpy().copy() for k, v in net.state_dict().items()}
 
 
+@pytest.mark.parametrize('tc_wgrad', [True, False])
 @pytest.mark.parametrize('size,B', [(6, 32), (3, 8), (15, 48), (9, 130)])
-def test_forward_loss_and_every_gradient_match_the_oracle(size, B):
+def test_forward_loss_and_every_gradient_match_the_oracle(size, B, tc_wgrad):
+    """tc_wgrad: the convolutions' weight gradients on the tensor cores (bf16 high/low pairs, four partial products
+    in fp32 accumulators -- the default up to 15x15) or on the float32 CUDA-core kernel; both within 1e-5."""
     from oracle import train_oracle
     from rlzero_b200.games.gomoku.policy_value_net import PolicyValueNet
     from rlzero_b200.learn import NativeTrainer
     torch.manual_seed(size)
     net = PolicyValueNet(size).cuda()
     tr = NativeTrainer(net)
+    tr.use_tc_wgrad = tc_wgrad
     x, pi, z = _batch(size, B, 1)
     p = _oracle_params(net)
     logp_o, v_o, _ = train_oracle.forward(p, x.astype(np.float64))
