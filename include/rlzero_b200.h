@@ -411,6 +411,13 @@ int rz_learn_conv_wgrad_tc(const void* x, const void* dy, float* dw_oihw, float*
 /* nn.Conv2d weight fp32 [128][128][3][3] -> bf16 w_fwd [tap][cout][cin] (rz_net_conv3x3_tc2's layout) and w_bwd
    [8-tap][cin][cout]: rz_net_conv3x3_tc2(dy, w_bwd, zero bias, residual = skip gradient, ...) is the data gradient */
 int rz_learn_pack_conv_tc(const float* w_oihw, void* w_fwd, void* w_bwd, void* stream);
+/* inference weights of a 128 -> 128 trunk layer from the float32 parameters on the device: nn.Conv2d weight
+   [128][128][3][3] (+ bias) with an eval-mode nn.BatchNorm2d folded in (gamma NULL = no BatchNorm; float64 arithmetic)
+   -> bf16 [tap][cout][cin] and fp32 bias [128], the operands of rz_net_conv3x3_tc2 / _tc3: re-packing after a training
+   step is one launch per layer, no host round trip */
+int rz_net_pack_conv_bn_tc(const float* w_oihw, const float* conv_bias, const float* gamma, const float* beta,
+                           const float* running_mean, const float* running_var, float eps, void* w_out, float* b_out,
+                           void* stream);
 /* stem weight fp32 [128][4][3][3] -> bf16 [128][64] (k = tap*4 + plane, rz_net_stem_tc's layout) */
 int rz_learn_pack_stem_tc(const float* w_oihw, void* w_stem, void* stream);
 /* nn.BatchNorm2d in training mode + skip + ReLU: batch statistics of y over the board squares (biased variance),

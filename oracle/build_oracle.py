@@ -11,15 +11,17 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'c', 'rz_oracle.c')
+SRC_GO = os.path.join(HERE, 'c', 'rz_go_oracle.c')      # Go rules + search (config 4), same shared object
 OUT_DIR = os.path.join(HERE, '_build')
 LIB = os.path.join(OUT_DIR, 'librz_oracle.so')
 
 
 def build(force=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) > os.path.getmtime(SRC):
+    if (not force and os.path.exists(LIB) and os.path.getmtime(LIB) > os.path.getmtime(SRC)
+            and os.path.getmtime(LIB) > os.path.getmtime(SRC_GO)):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = ['gcc', '-O2', '-ffp-contract=off', '-fopenmp', '-shared', '-fPIC', '-o', LIB + '.tmp', SRC, '-lm']
+    cmd = ['gcc', '-O2', '-ffp-contract=off', '-fopenmp', '-shared', '-fPIC', '-o', LIB + '.tmp', SRC, SRC_GO, '-lm']
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if out.returncode != 0:
         raise RuntimeError('gcc failed:\n' + out.stdout.decode())
@@ -57,6 +59,13 @@ def load():
         lib.rzo_dm_search_batch.restype = C.c_int
         lib.rzo_dm_search_batch.argtypes = [C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double, C.c_int,
                                             C.c_int, C.c_int, C.c_int, i32p, f64p, i32p, i32p, f64p, i32p, i32p]
+        i8p = C.POINTER(C.c_int8)
+        lib.rzo_go_search_batch.restype = C.c_int
+        lib.rzo_go_search_batch.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, i32p, i32p, C.c_int, C.c_int, C.c_double,
+                                            C.c_int, C.c_int, i32p, f64p, i32p, f64p]
+        lib.rzo_go_random_games.restype = C.c_int
+        lib.rzo_go_random_games.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, i32p, C.c_int, C.c_uint64, i32p, i32p,
+                                            i8p, i32p, i32p, i32p, f64p, i8p]
         _lib = lib
     return _lib
 
@@ -236,3 +245,50 @@ def dm_search_batch(size, k, move_lists, sims, uct_c=2.0, method='puct', solve=T
 
 if __name__ == '__main__':
     print(build(force=True))
+
+
+def go_search_batch(n, move_lists, n_playout, komi=7.5, move_cap=0, cpuct=5.0, rule=0, eval_id=2):
+    """One fresh AlphaZero search per Go position (oracle/c/rz_go_oracle.c), all host cores.
+    Returns (visits [G, n*n+1], W, root_N, root_W)."""
+    import numpy as np
+    lib = load()
+    G, A = len(move_lists), n * n + 1
+    mx = max(1, max((len(m) for m in move_lists), default=0))
+    mv = np.zeros((G, mx), dtype=np.int32)
+    nm = np.zeros(G, dtype=np.int32)
+    for g, m in enumerate(move_lists):
+        mv[g, :len(m)] = m
+        nm[g] = len(m)
+    visits = np.zeros((G, A), dtype=np.int32)
+    w = np.zeros((G, A), dtype=np.float64)
+    rn = np.zeros(G, dtype=np.int32)
+    rw = np.zeros(G, dtype=np.float64)
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    rc = lib.rzo_go_search_batch(G, n, float(komi), int(move_cap), mv.ctypes.data_as(i32p), nm.ctypes.data_as(i32p), mx,
+                                 n_playout, float(cpuct), int(rule), int(eval_id), visits.ctypes.data_as(i32p),
+                                 w.ctypes.data_as(f64p), rn.ctypes.data_as(i32p), rw.ctypes.data_as(f64p))
+    if rc:
+        raise RuntimeError('rzo_go_search_batch failed (%d)' % rc)
+    return visits, w, rn, rw
+
+
+def go_random_games(G, n, n_plies, komi=7.5, move_cap=0, seed=1):
+    """Random legal Go games by the C oracle's rules: dict(moves [G, max], played [G], cell [G, n*n] (+1 black, -1
+    white), ko, to_play (0 black), over, score float64, legal [G, n*n+1])."""
+    import numpy as np
+    lib = load()
+    plies = np.ascontiguousarray(np.broadcast_to(np.asarray(n_plies, dtype=np.int32), (G,)))
+    mx = max(1, int(plies.max()))
+    out = dict(moves=np.zeros((G, mx), dtype=np.int32), played=np.zeros(G, dtype=np.int32),
+               cell=np.zeros((G, n * n), dtype=np.int8), ko=np.zeros(G, dtype=np.int32),
+               to_play=np.zeros(G, dtype=np.int32), over=np.zeros(G, dtype=np.int32),
+               score=np.zeros(G, dtype=np.float64), legal=np.zeros((G, n * n + 1), dtype=np.int8))
+    i32p, f64p, i8p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_int8)
+    rc = lib.rzo_go_random_games(G, n, float(komi), int(move_cap), plies.ctypes.data_as(i32p), mx, int(seed),
+                                 out['moves'].ctypes.data_as(i32p), out['played'].ctypes.data_as(i32p),
+                                 out['cell'].ctypes.data_as(i8p), out['ko'].ctypes.data_as(i32p),
+                                 out['to_play'].ctypes.data_as(i32p), out['over'].ctypes.data_as(i32p),
+                                 out['score'].ctypes.data_as(f64p), out['legal'].ctypes.data_as(i8p))
+    if rc:
+        raise RuntimeError('rzo_go_random_games failed (%d)' % rc)
+    return out

@@ -135,6 +135,7 @@ SIGNATURES = {
     'rz_learn_conv_wgrad_tc': (C.c_int, [_vp, _vp, _vp, _vp, C.c_longlong, C.c_int, C.c_int, _vp]),
     'rz_learn_pack_conv_tc': (C.c_int, [_vp, _vp, _vp, _vp]),
     'rz_learn_pack_stem_tc': (C.c_int, [_vp, _vp, _vp]),
+    'rz_net_pack_conv_bn_tc': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp]),
     'rz_learn_bn_forward': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, C.c_int, C.c_int,
                                       C.c_int, _vp]),
     'rz_learn_bn_backward': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),

@@ -176,6 +176,25 @@ __global__ void rz_pack_conv_tc_kernel(const float* __restrict__ w, __nv_bfloat1
   wf[((size_t)tap * 128 + co) * 128 + ci] = v;
   wb[((size_t)(8 - tap) * 128 + ci) * 128 + co] = v;
 }
+// inference weights of a 128 -> 128 trunk layer straight from the float32 parameters: eval-mode BatchNorm folded in
+// (float64 arithmetic, like the host packing of NativeForward.refresh_weights), bf16 [tap][cout][cin] + fp32 bias
+__global__ void rz_pack_conv_bn_tc_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                          __nv_bfloat16* __restrict__ wout, float* __restrict__ bout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128 * 128 * 9) return;
+  const int tap = i % 9, ci = (i / 9) & 127, co = i / (9 * 128);
+  double sc = 1.0;
+  if (gamma) sc = (double)gamma[co] / sqrt((double)var[co] + (double)eps);
+  wout[((size_t)tap * 128 + co) * 128 + ci] = __double2bfloat16((double)w[i] * sc);
+  if (tap == 0 && ci == 0) {
+    double b = cbias ? (double)cbias[co] : 0.0;
+    if (gamma) b = (b - (double)mean[co]) * sc + (double)beta[co];
+    bout[co] = (float)b;
+  }
+}
+
 // stem: fp32 [128][4][3][3] -> bf16 [128][64], k = tap*4 + plane (rz_net_stem_tc's layout)
 __global__ void rz_pack_stem_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -492,6 +511,17 @@ extern "C" int rz_learn_pack_conv_tc(const float* w_oihw, void* w_fwd, void* w_b
   rz_pack_conv_tc_kernel<<<(128 * 128 * 9 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       w_oihw, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_bwd);
   RZ_LAUNCH_CHECK("rz_learn_pack_conv_tc");
+  return 0;
+}
+
+extern "C" int rz_net_pack_conv_bn_tc(const float* w_oihw, const float* conv_bias, const float* gamma, const float* beta,
+                                      const float* running_mean, const float* running_var, float eps, void* w_out,
+                                      float* b_out, void* stream) {
+  RZ_REQUIRE(w_oihw && w_out && b_out, "rz_net_pack_conv_bn_tc: null argument");
+  RZ_REQUIRE(!gamma || (beta && running_mean && running_var), "rz_net_pack_conv_bn_tc: incomplete BatchNorm");
+  rz_pack_conv_bn_tc_kernel<<<(128 * 128 * 9 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, conv_bias, gamma, beta, running_mean, running_var, eps, (__nv_bfloat16*)w_out, b_out);
+  RZ_LAUNCH_CHECK("rz_net_pack_conv_bn_tc");
   return 0;
 }
 

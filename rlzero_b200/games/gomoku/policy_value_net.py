@@ -235,6 +235,19 @@ class NativeForward(object):
         if self.mode == 'tc32':
             self._pack_tc32()
         for conv, bn, skip, relu in (m.trunk_layers() if self.mode != 'tc32' else []):
+            if (self.mode == 'tc' and conv.in_channels == 128 and conv.out_channels == 128 and len(self.layers) > 0
+                    and conv.weight.is_cuda and conv.weight.dtype == torch.float32 and conv.weight.is_contiguous()):
+                # a 128 -> 128 trunk layer whose parameters live on the device: folded and packed by one kernel
+                wd = torch.empty(9, 128, 128, dtype=torch.bfloat16, device=dev)
+                bd = torch.empty(128, dtype=torch.float32, device=dev)
+                cb = conv.bias.detach() if conv.bias is not None else None
+                L.check(self.lib.rz_net_pack_conv_bn_tc(
+                    L.ptr(conv.weight.detach()), L.ptr(cb), L.ptr(bn.weight.detach()) if bn is not None else None,
+                    L.ptr(bn.bias.detach()) if bn is not None else None, L.ptr(bn.running_mean) if bn is not None else None,
+                    L.ptr(bn.running_var) if bn is not None else None, float(bn.eps) if bn is not None else 0.0,
+                    L.ptr(wd), L.ptr(bd), L.stream_ptr()), 'rz_net_pack_conv_bn_tc')
+                self.layers.append(dict(w=wd, b=bd, cin=128, cout=128, skip=skip, relu=bool(relu)))
+                continue
             w, b = _fold_bn(conv, bn)                      # [Cout][Cin][3][3]
             cout, cin = w.shape[0], w.shape[1]
             if self.mode == 'tc':

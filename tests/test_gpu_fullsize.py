@@ -356,3 +356,60 @@ def test_8192_random_games_to_the_end_equal_the_c_oracle(size, k):
         played[g, moves[g, :end_ply[g]]] = True
         assert np.array_equal(legal[g], ~played[g]), g
     assert (legal.sum(1) == A - end_ply).all()
+
+
+# ------------------------------------------------------------------ config 4: Go 19x19 at full width
+@pytest.mark.parametrize('rule', [0, 1])
+def test_config4_all_8192_go_trees_at_800_playouts_equal_the_c_oracle(rule):
+    """BASELINE config-4 size, every tree checked: 8192 Go positions on 19x19 (komi 7.5, move cap 722) reached by up
+    to 30 random legal moves, 800 playouts each with the closed-form HASH evaluator on both sides: visit counts, fp64
+    value-sum bit patterns and root statistics of ALL trees equal the plain-C Go oracle (oracle/c/rz_go_oracle.c,
+    pinned on the CPU to oracle/go_oracle.py by tests/test_go_oracle_c.py; parity with the reference's own engine
+    remains unpinned -- pettingzoo's go_base is absent).  The positions are replayed on the device through
+    rz_go_step, so a rules disagreement in the prefix would already fault."""
+    from oracle import build_oracle
+    from oracle.evaluators import EVAL_HASH
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.engine import ClosedFormEvaluator, SearchForest
+    n, komi, cap, n_playout = 19, 7.5, 722, 800
+    games = build_oracle.go_random_games(G, n, [(1000 + g) % 31 for g in range(G)], komi, cap, seed=5)
+    lists = [games['moves'][g][:games['played'][g]].tolist() for g in range(G)]
+    f = SearchForest(G, n, 1, n_playout=n_playout, c_puct=5.0, rule=rule, max_carry=0, game_type=L.GAME_GO, komi=komi,
+                     max_moves=cap)
+    f.set_positions(lists)
+    f.search(ClosedFormEvaluator(EVAL_HASH))
+    torch.cuda.synchronize()
+    f.raise_faults()
+    visits, w, has, root_n, root_w = f.root_stats()
+    cv, cw, crn, crw = build_oracle.go_search_batch(n, lists, n_playout, komi, cap, 5.0, rule, EVAL_HASH)
+    assert np.array_equal(visits, cv)
+    assert np.array_equal(w.view(np.int64), cw.view(np.int64))
+    assert np.array_equal(root_n, crn) and np.array_equal(root_w.view(np.int64), crw.view(np.int64))
+    assert (visits.sum(1) == n_playout - 1).all()
+    assert (visits[:, n * n] > 0).all()                 # the pass is a child of every root
+
+
+def test_config4_8192_random_go_games_to_the_end_equal_the_c_oracle():
+    """8192 random Go games of up to 420 plies (captures, ko, suicide bans, passes, two-pass ends, the move cap) played by
+    the C oracle and replayed on the device (rz_go_step): final boards, ko squares, side to move, game-over flags,
+    Tromp-Taylor scores and the legal-move masks of every game."""
+    from oracle import build_oracle
+    from rlzero_b200 import _lib as L
+    from rlzero_b200.games.go import GoBoards
+    n, komi, cap = 19, 7.5, 400
+    plies = [20 + (37 * g) % 401 for g in range(G)]
+    games = build_oracle.go_random_games(G, n, plies, komi, cap, seed=9)
+    gb = GoBoards(G, n, komi, max_moves=cap)
+    mx = int(games['played'].max())
+    for t in range(mx):
+        gb.step(np.where(t < games['played'], games['moves'][:, min(t, games['moves'].shape[1] - 1)], -1))
+    assert not gb.faults().any()
+    assert np.array_equal(gb.boards().reshape(G, -1), games['cell'])
+    meta = gb.meta.cpu().numpy()
+    assert np.array_equal(meta[:, L.META_KO], games['ko'])
+    assert np.array_equal(meta[:, L.META_PLAYER], games['to_play'])
+    assert np.array_equal((meta[:, L.META_STATUS] != L.ACTIVE).astype(np.int32), games['over'])
+    score, result = (x.cpu().numpy() for x in gb.score())
+    assert np.array_equal(score, games['score'])
+    assert np.array_equal(gb.legal_mask().cpu().numpy().astype(np.int8), games['legal'])
+    assert games['over'].sum() > 100 and (games['played'] < np.asarray(plies)).sum() > 100    # many games really ended
