@@ -382,11 +382,14 @@ def test_config4_all_8192_go_trees_at_800_playouts_equal_the_c_oracle(rule):
     f.raise_faults()
     visits, w, has, root_n, root_w = f.root_stats()
     cv, cw, crn, crw = build_oracle.go_search_batch(n, lists, n_playout, komi, cap, 5.0, rule, EVAL_HASH)
-    assert np.array_equal(visits, cv)
-    assert np.array_equal(w.view(np.int64), cw.view(np.int64))
-    assert np.array_equal(root_n, crn) and np.array_equal(root_w.view(np.int64), crw.view(np.int64))
-    assert (visits.sum(1) == n_playout - 1).all()
-    assert (visits[:, n * n] > 0).all()                 # the pass is a child of every root
+    live = games['over'] == 0          # a random prefix may end with two passes: the engine skips finished games
+    assert live.sum() > G - 256
+    assert np.array_equal(visits[live], cv[live])
+    assert np.array_equal(w[live].view(np.int64), cw[live].view(np.int64))
+    assert np.array_equal(root_n[live], crn[live]) and np.array_equal(root_w[live].view(np.int64), crw[live].view(np.int64))
+    assert (visits[live].sum(1) == n_playout - 1).all()
+    if rule == 0:
+        assert (visits[live][:, n * n] > 0).all()       # UCB1 visits every child once: the pass is one of them
 
 
 def test_config4_8192_random_go_games_to_the_end_equal_the_c_oracle():
