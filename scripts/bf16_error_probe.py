@@ -34,7 +34,38 @@ def compare(agent, x):
     probs, vals = agent.policy_value(x.cpu().numpy())
     dp = float(np.abs(probs - lt.exp().numpy()).max())
     dv = float(np.abs(vals.reshape(-1) - vt.reshape(-1).numpy()).max())
-    return dp, dv, float((lt.max(dim=1).values - lt.min(dim=1).values).max()), float(lt.exp().max()), float(vt.abs().max())
+    # the same network in PyTorch fp32 arithmetic with bf16 STORAGE where the kernels have it (folded weights and the
+    # activation between layers): what any bf16-activation implementation of this net computes
+    import torch.nn.functional as F
+    from rlzero_b200.games.gomoku.policy_value_net import _fold_bn
+    r = lambda t: t.to(torch.bfloat16).float()
+    with torch.no_grad():
+        layers = ref.trunk_layers()
+        outs = []
+        a = x.cpu()
+        for conv, bn, skip, relu in layers:
+            w, b = _fold_bn(conv, bn)
+            y = F.conv2d(a, r(w.float()), b.float(), padding=1)
+            if skip is not None:
+                y = y + outs[skip]
+            a = r(F.relu(y))
+            outs.append(a)
+        le, ve = ref.heads(a)
+        # A/B by emulation: the residual stream kept in fp32 (only the convolutions' inputs are rounded to bf16) -- what
+        # an fp32-skip variant of the kernels would compute
+        outs, a32 = [], x.cpu()
+        for conv, bn, skip, relu in layers:
+            w, b = _fold_bn(conv, bn)
+            y = F.conv2d(r(a32), r(w.float()), b.float(), padding=1)
+            if skip is not None:
+                y = y + outs[skip]
+            a32 = F.relu(y)
+            outs.append(a32)
+        ls, vs = ref.heads(a32)
+    emu_dp = float((le.exp() - lt.exp()).abs().max())
+    emu_dv = float((ve.reshape(-1) - vt.reshape(-1)).abs().max())
+    return (dp, dv, float((lt.max(dim=1).values - lt.min(dim=1).values).max()), float(lt.exp().max()), float(vt.abs().max()),
+            emu_dp, emu_dv, float((ls.exp() - lt.exp()).abs().max()), float((vs.reshape(-1) - vt.reshape(-1)).abs().max()))
 
 
 def run(board=15, blocks=10, gens=8, steps=40, games=2048, playouts=48, batch=2048, log=print):
@@ -75,8 +106,10 @@ def run(board=15, blocks=10, gens=8, steps=40, games=2048, playouts=48, batch=20
                 losses.append(agent.learn(states[idx], pis[idx], zs[idx])[0])
                 step += 1
         x = held if held is not None else torch.from_numpy((np.random.RandomState(0).rand(256, 4, H, H) < 0.15).astype(np.float32))
-        dp, dv, rng, pmax, vmax = compare(agent, x)
-        out = {'generation': gen, 'steps': step, 'max_dp': dp, 'max_dv': dv, 'max_logit_range': rng, 'max_p': pmax, 'max_abs_v': vmax}
+        dp, dv, rng, pmax, vmax, emu_dp, emu_dv, skip_dp, skip_dv = compare(agent, x)
+        out = {'generation': gen, 'steps': step, 'max_dp': dp, 'max_dv': dv, 'max_logit_range': rng, 'max_p': pmax,
+               'max_abs_v': vmax, 'torch_bf16_storage_emulation_max_dp': emu_dp, 'torch_bf16_storage_emulation_max_dv': emu_dv,
+               'emulated_fp32_skip_stream_max_dp': skip_dp, 'emulated_fp32_skip_stream_max_dv': skip_dv}
         if gen > 0:
             out['loss_first'], out['loss_last'] = losses[0], losses[-1]
             out['records'] = int(states.shape[0])
