@@ -528,13 +528,15 @@ def train_block(peaks):
         pi = torch.from_numpy(rs.dirichlet(0.3 * np.ones(H * H), size=B).astype(np.float32)).cuda()
         z = torch.from_numpy(rs.choice([-1.0, 0.0, 1.0], size=B).astype(np.float32)).cuda()
         entry = {'step': 'AlphaZeroAgent.learn, ' + name}
-        for kind in ('native', 'autograd', 'autograd_fp32_strict'):
+        kinds = ('native', 'native_tc', 'autograd', 'autograd_fp32_strict') if 'stock' in name else (
+            'native', 'autograd', 'autograd_fp32_strict')
+        for kind in kinds:
             torch.manual_seed(0)
             net = make()
             strict = kind == 'autograd_fp32_strict'
             torch.backends.cudnn.allow_tf32 = not strict
             torch.backends.cuda.matmul.allow_tf32 = False
-            agent = AlphaZeroAgent(H, net=net, trainer='native' if kind == 'native' else 'autograd')
+            agent = AlphaZeroAgent(H, net=net, trainer=kind if kind.startswith('native') else 'autograd')
             if flops is None:
                 flops = net.flops_per_eval()
             for _ in range(2):
@@ -550,7 +552,9 @@ def train_block(peaks):
             tf = 3.0 * flops * B / ms / 1e9
             entry[kind] = {'ms_per_step': ms, 'steps_per_s': 1e3 / ms, 'samples_per_s': B * 1e3 / ms, 'tflops': tf,
                            'frac_of_sustained_bf16_peak': tf / sustained, 'loss_after': loss,
-                           'path': ('hand-written kernels (%s)' % type(agent.trainer).__name__) if agent.trainer is not None
+                           'path': ('hand-written kernels (%s%s)' % (type(agent.trainer).__name__, ', whole trunk on the tensor '
+                                    'cores: gradients within 1e-2 of the float64 oracle instead of 1e-5' if kind == 'native_tc'
+                                    else '')) if agent.trainer is not None
                            else ('PyTorch autograd, cuDNN/cuBLAS, true fp32 convolutions (cudnn.allow_tf32 = False): the '
                                  'accuracy class of the float32 native step' if strict else
                                  'PyTorch autograd, cuDNN/cuBLAS, fp32 tensors with TF32 convolutions (PyTorch default)')}
@@ -594,6 +598,8 @@ def train_block(peaks):
         entry['speedup_vs_autograd'] = entry['autograd']['ms_per_step'] / entry['native']['ms_per_step']
         entry['speedup_vs_autograd_bf16_autocast'] = entry['autograd_bf16_autocast']['ms_per_step'] / entry['native']['ms_per_step']
         entry['speedup_vs_autograd_fp32_strict'] = entry['autograd_fp32_strict']['ms_per_step'] / entry['native']['ms_per_step']
+        if 'native_tc' in entry:
+            entry['native_tc_speedup_vs_autograd'] = entry['autograd']['ms_per_step'] / entry['native_tc']['ms_per_step']
         entry['includes'] = 'forward, loss, backward, Adam, and the re-pack of the inference weights (refresh_weights)'
         out.append(entry)
     return out

@@ -440,6 +440,18 @@ int rz_learn_planes_to_tile(const float* planes, void* tile, int n_boards, int b
    low gradient tile) then hold all four partial products of the float32 weight gradient. */
 int rz_learn_nhwc_to_tile_hilo(const float* in, int channels, void* tile_a, void* tile_b, int mode, int n_boards,
                                int board_rows, int board_cols, void* stream);
+/* the same for a slice [channel_offset, channel_offset + channels) of a wider tensor (mode 0 layout, 2*channels <= 128) */
+int rz_learn_nhwc_to_tile_hilo_slice(const float* in, int channels_total, int channel_offset, int channels, void* tile_a,
+                                     int n_boards, int board_rows, int board_cols, void* stream);
+/* float32 tile [n*256][128] (first `channels` channels) -> float32 channels-last [n][HW][channels] */
+int rz_learn_tile_f32_to_nhwc(const float* tile, float* out, int channels, int n_boards, int board_rows, int board_cols,
+                              void* stream);
+/* data gradient of a float32-accurate layer in tile space: g = (grad_a + grad_b) * (act > 0) on the first `channels`
+   channels (grad_a / grad_b: float32 tiles written by rz_net_conv3x3_tc2 with flag 64, grad_b may be NULL; act_pair: the
+   layer's activation as a bf16 [hi | lo] pair tile).  g overwrites grad_a (float32) and leaves as bf16 pairs: pair_out =
+   [hi | lo] in one tile (may be NULL), hi_out / lo_out separately (the gradient operands of rz_learn_conv_wgrad_tc) */
+int rz_learn_tile_grad_mask_split(float* grad_a, const float* grad_b, const void* act_pair, int channels, void* pair_out,
+                                  void* hi_out, void* lo_out, int n_boards, void* stream);
 /* out[c] = sum over the rows of a bf16 tile [n*256][128] (a bias gradient); scratch: 148 * 2 * 256 floats */
 int rz_learn_tile_colsum(const void* tile, float* out, float* scratch, int n_boards, void* stream);
 /* grad = dout * (act > 0) on bf16 tiles (ReLU without BatchNorm: the stem) */
@@ -519,7 +531,8 @@ int rz_net_conv3x3_tc2_head(const void* act_in, const void* weight, const float*
    products per tap: hi*Whi + lo*Whi + hi*Wlo), 32 = the 1x1 head convolutions read the float32 accumulators instead
    of bf16-rounded activations.  Together: conv3 (64 -> 128) + act_conv1 / val_conv1 of the reference's own
    PolicyValueNet at float32-level accuracy on the tensor cores.  Likewise rz_net_conv3x3_tc2 accepts flags 8 =
-   split output (64 real output channels written as [hi 0..63 | lo 0..63]; needs flag 2), and the `relu` argument of
+   split output (64 real output channels written as [hi 0..63 | lo 0..63]; needs flag 2) and 64 = float32 output (act_out
+   is float [rows][128]; needs flag 2, no residual), and the `relu` argument of
    rz_net_stem_tc / rz_net_stem_tc_planes bit 1 = 32-channel float32-accurate stem: weight rows 0..31 / 32..63 hold
    the high parts / residues of the 32 filters, the output row is [hi 0..31 | lo 0..31 | hi 0..31 | lo 0..31]. */
 int rz_net_conv3x3_tc2_head_ex(const void* act_in, const void* weight, const float* bias, const void* residual,

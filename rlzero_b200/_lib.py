@@ -143,6 +143,9 @@ SIGNATURES = {
     'rz_learn_planes_to_tile': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_learn_tile_colsum': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     'rz_learn_nhwc_to_tile_hilo': (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_learn_nhwc_to_tile_hilo_slice': (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_learn_tile_f32_to_nhwc': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'rz_learn_tile_grad_mask_split': (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     'rz_learn_tile_to_nhwc': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_learn_nhwc_to_tile': (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rz_eval_rollout': (C.c_int, [_TD, C.c_int, C.c_ulonglong, C.c_int, _vp, _vp, _vp]),

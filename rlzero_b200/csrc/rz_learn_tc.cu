@@ -438,7 +438,7 @@ rz_planes_to_tile_kernel(const float* __restrict__ planes, __nv_bfloat16* __rest
 //   mode 0 (the layer input, 2C <= 128): tile_a[:, 0:C] = hi, tile_a[:, C:2C] = lo
 //   mode 1 (the output gradient, C <= 128): tile_a[:, 0:C] = hi, tile_b[:, 0:C] = lo
 __global__ void __launch_bounds__(256)
-rz_nhwc_to_tile_hilo_kernel(const float* __restrict__ in, int C, __nv_bfloat16* __restrict__ tile_a,
+rz_nhwc_to_tile_hilo_kernel(const float* __restrict__ in, int C_total, int c_off, int C, __nv_bfloat16* __restrict__ tile_a,
                             __nv_bfloat16* __restrict__ tile_b, int mode, int n, int H, int W) {
   const int lane = threadIdx.x & 31, c0 = lane * 4, HW = H * W;
   const long long rows = (long long)n * 256;
@@ -448,7 +448,7 @@ rz_nhwc_to_tile_hilo_kernel(const float* __restrict__ in, int C, __nv_bfloat16* 
     for (int e = 0; e < 4; ++e) { a.v[e] = 0.0f; b.v[e] = 0.0f; }
     if (row_on_board(r, H, W)) {
       const int pos = (int)(r & 255);
-      const float* src = in + ((r >> 8) * HW + (pos >> 4) * W + (pos & 15)) * C;
+      const float* src = in + ((r >> 8) * HW + (pos >> 4) * W + (pos & 15)) * C_total + c_off;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = c0 + e;
@@ -463,6 +463,62 @@ rz_nhwc_to_tile_hilo_kernel(const float* __restrict__ in, int C, __nv_bfloat16* 
     }
     st_bf16x4(tile_a + r * 128 + c0, a);
     if (mode == 1) st_bf16x4(tile_b + r * 128 + c0, b);
+  }
+}
+
+// float32 tile [n*256][128] (first C channels) -> float32 channels-last [n][HW][C]
+__global__ void __launch_bounds__(256)
+rz_tile_f32_to_nhwc_kernel(const float* __restrict__ tile, float* __restrict__ out, int C, int n, int H, int W) {
+  const int lane = threadIdx.x & 31, HW = H * W;
+  const long long rows = (long long)n * HW;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    const int b = (int)(r / HW), pos = (int)(r - (long long)b * HW);
+    const float* src = tile + ((long long)b * 256 + (pos / W) * 16 + pos % W) * 128;
+    for (int c = lane; c < C; c += 32) out[r * C + c] = src[c];
+  }
+}
+
+// the data gradient of a float32-accurate layer back in tile space: g = (grad_a + grad_b) * (act > 0) on the first C
+// channels (act: the layer's activation as a [hi | lo ...] pair tile, its sign is the sign of the high part); g is
+// written back to grad_a as float32 (for the bias gradient) and as bf16 pairs: pair_out = [hi | lo] in one tile (the
+// input of the next data gradient; may be NULL), hi_out / lo_out = the two gradient tiles of the weight gradient
+__global__ void __launch_bounds__(256)
+rz_tile_grad_mask_split_kernel(float* __restrict__ grad_a, const float* __restrict__ grad_b,
+                               const __nv_bfloat16* __restrict__ act, int C, __nv_bfloat16* __restrict__ pair_out,
+                               __nv_bfloat16* __restrict__ hi_out, __nv_bfloat16* __restrict__ lo_out, long long rows) {
+  const int lane = threadIdx.x & 31, c0 = lane * 4;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    f4 hi, lo, pr;
+    float g[4];
+    const f4 av = ld_bf16x4(act + r * 128 + (c0 < C ? c0 : 0));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = c0 + e;
+      g[e] = 0.0f;
+      if (c < C) {
+        float x = grad_a[r * 128 + c] + (grad_b ? grad_b[r * 128 + c] : 0.0f);
+        g[e] = av.v[e] > 0.0f ? x : 0.0f;
+      }
+      hi.v[e] = __bfloat162float(__float2bfloat16_rn(g[e]));
+      lo.v[e] = g[e] - hi.v[e];
+    }
+    if (c0 < C) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (c0 + e < C) grad_a[r * 128 + c0 + e] = g[e];
+    }
+    st_bf16x4(hi_out + r * 128 + c0, hi);
+    st_bf16x4(lo_out + r * 128 + c0, lo);
+    if (pair_out) {
+      // channel c of the pair tile: hi for c < C, lo of channel c - C for C <= c < 2C (C is a multiple of 4): the low
+      // parts come from the lane that owns those channels
+      const int src_lane = lane - (C >> 2);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo_other = __shfl_sync(RZ_FULL, lo.v[e], src_lane < 0 ? 0 : src_lane);
+        pr.v[e] = c0 < C ? hi.v[e] : (c0 < 2 * C ? lo_other : 0.0f);
+      }
+      st_bf16x4(pair_out + r * 128 + c0, pr);
+    }
   }
 }
 
@@ -585,8 +641,39 @@ extern "C" int rz_learn_nhwc_to_tile_hilo(const float* in, int channels, void* t
   RZ_REQUIRE((mode == 0 && channels >= 1 && 2 * channels <= 128) || (mode == 1 && channels >= 1 && channels <= 128),
              "rz_learn_nhwc_to_tile_hilo: mode %d with %d channels", mode, channels);
   rz_nhwc_to_tile_hilo_kernel<<<row_grid((long long)n_boards * 256), 256, 0, (cudaStream_t)stream>>>(
-      in, channels, (__nv_bfloat16*)tile_a, (__nv_bfloat16*)tile_b, mode, n_boards, board_rows, board_cols);
+      in, channels, 0, channels, (__nv_bfloat16*)tile_a, (__nv_bfloat16*)tile_b, mode, n_boards, board_rows, board_cols);
   RZ_LAUNCH_CHECK("rz_learn_nhwc_to_tile_hilo");
+  return 0;
+}
+
+extern "C" int rz_learn_nhwc_to_tile_hilo_slice(const float* in, int channels_total, int channel_offset, int channels,
+                                                void* tile_a, int n_boards, int board_rows, int board_cols, void* stream) {
+  RZ_REQUIRE(in && tile_a && n_boards >= 1 && board_rows <= 15 && board_cols <= 15 && channels >= 1 && 2 * channels <= 128 &&
+             channel_offset >= 0 && channel_offset + channels <= channels_total, "rz_learn_nhwc_to_tile_hilo_slice: bad arguments");
+  rz_nhwc_to_tile_hilo_kernel<<<row_grid((long long)n_boards * 256), 256, 0, (cudaStream_t)stream>>>(
+      in, channels_total, channel_offset, channels, (__nv_bfloat16*)tile_a, nullptr, 0, n_boards, board_rows, board_cols);
+  RZ_LAUNCH_CHECK("rz_learn_nhwc_to_tile_hilo_slice");
+  return 0;
+}
+
+extern "C" int rz_learn_tile_f32_to_nhwc(const float* tile, float* out, int channels, int n_boards, int board_rows,
+                                         int board_cols, void* stream) {
+  RZ_REQUIRE(tile && out && n_boards >= 1 && board_rows <= 15 && board_cols <= 15 && channels >= 1 && channels <= 128,
+             "rz_learn_tile_f32_to_nhwc: bad arguments");
+  rz_tile_f32_to_nhwc_kernel<<<row_grid((long long)n_boards * board_rows * board_cols), 256, 0, (cudaStream_t)stream>>>(
+      tile, out, channels, n_boards, board_rows, board_cols);
+  RZ_LAUNCH_CHECK("rz_learn_tile_f32_to_nhwc");
+  return 0;
+}
+
+extern "C" int rz_learn_tile_grad_mask_split(float* grad_a, const float* grad_b, const void* act_pair, int channels,
+                                             void* pair_out, void* hi_out, void* lo_out, int n_boards, void* stream) {
+  RZ_REQUIRE(grad_a && act_pair && hi_out && lo_out && n_boards >= 1 && channels >= 1 && 2 * channels <= 128,
+             "rz_learn_tile_grad_mask_split: bad arguments");
+  rz_tile_grad_mask_split_kernel<<<row_grid((long long)n_boards * 256), 256, 0, (cudaStream_t)stream>>>(
+      grad_a, grad_b, (const __nv_bfloat16*)act_pair, channels, (__nv_bfloat16*)pair_out, (__nv_bfloat16*)hi_out,
+      (__nv_bfloat16*)lo_out, (long long)n_boards * 256);
+  RZ_LAUNCH_CHECK("rz_learn_tile_grad_mask_split");
   return 0;
 }
 

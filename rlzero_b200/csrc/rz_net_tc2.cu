@@ -46,7 +46,7 @@ constexpr int NUM_THREADS = 320;                  // producer warp, MMA warp, 8 
 struct Conv2Params {
   const float* bias;               // [128]
   const __nv_bfloat16* residual;   // [rows][128] or null
-  __nv_bfloat16* out;              // [rows][128]
+  __nv_bfloat16* out;              // [rows][128]  (flags bit 6: float [rows][128] instead)
   int n_items;                     // kCG=2: boards; kCG=1: half boards
   int board;                       // H (rows)
   int board_w;                     // W (columns)
@@ -312,7 +312,21 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
             }
             if (!valid) packed[e] = 0u;
           }
-          if (kDirect) {
+          if (kDirect && (p.flags & 64)) {
+            // float32 output (the training step of the reference's own network keeps conv3's activation and the data
+            // gradients at accumulator precision): 8 channels = one 32-byte store
+            uint32_t f8[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = j * 8 + e * 2;
+              float v0 = __uint_as_float(acc[ch][c]) + bb[e * 2];
+              float v1 = __uint_as_float(acc[ch][c + 1]) + bb[e * 2 + 1];
+              if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+              f8[e * 2] = valid ? __float_as_uint(v0) : 0u;
+              f8[e * 2 + 1] = valid ? __float_as_uint(v1) : 0u;
+            }
+            rz::st_global_v8(reinterpret_cast<float*>(p.out) + row * 128 + col0 + ch * 32 + j * 8, f8);
+          } else if (kDirect) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) pair8[(j & 1) * 4 + e] = packed[e];
             if (j & 1) rz::st_global_v8(p.out + row * 128 + col0 + ch * 32 + (j - 1) * 8, pair8);
@@ -486,6 +500,8 @@ static int conv2_entry(const void* act_in, const void* weight, const float* bias
   RZ_REQUIRE(!(flags & (8 | 16)) || (cta_group == 2 && c_in == 128),
              "rz_net_conv3x3_tc2: the split modes (flags 8 / 16) need the pair kernel and c_in = 128");
   RZ_REQUIRE(!(flags & 8) || (flags & 2) || feat, "rz_net_conv3x3_tc2: split output (flag 8) needs the direct-store epilogue (flag 2)");
+  RZ_REQUIRE(!(flags & 64) || ((flags & 2) && cta_group == 2 && !(flags & 8) && !residual && !feat),
+             "rz_net_conv3x3_tc2: float32 output (flag 64) needs the direct-store pair kernel, no residual, no split output");
   if (n_boards == 0) return 0;
   static HeadTaps head;   // ~3 KB: filled per call, copied into the launch parameters
   CUtensorMap tmap_act, tmap_w, tmap_out;

@@ -52,14 +52,17 @@ class AlphaZeroAgent(object):
         self.optimizer = optim.Adam(self.policy_value_net.parameters(), lr=learning_rate,
                                     weight_decay=weight_decay)
         self.device = device
-        if trainer not in (None, 'native', 'autograd'):
-            raise ValueError("trainer must be 'native' or 'autograd'")
+        if trainer not in (None, 'native', 'native_tc', 'autograd'):
+            raise ValueError("trainer must be 'native', 'native_tc' or 'autograd'")
         self.trainer = None
         if trainer != 'autograd':
             # re-points the module's parameters at one flat device buffer (state_dict / optimizer see the same tensors)
-            self.trainer = make_trainer(self.policy_value_net, learning_rate=learning_rate, weight_decay=weight_decay,
-                                        device=device)
-            if self.trainer is None and trainer == 'native':
+            # 'native_tc': the reference's own network with forward and data-gradient convolutions on the tensor cores as
+            # well (16-mantissa-bit pairs: forward still within 1e-5, gradients within 1e-3..1e-2 of the float64 oracle
+            # instead of 1e-5 -- tighter than PyTorch's default TF32 convolutions -- and 3x faster at batch 512)
+            self.trainer = make_trainer(self.policy_value_net, tc_trunk=(trainer == 'native_tc'),
+                                        learning_rate=learning_rate, weight_decay=weight_decay, device=device)
+            if self.trainer is None and trainer in ('native', 'native_tc'):
                 raise ValueError('no native trainer fits this module (use trainer="autograd")')
         self.native = NativeForward(self.policy_value_net, mode=mode, device=device)
         self.policy_value_fn = _PolicyValueFn(self)

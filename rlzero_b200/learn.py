@@ -77,6 +77,10 @@ class NativeTrainer(object):
             raise ValueError('NativeTrainer trains the 4 -> 32 -> 64 -> 128 trunk of the reference')
 
     use_tc_wgrad = True        # False: the float32 CUDA-core weight-gradient kernel (any board size)
+    use_tc_trunk = False       # True ('native_tc'): forward AND data-gradient convolutions on the tensor cores too, on
+                               # 16-mantissa-bit pairs: 3x faster at batch 512.  Forward within 1e-5 as before; the
+                               # gradients within ~1e-3..1e-2 of the float64 oracle instead of 1e-5 (ReLU masks of
+                               # pre-activations within 2e-6 of zero flip) -- tighter than PyTorch's default TF32
 
     def _init_trunk(self):
         f32 = torch.float32
@@ -89,6 +93,49 @@ class NativeTrainer(object):
         for i, (ci, co) in enumerate(self.chan):
             L.check(self.lib.rz_learn_pack_conv(L.ptr(self._p('conv%d.weight' % (i + 1))), L.ptr(self.wf[i]),
                                                 L.ptr(self.wb[i]), ci, co, s), 'rz_learn_pack_conv')
+        if self.H <= 15 and self.use_tc_trunk:
+            self._repack_tc()
+
+    @staticmethod
+    def _split(w):
+        w = w.float()
+        hi = w.to(torch.bfloat16)
+        return hi, (w - hi.float()).to(torch.bfloat16)
+
+    def _repack_tc(self):
+        """bf16 (high, low) weight tiles of the float32-accurate tensor-core trunk (the layouts of NativeForward's mode
+        'tc32' for the forward pass; mirrored taps and swapped channel roles for the data gradients)."""
+        dev, bf = self.device, torch.bfloat16
+        w1 = self._p('conv1.weight').view(32, 4, 3, 3).double().permute(0, 2, 3, 1).reshape(32, 36)
+        hi, lo = self._split(w1)
+        ws = torch.zeros(128, 64, dtype=bf, device=dev)
+        ws[:32, :36], ws[32:64, :36] = hi, lo
+        b1 = torch.zeros(128, device=dev)
+        b1[:32] = self._p('conv1.bias')
+        w2 = self._p('conv2.weight').view(64, 32, 3, 3).double()
+        hi, lo = self._split(w2.permute(2, 3, 0, 1).reshape(9, 64, 32))                  # [tap][co][ci]
+        wt2 = torch.zeros(9, 128, 128, dtype=bf, device=dev)
+        wt2[:, :64, 0:32], wt2[:, :64, 32:64], wt2[:, :64, 64:96], wt2[:, :64, 96:128] = hi, hi, lo, lo
+        b2 = torch.zeros(128, device=dev)
+        b2[:64] = self._p('conv2.bias')
+        w3 = self._p('conv3.weight').view(128, 64, 3, 3).double()
+        hi, lo = self._split(w3.permute(2, 3, 0, 1).reshape(9, 128, 64))
+        wt3 = torch.cat([hi, lo], dim=2).contiguous()
+        # data gradients: wT[8 - tap][ci][co] = w[co][ci][tap]; conv3 in two passes over the halves of its 128 output
+        # channels (the kernel's K is 128 = [hi 64 | lo 64] of one half), conv2 in one
+        flip = lambda w: torch.flip(w.permute(2, 3, 1, 0).reshape(9, w.shape[1], w.shape[0]), dims=[0])   # [8-tap][ci][co]
+        w3t = flip(w3)                                                                   # [9][64 ci][128 co]
+        d3 = []
+        for h in range(2):
+            hi, lo = self._split(w3t[:, :, 64 * h:64 * h + 64])
+            t = torch.zeros(9, 128, 128, dtype=bf, device=dev)
+            t[:, :64, :64], t[:, :64, 64:] = hi, lo
+            d3.append(t.contiguous())
+        hi, lo = self._split(flip(w2))                                                   # [9][32 ci][64 co]
+        d2 = torch.zeros(9, 128, 128, dtype=bf, device=dev)
+        d2[:, :32, :64], d2[:, :32, 64:] = hi, lo
+        self.tcw = dict(stem=ws.contiguous(), b1=b1, w2=wt2.contiguous(), b2=b2, w3=wt3,
+                        b3=self._p('conv3.bias'), d3=d3, d2=d2.contiguous())
 
     def _alloc_trunk(self, B):
         z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=self.device)
@@ -97,6 +144,14 @@ class NativeTrainer(object):
         self.a = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]
         self.d = [z(B, HW, 32), z(B, HW, 64), z(B, HW, 128)]     # gradients at the activations
         self.a_last, self.d_last = self.a[2], self.d[2]
+        # the float32-accurate tensor-core trunk: activations as bf16 pair tiles, conv3's output and the data gradients
+        # as float32 tiles
+        self.tc = None
+        if self.H <= 15 and self.use_tc_trunk and self.use_tc_wgrad:
+            bft = lambda: torch.zeros(B * 256, 128, dtype=torch.bfloat16, device=self.device)
+            f32t = lambda: torch.zeros(B * 256, 128, dtype=torch.float32, device=self.device)
+            self.tc = dict(T1=bft(), T2=bft(), X0=bft(), XP=bft(), A3=f32t(), P1=f32t(), P2=f32t())
+            self.gdesc = L.GameDesc(self.H, min(5, self.H), self.HW, self.AS, self.H, L.GAME_GOMOKU, 0.0, 0, 16)
         # operands of the tensor-core weight gradient: one [hi | lo] input tile, the high and the low gradient tile
         self.wg_tiles = None
         if self.H <= 15 and self.use_tc_wgrad:
@@ -105,7 +160,61 @@ class NativeTrainer(object):
             self.dw_a = torch.zeros(128 * 128 * 9, dtype=torch.float32, device=self.device)
             self.dw_b = torch.zeros(128 * 128 * 9, dtype=torch.float32, device=self.device)
 
+    def _tc_conv(self, inp, w, bias, out, relu, flags):
+        L.check(self.lib.rz_net_conv3x3_tc2(L.ptr(inp), L.ptr(w), L.ptr(bias), None, L.ptr(out), self.B, self.H, self.H, 128,
+                                            int(relu), 2, flags, 0, L.stream_ptr()), 'rz_net_conv3x3_tc2')
+
+    def _trunk_forward_tc(self, st):
+        """The three convolutions on the tensor cores at float32-level accuracy (mode 'tc32' of the inference path):
+        split stem -> one-pass conv2 with split output -> three-product conv3 with float32 output."""
+        lib, s, B, H, t, w = self.lib, L.stream_ptr(), self.B, self.H, self.tc, self.tcw
+        self.planes = st
+        L.check(lib.rz_net_stem_tc_planes(C.byref(self.gdesc), L.ptr(st), L.ptr(w['stem']), L.ptr(w['b1']), L.ptr(t['T1']), B,
+                                          1 | 2, 0, s), 'rz_net_stem_tc_planes')
+        self._tc_conv(t['T1'], w['w2'], w['b2'], t['T2'], True, 2 | 8)
+        self._tc_conv(t['T2'], w['w3'], w['b3'], t['A3'], True, 2 | 16 | 64)
+        L.check(lib.rz_learn_tile_f32_to_nhwc(L.ptr(t['A3']), L.ptr(self.a[2]), 128, B, H, H, s), 'rz_learn_tile_f32_to_nhwc')
+
+    def _wgrad_pair(self, xt, dhi, dlo, ci, co, gw):
+        scr, nscr, s = L.ptr(self.scratch), self.scratch.numel(), L.stream_ptr()
+        L.check(self.lib.rz_learn_conv_wgrad_tc(L.ptr(xt), L.ptr(dhi), L.ptr(self.dw_a), scr, nscr, self.B, 0, s),
+                'rz_learn_conv_wgrad_tc')
+        L.check(self.lib.rz_learn_conv_wgrad_tc(L.ptr(xt), L.ptr(dlo), L.ptr(self.dw_b), scr, nscr, self.B, 0, s),
+                'rz_learn_conv_wgrad_tc')
+        da, db = self.dw_a.view(128, 128, 9), self.dw_b.view(128, 128, 9)
+        torch.add(da[:co, :ci] + da[:co, ci:2 * ci], db[:co, :ci] + db[:co, ci:2 * ci], out=gw.view(co, ci, 9))
+
+    def _trunk_backward_tc(self):
+        lib, s, B, H, HW, t, w = self.lib, L.stream_ptr(), self.B, self.H, self.HW, self.tc, self.tcw
+        xt, dhi, dlo = self.wg_tiles
+        # conv3: ReLU mask in channels-last float32 (where the heads left the gradient), weight gradient against the
+        # stored [hi | lo] tile of a2, bias gradient
+        L.check(lib.rz_learn_relu_bwd(L.ptr(self.a[2]), L.ptr(self.d[2]), B * HW * 128, s), 'rz_learn_relu_bwd')
+        L.check(lib.rz_learn_nhwc_to_tile_hilo(L.ptr(self.d[2]), 128, L.ptr(dhi), L.ptr(dlo), 1, B, H, H, s),
+                'rz_learn_nhwc_to_tile_hilo')
+        self._wgrad_pair(t['T2'], dhi, dlo, 64, 128, self._g('conv3.weight'))
+        self._colsum(self.d[2], B * HW, 128, 128, self._g('conv3.bias'), slices=96)
+        # data gradient of conv3 in two passes over the halves of its output channels, float32 out
+        for h, out in ((0, t['P1']), (1, t['P2'])):
+            L.check(lib.rz_learn_nhwc_to_tile_hilo_slice(L.ptr(self.d[2]), 128, 64 * h, 64, L.ptr(t['XP']), B, H, H, s),
+                    'rz_learn_nhwc_to_tile_hilo_slice')
+            self._tc_conv(t['XP'], w['d3'][h], self.zero_bias, out, False, 2 | 16 | 64)
+        # dz2 = (P1 + P2) * (a2 > 0): float32 back into P1, [hi | lo] pair tile for the next data gradient, hi / lo tiles
+        L.check(lib.rz_learn_tile_grad_mask_split(L.ptr(t['P1']), L.ptr(t['P2']), L.ptr(t['T2']), 64, L.ptr(t['XP']), L.ptr(dhi),
+                                                  L.ptr(dlo), B, s), 'rz_learn_tile_grad_mask_split')
+        self._wgrad_pair(t['T1'], dhi, dlo, 32, 64, self._g('conv2.weight'))
+        self._colsum(t['P1'], B * 256, 64, 128, self._g('conv2.bias'), slices=96)
+        # conv2's data gradient (one pass: 64 channels in = one [hi | lo] tile), then dz1 and conv1's gradients
+        self._tc_conv(t['XP'], w['d2'], self.zero_bias, t['P2'], False, 2 | 16 | 64)
+        L.check(lib.rz_learn_tile_grad_mask_split(L.ptr(t['P2']), None, L.ptr(t['T1']), 32, None, L.ptr(dhi), L.ptr(dlo), B, s),
+                'rz_learn_tile_grad_mask_split')
+        L.check(lib.rz_learn_planes_to_tile(L.ptr(self.planes), L.ptr(t['X0']), B, H, H, s), 'rz_learn_planes_to_tile')
+        self._wgrad_pair(t['X0'], dhi, dlo, 4, 32, self._g('conv1.weight'))
+        self._colsum(t['P2'], B * 256, 32, 128, self._g('conv1.bias'), slices=96)
+
     def _trunk_forward(self, st):
+        if self.tc is not None:
+            return self._trunk_forward_tc(st)
         L.check(self.lib.rz_learn_nchw_to_nhwc(L.ptr(st), L.ptr(self.x), self.B, 4, self.HW, L.stream_ptr()),
                 'rz_learn_nchw_to_nhwc')
         inp = self.x
@@ -131,6 +240,8 @@ class NativeTrainer(object):
         self._colsum(dz, B * self.HW, co, co, gb, slices=96)
 
     def _trunk_backward(self):
+        if self.tc is not None:
+            return self._trunk_backward_tc()
         # last layer first: ReLU mask, weight/bias gradient, data gradient
         lib, s, B, HW = self.lib, L.stream_ptr(), self.B, self.HW
         inputs = [self.x, self.a[0], self.a[1]]
@@ -418,11 +529,15 @@ class ResNetTrainer(NativeTrainer):
         L.check(lib.rz_learn_tile_colsum(L.ptr(dy), L.ptr(self._g('stem.bias')), scr, B, s), 'rz_learn_tile_colsum')
 
 
-def make_trainer(module, **kw):
-    """The native trainer that fits ``module``, or None (the caller then falls back to its autograd path)."""
+def make_trainer(module, tc_trunk=False, **kw):
+    """The native trainer that fits ``module``, or None (the caller then falls back to its autograd path).
+    ``tc_trunk``: the reference's own network with the whole trunk on the tensor cores (``NativeTrainer.use_tc_trunk``)."""
     from .games.gomoku.policy_value_net import PolicyValueNet, ResNetPolicyValueNet
     if type(module) is PolicyValueNet:
-        return NativeTrainer(module, **kw)
+        t = NativeTrainer(module, **kw)
+        t.use_tc_trunk = bool(tc_trunk)
+        t._repack()
+        return t
     if isinstance(module, ResNetPolicyValueNet):
         W = int(getattr(module, 'board_width', module.board_size))
         if (W == module.board_size and module.board_size <= 15 and module.stem.in_channels == 4

@@ -30,18 +30,25 @@ def _oracle_params(net):
     return {k: v.detach().cpu().double().numpy().copy() for k, v in net.state_dict().items()}
 
 
-@pytest.mark.parametrize('tc_wgrad', [True, False])
+@pytest.mark.parametrize('path', ['tc', 'tc_wgrad', 'f32'])
 @pytest.mark.parametrize('size,B', [(6, 32), (3, 8), (15, 48), (9, 130)])
-def test_forward_loss_and_every_gradient_match_the_oracle(size, B, tc_wgrad):
-    """tc_wgrad: the convolutions' weight gradients on the tensor cores (bf16 high/low pairs, four partial products
-    in fp32 accumulators -- the default up to 15x15) or on the float32 CUDA-core kernel; both within 1e-5."""
+def test_forward_loss_and_every_gradient_match_the_oracle(size, B, path):
+    """path 'tc_wgrad' (the default up to 15x15): forward and data-gradient convolutions on the float32 CUDA-core
+    kernel, the weight gradients on the tensor cores (bf16 high/low pairs, four partial products in fp32 accumulators);
+    'f32': everything on CUDA cores.  Both within 1e-5 of the oracle (relative to each tensor's largest gradient).
+    'tc' (AlphaZeroAgent(trainer='native_tc')): the whole trunk on the tensor cores (16-mantissa-bit pairs).  Its forward
+    outputs are still within 1e-5, but a forward pass that differs by 2e-6 flips the ReLU mask of the pre-activations
+    that close to zero, and a flipped mask is a 100 % error on that gradient element: measured 1e-3 ... 7e-3 of each
+    trunk tensor's largest gradient (heads: 4e-6).  That is the class of ANY lower-precision forward -- PyTorch's default
+    TF32 convolutions, three decimal digits, sit well above it -- so the test holds 'tc' to 2e-2."""
     from oracle import train_oracle
     from rlzero_b200.games.gomoku.policy_value_net import PolicyValueNet
     from rlzero_b200.learn import NativeTrainer
     torch.manual_seed(size)
     net = PolicyValueNet(size).cuda()
     tr = NativeTrainer(net)
-    tr.use_tc_wgrad = tc_wgrad
+    tr.use_tc_trunk, tr.use_tc_wgrad = path == 'tc', path != 'f32'
+    tr._repack()
     x, pi, z = _batch(size, B, 1)
     p = _oracle_params(net)
     logp_o, v_o, _ = train_oracle.forward(p, x.astype(np.float64))
@@ -52,11 +59,14 @@ def test_forward_loss_and_every_gradient_match_the_oracle(size, B, tc_wgrad):
     np.testing.assert_allclose(v.cpu().numpy(), v_o.reshape(-1), atol=1e-5, rtol=0)
     vl, pl, ent = tr.backward(torch.from_numpy(pi).cuda(), torch.from_numpy(z).cuda()).tolist()
     assert abs((vl + pl) - loss_o) < 1e-5 and abs(ent - ent_o) < 1e-5
+    worst = 0.0
     for name, g in tr.grads().items():
         ref = g_o[name]
         err = np.abs(g.cpu().numpy().astype(np.float64) - ref).max()
         scale = max(np.abs(ref).max(), 1e-3)
-        assert err <= 1e-5 * scale + 1e-7, (name, err, scale)      # 1e-5 relative to the tensor's largest gradient
+        worst = max(worst, err / scale)
+        assert err <= (2e-2 if path == 'tc' else 1e-5) * scale + 1e-7, (name, err, scale)
+    print('%s %dx%d B=%d: worst gradient error / largest gradient = %.1e' % (path, size, size, B, worst))
 
 
 @pytest.mark.parametrize('size,B,steps', [(6, 32, 3), (15, 64, 2)])
