@@ -166,5 +166,7 @@ def generation_step(selfplay, agent, n_moves=1, batch_size=512, epochs=1, learne
             idx = torch.randperm(states.shape[0], generator=g)[:batch_size].to(states.device)
             loss, _ = agent.learn(states[idx], pis[idx], zs[idx])
     moved = broadcast_weights(agent.policy_value_net, src=learner, group=group)
+    if getattr(agent, 'trainer', None) is not None:
+        agent.trainer.weights_changed()        # the trainer's own packed copies (non-learner ranks may train later)
     agent.native.refresh_weights()
     return dict(records=n, per_rank=counts, loss=loss, weight_bytes=moved)
