@@ -21,25 +21,32 @@ namespace {
 // C[m][n] = alpha * sum_k A(m,k) * B(k,n) (+ C[m][n] if accumulate), A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]
 // 64x64 tile per block, 16x16 threads, 4x4 outputs per thread, k ascending: deterministic.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int SG_KT = 32;
 __global__ void __launch_bounds__(256)
 rz_sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long long sam, long long sak,
                 const float* __restrict__ B, long long sbk, long long sbn, float* __restrict__ Cm, long long ldc,
                 float alpha, int accumulate) {
-  __shared__ float As[16][64 + 1];
-  __shared__ float Bs[16][64 + 1];
+  __shared__ float As[SG_KT][64 + 1];
+  __shared__ float Bs[SG_KT][64 + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  // consecutive threads read along whichever index is contiguous in memory (coalesced either way); the odd row
+  // length of the shared tiles keeps both write patterns conflict-free
+  const bool a_k = sak == 1, b_k = sbk == 1;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-      const int kk = i >> 6, mm = i & 63;
-      const int m = m0 + mm, n = n0 + mm, k = k0 + kk;
+  for (int k0 = 0; k0 < K; k0 += SG_KT) {
+    for (int i = threadIdx.x; i < SG_KT * 64; i += 256) {
+      int kk = a_k ? (i % SG_KT) : (i >> 6), mm = a_k ? (i / SG_KT) : (i & 63);
+      int m = m0 + mm, k = k0 + kk;
       As[kk][mm] = (m < M && k < K) ? A[(long long)m * sam + (long long)k * sak] : 0.0f;
+      kk = b_k ? (i % SG_KT) : (i >> 6); mm = b_k ? (i / SG_KT) : (i & 63);
+      const int n = n0 + mm;
+      k = k0 + kk;
       Bs[kk][mm] = (n < N && k < K) ? B[(long long)k * sbk + (long long)n * sbn] : 0.0f;
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
+    for (int kk = 0; kk < SG_KT; ++kk) {
       float a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty + 16 * i]; b[i] = Bs[kk][tx + 16 * i]; }
