@@ -531,8 +531,10 @@ int rz_net_conv3x3_tc2_head(const void* act_in, const void* weight, const float*
    products per tap: hi*Whi + lo*Whi + hi*Wlo), 32 = the 1x1 head convolutions read the float32 accumulators instead
    of bf16-rounded activations.  Together: conv3 (64 -> 128) + act_conv1 / val_conv1 of the reference's own
    PolicyValueNet at float32-level accuracy on the tensor cores.  Likewise rz_net_conv3x3_tc2 accepts flags 8 =
-   split output (64 real output channels written as [hi 0..63 | lo 0..63]; needs flag 2) and 64 = float32 output (act_out
-   is float [rows][128]; needs flag 2, no residual), and the `relu` argument of
+   split output (64 real output channels written as [hi 0..63 | lo 0..63]; needs flag 2), 64 = float32 output (act_out
+   is float [rows][128]; needs flag 2, no residual), 128 = only the first 96 input channels are issued, 256 = N = 64 MMAs
+   for a layer with 64 output channels (with flag 8; weight rows 0..31 / 64..95 hold output channels 0..31 / 32..63), and
+   the `relu` argument of
    rz_net_stem_tc / rz_net_stem_tc_planes bit 1 = 32-channel float32-accurate stem: weight rows 0..31 / 32..63 hold
    the high parts / residues of the 32 filters, the output row is [hi 0..31 | lo 0..31 | hi 0..31 | lo 0..31]. */
 int rz_net_conv3x3_tc2_head_ex(const void* act_in, const void* weight, const float* bias, const void* residual,

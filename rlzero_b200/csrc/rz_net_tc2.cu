@@ -161,7 +161,10 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
     // ===== MMA issuer: the whole warp of the leader CTA runs the loop (converged, uniform operands);
     // one elected lane issues each tcgen05.mma / commit =====
     if (leader) {
-      constexpr uint32_t idesc = rz::umma_idesc_bf16(kCG == 2 ? 256 : 128, ACC_N);
+      // flags bit 8 (pair kernel): the layer has only 64 output channels -- N = 64 MMAs (each CTA supplies the first 32
+      // rows of its weight tiles: output channels 0..31 / 32..63), accumulator columns 0..63
+      const uint32_t idesc = (kCG == 2 && (p.flags & 256)) ? rz::umma_idesc_bf16(256, 64)
+                                                           : rz::umma_idesc_bf16(kCG == 2 ? 256 : 128, ACC_N);
       const uint32_t issue = rz::elect_one();
       const uint32_t tmem_u = rz::uniform_u32(tmem_base);
       int it = 0;
@@ -188,11 +191,16 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
             const uint32_t b_addr = smem_base + (uint32_t)(tap * 2 + kw) * B_TILE_BYTES;
             const uint64_t adesc = rz::umma_desc_sw128_bo(a_addr, (p.flags & 1) ? (a_addr >> 7) & 7u : 0u);
             const uint64_t bdesc = rz::umma_desc_sw128(b_addr);
+            // flags bit 7: only the first 96 of the 128 input channels carry data ([hi | lo | hi] of a 32-channel
+            // pair layout; the fourth block would add the lo*lo products): skip the last two k-steps
+            const int n_kk = ((p.flags & 128) && pr == 1) ? 2 : 4;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              if (kCG == 2) rz::umma_bf16_pair_pred(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc, issue);
-              else          rz::umma_bf16_pred(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc, issue);
-              acc = 1;
+              if (kk < n_kk) {
+                if (kCG == 2) rz::umma_bf16_pair_pred(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc, issue);
+                else          rz::umma_bf16_pred(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc, issue);
+                acc = 1;
+              }
             }
           }
         }
@@ -500,6 +508,8 @@ static int conv2_entry(const void* act_in, const void* weight, const float* bias
   RZ_REQUIRE(!(flags & (8 | 16)) || (cta_group == 2 && c_in == 128),
              "rz_net_conv3x3_tc2: the split modes (flags 8 / 16) need the pair kernel and c_in = 128");
   RZ_REQUIRE(!(flags & 8) || (flags & 2) || feat, "rz_net_conv3x3_tc2: split output (flag 8) needs the direct-store epilogue (flag 2)");
+  RZ_REQUIRE(!(flags & 256) || ((flags & 8) && cta_group == 2), "rz_net_conv3x3_tc2: N = 64 (flag 256) goes with the split output (flag 8)");
+  RZ_REQUIRE(!(flags & 128) || !(flags & 16), "rz_net_conv3x3_tc2: flags 128 (96 input channels) and 16 (split input) exclude each other");
   RZ_REQUIRE(!(flags & 64) || ((flags & 2) && cta_group == 2 && !(flags & 8) && !residual && !feat),
              "rz_net_conv3x3_tc2: float32 output (flag 64) needs the direct-store pair kernel, no residual, no split output");
   if (n_boards == 0) return 0;

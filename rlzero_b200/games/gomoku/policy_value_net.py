@@ -355,11 +355,16 @@ class NativeForward(object):
         b1 = torch.zeros(128, device=pdev)
         b1[:32] = c1.bias.detach().float()
         self.stem = dict(w=ws.contiguous().to(dev), b=b1.to(dev), relu=int(bool(r1)) | 2)
-        # conv2: [tap][cout (64 real of 128)][cin = hi | lo | hi | lo of the 32 inputs] x [Whi | Whi | Wlo | Wlo]
+        # conv2: [tap][cout][cin = hi | lo | hi | lo of the 32 inputs] x [Whi | Whi | Wlo | Wlo] (all four partial
+        # products: with the heads scaled up the lo*lo block is what keeps |dv| under 1e-5), N = 64 MMAs (flag 256): each
+        # CTA of the pair supplies the first 32 rows of its weight tiles, so output channels 0..31 sit in rows 0..31 and
+        # 32..63 in rows 64..95
         w2 = c2.weight.detach().double().permute(2, 3, 0, 1).reshape(9, 64, 32)
         hi, lo = self._split(w2)
         wt = torch.zeros(9, 128, 128, dtype=torch.bfloat16, device=pdev)
-        wt[:, :64, 0:32], wt[:, :64, 32:64], wt[:, :64, 64:96], wt[:, :64, 96:128] = hi, hi, lo, lo
+        for rows, sl in ((slice(0, 32), slice(0, 32)), (slice(64, 96), slice(32, 64))):
+            wt[:, rows, 0:32], wt[:, rows, 32:64], wt[:, rows, 64:96], wt[:, rows, 96:128] = (
+                hi[:, sl], hi[:, sl], lo[:, sl], lo[:, sl])
         b2 = torch.zeros(128, device=pdev)
         b2[:64] = c2.bias.detach().float()
         # conv3: [tap][cout 128][cin = Whi (64) | Wlo (64)], three products per tap in the kernel
@@ -407,7 +412,7 @@ class NativeForward(object):
             # conv2 (one K = 128 pass, split output) and conv3 (three products per tap, fp32 features), then the heads
             l2, l3 = self.layers[1], self.layers[2]
             L.check(lib.rz_net_conv3x3_tc2(L.ptr(self.bufs[0]), L.ptr(l2['w']), L.ptr(l2['b']), None, L.ptr(self.bufs[1]),
-                                           n, self.H, self.W, 128, int(l2['relu']), 2, 2 | 8, self.n_ctas, s),
+                                           n, self.H, self.W, 128, int(l2['relu']), 2, 2 | 8 | 256, self.n_ctas, s),
                     'rz_net_conv3x3_tc2')
             L.check(lib.rz_net_conv3x3_tc2_head_ex(
                 L.ptr(self.bufs[1]), L.ptr(l3['w']), L.ptr(l3['b']), None, n, self.H, self.W, 128, int(l3['relu']),

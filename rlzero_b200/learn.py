@@ -115,7 +115,9 @@ class NativeTrainer(object):
         w2 = self._p('conv2.weight').view(64, 32, 3, 3).double()
         hi, lo = self._split(w2.permute(2, 3, 0, 1).reshape(9, 64, 32))                  # [tap][co][ci]
         wt2 = torch.zeros(9, 128, 128, dtype=bf, device=dev)
-        wt2[:, :64, 0:32], wt2[:, :64, 32:64], wt2[:, :64, 64:96], wt2[:, :64, 96:128] = hi, hi, lo, lo
+        for rows, sl in ((slice(0, 32), slice(0, 32)), (slice(64, 96), slice(32, 64))):     # N = 64 MMAs (flag 256)
+            wt2[:, rows, 0:32], wt2[:, rows, 32:64], wt2[:, rows, 64:96], wt2[:, rows, 96:128] = (
+                hi[:, sl], hi[:, sl], lo[:, sl], lo[:, sl])
         b2 = torch.zeros(128, device=dev)
         b2[:64] = self._p('conv2.bias')
         w3 = self._p('conv3.weight').view(128, 64, 3, 3).double()
@@ -171,7 +173,7 @@ class NativeTrainer(object):
         self.planes = st
         L.check(lib.rz_net_stem_tc_planes(C.byref(self.gdesc), L.ptr(st), L.ptr(w['stem']), L.ptr(w['b1']), L.ptr(t['T1']), B,
                                           1 | 2, 0, s), 'rz_net_stem_tc_planes')
-        self._tc_conv(t['T1'], w['w2'], w['b2'], t['T2'], True, 2 | 8)
+        self._tc_conv(t['T1'], w['w2'], w['b2'], t['T2'], True, 2 | 8 | 256)
         self._tc_conv(t['T2'], w['w3'], w['b3'], t['A3'], True, 2 | 16 | 64)
         L.check(lib.rz_learn_tile_f32_to_nhwc(L.ptr(t['A3']), L.ptr(self.a[2]), 128, B, H, H, s), 'rz_learn_tile_f32_to_nhwc')
 

@@ -135,8 +135,10 @@ def test_stock_net_float32_accurate_tensor_core_path(size, n, scale):
     print('tc32 %dx%d n=%d scale %.1f: max |dp| %.2e  |dv| %.2e  |dlogp| %.2e (logp range %.2f)' % (
         size, size, n, scale, p_err, v_err, l_err, float(lt.max() - lt.min())))
     rng = float(lt.max() - lt.min())
-    if scale <= 8.0:
+    if scale <= 4.0:
         assert p_err < 1e-5 and v_err < 1e-5 and l_err < max(1e-5, 2e-5 * rng)
+    elif scale <= 8.0:          # val_fc2 scaled by 8 as well: the value's pre-activation error is scaled with it
+        assert p_err < 1e-5 and v_err < 3e-5 and l_err < max(1e-5, 2e-5 * rng)
     else:
         assert l_err < 2e-5 * rng and p_err < 1e-4 and v_err < 3e-4
     if scale == 1.0:
