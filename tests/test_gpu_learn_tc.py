@@ -279,8 +279,11 @@ def test_bf16_inference_error_with_trained_weights():
     ResNet-10 / 15x15 / 320 steps, max |dp| 1.5e-4 -> 9.9e-4 while the logit range grows 0.5 -> 18:
     profiles/r2_run15_bf16_error_probe.log), but the VALUE output of a trained net leaves the 1e-3 band: up to 4e-3
     here after 40 steps (the value head sums 2*H*W features whose bf16 errors are correlated through the residual
-    stream).  The test therefore asserts what holds -- |dp| < 1e-3, |dv| < 1e-2 -- and DESIGN.md section 3.4 states
-    the bound and the paths for stricter needs (mode 'f32'; 'tc32' for the reference's own network)."""
+    stream), 1e-2 ... 3e-2 once |v| approaches 1.  A PyTorch forward with fp32 arithmetic and bf16 STORAGE at the same
+    places shows the same error, so this is the precision class of bf16 activations, not of these kernels.  The test
+    asserts what holds -- |dp| < 1e-3 throughout, |dv| < 1e-3 at random init, and afterwards |dv| within a factor of
+    two of that emulation's -- and DESIGN.md section 3.4 states the bound and the paths for stricter needs (mode 'f32';
+    'tc32' for the reference's own network)."""
     import importlib.util
     import os
     spec = importlib.util.spec_from_file_location(
@@ -293,7 +296,11 @@ def test_bf16_inference_error_with_trained_weights():
     assert trained and trained[-1]['steps'] == 120
     assert trained[-1]['loss_last'] < trained[0]['loss_first'] - 0.3
     assert trained[-1]['max_logit_range'] > 2.5 * recs[0]['max_logit_range']
-    print('bf16 vs fp32 after training:', [(r['steps'], '%.1e' % r['max_dp'], '%.1e' % r['max_dv']) for r in recs])
+    print('bf16 vs fp32 after training (steps, |dp|, |dv|, emulated |dv|):',
+          [(r['steps'], '%.1e' % r['max_dp'], '%.1e' % r['max_dv'], '%.1e' % r['torch_bf16_storage_emulation_max_dv'])
+           for r in recs])
     assert recs[0]['max_dp'] < 1e-3 and recs[0]['max_dv'] < 1e-3          # random init: the north star's bound
     for r in recs:
-        assert r['max_dp'] < 1e-3 and r['max_dv'] < 1e-2, r
+        emu = r['torch_bf16_storage_emulation_max_dv']
+        assert r['max_dp'] < 1e-3 and r['max_dv'] < 0.1, r
+        assert r['max_dv'] <= 2.0 * emu + 1e-3 and emu <= 2.0 * r['max_dv'] + 1e-3, r
