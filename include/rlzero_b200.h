@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RZ_ABI_VERSION 8
+#define RZ_ABI_VERSION 9
 #define RZ_MAX_BOARD 19          /* rows live one per lane; A <= 362 (19x19 Go incl. the pass) */
 #define RZ_META_STRIDE 12
 #define RZ_GO_HIST 14            /* history planes a Go position carries besides the current board */
@@ -514,7 +514,13 @@ int rz_net_conv3x3_tc(const void* act_in, const void* weight, const float* bias,
    and each 128-position activation tile is loaded once with its 17-row halo; the 9 taps are
    row-shifted UMMA descriptors on that tile.  cta_group = 1 runs the same data path on single CTAs
    (each computes 64 of the 128 output channels).  flags bit 0: set the base-offset field of the
-   shifted descriptors.  n_ctas <= 0 picks 148. */
+   shifted descriptors.  n_ctas <= 0 picks 148.
+   Programmatic dependent launch: this kernel, rev. 3, the stems, the heads and the tree kernels of a wave are launched
+   with cudaLaunchAttributeProgrammaticStreamSerialization and call griddepcontrol.wait before they read or write
+   anything another kernel of the stream touches (RZ_PDL=0 in the environment turns it off).  flags bit 9 (512; for
+   rev. 3: bit 1 of `relu`) = STATIC WEIGHTS: weight and bias are fetched BEFORE that wait, under the tail of the
+   previous kernel -- the caller guarantees that the kernel launched immediately before on the stream does not
+   write them (the search's forward pass: weights are packed at refresh_weights, which synchronises). */
 int rz_net_conv3x3_tc2(const void* act_in, const void* weight, const float* bias, const void* residual,
                        void* act_out, int n_boards, int board_size, int board_cols, int c_in, int relu,
                        int cta_group, int flags, int n_ctas, void* stream);
@@ -541,6 +547,22 @@ int rz_net_conv3x3_tc2_head_ex(const void* act_in, const void* weight, const flo
                                int n_boards, int board_size, int board_cols, int c_in, int relu, int flags,
                                const float* w1x1_host, const float* b1x1_host, float* feat, int n_ctas,
                                void* stream);
+/* small-batch latency path: the WHOLE 128-channel trunk of a board in one launch (the single-position evaluation of a
+   sequential search, rlzero/mcts/alphazero_mcts.py:73-94).  One CTA pair per board keeps the activation in shared
+   memory across all layers (ping-pong halo tiles written by the epilogue, the rows next to the seam between the two
+   CTAs also into the peer's tile through distributed shared memory); the weights of all layers stream through a ring
+   of taps; the MMAs, their order and the epilogue arithmetic are those of rz_net_conv3x3_tc2, so the results are
+   bit-identical to n_layers launches of it followed by the fused-heads epilogue of rz_net_conv3x3_tc2_head.
+   act_in bf16 [n][256][128] (the stem's output); weights bf16 [n_layers][9][128][128] (layer, tap, out channel, in
+   channel); biases f32 [n_layers][128]; bit l of relu_mask: ReLU after layer l; bit l of res_mask: layer l adds the
+   input of layer l-1 (the block's skip connection) before its ReLU; feat f32 [n][6][256] as _tc2_head.  n_layers <= 24.
+   Weights and biases are STATIC in the sense of flag 512 above. */
+int rz_net_trunk_small(const void* act_in, const void* weights, const float* biases, int n_layers,
+                       unsigned relu_mask, unsigned res_mask, int n_boards, int board_size, int board_cols,
+                       const float* w1x1_host, const float* b1x1_host, float* feat, void* stream);
+/* profiling aid: rz_net_trunk_small writes four %globaltimer stamps per layer of board 0 (inputs ready / MMAs issued /
+   accumulator complete / layer stored) into this device buffer of 4 * n_layers uint64; NULL (the default) = off. */
+int rz_debug_set_probe(void* device_buffer);
 /* revision 3 of the convolution: the same data path for any row stride of the padded position
    layout (row = board*S*S + y*S + x; S = row_stride = 8 for boards up to 7x7 such as Connect Four 6x7, 16 up
    to 15x15, 20 up to 19x19), tiles of 128 rows that may straddle boards (S = 20) or hold two boards (S = 8), a 3-slot ring of k-block halo tiles and a half-staged TMA-store

@@ -85,8 +85,51 @@ static inline int rz_row_stride(int H, int W, int requested) {
   return m <= 7 ? 8 : (m <= 15 ? 16 : (m <= 19 ? 20 : 0));
 }
 
+// ---- programmatic dependent launch ------------------------------------------
+// The kernels of one wave run back to back on one stream.  A kernel launched with the programmatic-serialization
+// attribute may start (barrier / TMEM set-up, loads of operands no kernel of the wave writes) while its predecessor is
+// still running; rz::grid_dep_wait() blocks until every earlier grid has completed and flushed.  Every kernel launched
+// this way calls grid_dep_wait() BEFORE it touches anything another kernel of the stream reads or writes and only THEN
+// grid_dep_launch(): a dependent can therefore start no earlier than its predecessor's own wait has returned, so its
+// set-up phase sees everything that was written two or more kernels back.  RZ_PDL=0 in the environment turns the
+// attribute off (the device-side instructions are then no-ops).
+bool rz_pdl_enabled();
+// timing probe (rz_debug_set_probe; null in production): kernels that support it write %globaltimer stamps there
+extern unsigned long long* rz_probe_buffer;
+static inline int rz_pdl_attr(cudaLaunchAttribute* a) {
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = rz_pdl_enabled() ? 1 : 0;
+  return 1;
+}
+
 // ---- device helpers --------------------------------------------------------
 #ifdef __CUDACC__
+
+// <<<grid, block, smem, stream>>> with the programmatic-serialization attribute.  The kernel must begin with
+// rz::grid_dep_wait(); rz::grid_dep_launch();  Errors surface through cudaGetLastError() (RZ_LAUNCH_CHECK).
+template <typename... KArgs, typename... Args>
+static inline void rz_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = rz_pdl_attr(&attr[0]);
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+namespace rz {
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+}  // namespace rz
 
 __device__ __forceinline__ int rz_lane() { return threadIdx.x & 31; }
 

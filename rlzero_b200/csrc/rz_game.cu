@@ -194,6 +194,8 @@ rz_gomoku_encode_tc_kernel(rz_game_desc gd, const uint32_t* rows, const int32_t*
 template <class GM>
 __global__ void __launch_bounds__(RZ_GAME_THREADS)
 rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* value) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);     // a leaf slot (tree*K + k in leaf-parallel mode)
   if (g >= t.n_trees * (t.leaves_per_tree > 1 ? t.leaves_per_tree : 1)) return;
   if (t.depth[g] < 0) return;
@@ -245,6 +247,8 @@ rz_eval_closed_form_kernel(rz_tree_desc t, int eval_id, float* prior, float* val
 __global__ void __launch_bounds__(RZ_GAME_THREADS)
 rz_eval_rollout_kernel(rz_tree_desc t, int mode, unsigned long long seed, int n_limit, float* prior,
                        float* value) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   if (t.depth[g] < 0) return;
@@ -316,6 +320,8 @@ template <class GM>
 __global__ void __launch_bounds__(RZ_GAME_THREADS)
 rz_eval_rollout_dm_kernel(rz_tree_desc t, int n_rollouts, unsigned long long seed, int n_limit, float* prior,
                           double* ret64) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   const int g = blockIdx.x * RZ_GAME_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   if (t.depth[g] < 0) return;
@@ -482,8 +488,7 @@ extern "C" int rz_eval_rollout(const rz_tree_desc* t, int mode, unsigned long lo
   RZ_REQUIRE(t->game.game_type != RZ_GAME_GO, "rz_eval_rollout: not implemented for Go");
   RZ_REQUIRE(t->leaves_per_tree <= 1, "rz_eval_rollout: leaf-parallel waves are not supported by the rollout evaluator");
   if (t->n_trees == 0) return 0;
-  rz_eval_rollout_kernel<<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
-                           (cudaStream_t)stream>>>(*t, mode, seed, n_limit, prior, value);
+  rz_launch_pdl(rz_eval_rollout_kernel, rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream, *t, mode, seed, n_limit, prior, value);
   RZ_LAUNCH_CHECK("rz_eval_rollout");
   return 0;
 }
@@ -496,11 +501,9 @@ extern "C" int rz_eval_closed_form(const rz_tree_desc* t, int eval_id, float* pr
   if (t->n_trees == 0) return 0;
   const int n_leaves = t->n_trees * (t->leaves_per_tree > 1 ? t->leaves_per_tree : 1);
   if (t->game.game_type == RZ_GAME_GO)
-    rz_eval_closed_form_kernel<rz_go_game><<<rz_grid(n_leaves, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
-                                             (cudaStream_t)stream>>>(*t, eval_id, prior, value);
+    rz_launch_pdl(rz_eval_closed_form_kernel<rz_go_game>, rz_grid(n_leaves, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream, *t, eval_id, prior, value);
   else
-    rz_eval_closed_form_kernel<rz_line_game><<<rz_grid(n_leaves, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
-                                               (cudaStream_t)stream>>>(*t, eval_id, prior, value);
+    rz_launch_pdl(rz_eval_closed_form_kernel<rz_line_game>, rz_grid(n_leaves, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream, *t, eval_id, prior, value);
   RZ_LAUNCH_CHECK("rz_eval_closed_form");
   return 0;
 }
@@ -516,11 +519,9 @@ extern "C" int rz_eval_rollout_dm(const rz_tree_desc* t, int n_rollouts, unsigne
   RZ_REQUIRE(t->leaves_per_tree <= 1, "rz_eval_rollout_dm: leaf-parallel waves are not supported by the rollout evaluator");
   if (t->n_trees == 0) return 0;
   if (t->game.game_type == RZ_GAME_GO)
-    rz_eval_rollout_dm_kernel<rz_go_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
-                                            (cudaStream_t)stream>>>(*t, n_rollouts, seed, n_limit, prior, ret64);
+    rz_launch_pdl(rz_eval_rollout_dm_kernel<rz_go_game>, rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream, *t, n_rollouts, seed, n_limit, prior, ret64);
   else
-    rz_eval_rollout_dm_kernel<rz_line_game><<<rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0,
-                                              (cudaStream_t)stream>>>(*t, n_rollouts, seed, n_limit, prior, ret64);
+    rz_launch_pdl(rz_eval_rollout_dm_kernel<rz_line_game>, rz_grid(t->n_trees, RZ_GAME_WARPS), RZ_GAME_THREADS, 0, (cudaStream_t)stream, *t, n_rollouts, seed, n_limit, prior, ret64);
   RZ_LAUNCH_CHECK("rz_eval_rollout_dm");
   return 0;
 }

@@ -111,6 +111,8 @@ rz_mz_root_kernel(rz_mz_desc t, const float* __restrict__ logp, const uint8_t* _
 // select_child down to the first unexpanded child (run_mcts inner loop)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(RZ_MZ_THREADS) rz_mz_select_kernel(rz_mz_desc t) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   const int g = blockIdx.x * RZ_MZ_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   const int lane = rz_lane(), AS = t.action_stride, iters = AS >> 5;
@@ -173,6 +175,8 @@ __global__ void __launch_bounds__(RZ_MZ_THREADS) rz_mz_select_kernel(rz_mz_desc 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(RZ_MZ_THREADS)
 rz_mz_expand_backup_kernel(rz_mz_desc t, const float* __restrict__ logp, const float* __restrict__ value) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   const int g = blockIdx.x * RZ_MZ_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   const int depth = t.depth[g];
@@ -274,7 +278,7 @@ extern "C" int rz_mz_root(const rz_mz_desc* t, const float* logp, const uint8_t*
 extern "C" int rz_mz_select(const rz_mz_desc* t, void* stream) {
   if (rz_check_mz(t, "rz_mz_select")) return -1;
   if (t->n_trees == 0) return 0;
-  rz_mz_select_kernel<<<rz_mz_grid(t->n_trees), RZ_MZ_THREADS, 0, (cudaStream_t)stream>>>(*t);
+  rz_launch_pdl(rz_mz_select_kernel, rz_mz_grid(t->n_trees), RZ_MZ_THREADS, 0, (cudaStream_t)stream, *t);
   RZ_LAUNCH_CHECK("rz_mz_select");
   return 0;
 }
@@ -283,7 +287,7 @@ extern "C" int rz_mz_expand_backup(const rz_mz_desc* t, const float* logp, const
   if (rz_check_mz(t, "rz_mz_expand_backup")) return -1;
   RZ_REQUIRE(logp && value, "rz_mz_expand_backup: null network output");
   if (t->n_trees == 0) return 0;
-  rz_mz_expand_backup_kernel<<<rz_mz_grid(t->n_trees), RZ_MZ_THREADS, 0, (cudaStream_t)stream>>>(*t, logp, value);
+  rz_launch_pdl(rz_mz_expand_backup_kernel, rz_mz_grid(t->n_trees), RZ_MZ_THREADS, 0, (cudaStream_t)stream, *t, logp, value);
   RZ_LAUNCH_CHECK("rz_mz_expand_backup");
   return 0;
 }

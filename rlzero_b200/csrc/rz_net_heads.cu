@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256)
 rz_conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
                       const float* __restrict__ bias, const float* __restrict__ residual,
                       float* __restrict__ out, int H, int Cin, int Cout, int relu) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   extern __shared__ float s_in[];  // [HW][Cin]
   const int b = blockIdx.x, HW = H * H;
   const float* ib = in + (size_t)b * HW * Cin;
@@ -61,6 +63,8 @@ __global__ void __launch_bounds__(256)
 rz_conv3x3_f32_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w,
                             const float* __restrict__ bias, const float* __restrict__ residual,
                             float* __restrict__ out, int H, int Cin, int Cout, int relu) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   extern __shared__ float s_in[];  // [HW][Cin]
   const int b = blockIdx.x, HW = H * H;
   const float* ib = in + (size_t)b * HW * Cin;
@@ -223,6 +227,8 @@ enum { SRC_F32 = 0, SRC_TILE = 1, SRC_FEAT = 2 };
 
 template <int kSrc>
 __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsParams p) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   extern __shared__ __align__(16) float sm[];
   const int HW = p.HW;
   float* s_f = sm;                              // [6*HW][NB]  k-major features (policy 4*HW, then value 2*HW)
@@ -386,6 +392,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) rz_heads_kernel(const HeadsPa
 // fused last trunk layer writes from its epilogue (same summation order, conv1x1_position).  Padding squares hold
 // relu(bias), as there (their activations are zero); the FC weights are zero at those columns.
 __global__ void __launch_bounds__(256) rz_head_features_kernel(const HeadsParams p, float* __restrict__ feat) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   __shared__ __align__(16) float s_w[6 * HEAD_C];
   for (int i = threadIdx.x; i < 6 * HEAD_C; i += blockDim.x) s_w[i] = p.w1x1[i];
   __syncthreads();
@@ -410,7 +418,7 @@ template <int kSrc>
 int heads_launch(const HeadsParams& p, size_t smem, int grid, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(rz_heads_kernel<kSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { rz_set_error("rz_net_heads: smem attribute: %s", cudaGetErrorString(e)); return -2; }
-  rz_heads_kernel<kSrc><<<grid, HEAD_THREADS, smem, stream>>>(p);
+  rz_launch_pdl(rz_heads_kernel<kSrc>, grid, HEAD_THREADS, smem, stream, p);
   RZ_LAUNCH_CHECK("rz_net_heads");
   return 0;
 }
@@ -449,13 +457,13 @@ extern "C" int rz_net_conv3x3_f32(const float* in, const float* weight, const fl
     const int tiles = (c_out >> 2) * ((board_size * board_size + tp - 1) / tp);
     if (split > (tiles + 255) / 256) split = (tiles + 255) / 256;
     if (tp == 1)
-      rz_conv3x3_f32_tiled_kernel<1><<<dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream>>>(
+      rz_launch_pdl(rz_conv3x3_f32_tiled_kernel<1>, dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream, 
           in, weight, bias, residual, out, board_size, c_in, c_out, relu);
     else
-      rz_conv3x3_f32_tiled_kernel<4><<<dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream>>>(
+      rz_launch_pdl(rz_conv3x3_f32_tiled_kernel<4>, dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream, 
           in, weight, bias, residual, out, board_size, c_in, c_out, relu);
   } else {
-    rz_conv3x3_f32_kernel<<<dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream>>>(
+    rz_launch_pdl(rz_conv3x3_f32_kernel, dim3((unsigned)n_boards, (unsigned)split), 256, smem, (cudaStream_t)stream, 
         in, weight, bias, residual, out, board_size, c_in, c_out, relu);
   }
   RZ_LAUNCH_CHECK("rz_net_conv3x3_f32");
@@ -505,7 +513,7 @@ extern "C" int rz_net_head_features(const rz_heads_desc* h, const void* act, flo
   p.act = act; p.w1x1 = h->w1x1; p.b1x1 = h->b1x1;
   p.n_boards = n_boards; p.H = h->board_size; p.W = W; p.HW = h->board_size * W; p.S = S; p.P = S * S;
   const long long total = (long long)n_boards * p.P;
-  rz_head_features_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, feat);
+  rz_launch_pdl(rz_head_features_kernel, (unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream, p, feat);
   RZ_LAUNCH_CHECK("rz_net_head_features");
   return 0;
 }

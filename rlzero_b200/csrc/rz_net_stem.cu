@@ -44,6 +44,8 @@ struct StemParams {
 template <bool kPlanes, int kS>
 __global__ void __launch_bounds__(STEM_THREADS)
 rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   static_assert(kS * kS >= 64, "a 128-row tile must not touch more than two boards");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (rz::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -247,6 +249,8 @@ template <bool kPlanes, int kS>
 __global__ void __launch_bounds__(STEM_THREADS)
 rz_stem_go_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                      const GoStemParams p) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (rz::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* al = smem_raw + (base - rz::smem_u32(smem_raw));
@@ -435,14 +439,14 @@ static int stem_launch(const rz_game_desc* g, const uint32_t* rows, const int32_
   if (ctas > p.n_tiles) ctas = p.n_tiles;
   cudaStream_t st = (cudaStream_t)stream;
   if (S == 8) {
-    if (planes) rz_stem_tc_kernel<true, 8><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
-    else        rz_stem_tc_kernel<false, 8><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
+    if (planes) rz_launch_pdl(rz_stem_tc_kernel<true, 8>, ctas, STEM_THREADS, STEM_SMEM, st, tmap_w, p);
+    else        rz_launch_pdl(rz_stem_tc_kernel<false, 8>, ctas, STEM_THREADS, STEM_SMEM, st, tmap_w, p);
   } else if (S == 16) {
-    if (planes) rz_stem_tc_kernel<true, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
-    else        rz_stem_tc_kernel<false, 16><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
+    if (planes) rz_launch_pdl(rz_stem_tc_kernel<true, 16>, ctas, STEM_THREADS, STEM_SMEM, st, tmap_w, p);
+    else        rz_launch_pdl(rz_stem_tc_kernel<false, 16>, ctas, STEM_THREADS, STEM_SMEM, st, tmap_w, p);
   } else {
-    if (planes) rz_stem_tc_kernel<true, 20><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
-    else        rz_stem_tc_kernel<false, 20><<<ctas, STEM_THREADS, STEM_SMEM, st>>>(tmap_w, p);
+    if (planes) rz_launch_pdl(rz_stem_tc_kernel<true, 20>, ctas, STEM_THREADS, STEM_SMEM, st, tmap_w, p);
+    else        rz_launch_pdl(rz_stem_tc_kernel<false, 20>, ctas, STEM_THREADS, STEM_SMEM, st, tmap_w, p);
   }
   RZ_LAUNCH_CHECK("rz_net_stem_tc");
   return 0;
@@ -496,11 +500,11 @@ static int go_stem_launch(const rz_game_desc* g, const uint32_t* rows, const uin
   if (ctas > p.n_tiles) ctas = p.n_tiles;
   cudaStream_t st = (cudaStream_t)stream;
   if (S == 16) {
-    if (planes) rz_stem_go_tc_kernel<true, 16><<<ctas, STEM_THREADS, GO_STEM_SMEM, st>>>(tmap_w, tmap_out, p);
-    else        rz_stem_go_tc_kernel<false, 16><<<ctas, STEM_THREADS, GO_STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+    if (planes) rz_launch_pdl(rz_stem_go_tc_kernel<true, 16>, ctas, STEM_THREADS, GO_STEM_SMEM, st, tmap_w, tmap_out, p);
+    else        rz_launch_pdl(rz_stem_go_tc_kernel<false, 16>, ctas, STEM_THREADS, GO_STEM_SMEM, st, tmap_w, tmap_out, p);
   } else {
-    if (planes) rz_stem_go_tc_kernel<true, 20><<<ctas, STEM_THREADS, GO_STEM_SMEM, st>>>(tmap_w, tmap_out, p);
-    else        rz_stem_go_tc_kernel<false, 20><<<ctas, STEM_THREADS, GO_STEM_SMEM, st>>>(tmap_w, tmap_out, p);
+    if (planes) rz_launch_pdl(rz_stem_go_tc_kernel<true, 20>, ctas, STEM_THREADS, GO_STEM_SMEM, st, tmap_w, tmap_out, p);
+    else        rz_launch_pdl(rz_stem_go_tc_kernel<false, 20>, ctas, STEM_THREADS, GO_STEM_SMEM, st, tmap_w, tmap_out, p);
   }
   RZ_LAUNCH_CHECK("rz_net_stem_go_tc");
   return 0;

@@ -99,6 +99,11 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
   const bool leader = rank == 0;
   const int worker = blockIdx.x >> 1, n_workers = gridDim.x >> 1;
 
+  // flags bit 9: the weights and the bias are not written by any kernel near this one on the stream (the search's
+  // network forward): they are fetched BEFORE the grid dependency resolves, i.e. while the previous layer is still
+  // running (rz_common.cuh, programmatic dependent launch).  Otherwise the kernel waits first.
+  const bool early_w = (p.flags & 512) != 0;
+  if (!early_w) rz::grid_dep_wait();
   if (threadIdx.x == 0 && (smem_base & 1023u)) __trap();  // layout below assumes a 1024-byte base
   if (warp == 0 && lane == 0) {
     rz::tma_prefetch_desc(&tmap_act);
@@ -128,6 +133,8 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
     return (kCG == 2) ? item * 256 + (int)rank * TILE_M : item * TILE_M;
   };
 
+  if (early_w && threadIdx.x != 0) rz::grid_dep_wait();   // thread 0 (the producer) first requests the weights
+  if (threadIdx.x != 0) rz::grid_dep_launch();
   if (warp == 0) {
     // ===== TMA producer (every CTA loads its own operands; completion is credited to the leader) =====
     if (lane == 0) {
@@ -142,6 +149,8 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
           }
         }
       };
+      if (early_w) { if (worker < p.n_items) load_weights(); rz::grid_dep_wait(); }
+      rz::grid_dep_launch();
       int it = 0;
       for (int item = worker; item < p.n_items; item += n_workers, ++it) {
         const int buf = it & 1;
@@ -154,7 +163,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
           if (kCG == 2) rz::tma_load_2d_pair(dst, &tmap_act, l_afull, kb * 64, row0);
           else          rz::tma_load_2d(dst, &tmap_act, l_afull, kb * 64, row0);
         }
-        if (it == 0) load_weights();      // right behind the first activation tile
+        if (it == 0 && !early_w) load_weights();      // right behind the first activation tile
       }
     }
   } else if (warp == 1) {
@@ -480,13 +489,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, 
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 1 + rz_pdl_attr(&attr[1]);
   cudaError_t e = cudaLaunchKernelEx(&cfg, rz_conv3x3_tc2_kernel<kCG, kHead, kDirect>, ta, tw, to, p, head);
   if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc2: launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
@@ -568,7 +577,7 @@ extern "C" int rz_net_conv3x3_tc2_head_ex(const void* act_in, const void* weight
                                           int c_in, int relu, int flags, const float* w1x1_host,
                                           const float* b1x1_host, float* feat, int n_ctas, void* stream) {
   RZ_REQUIRE(w1x1_host && b1x1_host && feat, "rz_net_conv3x3_tc2_head_ex: null head argument");
-  RZ_REQUIRE((flags & ~(16 | 32)) == 0, "rz_net_conv3x3_tc2_head_ex: flags %d (16 = split input, 32 = float32 features)", flags);
+  RZ_REQUIRE((flags & ~(16 | 32 | 512)) == 0, "rz_net_conv3x3_tc2_head_ex: flags %d (16 = split input, 32 = float32 features, 512 = static weights)", flags);
   return conv2_entry(act_in, weight, bias, residual, nullptr, n_boards, board_size, board_cols, c_in, relu, 2, flags, n_ctas,
                      w1x1_host, b1x1_host, feat, stream);
 }

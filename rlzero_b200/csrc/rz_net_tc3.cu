@@ -56,6 +56,7 @@ struct Conv3Params {
   int total_rows;                  // n_boards * P (rows beyond it are padding)
   int H, W;
   int relu;
+  int early_w;
 };
 
 struct HeadTaps3 {
@@ -92,6 +93,10 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
   const bool leader = rank == 0;
   const int worker = blockIdx.x >> 1, n_workers = gridDim.x >> 1;
 
+  // static weights (relu bit 1 of the entry points): weights and bias are fetched before the grid dependency resolves,
+  // i.e. under the tail of the previous layer (rz_common.cuh, programmatic dependent launch)
+  const bool early_w = p.early_w != 0;
+  if (!early_w) rz::grid_dep_wait();
   if (threadIdx.x == 0 && (smem_base & 1023u)) __trap();
   if (warp == 0 && lane == 0) {
     rz::tma_prefetch_desc(&tmap_act);
@@ -115,6 +120,8 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
   rz::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  if (early_w && threadIdx.x != 0) rz::grid_dep_wait();   // thread 0 (the producer) first requests the weights
+  if (threadIdx.x != 0) rz::grid_dep_launch();
   if (warp == 0) {
     // ===== TMA producer: one (tile, k-block) halo tile per ring slot; the weights once, k-block-major, right behind
     // the first tile's two activation k-blocks =====
@@ -127,6 +134,8 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
                                kb * 64, tap * 128 + (int)rank * 64);
         }
       };
+      if (early_w) { if (worker < p.n_items) { load_weights(0); load_weights(1); } rz::grid_dep_wait(); }
+      rz::grid_dep_launch();
       int u = 0;   // running (tile, k-block) index
       for (int item = worker; item < p.n_items; item += n_workers) {
         const int row0 = item * 256 + (int)rank * TILE_M - G::HALO;
@@ -136,7 +145,7 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
           if (leader) rz::mbar_expect_tx(bar_afull + 8 * slot, (uint32_t)(2 * G::SLOT_BYTES));
           rz::tma_load_2d_pair(ring + (uint32_t)slot * G::SLOT_BYTES, &tmap_act,
                                rz::mapa_shared(bar_afull + 8 * slot, 0), kb * 64, row0);
-          if (u < 2) load_weights(u);     // first tile only: k-block u's weights right behind its activations
+          if (u < 2 && !early_w) load_weights(u);     // first tile only: k-block u's weights right behind its activations
         }
       }
     }
@@ -367,13 +376,13 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to,
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Geo<kS>::SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 1 + rz_pdl_attr(&attr[1]);
   cudaError_t e = cudaLaunchKernelEx(&cfg, rz_conv3x3_tc3_kernel<kS, kHead>, ta, tw, to, p, head);
   if (e != cudaSuccess) { rz_set_error("rz_net_conv3x3_tc3: launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
@@ -409,7 +418,8 @@ static int conv3_entry(const void* act_in, const void* weight, const float* bias
   p.total_rows = (int)total;
   p.H = board_rows;
   p.W = board_cols;
-  p.relu = relu;
+  p.relu = relu & 1;
+  p.early_w = (relu >> 1) & 1;
   int ctas = n_ctas > 0 ? n_ctas : 148;
   ctas &= ~1;
   if (ctas < 2) ctas = 2;

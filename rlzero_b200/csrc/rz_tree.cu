@@ -222,6 +222,8 @@ __device__ __forceinline__ void rz_select_one(const rz_tree_desc& t, const int g
 
 template <class GM, bool DM>
 __global__ void __launch_bounds__(RZ_TREE_THREADS) rz_select_kernel(rz_tree_desc t) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   const int lane = rz_lane();
@@ -543,6 +545,8 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
                         float noise_eps, float noise_alpha,
                         unsigned long long seed, long long global_offset,
                         const double* __restrict__ noise64, const double* __restrict__ prior64) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
   const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
   if (g >= t.n_trees) return;
   const rz_geom q = rz_geom_of(t.game);
@@ -997,10 +1001,10 @@ extern "C" int rz_tree_select(const rz_tree_desc* t, void* stream) {
   const dim3 grid = rz_tree_grid(t->n_trees);
   cudaStream_t st = (cudaStream_t)stream;
   const bool go = t->game.game_type == RZ_GAME_GO, dm = t->flavour == RZ_FLAVOUR_DEEPMIND;
-  if (go && dm) rz_select_kernel<rz_go_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(*t);
-  else if (go) rz_select_kernel<rz_go_game, false><<<grid, RZ_TREE_THREADS, 0, st>>>(*t);
-  else if (dm) rz_select_kernel<rz_line_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(*t);
-  else rz_select_kernel<rz_line_game, false><<<grid, RZ_TREE_THREADS, 0, st>>>(*t);
+  if (go && dm) rz_launch_pdl(rz_select_kernel<rz_go_game, true>, grid, RZ_TREE_THREADS, 0, st, *t);
+  else if (go) rz_launch_pdl(rz_select_kernel<rz_go_game, false>, grid, RZ_TREE_THREADS, 0, st, *t);
+  else if (dm) rz_launch_pdl(rz_select_kernel<rz_line_game, true>, grid, RZ_TREE_THREADS, 0, st, *t);
+  else rz_launch_pdl(rz_select_kernel<rz_line_game, false>, grid, RZ_TREE_THREADS, 0, st, *t);
   RZ_LAUNCH_CHECK("rz_tree_select");
   return 0;
 }
@@ -1051,10 +1055,10 @@ static int rz_expand_backup_launch(const rz_tree_desc* t, const float* prior, in
   cudaStream_t st = (cudaStream_t)stream;
   const bool go = t->game.game_type == RZ_GAME_GO, dm = t->flavour == RZ_FLAVOUR_DEEPMIND;
 #define RZ_EB_ARGS *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset, noise64, prior64
-  if (go && dm) rz_expand_backup_kernel<rz_go_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
-  else if (go) rz_expand_backup_kernel<rz_go_game, false><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
-  else if (dm) rz_expand_backup_kernel<rz_line_game, true><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
-  else rz_expand_backup_kernel<rz_line_game, false><<<grid, RZ_TREE_THREADS, 0, st>>>(RZ_EB_ARGS);
+  if (go && dm) rz_launch_pdl(rz_expand_backup_kernel<rz_go_game, true>, grid, RZ_TREE_THREADS, 0, st, RZ_EB_ARGS);
+  else if (go) rz_launch_pdl(rz_expand_backup_kernel<rz_go_game, false>, grid, RZ_TREE_THREADS, 0, st, RZ_EB_ARGS);
+  else if (dm) rz_launch_pdl(rz_expand_backup_kernel<rz_line_game, true>, grid, RZ_TREE_THREADS, 0, st, RZ_EB_ARGS);
+  else rz_launch_pdl(rz_expand_backup_kernel<rz_line_game, false>, grid, RZ_TREE_THREADS, 0, st, RZ_EB_ARGS);
 #undef RZ_EB_ARGS
   RZ_LAUNCH_CHECK("rz_tree_expand_backup");
   return 0;

@@ -221,7 +221,10 @@ class NativeForward(object):
         # rz_net_conv3x3_tc2 flags: bit 1 = direct-store epilogue, the default (853 k vs 840 k sims/s sustained on
         # one box, profiles/r1_run24_bench_ab.log; bit-identical tensors); RZ_CONV_FLAGS=0 selects the staged TMA store
         import os
-        self.conv_flags = int(os.environ.get('RZ_CONV_FLAGS', '2'))
+        # boards up to which the one-launch trunk of rz_net_trunk_small.cu is used (one CTA pair per board: 74 pairs on
+        # 148 SMs); RZ_SMALL_BATCH_MAX=0 turns it off
+        self.small_batch_max = int(os.environ.get('RZ_SMALL_BATCH_MAX', '74'))
+        self.conv_flags = int(os.environ.get('RZ_CONV_FLAGS', '514'))   # 2 | 512: direct store, static weights
         self.max_batch = 0
         self.refresh_weights()
         self._alloc(max_batch)
@@ -266,6 +269,21 @@ class NativeForward(object):
                 wd = w.permute(2, 3, 1, 0).reshape(9, cin, cout).float().contiguous().to(dev)  # [tap][cin][cout]
             self.layers.append(dict(w=wd, b=b.float().contiguous().to(dev), cin=cin_p, cout=cout,
                                     skip=skip, relu=bool(relu)))
+        # small-batch latency path (rz_net_trunk_small.cu): the 128 -> 128 layers behind the stem in one stacked buffer
+        # [layer][tap][cout][cin]; the per-layer tensors become views of it, so both paths read the same bytes
+        self.trunk_small = None
+        if (self.mode == 'tc' and self.S == 16 and 2 <= len(self.layers) <= 25
+                and all(l['cin'] == 128 and l['cout'] == 128 for l in self.layers[1:])
+                and self.layers[1]['skip'] is None):
+            tail = self.layers[1:]
+            wst = torch.stack([l['w'] for l in tail]).contiguous()
+            bst = torch.stack([l['b'] for l in tail]).contiguous()
+            relu_mask = res_mask = 0
+            for i, l in enumerate(tail):
+                l['w'], l['b'] = wst[i], bst[i]
+                relu_mask |= int(bool(l['relu'])) << i
+                res_mask |= int(l['skip'] is not None) << i
+            self.trunk_small = dict(w=wst, b=bst, n=len(tail), relu_mask=relu_mask, res_mask=res_mask)
         # fused encoder + stem (rz_net_stem.cu): weight [cout][k = tap*4 + plane], k padded to 64
         conv0 = m.trunk_layers()[0][0]
         if self.mode != 'tc32':
@@ -321,7 +339,9 @@ class NativeForward(object):
             wlo = (wall - whi.float()).to(torch.bfloat16)
             self.heads['wtc_hi'] = whi.contiguous().to(dev)
             self.heads['wtc_lo'] = wlo.contiguous().to(dev)
-        # host copies of the 1x1 filters: they travel in the launch parameters of the fused last layer
+        # host copies of the 1x1 filters: they travel in the launch parameters of the fused last layer.  (The .cpu()
+        # below also synchronises the stream: every pack kernel above has finished before a forward pass can be
+        # launched, which the static-weights flag of the convolutions relies on -- include/rlzero_b200.h.)
         self.w1x1_host = np.ascontiguousarray(w1.float().cpu().numpy().reshape(-1))
         self.b1x1_host = np.ascontiguousarray(b1.float().cpu().numpy().reshape(-1))
         self.weights_version += 1
@@ -412,14 +432,29 @@ class NativeForward(object):
             # conv2 (one K = 128 pass, split output) and conv3 (three products per tap, fp32 features), then the heads
             l2, l3 = self.layers[1], self.layers[2]
             L.check(lib.rz_net_conv3x3_tc2(L.ptr(self.bufs[0]), L.ptr(l2['w']), L.ptr(l2['b']), None, L.ptr(self.bufs[1]),
-                                           n, self.H, self.W, 128, int(l2['relu']), 2, 2 | 8 | 256, self.n_ctas, s),
+                                           n, self.H, self.W, 128, int(l2['relu']), 2, 2 | 8 | 256 | 512, self.n_ctas, s),
                     'rz_net_conv3x3_tc2')
             L.check(lib.rz_net_conv3x3_tc2_head_ex(
                 L.ptr(self.bufs[1]), L.ptr(l3['w']), L.ptr(l3['b']), None, n, self.H, self.W, 128, int(l3['relu']),
-                16 | 32, self.w1x1_host.ctypes.data_as(C.c_void_p), self.b1x1_host.ctypes.data_as(C.c_void_p),
+                16 | 32 | 512, self.w1x1_host.ctypes.data_as(C.c_void_p), self.b1x1_host.ctypes.data_as(C.c_void_p),
                 L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc2_head_ex')
             L.check(lib.rz_net_heads_tc(C.byref(self.hdesc), L.ptr(self.feat), L.ptr(logp), L.ptr(value), n, s),
                     'rz_net_heads_tc')
+            return
+        if (self.mode == 'tc' and stem_done and self.trunk_small is not None and n <= self.small_batch_max
+                and self.fused_head and self.conv_rev == 2):
+            # few boards (a sequential search evaluates ONE): the whole trunk in one launch, one CTA pair per board
+            ts = self.trunk_small
+            L.check(lib.rz_net_trunk_small(
+                L.ptr(self.bufs[0]), L.ptr(ts['w']), L.ptr(ts['b']), ts['n'], ts['relu_mask'], ts['res_mask'], n,
+                self.H, self.W, self.w1x1_host.ctypes.data_as(C.c_void_p), self.b1x1_host.ctypes.data_as(C.c_void_p),
+                L.ptr(self.feat), s), 'rz_net_trunk_small')
+            if self.heads_tc:
+                L.check(lib.rz_net_heads_tc(C.byref(self.hdesc), L.ptr(self.feat), L.ptr(logp), L.ptr(value), n, s),
+                        'rz_net_heads_tc')
+            else:
+                L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(self.feat), 2, L.ptr(logp), L.ptr(value), n, s),
+                        'rz_net_heads')
             return
         if self.mode == 'tc':
             # ping-pong: the residual of a block is the buffer its second conv overwrites
@@ -441,11 +476,11 @@ class NativeForward(object):
                     if rev3:
                         L.check(lib.rz_net_conv3x3_tc3_head(
                             L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), n, self.H, self.W, self.S,
-                            int(l['relu']), w1p, b1p, L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc3_head')
+                            int(l['relu']) | 2, w1p, b1p, L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc3_head')
                     else:
-                        L.check(lib.rz_net_conv3x3_tc2_head(
+                        L.check(lib.rz_net_conv3x3_tc2_head_ex(
                             L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res), n, self.H, self.W, l['cin'],
-                            int(l['relu']), w1p, b1p, L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc2_head')
+                            int(l['relu']), 512, w1p, b1p, L.ptr(self.feat), self.n_ctas, s), 'rz_net_conv3x3_tc2_head_ex')
                     if self.heads_tc:
                         L.check(lib.rz_net_heads_tc(C.byref(self.hdesc), L.ptr(self.feat), L.ptr(logp), L.ptr(value),
                                                     n, s), 'rz_net_heads_tc')
@@ -455,7 +490,7 @@ class NativeForward(object):
                     return
                 if rev3:
                     L.check(lib.rz_net_conv3x3_tc3(L.ptr(inp), L.ptr(l['w']), L.ptr(l['b']), L.ptr(res),
-                                                   L.ptr(outs[dst]), n, self.H, self.W, self.S, int(l['relu']),
+                                                   L.ptr(outs[dst]), n, self.H, self.W, self.S, int(l['relu']) | 2,
                                                    self.n_ctas, s), 'rz_net_conv3x3_tc3')
                 elif self.S != 16:
                     raise ValueError('19x19 boards need the fused stem (the generic first layer is stride-16 only)')
@@ -494,10 +529,13 @@ class NativeForward(object):
             L.check(lib.rz_net_heads(C.byref(self.hdesc), L.ptr(inp), 0, L.ptr(logp), L.ptr(value), n, s),
                     'rz_net_heads')
 
-    def kernels_per_forward(self):
-        """Kernel launches of one forward_boards call (for bench.py's gpu_launches)."""
+    def kernels_per_forward(self, n=None):
+        """Kernel launches of one forward_boards call of ``n`` boards (for bench.py's gpu_launches)."""
         if self.mode == 'tc32':
             return 4                                        # stem, conv2, conv3 + 1x1 heads, FC heads
+        if (n is not None and self.mode == 'tc' and self.trunk_small is not None and n <= self.small_batch_max
+                and self.fused_head and self.conv_rev == 2 and self.stem is not None and self.fused_stem):
+            return 3                                        # stem, one-launch trunk + 1x1 heads, FC heads
         n_conv = len(self.layers)
         fused = self.mode == 'tc' and self.stem is not None and self.fused_stem
         heads = 2 if (self.heads_tc and not self.fused_head) else 1   # [1x1 features +] FC heads

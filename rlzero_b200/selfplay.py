@@ -136,7 +136,12 @@ class BatchedSelfPlay(object):
     def kernels_per_wave(self):
         # select + evaluator kernels + expand/backup
         kpf = getattr(self.evaluator, 'kernels_per_forward', None)
-        return 1 + (kpf() if kpf else 1) + 1
+        if kpf is None:
+            return 3
+        try:
+            return 1 + kpf(self.forest.n_leaves) + 1
+        except TypeError:
+            return 1 + kpf() + 1
 
     def warm_up(self):
         """One eager wave (lazy attribute set-up) and capture of the wave graph."""

@@ -343,6 +343,35 @@ def test_fused_head_matches_separate_heads(size, blocks, n):
     assert torch.equal(la, lb) and torch.equal(va, vb)
 
 
+@pytest.mark.parametrize('size,blocks,n', [(15, 10, 1), (15, 3, 5), (15, 2, 74), (9, 2, 3), (8, 1, 2), (11, 1, 1)])
+def test_one_launch_trunk_is_bit_identical_to_the_layer_kernels(size, blocks, n):
+    """rz_net_trunk_small (one CTA pair keeps a board's activation in shared memory through the whole trunk, the seam
+    rows exchanged through distributed shared memory) against the same layers launched one by one: the same MMAs in the
+    same order and the same epilogue arithmetic, so the logits and values are equal bit for bit -- which is what keeps
+    a single-position evaluation (the sequential search, alphazero_mcts.py:73-94) consistent with the batched one."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(size + blocks)
+    net = ResNetPolicyValueNet(size, n_blocks=blocks).cuda().eval()
+    with torch.no_grad():
+        for m in net.modules():            # non-trivial BatchNorm statistics, so that folded scales and biases matter
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0.0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0.0, 0.2)
+    x = _random_boards(n, size, 3)
+    a = NativeForward(net, max_batch=n)
+    assert a.trunk_small is not None and a.small_batch_max >= n and a.kernels_per_forward(n) == 3
+    b = NativeForward(net, max_batch=n)
+    b.small_batch_max = 0
+    la, va = (t.clone() for t in a.forward_planes(x))
+    lb, vb = (t.clone() for t in b.forward_planes(x))
+    assert torch.isfinite(la[:, :size * size]).all() and torch.equal(la, lb) and torch.equal(va, vb)
+    # and twice in a row (the ring and the barriers start from scratch in every launch)
+    la2, va2 = a.forward_planes(x)
+    assert torch.equal(la2, la) and torch.equal(va2, va)
+
+
 def test_graph_recaptured_after_weight_refresh():
     """A CUDA-graph-captured wave holds weight pointers by value: after AlphaZeroAgent.learn /
     refresh_weights the self-play driver must capture again (stale weights otherwise)."""
