@@ -469,6 +469,17 @@ def config_block(args, peaks):
               note='the CPU sample of this search is cpu_baseline.stock_net of the headline')
         del sp
         torch.cuda.empty_cache()
+    # small batches of the headline configuration (the sequential single-game search the reference's training script
+    # runs, alphazero_mcts.py:73-94, and 64 games side by side): stem, one-launch trunk, cluster heads per wave
+    net3 = ResNetPolicyValueNet(15, n_blocks=10).cuda().eval()
+    for G in (1, 64):
+        sp = BatchedSelfPlay(G, 15, 5, net=net3, n_playout=800, add_noise=True, seed=1)
+        entry('small batch: Gomoku 15x15, 800 sims/move, ResNet-10 bf16, %d game(s)' % G, sp, net3.flops_per_eval(), 800,
+              50, 31, note='latency bound: one CTA pair per board keeps the activation in shared memory across the 20 '
+                           'trunk layers (rz_net_trunk_small.cu); per-layer kernels took 250 us per wave for one game')
+        del sp
+    del net3
+    torch.cuda.empty_cache()
     # config 5: MuZero on Gomoku 15x15, 50 latent simulations/move, 8192 games (no reference code: parity unpinned)
     from rlzero_b200.muzero import BatchedMuZeroSelfPlay, MuZeroConfig, MuZeroNet
     net5 = MuZeroNet(15, repr_blocks=10, dyn_blocks=5).cuda().eval()

@@ -221,9 +221,10 @@ class NativeForward(object):
         # rz_net_conv3x3_tc2 flags: bit 1 = direct-store epilogue, the default (853 k vs 840 k sims/s sustained on
         # one box, profiles/r1_run24_bench_ab.log; bit-identical tensors); RZ_CONV_FLAGS=0 selects the staged TMA store
         import os
-        # boards up to which the one-launch trunk of rz_net_trunk_small.cu is used (one CTA pair per board: 74 pairs on
-        # 148 SMs); RZ_SMALL_BATCH_MAX=0 turns it off
-        self.small_batch_max = int(os.environ.get('RZ_SMALL_BATCH_MAX', '74'))
+        # boards up to which the one-launch trunk of rz_net_trunk_small.cu is used (one CTA pair per board, 74 pairs at a
+        # time on 148 SMs; measured crossover with the per-layer kernels near 200 boards, profiles/r2_run43_crossover.log);
+        # RZ_SMALL_BATCH_MAX=0 turns it off
+        self.small_batch_max = int(os.environ.get('RZ_SMALL_BATCH_MAX', '148'))
         self.conv_flags = int(os.environ.get('RZ_CONV_FLAGS', '514'))   # 2 | 512: direct store, static weights
         self.max_batch = 0
         self.refresh_weights()

@@ -343,7 +343,7 @@ def test_fused_head_matches_separate_heads(size, blocks, n):
     assert torch.equal(la, lb) and torch.equal(va, vb)
 
 
-@pytest.mark.parametrize('size,blocks,n', [(15, 10, 1), (15, 3, 5), (15, 2, 74), (9, 2, 3), (8, 1, 2), (11, 1, 1)])
+@pytest.mark.parametrize('size,blocks,n', [(15, 10, 1), (15, 3, 5), (15, 2, 74), (15, 1, 148), (9, 2, 3), (8, 1, 2), (11, 1, 1)])
 def test_one_launch_trunk_is_bit_identical_to_the_layer_kernels(size, blocks, n):
     """rz_net_trunk_small (one CTA pair keeps a board's activation in shared memory through the whole trunk, the seam
     rows exchanged through distributed shared memory) against the same layers launched one by one: the same MMAs in the
