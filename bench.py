@@ -203,7 +203,7 @@ def _cpu_worker(args):
     return n, time.time() - t0
 
 
-def cpu_baseline(which, seconds, blocks=None, n_playout=None):
+def cpu_baseline(which, seconds, blocks=None, n_playout=None, processes=None):
     import multiprocessing as mp
     spec = dict(CPU_SPECS[which])
     if blocks is not None and spec['net'] == 'resnet':
@@ -214,6 +214,8 @@ def cpu_baseline(which, seconds, blocks=None, n_playout=None):
         cores = len(os.sched_getaffinity(0))
     except Exception:
         cores = os.cpu_count() or 1
+    if processes is not None:
+        cores = max(1, min(cores, int(processes)))
     ctx = mp.get_context('spawn')
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, [(i, spec, seconds) for i in range(cores)])
@@ -638,13 +640,17 @@ def exchange_block(sp, net, world, rank, dist):
     torch.cuda.synchronize()
     dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    g_rows, g_info, g_pi, counts = parallel.gather_records_device(rows, info, pi, global_offset=rank * f.G)
-    e1.record()
-    torch.cuda.synchronize()
+    ag_best = 1e30
+    for _ in range(3):          # best of 3: the first exchange of a new size also pays NCCL's buffer set-up
+        dist.barrier()
+        e0.record()
+        g_rows, g_info, g_pi, counts = parallel.gather_records_device(rows, info, pi, global_offset=rank * f.G)
+        e1.record()
+        torch.cuda.synchronize()
+        ag_best = min(ag_best, e0.elapsed_time(e1))
     ok_gather = (g_info.shape[0] == n_rec * world and
                  bool(torch.equal(g_pi[rank * n_rec:(rank + 1) * n_rec], pi)))
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ag_best], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ag_ms = float(t.item())
     recv_bytes = rec_bytes * n_rec * (world - 1)       # what every GPU receives over NVLink
@@ -667,12 +673,14 @@ def exchange_block(sp, net, world, rank, dist):
     # -- weight broadcast + re-pack + graph re-capture
     dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    e0.record()
-    moved = parallel.broadcast_weights(net, src=0)
-    e1.record()
-    torch.cuda.synchronize()
-    bc_ms = e0.elapsed_time(e1)
+    bc_ms = 1e30
+    for _ in range(3):          # best of 3, as above
+        dist.barrier()
+        e0.record()
+        moved = parallel.broadcast_weights(net, src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        bc_ms = min(bc_ms, e0.elapsed_time(e1))
     t1 = time.perf_counter()
     sp.evaluator.refresh_weights()
     sp.step_wave()                                       # re-captures the wave graph with the new weights
@@ -888,6 +896,10 @@ def run_b200(args):
             stock = cpu_baseline('stock15', min(8.0, args.cpu_seconds), n_playout=P)
             line['cpu_baseline']['stock_net'] = {'value': stock['value'], 'unit': stock['unit'], 'cores': stock['cores'],
                                                  'sample': stock['sample']}
+            # ONE process, the way the reference's own training script runs the search
+            one = cpu_baseline('stock15', min(4.0, args.cpu_seconds), n_playout=P, processes=1)
+            line['cpu_baseline']['stock_net_single_process'] = {'value': one['value'], 'unit': one['unit'], 'cores': 1,
+                                                                'sample': one['sample']}
         line['hbm_bytes_node_pools_and_scratch'] = hbm_main
         print(json.dumps(line))
     if world > 1:
