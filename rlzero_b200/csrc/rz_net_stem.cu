@@ -76,23 +76,37 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p
   constexpr uint32_t ONE = 0x3F80u;  // bf16 1.0
 
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  // the board words of a tile are fetched ONE TILE AHEAD into registers (their L2 / HBM latency, ~1 us of a ~4 us tile,
+  // used to sit between the tile's first barrier and its im2col phase)
+  auto fetch_board = [&](int tile_, uint32_t& word, uint32_t& metaw) {
+    word = 0u; metaw = 0u;
+    if (kPlanes || tile_ >= p.n_tiles) return;
+    const int sel = tid >> 6, t = tid & 63, bb = (tile_ * 128) / P + sel;
+    const int c = t >> 5, y = t & 31;
+    if (y < H && bb < p.n_boards) word = p.rows[((size_t)bb * 2 + c) * H + y];
+    if (t < 4 && bb < p.n_boards) metaw = (uint32_t)p.meta[(size_t)bb * RZ_META_STRIDE + t];
+  };
+  uint32_t nxt_word, nxt_meta;
+  fetch_board(blockIdx.x, nxt_word, nxt_meta);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
     const int b_first = (tile * 128) / P;
     const int my_row = tile * 128 + tid;
     const int b = my_row / P, bsel = b - b_first;       // this thread's board (0 or 1 within the tile)
     // ---- the (at most two) boards of this tile -> shared memory (rows beyond H / boards beyond n are zero)
+    uint32_t* s_rows_t = s_rows;     // (every read of the previous tile's words is behind the barrier that ends its iteration)
     if (!kPlanes) {
-      const int sel = tid >> 6, t = tid & 63, bb = b_first + sel;
-      const int c = t >> 5, y = t & 31;
-      s_rows[sel * 68 + t] = (y < H && bb < p.n_boards) ? p.rows[((size_t)bb * 2 + c) * H + y] : 0u;
-      if (t < 4) s_rows[sel * 68 + 64 + t] = bb < p.n_boards ? (uint32_t)p.meta[(size_t)bb * RZ_META_STRIDE + t] : 0u;
+      const int sel = tid >> 6, t = tid & 63;
+      s_rows_t[sel * 68 + t] = nxt_word;
+      if (t < 4) s_rows_t[sel * 68 + 64 + t] = nxt_meta;
+      fetch_board(tile + gridDim.x, nxt_word, nxt_meta);
     }
     __syncthreads();
     // ---- im2col row of position r: k = tap*4 + plane (gomoku_env.py:95-114 per tap)
     {
       const int pos = my_row - b * P;
       const int y = pos / kS, x = pos - y * kS;
-      const uint32_t* brd = s_rows + bsel * 68;
+      const uint32_t* brd = s_rows_t + bsel * 68;
       const int player = (int)brd[64] & 1, last = (int)brd[65], stones = (int)brd[66];
       const uint32_t colour = (stones & 1) ? 0u : ONE;
       const bool out_inside = (x < W) && (y < H) && b < p.n_boards;
@@ -190,25 +204,31 @@ rz_stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const StemParams p
       const int pos = my_row - b * P;
       const bool valid = (pos % kS < W) && (pos / kS < H) && b < p.n_boards;
       __nv_bfloat16* orow = p.out + (size_t)my_row * 128;
+      // two 32-column chunks in flight per wait (four serial load / wait round trips cost ~0.4 us of a ~4 us tile)
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t acc[32];
-        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ch * 32), acc);
+      for (int cp = 0; cp < 2; ++cp) {
+        uint32_t acc2[2][32];
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cp * 64), acc2[0]);
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cp * 64 + 32), acc2[1]);
         rz::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint32_t packed[8];
+        for (int h = 0; h < 2; ++h) {
+          const int ch = cp * 2 + h;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = j * 16 + e * 2;
-            float v0 = __uint_as_float(acc[c]) + s_bias[ch * 32 + c];
-            float v1 = __uint_as_float(acc[c + 1]) + s_bias[ch * 32 + c + 1];
-            if (p.relu & 1) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
-            if (!valid) { v0 = 0.0f; v1 = 0.0f; }
-            const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
-            packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
+          for (int j = 0; j < 2; ++j) {
+            uint32_t packed[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = j * 16 + e * 2;
+              float v0 = __uint_as_float(acc2[h][c]) + s_bias[ch * 32 + c];
+              float v1 = __uint_as_float(acc2[h][c + 1]) + s_bias[ch * 32 + c + 1];
+              if (p.relu & 1) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+              if (!valid) { v0 = 0.0f; v1 = 0.0f; }
+              const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
+              packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
+            }
+            if (my_row < p.rows_alloc) rz::st_global_v8(orow + ch * 32 + j * 16, packed);
           }
-          if (my_row < p.rows_alloc) rz::st_global_v8(orow + ch * 32 + j * 16, packed);
         }
       }
     }

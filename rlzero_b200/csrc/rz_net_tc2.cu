@@ -78,7 +78,9 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
                       const __grid_constant__ HeadTaps head) {
   static_assert(!kHead || kCG == 2, "the fused 1x1 heads need all 128 channels of a row in one thread");
   constexpr int ACC_N = (kCG == 2) ? 128 : 64;     // accumulator columns per buffer
-  constexpr int TMEM_COLS = 2 * ACC_N;
+  // fused-heads layer: 16 more columns (two slots of 8) carry the upper channel half's partial sums from one warp of a
+  // lane quarter to the other; the allocation is a power of two
+  constexpr int TMEM_COLS = kHead ? 512 : 2 * ACC_N;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = rz::smem_u32(smem_raw);
   const uint32_t a_base = smem_base + B_BYTES;
@@ -112,7 +114,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
     for (int tap = 0; tap < 9; ++tap) rz::mbar_init(bar_btap + 8 * tap, 1);
     for (int b = 0; b < 2; ++b) {
       rz::mbar_init(bar_afull + 8 * b, 1);
-      rz::mbar_init(bar_aempty + 8 * b, kHead ? 4 : 1);   // fused-heads layer: the 4 warps that read the scratch
+      rz::mbar_init(bar_aempty + 8 * b, 1);
       rz::mbar_init(bar_tfull + 8 * b, 1);
       rz::mbar_init(bar_tempty + 8 * b, 8 * kCG);
     }
@@ -402,6 +404,7 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
       }
       rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
       rz::tc_fence_after();
+      if (warp == 2 && lane == 0) rz::mbar_arrive(bar_aempty + 8 * buf);   // MMAs done: the A tile is dead
       uint32_t acc[2][32];
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch)
@@ -447,21 +450,29 @@ rz_conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act,
           }
         }
       }
-      // partial sums of channels 64..127 -> scratch rows of 8 floats in the (dead) A buffer of this tile
-      float* scratch = reinterpret_cast<float*>(smem_raw + B_BYTES + buf * A_BUF_BYTES) + r_in_tile * 8;
+      // partial sums of channels 64..127 -> 8 spare TMEM columns of this lane quarter (slot = tile parity); the partner
+      // warp of the quarter reads them back.  (They used to travel through the tile's A buffer, which therefore went
+      // back to the producer only at the END of this epilogue: the reload of the next-but-one tile started late and the
+      // layer took 60 us longer than a plain one, profiles/r2_run48_wave_timeline_8192.log.)
+      const uint32_t t_scr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * ACC_N + buf * 8);
       if (hsel == 1) {
+        uint32_t hv[8];
 #pragma unroll
-        for (int f = 0; f < 6; ++f) scratch[f] = hacc[f];
+        for (int f = 0; f < 6; ++f) hv[f] = __float_as_uint(hacc[f]);
+        hv[6] = 0u; hv[7] = 0u;
+        rz::tmem_st_32x8(t_scr, hv);
+        rz::tmem_st_wait();
+        rz::tc_fence_before();
       }
       rz::named_bar_sync(1, 256);
       if (hsel == 0) {
+        rz::tc_fence_after();
+        uint32_t hv[8];
+        rz::tmem_ld_32x8(t_scr, hv);
+        rz::tmem_ld_wait();
         float* fo = head.feat + (size_t)(row >> 8) * (6 * 256) + pos;
 #pragma unroll
-        for (int f = 0; f < 6; ++f) fo[f * 256] = fmaxf(hacc[f] + scratch[f], 0.0f);
-        // the scratch has been read: the A buffer may be refilled (generic -> async proxy hand-over)
-        rz::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) rz::mbar_arrive(bar_aempty + 8 * buf);
+        for (int f = 0; f < 6; ++f) fo[f * 256] = fmaxf(hacc[f] + __uint_as_float(hv[f]), 0.0f);
       }
     }
   }
