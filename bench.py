@@ -289,7 +289,7 @@ def tree_roofline(sp, ms_per_step, peaks, n_rep=20):
                 body()
         return g
 
-    def timed(g, reps=3):
+    def timed(g, reps=10):
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g.replay()
         torch.cuda.synchronize()
@@ -316,7 +316,7 @@ def tree_roofline(sp, ms_per_step, peaks, n_rep=20):
            'achieved': sel_bytes / sel_ms / 1e6, 'peak': hbm, 'unit': 'GB/s', 'frac': sel_bytes / sel_ms / 1e6 / hbm,
            'launch_ms': sel_ms, 'algorithmic_bytes_per_launch': sel_bytes, 'share_of_step': sel_ms / ms_per_step,
            'peak_source': src,
-           'how': '%d launches captured in one CUDA graph, replayed, CUDA events around the replay, best of 3 '
+           'how': '%d launches captured in one CUDA graph, replayed, CUDA events around the replay, best of 10 '
                   '(compare profiles/*wave_launches.csv: ncu times the same kernel alone)' % n_rep}
 
     def pair():
