@@ -109,11 +109,12 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
     }
     for (int b = 0; b < 2; ++b) {
       rz::mbar_init(bar_tfull + 8 * b, 1);
-      rz::mbar_init(bar_tempty + 8 * b, kHead ? 8 : 16);     // 4 / 8 epilogue warps of each CTA
+      rz::mbar_init(bar_tempty + 8 * b, 16);                 // the 8 epilogue warps of each CTA
     }
     rz::fence_barrier_init();
   }
-  if (warp == 1) { rz::tmem_alloc_pair(rz::smem_u32(tmem_holder), 256); rz::tmem_relinquish_pair(); }
+  // (fused-heads layer: 16 more columns carry partial sums between the two warps of a lane quarter)
+  if (warp == 1) { rz::tmem_alloc_pair(rz::smem_u32(tmem_holder), kHead ? 512 : 256); rz::tmem_relinquish_pair(); }
   if (threadIdx.x >= 64 && threadIdx.x < 192) s_bias[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
   rz::tc_fence_before();
   rz::cluster_sync_all();
@@ -259,57 +260,72 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
         }
       }
     }
-  } else if (warp < 6) {
-    // ===== fused-heads layer: epilogue warps 2..5, TMEM lane quarter = warp % 4, one output row per thread =====
+  } else {
+    // ===== fused-heads layer: the same 8 epilogue warps (TMEM lane quarter = warp % 4, channel half = (warp - 2) / 4).
+    // Every thread turns its 64 channels of a row into bf16 activations (never stored) and 6 partial dot products with the
+    // heads' 1x1 filters; the warp holding channels 64..127 hands its sums to its partner of the same lane quarter
+    // through 8 spare TMEM columns (slot = tile parity), which adds them, applies ReLU and writes the 6 features.
+    // Summation order = rz_net_heads.cu's conv1x1_position: channels 0..63 onto the bias, 64..127 onto zero.  (Until
+    // round 2 four warps did all 128 channels of a row each -- 1536 FFMAs per thread and tile: the layer took 75 us
+    // against 50 us for a plain one at Connect Four's size, profiles/r2_run51_wave_timeline_c4.log.)
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
+    const int col0 = hsel * 64;
+    const int r_in_tile = q * 32 + lane;
+    auto row_valid = [&](int row_) {
+      const int board_ = row_ / G::P, pos_ = row_ - board_ * G::P;
+      const int y_ = pos_ / kS, x_ = pos_ - y_ * kS;
+      return row_ < p.total_rows && x_ < p.W && y_ < p.H;
+    };
+    uint32_t res[4][8], resn[4][8];
+    bool next_res = false;
+    auto load_res = [&](int item_) {
+      const int row_ = item_ * 256 + (int)rank * TILE_M + r_in_tile;
+      next_res = p.residual != nullptr && row_valid(row_);
+      if (next_res) {
+        const __nv_bfloat16* rrow = p.residual + (size_t)row_ * 128 + col0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rz::ld_global_v8_stream(rrow + j * 16, resn[j]);
+      }
+    };
+    if (worker < p.n_items) load_res(worker);
     int it = 0;
-    bool store_pending = false;
     for (int item = worker; item < p.n_items; item += n_workers, ++it) {
       const int buf = it & 1;
-      const int row0 = item * 256 + (int)rank * TILE_M;
-      const int r_in_tile = q * 32 + lane;
-      const int row = row0 + r_in_tile;
+      const int row = item * 256 + (int)rank * TILE_M + r_in_tile;
       const int board = row / G::P, pos = row - board * G::P;
-      const int y = pos / kS, x = pos - y * kS;
       const bool in_tensor = row < p.total_rows;
-      const bool valid = in_tensor && x < p.W && y < p.H;
-      uint32_t res[8][8];
-      const bool have_res = p.residual != nullptr && valid;
+      const bool valid = row_valid(row);
+      const bool have_res = next_res;
       if (have_res) {
-        const __nv_bfloat16* rrow = p.residual + (size_t)row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) rz::ld_global_v8(rrow + j * 16, res[j]);
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) res[j][e] = resn[j][e];
       }
+      if (item + n_workers < p.n_items) load_res(item + n_workers); else next_res = false;
       rz::mbar_wait(bar_tfull + 8 * buf, (uint32_t)(it >> 1) & 1u);
       rz::tc_fence_after();
-      // summation order of rz_net_heads.cu's conv1x1_position: channels 0..63 onto the bias, 64..127 onto zero
-      float hacc[6], hacc_hi[6];
+      uint32_t acc[2][32];
 #pragma unroll
-      for (int f = 0; f < 6; ++f) { hacc[f] = kHead ? head.b[f] : 0.0f; hacc_hi[f] = 0.0f; }
-      const uint32_t srow = stage + (uint32_t)r_in_tile * 128u;
+      for (int ch = 0; ch < 2; ++ch)
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + col0 + ch * 32), acc[ch]);
+      rz::tmem_ld_wait();
+      rz::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) rz::mbar_arrive_cluster_relaxed(rz::mapa_shared(bar_tempty + 8 * buf, 0));
+      float hacc[6];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t acc[32];
-        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + ch * 32), acc);
-        rz::tmem_ld_wait();
-        if (ch == 3) {
-          rz::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) rz::mbar_arrive_cluster_relaxed(rz::mapa_shared(bar_tempty + 8 * buf, 0));
-        }
-        if (!kHead && (ch & 1) == 0) {
-          // the staging buffer is free once the previous half's TMA store has read it
-          if (warp == 2 && lane == 0 && store_pending) rz::tma_store_wait_read();
-          rz::named_bar_sync(1, 128);
-        }
+      for (int f = 0; f < 6; ++f) hacc[f] = hsel == 0 ? head.b[f] : 0.0f;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t packed[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = j * 8 + e * 2;
-            float v0 = __uint_as_float(acc[c]) + s_bias[ch * 32 + c];
-            float v1 = __uint_as_float(acc[c + 1]) + s_bias[ch * 32 + c + 1];
+            float v0 = __uint_as_float(acc[ch][c]) + s_bias[col0 + ch * 32 + c];
+            float v1 = __uint_as_float(acc[ch][c + 1]) + s_bias[col0 + ch * 32 + c + 1];
             if (have_res) {
               const uint32_t rw = res[ch * 2 + (j >> 1)][(j & 1) * 4 + e];
               v0 += __uint_as_float(rw << 16);
@@ -318,46 +334,45 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
             if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
             if (!valid) { v0 = 0.0f; v1 = 0.0f; }
             const __nv_bfloat162 o2 = __floats2bfloat162_rn(v0, v1);
-            packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
-            if (kHead) {
-              const float r0 = __uint_as_float(packed[e] << 16), r1 = __uint_as_float(packed[e] & 0xffff0000u);
+            const uint32_t pk = *reinterpret_cast<const uint32_t*>(&o2);
+            const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+            const int cc = col0 + ch * 32 + c;
 #pragma unroll
-              for (int f = 0; f < 6; ++f) {
-                const float a0 = ch < 2 ? hacc[f] : hacc_hi[f];
-                const float a1 = fmaf(r1, head.w[f * 128 + ch * 32 + c + 1], fmaf(r0, head.w[f * 128 + ch * 32 + c], a0));
-                if (ch < 2) hacc[f] = a1; else hacc_hi[f] = a1;
-              }
-            }
+            for (int f = 0; f < 6; ++f)
+              hacc[f] = fmaf(r1, head.w[f * 128 + cc + 1], fmaf(r0, head.w[f * 128 + cc], hacc[f]));
           }
-          if (!kHead) {
-            const uint32_t chunk = (uint32_t)((ch & 1) * 4 + j);
-            rz::st_shared_v4(srow + ((chunk ^ ((srow >> 7) & 7u)) << 4), packed[0], packed[1], packed[2], packed[3]);
-          }
-        }
-        if (!kHead && (ch & 1) == 1) {
-          rz::fence_proxy_async();
-          rz::named_bar_sync(2, 128);
-          if (warp == 2 && lane == 0) {
-            rz::tma_store_2d(&tmap_out, stage, (ch >> 1) * 64, row0);
-            rz::tma_store_commit();
-          }
-          store_pending = true;
         }
       }
-      if (kHead && in_tensor) {
-        float* fo = head.feat + (size_t)board * (6 * G::P) + pos;
+      const uint32_t t_scr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + buf * 8);
+      if (hsel == 1) {
+        uint32_t hv[8];
 #pragma unroll
-        for (int f = 0; f < 6; ++f) fo[f * G::P] = fmaxf(hacc[f] + hacc_hi[f], 0.0f);
+        for (int f = 0; f < 6; ++f) hv[f] = __float_as_uint(hacc[f]);
+        hv[6] = 0u; hv[7] = 0u;
+        rz::tmem_st_32x8(t_scr, hv);
+        rz::tmem_st_wait();
+        rz::tc_fence_before();
+      }
+      rz::named_bar_sync(1, 256);
+      if (hsel == 0) {
+        rz::tc_fence_after();
+        uint32_t hv[8];
+        rz::tmem_ld_32x8(t_scr, hv);
+        rz::tmem_ld_wait();
+        if (in_tensor) {
+          float* fo = head.feat + (size_t)board * (6 * G::P) + pos;
+#pragma unroll
+          for (int f = 0; f < 6; ++f) fo[f * G::P] = fmaxf(hacc[f] + __uint_as_float(hv[f]), 0.0f);
+        }
       }
     }
-    if (warp == 2 && lane == 0 && store_pending) rz::tma_store_wait_all();
   }
 
   rz::tc_fence_before();
   rz::cluster_sync_all();
   if (warp == 1) {
     rz::tc_fence_after();
-    rz::tmem_dealloc_pair(tmem_base, 256);
+    rz::tmem_dealloc_pair(tmem_base, kHead ? 512 : 256);
   }
 }
 

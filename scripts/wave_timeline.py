@@ -14,9 +14,15 @@ from rlzero_b200.selfplay import BatchedSelfPlay  # noqa: E402
 
 G = int(os.environ.get('RZ_G', '8192'))
 torch.manual_seed(0)
-net = ResNetPolicyValueNet(15, n_blocks=10).cuda().eval()
-sp = BatchedSelfPlay(G, 15, 5, net=net, n_playout=800, add_noise=True, seed=1)
-sp.set_random_start_positions()
+if os.environ.get('RZ_CFG') == 'c4':      # BASELINE config 2: Connect Four 6x7, ResNet-6, 4096 games
+    from rlzero_b200 import _lib as L
+    G = int(os.environ.get('RZ_G', '4096'))
+    net = ResNetPolicyValueNet(6, n_blocks=6, board_width=7, n_actions=7).cuda().eval()
+    sp = BatchedSelfPlay(G, 6, 4, net=net, n_playout=200, add_noise=True, seed=2, board_width=7, game_type=L.GAME_CONNECT4)
+else:
+    net = ResNetPolicyValueNet(15, n_blocks=10).cuda().eval()
+    sp = BatchedSelfPlay(G, 15, 5, net=net, n_playout=800, add_noise=True, seed=1)
+sp.set_random_start_positions(max_random_moves=3) if os.environ.get('RZ_CFG') == 'c4' else sp.set_random_start_positions()
 sp.warm_up()
 for _ in range(int(os.environ.get('RZ_WARM', '1500'))):
     sp.step_wave()
