@@ -2,7 +2,7 @@
  *
  * The reference (jianzhnie/RLZero) has no FFI layer; its boundary is the
  * duck-typed Python API of rlzero/mcts/alphazero_mcts.py and
- * rlzero/games/gomoku/*.py.  This header is the C-ABI a
+ * rlzero/games/gomoku/ (SURVEY.md section 8b).  This header is the C-ABI a
  * maintainer would bind underneath those classes (ctypes stub in
  * INTEGRATION.md).  Each entry point cites the reference function it replaces.
  *
@@ -565,8 +565,8 @@ int rz_net_trunk_small(const void* act_in, const void* weights, const float* bia
 int rz_debug_set_probe(void* device_buffer);
 /* revision 3 of the convolution: the same data path for any row stride of the padded position
    layout (row = board*S*S + y*S + x; S = row_stride = 8 for boards up to 7x7 such as Connect Four 6x7, 16 up
-   to 15x15, 20 up to 19x19), tiles of 128 rows that may straddle boards (S = 20) or hold two boards (S = 8), a 3-slot ring of k-block halo tiles and a half-staged TMA-store
-   epilogue (shared-memory budget of the 170-row halo at S = 20).  c_in = c_out = 128.  Tensors are
+   to 15x15, 20 up to 19x19), tiles of 128 rows that may straddle boards (S = 20) or hold two boards (S = 8), a ring of k-block halo tiles (3 slots at S = 20, 4 at S = 8 / 16: the
+   shared-memory budget of the 170-row halo) and rev. 2's direct-store epilogue.  c_in = c_out = 128.  Tensors are
    bf16 [round_up(n_boards*S*S, 256)][128].  The _head variant writes feat f32 [n_boards][6][S*S]. */
 int rz_net_conv3x3_tc3(const void* act_in, const void* weight, const float* bias, const void* residual,
                        void* act_out, int n_boards, int board_rows, int board_cols, int row_stride, int relu,

@@ -19,9 +19,10 @@
 //     activation k-block tiles (170 x 128 B = 21.8 KB) cycle through a 3-slot ring: a slot is
 //     released as soon as its 36 MMAs have completed, half a tile early, and refilled with the
 //     next tile's data;
-//   * the epilogue stages the bf16 output tile in two halves of 64 channels through one 16 KB
-//     buffer (TMA store per half) instead of re-using a whole activation buffer.
-// Shared memory: 147456 (weights) + 3*21760 (ring) + 16384 (staging) + 1024 = 230144 B.
+//   * the epilogue writes its rows straight from registers (256-bit global stores, as rev. 2's direct-store
+//     epilogue; the 16 KB staging buffer of the first version is gone), which leaves room for a fourth ring slot at
+//     strides 8 and 16.
+// Shared memory: 147456 (weights) + 3*21760 (ring, stride 20) + 1024 = 213760 B; 4*20736 at stride 16: 231424 B.
 #include <cuda_bf16.h>
 
 #include "rz_common.cuh"
@@ -32,9 +33,7 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int B_TILE_BYTES = 64 * 128;            // 64 output channels x 64 input channels
 constexpr int B_BYTES = 9 * 2 * B_TILE_BYTES;     // 147456
-constexpr int STAGE_BYTES = TILE_M * 128;         // 128 rows x 64 channels bf16
 constexpr int NUM_THREADS = 320;    // producer warp, MMA warp, 8 epilogue warps (4 in the fused-heads layer)
-constexpr int N_SLOTS = 3;
 
 template <int kS>
 struct Geo {
@@ -43,8 +42,8 @@ struct Geo {
   static constexpr int SLOT_BYTES = A_ROWS * 128;
   static constexpr int P = kS * kS;
   static constexpr int OFF_RING = B_BYTES;
-  static constexpr int OFF_STAGE = (OFF_RING + N_SLOTS * SLOT_BYTES + 127) / 128 * 128;
-  static constexpr int OFF_CTRL = OFF_STAGE + STAGE_BYTES;
+  static constexpr int N_SLOTS = (B_BYTES + 4 * SLOT_BYTES + 1024 <= 232448) ? 4 : 3;   // k-block halo tiles in flight
+  static constexpr int OFF_CTRL = (OFF_RING + N_SLOTS * SLOT_BYTES + 127) / 128 * 128;
   static constexpr int SMEM = OFF_CTRL + 1024;
 };
 
@@ -76,14 +75,13 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = rz::smem_u32(smem_raw);
   const uint32_t ring = smem_base + G::OFF_RING;
-  const uint32_t stage = smem_base + G::OFF_STAGE;
   const uint32_t ctrl = smem_base + G::OFF_CTRL;
   uint8_t* ctrl_ptr = smem_raw + G::OFF_CTRL;
   // weights: one barrier per (k-block, tap) at ctrl + 640 .. 783, loaded in the order the MMA loop consumes them and
   // right behind the first activation k-block, so the first tile starts after 16 KB of weights instead of 147 KB
-  const uint32_t bar_btap = ctrl + 640, bar_afull = ctrl + 8, bar_aempty = ctrl + 32;
-  const uint32_t bar_tfull = ctrl + 56, bar_tempty = ctrl + 72;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ctrl_ptr + 88);
+  const uint32_t bar_btap = ctrl + 640, bar_afull = ctrl + 8, bar_aempty = ctrl + 40;   // [<= 4 slots] each
+  const uint32_t bar_tfull = ctrl + 72, bar_tempty = ctrl + 88;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ctrl_ptr + 104);
   float* s_bias = reinterpret_cast<float*>(ctrl_ptr + 128);
 
   // warp index / cluster rank through a shuffle: provably warp-uniform, so the role branches are uniform and
@@ -103,7 +101,7 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
     rz::tma_prefetch_desc(&tmap_w);
     rz::tma_prefetch_desc(&tmap_out);
     for (int j = 0; j < 18; ++j) rz::mbar_init(bar_btap + 8 * j, 1);
-    for (int s = 0; s < N_SLOTS; ++s) {
+    for (int s = 0; s < G::N_SLOTS; ++s) {
       rz::mbar_init(bar_afull + 8 * s, 1);
       rz::mbar_init(bar_aempty + 8 * s, 1);
     }
@@ -141,8 +139,8 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
       for (int item = worker; item < p.n_items; item += n_workers) {
         const int row0 = item * 256 + (int)rank * TILE_M - G::HALO;
         for (int kb = 0; kb < 2; ++kb, ++u) {
-          const int slot = u % N_SLOTS;
-          rz::mbar_wait(bar_aempty + 8 * slot, ((uint32_t)(u / N_SLOTS) & 1u) ^ 1u);
+          const int slot = u % G::N_SLOTS;
+          rz::mbar_wait(bar_aempty + 8 * slot, ((uint32_t)(u / G::N_SLOTS) & 1u) ^ 1u);
           if (leader) rz::mbar_expect_tx(bar_afull + 8 * slot, (uint32_t)(2 * G::SLOT_BYTES));
           rz::tma_load_2d_pair(ring + (uint32_t)slot * G::SLOT_BYTES, &tmap_act,
                                rz::mapa_shared(bar_afull + 8 * slot, 0), kb * 64, row0);
@@ -163,8 +161,8 @@ rz_conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmap_act,
         const uint32_t d_tmem = tmem_u + (uint32_t)(buf * 128);
         uint32_t acc = 0;
         for (int kb = 0; kb < 2; ++kb, ++u) {
-          const int slot = u % N_SLOTS;
-          rz::mbar_wait(bar_afull + 8 * slot, (uint32_t)(u / N_SLOTS) & 1u);
+          const int slot = u % G::N_SLOTS;
+          rz::mbar_wait(bar_afull + 8 * slot, (uint32_t)(u / G::N_SLOTS) & 1u);
           rz::tc_fence_after();
           const uint32_t a_slot = ring + (uint32_t)slot * G::SLOT_BYTES;
 #pragma unroll 1
