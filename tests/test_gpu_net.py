@@ -372,6 +372,25 @@ def test_one_launch_trunk_is_bit_identical_to_the_layer_kernels(size, blocks, n)
     assert torch.equal(la2, la) and torch.equal(va2, va)
 
 
+def test_small_and_large_batch_paths_agree_bit_for_bit():
+    """Batch invariance ACROSS the path boundary: a board evaluated alone or among 100 (one-launch trunk, one CTA pair per
+    board) gives exactly the logits and value it gets among 300 (one launch per layer, persistent CTA pairs over
+    tiles) -- what lets the oracle's board-by-board evaluations check a search that evaluates 8192 boards at once."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(5)
+    net = ResNetPolicyValueNet(15, n_blocks=4).cuda().eval()
+    nf = NativeForward(net, max_batch=300)
+    assert nf.trunk_small is not None and 100 <= nf.small_batch_max < 300
+    x = _random_boards(300, 15, 11)
+    l_all, v_all = (t.clone() for t in nf.forward_planes(x))
+    assert nf.kernels_per_forward(300) > 3 and nf.kernels_per_forward(100) == 3 and nf.kernels_per_forward(1) == 3
+    for i in (0, 17, 148, 299):
+        l1, v1 = nf.forward_planes(x[i:i + 1])
+        assert torch.equal(l1[0], l_all[i]) and torch.equal(v1[0], v_all[i]), i
+    l100, v100 = nf.forward_planes(x[150:250])
+    assert torch.equal(l100[:100], l_all[150:250]) and torch.equal(v100[:100], v_all[150:250])
+
+
 def test_graph_recaptured_after_weight_refresh():
     """A CUDA-graph-captured wave holds weight pointers by value: after AlphaZeroAgent.learn /
     refresh_weights the self-play driver must capture again (stale weights otherwise)."""
