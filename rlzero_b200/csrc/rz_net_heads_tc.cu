@@ -275,14 +275,17 @@ rz_heads_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_co
 
 // ---- the same GEMM split over K across a cluster of four CTAs (action_stride <= 256) -------------------------------------
 // One CTA streams 1.2 MB of split weights and converts 6P features per board chunk after chunk: 55 us for a single board,
-// 84 us for 8192 (64 CTAs on 148 SMs) -- profiles/r2_run38_*, run40.  Here the four CTAs of a cluster share the 128 boards
-// of a tile: CTA r takes the feature chunks r, r + 4, r + 8, ... (its own quarter of the weights, its own quarter of the
-// conversion work), accumulates a partial [128 boards][AS + 64] product in its TMEM, and the partials meet through
-// distributed shared memory: TMEM lane quarter q (boards 32q .. 32q+31) of every CTA goes to CTA q, which adds the four
-// partials in rank order and finishes log_softmax / the value head for its 32 boards.  The arithmetic of a board does
+// 84 us for 8192 (64 CTAs on 148 SMs) -- profiles/r2_run38_*, run40.  Here the HT4_CLUSTER = 4 CTAs of a cluster share the 128 boards
+// of a tile: CTA r takes the feature chunks r, r + 4, r + 8, ... (its own share of the weights and of the conversion
+// work), accumulates a partial [128 boards][AS + 64] product in its TMEM, and the partials meet through
+// distributed shared memory: the rows of boards 32 r .. 32 r + 31 of every CTA's accumulator go to CTA r, which adds the
+// partials in rank order and finishes log_softmax / the value head for its boards.  The arithmetic of a board does
 // not depend on how many boards are evaluated, nor on its place in the tile.
-constexpr int HT4_CLUSTER = 4;
-constexpr int HT4_RSTRIDE = 33;                 // floats per column of the exchange buffers (32 boards + 1: no bank conflicts)
+constexpr int HT4_CLUSTER = 4;                  // CTAs per 128-board tile.  (8 was measured: 18 instead of 20 us for one board,
+                                                // but 150 instead of 76 us for 8192 -- clusters of eight 199 KB CTAs schedule badly;
+                                                // profiles/r2_run55_*.  The size is fixed: it defines the summation order.)
+constexpr int HT4_ROWS = 128 / HT4_CLUSTER;     // boards a CTA finishes
+constexpr int HT4_RSTRIDE = HT4_ROWS + 1;       // floats per column of the exchange buffers (+ 1: no bank conflicts)
 
 __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
@@ -311,7 +314,7 @@ rz_heads_tc4_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_c
   const bool row_live = b0 + r < p.n_boards;
   const int K6 = 6 * P, K4 = 4 * P;
   const int n_chunks = (K6 + 63) >> 6, n_pol = K4 >> 6;
-  const int n_my = (n_chunks - (int)rank + HT4_CLUSTER - 1) / HT4_CLUSTER;      // own chunks c = rank + 4 i
+  const int n_my = (n_chunks - (int)rank + HT4_CLUSTER - 1) / HT4_CLUSTER;      // own chunks c = rank + HT4_CLUSTER i
   const bool has_pol = (int)rank < n_pol;
   const int first_val = (int)rank + (((int)rank < n_pol) ? (n_pol - (int)rank + HT4_CLUSTER - 1) / HT4_CLUSTER * HT4_CLUSTER : 0);
   const bool has_val = first_val < n_chunks;
@@ -426,11 +429,11 @@ rz_heads_tc4_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_c
     step(i, pre[0]);
     if (i + 1 < n_my) step(i + 1, pre[1]);
   }
-  rz::mbar_wait(bar_done, 0);
+  if (n_my > 0) rz::mbar_wait(bar_done, 0);
   rz::tc_fence_after();
 
   // ---- exchange: every CTA has finished its MMAs, the stages are dead: they become the receive buffers
-  // rb[src rank][column][HT4_RSTRIDE] float32 of the 32 boards this CTA finishes
+  // rb[src rank][column][HT4_RSTRIDE] float32 of the HT4_ROWS boards this CTA finishes
   rz::cluster_sync_all();
   const uint32_t rb = base;
   {
@@ -446,7 +449,9 @@ rz_heads_tc4_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_c
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = 0u;
       }
-      const uint32_t dst = rz::mapa_shared(rb + (uint32_t)((((int)rank * NC + c0) * HT4_RSTRIDE + lane) * 4), (uint32_t)q);
+      // board row q * 32 + lane of the tile is finished by CTA (q * 32 + lane) / HT4_ROWS, as its row (lane % HT4_ROWS)
+      const uint32_t dst = rz::mapa_shared(rb + (uint32_t)((((int)rank * NC + c0) * HT4_RSTRIDE + (lane % HT4_ROWS)) * 4),
+                                           (uint32_t)((q * 32 + lane) / HT4_ROWS));
 #pragma unroll
       for (int j = 0; j < 32; ++j) st_cluster_f32(dst + (uint32_t)(j * HT4_RSTRIDE * 4), acc[j]);
     }
@@ -456,15 +461,17 @@ rz_heads_tc4_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_c
 
   // ---- finish boards b0 + 32 rank + (0..31): partials added in rank order, biases, log_softmax / value head
   float* rbf = reinterpret_cast<float*>(smem_raw);
-  for (int idx = tid; idx < NC * 32; idx += HT_THREADS) {
-    const int col = idx >> 5, row = idx & 31;
+  for (int idx = tid; idx < NC * HT4_ROWS; idx += HT_THREADS) {
+    const int col = idx / HT4_ROWS, row = idx % HT4_ROWS;
     const int o = col * HT4_RSTRIDE + row;
-    const float v = ((rbf[o] + rbf[NC * HT4_RSTRIDE + o]) + rbf[2 * NC * HT4_RSTRIDE + o]) + rbf[3 * NC * HT4_RSTRIDE + o];
+    float v = rbf[o];
+#pragma unroll
+    for (int src = 1; src < HT4_CLUSTER; ++src) v += rbf[src * NC * HT4_RSTRIDE + o];
     rbf[o] = v + (col < AS ? s_bp[col] : s_bv1[col - AS]);
   }
   __syncthreads();
-  for (int rr = warp * 4; rr < warp * 4 + 4; ++rr) {             // 8 warps x 4 boards
-    const int board = b0 + 32 * (int)rank + rr;
+  for (int rr = warp; rr < HT4_ROWS; rr += HT_THREADS / 32) {     // one warp per board
+    const int board = b0 + HT4_ROWS * (int)rank + rr;
     // act_fc1 + log_softmax over the A real outputs (:43-44): lanes stride over the columns, butterfly reductions
     float mx = -3.0e38f;
     for (int c = lane; c < p.A; c += 32) mx = fmaxf(mx, rbf[c * HT4_RSTRIDE + rr]);
