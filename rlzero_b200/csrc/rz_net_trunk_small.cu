@@ -203,6 +203,14 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
 #pragma unroll
         for (int j = 0; j < 8; ++j) ld_shared_v4(srow + (((uint32_t)j ^ sw) << 4), res[j]);
       }
+      // this layer's 64 biases into registers while the MMAs still run (the epilogue is on the critical path of every
+      // layer: nothing else overlaps it)
+      float4 bias_r[16];
+      {
+        const float4* bias4 = reinterpret_cast<const float4*>(s_bias + l * 128 + col0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bias_r[i] = bias4[i];
+      }
       rz::mbar_wait(bar_tfull, (uint32_t)l & 1u);
       rz::tc_fence_after();
       if (p.probe && board == 0 && leader && warp == 2 && lane == 0) p.probe[l * 8 + 2] = rz::globaltimer_ns();
@@ -213,7 +221,6 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
       rz::tmem_ld_wait();
       const bool stamp = p.probe && board == 0 && leader && warp == 2 && lane == 0;
       if (stamp) p.probe[l * 8 + 3] = rz::globaltimer_ns();
-      const float4* bias4 = reinterpret_cast<const float4*>(s_bias + l * 128 + col0);
       if (!last) {
         const uint32_t srow = dst + row_off;
         const uint32_t sw = (srow >> 7) & 7u;
@@ -223,7 +230,7 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
         for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 b0 = bias4[ch * 8 + j * 2], b1 = bias4[ch * 8 + j * 2 + 1];
+            const float4 b0 = bias_r[ch * 8 + j * 2], b1 = bias_r[ch * 8 + j * 2 + 1];
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint32_t packed[4];
 #pragma unroll
@@ -263,7 +270,7 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
         for (int ch = 0; ch < 2; ++ch) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 b0 = bias4[ch * 8 + j * 2], b1 = bias4[ch * 8 + j * 2 + 1];
+            const float4 b0 = bias_r[ch * 8 + j * 2], b1 = bias_r[ch * 8 + j * 2 + 1];
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
