@@ -299,6 +299,13 @@ int rz_tree_select(const rz_tree_desc* t, void* stream);
 int rz_tree_expand_backup(const rz_tree_desc* t, const float* prior, int prior_is_log,
                           const float* value, const double* value64, float noise_eps, float noise_alpha,
                           unsigned long long seed, void* stream);
+/* rz_tree_expand_backup of wave w and rz_tree_select of wave w + 1 in ONE launch (one leaf per tree and wave only): the same
+   results as the two calls in sequence, one kernel boundary less per wave.  `value64` as in rz_tree_expand_backup
+   (AlphaZero flavour) / rz_tree_expand_backup_dm (DeepMindMCTS flavour: the evaluator's returns [G][2]).
+   Replaces the tail of one _playout and the head of the next (rlzero/mcts/alphazero_mcts.py:41-71). */
+int rz_tree_expand_backup_select(const rz_tree_desc* t, const float* prior, int prior_is_log, const float* value,
+                                 const double* value64, float noise_eps, float noise_alpha, unsigned long long seed,
+                                 void* stream);
 /* the same step with host-supplied randomness (seeded parity with the reference, whose noise comes from the global
    numpy stream, node.py:63-69; SURVEY 8 b2 `noise*|NULL`).  Either of
      noise64 [G*K][AS] float64: a Dirichlet sample per leaf, entry s = the noise of the child reached by action s

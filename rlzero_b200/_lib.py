@@ -107,6 +107,8 @@ SIGNATURES = {
     'rz_tree_select': (C.c_int, [_TD, _vp]),
     'rz_tree_expand_backup': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,
                                         C.c_ulonglong, _vp]),
+    'rz_tree_expand_backup_select': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,
+                                               C.c_ulonglong, _vp]),
     'rz_tree_expand_backup_ex': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,
                                            C.c_ulonglong, _vp, _vp, _vp]),
     'rz_tree_expand_backup_dm': (C.c_int, [_TD, _vp, C.c_int, _vp, _vp, C.c_float, C.c_float,

@@ -583,6 +583,34 @@ rz_expand_backup_kernel(rz_tree_desc t, const float* __restrict__ prior, int pri
 }
 
 // ---------------------------------------------------------------------------
+// Expand + backup of wave w followed, in the same launch, by the selection of wave w + 1 (one leaf per tree and wave
+// only).  The two halves belong to the same warp and the same tree, so nothing but a warp barrier lies between them:
+// one launch and one kernel boundary less per wave, and the root's edge blocks the backup just touched are still in
+// cache for the descent.  It matters where a wave is a handful of short kernels (a single game: ~5 us of ~50).
+// ---------------------------------------------------------------------------
+template <class GM, bool DM>
+__global__ void __launch_bounds__(RZ_TREE_THREADS)
+rz_expand_backup_select_kernel(rz_tree_desc t, const float* __restrict__ prior, int prior_is_log,
+                               const float* __restrict__ value, const double* __restrict__ value64,
+                               float noise_eps, float noise_alpha, unsigned long long seed, long long global_offset) {
+  rz::grid_dep_wait();     // programmatic dependent launch: see rz_common.cuh
+  rz::grid_dep_launch();
+  const int g = blockIdx.x * RZ_TREE_WARPS + (threadIdx.x >> 5);
+  if (g >= t.n_trees) return;
+  const rz_geom q = rz_geom_of(t.game);
+  if (t.seed_dev) seed += *t.seed_dev;
+  rz_expand_backup_one<GM, DM>(t, g, g, false, q, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed,
+                               global_offset, nullptr, nullptr);
+  __syncwarp();            // the lanes read each other's updates of the path below
+  int32_t* rmeta = t.root_meta + (size_t)g * RZ_META_STRIDE;
+  if (rmeta[RZ_META_STATUS] != RZ_ACTIVE || (DM && t.root_O[g] != 0)) {
+    if (rz_lane() == 0) t.depth[g] = -1;
+    return;
+  }
+  rz_select_one<GM, DM>(t, g, g, q, rmeta);
+}
+
+// ---------------------------------------------------------------------------
 // K7: root policy  pi = softmax(log(N + 1e-10) / T) over the root's children and move sampling
 // (alphazero_mcts.py:86-94, 144-148).  Sampling mirrors numpy.random.choice: first index
 // whose normalised cumulative probability exceeds u.
@@ -1040,6 +1068,30 @@ extern "C" int rz_tree_expand_backup_ex(const rz_tree_desc* t, const float* prio
   RZ_REQUIRE(!noise64 || (noise_eps > 0.0f && prior), "rz_tree_expand_backup_ex: noise64 needs noise_eps > 0 and a prior");
   return rz_expand_backup_launch(t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, stream, noise64,
                                  prior64);
+}
+
+extern "C" int rz_tree_expand_backup_select(const rz_tree_desc* t, const float* prior, int prior_is_log,
+                                            const float* value, const double* value64, float noise_eps,
+                                            float noise_alpha, unsigned long long seed, void* stream) {
+  if (rz_check_tree(t, "rz_tree_expand_backup_select")) return -1;
+  RZ_REQUIRE(t->leaves_per_tree <= 1, "rz_tree_expand_backup_select: one leaf per tree and wave only (leaves_per_tree %d)",
+             t->leaves_per_tree);
+  RZ_REQUIRE(value || value64, "rz_tree_expand_backup_select: null value");
+  RZ_REQUIRE(prior || !t->store_priors, "rz_tree_expand_backup_select: null prior with store_priors");
+  RZ_REQUIRE(noise_eps >= 0.0f && noise_eps <= 1.0f, "rz_tree_expand_backup_select: noise_eps %f", noise_eps);
+  RZ_REQUIRE(noise_eps == 0.0f || noise_alpha > 0.0f, "rz_tree_expand_backup_select: noise_alpha %f", noise_alpha);
+  if (t->n_trees == 0) return 0;
+  const dim3 grid = rz_tree_grid(t->n_trees);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool go = t->game.game_type == RZ_GAME_GO, dm = t->flavour == RZ_FLAVOUR_DEEPMIND;
+#define RZ_EBS_ARGS *t, prior, prior_is_log, value, value64, noise_eps, noise_alpha, seed, t->global_offset
+  if (go && dm) rz_launch_pdl(rz_expand_backup_select_kernel<rz_go_game, true>, grid, RZ_TREE_THREADS, 0, st, RZ_EBS_ARGS);
+  else if (go) rz_launch_pdl(rz_expand_backup_select_kernel<rz_go_game, false>, grid, RZ_TREE_THREADS, 0, st, RZ_EBS_ARGS);
+  else if (dm) rz_launch_pdl(rz_expand_backup_select_kernel<rz_line_game, true>, grid, RZ_TREE_THREADS, 0, st, RZ_EBS_ARGS);
+  else rz_launch_pdl(rz_expand_backup_select_kernel<rz_line_game, false>, grid, RZ_TREE_THREADS, 0, st, RZ_EBS_ARGS);
+#undef RZ_EBS_ARGS
+  RZ_LAUNCH_CHECK("rz_tree_expand_backup_select");
+  return 0;
 }
 
 static int rz_expand_backup_launch(const rz_tree_desc* t, const float* prior, int prior_is_log,

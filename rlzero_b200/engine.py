@@ -15,6 +15,7 @@ PyTorch is used for device memory, streams and CUDA graphs only.
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -292,6 +293,13 @@ class SearchForest(object):
                                                float(noise_alpha), int(seed), self._s()),
                 'rz_tree_expand_backup')
 
+    def expand_backup_select(self, prior_is_log=False, noise_eps=0.0, noise_alpha=0.3, seed=0, value64=None):
+        """expand_backup of this wave and select of the next one in one launch (one leaf per tree and wave)."""
+        L.check(self.lib.rz_tree_expand_backup_select(C.byref(self.desc), L.ptr(self.prior), int(prior_is_log),
+                                                      L.ptr(self.value), L.ptr(value64), float(noise_eps),
+                                                      float(noise_alpha), int(seed), self._s()),
+                'rz_tree_expand_backup_select')
+
     def eval_closed_form(self, eval_id):
         L.check(self.lib.rz_eval_closed_form(C.byref(self.desc), int(eval_id), L.ptr(self.prior),
                                              L.ptr(self.value), self._s()), 'rz_eval_closed_form')
@@ -345,25 +353,62 @@ class SearchForest(object):
             for _ in range(n_waves):
                 wave()
             return
+        # one leaf per tree and wave, no host-supplied priors: the backup of wave w and the selection of wave w + 1 share a
+        # launch (rz_tree_expand_backup_select).  A search of n waves is  select | (n - 1) x [evaluate, backup + select] |
+        # [evaluate, backup]  -- two captured graphs instead of one
+        fuse = (self.K == 1 and getattr(evaluator, 'prior64', None) is None
+                and os.environ.get('RZ_FUSE_SELECT', '1') != '0')
+        value64 = getattr(evaluator, 'value64', None)
+
+        def mid():
+            evaluator(self)
+            self.expand_backup_select(prior_is_log, noise_eps, noise_alpha, 0, value64=value64)
+
+        def last():
+            evaluator(self)
+            self.expand_backup(prior_is_log, noise_eps, noise_alpha, 0, value64=value64,
+                               prior64=getattr(evaluator, 'prior64', None))
+
         # weights_version: a captured graph holds the weight pointers (and the fused head's filter taps) and the
         # evaluator's activation buffers by value, so repacked weights or re-allocated buffers need a new capture
         # (NativeForward bumps it in both cases).  The cache entry keeps the evaluator alive: its id() is the key
         key = (id(evaluator), getattr(evaluator, 'weights_version', 0), prior_is_log, float(noise_eps),
-               float(noise_alpha))
+               float(noise_alpha), fuse)
         graphs = self.__dict__.setdefault('_graphs', {})
         if key not in graphs and len(graphs) >= 8:
             graphs.clear()                                              # bounded cache
         if key not in graphs:
-            # warm-up outside capture (lazy module loads etc.), then capture one wave
+            # warm-up outside capture (lazy module loads etc.), then capture
+            if fuse:
+                self.select()
+                mid()                       # wave 1; leaves the leaves of wave 2 selected
+                n_waves -= 1
+                torch.cuda.synchronize()
+                g_mid, g_last = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_mid):
+                    mid()
+                with torch.cuda.graph(g_last):
+                    last()
+                graphs[key] = (g_mid, evaluator, g_last)
+                for _ in range(n_waves - 1):
+                    g_mid.replay()
+                g_last.replay()
+                return
             wave()
             n_waves -= 1
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 wave()
-            graphs[key] = (g, evaluator)
+            graphs[key] = (g, evaluator, None)
             # the capture itself did not run the wave
-        g = graphs[key][0]
+        g, _, g_last = graphs[key]
+        if g_last is not None:
+            self.select()
+            for _ in range(n_waves - 1):
+                g.replay()
+            g_last.replay()
+            return
         for _ in range(n_waves):
             g.replay()
 
