@@ -372,6 +372,34 @@ def test_one_launch_trunk_is_bit_identical_to_the_layer_kernels(size, blocks, n)
     assert torch.equal(la2, la) and torch.equal(va2, va)
 
 
+def test_one_launch_trunk_on_a_rectangular_board_and_at_the_layer_limit():
+    """The one-launch trunk with H != W (9 rows x 11 columns in the 16-stride layout), with 24 layers behind the stem
+    (its limit: the biases of all layers sit in shared memory), and the fallback to the per-layer kernels beyond it."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, ResNetPolicyValueNet
+    torch.manual_seed(3)
+    rect = ResNetPolicyValueNet(9, n_blocks=2, board_width=11).cuda().eval()
+    a = NativeForward(rect, max_batch=3)
+    b = NativeForward(rect, max_batch=3)
+    b.small_batch_max = 0
+    x = (np.random.RandomState(0).rand(3, 4, 9, 11) < 0.3).astype(np.float32)
+    la, va = (t.clone() for t in a.forward_planes(x))
+    lb, vb = (t.clone() for t in b.forward_planes(x))
+    assert a.kernels_per_forward(3) == 3 and torch.equal(la, lb) and torch.equal(va, vb)
+    deep = ResNetPolicyValueNet(8, n_blocks=12).cuda().eval()          # 24 layers behind the stem
+    a = NativeForward(deep, max_batch=2)
+    b = NativeForward(deep, max_batch=2)
+    b.small_batch_max = 0
+    x = _random_boards(2, 8, 1)
+    la, va = (t.clone() for t in a.forward_planes(x))
+    lb, vb = (t.clone() for t in b.forward_planes(x))
+    assert a.trunk_small is not None and a.trunk_small['n'] == 24 and torch.equal(la, lb) and torch.equal(va, vb)
+    deeper = ResNetPolicyValueNet(8, n_blocks=13).cuda().eval()        # 26 layers: per-layer kernels
+    c = NativeForward(deeper, max_batch=2)
+    assert c.trunk_small is None
+    lc, vc = c.forward_planes(x)
+    assert torch.isfinite(lc[:, :64]).all() and torch.isfinite(vc).all()
+
+
 def test_small_and_large_batch_paths_agree_bit_for_bit():
     """Batch invariance ACROSS the path boundary: a board evaluated alone or among 100 (one-launch trunk, one CTA pair per
     board) gives exactly the logits and value it gets among 300 (one launch per layer, persistent CTA pairs over
