@@ -567,6 +567,15 @@ int rz_net_conv3x3_tc2_head_ex(const void* act_in, const void* weight, const flo
 int rz_net_trunk_small(const void* act_in, const void* weights, const float* biases, int n_layers,
                        unsigned relu_mask, unsigned res_mask, int n_boards, int board_size, int board_cols,
                        const float* w1x1_host, const float* b1x1_host, float* feat, void* stream);
+/* the same with the modes of the float32-accurate path of the reference's own PolicyValueNet (flags 8 | 256 / 16 / 32 of
+   rz_net_conv3x3_tc2[_head_ex]): bit l of n64_mask = layer l has 64 real output channels (N = 64 MMAs) and leaves as
+   [hi 0..63 | lo 0..63]; bit l of split_in_mask = layer l takes such a row against weights [Whi | Wlo] (three products
+   per tap); head_f32 = the 1x1 head convolutions read the float32 activations.  conv2 + conv3 + act_conv1 / val_conv1
+   (policy_value_net.py:37-38,41,47) of one position in one launch, bit-identical to the two per-layer launches. */
+int rz_net_trunk_small_ex(const void* act_in, const void* weights, const float* biases, int n_layers,
+                          unsigned relu_mask, unsigned res_mask, unsigned n64_mask, unsigned split_in_mask, int head_f32,
+                          int n_boards, int board_size, int board_cols, const float* w1x1_host,
+                          const float* b1x1_host, float* feat, void* stream);
 /* profiling aid: rz_net_trunk_small writes four %globaltimer stamps per layer of board 0 (inputs ready / MMAs issued /
    accumulator complete / layer stored) into this device buffer of 4 * n_layers uint64; NULL (the default) = off. */
 int rz_debug_set_probe(void* device_buffer);

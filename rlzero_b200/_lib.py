@@ -164,6 +164,8 @@ SIGNATURES = {
     'rz_net_conv3x3_tc2_head': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                                           _vp, _vp, C.c_int, _vp]),
     'rz_debug_set_probe': (C.c_int, [_vp]),
+    'rz_net_trunk_small_ex': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     'rz_net_trunk_small': (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
                                       _vp]),
     'rz_net_conv3x3_tc2_head_ex': (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

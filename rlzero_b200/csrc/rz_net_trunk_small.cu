@@ -47,6 +47,10 @@ struct TrunkParams {
   int n_boards;
   int board, board_w;
   unsigned relu_mask, res_mask;    // bit l: ReLU after layer l / layer l adds the activation two layers back
+  // the float32-accurate layers of the reference's own PolicyValueNet (mode 'tc32', rz_net_conv3x3_tc2 flags 8|256 / 16 / 32):
+  unsigned n64_mask;               // bit l: 64 real output channels, N = 64 MMAs, the row leaves as [hi 0..63 | lo 0..63]
+  unsigned split_in_mask;          // bit l: input [hi 0..63 | lo 0..63] against weights [Whi | Wlo]: hi*Whi + lo*Whi + hi*Wlo
+  int head_f32;                    // the 1x1 head convolutions read the float32 activations, not their bf16 rounding
   unsigned long long* probe;       // timing probe (rz_debug_set_probe; null in production): 4 globaltimer stamps / layer
 };
 
@@ -153,6 +157,9 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
         rz::tc_fence_after();
         if (p.probe && board == 0 && lane == 0) p.probe[l * 8 + 0] = rz::globaltimer_ns();
         const uint32_t a_buf = a_base + (uint32_t)(l & 1) * A_BUF_BYTES;
+        const bool split_in = (p.split_in_mask >> l) & 1u;
+        const uint32_t idesc_l = ((p.n64_mask >> l) & 1u) ? rz::umma_idesc_bf16(256, 64) : idesc;
+        const int n_prod = split_in ? 3 : 2;
         uint32_t acc = 0;
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap, ++idx) {
@@ -160,13 +167,14 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
           const int shift = HALO + (tap / 3 - 1) * 16 + (tap % 3 - 1);
           rz::mbar_wait(bar_wfull + 8 * slot, (uint32_t)(idx / N_SLOTS) & 1u);
           rz::tc_fence_after();
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t adesc = rz::umma_desc_sw128(a_buf + (uint32_t)kb * A_KB_BYTES + (uint32_t)shift * 128u);
-            const uint64_t bdesc = rz::umma_desc_sw128(smem_base + (uint32_t)slot * SLOT_BYTES + (uint32_t)kb * B_TILE_BYTES);
+          for (int pr = 0; pr < n_prod; ++pr) {
+            const int ka = split_in ? (pr == 1 ? 1 : 0) : pr;      // k-block of the activation tile
+            const int kw = split_in ? (pr == 2 ? 1 : 0) : pr;      // k-block of the weights
+            const uint64_t adesc = rz::umma_desc_sw128(a_buf + (uint32_t)ka * A_KB_BYTES + (uint32_t)shift * 128u);
+            const uint64_t bdesc = rz::umma_desc_sw128(smem_base + (uint32_t)slot * SLOT_BYTES + (uint32_t)kw * B_TILE_BYTES);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              rz::umma_bf16_pair_pred(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc, issue);
+              rz::umma_bf16_pair_pred(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc_l, acc, issue);
               acc = 1;
             }
           }
@@ -195,6 +203,10 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
       const bool last = l == L - 1;
       const bool relu = (p.relu_mask >> l) & 1u;
       const bool have_res = ((p.res_mask >> l) & 1u) && valid;
+      // 64-channel layer with split output: both column halves of the epilogue read accumulator columns 0..63; the
+      // upper half's threads write the rounding residues of the (ReLU'd) float32 values after their bf16 high parts
+      const bool split_out = (p.n64_mask >> l) & 1u;
+      const int csrc = split_out ? 0 : col0;
       const uint32_t dst = a_base + (uint32_t)((l + 1) & 1) * A_BUF_BYTES;   // next layer's input = this layer's residual
       uint32_t res[8][4];
       if (have_res) {
@@ -207,7 +219,7 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
       // layer: nothing else overlaps it)
       float4 bias_r[16];
       {
-        const float4* bias4 = reinterpret_cast<const float4*>(s_bias + l * 128 + col0);
+        const float4* bias4 = reinterpret_cast<const float4*>(s_bias + l * 128 + csrc);
 #pragma unroll
         for (int i = 0; i < 16; ++i) bias_r[i] = bias4[i];
       }
@@ -217,7 +229,7 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
       uint32_t acc[2][32];
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch)
-        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + ch * 32), acc[ch]);
+        rz::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(csrc + ch * 32), acc[ch]);
       rz::tmem_ld_wait();
       const bool stamp = p.probe && board == 0 && leader && warp == 2 && lane == 0;
       if (stamp) p.probe[l * 8 + 3] = rz::globaltimer_ns();
@@ -244,6 +256,10 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
                 v1 += __uint_as_float(rw & 0xffff0000u);
               }
               packed[e] = relu ? rz::pack_bf16x2_relu(v0, v1) : rz::pack_bf16x2(v0, v1);
+              if (split_out && hsel == 1) {
+                if (relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+                packed[e] = rz::pack_bf16x2(v0 - __uint_as_float(packed[e] << 16), v1 - __uint_as_float(packed[e] & 0xffff0000u));
+              }
               if (!valid) packed[e] = 0u;
             }
             const uint32_t chunk = (uint32_t)(ch * 4 + j);
@@ -284,7 +300,11 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
               }
               uint32_t pk = relu ? rz::pack_bf16x2_relu(v0, v1) : rz::pack_bf16x2(v0, v1);
               if (!valid) pk = 0u;
-              const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+              float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+              if (p.head_f32) {
+                r0 = valid ? (relu ? fmaxf(v0, 0.0f) : v0) : 0.0f;
+                r1 = valid ? (relu ? fmaxf(v1, 0.0f) : v1) : 0.0f;
+              }
               const int cc = ch * 32 + c;
 #pragma unroll
               for (int f = 0; f < 6; ++f)
@@ -317,9 +337,10 @@ rz_trunk_small_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
 
 }  // namespace
 
-extern "C" int rz_net_trunk_small(const void* act_in, const void* weights, const float* biases, int n_layers,
-                                  unsigned relu_mask, unsigned res_mask, int n_boards, int board_size, int board_cols,
-                                  const float* w1x1_host, const float* b1x1_host, float* feat, void* stream) {
+static int trunk_small_entry(const void* act_in, const void* weights, const float* biases, int n_layers,
+                             unsigned relu_mask, unsigned res_mask, unsigned n64_mask, unsigned split_in_mask, int head_f32,
+                             int n_boards, int board_size, int board_cols, const float* w1x1_host,
+                             const float* b1x1_host, float* feat, void* stream) {
   RZ_REQUIRE(act_in && weights && biases && w1x1_host && b1x1_host && feat, "rz_net_trunk_small: null argument");
   RZ_REQUIRE(n_layers >= 1 && n_layers <= MAX_LAYERS, "rz_net_trunk_small: n_layers %d not in [1,%d]", n_layers, MAX_LAYERS);
   RZ_REQUIRE(n_boards >= 0, "rz_net_trunk_small: n_boards %d", n_boards);
@@ -339,6 +360,9 @@ extern "C" int rz_net_trunk_small(const void* act_in, const void* weights, const
   p.board_w = board_cols;
   p.relu_mask = relu_mask;
   p.res_mask = res_mask;
+  p.n64_mask = n64_mask;
+  p.split_in_mask = split_in_mask;
+  p.head_f32 = head_f32;
   p.probe = rz_probe_buffer;
   for (int i = 0; i < 6 * 128; ++i) head.w[i] = w1x1_host[i];
   for (int i = 0; i < 6; ++i) head.b[i] = b1x1_host[i];
@@ -364,4 +388,23 @@ extern "C" int rz_net_trunk_small(const void* act_in, const void* weights, const
   cudaError_t e = cudaLaunchKernelEx(&cfg, rz_trunk_small_kernel, tmap_act, tmap_w, p, head);
   if (e != cudaSuccess) { rz_set_error("rz_net_trunk_small: launch failed: %s", cudaGetErrorString(e)); return -2; }
   return 0;
+}
+
+extern "C" int rz_net_trunk_small(const void* act_in, const void* weights, const float* biases, int n_layers,
+                                  unsigned relu_mask, unsigned res_mask, int n_boards, int board_size, int board_cols,
+                                  const float* w1x1_host, const float* b1x1_host, float* feat, void* stream) {
+  return trunk_small_entry(act_in, weights, biases, n_layers, relu_mask, res_mask, 0u, 0u, 0, n_boards, board_size, board_cols,
+                           w1x1_host, b1x1_host, feat, stream);
+}
+
+// the same with the modes of the float32-accurate path of the reference's own PolicyValueNet (rz_net_conv3x3_tc2 flags
+// 8 | 256: n64_mask, 16: split_in_mask, 32: head_f32): conv2 and conv3 + the 1x1 head convolutions in one launch
+extern "C" int rz_net_trunk_small_ex(const void* act_in, const void* weights, const float* biases, int n_layers,
+                                     unsigned relu_mask, unsigned res_mask, unsigned n64_mask, unsigned split_in_mask,
+                                     int head_f32, int n_boards, int board_size, int board_cols,
+                                     const float* w1x1_host, const float* b1x1_host, float* feat, void* stream) {
+  RZ_REQUIRE(!(n64_mask & res_mask) && !(n64_mask >> (n_layers - 1) & 1u),
+             "rz_net_trunk_small_ex: a 64-channel split-output layer has no skip input and is not the last layer");
+  return trunk_small_entry(act_in, weights, biases, n_layers, relu_mask, res_mask, n64_mask, split_in_mask, head_f32,
+                           n_boards, board_size, board_cols, w1x1_host, b1x1_host, feat, stream);
 }

@@ -273,6 +273,14 @@ class NativeForward(object):
         # small-batch latency path (rz_net_trunk_small.cu): the 128 -> 128 layers behind the stem in one stacked buffer
         # [layer][tap][cout][cin]; the per-layer tensors become views of it, so both paths read the same bytes
         self.trunk_small = None
+        if self.mode == 'tc32' and self.S == 16:
+            # conv2 (64 channels, split output) and conv3 (split input, float32 head features) of the reference's own net
+            l2, l3 = self.layers[1], self.layers[2]
+            wst = torch.stack([l2['w'], l3['w']]).contiguous()
+            bst = torch.stack([l2['b'], l3['b']]).contiguous()
+            l2['w'], l2['b'], l3['w'], l3['b'] = wst[0], bst[0], wst[1], bst[1]
+            self.trunk_small = dict(w=wst, b=bst, n=2, relu_mask=int(bool(l2['relu'])) | (int(bool(l3['relu'])) << 1),
+                                    res_mask=0, n64_mask=1, split_in_mask=2, head_f32=1)
         if (self.mode == 'tc' and self.S == 16 and 2 <= len(self.layers) <= 25
                 and all(l['cin'] == 128 and l['cout'] == 128 for l in self.layers[1:])
                 and self.layers[1]['skip'] is None):
@@ -429,6 +437,17 @@ class NativeForward(object):
     def _trunk_and_heads(self, n, logp, value, stem_done=False):
         s = L.stream_ptr()
         lib = self.lib
+        if self.mode == 'tc32' and self.trunk_small is not None and n <= self.small_batch_max:
+            # few boards: conv2 + conv3 + the 1x1 heads in one launch (rz_net_trunk_small_ex), then the FC heads
+            ts = self.trunk_small
+            L.check(lib.rz_net_trunk_small_ex(
+                L.ptr(self.bufs[0]), L.ptr(ts['w']), L.ptr(ts['b']), ts['n'], ts['relu_mask'], ts['res_mask'],
+                ts['n64_mask'], ts['split_in_mask'], ts['head_f32'], n, self.H, self.W,
+                self.w1x1_host.ctypes.data_as(C.c_void_p), self.b1x1_host.ctypes.data_as(C.c_void_p), L.ptr(self.feat), s),
+                'rz_net_trunk_small_ex')
+            L.check(lib.rz_net_heads_tc(C.byref(self.hdesc), L.ptr(self.feat), L.ptr(logp), L.ptr(value), n, s),
+                    'rz_net_heads_tc')
+            return
         if self.mode == 'tc32':
             # conv2 (one K = 128 pass, split output) and conv3 (three products per tap, fp32 features), then the heads
             l2, l3 = self.layers[1], self.layers[2]
@@ -533,6 +552,8 @@ class NativeForward(object):
     def kernels_per_forward(self, n=None):
         """Kernel launches of one forward_boards call of ``n`` boards (for bench.py's gpu_launches)."""
         if self.mode == 'tc32':
+            if n is not None and self.trunk_small is not None and n <= self.small_batch_max:
+                return 3                                    # stem, conv2 + conv3 + 1x1 heads in one launch, FC heads
             return 4                                        # stem, conv2, conv3 + 1x1 heads, FC heads
         if (n is not None and self.mode == 'tc' and self.trunk_small is not None and n <= self.small_batch_max
                 and self.fused_head and self.conv_rev == 2 and self.stem is not None and self.fused_stem):

@@ -400,6 +400,24 @@ def test_one_launch_trunk_on_a_rectangular_board_and_at_the_layer_limit():
     assert torch.isfinite(lc[:, :64]).all() and torch.isfinite(vc).all()
 
 
+@pytest.mark.parametrize('size,n', [(15, 1), (15, 9), (9, 3), (6, 2), (3, 1)])
+def test_one_launch_trunk_of_the_reference_net_is_bit_identical(size, n):
+    """The float32-accurate path of the reference's own PolicyValueNet for a few boards: conv2 (64 channels, split
+    output), conv3 (split input) and the 1x1 head convolutions in ONE launch (rz_net_trunk_small_ex) against the two
+    per-layer launches -- equal bit for bit, so a single-game search evaluates exactly what a batched one does."""
+    from rlzero_b200.games.gomoku.policy_value_net import NativeForward, PolicyValueNet
+    torch.manual_seed(size)
+    net = PolicyValueNet(size).cuda().eval()
+    a = NativeForward(net, max_batch=n)
+    b = NativeForward(net, max_batch=n)
+    b.small_batch_max = 0
+    assert a.mode == 'tc32' and a.trunk_small is not None and a.kernels_per_forward(n) == 3 and b.kernels_per_forward(n) == 4
+    x = _random_boards(n, size, 7)
+    la, va = (t.clone() for t in a.forward_planes(x))
+    lb, vb = (t.clone() for t in b.forward_planes(x))
+    assert torch.isfinite(la[:, :size * size]).all() and torch.equal(la, lb) and torch.equal(va, vb)
+
+
 def test_small_and_large_batch_paths_agree_bit_for_bit():
     """Batch invariance ACROSS the path boundary: a board evaluated alone or among 100 (one-launch trunk, one CTA pair per
     board) gives exactly the logits and value it gets among 300 (one launch per layer, persistent CTA pairs over
