@@ -37,6 +37,7 @@ struct HeadsTcParams {
   float* value;           // [n]
   int n_boards, A, AS, P;
   int n_wslots;           // weight ring slots (2..4)
+  int live_per_plane;     // cluster kernel: 64-feature chunks of a plane that hold real squares (the rest is zero padding)
   int w_box;              // rows per TMA box of the policy weights (divides AS)
   int tmem_cols;          // power of two >= AS + 64
   unsigned long long* probe;   // timing probe (rz_debug_set_probe; null in production): 8 stamps per chunk of CTA 0
@@ -313,14 +314,21 @@ rz_heads_tc4_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_c
   const int r = tid & 127, khalf = tid >> 7;          // this thread builds row r, k in [32*khalf, 32*khalf + 32)
   const bool row_live = b0 + r < p.n_boards;
   const int K6 = 6 * P, K4 = 4 * P;
-  const int n_chunks = (K6 + 63) >> 6, n_pol = K4 >> 6;
-  const int n_my = (n_chunks - (int)rank + HT4_CLUSTER - 1) / HT4_CLUSTER;      // own chunks c = rank + HT4_CLUSTER i
-  const bool has_pol = (int)rank < n_pol;
-  const int first_val = (int)rank + (((int)rank < n_pol) ? (n_pol - (int)rank + HT4_CLUSTER - 1) / HT4_CLUSTER * HT4_CLUSTER : 0);
-  const bool has_val = first_val < n_chunks;
+  // Chunks that hold only padding squares are skipped: a plane of the padded layout is P = S*S features of which the
+  // first H*S are rows of the board (their zero features times zero weights add exact zeros, so the result is the
+  // same bit for bit): 6 of 24 chunks for a 3x3 board at stride 16, 12 for 6x6, all 24 for 15x15.  The LIVE chunks,
+  // numbered j = 0, 1, ... in ascending k, go round robin over the CTAs: CTA r takes j = r, r + 4, ...
+  const int cpp = P >> 6, lpp = p.live_per_plane;               // chunks per plane: all, live
+  const int n_live = 6 * lpp, n_pol_live = 4 * lpp;
+  auto chunk_of = [&](int j) { return (j / lpp) * cpp + (j % lpp); };
+  const int n_my = (n_live - (int)rank + HT4_CLUSTER - 1) / HT4_CLUSTER;
+  const bool has_pol = (int)rank < n_pol_live;
+  const int first_val_j = (int)rank + (((int)rank < n_pol_live) ? (n_pol_live - (int)rank + HT4_CLUSTER - 1) / HT4_CLUSTER * HT4_CLUSTER : 0);
+  const bool has_val = first_val_j < n_live;
+  const int n_pol = K4 >> 6;
 
   auto issue_w = [&](int i) {                         // weights of own chunk i into stage i & 1 (thread 0)
-    const int c = (int)rank + HT4_CLUSTER * i, s = i & 1;
+    const int c = chunk_of((int)rank + HT4_CLUSTER * i), s = i & 1;
     const uint32_t w_hi = base + (uint32_t)s * stage_bytes + 2 * HT_A_BYTES, w_lo = w_hi + ht_w_rows(AS) * 128u;
     if (c < n_pol) {
       rz::mbar_expect_tx(bar_w + 8 * s, 2u * (uint32_t)AS * 128u);
@@ -360,7 +368,7 @@ rz_heads_tc4_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_c
   const float* frow = p.feat + (size_t)(b0 + r) * K6 + 32 * khalf;
   float4 pre[2][8];                                   // the features of own chunks i, i + 1 in registers
   auto prefetch = [&](int i, float4 (&dst)[8]) {
-    const int c = (int)rank + HT4_CLUSTER * i;
+    const int c = chunk_of((int)rank + HT4_CLUSTER * i);
     const int k0 = c * 64 + 32 * khalf;
     const bool live = row_live && i < n_my && k0 < K6;   // K6 is a multiple of 32
     const float4* src = reinterpret_cast<const float4*>(frow + (size_t)c * 64);
@@ -373,7 +381,7 @@ rz_heads_tc4_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_c
   const uint32_t idesc_v = rz::umma_idesc_bf16(128, 64);
   const uint32_t idesc_p = rz::umma_idesc_bf16(128, AS);
   auto step = [&](const int i, float4 (&cur)[8]) {
-    const int c = (int)rank + HT4_CLUSTER * i, s = i & 1;
+    const int j_live = (int)rank + HT4_CLUSTER * i, c = chunk_of(j_live), s = i & 1;
     const uint32_t st = base + (uint32_t)s * stage_bytes;
     const uint32_t a_hi = st, a_lo = st + HT_A_BYTES, w_hi = st + 2 * HT_A_BYTES, w_lo = w_hi + ht_w_rows(AS) * 128u;
     const bool policy = c < n_pol;
@@ -408,7 +416,7 @@ rz_heads_tc4_kernel(const __grid_constant__ CUtensorMap tmap_whi, const __grid_c
       const uint64_t d_whi = rz::umma_desc_sw128(w_hi), d_wlo = rz::umma_desc_sw128(w_lo);
       const uint32_t d = tmem_base + (policy ? 0u : (uint32_t)AS);
       const uint32_t idesc = policy ? idesc_p : idesc_v;
-      const bool first = policy ? (i == 0) : (c == first_val);
+      const bool first = policy ? (i == 0) : (j_live == first_val_j);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         rz::umma_bf16(d, d_ahi + (uint64_t)(2 * kk), d_whi + (uint64_t)(2 * kk), idesc, (!first || kk > 0) ? 1u : 0u);
@@ -525,6 +533,8 @@ extern "C" int rz_net_heads_tc(const rz_heads_desc* h, const float* feat, float*
   p.feat = feat; p.bp = h->bp; p.bv1 = h->bv1; p.wv2 = h->wv2; p.bv2 = h->bv2; p.logp = logp; p.value = value;
   p.n_boards = n_boards; p.A = A; p.AS = AS; p.P = P;
   p.probe = rz_probe_buffer;
+  // rows 0 .. H-1 of a plane are real squares: ceil(H*S / 64) of its P / 64 chunks (P is 64 or 256 in the cluster kernel)
+  p.live_per_plane = (P % 64 == 0) ? ((h->board_size * S + 63) / 64 < P / 64 ? (h->board_size * S + 63) / 64 : P / 64) : 0;
   p.w_box = (AS % 128 == 0) ? 128 : ((AS % 64 == 0) ? 64 : 32);
   p.tmem_cols = 32;
   while (p.tmem_cols < AS + 64) p.tmem_cols *= 2;
@@ -541,7 +551,7 @@ extern "C" int rz_net_heads_tc(const rz_heads_desc* h, const float* feat, float*
   if (rz::make_tmap_2d(&t_wlo, wlo, (uint64_t)AS, (uint64_t)KP, (uint32_t)p.w_box)) return -1;
   if (rz::make_tmap_2d(&t_vhi, whi + (size_t)AS * KP, 64, (uint64_t)KP, 64)) return -1;
   if (rz::make_tmap_2d(&t_vlo, wlo + (size_t)AS * KP, 64, (uint64_t)KP, 64)) return -1;
-  if (AS <= 256 && !getenv_flag_off()) {
+  if (AS <= 256 && p.live_per_plane > 0 && !getenv_flag_off()) {
     // the cluster-of-four split-K kernel
     const size_t smem4 = 2 * (2 * HT_A_BYTES + slot) + HT_CTRL_BYTES;
     static size_t attr_smem4 = 0;

@@ -384,15 +384,18 @@ class SearchForest(object):
                 mid()                       # wave 1; leaves the leaves of wave 2 selected
                 n_waves -= 1
                 torch.cuda.synchronize()
-                g_mid, g_last = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                g_mid, g_last, g_mid8 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g_mid):
                     mid()
                 with torch.cuda.graph(g_last):
                     last()
-                graphs[key] = (g_mid, evaluator, g_last)
-                for _ in range(n_waves - 1):
-                    g_mid.replay()
-                g_last.replay()
+                # eight waves per launch: for one game a wave is ~40 us of GPU time, about what the host needs to launch
+                # a graph -- the search of a single game was bound by cudaGraphLaunch calls
+                with torch.cuda.graph(g_mid8):
+                    for _ in range(8):
+                        mid()
+                graphs[key] = (g_mid, evaluator, g_last, g_mid8)
+                self._replay_fused(graphs[key], n_waves - 1)
                 return
             wave()
             n_waves -= 1
@@ -400,17 +403,25 @@ class SearchForest(object):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 wave()
-            graphs[key] = (g, evaluator, None)
+            graphs[key] = (g, evaluator, None, None)
             # the capture itself did not run the wave
-        g, _, g_last = graphs[key]
+        g, _, g_last, _ = graphs[key]
         if g_last is not None:
             self.select()
-            for _ in range(n_waves - 1):
-                g.replay()
-            g_last.replay()
+            self._replay_fused(graphs[key], n_waves - 1)
             return
         for _ in range(n_waves):
             g.replay()
+
+    @staticmethod
+    def _replay_fused(entry, n_mid):
+        """``n_mid`` x [evaluate, backup + select] (eight per graph launch while they last), then [evaluate, backup]."""
+        g_mid, _, g_last, g_mid8 = entry
+        for _ in range(n_mid // 8):
+            g_mid8.replay()
+        for _ in range(n_mid % 8):
+            g_mid.replay()
+        g_last.replay()
 
     def search(self, evaluator, n_playout=None, **kw):
         """``n_playout`` playouts for every tree (``AlphaZeroMCTS.simulate``, alphazero_mcts.py:83-85).  In
