@@ -284,7 +284,8 @@ def tree_roofline(sp, ms_per_step, peaks, n_rep=20):
         body()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        from rlzero_b200.engine import capture_graph
+        with capture_graph(g):
             for _ in range(n_rep):
                 body()
         return g
@@ -385,13 +386,11 @@ def games_per_hour(sp, args, world, dist):
 def _timed_waves(sp, waves, warm):
     import torch
     sp.warm_up()
-    for _ in range(warm):
-        sp.step_wave()
+    sp.step_waves(max(warm, 8))        # (also captures the eight-wave graph small batches are replayed with)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(waves):
-        sp.step_wave()
+    sp.step_waves(waves)
     e1.record()
     torch.cuda.synchronize()
     sp.forest.raise_faults()

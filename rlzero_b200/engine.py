@@ -23,6 +23,37 @@ import torch
 from . import _lib as L
 
 
+class capture_graph:
+    """``with capture_graph(g): ...`` = ``torch.cuda.graph(g)`` made safe against Python's garbage collector: a dead
+    object that owns a ``CUDAGraph`` (an earlier forest and its closures form reference cycles) must not be destroyed
+    WHILE a capture is under way -- freeing a graph is an operation the capturing stream does not permit, and it
+    invalidates the capture.  This torch version no longer collects garbage when a capture starts, so: collect first,
+    keep the collector off until the capture has ended."""
+
+    def __init__(self, g, **kw):
+        self.ctx = torch.cuda.graph(g, **kw)
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        self.gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            return self.ctx.__enter__()
+        except BaseException:
+            if self.gc_was_on:
+                gc.enable()
+            raise
+
+    def __exit__(self, *exc):
+        import gc
+        try:
+            return self.ctx.__exit__(*exc)
+        finally:
+            if self.gc_was_on:
+                gc.enable()
+
+
 def _round_up(x, m):
     return (x + m - 1) // m * m
 
@@ -385,13 +416,13 @@ class SearchForest(object):
                 n_waves -= 1
                 torch.cuda.synchronize()
                 g_mid, g_last, g_mid8 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g_mid):
+                with capture_graph(g_mid):
                     mid()
-                with torch.cuda.graph(g_last):
+                with capture_graph(g_last):
                     last()
                 # eight waves per launch: for one game a wave is ~40 us of GPU time, about what the host needs to launch
                 # a graph -- the search of a single game was bound by cudaGraphLaunch calls
-                with torch.cuda.graph(g_mid8):
+                with capture_graph(g_mid8):
                     for _ in range(8):
                         mid()
                 graphs[key] = (g_mid, evaluator, g_last, g_mid8)
@@ -401,7 +432,7 @@ class SearchForest(object):
             n_waves -= 1
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with capture_graph(g):
                 wave()
             graphs[key] = (g, evaluator, None, None)
             # the capture itself did not run the wave

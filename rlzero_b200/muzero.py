@@ -27,6 +27,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib as L
+from .engine import capture_graph
 from .games.gomoku.policy_value_net import NativeForward, _ResBlock
 
 
@@ -367,7 +368,7 @@ class MuZeroSearch(object):
                 self.simulate(0)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with capture_graph(g):
                     self.root(rows, meta, legal, add_noise, 0, move_ids)
                     for i in range(S):
                         self.simulate(i)

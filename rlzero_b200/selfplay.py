@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import SearchForest
+from .engine import SearchForest, capture_graph
 from .games.gomoku.policy_value_net import NativeForward
 
 
@@ -60,6 +60,7 @@ class BatchedSelfPlay(object):
         self.waves_in_move = 0
         self.moves_played = 0
         self._graph = None
+        self._graph8 = None           # eight waves per launch (small batches: a wave is shorter than a graph launch)
         self._graph_version = getattr(evaluator, 'weights_version', 0)
         self._pinned = None
 
@@ -151,7 +152,7 @@ class BatchedSelfPlay(object):
         torch.cuda.synchronize()
         if getattr(self.evaluator, 'graph_capturable', False):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with capture_graph(g):
                 self._wave()
             self._graph = g
         self.waves_in_move += 1
@@ -162,9 +163,10 @@ class BatchedSelfPlay(object):
         if self._graph is not None and v != self._graph_version:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with capture_graph(g):
                 self._wave()
             self._graph = g
+            self._graph8 = None
         self._graph_version = v
 
     def step_wave(self):
@@ -178,6 +180,32 @@ class BatchedSelfPlay(object):
         if self.waves_in_move >= self.waves_per_move:
             self.commit_move()
 
+    def step_waves(self, n):
+        """``n`` waves; with a captured graph, eight waves share a launch while they do not cross a move commit.  For a
+        handful of games a wave (40 .. 130 us of GPU time) is about as long as the host needs for one graph launch."""
+        n = int(n)
+        while n > 0:
+            k = min(n, self.waves_per_move - self.waves_in_move)
+            if self._graph is None or k < 8 or self.forest.n_leaves > 512:      # (long waves: nothing to gain)
+                self.step_wave()
+                n -= 1
+                continue
+            self._check_weights()
+            if self._graph8 is None:
+                torch.cuda.synchronize()
+                g8 = torch.cuda.CUDAGraph()
+                with capture_graph(g8):
+                    for _ in range(8):
+                        self._wave()
+                self._graph8 = g8
+            for _ in range(k // 8):
+                self._graph8.replay()
+            done = (k // 8) * 8
+            self.waves_in_move += done
+            n -= done
+            if self.waves_in_move >= self.waves_per_move:
+                self.commit_move()
+
     def commit_move(self):
         """pi + sampled move on the device, play it, re-root, record, refill finished games."""
         f = self.forest
@@ -189,8 +217,7 @@ class BatchedSelfPlay(object):
 
     def play(self, n_moves):
         self.warm_up()
-        for _ in range(n_moves * self.waves_per_move):
-            self.step_wave()
+        self.step_waves(n_moves * self.waves_per_move)
 
     # ------------------------------------------------- host-buffer API (end to end)
     def get_actions(self, rows_host, meta_host, temperature=None, hist_host=None):
@@ -244,7 +271,7 @@ class BatchedSelfPlay(object):
             self._wave()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with capture_graph(g):
                 self._wave()
             self._graph = g
             f.reset_trees()

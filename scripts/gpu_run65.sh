@@ -1,0 +1,9 @@
+#!/bin/bash
+# state of the tree near the end of round 2: GPU suite, smoke, the bench line (both arms), launch list of the same command
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r2_run65_pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/r2_run65_smoke.log 2>&1
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2_run65_bench.json 2> gpurun_out/r2_run65_bench.err
+timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_run65_bench_reference.json 2> gpurun_out/r2_run65_bench_reference.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"rz_(select|stem|conv|heads|expand)" -s 2400 -c 72 --csv \
+  --log-file gpurun_out/r2_run65_wave_launches.csv python bench.py --steps 4 --warmup 100 --no-cpu-baseline --no-e2e --no-configs --no-exchange > gpurun_out/r2_run65_ncu.log 2>&1
