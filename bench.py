@@ -259,6 +259,37 @@ def bench_config(args, games_per_unit):
             'parallelism': 'games sharded over %d GPU(s), no data-path collective' % args.gpus}
 
 
+def conv_share_in_step(sp, n_waves=4):
+    """Share of a wave spent in the trunk convolutions, measured INSIDE the step: CUPTI timeline (torch.profiler) of a few
+    graph-replayed waves; a kernel's time is end - max(start, end of its predecessor), because with programmatic
+    dependent launch a kernel is resident (and waiting) before its predecessor ends.  None if the profiler is
+    unavailable."""
+    try:
+        import torch
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(n_waves):
+                sp.step_wave()
+            torch.cuda.synchronize()
+        ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.name
+              and 'Memcpy' not in e.name and 'Memset' not in e.name]
+        ev.sort(key=lambda e: e.time_range.start)
+        if len(ev) < 8:
+            return None
+        conv = total = 0.0
+        prev_end = ev[0].time_range.start
+        for e in ev:
+            st, en = e.time_range.start, e.time_range.end
+            eff = max(0.0, en - max(st, prev_end))
+            total += eff + max(0.0, st - prev_end)          # gaps count towards the wave
+            if 'conv3x3' in e.name:
+                conv += eff
+            prev_end = max(prev_end, en)
+        return conv / total if total > 0 else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -814,7 +845,12 @@ def run_b200(args):
         conv_ms = conv_ms_cold
         flops = 2.0 * G * BOARD * BOARD * 128 * 128 * 9      # algorithmic: 225 squares x 128 x 1152 MACs
         n_conv = len(ev.layers) - 1
-        in_step = min(1.0, n_conv * conv_ms_hot / (ms / args.steps))
+        in_step_est = min(1.0, n_conv * conv_ms_hot / (ms / args.steps))
+        in_step = conv_share_in_step(sp)
+        share_how = ('CUPTI timeline of 4 graph-replayed waves right after the timed region: sum over the conv launches of '
+                     'end - max(start, end of the previous kernel), divided by the wave time')
+        if in_step is None:
+            in_step, share_how = in_step_est, 'launches_per_step x launch_ms_after_sustained_run / ms_per_step (upper bound)'
         peak = peaks.get('bf16_tflops') or 1590.0          # burst figure: the kernel is timed alone
         sustained = peaks.get('bf16_tflops_sustained') or 1400.0
         traffic = None
@@ -828,7 +864,8 @@ def run_b200(args):
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst, of measured)' if peaks else 'fallback 1590 (of fallback)',
                 'launch_ms': conv_ms, 'launch_ms_after_sustained_run': conv_ms_hot,
                 'frac_after_sustained_run_of_sustained_peak': flops / conv_ms_hot / 1e9 / sustained,
-                'launches_per_step': n_conv, 'share_of_step': in_step,
+                'launches_per_step': n_conv, 'share_of_step': in_step, 'share_of_step_how': share_how,
+                'share_of_step_upper_bound': in_step_est,
                 'traffic': traffic,
                 'issued_tflops': flops * 256.0 / 225.0 / conv_ms / 1e9,
                 'issued_frac_of_nominal_2250': flops * 256.0 / 225.0 / conv_ms / 1e9 / 2250.0,
